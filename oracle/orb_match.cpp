@@ -1,0 +1,247 @@
+/*
+ * oracle/orb_match.cpp — CPU restatement of ORBmatcher (TEST INFRASTRUCTURE, see orb_oracle.h).
+ * Follows /root/reference/src/ORBmatcher.cc on flattened arrays (the pointer graph of
+ * Frame/KeyFrame/MapPoint is gathered by the host shim).
+ */
+#include "orb_oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <vector>
+
+namespace {
+const int HISTO_LENGTH = 30;  // src/ORBmatcher.cc:51
+
+// ComputeThreeMaxima — src/ORBmatcher.cc:1866-1908
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  for (int i = 0; i < L; i++) {
+    const int s = (int)histo[i].size();
+    if (s > max1) {
+      max3 = max2; max2 = max1; max1 = s;
+      ind3 = ind2; ind2 = ind1; ind1 = i;
+    } else if (s > max2) {
+      max3 = max2; max2 = s;
+      ind3 = ind2; ind2 = i;
+    } else if (s > max3) {
+      max3 = s;
+      ind3 = i;
+    }
+  }
+  if (max2 < 0.1f * (float)max1) {
+    ind2 = -1;
+    ind3 = -1;
+  } else if (max3 < 0.1f * (float)max1) {
+    ind3 = -1;
+  }
+}
+
+inline int rot_bin(float angA, float angB) {
+  const float factor = HISTO_LENGTH / 360.0f;  // :246 (this fork; == 1.0f/HISTO_LENGTH bug of upstream is fixed here)
+  float rot = angA - angB;
+  if (rot < 0.0) rot += 360.0f;
+  int bin = (int)std::round(rot * factor);  // C round(): half away from zero
+  if (bin == HISTO_LENGTH) bin = 0;
+  return bin;
+}
+}  // namespace
+
+// DescriptorDistance — src/ORBmatcher.cc:1913-1933 (bit-twiddling popcount over 8 int32 words)
+extern "C" int orc_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+  int dist = 0;
+  for (int i = 0; i < 8; i++) {
+    uint32_t wa, wb;
+    std::memcpy(&wa, a + 4 * i, 4);
+    std::memcpy(&wb, b + 4 * i, 4);
+    unsigned int v = wa ^ wb;
+    v = v - ((v >> 1) & 0x55555555);
+    v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+    dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+  }
+  return dist;
+}
+
+// SearchByBoW — :230-382 (strict_lt=0) and :656-799 (strict_lt=1, validB used as "F side needs a MapPoint")
+extern "C" int orc_search_by_bow(const uint8_t* descA, const int32_t* nodeA, const uint8_t* validA, const float* angA,
+                                 int nA, const uint8_t* descB, const int32_t* nodeB, const uint8_t* validB,
+                                 const float* angB, int nB, int th_low, float nnratio, int strict_lt, int check_ori,
+                                 int32_t* matchB) {
+  // DBoW2::FeatureVector = std::map<NodeId, vector<unsigned>>; addFeature push_back in feature order
+  std::map<int, std::vector<int>> fvA, fvB;
+  for (int i = 0; i < nA; i++) fvA[nodeA[i]].push_back(i);
+  for (int j = 0; j < nB; j++) fvB[nodeB[j]].push_back(j);
+  for (int j = 0; j < nB; j++) matchB[j] = -1;
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  auto ita = fvA.begin();
+  auto itb = fvB.begin();
+  while (ita != fvA.end() && itb != fvB.end()) {
+    if (ita->first == itb->first) {
+      const std::vector<int>& ia = ita->second;
+      const std::vector<int>& ib = itb->second;
+      for (size_t k = 0; k < ia.size(); k++) {
+        const int realA = ia[k];
+        if (validA && !validA[realA]) continue;  // no MapPoint / bad
+        const uint8_t* dA = descA + (size_t)realA * 32;
+        int best1 = 256, bestIdx = -1, best2 = 256;
+        for (size_t m = 0; m < ib.size(); m++) {
+          const int realB = ib[m];
+          if (matchB[realB] >= 0) continue;  // already matched (:288 / :717)
+          if (validB && !validB[realB]) continue;  // KF-KF variant: F side needs a good MapPoint (:722-728)
+          const int dist = orc_descriptor_distance(dA, descB + (size_t)realB * 32);
+          if (dist < best1) {
+            best2 = best1;
+            best1 = dist;
+            bestIdx = realB;
+          } else if (dist < best2) {
+            best2 = dist;
+          }
+        }
+        const bool pass = strict_lt ? (best1 < th_low) : (best1 <= th_low);
+        if (pass) {
+          if ((float)best1 < nnratio * (float)best2) {
+            matchB[bestIdx] = realA;
+            if (check_ori) rotHist[rot_bin(angA[realA], angB[bestIdx])].push_back(bestIdx);
+            nmatches++;
+          }
+        }
+      }
+      ++ita;
+      ++itb;
+    } else if (ita->first < itb->first) {
+      ita = fvA.lower_bound(itb->first);
+    } else {
+      itb = fvB.lower_bound(ita->first);
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (size_t j = 0; j < rotHist[i].size(); j++) {
+        matchB[rotHist[i][j]] = -1;
+        nmatches--;
+      }
+    }
+  }
+  return nmatches;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Frame grid (src/Frame.cc:461-491 AssignFeaturesToGrid, :863-877 PosInGrid, :741-850 GetFeaturesInArea)
+ * ------------------------------------------------------------------------------------------ */
+namespace {
+const int GRID_COLS = 64, GRID_ROWS = 48;  // include/Frame.h:55,60
+
+struct Grid {
+  std::vector<int> cell[GRID_COLS][GRID_ROWS];
+  float minX, minY, invW, invH;
+  void build(const float* kpx, const float* kpy, int n, const orc_frame_geom* g) {
+    minX = g->mnMinX;
+    minY = g->mnMinY;
+    invW = (float)GRID_COLS / (g->mnMaxX - g->mnMinX);  // src/Frame.cc:213-214
+    invH = (float)GRID_ROWS / (g->mnMaxY - g->mnMinY);
+    for (int i = 0; i < n; i++) {
+      int px = (int)std::round((kpx[i] - minX) * invW);
+      int py = (int)std::round((kpy[i] - minY) * invH);
+      if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+      cell[px][py].push_back(i);
+    }
+  }
+  void in_area(float x, float y, float r, int minLevel, int maxLevel, const float* kpx, const float* kpy,
+               const int32_t* octave, std::vector<int>& out) const {
+    out.clear();
+    const int nMinCellX = std::max(0, (int)std::floor((x - minX - r) * invW));
+    if (nMinCellX >= GRID_COLS) return;
+    const int nMaxCellX = std::min(GRID_COLS - 1, (int)std::ceil((x - minX + r) * invW));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = std::max(0, (int)std::floor((y - minY - r) * invH));
+    if (nMinCellY >= GRID_ROWS) return;
+    const int nMaxCellY = std::min(GRID_ROWS - 1, (int)std::ceil((y - minY + r) * invH));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+      for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+        const std::vector<int>& v = cell[ix][iy];
+        for (size_t j = 0; j < v.size(); j++) {
+          const int id = v[j];
+          if (bCheckLevels) {
+            if (octave[id] < minLevel) continue;
+            if (maxLevel >= 0)
+              if (octave[id] > maxLevel) continue;
+          }
+          const float distx = kpx[id] - x;
+          const float disty = kpy[id] - y;
+          if (std::fabs(distx) < r && std::fabs(disty) < r) out.push_back(id);
+        }
+      }
+  }
+};
+}  // namespace
+
+// SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) — src/ORBmatcher.cc:1569-1728, from the
+// point where the last frame's map points have been projected (u, v, invzc computed by the shim at :1607-1626).
+extern "C" int orc_search_by_projection_last(const orc_proj_query* q, int nq, const float* kpx, const float* kpy,
+                                             const int32_t* octave, const float* angle, const float* uright,
+                                             const uint8_t* occupied_in, const uint8_t* desc, int nf,
+                                             const orc_frame_geom* g, float th, int mode, int th_high, int check_ori,
+                                             int32_t* match_cur) {
+  Grid* grid = new Grid();
+  grid->build(kpx, kpy, nf, g);
+  std::vector<uint8_t> occupied(nf, 0);
+  if (occupied_in) std::copy(occupied_in, occupied_in + nf, occupied.begin());
+  for (int j = 0; j < nf; j++) match_cur[j] = -1;
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  std::vector<int> cand;
+  for (int i = 0; i < nq; i++) {
+    const float u = q[i].u, v = q[i].v, invzc = q[i].invz;
+    if (invzc < 0) continue;
+    if (u < g->mnMinX || u > g->mnMaxX) continue;
+    if (v < g->mnMinY || v > g->mnMaxY) continue;
+    const int nLastOctave = q[i].octave;
+    const float radius = th * g->scale_factors[nLastOctave];
+    if (mode == 1) grid->in_area(u, v, radius, nLastOctave, -1, kpx, kpy, octave, cand);
+    else if (mode == 2) grid->in_area(u, v, radius, 0, nLastOctave, kpx, kpy, octave, cand);
+    else grid->in_area(u, v, radius, nLastOctave - 1, nLastOctave + 1, kpx, kpy, octave, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (size_t c = 0; c < cand.size(); c++) {
+      const int i2 = cand[c];
+      if (occupied[i2]) continue;
+      if (uright[i2] > 0) {
+        const float ur = u - g->bf * invzc;
+        const float er = std::fabs(ur - uright[i2]);
+        if (er > radius) continue;
+      }
+      const int dist = orc_descriptor_distance(q[i].desc, desc + (size_t)i2 * 32);
+      if (dist < bestDist) {
+        bestDist = dist;
+        bestIdx2 = i2;
+      }
+    }
+    if (bestDist <= th_high) {
+      match_cur[bestIdx2] = i;
+      occupied[bestIdx2] = q[i].has_obs ? 1 : 0;
+      nmatches++;
+      if (check_ori) rotHist[rot_bin(q[i].angle, angle[bestIdx2])].push_back(bestIdx2);
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i != ind1 && i != ind2 && i != ind3) {
+        for (size_t j = 0; j < rotHist[i].size(); j++) {
+          match_cur[rotHist[i][j]] = -1;
+          nmatches--;
+        }
+      }
+    }
+  }
+  delete grid;
+  return nmatches;
+}

@@ -1,0 +1,133 @@
+/*
+ * oracle/orb_oracle.h — C API of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a CPU restatement of the reference algorithm for the hot
+ * path (ORBextractor::operator(), ORBmatcher::SearchBy*, Optimizer::LocalBundleAdjustment of
+ * DreamWaterFound/self_commit_ORB-SLAM2).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it.  The product (libb200slam.so) never links,
+ * loads or calls anything in this directory.
+ *
+ * PARITY PINNING: the reference ships no tests or golden vectors and cannot be
+ * built here (needs OpenCV C++/Eigen3/Pangolin, all absent), so the oracle is pinned where it can
+ * be: its OpenCV-owned stages (resize, FAST, GaussianBlur, fastAtan2) are checked bit-for-bit
+ * against Python cv2 4.13 (the same OpenCV code the reference links) in tests/test_oracle_cv2.py;
+ * the stages that are the reference's own code (quadtree, IC_Angle, rBRIEF, matchers, LocalBA)
+ * have no independent pin -> "parity unpinned" for those.
+ */
+#ifndef ORB_ORACLE_H
+#define ORB_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Layout-compatible with cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id */
+typedef struct {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} orc_keypoint;
+
+/* ---------------- extractor (src/ORBextractor.cc) ---------------- */
+void* orc_extractor_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+void orc_extractor_destroy(void* h);
+/* ORBextractor::operator() (src/ORBextractor.cc:1544-1668). Returns N (<= cap) or -1 if cap too small. */
+int orc_extract(void* h, const uint8_t* img, int w, int hgt, int stride, orc_keypoint* kps, uint8_t* desc, int cap);
+/* getters (include/ORBextractor.h:118-161) */
+void orc_extractor_tables(void* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int* nfeat_per_level,
+                          int* umax16);
+/* introspection of the last orc_extract() call (test hooks) */
+int orc_level_dims(void* h, int level, int* w, int* hgt);
+const uint8_t* orc_level_image(void* h, int level);   /* contiguous w*h, pyramid level (no border) */
+const uint8_t* orc_level_blurred(void* h, int level); /* contiguous w*h, or NULL if the level had no keypoints */
+int orc_level_candidates(void* h, int level, orc_keypoint* out, int cap); /* pre-quadtree, border-relative coords */
+int orc_level_keypoints(void* h, int level, orc_keypoint* out, int cap);  /* post-quadtree, level coords, with angle */
+
+/* OpenCV-owned primitives, restated; cross-checked against cv2 in tests */
+void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride);
+void orc_gaussian_blur7_s2_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride);
+/* cv::FAST(roi, kps, th, true): returns count; xy = (x,y) pairs in ROI coords, resp = score */
+int orc_fast9_16_nms(const uint8_t* roi, int w, int h, int stride, int th, int* xy, int* resp, int cap);
+/* full score map M (corner at th <=> M > th, response = M-1), 0 on the 3-px rim */
+void orc_fast_score_map(const uint8_t* roi, int w, int h, int stride, uint8_t* score, int score_stride);
+float orc_fast_atan2(float y, float x);
+/* quadtree alone: DistributeOctTree (src/ORBextractor.cc:706-1049) */
+int orc_distribute_octtree(const orc_keypoint* in, int n, int minX, int maxX, int minY, int maxY, int N, orc_keypoint* out,
+                           int cap);
+
+/* ---------------- matcher (src/ORBmatcher.cc) ---------------- */
+int orc_descriptor_distance(const uint8_t* a, const uint8_t* b); /* :1913-1933 */
+
+/* SearchByBoW(KeyFrame*,Frame&,...) :230-382 and (KeyFrame*,KeyFrame*,...) :656-799 on flattened arrays.
+ * descA/nodeA/validA/angA: the keyframe side ("KF"); descB/nodeB/angB: the frame side ("F").
+ * node ids: features sharing a node id are candidates of each other; iteration order = ascending node id,
+ * ascending feature index inside a node (std::map + push_back order).
+ * strict_lt=0: accept best<=th_low (M1); strict_lt=1: best<th_low (M2).
+ * matchB[j] = index into A or -1.  Returns nmatches. */
+int orc_search_by_bow(const uint8_t* descA, const int32_t* nodeA, const uint8_t* validA, const float* angA, int nA,
+                      const uint8_t* descB, const int32_t* nodeB, const uint8_t* validB, const float* angB, int nB,
+                      int th_low, float nnratio, int strict_lt, int check_ori, int32_t* matchB);
+
+/* Frame feature grid (src/Frame.cc:461-491, 741-877) + SearchByProjection(Cur,Last,th,mono) (:1569-1728).
+ * Queries are the last frame's map points already projected by the host shim with the current pose. */
+typedef struct {
+  float u, v;          /* projection in the current frame */
+  float invz;          /* 1/zc (float, as computed at :1614) */
+  float angle;         /* LastFrame.mvKeysUn[i].angle */
+  int32_t octave;      /* LastFrame.mvKeys[i].octave */
+  int32_t has_obs;     /* pMP->Observations()>0 */
+  uint8_t desc[32];    /* pMP->GetDescriptor() */
+} orc_proj_query;
+
+typedef struct {
+  float mnMinX, mnMinY, mnMaxX, mnMaxY;
+  float bf;            /* CurrentFrame.mbf */
+  const float* scale_factors; /* mvScaleFactors[nlevels] */
+  int nlevels;
+} orc_frame_geom;
+
+/* feats: current frame; kpx,kpy,octave,angle from mvKeysUn; uright = mvuRight; occupied = feature already holds a
+ * MapPoint with Observations()>0 (src/ORBmatcher.cc:1658-1660).
+ * mode: 0 = neither forward nor backward (levels [oct-1, oct+1]), 1 = forward (>= oct), 2 = backward ([0, oct]).
+ * match_cur[j] = query index or -1. Returns nmatches (as the reference counts them). */
+int orc_search_by_projection_last(const orc_proj_query* q, int nq, const float* kpx, const float* kpy,
+                                  const int32_t* octave, const float* angle, const float* uright,
+                                  const uint8_t* occupied, const uint8_t* desc, int nf, const orc_frame_geom* g,
+                                  float th, int mode, int th_high, int check_ori, int32_t* match_cur);
+
+/* ---------------- LocalBA (src/Optimizer.cc:629-997 + vendored g2o) ---------------- */
+typedef struct {
+  int32_t kf;        /* index into poses[] */
+  int32_t mp;        /* index into points[] */
+  float obs[3];      /* kpUn.pt.x, kpUn.pt.y, mvuRight (<0 => mono edge) */
+  float inv_sigma2;  /* mvInvLevelSigma2[octave] */
+} orc_ba_edge;
+
+typedef struct {
+  int n_kf;               /* local KFs first [0,n_local), then fixed cameras */
+  int n_local;            /* number of local keyframes (lLocalKeyFrames) */
+  const float* Tcw;       /* n_kf x 16 (row-major 4x4 float, KeyFrame::GetPose) */
+  const uint8_t* fixed;   /* n_kf: 1 => setFixed(true) (id==0 or fixed camera) */
+  int n_mp;
+  const float* points;    /* n_mp x 3 float (MapPoint::GetWorldPos) */
+  int n_edges;
+  const orc_ba_edge* edges; /* insertion order */
+  float fx, fy, cx, cy, bf;
+  int its1, its2;         /* 5, 10 */
+} orc_ba_problem;
+
+typedef struct {
+  float* Tcw_out;          /* n_local x 16 */
+  float* points_out;       /* n_mp x 3 */
+  uint8_t* edge_outlier;   /* n_edges: 1 => goes to vToErase (src/Optimizer.cc:927-958) */
+  int32_t* trace;          /* optional, >= 256 ints: accept(1)/reject(0) sequence of LM trials, -1 terminated */
+  double chi2_final;
+  int n_trials;
+} orc_ba_result;
+
+/* stop: optional async abort flag (pbStopFlag). Returns 0 ok, 1 aborted before round 1 (no write-back). */
+int orc_local_ba(const orc_ba_problem* p, const volatile uint8_t* stop, orc_ba_result* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,157 @@
+"""Deterministic synthetic inputs (integer-only numpy so they reproduce bit-for-bit on any box).
+
+SURVEY.md §8(d): textured images that fill the per-level quotas; stereo pairs with band disparity;
+descriptor sets with known correspondences; a KITTI-shaped LocalBA window.
+"""
+import numpy as np
+
+
+def _blur5(a):
+    """separable [1,4,6,4,1]/16 integer blur with edge replication"""
+    a = a.astype(np.int32)
+    k = (1, 4, 6, 4, 1)
+    p = np.pad(a, ((0, 0), (2, 2)), mode="edge")
+    h = sum(k[i] * p[:, i:i + a.shape[1]] for i in range(5))
+    p = np.pad(h, ((2, 2), (0, 0)), mode="edge")
+    v = sum(k[i] * p[i:i + a.shape[0], :] for i in range(5))
+    return (v + 128) >> 8
+
+
+def synth_image(w, h, seed, blocks=True):
+    rng = np.random.RandomState(seed)
+    noise = rng.randint(0, 256, size=(h, w)).astype(np.int32)
+    base = _blur5(noise) // 2 + 40
+    if blocks:
+        bs = 12
+        gh, gw = (h + bs - 1) // bs, (w + bs - 1) // bs
+        on = rng.randint(0, 100, size=(gh, gw)) < 22
+        amp = rng.randint(60, 121, size=(gh, gw)) * on
+        amp = np.kron(amp, np.ones((bs, bs), dtype=np.int32))[:h, :w]
+        base = base + amp
+    # a few smooth gradients so low-texture cells exist (exercise the minThFAST fallback)
+    yy, xx = np.mgrid[0:h, 0:w]
+    flat = ((xx // 97 + yy // 61) % 5 == 0)
+    base = np.where(flat, 90 + ((xx + yy) >> 5), base)
+    return np.clip(base, 0, 255).astype(np.uint8)
+
+
+def synth_stereo(w, h, seed):
+    left = synth_image(w, h, seed)
+    rng = np.random.RandomState(seed + 100003)
+    right = np.empty_like(left)
+    band = 47
+    for y0 in range(0, h, band):
+        d = int(rng.randint(5, 61))
+        rows = left[y0:y0 + band]
+        shifted = np.empty_like(rows)
+        shifted[:, :w - d] = rows[:, d:]
+        shifted[:, w - d:] = rows[:, w - d - 1:w - d]  # replicate
+        right[y0:y0 + band] = shifted
+    jitter = rng.randint(-2, 3, size=(h, w))
+    right = np.clip(right.astype(np.int32) + jitter, 0, 255).astype(np.uint8)
+    return left, right
+
+
+def synth_descriptors(n, seed=1234, match_frac=0.7, max_flips=40, n_nodes=100):
+    """A (keyframe side) and B (frame side) descriptor sets, node ids, angles (SURVEY §8d Matching)."""
+    rng = np.random.RandomState(seed)
+    A = rng.randint(0, 256, size=(n, 32)).astype(np.uint8)
+    perm = rng.permutation(n)
+    B = rng.randint(0, 256, size=(n, 32)).astype(np.uint8)
+    angA = (rng.randint(0, 360000, size=n) / 1000.0).astype(np.float32)
+    angB = (rng.randint(0, 360000, size=n) / 1000.0).astype(np.float32)
+    nodeA = rng.randint(0, n_nodes, size=n).astype(np.int32)
+    nodeB = rng.randint(0, n_nodes, size=n).astype(np.int32)
+    for i in range(n):
+        if rng.randint(0, 1000) < match_frac * 1000:
+            j = perm[i]
+            d = A[j].copy()
+            k = int(rng.randint(0, max_flips + 1))
+            bits = rng.choice(256, size=k, replace=False)
+            for b in bits:
+                d[b >> 3] ^= np.uint8(1 << (b & 7))
+            B[i] = d
+            nodeB[i] = nodeA[j]
+            a = float(angA[j]) + float(rng.randint(-15000, 15001)) / 3000.0
+            angB[i] = np.float32(a % 360.0)
+    validA = (rng.randint(0, 100, size=n) < 95).astype(np.uint8)
+    return A, nodeA, validA, angA, B, nodeB, angB
+
+
+def synth_local_ba(n_kf=50, n_fixed=10, n_mp=5000, obs_per_mp=6, seed=42, mono_frac=0.0, outlier_frac=0.03):
+    """KITTI-shaped LocalBA window: forward path, stereo edges, 3 % gross outliers.
+
+    Returns dict with float32 arrays exactly as Converter would hand them over.
+    Keyframes [0, n_kf-n_fixed) are local (free, except index 0 which plays mnId==0 only if fix_first),
+    the last n_fixed are fixed cameras.
+    """
+    rng = np.random.RandomState(seed)
+    fx = fy = 718.856
+    cx, cy, bf = 607.1928, 185.2157, 386.1448
+    W, H = 1241, 376
+    n_local = n_kf - n_fixed
+    # true poses: camera moves along +z, 1 m spacing, small yaw jitter. Tcw = [R | -R*c]
+    Tcw_true = np.zeros((n_kf, 4, 4))
+    for k in range(n_kf):
+        yaw = np.deg2rad(rng.uniform(-2, 2))
+        c, s = np.cos(yaw), np.sin(yaw)
+        R = np.array([[c, 0, -s], [0, 1, 0], [s, 0, c]])
+        center = np.array([rng.uniform(-0.1, 0.1), rng.uniform(-0.05, 0.05), 1.0 * k])
+        Tcw_true[k, :3, :3] = R
+        Tcw_true[k, :3, 3] = -R @ center
+        Tcw_true[k, 3, 3] = 1
+    pts_true = np.zeros((n_mp, 3))
+    edges = []
+    order = rng.permutation(n_kf)
+    for m in range(n_mp):
+        # pick an anchor KF, place the point in its frustum 5-60 m ahead
+        for _ in range(100):
+            ka = int(rng.randint(0, n_kf))
+            z = rng.uniform(5, 60)
+            u = rng.uniform(50, W - 50)
+            v = rng.uniform(30, H - 30)
+            Xc = np.array([(u - cx) * z / fx, (v - cy) * z / fy, z])
+            Ra, ta = Tcw_true[ka, :3, :3], Tcw_true[ka, :3, 3]
+            Xw = Ra.T @ (Xc - ta)
+            # which KFs see it
+            vis = []
+            for k in range(n_kf):
+                Xk = Tcw_true[k, :3, :3] @ Xw + Tcw_true[k, :3, 3]
+                if Xk[2] < 2.0:
+                    continue
+                uu = fx * Xk[0] / Xk[2] + cx
+                vv = fy * Xk[1] / Xk[2] + cy
+                if 0 < uu < W and 0 < vv < H:
+                    vis.append((abs(k - ka), k, uu, vv, Xk[2]))
+            if len(vis) >= obs_per_mp:
+                break
+        vis.sort()
+        pts_true[m] = Xw
+        for (_, k, uu, vv, zz) in sorted(vis[:obs_per_mp], key=lambda t: t[1]):
+            octv = int(rng.randint(0, 8))
+            sig = 1.2 ** octv
+            nu, nv, nr = rng.normal(0, sig, 3)
+            ur = uu - bf / zz
+            if rng.uniform() < outlier_frac:
+                nu += 30.0
+            mono = rng.uniform() < mono_frac
+            edges.append((k, m, uu + nu, vv + nv, -1.0 if mono else ur + nr, 1.0 / (1.2 ** (2 * octv))))
+    # perturbed initial state
+    Tcw0 = Tcw_true.copy()
+    for k in range(n_local):
+        dyaw = np.deg2rad(rng.normal(0, 0.2))
+        c, s = np.cos(dyaw), np.sin(dyaw)
+        dR = np.array([[c, 0, -s], [0, 1, 0], [s, 0, c]])
+        Tcw0[k, :3, :3] = dR @ Tcw_true[k, :3, :3]
+        Tcw0[k, :3, 3] = dR @ Tcw_true[k, :3, 3] + rng.normal(0, 0.02, 3)
+    pts0 = pts_true + rng.normal(0, 0.05, pts_true.shape)
+    fixed = np.zeros(n_kf, np.uint8)
+    fixed[n_local:] = 1
+    fixed[0] = 1  # plays the role of mnId==0
+    edge_dt = np.dtype([("kf", "i4"), ("mp", "i4"), ("obs", "f4", 3), ("inv_sigma2", "f4")])
+    E = np.zeros(len(edges), edge_dt)
+    for i, (k, m, a, b_, c_, w) in enumerate(edges):
+        E[i] = (k, m, (np.float32(a), np.float32(b_), np.float32(c_)), np.float32(w))
+    return dict(n_kf=n_kf, n_local=n_local, Tcw=Tcw0.astype(np.float32).reshape(n_kf, 16), fixed=fixed,
+                points=pts0.astype(np.float32), edges=E, fx=np.float32(fx), fy=np.float32(fy), cx=np.float32(cx),
+                cy=np.float32(cy), bf=np.float32(bf), Tcw_true=Tcw_true, pts_true=pts_true)
