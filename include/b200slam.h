@@ -1,0 +1,184 @@
+/*
+ * include/b200slam.h — C ABI of libb200slam.so: the B200-native (sm_100a) replacement for the hot path of
+ * DreamWaterFound/self_commit_ORB-SLAM2.
+ *
+ * The reference has no FFI layer: its boundary is three C++ classes.  The entry points below
+ * are what a C++ shim with the reference's own signatures binds to (the shim lives in
+ * self_commit_orb-slam2_b200/host/, the reference-side patch in INTEGRATION.md):
+ *
+ *   ORBextractor::ORBextractor(...)            /root/reference/include/ORBextractor.h:92,  src/ORBextractor.cc:492
+ *   ORBextractor::operator()(...)              include/ORBextractor.h:110, src/ORBextractor.cc:1544
+ *   ORBextractor::Get*()                       include/ORBextractor.h:118-161
+ *   ORBmatcher::DescriptorDistance             include/ORBmatcher.h,  src/ORBmatcher.cc:1913
+ *   ORBmatcher::SearchByBoW (2 overloads)      src/ORBmatcher.cc:230, :656
+ *   ORBmatcher::SearchByProjection(F,F,th,mono) src/ORBmatcher.cc:1569
+ *   Optimizer::LocalBundleAdjustment           include/Optimizer.h:112, src/Optimizer.cc:629
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns an int status
+ * (B2S_OK = 0) and never throws; buffers are caller-owned, device memory is owned by handles; handles are
+ * independent (one CUDA stream each, no global mutable state) so left/right extractors may run on two
+ * threads like src/Frame.cc:159-167.  There is NO CPU fallback: without a CUDA device every call fails
+ * with B2S_ERR_NO_DEVICE.
+ */
+#ifndef B200SLAM_H
+#define B200SLAM_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  B2S_OK = 0,
+  B2S_ERR_NO_DEVICE = 1,    /* no CUDA device / driver: the product does not fall back to the CPU */
+  B2S_ERR_BAD_ARG = 2,
+  B2S_ERR_CUDA = 3,         /* a CUDA call failed; b2s_last_error() has the text */
+  B2S_ERR_CAPACITY = 4,     /* caller buffer (cap) or an internal candidate buffer too small */
+  B2S_ERR_ABORTED = 5       /* LocalBA: stop flag was set before the first round (no write-back) */
+};
+
+const char* b2s_last_error(void);   /* thread-local text of the last failure */
+int b2s_version(void);
+int b2s_device_count(void);
+
+/* Layout-identical to cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id */
+typedef struct {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} b2s_keypoint;
+
+/* ------------------------------------------------------------------ extractor */
+typedef struct b2s_extractor b2s_extractor;
+
+/* ctor: src/ORBextractor.cc:492-609. max_width/max_height/max_batch size the device buffers. */
+int b2s_extractor_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int max_width,
+                         int max_height, int max_batch, int device, b2s_extractor** out);
+void b2s_extractor_destroy(b2s_extractor* h);
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares + per-level quotas;
+ * any pointer may be NULL; arrays hold nlevels entries. */
+int b2s_extractor_tables(const b2s_extractor* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                         int32_t* nfeatures_per_level);
+int b2s_extractor_max_keypoints(const b2s_extractor* h); /* upper bound of N for one image (nfeatures + 2*nlevels..) */
+
+/* operator(): one image, HOST buffers (H2D/D2H inside). kps: cap entries; desc: cap x 32 bytes.
+ * pyr_out: optional array of nlevels host pointers that receive mvImagePyramid level images (tightly packed
+ * w_l x h_l) — needed by Frame::ComputeStereoMatches (src/Frame.cc:1044); NULL to skip the D2H.
+ * Empty image (w<=0||h<=0||img==NULL) -> *n_out = 0, B2S_OK (src/ORBextractor.cc:1553). */
+int b2s_extract(b2s_extractor* h, const uint8_t* img, int width, int height, int stride, b2s_keypoint* kps, uint8_t* desc,
+                int cap, int* n_out, uint8_t* const* pyr_out);
+
+/* Batched: B same-sized images (e.g. L/R pairs of several frames), HOST buffers; imgs = B pointers;
+ * kps: B*cap, desc: B*cap*32, n_out: B. */
+int b2s_extract_batch(b2s_extractor* h, const uint8_t* const* imgs, int batch, int width, int height, int stride,
+                      b2s_keypoint* kps, uint8_t* desc, int cap, int* n_out);
+
+/* Batched, DEVICE-resident: d_imgs = batch images at d_imgs + b*img_pitch_bytes (row stride `stride`), results stay
+ * in HBM as fixed-size records (the layout that is all-gathered over NVLink):
+ *   d_kps[b*cap + i], d_desc[(b*cap + i)*32], d_counts[b].   stream: a cudaStream_t (NULL = the handle's own stream);
+ * the call is asynchronous on that stream. */
+int b2s_extract_batch_device(b2s_extractor* h, const uint8_t* d_imgs, size_t img_pitch_bytes, int batch, int width,
+                             int height, int stride, b2s_keypoint* d_kps, uint8_t* d_desc, int32_t* d_counts, int cap,
+                             void* stream);
+/* status of the last device batch (candidate-buffer overflow etc.); synchronises the handle's stream. */
+int b2s_extractor_check(b2s_extractor* h);
+/* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
+long long b2s_extractor_launch_count(const b2s_extractor* h);
+
+/* test hooks: device -> host copies of intermediates of image `b` of the last call */
+int b2s_extractor_debug_level(b2s_extractor* h, int b, int level, int blurred, uint8_t* out, int* w, int* hgt);
+int b2s_extractor_debug_candidates(b2s_extractor* h, int b, int level, int32_t* xy /*2*cap*/, int32_t* resp, int cap,
+                                   int* n);
+
+/* ------------------------------------------------------------------ matcher */
+typedef struct b2s_matcher b2s_matcher;
+int b2s_matcher_create(int max_features, int max_batch, int device, b2s_matcher** out);
+void b2s_matcher_destroy(b2s_matcher* h);
+long long b2s_matcher_launch_count(const b2s_matcher* h);
+
+/* DescriptorDistance (src/ORBmatcher.cc:1913): n pairs a[i] vs b[i], HOST buffers -> dist[n] */
+int b2s_descriptor_distance(b2s_matcher* h, const uint8_t* a, const uint8_t* b, int n, int32_t* dist);
+
+/* SearchByBoW on flattened arrays (HOST buffers).  A = keyframe side, B = frame side.
+ * nodeA/nodeB: DBoW2 FeatureVector node id per feature (features with equal ids are candidates);
+ * validA/validB: 1 = has a usable MapPoint (validB may be NULL: SearchByBoW(KF,F) does not need it);
+ * strict_lt: 0 -> best<=th_low (KF,F variant :308), 1 -> best<th_low (KF,KF variant :741).
+ * matchB[j] = index into A, or -1. */
+int b2s_search_by_bow(b2s_matcher* h, const uint8_t* descA, const int32_t* nodeA, const uint8_t* validA, const float* angA,
+                      int nA, const uint8_t* descB, const int32_t* nodeB, const uint8_t* validB, const float* angB, int nB,
+                      int th_low, float nnratio, int strict_lt, int check_ori, int32_t* matchB, int* nmatches);
+
+/* Batched device-resident variant: `batch` independent (A,B) pairs with strides capA/capB features. All pointers are
+ * DEVICE pointers; nA/nB are device int arrays [batch]. Asynchronous on `stream`. */
+int b2s_search_by_bow_device(b2s_matcher* h, int batch, const uint8_t* d_descA, const int32_t* d_nodeA,
+                             const uint8_t* d_validA, const float* d_angA, const int32_t* d_nA, int capA,
+                             const uint8_t* d_descB, const int32_t* d_nodeB, const uint8_t* d_validB,
+                             const float* d_angB, const int32_t* d_nB, int capB, int th_low, float nnratio, int strict_lt,
+                             int check_ori, int32_t* d_matchB, int32_t* d_nmatches, void* stream);
+
+/* SearchByProjection(CurrentFrame, LastFrame, th, bMono) (src/ORBmatcher.cc:1569) after projection. */
+typedef struct {
+  float u, v;      /* projection of the last frame's map point into the current frame (:1620-1621) */
+  float invz;      /* 1/zc (:1614) */
+  float angle;     /* LastFrame.mvKeysUn[i].angle */
+  int32_t octave;  /* LastFrame.mvKeys[i].octave */
+  int32_t has_obs; /* pMP->Observations()>0 */
+  uint8_t desc[32];/* pMP->GetDescriptor() */
+} b2s_proj_query;
+
+typedef struct {
+  float mnMinX, mnMinY, mnMaxX, mnMaxY; /* Frame::mnMinX.. (src/Frame.cc:193-214) */
+  float bf;                             /* Frame::mbf */
+  const float* scale_factors;           /* mvScaleFactors, nlevels entries (host pointer) */
+  int nlevels;
+} b2s_frame_geom;
+
+/* mode: 0 levels [oct-1,oct+1]; 1 forward (>=oct); 2 backward ([0,oct]) (:1637-1642).
+ * match_cur[j] = query index or -1; *nmatches as the reference counts them. HOST buffers. */
+int b2s_search_by_projection_last(b2s_matcher* h, const b2s_proj_query* q, int nq, const float* kpx, const float* kpy,
+                                  const int32_t* octave, const float* angle, const float* uright,
+                                  const uint8_t* occupied, const uint8_t* desc, int nf, const b2s_frame_geom* g, float th,
+                                  int mode, int th_high, int check_ori, int32_t* match_cur, int* nmatches);
+
+/* ------------------------------------------------------------------ LocalBA */
+typedef struct {
+  int32_t kf;       /* index into Tcw[] */
+  int32_t mp;       /* index into points[] */
+  float obs[3];     /* kpUn.pt.x, kpUn.pt.y, mvuRight (<0: monocular edge, src/Optimizer.cc:794) */
+  float inv_sigma2; /* mvInvLevelSigma2[octave] */
+} b2s_ba_edge;
+
+typedef struct {
+  int n_kf;             /* local keyframes first [0,n_local), then fixed cameras */
+  int n_local;
+  const float* Tcw;     /* n_kf x 16, KeyFrame::GetPose() row-major 4x4 float */
+  const uint8_t* fixed; /* n_kf: setFixed(true) (mnId==0 or lFixedCameras) */
+  int n_mp;
+  const float* points;  /* n_mp x 3, MapPoint::GetWorldPos() */
+  int n_edges;
+  const b2s_ba_edge* edges; /* insertion order of src/Optimizer.cc:770-853 */
+  float fx, fy, cx, cy, bf;
+  int its1, its2;       /* optimize(5), optimize(10) */
+} b2s_ba_problem;
+
+typedef struct {
+  float* Tcw_out;        /* n_local x 16 (SetPose values) */
+  float* points_out;     /* n_mp x 3 (SetWorldPos values) */
+  uint8_t* edge_outlier; /* n_edges: 1 -> (KF,MP) goes to vToErase (:927-958) */
+  int32_t* trace;        /* optional (>=256): accept(1)/reject(0) per LM trial, -1 terminated */
+  double chi2_final;
+  int n_trials;
+} b2s_ba_result;
+
+typedef struct b2s_ba_solver b2s_ba_solver;
+int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batch, int device, b2s_ba_solver** out);
+void b2s_ba_destroy(b2s_ba_solver* h);
+long long b2s_ba_launch_count(const b2s_ba_solver* h);
+/* Optimizer::LocalBundleAdjustment from graph construction to write-back values. stop: pbStopFlag (may be NULL). */
+int b2s_local_ba(b2s_ba_solver* h, const b2s_ba_problem* p, const volatile uint8_t* stop, b2s_ba_result* r);
+/* `batch` independent windows solved concurrently (replicas). */
+int b2s_local_ba_batch(b2s_ba_solver* h, int batch, const b2s_ba_problem* p, b2s_ba_result* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -127,6 +127,11 @@ typedef struct {
 /* stop: optional async abort flag (pbStopFlag). Returns 0 ok, 1 aborted before round 1 (no write-back). */
 int orc_local_ba(const orc_ba_problem* p, const volatile uint8_t* stop, orc_ba_result* r);
 
+/* ---------------- helpers (orb_misc.cpp) ---------------- */
+void orc_sincosf_batch(const float* in, long n, float* s, float* c, int threads); /* glibc sinf/cosf */
+int orc_extract_many(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t* imgs, int count,
+                     int w, int h, orc_keypoint* kps, uint8_t* desc, int cap, int* n_out, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,349 @@
+"""self_commit_orb-slam2_b200 — B200-native hot path of ORB-SLAM2 (extract -> match -> LocalBA).
+
+This package is a thin ctypes binding over ``libb200slam.so`` (hand-written sm_100a CUDA behind the C ABI of
+``include/b200slam.h``).  The Python classes mirror the reference's operator interface
+(``ORBextractor.__call__`` = ``ORBextractor::operator()``, ``ORBmatcher.SearchByBoW`` ...), so the tests read like
+calls into the reference.  There is no CPU fallback: if the CUDA library is missing or no GPU is present the calls
+raise ``B200SlamError``.
+
+The directory name contains a dash, so import it with
+``importlib.import_module("self_commit_orb-slam2_b200")`` (or ``from b200slam_loader import pkg`` in tests).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200slam.so")
+
+OK, ERR_NO_DEVICE, ERR_BAD_ARG, ERR_CUDA, ERR_CAPACITY, ERR_ABORTED = range(6)
+
+keypoint_dtype = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                           ("octave", "<i4"), ("class_id", "<i4")])
+proj_query_dtype = np.dtype([("u", "<f4"), ("v", "<f4"), ("invz", "<f4"), ("angle", "<f4"), ("octave", "<i4"),
+                             ("has_obs", "<i4"), ("desc", "u1", 32)])
+ba_edge_dtype = np.dtype([("kf", "<i4"), ("mp", "<i4"), ("obs", "<f4", 3), ("inv_sigma2", "<f4")])
+
+TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30  # src/ORBmatcher.cc:49-51
+
+
+class B200SlamError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("libb200slam error %d: %s" % (code, text))
+        self.code = code
+
+
+_vp = ctypes.c_void_p
+_lib = None
+
+
+class _FrameGeom(ctypes.Structure):
+    _fields_ = [("mnMinX", ctypes.c_float), ("mnMinY", ctypes.c_float), ("mnMaxX", ctypes.c_float),
+                ("mnMaxY", ctypes.c_float), ("bf", ctypes.c_float), ("scale_factors", _vp), ("nlevels", ctypes.c_int)]
+
+
+class _BaProblem(ctypes.Structure):
+    _fields_ = [("n_kf", ctypes.c_int), ("n_local", ctypes.c_int), ("Tcw", _vp), ("fixed", _vp), ("n_mp", ctypes.c_int),
+                ("points", _vp), ("n_edges", ctypes.c_int), ("edges", _vp), ("fx", ctypes.c_float),
+                ("fy", ctypes.c_float), ("cx", ctypes.c_float), ("cy", ctypes.c_float), ("bf", ctypes.c_float),
+                ("its1", ctypes.c_int), ("its2", ctypes.c_int)]
+
+
+class _BaResult(ctypes.Structure):
+    _fields_ = [("Tcw_out", _vp), ("points_out", _vp), ("edge_outlier", _vp), ("trace", _vp),
+                ("chi2_final", ctypes.c_double), ("n_trials", ctypes.c_int)]
+
+
+def lib():
+    """Loads libb200slam.so (built in-tree by build.py). Fails loudly if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200SlamError(-1, "%s not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                    "(there is no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.b2s_last_error.restype = ctypes.c_char_p
+        L.b2s_extractor_launch_count.restype = ctypes.c_longlong
+        L.b2s_extractor_launch_count.argtypes = [_vp]
+        L.b2s_extractor_create.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
+        L.b2s_extractor_destroy.argtypes = [_vp]
+        L.b2s_extractor_destroy.restype = None
+        L.b2s_extractor_tables.argtypes = [_vp] * 6
+        L.b2s_extractor_max_keypoints.argtypes = [_vp]
+        L.b2s_extract.argtypes = [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp]
+        L.b2s_extract_batch.argtypes = [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp,
+                                        ctypes.c_int, _vp]
+        L.b2s_extract_batch_device.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, _vp, _vp, _vp, ctypes.c_int, _vp]
+        L.b2s_extractor_check.argtypes = [_vp]
+        L.b2s_extractor_debug_level.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]
+        L.b2s_extractor_debug_candidates.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp]
+        if hasattr(L, "b2s_matcher_create"):
+            L.b2s_matcher_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
+            L.b2s_matcher_destroy.argtypes = [_vp]
+            L.b2s_matcher_destroy.restype = None
+            L.b2s_matcher_launch_count.restype = ctypes.c_longlong
+            L.b2s_matcher_launch_count.argtypes = [_vp]
+            L.b2s_descriptor_distance.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp]
+            L.b2s_search_by_bow.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, _vp, _vp]
+            L.b2s_search_by_bow_device.argtypes = [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp,
+                                                   _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                                   ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]
+            L.b2s_search_by_projection_last.argtypes = [_vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                        ctypes.c_int, _vp, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                                        ctypes.c_int, _vp, _vp]
+        if hasattr(L, "b2s_ba_create"):
+            L.b2s_ba_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
+            L.b2s_ba_destroy.argtypes = [_vp]
+            L.b2s_ba_destroy.restype = None
+            L.b2s_ba_launch_count.restype = ctypes.c_longlong
+            L.b2s_ba_launch_count.argtypes = [_vp]
+            L.b2s_local_ba.argtypes = [_vp, _vp, _vp, _vp]
+            L.b2s_local_ba_batch.argtypes = [_vp, ctypes.c_int, _vp, _vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != OK:
+        raise B200SlamError(rc, lib().b2s_last_error().decode("utf-8", "replace"))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def device_count():
+    return lib().b2s_device_count()
+
+
+class ORBextractor:
+    """Mirror of ORB_SLAM2::ORBextractor (include/ORBextractor.h:92-161)."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_width=1280, max_height=1024,
+                 max_batch=1, device=0):
+        self._h = _vp()
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self.max_batch = max_batch
+        _check(lib().b2s_extractor_create(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_width, max_height,
+                                          max_batch, device, ctypes.byref(self._h)))
+        self.cap = lib().b2s_extractor_max_keypoints(self._h)
+        s = [np.zeros(nlevels, np.float32) for _ in range(4)]
+        nf = np.zeros(nlevels, np.int32)
+        _check(lib().b2s_extractor_tables(self._h, _p(s[0]), _p(s[1]), _p(s[2]), _p(s[3]), _p(nf)))
+        self.mvScaleFactor, self.mvInvScaleFactor, self.mvLevelSigma2, self.mvInvLevelSigma2 = s
+        self.mnFeaturesPerLevel = nf
+        self.mvImagePyramid = []
+
+    def close(self):
+        if self._h:
+            lib().b2s_extractor_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # getters of include/ORBextractor.h:118-161
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactors(self):
+        return self.mvScaleFactor
+
+    def GetInverseScaleFactors(self):
+        return self.mvInvScaleFactor
+
+    def GetScaleSigmaSquares(self):
+        return self.mvLevelSigma2
+
+    def GetInverseScaleSigmaSquares(self):
+        return self.mvInvLevelSigma2
+
+    def __call__(self, image, mask=None, want_pyramid=False):
+        """operator()(image, mask, keypoints, descriptors): returns (keypoints[N], descriptors[N,32])."""
+        if image is None or image.size == 0:
+            return np.zeros(0, keypoint_dtype), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2  # assert(image.type() == CV_8UC1)
+        h, w = image.shape
+        kps = np.zeros(self.cap, keypoint_dtype)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        n = ctypes.c_int(0)
+        pyr_ptrs = None
+        if want_pyramid:
+            dims = self.level_dims(w, h)
+            self.mvImagePyramid = [np.zeros((lh, lw), np.uint8) for (lw, lh) in dims]
+            arr = (_vp * self.nlevels)(*[p.ctypes.data for p in self.mvImagePyramid])
+            pyr_ptrs = ctypes.cast(arr, _vp)
+        _check(lib().b2s_extract(self._h, image.ctypes.data_as(_vp), w, h, image.strides[0], _p(kps), _p(desc), self.cap,
+                                 ctypes.byref(n), pyr_ptrs))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def level_dims(self, w, h):
+        return [(int(np.rint(np.float32(w) * s)), int(np.rint(np.float32(h) * s))) for s in self.mvInvScaleFactor]
+
+    def extract_batch(self, images):
+        B = len(images)
+        h, w = images[0].shape
+        kps = np.zeros((B, self.cap), keypoint_dtype)
+        desc = np.zeros((B, self.cap, 32), np.uint8)
+        n = np.zeros(B, np.int32)
+        imgs = [np.ascontiguousarray(im) for im in images]
+        ptrs = (_vp * B)(*[im.ctypes.data for im in imgs])
+        _check(lib().b2s_extract_batch(self._h, ctypes.cast(ptrs, _vp), B, w, h, w, _p(kps), _p(desc), self.cap, _p(n)))
+        return [(kps[b, :n[b]].copy(), desc[b, :n[b]].copy()) for b in range(B)]
+
+    def extract_batch_device(self, d_imgs_ptr, img_pitch_bytes, batch, w, h, stride, d_kps_ptr, d_desc_ptr, d_counts_ptr,
+                             cap, stream=None):
+        _check(lib().b2s_extract_batch_device(self._h, _vp(d_imgs_ptr), img_pitch_bytes, batch, w, h, stride,
+                                              _vp(d_kps_ptr), _vp(d_desc_ptr), _vp(d_counts_ptr), cap,
+                                              _vp(stream) if stream else None))
+
+    def check(self):
+        _check(lib().b2s_extractor_check(self._h))
+
+    def launch_count(self):
+        return lib().b2s_extractor_launch_count(self._h)
+
+    # test hooks
+    def debug_level(self, b, level, blurred=False):
+        w, h = ctypes.c_int(0), ctypes.c_int(0)
+        _check(lib().b2s_extractor_debug_level(self._h, b, level, int(blurred), None, ctypes.byref(w), ctypes.byref(h)))
+        out = np.zeros((h.value, w.value), np.uint8)
+        _check(lib().b2s_extractor_debug_level(self._h, b, level, int(blurred), _p(out), None, None))
+        return out
+
+    def debug_candidates(self, b, level):
+        cap = 70000
+        xy = np.zeros((cap, 2), np.int32)
+        resp = np.zeros(cap, np.int32)
+        n = ctypes.c_int(0)
+        _check(lib().b2s_extractor_debug_candidates(self._h, b, level, _p(xy), _p(resp), cap, ctypes.byref(n)))
+        return xy[:n.value].copy(), resp[:n.value].copy()
+
+
+class ORBmatcher:
+    """Mirror of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:57-215) on flattened arrays."""
+    TH_HIGH, TH_LOW, HISTO_LENGTH = TH_HIGH, TH_LOW, HISTO_LENGTH
+
+    def __init__(self, nnratio=0.6, checkOri=True, max_features=4096, max_batch=1, device=0):
+        self.mfNNratio = np.float32(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+        self._h = _vp()
+        _check(lib().b2s_matcher_create(max_features, max_batch, device, ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().b2s_matcher_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_count(self):
+        return lib().b2s_matcher_launch_count(self._h)
+
+    def DescriptorDistance(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        out = np.zeros(len(a), np.int32)
+        _check(lib().b2s_descriptor_distance(self._h, _p(a), _p(b), len(a), _p(out)))
+        return out
+
+    def SearchByBoW(self, descA, nodeA, validA, angA, descB, nodeB, angB, validB=None, strict_lt=False, th_low=TH_LOW):
+        nA, nB = len(descA), len(descB)
+        match = np.full(nB, -1, np.int32)
+        nm = ctypes.c_int(0)
+        _check(lib().b2s_search_by_bow(self._h, _p(descA), _p(nodeA), _p(validA), _p(angA), nA, _p(descB), _p(nodeB),
+                                       _p(validB), _p(angB), nB, th_low, float(self.mfNNratio), int(strict_lt),
+                                       int(self.mbCheckOrientation), _p(match), ctypes.byref(nm)))
+        return nm.value, match
+
+    def SearchByProjection(self, queries, kpx, kpy, octave, angle, uright, occupied, desc, geom, th, mode=0,
+                           th_high=TH_HIGH):
+        nf = len(kpx)
+        sf = np.ascontiguousarray(geom["scale_factors"], np.float32)
+        g = _FrameGeom(geom["mnMinX"], geom["mnMinY"], geom["mnMaxX"], geom["mnMaxY"], geom["bf"], sf.ctypes.data, len(sf))
+        match = np.full(nf, -1, np.int32)
+        nm = ctypes.c_int(0)
+        _check(lib().b2s_search_by_projection_last(self._h, _p(queries), len(queries), _p(kpx), _p(kpy), _p(octave),
+                                                   _p(angle), _p(uright), _p(occupied), _p(desc), nf, ctypes.byref(g),
+                                                   float(th), mode, th_high, int(self.mbCheckOrientation), _p(match),
+                                                   ctypes.byref(nm)))
+        return nm.value, match
+
+
+class Optimizer:
+    """Mirror of ORB_SLAM2::Optimizer::LocalBundleAdjustment (include/Optimizer.h:112) on a flattened window."""
+
+    def __init__(self, max_kf=64, max_mp=8192, max_edges=65536, max_batch=1, device=0):
+        self._h = _vp()
+        _check(lib().b2s_ba_create(max_kf, max_mp, max_edges, max_batch, device, ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().b2s_ba_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_count(self):
+        return lib().b2s_ba_launch_count(self._h)
+
+    @staticmethod
+    def _problem(d, its1=5, its2=10):
+        keep = dict(Tcw=np.ascontiguousarray(d["Tcw"], np.float32), fixed=np.ascontiguousarray(d["fixed"], np.uint8),
+                    points=np.ascontiguousarray(d["points"], np.float32), edges=np.ascontiguousarray(d["edges"]))
+        assert keep["edges"].dtype == ba_edge_dtype
+        p = _BaProblem(d["n_kf"], d["n_local"], keep["Tcw"].ctypes.data, keep["fixed"].ctypes.data, len(keep["points"]),
+                       keep["points"].ctypes.data, len(keep["edges"]), keep["edges"].ctypes.data, d["fx"], d["fy"],
+                       d["cx"], d["cy"], d["bf"], its1, its2)
+        return p, keep
+
+    @staticmethod
+    def _result(d):
+        out = dict(Tcw=np.zeros((d["n_local"], 16), np.float32), points=np.zeros((len(d["points"]), 3), np.float32),
+                   outlier=np.zeros(len(d["edges"]), np.uint8), trace=np.full(256, -1, np.int32))
+        r = _BaResult(out["Tcw"].ctypes.data, out["points"].ctypes.data, out["outlier"].ctypes.data,
+                      out["trace"].ctypes.data, 0.0, 0)
+        return r, out
+
+    def LocalBundleAdjustment(self, d, stop=None, its1=5, its2=10):
+        p, keep = self._problem(d, its1, its2)
+        r, out = self._result(d)
+        rc = lib().b2s_local_ba(self._h, ctypes.byref(p), _p(stop), ctypes.byref(r))
+        if rc == ERR_ABORTED:
+            return None
+        _check(rc)
+        out["chi2"] = r.chi2_final
+        out["n_trials"] = r.n_trials
+        return out
+
+    def LocalBundleAdjustmentBatch(self, ds, its1=5, its2=10):
+        B = len(ds)
+        probs = (_BaProblem * B)()
+        ress = (_BaResult * B)()
+        keeps, outs = [], []
+        for i, d in enumerate(ds):
+            p, keep = self._problem(d, its1, its2)
+            r, out = self._result(d)
+            probs[i], ress[i] = p, r
+            keeps.append(keep)
+            outs.append(out)
+        _check(lib().b2s_local_ba_batch(self._h, B, ctypes.cast(probs, _vp), ctypes.cast(ress, _vp)))
+        for i in range(B):
+            outs[i]["chi2"] = ress[i].chi2_final
+            outs[i]["n_trials"] = ress[i].n_trials
+        return outs

@@ -1,0 +1,1274 @@
+// extractor.cu — B200 (sm_100a) ORB extractor: pyramid, per-cell FAST-9/16 + NMS + dual threshold, parallel
+// order-preserving quadtree, intensity-centroid orientation, Q8 Gaussian blur, steered rBRIEF.
+//
+// Replaces the body of ORBextractor::operator() (/root/reference/src/ORBextractor.cc:1544-1668) and the OpenCV
+// primitives it calls.  Every stage is integer- or explicitly-rounded-float arithmetic so results are bit-identical
+// to the reference CPU path (tests/test_extractor_gpu.py checks against oracle/).
+#include <math.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "extractor.cuh"
+
+namespace b2s {
+
+// rBRIEF pattern: 256 x (x0,y0,x1,y1) int8 (data/orb_pattern_31.inc; reference table src/ORBextractor.cc:231-489)
+static const int8_t h_pattern[1024] = {
+#include "../../data/orb_pattern_31.inc"
+};
+__constant__ int8_t c_pattern[1024];
+__constant__ int c_umax[16];
+
+// ------------------------------------------------------------------------------------------------
+// K1: pyramid level l from level l-1 — cv::resize INTER_LINEAR u8 fixed-point recipe,
+//     called at src/ORBextractor.cc:1696.  Tables are built on the host with the same float arithmetic.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_resize(ExtractGeom g, int l, uint8_t* __restrict__ pyr,
+                                                const int16_t* __restrict__ rxOfs, const uint32_t* __restrict__ rxAlpha,
+                                                const int16_t* __restrict__ ryOfs, const uint32_t* __restrict__ ryBeta) {
+  const LevelGeom& S = g.lv[l - 1];
+  const LevelGeom& D = g.lv[l];
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= D.w) return;
+  const uint8_t* src = pyr + (size_t)blockIdx.z * g.pyrBytes + S.off;
+  uint8_t* dst = pyr + (size_t)blockIdx.z * g.pyrBytes + D.off;
+  const int sy = ryOfs[D.ryOff + y];
+  const uint32_t bb = ryBeta[D.ryOff + y];
+  const int b0 = (int16_t)(bb & 0xffffu), b1 = (int16_t)(bb >> 16);
+  const int sy0 = min(max(sy, 0), S.h - 1), sy1 = min(max(sy + 1, 0), S.h - 1);
+  const int sx = rxOfs[D.rxOff + x];
+  const uint32_t aa = rxAlpha[D.rxOff + x];
+  const int a0 = (int16_t)(aa & 0xffffu), a1 = (int16_t)(aa >> 16);
+  const int sx1 = min(sx + 1, S.w - 1);
+  const uint8_t* r0 = src + (size_t)sy0 * S.pitch;
+  const uint8_t* r1 = src + (size_t)sy1 * S.pitch;
+  const int h0 = r0[sx] * a0 + r0[sx1] * a1;
+  const int h1 = r1[sx] * a0 + r1[sx1] * a1;
+  dst[(size_t)y * D.pitch + x] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: per-cell FAST-9/16 score + 3x3 NMS + ini->min threshold fallback.
+//     One CTA per 30-px cell of src/ORBextractor.cc:1089-1157 (cv::FAST on the cell ROI, :1126,1135).
+//     M = max over the 16 arcs of min|v-p| (same sign); corner at th <=> M > th; response = M-1.
+// ------------------------------------------------------------------------------------------------
+constexpr int FP = 72;  // smem pitch of the cell ROI (ROI width <= 66)
+constexpr int FR = 68;  // max ROI rows
+// Bresenham circle r=3 offsets (dx,dy) in OpenCV order
+#define B2S_CIRCLE(F) \
+  F(0, 0, 3) F(1, 1, 3) F(2, 2, 2) F(3, 3, 1) F(4, 3, 0) F(5, 3, -1) F(6, 2, -2) F(7, 1, -3) F(8, 0, -3) F(9, -1, -3) \
+      F(10, -2, -2) F(11, -3, -1) F(12, -3, 0) F(13, -3, 1) F(14, -2, 2) F(15, -1, 3)
+
+__device__ __forceinline__ int fast_arc_strength(const uint8_t* c, int minTh) {
+  const int v = c[0];
+  int d[16];
+#define LD(k, dx, dy) d[k] = v - (int)c[(dy)*FP + (dx)];
+  B2S_CIRCLE(LD)
+#undef LD
+  // exact quick reject: every 9-arc holds one pixel of each opposite pair (k,k+8)
+  int dk = __vimin3_s32(max(d[0], d[8]), max(d[1], d[9]), max(d[2], d[10]));
+  dk = __vimin3_s32(dk, max(d[3], d[11]), max(d[4], d[12]));
+  dk = __vimin3_s32(dk, max(d[5], d[13]), max(d[6], d[14]));
+  dk = min(dk, max(d[7], d[15]));
+  int br = __vimax3_s32(min(d[0], d[8]), min(d[1], d[9]), min(d[2], d[10]));
+  br = __vimax3_s32(br, min(d[3], d[11]), min(d[4], d[12]));
+  br = __vimax3_s32(br, min(d[5], d[13]), min(d[6], d[14]));
+  br = max(br, min(d[7], d[15]));
+  if (dk <= minTh && -br <= minTh) return 0;
+  int t3n[16], t3x[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    t3n[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    t3x[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+  }
+  int dark = -512, bright = 512;
+#pragma unroll
+  for (int s = 0; s < 16; s++) {
+    dark = max(dark, __vimin3_s32(t3n[s], t3n[(s + 3) & 15], t3n[(s + 6) & 15]));
+    bright = min(bright, __vimax3_s32(t3x[s], t3x[(s + 3) & 15], t3x[(s + 6) & 15]));
+  }
+  return __vimax3_s32(dark, -bright, 0);
+}
+
+__global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t* __restrict__ pyr,
+                                                    uint32_t* __restrict__ candXY, uint32_t* __restrict__ candKey,
+                                                    uint8_t* __restrict__ candResp, int32_t* __restrict__ candCount,
+                                                    int32_t* __restrict__ status) {
+  __shared__ __align__(16) uint8_t tile[FR * FP];
+  __shared__ __align__(16) uint8_t score[FR * FP];
+  __shared__ uint32_t list[1024];
+  __shared__ int sN, sHi, sBase, sEmit;
+  const int b = blockIdx.y;
+  const int cid = blockIdx.x;
+  int l = 0;
+  while (l + 1 < g.nlevels && cid >= g.lv[l + 1].cellStart) l++;
+  const LevelGeom& L = g.lv[l];
+  const int c = cid - L.cellStart;
+  const int ci = c / L.nCols, cj = c - ci * L.nCols;
+  const int iniY = kMinBorder + ci * L.hCell;
+  int maxY = iniY + L.hCell + 6;
+  if (iniY >= L.maxBY - 3) return;  // :1099
+  if (maxY > L.maxBY) maxY = L.maxBY;
+  const int iniX = kMinBorder + cj * L.wCell;
+  int maxX = iniX + L.wCell + 6;
+  if (iniX >= L.maxBX - 6) return;  // :1116
+  if (maxX > L.maxBX) maxX = L.maxBX;
+  const int rw = maxX - iniX, rh = maxY - iniY;
+  if (rw < 7 || rh < 7) return;
+  const int tid = threadIdx.x;
+  const uint8_t* src = pyr + (size_t)b * g.pyrBytes + L.off + (size_t)iniY * L.pitch + iniX;
+  for (int idx = tid; idx < rh * FP; idx += 128) {
+    const int y = idx / FP, x = idx - y * FP;
+    tile[idx] = (x < rw) ? src[(size_t)y * L.pitch + x] : 0;
+    score[idx] = 0;
+  }
+  if (tid == 0) {
+    sN = 0;
+    sHi = 0;
+  }
+  __syncthreads();
+  const int iw = rw - 6, ih = rh - 6;
+  for (int p = tid; p < iw * ih; p += 128) {
+    const int y = p / iw + 3, x = p - (y - 3) * iw + 3;
+    const int M = fast_arc_strength(&tile[y * FP + x], g.minTh);
+    score[y * FP + x] = (uint8_t)min(M, 255);
+  }
+  __syncthreads();
+  // 3x3 NMS inside the cell's detectable area (rim scores are 0 == "not a corner" in OpenCV's buffers)
+  for (int p = tid; p < iw * ih; p += 128) {
+    const int y = p / iw + 3, x = p - (y - 3) * iw + 3;
+    const uint8_t* s = &score[y * FP + x];
+    const int M = s[0];
+    if (M <= g.minTh) continue;
+    const int nb = max(max(max(s[-FP - 1], s[-FP]), max(s[-FP + 1], s[-1])), max(max(s[1], s[FP - 1]), max(s[FP], s[FP + 1])));
+    if (M > nb) {
+      const int slot = atomicAdd(&sN, 1);
+      if (M > g.iniTh) atomicAdd(&sHi, 1);
+      if (slot < 1024) list[slot] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)M << 16);
+    }
+  }
+  __syncthreads();
+  const int nList = min(sN, 1024);
+  const bool useHi = sHi > 0;  // cell produced corners at iniThFAST -> keep only those (:1132-1139)
+  if (tid == 0) {
+    sEmit = 0;
+    const int nEmit = useHi ? sHi : sN;
+    sBase = nEmit ? atomicAdd(&candCount[b * kMaxLevels + l], nEmit) : 0;
+    if (sN > 1024 || (nEmit && sBase + nEmit > L.candCap)) atomicOr(status, 1);
+  }
+  __syncthreads();
+  const size_t cbase = (size_t)b * g.totalCandCap + L.candOff;
+  for (int k = tid; k < nList; k += 128) {
+    const uint32_t e = list[k];
+    const int x = e & 0xff, y = (e >> 8) & 0xff, M = e >> 16;
+    if (useHi && M <= g.iniTh) continue;
+    const int slot = sBase + atomicAdd(&sEmit, 1);
+    if (slot >= L.candCap) continue;
+    candXY[cbase + slot] = (uint32_t)(x + cj * L.wCell) | ((uint32_t)(y + ci * L.hCell) << 16);  // :1150-1151
+    candKey[cbase + slot] = ((uint32_t)c << 12) | ((uint32_t)(y - 3) << 6) | (uint32_t)(x - 3);
+    candResp[cbase + slot] = (uint8_t)(M - 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: DistributeOctTree (src/ORBextractor.cc:706-1049) as a data-parallel, order-preserving emulation.
+//     One CTA per (image, level).  The std::list is an array in list order; a pass over the list becomes:
+//     histogram the keypoints of every splittable node into 4 quadrants, scan to get the new list positions
+//     (children are push_front'ed -> the new front section is in reverse creation order, untouched nodes keep
+//     their relative order behind it), relabel the keypoints.  The "expand largest first" phase (:929-1010)
+//     sorts candidates by (count desc, creation order desc), prefix-sums the growth and cuts where size>=N.
+//     The first-max-response-in-insertion-order rule (:1022-1045) is an atomicMax over (response, ~orderkey).
+// ------------------------------------------------------------------------------------------------
+struct QtNodes {
+  int16_t *x0, *x1, *y0, *y1;
+  int* cnt;
+  uint8_t* created;
+};
+
+__device__ void warp0_excl_scan(int* a, int n, int* total) {  // call from all threads; caller syncs afterwards
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const int chunk = (n + 31) / 32;
+    const int beg = min(lane * chunk, n), end = min(beg + chunk, n);
+    int s = 0;
+    for (int i = beg; i < end; i++) s += a[i];
+    const int incl = warp_incl_scan(s, lane);
+    int run = incl - s;
+    for (int i = beg; i < end; i++) {
+      const int v = a[i];
+      a[i] = run;
+      run += v;
+    }
+    if (lane == 31) *total = incl;
+  }
+}
+
+__device__ __forceinline__ int qt_quadrant(int x, int y, int x0, int x1, int y0, int y1) {
+  const int mx = x0 + ((x1 - x0 + 1) >> 1);  // ceil(w/2), :641-642
+  const int my = y0 + ((y1 - y0 + 1) >> 1);
+  return (x < mx ? 0 : 1) + (y < my ? 0 : 2);  // n1=UL n2=UR n3=BL n4=BR
+}
+
+__global__ void __launch_bounds__(256) k_quadtree(ExtractGeom g, int capMax, const uint32_t* __restrict__ candXY,
+                                                  const uint32_t* __restrict__ candKey,
+                                                  const uint8_t* __restrict__ candResp, uint16_t* __restrict__ candNode,
+                                                  uint8_t* __restrict__ candQ, const int32_t* __restrict__ candCount,
+                                                  uint32_t* __restrict__ selXYR, int32_t* __restrict__ selCount,
+                                                  int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int l = blockIdx.x, b = blockIdx.y;
+  const LevelGeom& L = g.lv[l];
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int n = min(candCount[b * kMaxLevels + l], L.candCap);
+  int32_t* selCnt = selCount + b * kMaxLevels + l;
+  if (n == 0) {
+    if (tid == 0) *selCnt = 0;
+    return;
+  }
+  const size_t cbase = (size_t)b * g.totalCandCap + L.candOff;
+  const uint32_t* xy = candXY + cbase;
+  const uint32_t* key = candKey + cbase;
+  const uint8_t* resp = candResp + cbase;
+  uint16_t* node = candNode + cbase;
+  uint8_t* Q = candQ + cbase;
+  const int CAP = capMax;
+  // carve shared memory
+  uint8_t* p = smem;
+  unsigned long long* best = (unsigned long long*)p; p += sizeof(unsigned long long) * CAP;
+  int* cc = (int*)p; p += sizeof(int) * CAP * 4;
+  int* childPos = (int*)p; p += sizeof(int) * CAP * 4;
+  int* newPos = (int*)p; p += sizeof(int) * CAP;
+  int* aux1 = (int*)p; p += sizeof(int) * CAP;
+  int* aux2 = (int*)p; p += sizeof(int) * CAP;
+  int* aux3 = (int*)p; p += sizeof(int) * CAP;
+  int* aux4 = (int*)p; p += sizeof(int) * CAP;
+  QtNodes nb[2];
+  for (int k = 0; k < 2; k++) {
+    nb[k].cnt = (int*)p; p += sizeof(int) * CAP;
+  }
+  for (int k = 0; k < 2; k++) {
+    nb[k].x0 = (int16_t*)p; p += 2 * CAP;
+    nb[k].x1 = (int16_t*)p; p += 2 * CAP;
+    nb[k].y0 = (int16_t*)p; p += 2 * CAP;
+    nb[k].y1 = (int16_t*)p; p += 2 * CAP;
+  }
+  for (int k = 0; k < 2; k++) {
+    nb[k].created = p; p += CAP;
+  }
+  __shared__ int sTot1, sTot2, sSize, sNToExpand, sFlag, sCut;
+  int cur = 0;
+
+  const int N = L.N;
+  const int Hq = L.maxBY - kMinBorder;
+  // ---- roots (:719-767) ----
+  const int nIni = L.nIni;
+  if (tid < nIni) {
+    nb[0].x0[tid] = (int16_t)(int)__fmul_rn(L.hX, (float)tid);
+    nb[0].x1[tid] = (int16_t)(int)__fmul_rn(L.hX, (float)(tid + 1));
+    nb[0].y0[tid] = 0;
+    nb[0].y1[tid] = (int16_t)Hq;
+    nb[0].cnt[tid] = 0;
+    nb[0].created[tid] = 0;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += T) {
+    const int x = xy[i] & 0xffff;
+    int r = (int)__fdiv_rn((float)x, L.hX);  // vpIniNodes[kp.pt.x/hX] :766
+    r = min(r, nIni - 1);
+    node[i] = (uint16_t)r;
+    atomicAdd(&nb[0].cnt[r], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {  // erase empty roots, keep order (:771-786); nIni is tiny
+    int m = 0;
+    for (int r = 0; r < nIni; r++) {
+      if (nb[0].cnt[r] > 0) {
+        newPos[r] = m;
+        nb[1].x0[m] = nb[0].x0[r]; nb[1].x1[m] = nb[0].x1[r];
+        nb[1].y0[m] = nb[0].y0[r]; nb[1].y1[m] = nb[0].y1[r];
+        nb[1].cnt[m] = nb[0].cnt[r];
+        nb[1].created[m] = 0;
+        m++;
+      } else
+        newPos[r] = 0;
+    }
+    sSize = m;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += T) node[i] = (uint16_t)newPos[node[i]];
+  cur = 1;
+  int size = sSize;
+  __syncthreads();
+
+  bool finish = false;
+  bool overflow = false;
+  while (!finish) {
+    const int prevSize = size;
+    QtNodes A = nb[cur], B = nb[cur ^ 1];
+    // ---- full pass over the list (:801-905) ----
+    for (int k = tid; k < size * 4; k += T) cc[k] = 0;
+    if (tid == 0) sNToExpand = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += T) {
+      const int nd = node[i];
+      if (A.cnt[nd] > 1) {
+        const uint32_t v = xy[i];
+        const int q = qt_quadrant(v & 0xffff, v >> 16, A.x0[nd], A.x1[nd], A.y0[nd], A.y1[nd]);
+        Q[i] = (uint8_t)q;
+        atomicAdd(&cc[nd * 4 + q], 1);
+      }
+    }
+    __syncthreads();
+    for (int nd = tid; nd < size; nd += T) {
+      const bool e = A.cnt[nd] > 1;
+      const int nch = e ? ((cc[nd * 4] > 0) + (cc[nd * 4 + 1] > 0) + (cc[nd * 4 + 2] > 0) + (cc[nd * 4 + 3] > 0)) : 0;
+      aux1[nd] = nch;
+      aux3[nd] = nch;
+      aux2[nd] = e ? 0 : 1;
+    }
+    __syncthreads();
+    warp0_excl_scan(aux1, size, &sTot1);
+    __syncthreads();
+    warp0_excl_scan(aux2, size, &sTot2);
+    __syncthreads();
+    const int totalCh = sTot1, totalStay = sTot2;
+    const int newSize = totalCh + totalStay;
+    if (newSize > CAP) {
+      overflow = true;
+      break;
+    }
+    for (int nd = tid; nd < size; nd += T) {
+      if (A.cnt[nd] > 1) {
+        const int x0 = A.x0[nd], x1 = A.x1[nd], y0 = A.y0[nd], y1 = A.y1[nd];
+        const int mx = x0 + ((x1 - x0 + 1) >> 1), my = y0 + ((y1 - y0 + 1) >> 1);
+        int pos = totalCh - aux1[nd] - aux3[nd];
+        for (int q = 3; q >= 0; q--) {  // n4 was pushed last -> frontmost
+          const int cq = cc[nd * 4 + q];
+          if (cq == 0) continue;
+          B.x0[pos] = (int16_t)((q & 1) ? mx : x0);
+          B.x1[pos] = (int16_t)((q & 1) ? x1 : mx);
+          B.y0[pos] = (int16_t)((q & 2) ? my : y0);
+          B.y1[pos] = (int16_t)((q & 2) ? y1 : my);
+          B.cnt[pos] = cq;
+          B.created[pos] = 1;
+          childPos[nd * 4 + q] = pos;
+          if (cq > 1) atomicAdd(&sNToExpand, 1);
+          pos++;
+        }
+      } else {
+        const int pos = totalCh + aux2[nd];
+        B.x0[pos] = A.x0[nd]; B.x1[pos] = A.x1[nd];
+        B.y0[pos] = A.y0[nd]; B.y1[pos] = A.y1[nd];
+        B.cnt[pos] = A.cnt[nd];
+        B.created[pos] = 0;
+        newPos[nd] = pos;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += T) {
+      const int nd = node[i];
+      node[i] = (uint16_t)((A.cnt[nd] > 1) ? childPos[nd * 4 + Q[i]] : newPos[nd]);
+    }
+    const int nToExpand = sNToExpand;
+    __syncthreads();
+    cur ^= 1;
+    size = newSize;
+    if (size >= N || size == prevSize) {
+      finish = true;
+    } else if (size + nToExpand * 3 > N) {
+      // ---- expand-largest-first phase (:929-1010) ----
+      while (!finish) {
+        const int prevSize2 = size;
+        QtNodes C = nb[cur], D = nb[cur ^ 1];
+        for (int k = tid; k < size * 4; k += T) cc[k] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += T) {
+          const int nd = node[i];
+          if (C.created[nd] && C.cnt[nd] > 1) {
+            const uint32_t v = xy[i];
+            const int q = qt_quadrant(v & 0xffff, v >> 16, C.x0[nd], C.x1[nd], C.y0[nd], C.y1[nd]);
+            Q[i] = (uint8_t)q;
+            atomicAdd(&cc[nd * 4 + q], 1);
+          }
+        }
+        __syncthreads();
+        // rank candidates by (count desc, list position asc == creation order desc)
+        for (int a = tid; a < size; a += T) {
+          const bool isC = C.created[a] && C.cnt[a] > 1;
+          int r = -1;
+          if (isC) {
+            r = 0;
+            const int ca = C.cnt[a];
+            for (int o = 0; o < size; o++) {
+              if (!(C.created[o] && C.cnt[o] > 1)) continue;
+              const int co = C.cnt[o];
+              r += (co > ca) || (co == ca && o < a);
+            }
+          }
+          aux4[a] = r;  // rank of node a, -1 if not a candidate
+        }
+        for (int k = tid; k < size; k += T) aux1[k] = 0;
+        if (tid == 0) sFlag = 0;
+        __syncthreads();
+        for (int a = tid; a < size; a += T) {
+          const int r = aux4[a];
+          if (r >= 0) {
+            const int nch = (cc[a * 4] > 0) + (cc[a * 4 + 1] > 0) + (cc[a * 4 + 2] > 0) + (cc[a * 4 + 3] > 0);
+            aux1[r] = nch;  // children in rank order
+            aux3[r] = a;    // rank -> node
+            atomicAdd(&sFlag, 1);
+          }
+        }
+        __syncthreads();
+        const int m = sFlag;  // number of candidates
+        if (m == 0) {
+          finish = true;  // nothing to split: size == prevSize
+          break;
+        }
+        // inclusive prefix of children count in rank order (aux2), find the cut where size reaches N
+        for (int k = tid; k < m; k += T) aux2[k] = aux1[k];
+        __syncthreads();
+        warp0_excl_scan(aux2, m, &sTot1);
+        __syncthreads();
+        if (tid == 0) sCut = m - 1;
+        __syncthreads();
+        for (int r = tid; r < m; r += T) {
+          // size after processing ranks 0..r : size + sum(nch) - (r+1)
+          const int after = size + aux2[r] + aux1[r] - (r + 1);
+          if (after >= N) atomicMin(&sCut, r);
+        }
+        __syncthreads();
+        const int cut = sCut;
+        const int totalChP = aux2[cut] + aux1[cut];
+        const int np = cut + 1;
+        const int newSize2 = totalChP + (size - np);
+        if (newSize2 > CAP) {
+          overflow = true;
+          break;
+        }
+        // unprocessed nodes keep their relative order behind the new children
+        for (int a = tid; a < size; a += T) {
+          const int r = aux4[a];
+          newPos[a] = (r >= 0 && r <= cut) ? 0 : 1;
+        }
+        __syncthreads();
+        warp0_excl_scan(newPos, size, &sTot2);
+        __syncthreads();
+        for (int a = tid; a < size; a += T) {
+          const int r = aux4[a];
+          if (r >= 0 && r <= cut) {
+            const int x0 = C.x0[a], x1 = C.x1[a], y0 = C.y0[a], y1 = C.y1[a];
+            const int mx = x0 + ((x1 - x0 + 1) >> 1), my = y0 + ((y1 - y0 + 1) >> 1);
+            int pos = totalChP - (aux2[r] + aux1[r]);  // later-processed parents' children sit in front
+            for (int q = 3; q >= 0; q--) {
+              const int cq = cc[a * 4 + q];
+              if (cq == 0) continue;
+              D.x0[pos] = (int16_t)((q & 1) ? mx : x0);
+              D.x1[pos] = (int16_t)((q & 1) ? x1 : mx);
+              D.y0[pos] = (int16_t)((q & 2) ? my : y0);
+              D.y1[pos] = (int16_t)((q & 2) ? y1 : my);
+              D.cnt[pos] = cq;
+              D.created[pos] = 1;
+              childPos[a * 4 + q] = pos;
+              pos++;
+            }
+          } else {
+            const int pos = totalChP + newPos[a];
+            D.x0[pos] = C.x0[a]; D.x1[pos] = C.x1[a];
+            D.y0[pos] = C.y0[a]; D.y1[pos] = C.y1[a];
+            D.cnt[pos] = C.cnt[a];
+            D.created[pos] = 0;
+            newPos[a] = pos;
+          }
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += T) {
+          const int nd = node[i];
+          const int r = aux4[nd];
+          node[i] = (uint16_t)((r >= 0 && r <= cut) ? childPos[nd * 4 + Q[i]] : newPos[nd]);
+        }
+        __syncthreads();
+        cur ^= 1;
+        size = newSize2;
+        if (size >= N || size == prevSize2) finish = true;
+      }
+      if (overflow) break;
+    }
+  }
+  if (overflow) {
+    if (tid == 0) {
+      atomicOr(status, 4);
+      *selCnt = 0;
+    }
+    return;
+  }
+  // ---- keep the best keypoint of every node (:1022-1045) ----
+  for (int k = tid; k < size; k += T) best[k] = 0ull;
+  __syncthreads();
+  for (int i = tid; i < n; i += T) {
+    const unsigned long long v = ((unsigned long long)(resp[i] + 1u) << 32) | (unsigned long long)(0xFFFFFFFFu - key[i]);
+    atomicMax(&best[node[i]], v);
+  }
+  __syncthreads();
+  uint32_t* sel = selXYR + ((size_t)b * g.totalSelCap + L.selOff) * 2;
+  for (int k = tid; k < size; k += T) {
+    const unsigned long long v = best[k];
+    const uint32_t ky = 0xFFFFFFFFu - (uint32_t)(v & 0xFFFFFFFFull);
+    const uint32_t r = (uint32_t)(v >> 32) - 1u;
+    const int cell = ky >> 12, yl = (ky >> 6) & 63, xl = ky & 63;
+    const int ci = cell / L.nCols, cj = cell - ci * L.nCols;
+    const int x = cj * L.wCell + xl + 3 + kMinBorder;  // :1184-1185
+    const int y = ci * L.hCell + yl + 3 + kMinBorder;
+    sel[k * 2] = (uint32_t)x | ((uint32_t)y << 16);
+    sel[k * 2 + 1] = r;
+  }
+  if (tid == 0) *selCnt = size;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5a: GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101, OpenCV-4 fixed point (Q8 taps, one final rounding).
+//      src/ORBextractor.cc:1626-1634.  64x32 output tile per CTA, separable through shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int BT_W = 64, BT_H = 32, BT_P = 72;
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * (n - 1) - p;
+  return p;
+}
+
+__global__ void __launch_bounds__(256) k_blur(ExtractGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
+  __shared__ __align__(16) uint8_t in[(BT_H + 6) * BT_P];
+  __shared__ __align__(16) uint16_t Hs[(BT_H + 6) * BT_W];
+  const int b = blockIdx.y;
+  int l = 0;
+  while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].blurTileStart) l++;
+  const LevelGeom& L = g.lv[l];
+  const int t = blockIdx.x - L.blurTileStart;
+  const int ty = t / L.blurTilesX, tx = t - ty * L.blurTilesX;
+  const int ox = tx * BT_W, oy = ty * BT_H;
+  const uint8_t* src = pyr + (size_t)b * g.pyrBytes + L.off;
+  uint8_t* dst = blur + (size_t)b * g.pyrBytes + L.off;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < (BT_H + 6) * (BT_W + 6); idx += 256) {
+    const int r = idx / (BT_W + 6), c = idx - r * (BT_W + 6);
+    const int sy = reflect101(oy + r - 3, L.h), sx = reflect101(ox + c - 3, L.w);
+    in[r * BT_P + c] = src[(size_t)sy * L.pitch + sx];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < (BT_H + 6) * BT_W; idx += 256) {
+    const int r = idx / BT_W, c = idx - r * BT_W;
+    const uint8_t* q = &in[r * BT_P + c];
+    Hs[idx] = (uint16_t)(18 * (q[0] + q[6]) + 34 * (q[1] + q[5]) + 48 * (q[2] + q[4]) + 56 * q[3]);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < BT_H * BT_W; idx += 256) {
+    const int r = idx / BT_W, c = idx - r * BT_W;
+    const int x = ox + c, y = oy + r;
+    if (x >= L.w || y >= L.h) continue;
+    const uint16_t* q = &Hs[r * BT_W + c];
+    const uint32_t acc = 18u * (q[0] + q[6 * BT_W]) + 34u * (q[BT_W] + q[5 * BT_W]) + 48u * (q[2 * BT_W] + q[4 * BT_W]) +
+                         56u * q[3 * BT_W];
+    dst[(size_t)y * L.pitch + x] = (uint8_t)((acc + 32768u) >> 16);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4+K5b: IC_Angle (:108-161) + cv::fastAtan2 (:160) + computeOrbDescriptor (:173-227), one warp per keypoint.
+//      cosf/sinf restate glibc 2.39's FMA sincosf kernels operation by operation (DESIGN.md "float trig");
+//      tap coordinates use unfused float mul/add and round-half-even, like the oracle's -ffp-contract=off build.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dev_fast_atan2(float y, float x) {
+  const float scale = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale, p5 = 0.1555786518463281f * scale,
+              p7 = -0.04432655554792128f * scale;
+  const float eps = (float)2.2204460492503131e-16;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f,
+                  __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+// glibc 2.39 x86_64 __sinf_fma/__cosf_fma for |y| < 120 (sysdeps/ieee754/flt-32/s_sincosf.h), verified
+// exhaustively against libm over every float in [0, 2*pi] (tests/test_sincosf_mirror.py).
+__device__ __forceinline__ double sc_sinpoly(double xs, double x2) {
+  const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+  const double s1 = __fma_rn(S3, x2, S2);
+  const double x3 = __dmul_rn(x2, xs);
+  const double x5 = __dmul_rn(x2, x3);
+  const double s = __fma_rn(x3, S1, xs);
+  return __fma_rn(s1, x5, s);
+}
+__device__ __forceinline__ double sc_cospoly(double x2, double sg) {
+  const double C0 = 1.0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
+               C4 = 0x1.99343027bf8c3p-16;
+  const double x4 = __dmul_rn(x2, x2);
+  const double c1 = __fma_rn(sg * C1, x2, sg * C0);
+  const double c2 = __fma_rn(sg * C4, x2, sg * C3);
+  const double x6 = __dmul_rn(x2, x4);
+  const double c = __fma_rn(x4, sg * C2, c1);
+  return __fma_rn(c2, x6, c);
+}
+__device__ __forceinline__ void dev_sincosf(float y, float* sn, float* cs) {
+  const double HPI_INV = 0x1.45f306dc9c883p+23, HPI = 0x1.921fb54442d18p+0;
+  const double x = (double)y;
+  const uint32_t t = (__float_as_uint(y) >> 20) & 0x7ff;
+  if (t < 0x3f4) {
+    const double x2 = __dmul_rn(x, x);
+    if (t < 0x398) {
+      *sn = y;
+      *cs = 1.0f;
+      return;
+    }
+    *sn = (float)sc_sinpoly(x, x2);
+    *cs = (float)sc_cospoly(x2, 1.0);
+    return;
+  }
+  const double r = __dmul_rn(x, HPI_INV);
+  const int n = (__double2int_rz(r) + 0x800000) >> 24;
+  const double xr = __fma_rn(-(double)n, HPI, x);
+  const double x2 = __dmul_rn(xr, xr);
+  const double sg = (n & 2) ? -1.0 : 1.0;
+  const double sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+  const double sp = sc_sinpoly(__dmul_rn(xr, sgn), x2);
+  const double cp = sc_cospoly(x2, sg);
+  if ((n & 1) == 0) {
+    *sn = (float)sp;
+    *cs = (float)cp;
+  } else {
+    *sn = (float)cp;
+    *cs = (float)sp;
+  }
+}
+
+__global__ void k_sincos_test(const float* __restrict__ in, int n, float* __restrict__ s, float* __restrict__ c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dev_sincosf(in[i], &s[i], &c[i]);
+}
+
+__global__ void __launch_bounds__(256) k_orient_describe(ExtractGeom g, const uint8_t* __restrict__ pyr,
+                                                         const uint8_t* __restrict__ blur,
+                                                         const uint32_t* __restrict__ selXYR,
+                                                         const int32_t* __restrict__ selCount,
+                                                         b2s_keypoint* __restrict__ outKps, uint8_t* __restrict__ outDesc,
+                                                         int32_t* __restrict__ outCounts, int cap,
+                                                         int32_t* __restrict__ status) {
+  __shared__ uint32_t pat[256];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  {
+    const int8_t* cp = c_pattern + tid * 4;
+    pat[(tid & 7) * 32 + (tid >> 3)] = (uint32_t)(uint8_t)cp[0] | ((uint32_t)(uint8_t)cp[1] << 8) | ((uint32_t)(uint8_t)cp[2] << 16) |
+               ((uint32_t)(uint8_t)cp[3] << 24);
+  }
+  __syncthreads();
+  const int lane = tid & 31;
+  const int wi = blockIdx.x * 8 + (tid >> 5);
+  const int32_t* sc = selCount + b * kMaxLevels;
+  if (wi == 0 && lane == 0) {
+    int tot = 0;
+    for (int k = 0; k < g.nlevels; k++) tot += sc[k];
+    if (tot > cap) {
+      atomicOr(status, 2);
+      tot = cap;
+    }
+    outCounts[b] = tot;
+  }
+  if (wi >= g.totalSelCap) return;
+  int l = 0;
+  while (l + 1 < g.nlevels && wi >= g.lv[l + 1].selOff) l++;
+  const LevelGeom& L = g.lv[l];
+  const int idx = wi - L.selOff;
+  if (idx >= sc[l]) return;
+  int outIdx = idx;
+  for (int k = 0; k < l; k++) outIdx += sc[k];
+  if (outIdx >= cap) return;
+  const uint32_t* sel = selXYR + ((size_t)b * g.totalSelCap + wi) * 2;
+  const int cx = sel[0] & 0xffff, cy = sel[0] >> 16;
+  const uint32_t resp = sel[1];
+  // IC_Angle: m10 = sum u*I, m01 = sum v*I over the 31-row circular patch (lane = column)
+  const uint8_t* img = pyr + (size_t)b * g.pyrBytes + L.off;
+  int m01 = 0, m10 = 0;
+#pragma unroll 1
+  for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
+    const int d = c_umax[v < 0 ? -v : v];
+    const int u = lane - d;
+    if (u <= d) {
+      const int val = img[(size_t)(cy + v) * L.pitch + cx + u];
+      m10 += u * val;
+      m01 += v * val;
+    }
+  }
+  m01 = warp_reduce_sum(m01);
+  m10 = warp_reduce_sum(m10);
+  const float angle = dev_fast_atan2((float)m01, (float)m10);
+  // steered BRIEF: lane i builds descriptor byte i from pattern pairs 8i..8i+7
+  const float factorPI = (float)(3.14159265358979323846 / 180.f);
+  float a, bsn;
+  dev_sincosf(__fmul_rn(angle, factorPI), &bsn, &a);  // a = cos, b = sin (:181)
+  const uint8_t* bl = blur + (size_t)b * g.pyrBytes + L.off + (size_t)cy * L.pitch + cx;
+  uint32_t val = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint32_t pp = pat[k * 32 + lane];  // pair 8*lane+k, stored transposed (bank-conflict free)
+    const float x0 = (float)(int8_t)(pp & 0xff), y0 = (float)(int8_t)((pp >> 8) & 0xff);
+    const float x1 = (float)(int8_t)((pp >> 16) & 0xff), y1 = (float)(int8_t)(pp >> 24);
+    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, bsn), __fmul_rn(y0, a)));
+    const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bsn)));
+    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bsn), __fmul_rn(y1, a)));
+    const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, bsn)));
+    const int t0 = bl[r0 * L.pitch + c0];
+    const int t1 = bl[r1 * L.pitch + c1];
+    val |= (uint32_t)(t0 < t1) << k;
+  }
+  // gather the 32 bytes into 8 words on lanes 0..7, then one 256-bit store from lane 0
+  uint32_t w = val | (__shfl_down_sync(0xffffffffu, val, 1) << 8) | (__shfl_down_sync(0xffffffffu, val, 2) << 16) |
+               (__shfl_down_sync(0xffffffffu, val, 3) << 24);
+  u256 dsc;
+#pragma unroll
+  for (int k = 0; k < 8; k++) dsc.w[k] = __shfl_sync(0xffffffffu, w, k * 4);
+  if (lane == 0) {
+    st_u256(outDesc + ((size_t)b * cap + outIdx) * 32, dsc);
+    b2s_keypoint kp;
+    kp.x = (l != 0) ? __fmul_rn((float)cx, L.scale) : (float)cx;  // keypoint->pt *= scale (:1651-1660)
+    kp.y = (l != 0) ? __fmul_rn((float)cy, L.scale) : (float)cy;
+    kp.size = L.kpsize;
+    kp.angle = angle;
+    kp.response = (float)resp;
+    kp.octave = l;
+    kp.class_id = -1;
+    outKps[(size_t)b * cap + outIdx] = kp;
+  }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+static inline int cv_roundf(float v) { return (int)lrintf(v); }
+static inline int cv_floor(double v) {
+  int i = (int)v;
+  return i - (i > v);
+}
+
+static std::once_flag g_const_once[64];
+static int upload_constants(int device) {
+  int rc = B2S_OK;
+  std::call_once(g_const_once[device & 63], [&]() {
+    // umax (src/ORBextractor.cc:579-608)
+    int umax[16];
+    int v, v0, vmax = cv_floor(kHalfPatch * sqrt(2.f) / 2 + 1);
+    int vminc = (int)ceil(kHalfPatch * sqrt(2.f) / 2);
+    const double hp2 = kHalfPatch * kHalfPatch;
+    for (v = 0; v < 16; v++) umax[v] = 0;
+    for (v = 0; v <= vmax; ++v) umax[v] = (int)lrint(sqrt(hp2 - v * v));
+    for (v = kHalfPatch, v0 = 0; v >= vminc; --v) {
+      while (umax[v0] == umax[v0 + 1]) ++v0;
+      umax[v] = v0;
+      ++v0;
+    }
+    if (cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)) != cudaSuccess) rc = B2S_ERR_CUDA;
+    if (cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)) != cudaSuccess) rc = B2S_ERR_CUDA;
+  });
+  return rc;
+}
+
+static size_t quadtree_smem_bytes(int cap) {
+  return (size_t)cap * (8 + 16 + 16 + 4 * 5 + 2 * 4 + 2 * 8 + 2) + 64;
+}
+
+// Builds per-level geometry for a WxH image and (re)uploads the resize tables.
+static int build_geometry(b2s_extractor* h, int W, int H) {
+  ExtractGeom& g = h->geom;
+  memset(&g, 0, sizeof(g));
+  g.nlevels = h->nlevels;
+  g.iniTh = h->iniTh;
+  g.minTh = h->minTh;
+  uint32_t off = 0;
+  int cellStart = 0, candOff = 0, selOff = 0, tileStart = 0;
+  uint32_t rxOff = 0, ryOff = 0;
+  std::vector<int16_t> rxOfs, ryOfs;
+  std::vector<uint32_t> rxAlpha, ryBeta;
+  for (int l = 0; l < g.nlevels; l++) {
+    LevelGeom& L = g.lv[l];
+    const float s = h->invScale[l];
+    L.w = cv_roundf((float)W * s);  // :1680-1682
+    L.h = cv_roundf((float)H * s);
+    L.pitch = (int)align_up((size_t)L.w, 16);
+    L.off = off;
+    off += (uint32_t)align_up((size_t)L.pitch * L.h, 256);
+    L.maxBX = L.w - kEdge + 3;
+    L.maxBY = L.h - kEdge + 3;
+    const float width = (float)(L.maxBX - kMinBorder), height = (float)(L.maxBY - kMinBorder);
+    L.nCols = (int)(width / 30.f);
+    L.nRows = (int)(height / 30.f);
+    if (L.nCols <= 0 || L.nRows <= 0) {
+      set_error("pyramid level %d (%dx%d) is too small for the 30-px FAST cell grid", l, L.w, L.h);
+      return B2S_ERR_BAD_ARG;
+    }
+    L.wCell = (int)ceilf(width / L.nCols);
+    L.hCell = (int)ceilf(height / L.nRows);
+    if (L.wCell + 6 > FP - 4 || L.hCell + 6 > FR || L.wCell > 63 || L.hCell > 63) {
+      set_error("cell %dx%d at level %d exceeds the kernel tile", L.wCell, L.hCell, l);
+      return B2S_ERR_BAD_ARG;
+    }
+    L.cellStart = cellStart;
+    cellStart += L.nCols * L.nRows;
+    L.N = h->nFeat[l];
+    L.nIni = (int)roundf(width / height);  // :719 (C round)
+    if (L.nIni < 1) {
+      set_error("portrait level %dx%d: quadtree needs width >= height/2", L.w, L.h);
+      return B2S_ERR_BAD_ARG;
+    }
+    L.hX = width / L.nIni;
+    L.candCap = std::min(65535, std::max(1024, (L.w * L.h) / 10));
+    L.candOff = candOff;
+    candOff += (int)align_up((size_t)L.candCap, 64);
+    L.nodeCap = (int)align_up((size_t)std::max(L.N + 4, 4 * L.nIni), 8);
+    L.selOff = selOff;
+    selOff += L.nodeCap;
+    L.scale = h->scale[l];
+    L.kpsize = (float)(int)(kPatch * h->scale[l]);
+    L.blurTileStart = tileStart;
+    L.blurTilesX = div_up(L.w, BT_W);
+    L.blurTilesY = div_up(L.h, BT_H);
+    tileStart += L.blurTilesX * L.blurTilesY;
+    L.rxOff = rxOff;
+    L.ryOff = ryOff;
+    if (l > 0) {
+      const LevelGeom& S = g.lv[l - 1];
+      const double scale_x = 1. / ((double)L.w / S.w), scale_y = 1. / ((double)L.h / S.h);
+      for (int dx = 0; dx < L.w; dx++) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = cv_floor(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
+        rxOfs.push_back((int16_t)sx);
+        const int16_t a0 = (int16_t)cv_roundf((1.f - fx) * 2048.f), a1 = (int16_t)cv_roundf(fx * 2048.f);
+        rxAlpha.push_back((uint32_t)(uint16_t)a0 | ((uint32_t)(uint16_t)a1 << 16));
+      }
+      for (int dy = 0; dy < L.h; dy++) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = cv_floor(fy);
+        fy -= sy;
+        ryOfs.push_back((int16_t)sy);
+        const int16_t b0 = (int16_t)cv_roundf((1.f - fy) * 2048.f), b1 = (int16_t)cv_roundf(fy * 2048.f);
+        ryBeta.push_back((uint32_t)(uint16_t)b0 | ((uint32_t)(uint16_t)b1 << 16));
+      }
+      rxOff += L.w;
+      ryOff += L.h;
+    }
+  }
+  g.pyrBytes = off;
+  g.totalCells = cellStart;
+  g.totalCandCap = candOff;
+  g.totalSelCap = selOff;
+  g.totalBlurTiles = tileStart;
+  if (g.pyrBytes > h->pyrBytesAlloc || (size_t)g.totalCandCap > h->candCapAlloc || (size_t)g.totalSelCap > h->selCapAlloc ||
+      rxOfs.size() > h->rxAlloc || ryOfs.size() > h->ryAlloc) {
+    set_error("image %dx%d exceeds the extractor's max_width/max_height (%dx%d)", W, H, h->maxW, h->maxH);
+    return B2S_ERR_BAD_ARG;
+  }
+  if (!rxOfs.empty()) {
+    B2S_CUDA(cudaMemcpyAsync(h->d.rxOfs, rxOfs.data(), rxOfs.size() * 2, cudaMemcpyHostToDevice, h->stream));
+    B2S_CUDA(cudaMemcpyAsync(h->d.rxAlpha, rxAlpha.data(), rxAlpha.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    B2S_CUDA(cudaMemcpyAsync(h->d.ryOfs, ryOfs.data(), ryOfs.size() * 2, cudaMemcpyHostToDevice, h->stream));
+    B2S_CUDA(cudaMemcpyAsync(h->d.ryBeta, ryBeta.data(), ryBeta.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    B2S_CUDA(cudaStreamSynchronize(h->stream));  // the host vectors die here
+  }
+  {
+    int capMax = 0;
+    for (int l = 0; l < g.nlevels; l++) capMax = std::max(capMax, g.lv[l].nodeCap);
+    const size_t qsm = quadtree_smem_bytes(capMax);
+    if (qsm > 220 * 1024) {
+      set_error("quadtree node capacity %d needs %zu B of shared memory", capMax, qsm);
+      return B2S_ERR_BAD_ARG;
+    }
+    B2S_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(qsm, (size_t)49152)));
+  }
+  h->curW = W;
+  h->curH = H;
+  return B2S_OK;
+}
+
+// Enqueue the whole pipeline for `batch` images whose level-0 pixels are already in d.pyr.
+static int run_pipeline(b2s_extractor* h, int batch, b2s_keypoint* dKps, uint8_t* dDesc, int32_t* dCounts, int cap,
+                        cudaStream_t st) {
+  const ExtractGeom& g = h->geom;
+  DeviceBuffers& d = h->d;
+  B2S_CUDA(cudaMemsetAsync(d.candCount, 0, sizeof(int32_t) * kMaxLevels * batch, st));
+  for (int l = 1; l < g.nlevels; l++) {
+    dim3 grid(div_up(g.lv[l].w, 128), g.lv[l].h, batch);
+    k_resize<<<grid, 128, 0, st>>>(g, l, d.pyr, d.rxOfs, d.rxAlpha, d.ryOfs, d.ryBeta);
+    h->launches++;
+  }
+  k_fast_cells<<<dim3(g.totalCells, batch), 128, 0, st>>>(g, d.pyr, d.candXY, d.candKey, d.candResp, d.candCount, d.status);
+  h->launches++;
+  int capMax = 0;
+  for (int l = 0; l < g.nlevels; l++) capMax = std::max(capMax, g.lv[l].nodeCap);
+  const size_t qsm = quadtree_smem_bytes(capMax);
+  k_quadtree<<<dim3(g.nlevels, batch), 256, qsm, st>>>(g, capMax, d.candXY, d.candKey, d.candResp, d.candNode, d.candQ,
+                                                       d.candCount, d.selXYR, d.selCount, d.status);
+  h->launches++;
+  k_blur<<<dim3(g.totalBlurTiles, batch), 256, 0, st>>>(g, d.pyr, d.blur);
+  h->launches++;
+  k_orient_describe<<<dim3(div_up(g.totalSelCap, 8), batch), 256, 0, st>>>(g, d.pyr, d.blur, d.selXYR, d.selCount, dKps,
+                                                                           dDesc, dCounts, cap, d.status);
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" int b2s_extractor_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
+                                    int max_width, int max_height, int max_batch, int device, b2s_extractor** out) {
+  if (!out) return B2S_ERR_BAD_ARG;
+  *out = nullptr;
+  if (nfeatures <= 0 || nlevels < 1 || nlevels > kMaxLevels || !(scaleFactor > 1.0f) || minThFAST < 1 ||
+      iniThFAST < minThFAST || iniThFAST > 254 || max_width < 64 || max_height < 64 || max_width > 8192 ||
+      max_height > 8192 || max_batch < 1) {
+    set_error("b2s_extractor_create: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  int rc = select_device(device);
+  if (rc != B2S_OK) return rc;
+  rc = upload_constants(device);
+  if (rc != B2S_OK) {
+    set_error("constant upload failed");
+    return rc;
+  }
+  b2s_extractor* h = new b2s_extractor();
+  h->nfeatures = nfeatures;
+  h->nlevels = nlevels;
+  h->iniTh = iniThFAST;
+  h->minTh = minThFAST;
+  h->scaleFactor = scaleFactor;  // `double scaleFactor` member initialised from the float ctor argument
+  h->maxW = max_width;
+  h->maxH = max_height;
+  h->maxBatch = max_batch;
+  h->device = device;
+  // scale tables and per-level quotas — src/ORBextractor.cc:500-554
+  h->scale.resize(nlevels);
+  h->sigma2.resize(nlevels);
+  h->scale[0] = 1.0f;
+  h->sigma2[0] = 1.0f;
+  for (int i = 1; i < nlevels; i++) {
+    h->scale[i] = (float)(h->scale[i - 1] * h->scaleFactor);
+    h->sigma2[i] = h->scale[i] * h->scale[i];
+  }
+  h->invScale.resize(nlevels);
+  h->invSigma2.resize(nlevels);
+  for (int i = 0; i < nlevels; i++) {
+    h->invScale[i] = 1.0f / h->scale[i];
+    h->invSigma2[i] = 1.0f / h->sigma2[i];
+  }
+  h->nFeat.resize(nlevels);
+  {
+    float factor = (float)(1.0f / h->scaleFactor);
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+      h->nFeat[l] = cv_roundf(nDesired);
+      sum += h->nFeat[l];
+      nDesired *= factor;
+    }
+    h->nFeat[nlevels - 1] = std::max(nfeatures - sum, 0);
+  }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed");
+    delete h;
+    return B2S_ERR_CUDA;
+  }
+  // compute sizes without touching the device: replicate the size arithmetic
+  size_t pyrBytes = 0, candCap = 0, selCap = 0, rx = 0, ry = 0;
+  for (int l = 0; l < nlevels; l++) {
+    const int w = cv_roundf((float)max_width * h->invScale[l]), hh = cv_roundf((float)max_height * h->invScale[l]);
+    pyrBytes += align_up(align_up((size_t)w, 16) * hh, 256);
+    candCap += align_up((size_t)std::min(65535, std::max(1024, (w * hh) / 10)), 64);
+    selCap += align_up((size_t)std::max(h->nFeat[l] + 4, 64), 8);
+    if (l > 0) {
+      rx += w;
+      ry += hh;
+    }
+  }
+  // slack so that smaller images with different rounding still fit
+  pyrBytes += 4096;
+  candCap += 64 * nlevels;
+  selCap += 64 * nlevels;
+  h->pyrBytesAlloc = pyrBytes;
+  h->candCapAlloc = candCap;
+  h->selCapAlloc = selCap;
+  h->rxAlloc = rx + 16;
+  h->ryAlloc = ry + 16;
+  h->outCap = nfeatures + 4 * nlevels + 16;
+  DeviceBuffers& d = h->d;
+  const size_t B = (size_t)max_batch;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+  };
+  A((void**)&d.pyr, B * pyrBytes);
+  A((void**)&d.blur, B * pyrBytes);
+  A((void**)&d.candXY, B * candCap * 4);
+  A((void**)&d.candKey, B * candCap * 4);
+  A((void**)&d.candResp, B * candCap);
+  A((void**)&d.candNode, B * candCap * 2);
+  A((void**)&d.candQ, B * candCap);
+  A((void**)&d.candCount, B * kMaxLevels * 4);
+  A((void**)&d.selXYR, B * selCap * 8);
+  A((void**)&d.selCount, B * kMaxLevels * 4);
+  A((void**)&d.status, 4);
+  A((void**)&d.rxOfs, h->rxAlloc * 2);
+  A((void**)&d.rxAlpha, h->rxAlloc * 4);
+  A((void**)&d.ryOfs, h->ryAlloc * 2);
+  A((void**)&d.ryBeta, h->ryAlloc * 4);
+  A((void**)&d.outKps, B * h->outCap * sizeof(b2s_keypoint));
+  A((void**)&d.outDesc, B * h->outCap * 32);
+  A((void**)&d.outCounts, B * 4);
+  if (e == cudaSuccess) e = cudaMemset(d.status, 0, 4);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->hKps, B * h->outCap * sizeof(b2s_keypoint));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->hDesc, B * h->outCap * 32);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->hCounts, B * 4);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->hStatus, 4);
+  if (e == cudaSuccess) {
+    int capMax = 0;
+    for (int l = 0; l < nlevels; l++) capMax = std::max(capMax, (int)align_up((size_t)std::max(h->nFeat[l] + 4, 64), 8));
+    const size_t qsm = quadtree_smem_bytes(capMax);
+    if (qsm > 220 * 1024) {
+      set_error("nfeatures per level (%d) too large for the quadtree kernel's shared memory", capMax);
+      b2s_extractor_destroy(h);
+      return B2S_ERR_BAD_ARG;
+    }
+    e = cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(qsm, (size_t)49152));
+  }
+  if (e != cudaSuccess) {
+    set_error("b2s_extractor_create: %s", cudaGetErrorString(e));
+    b2s_extractor_destroy(h);
+    return B2S_ERR_CUDA;
+  }
+  *out = h;
+  return B2S_OK;
+}
+
+extern "C" void b2s_extractor_destroy(b2s_extractor* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  DeviceBuffers& d = h->d;
+  void* ptrs[] = {d.pyr, d.blur, d.candXY, d.candKey, d.candResp, d.candNode, d.candQ, d.candCount, d.selXYR,
+                  d.selCount, d.status, d.rxOfs, d.rxAlpha, d.ryOfs, d.ryBeta, d.outKps, d.outDesc, d.outCounts};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->hKps) cudaFreeHost(h->hKps);
+  if (h->hDesc) cudaFreeHost(h->hDesc);
+  if (h->hCounts) cudaFreeHost(h->hCounts);
+  if (h->hStatus) cudaFreeHost(h->hStatus);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int b2s_extractor_tables(const b2s_extractor* h, float* scale, float* inv_scale, float* sigma2,
+                                    float* inv_sigma2, int32_t* nfeatures_per_level) {
+  if (!h) return B2S_ERR_BAD_ARG;
+  for (int i = 0; i < h->nlevels; i++) {
+    if (scale) scale[i] = h->scale[i];
+    if (inv_scale) inv_scale[i] = h->invScale[i];
+    if (sigma2) sigma2[i] = h->sigma2[i];
+    if (inv_sigma2) inv_sigma2[i] = h->invSigma2[i];
+    if (nfeatures_per_level) nfeatures_per_level[i] = h->nFeat[i];
+  }
+  return B2S_OK;
+}
+
+extern "C" int b2s_extractor_max_keypoints(const b2s_extractor* h) { return h ? h->outCap : 0; }
+extern "C" long long b2s_extractor_launch_count(const b2s_extractor* h) { return h ? h->launches : 0; }
+
+static int ensure_geometry(b2s_extractor* h, int W, int H) {
+  if (h->curW == W && h->curH == H) return B2S_OK;
+  if (W > h->maxW || H > h->maxH) {
+    set_error("image %dx%d exceeds max %dx%d", W, H, h->maxW, h->maxH);
+    return B2S_ERR_BAD_ARG;
+  }
+  return build_geometry(h, W, H);
+}
+
+static int check_status(b2s_extractor* h) {
+  // d.status was copied to hStatus by the caller and the stream synchronised
+  const int s = *h->hStatus;
+  if (s) {
+    cudaMemsetAsync(h->d.status, 0, 4, h->stream);
+    set_error("extractor capacity exceeded (status bits %d: 1=candidates 2=output cap 4=quadtree nodes)", s);
+    return B2S_ERR_CAPACITY;
+  }
+  return B2S_OK;
+}
+
+extern "C" int b2s_extract_batch(b2s_extractor* h, const uint8_t* const* imgs, int batch, int width, int height, int stride,
+                                 b2s_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
+  if (!h || !n_out || batch < 1 || batch > h->maxBatch) {
+    set_error("b2s_extract_batch: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  if (!imgs || width <= 0 || height <= 0) {  // empty image -> silent return (src/ORBextractor.cc:1553)
+    for (int b = 0; b < batch; b++) n_out[b] = 0;
+    return B2S_OK;
+  }
+  if (!kps || !desc || stride < width) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  int rc = ensure_geometry(h, width, height);
+  if (rc != B2S_OK) return rc;
+  const ExtractGeom& g = h->geom;
+  for (int b = 0; b < batch; b++) {
+    if (!imgs[b]) return B2S_ERR_BAD_ARG;
+    B2S_CUDA(cudaMemcpy2DAsync(h->d.pyr + (size_t)b * g.pyrBytes + g.lv[0].off, g.lv[0].pitch, imgs[b], stride, width,
+                               height, cudaMemcpyHostToDevice, h->stream));
+  }
+  const int icap = h->outCap;
+  rc = run_pipeline(h, batch, h->d.outKps, h->d.outDesc, h->d.outCounts, icap, h->stream);
+  if (rc != B2S_OK) return rc;
+  B2S_CUDA(cudaMemcpyAsync(h->hKps, h->d.outKps, (size_t)batch * icap * sizeof(b2s_keypoint), cudaMemcpyDeviceToHost,
+                           h->stream));
+  B2S_CUDA(cudaMemcpyAsync(h->hDesc, h->d.outDesc, (size_t)batch * icap * 32, cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaMemcpyAsync(h->hCounts, h->d.outCounts, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaMemcpyAsync(h->hStatus, h->d.status, 4, cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaStreamSynchronize(h->stream));
+  rc = check_status(h);
+  if (rc != B2S_OK) return rc;
+  for (int b = 0; b < batch; b++) {
+    const int n = h->hCounts[b];
+    if (n > cap) {
+      set_error("b2s_extract: %d keypoints do not fit cap=%d", n, cap);
+      return B2S_ERR_CAPACITY;
+    }
+    n_out[b] = n;
+    memcpy(kps + (size_t)b * cap, h->hKps + (size_t)b * icap, (size_t)n * sizeof(b2s_keypoint));
+    memcpy(desc + (size_t)b * cap * 32, h->hDesc + (size_t)b * icap * 32, (size_t)n * 32);
+  }
+  return B2S_OK;
+}
+
+extern "C" int b2s_extract(b2s_extractor* h, const uint8_t* img, int width, int height, int stride, b2s_keypoint* kps,
+                           uint8_t* desc, int cap, int* n_out, uint8_t* const* pyr_out) {
+  if (!h || !n_out) return B2S_ERR_BAD_ARG;
+  if (!img || width <= 0 || height <= 0) {
+    *n_out = 0;
+    return B2S_OK;
+  }
+  const uint8_t* imgs[1] = {img};
+  int rc = b2s_extract_batch(h, imgs, 1, width, height, stride, kps, desc, cap, n_out);
+  if (rc != B2S_OK) return rc;
+  if (pyr_out) {  // mvImagePyramid for Frame::ComputeStereoMatches (src/Frame.cc:1044)
+    const ExtractGeom& g = h->geom;
+    for (int l = 0; l < g.nlevels; l++) {
+      if (!pyr_out[l]) continue;
+      B2S_CUDA(cudaMemcpy2DAsync(pyr_out[l], g.lv[l].w, h->d.pyr + g.lv[l].off, g.lv[l].pitch, g.lv[l].w, g.lv[l].h,
+                                 cudaMemcpyDeviceToHost, h->stream));
+    }
+    B2S_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return B2S_OK;
+}
+
+extern "C" int b2s_extract_batch_device(b2s_extractor* h, const uint8_t* d_imgs, size_t img_pitch_bytes, int batch,
+                                        int width, int height, int stride, b2s_keypoint* d_kps, uint8_t* d_desc,
+                                        int32_t* d_counts, int cap, void* stream) {
+  if (!h || !d_imgs || !d_kps || !d_desc || !d_counts || batch < 1 || batch > h->maxBatch || width <= 0 || height <= 0 ||
+      stride < width || cap < 1) {
+    set_error("b2s_extract_batch_device: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  B2S_CUDA(cudaSetDevice(h->device));
+  int rc = ensure_geometry(h, width, height);
+  if (rc != B2S_OK) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const ExtractGeom& g = h->geom;
+  // level 0 = copy of the input (src/ORBextractor.cc:1728); one strided 2D copy per image
+  for (int b = 0; b < batch; b++)
+    B2S_CUDA(cudaMemcpy2DAsync(h->d.pyr + (size_t)b * g.pyrBytes + g.lv[0].off, g.lv[0].pitch,
+                               d_imgs + (size_t)b * img_pitch_bytes, stride, width, height, cudaMemcpyDeviceToDevice, st));
+  return run_pipeline(h, batch, d_kps, d_desc, d_counts, cap, st);
+}
+
+extern "C" int b2s_extractor_check(b2s_extractor* h) {
+  if (!h) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  B2S_CUDA(cudaDeviceSynchronize());
+  B2S_CUDA(cudaMemcpy(h->hStatus, h->d.status, 4, cudaMemcpyDeviceToHost));
+  return check_status(h);
+}
+
+extern "C" int b2s_extractor_debug_level(b2s_extractor* h, int b, int level, int blurred, uint8_t* out, int* w, int* hgt) {
+  if (!h || level < 0 || level >= h->nlevels || b < 0 || b >= h->maxBatch || !h->curW) return B2S_ERR_BAD_ARG;
+  const LevelGeom& L = h->geom.lv[level];
+  if (w) *w = L.w;
+  if (hgt) *hgt = L.h;
+  if (out) {
+    B2S_CUDA(cudaSetDevice(h->device));
+    B2S_CUDA(cudaDeviceSynchronize());
+    const uint8_t* src = (blurred ? h->d.blur : h->d.pyr) + (size_t)b * h->geom.pyrBytes + L.off;
+    B2S_CUDA(cudaMemcpy2D(out, L.w, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+  }
+  return B2S_OK;
+}
+
+extern "C" int b2s_extractor_debug_candidates(b2s_extractor* h, int b, int level, int32_t* xy, int32_t* resp, int cap,
+                                              int* n) {
+  if (!h || level < 0 || level >= h->nlevels || b < 0 || b >= h->maxBatch || !h->curW || !n) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  B2S_CUDA(cudaDeviceSynchronize());
+  const LevelGeom& L = h->geom.lv[level];
+  int cnt = 0;
+  B2S_CUDA(cudaMemcpy(&cnt, h->d.candCount + b * kMaxLevels + level, 4, cudaMemcpyDeviceToHost));
+  cnt = std::min(cnt, L.candCap);
+  *n = cnt;
+  if (xy && resp && cnt > 0) {
+    std::vector<uint32_t> vxy(cnt), vkey(cnt);
+    std::vector<uint8_t> vr(cnt);
+    const size_t base = (size_t)b * h->geom.totalCandCap + L.candOff;
+    B2S_CUDA(cudaMemcpy(vxy.data(), h->d.candXY + base, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    B2S_CUDA(cudaMemcpy(vkey.data(), h->d.candKey + base, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    B2S_CUDA(cudaMemcpy(vr.data(), h->d.candResp + base, (size_t)cnt, cudaMemcpyDeviceToHost));
+    // return in reference insertion order (sort by order key)
+    std::vector<int> idx(cnt);
+    for (int i = 0; i < cnt; i++) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](int a, int c) { return vkey[a] < vkey[c]; });
+    for (int i = 0; i < cnt && i < cap; i++) {
+      xy[2 * i] = vxy[idx[i]] & 0xffff;
+      xy[2 * i + 1] = vxy[idx[i]] >> 16;
+      resp[i] = vr[idx[i]];
+    }
+  }
+  return B2S_OK;
+}
+
+// test hook: device sincosf mirror over n floats (host buffers)
+extern "C" int b2s_debug_sincosf(const float* in, int n, float* s, float* c) {
+  int rc = select_device(0);
+  if (rc != B2S_OK) return rc;
+  float *din, *ds, *dc;
+  B2S_CUDA(cudaMalloc(&din, (size_t)n * 4));
+  B2S_CUDA(cudaMalloc(&ds, (size_t)n * 4));
+  B2S_CUDA(cudaMalloc(&dc, (size_t)n * 4));
+  B2S_CUDA(cudaMemcpy(din, in, (size_t)n * 4, cudaMemcpyHostToDevice));
+  k_sincos_test<<<div_up(n, 256), 256>>>(din, n, ds, dc);
+  B2S_CUDA(cudaMemcpy(s, ds, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  B2S_CUDA(cudaMemcpy(c, dc, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(din);
+  cudaFree(ds);
+  cudaFree(dc);
+  return B2S_OK;
+}

@@ -1,0 +1,83 @@
+// extractor.cuh — geometry + handle of the B200 ORB extractor (see extractor.cu for the kernels).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace b2s {
+
+constexpr int kMaxLevels = 12;
+constexpr int kEdge = 19;       // EDGE_THRESHOLD, src/ORBextractor.cc:86
+constexpr int kMinBorder = 16;  // EDGE_THRESHOLD-3, :1064
+constexpr int kPatch = 31;      // PATCH_SIZE, :82
+constexpr int kHalfPatch = 15;  // HALF_PATCH_SIZE, :84
+
+// Per-level constants, passed to kernels by value inside ExtractGeom.
+struct LevelGeom {
+  int w, h, pitch;        // level image (no border), row pitch in bytes (multiple of 16)
+  uint32_t off;           // byte offset of the level inside one image's pyramid
+  int maxBX, maxBY;       // maxBorderX/Y = dim-16 (:1066-1070)
+  int nCols, nRows, wCell, hCell;  // cell grid (:1082-1086)
+  int cellStart;          // first FAST CTA index of this level
+  int N;                  // mnFeaturesPerLevel[level]
+  int nIni;               // quadtree roots (:719)
+  float hX;               // root width (:722)
+  int candCap, candOff;   // candidate capacity / offset (entries) inside one image's candidate arrays
+  int nodeCap, selOff;    // quadtree node capacity / offset of the level's selected keypoints
+  float scale;            // mvScaleFactor[level]
+  float kpsize;           // (float)(int)(PATCH_SIZE*scale) (:1175,1189)
+  int blurTileStart, blurTilesX, blurTilesY;
+  uint32_t rxOff, ryOff;  // resize tables (entries) for producing this level from level-1
+};
+
+struct ExtractGeom {
+  int nlevels;
+  int iniTh, minTh;
+  int totalCells, totalCandCap, totalSelCap, totalBlurTiles;
+  uint32_t pyrBytes;  // bytes of one image's pyramid
+  LevelGeom lv[kMaxLevels];
+};
+
+struct DeviceBuffers {
+  uint8_t* pyr = nullptr;      // B x pyrBytes
+  uint8_t* blur = nullptr;     // B x pyrBytes
+  uint32_t* candXY = nullptr;  // B x totalCandCap   (x | y<<16, border-relative)
+  uint32_t* candKey = nullptr; // B x totalCandCap   (order key: cell<<12 | ylocal<<6 | xlocal)
+  uint8_t* candResp = nullptr; // B x totalCandCap
+  uint16_t* candNode = nullptr;
+  uint8_t* candQ = nullptr;
+  int32_t* candCount = nullptr;  // B x kMaxLevels
+  uint32_t* selXYR = nullptr;    // B x totalSelCap x 2 (x|y<<16 level coords, response)
+  int32_t* selCount = nullptr;   // B x kMaxLevels
+  int32_t* status = nullptr;     // 1 int: bit0 cand overflow, bit1 output overflow, bit2 node overflow
+  int16_t* rxOfs = nullptr;      // resize tables
+  uint32_t* rxAlpha = nullptr;
+  int16_t* ryOfs = nullptr;
+  uint32_t* ryBeta = nullptr;
+  b2s_keypoint* outKps = nullptr;  // B x outCap (internal result records for the host-buffer entry points)
+  uint8_t* outDesc = nullptr;
+  int32_t* outCounts = nullptr;
+};
+
+}  // namespace b2s
+
+struct b2s_extractor {
+  int nfeatures, nlevels, iniTh, minTh;
+  double scaleFactor;
+  int maxW, maxH, maxBatch, device;
+  std::vector<float> scale, invScale, sigma2, invSigma2;
+  std::vector<int> nFeat;
+  int outCap;  // per-image record capacity of the internal output buffers
+  // geometry cache for the current image size
+  int curW = 0, curH = 0;
+  b2s::ExtractGeom geom;
+  b2s::DeviceBuffers d;
+  size_t pyrBytesAlloc = 0, candCapAlloc = 0, selCapAlloc = 0, rxAlloc = 0, ryAlloc = 0;
+  cudaStream_t stream = nullptr;
+  // pinned staging for the host-buffer entry points
+  b2s_keypoint* hKps = nullptr;
+  uint8_t* hDesc = nullptr;
+  int32_t* hCounts = nullptr;
+  int32_t* hStatus = nullptr;
+  long long launches = 0;
+};

@@ -1,0 +1,807 @@
+// matcher.cu — B200 (sm_100a) ORBmatcher: 256-bit Hamming as warp POPC reductions over 32-byte descriptors.
+//
+//   SearchByBoW            /root/reference/src/ORBmatcher.cc:230-382 (KF,F) and :656-799 (KF,KF)
+//   SearchByProjection     :1569-1728 (CurrentFrame, LastFrame) + Frame grid src/Frame.cc:461-491, 741-877
+//   DescriptorDistance     :1913-1933
+//
+// The reference matchers are greedy and order dependent (a frame feature matched by an earlier keyframe feature is
+// skipped by later ones, :288).  Distances are the parallel part: one warp per query row scans its candidates in the
+// reference's iteration order and keeps the K best by (distance, order) — removing already-matched candidates from
+// such a sorted list preserves both the first-minimum tie rule and the second-best value, so the order-dependent
+// part becomes a cheap resolver walking K-entry lists (with an exact full rescan when a list runs dry).
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b2s {
+
+constexpr int TOPK = 8;
+constexpr int HISTO = 30;             // HISTO_LENGTH, src/ORBmatcher.cc:51
+constexpr int GRID_COLS = 64, GRID_ROWS = 48;  // include/Frame.h:55,60
+constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+
+struct MatchParams {
+  int thLow;       // TH_LOW / TH_HIGH depending on the matcher
+  float nnratio;
+  int strictLt;
+  int checkOri;
+};
+
+__device__ __forceinline__ u256 ld_desc(const uint8_t* base, int i) { return ld_u256(base + (size_t)i * 32); }
+// 4-byte aligned descriptor (embedded in a query record)
+__device__ __forceinline__ u256 ld_desc_w(const uint8_t* p) {
+  u256 r;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+  for (int k = 0; k < 8; k++) r.w[k] = w[k];
+  return r;
+}
+
+// keep the K smallest keys of a stream (ascending, registers)
+__device__ __forceinline__ void topk_insert(uint32_t (&t)[TOPK], uint32_t key) {
+  if (key >= t[TOPK - 1]) return;
+  t[TOPK - 1] = key;
+#pragma unroll
+  for (int k = TOPK - 1; k > 0; k--) {
+    if (t[k] < t[k - 1]) {
+      const uint32_t tmp = t[k];
+      t[k] = t[k - 1];
+      t[k - 1] = tmp;
+    }
+  }
+}
+
+// merge the 32 per-lane sorted lists into the warp's global K smallest (result broadcast to all lanes)
+__device__ __forceinline__ void topk_warp_merge(uint32_t (&t)[TOPK], uint32_t (&out)[TOPK]) {
+  int head = 0;
+#pragma unroll
+  for (int k = 0; k < TOPK; k++) {
+    uint32_t mine = EMPTY;
+#pragma unroll
+    for (int q = 0; q < TOPK; q++)
+      if (q == head) mine = t[q];
+    uint32_t m = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    out[k] = m;
+    if (m != EMPTY && mine == m) head++;  // keys are unique (they embed the candidate order)
+  }
+}
+
+__device__ __forceinline__ int rot_bin(float angA, float angB) {
+  const float factor = HISTO / 360.0f;
+  float rot = __fsub_rn(angA, angB);
+  if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+  int bin = (int)roundf(__fmul_rn(rot, factor));  // C round(): half away from zero
+  if (bin == HISTO) bin = 0;
+  return bin;
+}
+
+// ------------------------------------------------------------------------------------------------
+// order[]: indices sorted by (key, index) — rank by counting (n <= a few thousand)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_rank_by_key(const int32_t* __restrict__ keyBase, const int32_t* __restrict__ nArr, int cap,
+                              int32_t* __restrict__ orderBase) {
+  const int pair = blockIdx.y;
+  const int n = nArr[pair];
+  const int32_t* key = keyBase + (size_t)pair * cap;
+  int32_t* order = orderBase + (size_t)pair * cap;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int ki = key[i];
+  int r = 0;
+  for (int k = 0; k < n; k++) {
+    const int kk = key[k];
+    r += (kk < ki) || (kk == ki && k < i);
+  }
+  order[r] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SearchByBoW, stage 1: per keyframe-side row, K best frame-side candidates of the same vocabulary node
+// key = dist<<16 | j   (j ascending == the reference's candidate iteration order inside a node)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bow_topk(const uint8_t* __restrict__ descA, const int32_t* __restrict__ nodeA,
+                                                  const uint8_t* __restrict__ validA, const int32_t* __restrict__ nAarr,
+                                                  int capA, const uint8_t* __restrict__ descB,
+                                                  const int32_t* __restrict__ nodeB, const uint8_t* __restrict__ validB,
+                                                  const int32_t* __restrict__ nBarr, int capB,
+                                                  uint32_t* __restrict__ topk, int32_t* __restrict__ candCnt) {
+  const int pair = blockIdx.y;
+  const int nA = nAarr[pair], nB = nBarr[pair];
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= nA) return;
+  const size_t oa = (size_t)pair * capA, ob = (size_t)pair * capB;
+  uint32_t t[TOPK];
+#pragma unroll
+  for (int k = 0; k < TOPK; k++) t[k] = EMPTY;
+  int cnt = 0;
+  if (!validA || validA[oa + i]) {
+    const u256 da = ld_desc(descA + oa * 32, i);
+    const int na = nodeA[oa + i];
+    for (int j = lane; j < nB; j += 32) {
+      if (nodeB[ob + j] != na) continue;
+      if (validB && !validB[ob + j]) continue;
+      const u256 db = ld_desc(descB + ob * 32, j);
+      const int d = hamming256(da, db);
+      cnt++;
+      topk_insert(t, ((uint32_t)d << 16) | (uint32_t)j);
+    }
+  }
+  uint32_t out[TOPK];
+  topk_warp_merge(t, out);
+  cnt = warp_reduce_sum(cnt);
+  if (lane < TOPK) {
+    uint32_t v = EMPTY;
+#pragma unroll
+    for (int k = 0; k < TOPK; k++)
+      if (k == lane) v = out[k];
+    topk[(oa + i) * TOPK + lane] = v;
+  }
+  if (lane == 0) candCnt[oa + i] = cnt;
+}
+
+// full rescan of row i against the still-unmatched candidates (exact fallback when the K-list runs dry)
+__device__ void bow_rescan(const u256& da, int na, const uint8_t* descB, const int32_t* nodeB, const uint8_t* validB,
+                           const int32_t* matchB, int nB, int lane, int& best1, int& idx1, int& best2) {
+  int b1 = 256, i1 = -1, b2 = 256;
+  for (int j = lane; j < nB; j += 32) {
+    if (nodeB[j] != na) continue;
+    if (validB && !validB[j]) continue;
+    if (matchB[j] >= 0) continue;
+    const int d = hamming256(da, ld_desc(descB, j));
+    if (d < b1) {
+      b2 = b1;
+      b1 = d;
+      i1 = j;
+    } else if (d < b2) {
+      b2 = d;
+    }
+  }
+  uint32_t key = (i1 >= 0) ? (((uint32_t)b1 << 16) | (uint32_t)i1) : EMPTY;
+  uint32_t m = key;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+  int second = (key == m && m != EMPTY) ? b2 : b1;  // the winner lane contributes its own second best
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) second = min(second, __shfl_xor_sync(0xffffffffu, second, o));
+  if (m == EMPTY) {
+    best1 = 256;
+    idx1 = -1;
+    best2 = 256;
+  } else {
+    best1 = (int)(m >> 16);
+    idx1 = (int)(m & 0xffff);
+    best2 = second;
+  }
+}
+
+// stage 2: one warp per vocabulary node (the warp at the first sorted position of a node owns it); keyframe-side
+// rows of the node are resolved in ascending index order (:268 loop), exactly as the reference's greedy loop.
+__global__ void __launch_bounds__(128) k_bow_resolve(const uint8_t* __restrict__ descA, const int32_t* __restrict__ nodeA,
+                                                     const uint8_t* __restrict__ validA, const float* __restrict__ angA,
+                                                     const int32_t* __restrict__ nAarr, int capA,
+                                                     const uint8_t* __restrict__ descB, const int32_t* __restrict__ nodeB,
+                                                     const uint8_t* __restrict__ validB, const float* __restrict__ angB,
+                                                     const int32_t* __restrict__ nBarr, int capB,
+                                                     const int32_t* __restrict__ orderA, const uint32_t* __restrict__ topk,
+                                                     const int32_t* __restrict__ candCnt, MatchParams mp,
+                                                     int32_t* __restrict__ matchB, int32_t* __restrict__ binB) {
+  const int pair = blockIdx.y;
+  const int nA = nAarr[pair], nB = nBarr[pair];
+  const int lane = threadIdx.x & 31;
+  int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= nA) return;
+  const size_t oa = (size_t)pair * capA, ob = (size_t)pair * capB;
+  const int32_t* order = orderA + oa;
+  const int32_t* nodeAp = nodeA + oa;
+  const int node = nodeAp[order[r]];
+  if (r > 0 && nodeAp[order[r - 1]] == node) return;  // not the head of a node segment
+  int32_t* mB = matchB + ob;
+  for (; r < nA; r++) {
+    const int i = order[r];
+    if (nodeAp[i] != node) break;
+    if (validA && !validA[oa + i]) continue;  // no MapPoint / bad (:272-277)
+    // walk the K-list: first two entries whose frame feature is still unmatched (:288)
+    const uint32_t e = (lane < TOPK) ? topk[(oa + i) * TOPK + lane] : EMPTY;
+    const bool avail = (e != EMPTY) && (mB[e & 0xffff] < 0);
+    const unsigned am = __ballot_sync(0xffffffffu, avail);
+    const int listed = __popc(__ballot_sync(0xffffffffu, e != EMPTY));
+    int best1 = 256, idx1 = -1, best2 = 256;
+    const int navail = __popc(am);
+    const bool complete = candCnt[oa + i] <= TOPK;  // the list holds every candidate of the row
+    if (navail >= 2 || (complete && navail >= 0)) {
+      if (navail >= 1) {
+        const int l1 = __ffs(am) - 1;
+        const uint32_t e1 = __shfl_sync(0xffffffffu, e, l1);
+        best1 = (int)(e1 >> 16);
+        idx1 = (int)(e1 & 0xffff);
+        if (navail >= 2) {
+          const int l2 = __ffs(am & (am - 1)) - 1;
+          best2 = (int)(__shfl_sync(0xffffffffu, e, l2) >> 16);
+        }
+      }
+    } else {
+      const u256 da = ld_desc(descA + oa * 32, i);
+      bow_rescan(da, node, descB + ob * 32, nodeB + ob, validB ? validB + ob : nullptr, mB, nB, lane, best1, idx1, best2);
+    }
+    (void)listed;
+    const bool pass = mp.strictLt ? (best1 < mp.thLow) : (best1 <= mp.thLow);
+    if (pass && (float)best1 < __fmul_rn(mp.nnratio, (float)best2)) {
+      if (lane == 0) {
+        mB[idx1] = i;
+        binB[ob + idx1] = mp.checkOri ? rot_bin(angA[oa + i], angB[ob + idx1]) : 0;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// rotation-histogram consistency (:356-379) + ComputeThreeMaxima (:1866-1908); one CTA per pair
+__global__ void __launch_bounds__(256) k_rot_cull(const int32_t* __restrict__ nBarr, int capB, int checkOri,
+                                                  int32_t* __restrict__ matchB, const int32_t* __restrict__ binB,
+                                                  const int32_t* __restrict__ extraCount,
+                                                  int32_t* __restrict__ nmatches) {
+  __shared__ int hist[HISTO];
+  __shared__ int keep[3];
+  __shared__ int total, culled;
+  const int pair = blockIdx.x;
+  const int nB = nBarr[pair];
+  int32_t* mB = matchB + (size_t)pair * capB;
+  const int32_t* bB = binB + (size_t)pair * capB;
+  if (threadIdx.x < HISTO) hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    total = 0;
+    culled = 0;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nB; j += blockDim.x)
+    if (mB[j] >= 0) {
+      atomicAdd(&total, 1);
+      if (checkOri) atomicAdd(&hist[bB[j]], 1);
+    }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+    for (int i = 0; i < HISTO; i++) {
+      const int s = hist[i];
+      if (s > max1) {
+        max3 = max2; max2 = max1; max1 = s;
+        ind3 = ind2; ind2 = ind1; ind1 = i;
+      } else if (s > max2) {
+        max3 = max2; max2 = s;
+        ind3 = ind2; ind2 = i;
+      } else if (s > max3) {
+        max3 = s;
+        ind3 = i;
+      }
+    }
+    if ((float)max2 < 0.1f * (float)max1) {
+      ind2 = -1;
+      ind3 = -1;
+    } else if ((float)max3 < 0.1f * (float)max1) {
+      ind3 = -1;
+    }
+    keep[0] = ind1;
+    keep[1] = ind2;
+    keep[2] = ind3;
+  }
+  __syncthreads();
+  if (checkOri) {
+    for (int j = threadIdx.x; j < nB; j += blockDim.x)
+      if (mB[j] >= 0) {
+        const int bn = bB[j];
+        if (bn != keep[0] && bn != keep[1] && bn != keep[2]) {
+          mB[j] = -1;
+          atomicAdd(&culled, 1);
+        }
+      }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) nmatches[pair] = total - culled + (extraCount ? extraCount[pair] : 0);
+}
+
+__global__ void k_fill_i32(int32_t* p, int v, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void k_desc_distance(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n,
+                                int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = hamming256(ld_desc(a, i), ld_desc(b, i));
+}
+
+// ------------------------------------------------------------------------------------------------
+// SearchByProjection(CurrentFrame, LastFrame): Frame grid + windowed candidates
+// ------------------------------------------------------------------------------------------------
+struct ProjGeom {
+  float minX, minY, maxX, maxY, invW, invH, bf, th;
+  int mode, thHigh, checkOri, nlevels;
+  float scale[16];
+};
+
+// PosInGrid (src/Frame.cc:863-877): cell = round(), features outside the grid get key = big (sorted last, ignored)
+__global__ void k_proj_cell_key(const float* __restrict__ kpx, const float* __restrict__ kpy, int nf, ProjGeom g,
+                                int32_t* __restrict__ cellKey) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nf) return;
+  const int px = (int)roundf(__fmul_rn(__fsub_rn(kpx[i], g.minX), g.invW));
+  const int py = (int)roundf(__fmul_rn(__fsub_rn(kpy[i], g.minY), g.invH));
+  cellKey[i] = (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) ? (GRID_COLS * GRID_ROWS) : (px * GRID_ROWS + py);
+}
+
+// cellStart[c] = first sorted position whose key >= c  (c in [0, 3072])
+__global__ void k_proj_cell_start(const int32_t* __restrict__ cellKey, const int32_t* __restrict__ order, int nf,
+                                  int32_t* __restrict__ cellStart) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > nf) return;
+  const int kPrev = (r == 0) ? -1 : cellKey[order[r - 1]];
+  const int kCur = (r == nf) ? (GRID_COLS * GRID_ROWS) : cellKey[order[r]];
+  for (int c = kPrev + 1; c <= kCur; c++) cellStart[c] = r;
+}
+
+struct __align__(8) ProjQuery {  // == b2s_proj_query
+  float u, v, invz, angle;
+  int32_t octave, has_obs;
+  uint8_t desc[32];
+};
+
+// stage 1: one warp per query; candidates are enumerated in GetFeaturesInArea order (src/Frame.cc:741-850:
+// ix outer, iy inner, insertion order inside a cell) and the K best by (distance, order) are kept.
+// key = dist<<20 | ord  (ord < 2^20 = running index in enumeration order); cand index stored alongside.
+__global__ void __launch_bounds__(256) k_proj_topk(const ProjQuery* __restrict__ q, int nq, const float* __restrict__ kpx,
+                                                   const float* __restrict__ kpy, const int32_t* __restrict__ octave,
+                                                   const float* __restrict__ uright, const uint8_t* __restrict__ occupied,
+                                                   const uint8_t* __restrict__ desc, const int32_t* __restrict__ order,
+                                                   const int32_t* __restrict__ cellStart, ProjGeom g,
+                                                   uint32_t* __restrict__ topk, int32_t* __restrict__ topkIdx,
+                                                   int32_t* __restrict__ candCnt) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= nq) return;
+  uint32_t t[TOPK];
+#pragma unroll
+  for (int k = 0; k < TOPK; k++) t[k] = EMPTY;
+  int cnt = 0;
+  const ProjQuery& Q = q[i];
+  const float u = Q.u, v = Q.v, invz = Q.invz;
+  bool ok = !(invz < 0) && !(u < g.minX || u > g.maxX) && !(v < g.minY || v > g.maxY);  // :1616-1626
+  int oct = Q.octave;
+  float r = 0.f;
+  int c0x = 0, c1x = -1, c0y = 0, c1y = -1, minL = 0, maxL = -1;
+  if (ok) {
+    r = __fmul_rn(g.th, g.scale[oct]);
+    if (g.mode == 1) { minL = oct; maxL = -1; }
+    else if (g.mode == 2) { minL = 0; maxL = oct; }
+    else { minL = oct - 1; maxL = oct + 1; }
+    c0x = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, g.minX), r), g.invW)));
+    c1x = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, g.minX), r), g.invW)));
+    c0y = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, g.minY), r), g.invH)));
+    c1y = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, g.minY), r), g.invH)));
+    if (c0x >= GRID_COLS || c1x < 0 || c0y >= GRID_ROWS || c1y < 0) ok = false;
+  }
+  if (ok) {
+    const bool checkLevels = (minL > 0) || (maxL >= 0);
+    const u256 dq = ld_desc_w(Q.desc);
+    const float ur = __fsub_rn(u, __fmul_rn(g.bf, invz));
+    // columns of cells ix; inside a column the cells iy=c0y..c1y are contiguous in the sorted array
+    int ord = 0;
+    for (int ix = c0x; ix <= c1x; ix++) {
+      const int beg = cellStart[ix * GRID_ROWS + c0y], end = cellStart[ix * GRID_ROWS + c1y + 1];
+      for (int p = beg + lane; p < end; p += 32) {
+        const int id = order[p];
+        bool take = true;
+        if (checkLevels) {
+          const int o = octave[id];
+          if (o < minL) take = false;
+          if (maxL >= 0 && o > maxL) take = false;
+        }
+        if (take) {
+          const float dx = __fsub_rn(kpx[id], u), dy = __fsub_rn(kpy[id], v);
+          if (!(fabsf(dx) < r && fabsf(dy) < r)) take = false;
+        }
+        if (take && occupied && occupied[id]) take = false;  // initially occupied features are never candidates
+        if (take) {
+          const float urr = uright[id];
+          if (urr > 0) {
+            const float er = fabsf(__fsub_rn(ur, urr));
+            if (er > r) take = false;
+          }
+        }
+        if (take) {
+          const int d = hamming256(dq, ld_desc(desc, id));
+          cnt++;
+          // order inside the enumeration: position p-beg within column ix, columns ascending
+          topk_insert(t, ((uint32_t)d << 20) | (uint32_t)(ord + (p - beg)));
+        }
+      }
+      ord += end - beg;
+    }
+  }
+  uint32_t out[TOPK];
+  topk_warp_merge(t, out);
+  cnt = warp_reduce_sum(cnt);
+  if (lane < TOPK) {
+    uint32_t e = EMPTY;
+#pragma unroll
+    for (int k = 0; k < TOPK; k++)
+      if (k == lane) e = out[k];
+    int id = -1;
+    if (e != EMPTY) {
+      // recover the feature index from the enumeration order
+      int ordv = (int)(e & 0xFFFFF);
+      for (int ix = c0x; ix <= c1x; ix++) {
+        const int beg = cellStart[ix * GRID_ROWS + c0y], end = cellStart[ix * GRID_ROWS + c1y + 1];
+        if (ordv < end - beg) {
+          id = order[beg + ordv];
+          break;
+        }
+        ordv -= end - beg;
+      }
+    }
+    topk[(size_t)i * TOPK + lane] = e;
+    topkIdx[(size_t)i * TOPK + lane] = id;
+  }
+  if (lane == 0) candCnt[i] = ok ? cnt : -1;
+}
+
+// stage 2: the greedy loop of :1600-1706 — one warp walks the queries in order; `taken[j]` = feature j now holds a
+// MapPoint with Observations()>0 (:1658-1660).  A query whose K-list ran dry is rescanned exactly.
+__global__ void __launch_bounds__(32) k_proj_resolve(const ProjQuery* __restrict__ q, int nq,
+                                                     const float* __restrict__ kpx, const float* __restrict__ kpy,
+                                                     const int32_t* __restrict__ octave, const float* __restrict__ angle,
+                                                     const float* __restrict__ uright,
+                                                     const uint8_t* __restrict__ occupied, const uint8_t* __restrict__ desc,
+                                                     const int32_t* __restrict__ order,
+                                                     const int32_t* __restrict__ cellStart, ProjGeom g,
+                                                     const uint32_t* __restrict__ topk, const int32_t* __restrict__ topkIdx,
+                                                     const int32_t* __restrict__ candCnt, uint8_t* __restrict__ taken,
+                                                     int32_t* __restrict__ matchCur, int32_t* __restrict__ pushList,
+                                                     int32_t* __restrict__ accepted, int32_t* __restrict__ histOut) {
+  const int lane = threadIdx.x;
+  __shared__ int hist[HISTO];
+  if (lane < HISTO) hist[lane] = 0;
+  __syncwarp();
+  int nAccepted = 0;
+  for (int i = 0; i < nq; i++) {
+    const int cc = candCnt[i];
+    if (cc <= 0) continue;
+    const uint32_t e = (lane < TOPK) ? topk[(size_t)i * TOPK + lane] : EMPTY;
+    const int id = (lane < TOPK) ? topkIdx[(size_t)i * TOPK + lane] : -1;
+    const bool avail = (e != EMPTY) && !taken[id];
+    const unsigned am = __ballot_sync(0xffffffffu, avail);
+    int bestDist = 256, bestIdx = -1;
+    if (am) {
+      const int l1 = __ffs(am) - 1;
+      bestDist = (int)(__shfl_sync(0xffffffffu, e, l1) >> 20);
+      bestIdx = __shfl_sync(0xffffffffu, id, l1);
+    } else if (cc > TOPK) {
+      // exact rescan in enumeration order
+      const ProjQuery& Q = q[i];
+      const float u = Q.u, v = Q.v, invz = Q.invz;
+      const int oct = Q.octave;
+      const float r = __fmul_rn(g.th, g.scale[oct]);
+      int minL, maxL;
+      if (g.mode == 1) { minL = oct; maxL = -1; }
+      else if (g.mode == 2) { minL = 0; maxL = oct; }
+      else { minL = oct - 1; maxL = oct + 1; }
+      const int c0x = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, g.minX), r), g.invW)));
+      const int c1x = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, g.minX), r), g.invW)));
+      const int c0y = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, g.minY), r), g.invH)));
+      const int c1y = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, g.minY), r), g.invH)));
+      const bool checkLevels = (minL > 0) || (maxL >= 0);
+      const u256 dq = ld_desc_w(Q.desc);
+      const float ur = __fsub_rn(u, __fmul_rn(g.bf, invz));
+      uint32_t bestKey = EMPTY;
+      int bestId = -1;
+      int ord = 0;
+      for (int ix = c0x; ix <= c1x; ix++) {
+        const int beg = cellStart[ix * GRID_ROWS + c0y], end = cellStart[ix * GRID_ROWS + c1y + 1];
+        for (int p = beg + lane; p < end; p += 32) {
+          const int fid = order[p];
+          bool take = true;
+          if (checkLevels) {
+            const int o = octave[fid];
+            if (o < minL) take = false;
+            if (maxL >= 0 && o > maxL) take = false;
+          }
+          if (take) {
+            const float dx = __fsub_rn(kpx[fid], u), dy = __fsub_rn(kpy[fid], v);
+            if (!(fabsf(dx) < r && fabsf(dy) < r)) take = false;
+          }
+          if (take && ((occupied && occupied[fid]) || taken[fid])) take = false;
+          if (take) {
+            const float urr = uright[fid];
+            if (urr > 0 && fabsf(__fsub_rn(ur, urr)) > r) take = false;
+          }
+          if (take) {
+            const uint32_t key = ((uint32_t)hamming256(dq, ld_desc(desc, fid)) << 20) | (uint32_t)(ord + (p - beg));
+            if (key < bestKey) {
+              bestKey = key;
+              bestId = fid;
+            }
+          }
+        }
+        ord += end - beg;
+      }
+      uint32_t m = bestKey;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (m != EMPTY) {
+        const unsigned who = __ballot_sync(0xffffffffu, bestKey == m);
+        bestDist = (int)(m >> 20);
+        bestIdx = __shfl_sync(0xffffffffu, bestId, __ffs(who) - 1);
+      }
+    }
+    if (bestDist <= g.thHigh) {  // :1683
+      if (lane == 0) {
+        matchCur[bestIdx] = i;
+        taken[bestIdx] = q[i].has_obs ? 1 : 0;
+        if (g.checkOri) {
+          const int bn = rot_bin(q[i].angle, angle[bestIdx]);
+          pushList[nAccepted] = (bn << 20) | bestIdx;  // rotHist[bin].push_back(bestIdx2) (:1700)
+          hist[bn]++;
+        }
+        nAccepted++;
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  if (lane == 0) accepted[0] = nAccepted;
+  if (lane < HISTO) histOut[lane] = hist[lane];
+}
+
+// rotation culling for SearchByProjection: the histogram holds every accepted push (a feature may have been pushed more
+// than once when a MapPoint without observations was overwritten, :1686); entries of non-kept bins are nulled and
+// nmatches decremented per entry (:1713-1724).
+__global__ void __launch_bounds__(256) k_proj_cull(int checkOri, const int32_t* __restrict__ hist,
+                                                   const int32_t* __restrict__ accepted, int32_t* __restrict__ matchCur,
+                                                   const int32_t* __restrict__ pushBins, int32_t* __restrict__ nmatches) {
+  __shared__ int keep[3];
+  __shared__ int culled;
+  if (threadIdx.x == 0) {
+    culled = 0;
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+    for (int i = 0; i < HISTO; i++) {
+      const int s = hist[i];
+      if (s > max1) {
+        max3 = max2; max2 = max1; max1 = s;
+        ind3 = ind2; ind2 = ind1; ind1 = i;
+      } else if (s > max2) {
+        max3 = max2; max2 = s;
+        ind3 = ind2; ind2 = i;
+      } else if (s > max3) {
+        max3 = s;
+        ind3 = i;
+      }
+    }
+    if ((float)max2 < 0.1f * (float)max1) {
+      ind2 = -1;
+      ind3 = -1;
+    } else if ((float)max3 < 0.1f * (float)max1) {
+      ind3 = -1;
+    }
+    keep[0] = ind1;
+    keep[1] = ind2;
+    keep[2] = ind3;
+  }
+  __syncthreads();
+  if (checkOri) {
+    // every push in a culled bin: null the feature, nmatches--
+    const int nPush = accepted[0];
+    for (int k = threadIdx.x; k < nPush; k += blockDim.x) {
+      const int packed = pushBins[k];
+      const int bn = packed >> 20, j = packed & 0xFFFFF;
+      if (bn != keep[0] && bn != keep[1] && bn != keep[2]) {
+        matchCur[j] = -1;
+        atomicAdd(&culled, 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) nmatches[0] = accepted[0] - culled;
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+struct b2s_matcher {
+  int maxF, maxBatch, device;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  // device work buffers
+  uint8_t *dDescA = nullptr, *dDescB = nullptr, *dValidA = nullptr, *dValidB = nullptr, *dOcc = nullptr, *dTaken = nullptr;
+  int32_t *dNodeA = nullptr, *dNodeB = nullptr, *dNA = nullptr, *dNB = nullptr, *dOrder = nullptr, *dCandCnt = nullptr;
+  int32_t *dMatch = nullptr, *dBin = nullptr, *dNMatches = nullptr, *dOct = nullptr, *dCellKey = nullptr;
+  int32_t *dCellStart = nullptr, *dTopkIdx = nullptr, *dExtra = nullptr, *dHist = nullptr, *dPush = nullptr;
+  float *dAngA = nullptr, *dAngB = nullptr, *dKpx = nullptr, *dKpy = nullptr, *dURight = nullptr;
+  uint32_t* dTopk = nullptr;
+  ProjQuery* dQueries = nullptr;
+};
+
+extern "C" int b2s_matcher_create(int max_features, int max_batch, int device, b2s_matcher** out) {
+  if (!out || max_features < 1 || max_features > 65535 || max_batch < 1) {
+    set_error("b2s_matcher_create: bad argument (max_features must be in [1,65535])");
+    return B2S_ERR_BAD_ARG;
+  }
+  *out = nullptr;
+  int rc = select_device(device);
+  if (rc != B2S_OK) return rc;
+  b2s_matcher* h = new b2s_matcher();
+  h->maxF = max_features;
+  h->maxBatch = max_batch;
+  h->device = device;
+  const size_t F = (size_t)max_features * max_batch;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  auto A = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+  };
+  A((void**)&h->dDescA, F * 32); A((void**)&h->dDescB, F * 32);
+  A((void**)&h->dValidA, F); A((void**)&h->dValidB, F); A((void**)&h->dOcc, F); A((void**)&h->dTaken, F);
+  A((void**)&h->dNodeA, F * 4); A((void**)&h->dNodeB, F * 4);
+  A((void**)&h->dNA, max_batch * 4); A((void**)&h->dNB, max_batch * 4);
+  A((void**)&h->dOrder, F * 4); A((void**)&h->dCandCnt, F * 4);
+  A((void**)&h->dMatch, F * 4); A((void**)&h->dBin, F * 4); A((void**)&h->dNMatches, max_batch * 4);
+  A((void**)&h->dOct, F * 4); A((void**)&h->dCellKey, F * 4);
+  A((void**)&h->dCellStart, (GRID_COLS * GRID_ROWS + 2) * 4);
+  A((void**)&h->dTopkIdx, F * TOPK * 4); A((void**)&h->dExtra, 4 * 4); A((void**)&h->dHist, HISTO * 4);
+  A((void**)&h->dPush, F * 4);
+  A((void**)&h->dAngA, F * 4); A((void**)&h->dAngB, F * 4);
+  A((void**)&h->dKpx, F * 4); A((void**)&h->dKpy, F * 4); A((void**)&h->dURight, F * 4);
+  A((void**)&h->dTopk, F * TOPK * 4);
+  A((void**)&h->dQueries, F * sizeof(ProjQuery));
+  if (e != cudaSuccess) {
+    set_error("b2s_matcher_create: %s", cudaGetErrorString(e));
+    b2s_matcher_destroy(h);
+    return B2S_ERR_CUDA;
+  }
+  *out = h;
+  return B2S_OK;
+}
+
+extern "C" void b2s_matcher_destroy(b2s_matcher* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  void* ptrs[] = {h->dDescA, h->dDescB, h->dValidA, h->dValidB, h->dOcc, h->dTaken, h->dNodeA, h->dNodeB, h->dNA, h->dNB,
+                  h->dOrder, h->dCandCnt, h->dMatch, h->dBin, h->dNMatches, h->dOct, h->dCellKey, h->dCellStart,
+                  h->dTopkIdx, h->dExtra, h->dHist, h->dPush, h->dAngA, h->dAngB, h->dKpx, h->dKpy, h->dURight, h->dTopk,
+                  h->dQueries};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" long long b2s_matcher_launch_count(const b2s_matcher* h) { return h ? h->launches : 0; }
+
+extern "C" int b2s_descriptor_distance(b2s_matcher* h, const uint8_t* a, const uint8_t* b, int n, int32_t* dist) {
+  if (!h || !a || !b || !dist || n < 0 || n > h->maxF * h->maxBatch) return B2S_ERR_BAD_ARG;
+  if (n == 0) return B2S_OK;
+  B2S_CUDA(cudaSetDevice(h->device));
+  B2S_CUDA(cudaMemcpyAsync(h->dDescA, a, (size_t)n * 32, cudaMemcpyHostToDevice, h->stream));
+  B2S_CUDA(cudaMemcpyAsync(h->dDescB, b, (size_t)n * 32, cudaMemcpyHostToDevice, h->stream));
+  k_desc_distance<<<div_up(n, 256), 256, 0, h->stream>>>(h->dDescA, h->dDescB, n, h->dMatch);
+  h->launches++;
+  B2S_CUDA(cudaMemcpyAsync(dist, h->dMatch, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaStreamSynchronize(h->stream));
+  return B2S_OK;
+}
+
+// device-resident, batched core (asynchronous)
+extern "C" int b2s_search_by_bow_device(b2s_matcher* h, int batch, const uint8_t* d_descA, const int32_t* d_nodeA,
+                                        const uint8_t* d_validA, const float* d_angA, const int32_t* d_nA, int capA,
+                                        const uint8_t* d_descB, const int32_t* d_nodeB, const uint8_t* d_validB,
+                                        const float* d_angB, const int32_t* d_nB, int capB, int th_low, float nnratio,
+                                        int strict_lt, int check_ori, int32_t* d_matchB, int32_t* d_nmatches,
+                                        void* stream) {
+  if (!h || batch < 1 || batch > h->maxBatch || capA < 1 || capB < 1 || capA > h->maxF || capB > h->maxF || !d_descA ||
+      !d_nodeA || !d_angA || !d_nA || !d_descB || !d_nodeB || !d_angB || !d_nB || !d_matchB || !d_nmatches) {
+    set_error("b2s_search_by_bow_device: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  MatchParams mp{th_low, nnratio, strict_lt, check_ori};
+  k_fill_i32<<<div_up(batch * capB, 256), 256, 0, st>>>(d_matchB, -1, (size_t)batch * capB);
+  k_rank_by_key<<<dim3(div_up(capA, 128), batch), 128, 0, st>>>(d_nodeA, d_nA, capA, h->dOrder);
+  k_bow_topk<<<dim3(div_up(capA, 8), batch), 256, 0, st>>>(d_descA, d_nodeA, d_validA, d_nA, capA, d_descB, d_nodeB,
+                                                           d_validB, d_nB, capB, h->dTopk, h->dCandCnt);
+  k_bow_resolve<<<dim3(div_up(capA, 4), batch), 128, 0, st>>>(d_descA, d_nodeA, d_validA, d_angA, d_nA, capA, d_descB,
+                                                              d_nodeB, d_validB, d_angB, d_nB, capB, h->dOrder, h->dTopk,
+                                                              h->dCandCnt, mp, d_matchB, h->dBin);
+  k_rot_cull<<<batch, 256, 0, st>>>(d_nB, capB, check_ori, d_matchB, h->dBin, nullptr, d_nmatches);
+  h->launches += 5;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+extern "C" int b2s_search_by_bow(b2s_matcher* h, const uint8_t* descA, const int32_t* nodeA, const uint8_t* validA,
+                                 const float* angA, int nA, const uint8_t* descB, const int32_t* nodeB,
+                                 const uint8_t* validB, const float* angB, int nB, int th_low, float nnratio,
+                                 int strict_lt, int check_ori, int32_t* matchB, int* nmatches) {
+  if (!h || nA < 0 || nB < 0 || nA > h->maxF || nB > h->maxF || !matchB || !nmatches) {
+    set_error("b2s_search_by_bow: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  *nmatches = 0;
+  for (int j = 0; j < nB; j++) matchB[j] = -1;
+  if (nA == 0 || nB == 0) return B2S_OK;
+  if (!descA || !nodeA || !angA || !descB || !nodeB || !angB) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  B2S_CUDA(cudaMemcpyAsync(h->dDescA, descA, (size_t)nA * 32, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNodeA, nodeA, (size_t)nA * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dAngA, angA, (size_t)nA * 4, cudaMemcpyHostToDevice, st));
+  if (validA) B2S_CUDA(cudaMemcpyAsync(h->dValidA, validA, (size_t)nA, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dDescB, descB, (size_t)nB * 32, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNodeB, nodeB, (size_t)nB * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dAngB, angB, (size_t)nB * 4, cudaMemcpyHostToDevice, st));
+  if (validB) B2S_CUDA(cudaMemcpyAsync(h->dValidB, validB, (size_t)nB, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNA, &nA, 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNB, &nB, 4, cudaMemcpyHostToDevice, st));
+  int rc = b2s_search_by_bow_device(h, 1, h->dDescA, h->dNodeA, validA ? h->dValidA : nullptr, h->dAngA, h->dNA, nA,
+                                    h->dDescB, h->dNodeB, validB ? h->dValidB : nullptr, h->dAngB, h->dNB, nB, th_low,
+                                    nnratio, strict_lt, check_ori, h->dMatch, h->dNMatches, st);
+  if (rc != B2S_OK) return rc;
+  B2S_CUDA(cudaMemcpyAsync(matchB, h->dMatch, (size_t)nB * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  return B2S_OK;
+}
+
+extern "C" int b2s_search_by_projection_last(b2s_matcher* h, const b2s_proj_query* q, int nq, const float* kpx,
+                                             const float* kpy, const int32_t* octave, const float* angle,
+                                             const float* uright, const uint8_t* occupied, const uint8_t* desc, int nf,
+                                             const b2s_frame_geom* g, float th, int mode, int th_high, int check_ori,
+                                             int32_t* match_cur, int* nmatches) {
+  static_assert(sizeof(ProjQuery) == sizeof(b2s_proj_query), "query layout");
+  if (!h || nq < 0 || nf < 0 || nq > h->maxF || nf > h->maxF || !match_cur || !nmatches || !g || !g->scale_factors ||
+      g->nlevels < 1 || g->nlevels > 16) {
+    set_error("b2s_search_by_projection_last: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  *nmatches = 0;
+  for (int j = 0; j < nf; j++) match_cur[j] = -1;
+  if (nq == 0 || nf == 0) return B2S_OK;
+  if (!q || !kpx || !kpy || !octave || !angle || !uright || !desc) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  ProjGeom pg;
+  pg.minX = g->mnMinX; pg.minY = g->mnMinY; pg.maxX = g->mnMaxX; pg.maxY = g->mnMaxY;
+  pg.invW = (float)GRID_COLS / (g->mnMaxX - g->mnMinX);  // src/Frame.cc:213-214
+  pg.invH = (float)GRID_ROWS / (g->mnMaxY - g->mnMinY);
+  pg.bf = g->bf; pg.th = th; pg.mode = mode; pg.thHigh = th_high; pg.checkOri = check_ori; pg.nlevels = g->nlevels;
+  for (int i = 0; i < 16; i++) pg.scale[i] = i < g->nlevels ? g->scale_factors[i] : 0.f;
+  B2S_CUDA(cudaMemcpyAsync(h->dQueries, q, (size_t)nq * sizeof(ProjQuery), cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dKpx, kpx, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dKpy, kpy, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dOct, octave, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dAngB, angle, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dURight, uright, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  if (occupied) B2S_CUDA(cudaMemcpyAsync(h->dOcc, occupied, (size_t)nf, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dDescB, desc, (size_t)nf * 32, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNB, &nf, 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemsetAsync(h->dTaken, 0, (size_t)nf, st));
+  k_fill_i32<<<div_up(nf, 256), 256, 0, st>>>(h->dMatch, -1, (size_t)nf);
+  k_proj_cell_key<<<div_up(nf, 256), 256, 0, st>>>(h->dKpx, h->dKpy, nf, pg, h->dCellKey);
+  k_rank_by_key<<<dim3(div_up(nf, 128), 1), 128, 0, st>>>(h->dCellKey, h->dNB, nf, h->dOrder);
+  k_proj_cell_start<<<div_up(nf + 1, 256), 256, 0, st>>>(h->dCellKey, h->dOrder, nf, h->dCellStart);
+  k_proj_topk<<<div_up(nq, 8), 256, 0, st>>>(h->dQueries, nq, h->dKpx, h->dKpy, h->dOct, h->dURight,
+                                             occupied ? h->dOcc : nullptr, h->dDescB, h->dOrder, h->dCellStart, pg,
+                                             h->dTopk, h->dTopkIdx, h->dCandCnt);
+  k_proj_resolve<<<1, 32, 0, st>>>(h->dQueries, nq, h->dKpx, h->dKpy, h->dOct, h->dAngB, h->dURight,
+                                   occupied ? h->dOcc : nullptr, h->dDescB, h->dOrder, h->dCellStart, pg, h->dTopk,
+                                   h->dTopkIdx, h->dCandCnt, h->dTaken, h->dMatch, h->dPush, h->dExtra, h->dHist);
+  k_proj_cull<<<1, 256, 0, st>>>(check_ori, h->dHist, h->dExtra, h->dMatch, h->dPush, h->dNMatches);
+  h->launches += 7;
+  B2S_CUDA(cudaGetLastError());
+  B2S_CUDA(cudaMemcpyAsync(match_cur, h->dMatch, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  return B2S_OK;
+}

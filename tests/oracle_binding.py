@@ -1,0 +1,221 @@
+"""ctypes binding of oracle/liborb_oracle.so — the CPU checker (test infrastructure only)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "liborb_oracle.so")
+vp = ctypes.c_void_p
+
+kp_dtype = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+proj_query_dtype = np.dtype([("u", "<f4"), ("v", "<f4"), ("invz", "<f4"), ("angle", "<f4"), ("octave", "<i4"),
+                             ("has_obs", "<i4"), ("desc", "u1", 32)])
+ba_edge_dtype = np.dtype([("kf", "<i4"), ("mp", "<i4"), ("obs", "<f4", 3), ("inv_sigma2", "<f4")])
+
+
+class FrameGeom(ctypes.Structure):
+    _fields_ = [("mnMinX", ctypes.c_float), ("mnMinY", ctypes.c_float), ("mnMaxX", ctypes.c_float),
+                ("mnMaxY", ctypes.c_float), ("bf", ctypes.c_float), ("scale_factors", vp), ("nlevels", ctypes.c_int)]
+
+
+class BaProblem(ctypes.Structure):
+    _fields_ = [("n_kf", ctypes.c_int), ("n_local", ctypes.c_int), ("Tcw", vp), ("fixed", vp), ("n_mp", ctypes.c_int),
+                ("points", vp), ("n_edges", ctypes.c_int), ("edges", vp), ("fx", ctypes.c_float), ("fy", ctypes.c_float),
+                ("cx", ctypes.c_float), ("cy", ctypes.c_float), ("bf", ctypes.c_float), ("its1", ctypes.c_int),
+                ("its2", ctypes.c_int)]
+
+
+class BaResult(ctypes.Structure):
+    _fields_ = [("Tcw_out", vp), ("points_out", vp), ("edge_outlier", vp), ("trace", vp), ("chi2_final", ctypes.c_double),
+                ("n_trials", ctypes.c_int)]
+
+
+def P(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+class Oracle:
+    def __init__(self, L):
+        self.L = L
+        L.orc_extractor_create.restype = vp
+        L.orc_extractor_create.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.orc_extractor_destroy.argtypes = [vp]
+        L.orc_extract.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]
+        L.orc_extractor_tables.argtypes = [vp] * 7
+        L.orc_level_dims.argtypes = [vp, ctypes.c_int, vp, vp]
+        L.orc_level_image.restype = ctypes.POINTER(ctypes.c_uint8)
+        L.orc_level_image.argtypes = [vp, ctypes.c_int]
+        L.orc_level_blurred.restype = ctypes.POINTER(ctypes.c_uint8)
+        L.orc_level_blurred.argtypes = [vp, ctypes.c_int]
+        L.orc_level_candidates.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int]
+        L.orc_level_keypoints.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int]
+        L.orc_resize_linear_u8.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int]
+        L.orc_gaussian_blur7_s2_u8.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int]
+        L.orc_fast9_16_nms.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]
+        L.orc_fast_atan2.restype = ctypes.c_float
+        L.orc_fast_atan2.argtypes = [ctypes.c_float, ctypes.c_float]
+        L.orc_distribute_octtree.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, vp, ctypes.c_int]
+        L.orc_descriptor_distance.argtypes = [vp, vp]
+        L.orc_search_by_bow.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_float, ctypes.c_int, ctypes.c_int, vp]
+        L.orc_search_by_projection_last.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp,
+                                                    ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+        L.orc_local_ba.argtypes = [vp, vp, vp]
+        L.orc_sincosf_batch.argtypes = [vp, ctypes.c_long, vp, vp, ctypes.c_int]
+        L.orc_extract_many.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, vp, ctypes.c_int]
+
+    # ---- extractor ----
+    def extractor(self, nfeatures, scaleFactor, nlevels, iniTh, minTh):
+        return OracleExtractor(self, nfeatures, scaleFactor, nlevels, iniTh, minTh)
+
+    def extract_many(self, params, imgs, threads):
+        nf, sf, nl, ini, mn = params
+        count, h, w = imgs.shape
+        cap = nf + 4 * nl + 16
+        kps = np.zeros((count, cap), kp_dtype)
+        desc = np.zeros((count, cap, 32), np.uint8)
+        n = np.zeros(count, np.int32)
+        rc = self.L.orc_extract_many(nf, sf, nl, ini, mn, P(imgs), count, w, h, P(kps), P(desc), cap, P(n), threads)
+        assert rc == 0
+        return kps, desc, n
+
+    def resize(self, src, dw, dh):
+        src = np.ascontiguousarray(src)
+        dst = np.zeros((dh, dw), np.uint8)
+        self.L.orc_resize_linear_u8(P(src), src.shape[1], src.shape[0], src.shape[1], P(dst), dw, dh, dw)
+        return dst
+
+    def blur(self, src):
+        src = np.ascontiguousarray(src)
+        dst = np.zeros_like(src)
+        self.L.orc_gaussian_blur7_s2_u8(P(src), src.shape[1], src.shape[0], src.shape[1], P(dst), src.shape[1])
+        return dst
+
+    def fast(self, img, th):
+        img = np.ascontiguousarray(img)
+        h, w = img.shape
+        cap = w * h
+        xy = np.zeros((cap, 2), np.int32)
+        rs = np.zeros(cap, np.int32)
+        n = self.L.orc_fast9_16_nms(P(img), w, h, w, th, P(xy), P(rs), cap)
+        return xy[:n].copy(), rs[:n].copy()
+
+    def fast_atan2(self, y, x):
+        return self.L.orc_fast_atan2(float(y), float(x))
+
+    def distribute_octtree(self, kps, minX, maxX, minY, maxY, N):
+        out = np.zeros(N + 16 + 64, kp_dtype)
+        n = self.L.orc_distribute_octtree(P(kps), len(kps), minX, maxX, minY, maxY, N, P(out), len(out))
+        assert n >= 0
+        return out[:n].copy()
+
+    # ---- matcher ----
+    def descriptor_distance(self, a, b):
+        return self.L.orc_descriptor_distance(P(np.ascontiguousarray(a)), P(np.ascontiguousarray(b)))
+
+    def search_by_bow(self, descA, nodeA, validA, angA, descB, nodeB, angB, validB=None, th_low=50, nnratio=0.7,
+                      strict_lt=False, check_ori=True):
+        m = np.full(len(descB), -1, np.int32)
+        n = self.L.orc_search_by_bow(P(descA), P(nodeA), P(validA), P(angA), len(descA), P(descB), P(nodeB), P(validB),
+                                     P(angB), len(descB), th_low, nnratio, int(strict_lt), int(check_ori), P(m))
+        return n, m
+
+    def search_by_projection_last(self, queries, kpx, kpy, octave, angle, uright, occupied, desc, geom, th, mode=0,
+                                  th_high=100, check_ori=True):
+        sf = np.ascontiguousarray(geom["scale_factors"], np.float32)
+        g = FrameGeom(geom["mnMinX"], geom["mnMinY"], geom["mnMaxX"], geom["mnMaxY"], geom["bf"], sf.ctypes.data, len(sf))
+        m = np.full(len(kpx), -1, np.int32)
+        n = self.L.orc_search_by_projection_last(P(queries), len(queries), P(kpx), P(kpy), P(octave), P(angle), P(uright),
+                                                 P(occupied), P(desc), len(kpx), ctypes.byref(g), th, mode, th_high,
+                                                 int(check_ori), P(m))
+        return n, m
+
+    # ---- LocalBA ----
+    def local_ba(self, d, stop=None, its1=5, its2=10):
+        Tcw = np.ascontiguousarray(d["Tcw"], np.float32)
+        fixed = np.ascontiguousarray(d["fixed"], np.uint8)
+        pts = np.ascontiguousarray(d["points"], np.float32)
+        edges = np.ascontiguousarray(d["edges"])
+        p = BaProblem(d["n_kf"], d["n_local"], Tcw.ctypes.data, fixed.ctypes.data, len(pts), pts.ctypes.data, len(edges),
+                      edges.ctypes.data, d["fx"], d["fy"], d["cx"], d["cy"], d["bf"], its1, its2)
+        out = dict(Tcw=np.zeros((d["n_local"], 16), np.float32), points=np.zeros((len(pts), 3), np.float32),
+                   outlier=np.zeros(len(edges), np.uint8), trace=np.full(256, -1, np.int32))
+        r = BaResult(out["Tcw"].ctypes.data, out["points"].ctypes.data, out["outlier"].ctypes.data,
+                     out["trace"].ctypes.data, 0.0, 0)
+        rc = self.L.orc_local_ba(ctypes.byref(p), P(stop), ctypes.byref(r))
+        if rc == 1:
+            return None
+        out["chi2"] = r.chi2_final
+        out["n_trials"] = r.n_trials
+        return out
+
+    def sincosf(self, x, threads=8):
+        x = np.ascontiguousarray(x, np.float32)
+        s = np.zeros_like(x)
+        c = np.zeros_like(x)
+        self.L.orc_sincosf_batch(P(x), len(x), P(s), P(c), threads)
+        return s, c
+
+
+class OracleExtractor:
+    def __init__(self, o, nfeatures, scaleFactor, nlevels, iniTh, minTh):
+        self.o = o
+        self.L = o.L
+        self.nlevels = nlevels
+        self.cap = nfeatures + 4 * nlevels + 16
+        self.h = vp(self.L.orc_extractor_create(nfeatures, scaleFactor, nlevels, iniTh, minTh))
+
+    def __del__(self):
+        try:
+            self.L.orc_extractor_destroy(self.h)
+        except Exception:
+            pass
+
+    def tables(self):
+        t = [np.zeros(self.nlevels, np.float32) for _ in range(4)]
+        nf = np.zeros(self.nlevels, np.int32)
+        um = np.zeros(16, np.int32)
+        self.L.orc_extractor_tables(self.h, P(t[0]), P(t[1]), P(t[2]), P(t[3]), P(nf), P(um))
+        return t, nf, um
+
+    def __call__(self, img):
+        img = np.ascontiguousarray(img)
+        h, w = img.shape
+        kps = np.zeros(self.cap, kp_dtype)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        n = self.L.orc_extract(self.h, P(img), w, h, w, P(kps), P(desc), self.cap)
+        assert n >= 0
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, l, blurred=False):
+        w, h = ctypes.c_int(0), ctypes.c_int(0)
+        self.L.orc_level_dims(self.h, l, ctypes.byref(w), ctypes.byref(h))
+        ptr = self.L.orc_level_blurred(self.h, l) if blurred else self.L.orc_level_image(self.h, l)
+        if not ptr:
+            return None
+        return np.ctypeslib.as_array(ptr, shape=(h.value, w.value)).copy()
+
+    def candidates(self, l):
+        n = self.L.orc_level_candidates(self.h, l, None, 0)
+        out = np.zeros(max(n, 1), kp_dtype)
+        self.L.orc_level_candidates(self.h, l, P(out), n)
+        return out[:n]
+
+    def keypoints(self, l):
+        n = self.L.orc_level_keypoints(self.h, l, None, 0)
+        out = np.zeros(max(n, 1), kp_dtype)
+        self.L.orc_level_keypoints(self.h, l, P(out), n)
+        return out[:n]
+
+
+def load():
+    if not os.path.exists(ORACLE_LIB):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "liborb_oracle.so"])
+    return Oracle(ctypes.CDLL(ORACLE_LIB))

@@ -1,0 +1,91 @@
+"""GPU parity of the extractor against the CPU oracle, stage by stage and end to end (bit-exact)."""
+import numpy as np
+import pytest
+
+from synth import synth_image, synth_stereo
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [(640, 480, 1000), (1241, 376, 2000)]
+
+
+def _cmp_kps(a, b):
+    assert len(a) == len(b)
+    for f in ("x", "y", "size", "angle", "response", "octave", "class_id"):
+        assert np.array_equal(a[f], b[f]), f
+
+
+@pytest.mark.parametrize("w,h,nf", CONFIGS)
+def test_stages_and_end_to_end(pkg, oracle, w, h, nf):
+    img = synth_image(w, h, 3)
+    ex = pkg.ORBextractor(nf, 1.2, 8, 20, 7, max_width=1280, max_height=512 if h < 512 else 1024)
+    oe = oracle.extractor(nf, 1.2, 8, 20, 7)
+    kps, desc = ex(img)
+    okps, odesc = oe(img)
+    (t, nfl, _) = oe.tables()
+    assert np.array_equal(ex.mvScaleFactor, t[0]) and np.array_equal(ex.mvInvScaleFactor, t[1])
+    assert np.array_equal(ex.mvLevelSigma2, t[2]) and np.array_equal(ex.mvInvLevelSigma2, t[3])
+    assert np.array_equal(ex.mnFeaturesPerLevel, nfl)
+    for l in range(8):
+        assert np.array_equal(ex.debug_level(0, l), oe.level(l)), "pyramid level %d" % l
+        ob = oe.level(l, blurred=True)
+        if ob is not None:
+            assert np.array_equal(ex.debug_level(0, l, blurred=True), ob), "blurred level %d" % l
+        xy, resp = ex.debug_candidates(0, l)
+        oc = oe.candidates(l)
+        assert len(xy) == len(oc), "level %d candidates %d vs %d" % (l, len(xy), len(oc))
+        assert np.array_equal(xy[:, 0], oc["x"].astype(np.int32)) and np.array_equal(xy[:, 1], oc["y"].astype(np.int32))
+        assert np.array_equal(resp, oc["response"].astype(np.int32))
+    _cmp_kps(kps, okps)
+    assert np.array_equal(desc, odesc)
+    assert len(kps) >= nf
+
+
+def test_stereo_pair_batch(pkg, oracle):
+    w, h, nf = 1241, 376, 2000
+    left, right = synth_stereo(w, h, 11)
+    ex = pkg.ORBextractor(nf, 1.2, 8, 20, 7, max_width=1280, max_height=512, max_batch=2)
+    oe = oracle.extractor(nf, 1.2, 8, 20, 7)
+    res = ex.extract_batch([left, right])
+    for im, (kps, desc) in zip((left, right), res):
+        okps, odesc = oe(im)
+        _cmp_kps(kps, okps)
+        assert np.array_equal(desc, odesc)
+
+
+def test_low_texture_and_empty(pkg, oracle):
+    ex = pkg.ORBextractor(500, 1.2, 8, 20, 7, max_width=640, max_height=480)
+    oe = oracle.extractor(500, 1.2, 8, 20, 7)
+    # empty image -> silent empty result (src/ORBextractor.cc:1553)
+    k, d = ex(np.zeros((0, 0), np.uint8))
+    assert len(k) == 0 and d.shape == (0, 32)
+    # flat image: no corners at all
+    flat = np.full((480, 640), 77, np.uint8)
+    k, d = ex(flat)
+    assert len(k) == 0
+    # weak texture only: exercises the minThFAST fallback in every cell
+    rng = np.random.RandomState(5)
+    weak = (100 + rng.randint(0, 24, size=(480, 640))).astype(np.uint8)
+    k, d = ex(weak)
+    ok, od = oe(weak)
+    _cmp_kps(k, ok)
+    assert np.array_equal(d, od)
+
+
+def test_sincosf_device_matches_glibc(pkg, oracle):
+    import ctypes
+    L = pkg.lib()
+    L.b2s_debug_sincosf.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    hi = np.float32(6.2832).view(np.uint32)
+    chunk = 1 << 26
+    bad = 0
+    for start in range(0, int(hi) + 1, chunk):
+        bits = np.arange(start, min(start + chunk, int(hi) + 1), dtype=np.uint32)
+        x = bits.view(np.float32)
+        s = np.zeros_like(x)
+        c = np.zeros_like(x)
+        rc = L.b2s_debug_sincosf(x.ctypes.data, len(x), s.ctypes.data, c.ctypes.data)
+        assert rc == 0
+        os_, oc = oracle.sincosf(x)
+        bad += int((s.view(np.uint32) != os_.view(np.uint32)).sum()) + int((c.view(np.uint32) != oc.view(np.uint32)).sum())
+    assert bad == 0
