@@ -14,7 +14,9 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "liborb_oracle.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler",
-              "-fPIC,-O3", "--fmad=false"]
+              "-fPIC,-O3"]
+# extractor/matcher: bit-exact float arithmetic, never contract a*b+c; LocalBA is FP64 with a 1e-5 bar -> FMA allowed
+NO_FMAD = {"extractor.cu", "matcher.cu", "common.cu"}
 
 
 def _newer(target, sources):
@@ -40,7 +42,8 @@ def build_cuda(force=False, verbose=False):
     for s in srcs:
         o = s[:-3] + ".o"
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + (["--fmad=false"] if os.path.basename(s) in NO_FMAD else []) + (
+            ["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for cmd, p in procs:
         out, _ = p.communicate()

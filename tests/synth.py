@@ -155,3 +155,51 @@ def synth_local_ba(n_kf=50, n_fixed=10, n_mp=5000, obs_per_mp=6, seed=42, mono_f
     return dict(n_kf=n_kf, n_local=n_local, Tcw=Tcw0.astype(np.float32).reshape(n_kf, 16), fixed=fixed,
                 points=pts0.astype(np.float32), edges=E, fx=np.float32(fx), fy=np.float32(fy), cx=np.float32(cx),
                 cy=np.float32(cy), bf=np.float32(bf), Tcw_true=Tcw_true, pts_true=pts_true)
+
+
+def synth_projection(nf=2000, nq=1800, seed=7, w=1241, h=376, cluster=False, th=7.0):
+    """Current-frame features + projected last-frame map points (SURVEY A5 / src/ORBmatcher.cc:1569)."""
+    rng = np.random.RandomState(seed)
+    scale = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+    if cluster:
+        kpx = (300 + rng.randint(0, 1200, size=nf) / 10.0).astype(np.float32)
+        kpy = (150 + rng.randint(0, 600, size=nf) / 10.0).astype(np.float32)
+    else:
+        kpx = (rng.randint(0, w * 10, size=nf) / 10.0).astype(np.float32)
+        kpy = (rng.randint(0, h * 10, size=nf) / 10.0).astype(np.float32)
+    octave = rng.randint(0, 8, size=nf).astype(np.int32)
+    angle = (rng.randint(0, 360000, size=nf) / 1000.0).astype(np.float32)
+    desc = rng.randint(0, 256, size=(nf, 32)).astype(np.uint8)
+    if cluster:  # near-duplicate descriptors so that K-lists run dry
+        base = rng.randint(0, 256, size=(4, 32)).astype(np.uint8)
+        desc = base[rng.randint(0, 4, size=nf)].copy()
+        for i in range(nf):
+            for b in rng.choice(256, size=int(rng.randint(0, 12)), replace=False):
+                desc[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    bf = np.float32(386.1448)
+    depth = rng.uniform(4, 60, size=nf).astype(np.float32)
+    uright = (kpx - bf / depth).astype(np.float32)
+    uright[rng.randint(0, 100, size=nf) < 20] = -1.0
+    occupied = (rng.randint(0, 100, size=nf) < 5).astype(np.uint8)
+    qdt = np.dtype([("u", "<f4"), ("v", "<f4"), ("invz", "<f4"), ("angle", "<f4"), ("octave", "<i4"),
+                    ("has_obs", "<i4"), ("desc", "u1", 32)])
+    q = np.zeros(nq, qdt)
+    src = rng.randint(0, nf, size=nq)
+    for i in range(nq):
+        j = src[i]
+        q["u"][i] = kpx[j] + np.float32(rng.randint(-40, 41) / 10.0)
+        q["v"][i] = kpy[j] + np.float32(rng.randint(-40, 41) / 10.0)
+        q["invz"][i] = np.float32(1.0) / depth[j] if rng.randint(0, 100) > 2 else np.float32(-0.1)
+        q["angle"][i] = np.float32((float(angle[j]) + rng.randint(-12000, 12001) / 1000.0) % 360.0)
+        q["octave"][i] = min(7, max(0, int(octave[j]) + int(rng.randint(-1, 2))))
+        q["has_obs"][i] = 1 if rng.randint(0, 100) < 85 else 0
+        d = desc[j].copy()
+        for b in rng.choice(256, size=int(rng.randint(0, 30)), replace=False):
+            d[b >> 3] ^= np.uint8(1 << (b & 7))
+        q["desc"][i] = d
+    # a few queries out of bounds
+    q["u"][:5] = -3.0
+    geom = dict(mnMinX=np.float32(0), mnMinY=np.float32(0), mnMaxX=np.float32(w), mnMaxY=np.float32(h), bf=bf,
+                scale_factors=scale)
+    return dict(q=q, kpx=kpx, kpy=kpy, octave=octave, angle=angle, uright=uright, occupied=occupied, desc=desc,
+                geom=geom, th=np.float32(th))

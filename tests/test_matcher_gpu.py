@@ -1,0 +1,88 @@
+"""GPU parity of the matchers against the CPU oracle: bit-exact match pairs and counts."""
+import numpy as np
+import pytest
+
+from synth import synth_descriptors, synth_projection
+
+pytestmark = pytest.mark.gpu
+
+
+def test_descriptor_distance(pkg, oracle):
+    rng = np.random.RandomState(0)
+    a = rng.randint(0, 256, size=(3000, 32)).astype(np.uint8)
+    b = rng.randint(0, 256, size=(3000, 32)).astype(np.uint8)
+    b[:10] = a[:10]
+    b[10:20] = ~a[10:20]
+    m = pkg.ORBmatcher()
+    d = m.DescriptorDistance(a, b)
+    ref = np.array([oracle.descriptor_distance(a[i], b[i]) for i in range(len(a))])
+    assert np.array_equal(d, ref)
+    assert d[0] == 0 and d[10] == 256
+
+
+@pytest.mark.parametrize("n_nodes", [100, 1, 17])
+@pytest.mark.parametrize("nnratio,strict,checkori", [(0.7, False, True), (0.75, True, True), (0.9, False, False)])
+def test_search_by_bow(pkg, oracle, n_nodes, nnratio, strict, checkori):
+    A, nA, vA, aA, B, nB, aB = synth_descriptors(2000, seed=1234 + n_nodes, n_nodes=n_nodes)
+    vB = None
+    if strict:  # KF-KF variant needs MapPoints on both sides
+        vB = (np.random.RandomState(3).randint(0, 100, size=len(B)) < 90).astype(np.uint8)
+    m = pkg.ORBmatcher(nnratio, checkori)
+    n, match = m.SearchByBoW(A, nA, vA, aA, B, nB, aB, validB=vB, strict_lt=strict)
+    on, omatch = oracle.search_by_bow(A, nA, vA, aA, B, nB, aB, validB=vB, nnratio=nnratio, strict_lt=strict,
+                                      check_ori=checkori)
+    assert n == on
+    assert np.array_equal(match, omatch)
+    assert n > 500
+
+
+def test_search_by_bow_contention(pkg, oracle):
+    """Near-duplicate descriptors in one node: many rows want the same frame feature -> K-lists run dry (rescan path)."""
+    rng = np.random.RandomState(9)
+    n = 600
+    base = rng.randint(0, 256, size=(3, 32)).astype(np.uint8)
+
+    def noisy(k):
+        d = base[rng.randint(0, 3, size=k)].copy()
+        for i in range(k):
+            for b in rng.choice(256, size=int(rng.randint(0, 10)), replace=False):
+                d[i, b >> 3] ^= np.uint8(1 << (b & 7))
+        return d
+
+    A, B = noisy(n), noisy(n)
+    nodeA = np.zeros(n, np.int32)
+    nodeB = np.zeros(n, np.int32)
+    vA = np.ones(n, np.uint8)
+    aA = np.zeros(n, np.float32)
+    aB = np.zeros(n, np.float32)
+    m = pkg.ORBmatcher(0.99, False)
+    cnt, match = m.SearchByBoW(A, nodeA, vA, aA, B, nodeB, aB)
+    on, omatch = oracle.search_by_bow(A, nodeA, vA, aA, B, nodeB, aB, nnratio=0.99, check_ori=False)
+    assert cnt == on and np.array_equal(match, omatch)
+
+
+def test_search_by_bow_ragged(pkg, oracle):
+    m = pkg.ORBmatcher(0.7, True)
+    A, nA, vA, aA, B, nB, aB = synth_descriptors(333, seed=5, n_nodes=7)
+    n, match = m.SearchByBoW(A, nA, vA, aA, B[:57], nB[:57], aB[:57])
+    on, om = oracle.search_by_bow(A, nA, vA, aA, B[:57], nB[:57], aB[:57])
+    assert n == on and np.array_equal(match, om)
+    n, match = m.SearchByBoW(A[:0], nA[:0], vA[:0], aA[:0], B, nB, aB)
+    assert n == 0 and (match == -1).all()
+    vz = np.zeros_like(vA)
+    n, match = m.SearchByBoW(A, nA, vz, aA, B, nB, aB)
+    assert n == 0 and (match == -1).all()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("cluster,th", [(False, 7.0), (False, 15.0), (True, 15.0)])
+def test_search_by_projection(pkg, oracle, mode, cluster, th):
+    d = synth_projection(seed=21 + mode, cluster=cluster, th=th)
+    m = pkg.ORBmatcher(0.9, True)
+    n, match = m.SearchByProjection(d["q"], d["kpx"], d["kpy"], d["octave"], d["angle"], d["uright"], d["occupied"],
+                                    d["desc"], d["geom"], d["th"], mode=mode)
+    on, om = oracle.search_by_projection_last(d["q"], d["kpx"], d["kpy"], d["octave"], d["angle"], d["uright"],
+                                              d["occupied"], d["desc"], d["geom"], float(d["th"]), mode=mode)
+    assert n == on
+    assert np.array_equal(match, om)
+    assert n > 100
