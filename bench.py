@@ -1,0 +1,325 @@
+#!/usr/bin/env python3
+"""bench.py — stereo frames/s of the hot path (extract + match + LocalBA) on N B200s, one process per GPU.
+
+    python bench.py --gpus 1 --steps K --warmup W                 # this framework (hand-written sm_100a kernels)
+    python bench.py --impl reference --gpus 1 --steps K --warmup W  # the reference algorithm on the host cores (oracle)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" = one batch of F synthetic KITTI-shaped stereo frames (1241x376, 2000 features, 8 levels) per GPU:
+extraction of the 2F images, temporal SearchByBoW (2000x2000 brute force, one vocabulary node) of every left image
+against its predecessor, one LocalBA (50 KF / 5000 MP / 30k edges) per 5 frames; with N > 1 the left-image feature
+records are all-gathered over NCCL.  Prints ONE JSON line (see DESIGN.md "Measurement").
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W_IMG, H_IMG, NFEAT = 1241, 376, 2000
+# algorithmic bytes per 1241x376 image
+B_STAGE_IMAGE = 9359539          # all extractor stages
+B_FAST_IMAGE = 1444097           # FAST stage: every pyramid pixel read once (sum of the 8 level sizes)
+BA_EVERY = 5
+
+
+def make_images(n_distinct, total, seed0=0):
+    """[2*total, h, w] uint8: L_0..L_{total-1}, R_0..R_{total-1}; n_distinct stereo pairs tiled."""
+    from synth import synth_stereo
+    base = [synth_stereo(W_IMG, H_IMG, seed0 + i) for i in range(n_distinct)]
+    out = np.empty((2 * total, H_IMG, W_IMG), np.uint8)
+    for i in range(total):
+        l, r = base[i % n_distinct]
+        out[i] = l
+        out[total + i] = r
+    return out
+
+
+def ba_window():
+    from synth import synth_local_ba
+    return synth_local_ba(n_kf=50, n_fixed=10, n_mp=5000, obs_per_mp=6, seed=42)
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def run_reference(args, rank, world):
+    """The reference algorithm's CPU path (oracle port: oracle/ restates it step for step) on all host cores."""
+    if rank != 0:
+        return
+    import oracle_binding
+    o = oracle_binding.load()
+    threads = os.cpu_count() or 1
+    S = args.ref_frames
+    imgs = make_images(min(S, 8), S)
+    ba = ba_window()
+    L = o.L
+    L.orc_stream_step.restype = ctypes.c_double
+    vp = ctypes.c_void_p
+    L.orc_stream_step.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]
+    keep = dict(Tcw=np.ascontiguousarray(ba["Tcw"], np.float32), fixed=np.ascontiguousarray(ba["fixed"], np.uint8),
+                points=np.ascontiguousarray(ba["points"], np.float32), edges=np.ascontiguousarray(ba["edges"]))
+    prob = oracle_binding.BaProblem(ba["n_kf"], ba["n_local"], keep["Tcw"].ctypes.data, keep["fixed"].ctypes.data,
+                                    len(keep["points"]), keep["points"].ctypes.data, len(keep["edges"]),
+                                    keep["edges"].ctypes.data, ba["fx"], ba["fy"], ba["cx"], ba["cy"], ba["bf"], 5, 10)
+
+    def step():
+        return L.orc_stream_step(NFEAT, 1.2, 8, 20, 7, imgs.ctypes.data_as(vp), S, W_IMG, H_IMG, ctypes.byref(prob),
+                                 BA_EVERY, threads, None)
+
+    for _ in range(args.warmup):
+        step()
+    t = 0.0
+    for _ in range(args.steps):
+        t += step()
+    fps = S * args.steps / t
+    line = {
+        "impl": "reference", "metric": "stereo_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (extract, match), f64 (LocalBA)", "data": "synthetic",
+        "config": workload_config(S, 1),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": "%d stereo frames per step (bounded sample of the workload), oracle port on %d host threads"
+                                   % (S, threads)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(frames_per_gpu, world):
+    return {"workload": "batched KITTI-shape stereo stream 1241x376, 2000 feat/img, 8 levels, FAST 20/7: extract L+R, "
+                        "temporal SearchByBoW 2000x2000 (one vocabulary node), LocalBA 50KF/5000MP/30k edges every 5th frame",
+            "frames_per_step_per_gpu": frames_per_gpu, "images_per_step_per_gpu": 2 * frames_per_gpu,
+            "parallelism": "frames sharded x%d, NCCL all-gather of left-image feature records" % world,
+            "l2": "inputs per step (%.0f MB of images per GPU) exceed the 126 MB L2"
+                  % (2 * frames_per_gpu * W_IMG * H_IMG / 1e6)}
+
+
+def run_b200(args, rank, local_rank, world):
+    import torch
+    pkg = importlib.import_module("self_commit_orb-slam2_b200")
+    stream_mod = importlib.import_module("self_commit_orb-slam2_b200.stream")
+    if pkg.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    F = args.frames
+    ba = ba_window()
+    ss = stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, ba_problem=ba, ba_every=BA_EVERY, device=local_rank, rank=rank,
+                                 world=world)
+    imgs = make_images(min(F, 16), F, seed0=1000 * rank)
+    pinned = torch.from_numpy(imgs).pin_memory()
+    ss.upload(pinned)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---------------- device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        ss.step_device()
+    ss.ex.check()
+    torch.cuda.synchronize()
+    barrier()
+    L = pkg.lib()
+    L.b2s_extractor_set_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.b2s_extractor_get_timing.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.b2s_extractor_set_timing(ss.ex._h, 1)
+    launches0 = ss.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        ss.step_device()
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    # the LocalBA batch runs on its own stream and is synchronous on the host, so the host wall clock bounds everything
+    dev_ms = max(ev0.elapsed_time(ev1), wall * 1e3)
+    launches = ss.launch_count() - launches0
+    stage = (ctypes.c_double * 5)()
+    calls = ctypes.c_longlong(0)
+    L.b2s_extractor_get_timing(ss.ex._h, stage, ctypes.byref(calls))
+    L.b2s_extractor_set_timing(ss.ex._h, 0)
+    ss.ex.check()
+    t_all = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    dev_ms = float(t_all.item())
+    value = world * F * args.steps / (dev_ms / 1e3)
+
+    # ---------------- end to end through the host-buffer C ABI (`e2e`)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    ss.step_host(imgs)  # warm
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        n, nm, ba_out, _ = ss.step_host(imgs)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * F * e2e_steps / float(t_e.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks, peak_src = load_peaks()
+    fast_ms = stage[1] / max(1, calls.value)
+    images_per_launch = 2 * F
+    achieved = B_FAST_IMAGE * images_per_launch / (fast_ms * 1e-3) / 1e9 if fast_ms > 0 else 0.0
+    ex_ms = sum(stage) / max(1, calls.value)
+    line = {
+        "metric": "stereo_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32 (extract, match), f64 (LocalBA)", "data": "synthetic",
+        "config": workload_config(F, world),
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": ss.h2d_bytes_per_step(),
+                "d2h_bytes_per_step": ss.d2h_bytes_per_step(), "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "k_fast_cells (per-cell FAST-9/16 score + NMS + dual threshold)", "bound": "hbm",
+                     "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": None, "peak_source": peak_src, "launch_ms": fast_ms,
+                     "algorithmic_bytes_per_launch": B_FAST_IMAGE * images_per_launch,
+                     "extractor_all_stages": {"ms_per_launch_set": ex_ms,
+                                              "achieved_GBps": B_STAGE_IMAGE * images_per_launch / (ex_ms * 1e-3) / 1e9
+                                              if ex_ms > 0 else 0.0,
+                                              "stage_ms": {"resize_chain": stage[0] / max(1, calls.value),
+                                                           "fast_cells": fast_ms,
+                                                           "quadtree": stage[2] / max(1, calls.value),
+                                                           "blur": stage[3] / max(1, calls.value),
+                                                           "orient_describe": stage[4] / max(1, calls.value)}}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline():
+    """Oracle port timed on this box's host cores, bounded sample (about 10-30 core-seconds)."""
+    import oracle_binding
+    o = oracle_binding.load()
+    threads = os.cpu_count() or 1
+    S = 48
+    imgs = make_images(8, S)
+    ba = ba_window()
+    L = o.L
+    vp = ctypes.c_void_p
+    L.orc_stream_step.restype = ctypes.c_double
+    L.orc_stream_step.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]
+    keep = dict(Tcw=np.ascontiguousarray(ba["Tcw"], np.float32), fixed=np.ascontiguousarray(ba["fixed"], np.uint8),
+                points=np.ascontiguousarray(ba["points"], np.float32), edges=np.ascontiguousarray(ba["edges"]))
+    prob = oracle_binding.BaProblem(ba["n_kf"], ba["n_local"], keep["Tcw"].ctypes.data, keep["fixed"].ctypes.data,
+                                    len(keep["points"]), keep["points"].ctypes.data, len(keep["edges"]),
+                                    keep["edges"].ctypes.data, ba["fx"], ba["fy"], ba["cx"], ba["cy"], ba["bf"], 5, 10)
+    t = L.orc_stream_step(NFEAT, 1.2, 8, 20, 7, imgs.ctypes.data_as(vp), S, W_IMG, H_IMG, ctypes.byref(prob), BA_EVERY,
+                          threads, None)
+    return {"value": S / t, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": "%d stereo frames (96 images, 48 matches, 10 LocalBA windows) on %d host threads, %.1f s" % (S, threads, t)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=160, help="stereo frames per step per GPU (160 -> 149 MB of images)")
+    ap.add_argument("--ref-frames", type=int, default=24, help="stereo frames per step of the CPU reference arm")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

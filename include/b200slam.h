@@ -84,6 +84,11 @@ int b2s_extractor_check(b2s_extractor* h);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
 long long b2s_extractor_launch_count(const b2s_extractor* h);
 
+/* per-stage CUDA-event timing on the launching stream (bench.py roofline): enable, run, then read the accumulated
+ * device milliseconds of {pyramid resize chain, FAST cells, quadtree, blur, orient+describe} and the call count. */
+int b2s_extractor_set_timing(b2s_extractor* h, int enable);
+int b2s_extractor_get_timing(b2s_extractor* h, double* stage_ms5, long long* calls);
+
 /* test hooks: device -> host copies of intermediates of image `b` of the last call */
 int b2s_extractor_debug_level(b2s_extractor* h, int b, int level, int blurred, uint8_t* out, int* w, int* hgt);
 int b2s_extractor_debug_candidates(b2s_extractor* h, int b, int level, int32_t* xy /*2*cap*/, int32_t* resp, int cap,
@@ -106,6 +111,13 @@ int b2s_descriptor_distance(b2s_matcher* h, const uint8_t* a, const uint8_t* b, 
 int b2s_search_by_bow(b2s_matcher* h, const uint8_t* descA, const int32_t* nodeA, const uint8_t* validA, const float* angA,
                       int nA, const uint8_t* descB, const int32_t* nodeB, const uint8_t* validB, const float* angB, int nB,
                       int th_low, float nnratio, int strict_lt, int check_ori, int32_t* matchB, int* nmatches);
+
+/* Batched HOST-buffer variant: `batch` independent (A,B) pairs laid out with strides capA/capB features;
+ * nA/nB: host int arrays [batch]; matchB: batch*capB; nmatches: batch. One H2D per array, one D2H per result. */
+int b2s_search_by_bow_batch(b2s_matcher* h, int batch, const uint8_t* descA, const int32_t* nodeA, const uint8_t* validA,
+                            const float* angA, const int32_t* nA, int capA, const uint8_t* descB, const int32_t* nodeB,
+                            const uint8_t* validB, const float* angB, const int32_t* nB, int capB, int th_low,
+                            float nnratio, int strict_lt, int check_ori, int32_t* matchB, int32_t* nmatches);
 
 /* Batched device-resident variant: `batch` independent (A,B) pairs with strides capA/capB features. All pointers are
  * DEVICE pointers; nA/nB are device int arrays [batch]. Asynchronous on `stream`. */

@@ -132,6 +132,11 @@ void orc_sincosf_batch(const float* in, long n, float* s, float* c, int threads)
 int orc_extract_many(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t* imgs, int count,
                      int w, int h, orc_keypoint* kps, uint8_t* desc, int cap, int* n_out, int threads);
 
+/* CPU reference arm of bench.py: extract 2S images + ring SearchByBoW (one node) + LocalBA every ba_every frames on
+ * `threads` host threads; returns wall seconds. imgs: L_0..L_{S-1}, R_0..R_{S-1}, each w*h tightly packed. */
+double orc_stream_step(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t* imgs, int S,
+                       int w, int h, const orc_ba_problem* ba, int ba_every, int threads, int* out_counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,8 @@ def lib():
         L.b2s_extract_batch_device.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int, _vp, _vp, _vp, ctypes.c_int, _vp]
         L.b2s_extractor_check.argtypes = [_vp]
+        L.b2s_extractor_set_timing.argtypes = [_vp, ctypes.c_int]
+        L.b2s_extractor_get_timing.argtypes = [_vp, _vp, _vp]
         L.b2s_extractor_debug_level.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]
         L.b2s_extractor_debug_candidates.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp]
         if hasattr(L, "b2s_matcher_create"):
@@ -89,6 +91,9 @@ def lib():
             L.b2s_descriptor_distance.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp]
             L.b2s_search_by_bow.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, _vp, _vp]
+            L.b2s_search_by_bow_batch.argtypes = [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, _vp,
+                                                  _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
+                                                  ctypes.c_int, _vp, _vp]
             L.b2s_search_by_bow_device.argtypes = [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp,
                                                    _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                                    ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]

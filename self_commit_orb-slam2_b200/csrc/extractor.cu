@@ -903,37 +903,85 @@ static int build_geometry(b2s_extractor* h, int W, int H) {
   return B2S_OK;
 }
 
+static void b2s_extractor_timing_collect(b2s_extractor* h);
+
 // Enqueue the whole pipeline for `batch` images whose level-0 pixels are already in d.pyr.
 static int run_pipeline(b2s_extractor* h, int batch, b2s_keypoint* dKps, uint8_t* dDesc, int32_t* dCounts, int cap,
                         cudaStream_t st) {
   const ExtractGeom& g = h->geom;
   DeviceBuffers& d = h->d;
   B2S_CUDA(cudaMemsetAsync(d.candCount, 0, sizeof(int32_t) * kMaxLevels * batch, st));
+  const bool tm = h->timing != 0;
+  if (tm) {
+    if (h->evPending) b2s_extractor_timing_collect(h);
+    cudaEventRecord(h->ev[0], st);
+  }
   for (int l = 1; l < g.nlevels; l++) {
     dim3 grid(div_up(g.lv[l].w, 128), g.lv[l].h, batch);
     k_resize<<<grid, 128, 0, st>>>(g, l, d.pyr, d.rxOfs, d.rxAlpha, d.ryOfs, d.ryBeta);
     h->launches++;
   }
+  if (tm) cudaEventRecord(h->ev[1], st);
   k_fast_cells<<<dim3(g.totalCells, batch), 128, 0, st>>>(g, d.pyr, d.candXY, d.candKey, d.candResp, d.candCount, d.status);
   h->launches++;
+  if (tm) cudaEventRecord(h->ev[2], st);
   int capMax = 0;
   for (int l = 0; l < g.nlevels; l++) capMax = std::max(capMax, g.lv[l].nodeCap);
   const size_t qsm = quadtree_smem_bytes(capMax);
   k_quadtree<<<dim3(g.nlevels, batch), 256, qsm, st>>>(g, capMax, d.candXY, d.candKey, d.candResp, d.candNode, d.candQ,
                                                        d.candCount, d.selXYR, d.selCount, d.status);
   h->launches++;
+  if (tm) cudaEventRecord(h->ev[3], st);
   k_blur<<<dim3(g.totalBlurTiles, batch), 256, 0, st>>>(g, d.pyr, d.blur);
   h->launches++;
+  if (tm) cudaEventRecord(h->ev[4], st);
   k_orient_describe<<<dim3(div_up(g.totalSelCap, 8), batch), 256, 0, st>>>(g, d.pyr, d.blur, d.selXYR, d.selCount, dKps,
                                                                            dDesc, dCounts, cap, d.status);
   h->launches++;
+  if (tm) {
+    cudaEventRecord(h->ev[5], st);
+    h->evPending = 1;
+  }
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;
+}
+
+static void b2s_extractor_timing_collect(b2s_extractor* h) {
+  if (!h->evPending) return;
+  if (cudaEventSynchronize(h->ev[5]) != cudaSuccess) return;
+  for (int k = 0; k < 5; k++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1]) == cudaSuccess) h->stageMs[k] += ms;
+  }
+  h->timedCalls++;
+  h->evPending = 0;
 }
 
 }  // namespace b2s
 
 using namespace b2s;
+
+extern "C" int b2s_extractor_set_timing(b2s_extractor* h, int enable) {
+  if (!h) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  if (enable && !h->ev[0])
+    for (int k = 0; k < 6; k++) B2S_CUDA(cudaEventCreate(&h->ev[k]));
+  b2s_extractor_timing_collect(h);
+  h->timing = enable;
+  for (int k = 0; k < 5; k++) h->stageMs[k] = 0;
+  h->timedCalls = 0;
+  return B2S_OK;
+}
+
+/* accumulated device milliseconds per stage since set_timing(1): resize chain, FAST, quadtree, blur, orient+describe */
+extern "C" int b2s_extractor_get_timing(b2s_extractor* h, double* stage_ms5, long long* calls) {
+  if (!h || !stage_ms5) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  b2s_extractor_timing_collect(h);
+  for (int k = 0; k < 5; k++) stage_ms5[k] = h->stageMs[k];
+  if (calls) *calls = h->timedCalls;
+  return B2S_OK;
+}
 
 extern "C" int b2s_extractor_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
                                     int max_width, int max_height, int max_batch, int device, b2s_extractor** out) {

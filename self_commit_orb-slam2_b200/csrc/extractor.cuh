@@ -80,4 +80,10 @@ struct b2s_extractor {
   int32_t* hCounts = nullptr;
   int32_t* hStatus = nullptr;
   long long launches = 0;
+  // optional per-stage CUDA-event timing (bench.py roofline): resize chain, FAST, quadtree, blur, describe
+  int timing = 0;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double stageMs[5] = {0, 0, 0, 0, 0};
+  long long timedCalls = 0;
+  int evPending = 0;
 };

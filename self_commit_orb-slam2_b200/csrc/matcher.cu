@@ -754,6 +754,41 @@ extern "C" int b2s_search_by_bow(b2s_matcher* h, const uint8_t* descA, const int
   return B2S_OK;
 }
 
+extern "C" int b2s_search_by_bow_batch(b2s_matcher* h, int batch, const uint8_t* descA, const int32_t* nodeA,
+                                       const uint8_t* validA, const float* angA, const int32_t* nA, int capA,
+                                       const uint8_t* descB, const int32_t* nodeB, const uint8_t* validB,
+                                       const float* angB, const int32_t* nB, int capB, int th_low, float nnratio,
+                                       int strict_lt, int check_ori, int32_t* matchB, int32_t* nmatches) {
+  if (!h || batch < 1 || batch > h->maxBatch || capA < 1 || capB < 1 || capA > h->maxF || capB > h->maxF || !descA ||
+      !nodeA || !angA || !nA || !descB || !nodeB || !angB || !nB || !matchB || !nmatches) {
+    set_error("b2s_search_by_bow_batch: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  for (int b = 0; b < batch; b++)
+    if (nA[b] < 0 || nA[b] > capA || nB[b] < 0 || nB[b] > capB) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t FA = (size_t)batch * capA, FB = (size_t)batch * capB;
+  B2S_CUDA(cudaMemcpyAsync(h->dDescA, descA, FA * 32, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNodeA, nodeA, FA * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dAngA, angA, FA * 4, cudaMemcpyHostToDevice, st));
+  if (validA) B2S_CUDA(cudaMemcpyAsync(h->dValidA, validA, FA, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dDescB, descB, FB * 32, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNodeB, nodeB, FB * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dAngB, angB, FB * 4, cudaMemcpyHostToDevice, st));
+  if (validB) B2S_CUDA(cudaMemcpyAsync(h->dValidB, validB, FB, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNA, nA, (size_t)batch * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNB, nB, (size_t)batch * 4, cudaMemcpyHostToDevice, st));
+  int rc = b2s_search_by_bow_device(h, batch, h->dDescA, h->dNodeA, validA ? h->dValidA : nullptr, h->dAngA, h->dNA, capA,
+                                    h->dDescB, h->dNodeB, validB ? h->dValidB : nullptr, h->dAngB, h->dNB, capB, th_low,
+                                    nnratio, strict_lt, check_ori, h->dMatch, h->dNMatches, st);
+  if (rc != B2S_OK) return rc;
+  B2S_CUDA(cudaMemcpyAsync(matchB, h->dMatch, FB * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  return B2S_OK;
+}
+
 extern "C" int b2s_search_by_projection_last(b2s_matcher* h, const b2s_proj_query* q, int nq, const float* kpx,
                                              const float* kpy, const int32_t* octave, const float* angle,
                                              const float* uright, const uint8_t* occupied, const uint8_t* desc, int nf,

@@ -1,0 +1,75 @@
+#include "ORBmatcher.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+namespace ORB_SLAM2 {
+
+static int dev() {
+  const char* e = getenv("B2S_DEVICE");
+  return e ? atoi(e) : 0;
+}
+static void fail(const char* where, int rc) {
+  fprintf(stderr, "%s: libb200slam error %d: %s\n", where, rc, b2s_last_error());
+  throw std::runtime_error(b2s_last_error());
+}
+
+ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+ORBmatcher::~ORBmatcher() { b2s_matcher_destroy(mpHandle); }
+
+void ORBmatcher::Ensure(int n) {
+  if (mpHandle && n <= mCap) return;
+  b2s_matcher_destroy(mpHandle);
+  mpHandle = nullptr;
+  mCap = n < 4096 ? 4096 : n;
+  int rc = b2s_matcher_create(mCap, 1, dev(), &mpHandle);
+  if (rc != B2S_OK) fail("ORBmatcher", rc);
+}
+
+int ORBmatcher::DescriptorDistance(const uint8_t* a, const uint8_t* b) {
+  int d = 0;
+  for (int i = 0; i < 4; i++) {
+    uint64_t x, y;
+    memcpy(&x, a + 8 * i, 8);
+    memcpy(&y, b + 8 * i, 8);
+    d += __builtin_popcountll(x ^ y);
+  }
+  return d;
+}
+
+int ORBmatcher::SearchByBoW(const BowSide& kf, const BowSide& f, std::vector<int32_t>& matchF) {
+  Ensure(kf.n > f.n ? kf.n : f.n);
+  matchF.assign(f.n, -1);
+  int nm = 0;
+  int rc = b2s_search_by_bow(mpHandle, kf.descriptors, kf.node, kf.valid, kf.angle, kf.n, f.descriptors, f.node, nullptr,
+                             f.angle, f.n, TH_LOW, mfNNratio, 0, mbCheckOrientation, matchF.data(), &nm);
+  if (rc != B2S_OK) fail("ORBmatcher::SearchByBoW", rc);
+  return nm;
+}
+
+int ORBmatcher::SearchByBoWKF(const BowSide& k1, const BowSide& k2, std::vector<int32_t>& match2) {
+  Ensure(k1.n > k2.n ? k1.n : k2.n);
+  match2.assign(k2.n, -1);
+  int nm = 0;
+  int rc = b2s_search_by_bow(mpHandle, k1.descriptors, k1.node, k1.valid, k1.angle, k1.n, k2.descriptors, k2.node, k2.valid,
+                             k2.angle, k2.n, TH_LOW, mfNNratio, 1, mbCheckOrientation, match2.data(), &nm);
+  if (rc != B2S_OK) fail("ORBmatcher::SearchByBoW(KF,KF)", rc);
+  return nm;
+}
+
+int ORBmatcher::SearchByProjection(const std::vector<b2s_proj_query>& q, const float* kpx, const float* kpy,
+                                   const int32_t* octave, const float* angle, const float* uright, const uint8_t* occupied,
+                                   const uint8_t* descriptors, int nF, const b2s_frame_geom& geom, float th, int mode,
+                                   std::vector<int32_t>& matchCur) {
+  Ensure((int)q.size() > nF ? (int)q.size() : nF);
+  matchCur.assign(nF, -1);
+  int nm = 0;
+  int rc = b2s_search_by_projection_last(mpHandle, q.data(), (int)q.size(), kpx, kpy, octave, angle, uright, occupied,
+                                         descriptors, nF, &geom, th, mode, TH_HIGH, mbCheckOrientation, matchCur.data(), &nm);
+  if (rc != B2S_OK) fail("ORBmatcher::SearchByProjection", rc);
+  return nm;
+}
+
+}  // namespace ORB_SLAM2

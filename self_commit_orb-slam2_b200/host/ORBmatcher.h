@@ -1,0 +1,51 @@
+// ORBmatcher.h — mirror of the part of /root/reference/include/ORBmatcher.h that is on the hot path, on flattened
+// views (the Frame/KeyFrame/MapPoint pointer graph is gathered by the caller-side adapters shown in INTEGRATION.md).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../include/b200slam.h"
+
+namespace ORB_SLAM2 {
+
+// What the adapters extract from a KeyFrame / Frame for SearchByBoW (src/ORBmatcher.cc:230-382, :656-799)
+struct BowSide {
+  const uint8_t* descriptors = nullptr;  // mDescriptors, N x 32
+  const int32_t* node = nullptr;         // DBoW2 FeatureVector node id of every feature (mFeatVec flattened)
+  const uint8_t* valid = nullptr;        // 1 if the feature has a MapPoint that is not bad (NULL: all valid)
+  const float* angle = nullptr;          // mvKeysUn[i].angle / mvKeys[i].angle
+  int n = 0;
+};
+
+class ORBmatcher {
+ public:
+  static const int TH_LOW = 50;        // src/ORBmatcher.cc:49-51
+  static const int TH_HIGH = 100;
+  static const int HISTO_LENGTH = 30;
+
+  ORBmatcher(float nnratio = 0.6, bool checkOri = true);
+  ~ORBmatcher();
+
+  // static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b) — src/ORBmatcher.cc:1913 (host popcount: a single
+  // pair is not worth a launch; the batched device version is b2s_descriptor_distance)
+  static int DescriptorDistance(const uint8_t* a, const uint8_t* b);
+
+  // SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&): matchF[j] = keyframe feature index or -1; returns nmatches
+  int SearchByBoW(const BowSide& kf, const BowSide& frame, std::vector<int32_t>& matchF);
+  // SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&): strict '<' TH_LOW, both sides need MapPoints
+  int SearchByBoWKF(const BowSide& kf1, const BowSide& kf2, std::vector<int32_t>& match2);
+  // SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) after the projection of the last frame's map points
+  int SearchByProjection(const std::vector<b2s_proj_query>& queries, const float* kpx, const float* kpy,
+                         const int32_t* octave, const float* angle, const float* uright, const uint8_t* occupied,
+                         const uint8_t* descriptors, int nFeatures, const b2s_frame_geom& geom, float th, int mode,
+                         std::vector<int32_t>& matchCur);
+
+ protected:
+  void Ensure(int n);
+  float mfNNratio;
+  bool mbCheckOrientation;
+  b2s_matcher* mpHandle = nullptr;
+  int mCap = 0;
+};
+
+}  // namespace ORB_SLAM2

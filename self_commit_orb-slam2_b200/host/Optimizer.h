@@ -1,0 +1,34 @@
+// Optimizer.h — mirror of Optimizer::LocalBundleAdjustment (/root/reference/include/Optimizer.h:112) on a flattened
+// window.  The adapter that walks KeyFrame/MapPoint (src/Optimizer.cc:633-854) and writes the results back under
+// Map::mMutexMapUpdate (:961-996) is listed in INTEGRATION.md.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../include/b200slam.h"
+
+namespace ORB_SLAM2 {
+
+struct LocalBAWindow {
+  int nLocal = 0;                    // lLocalKeyFrames.size(); local keyframes come first in Tcw/fixed
+  std::vector<float> Tcw;            // nKF x 16 (KeyFrame::GetPose(), row-major)
+  std::vector<uint8_t> fixed;        // nKF: mnId==0 or lFixedCameras
+  std::vector<float> points;         // nMP x 3
+  std::vector<b2s_ba_edge> edges;    // insertion order of :770-853
+  float fx = 0, fy = 0, cx = 0, cy = 0, bf = 0;
+};
+
+struct LocalBAResult {
+  std::vector<float> Tcw;            // nLocal x 16 -> KeyFrame::SetPose
+  std::vector<float> points;         // nMP x 3    -> MapPoint::SetWorldPos
+  std::vector<uint8_t> outlier;      // per edge   -> vToErase
+  bool aborted = false;              // stop flag was set before round 1: nothing to write back (:858-860)
+};
+
+class Optimizer {
+ public:
+  // void static LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap) on the flattened window
+  static void LocalBundleAdjustment(const LocalBAWindow& w, bool* pbStopFlag, LocalBAResult& out);
+};
+
+}  // namespace ORB_SLAM2

@@ -1,0 +1,148 @@
+"""Batched stereo-stream mode: frames sharded over GPUs, one process per GPU.
+
+Per step a rank owns F stereo frames (2F images).  Device-resident path:
+  1. b2s_extract_batch_device  : 2F images -> fixed-size feature records written straight into the buffer that is the
+                                 NCCL all-gather input (no staging copy)
+  2. all_gather (world > 1)    : left-image records of every rank over NVLink/NVSwitch (torch.distributed, NCCL)
+  3. b2s_search_by_bow_device  : temporal match left(t-1) -> left(t) for the rank's F frames, all features in one
+                                 vocabulary node (2000x2000 brute force); the frame before the shard's first one comes
+                                 from the previous rank's gathered records
+  4. b2s_local_ba_batch        : one LocalBA window per `ba_every` frames (replicas; its own stream, overlaps 1-3)
+torch is plumbing only: device memory, streams, torch.distributed.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import (ORBextractor, ORBmatcher, Optimizer, _check, _vp, ba_edge_dtype, keypoint_dtype, lib)
+
+KP_BYTES = keypoint_dtype.itemsize  # 28
+
+
+class StereoStream:
+    def __init__(self, frames_per_step, width, height, nfeatures=2000, scale=1.2, nlevels=8, ini_th=20, min_th=7,
+                 ba_problem=None, ba_every=5, device=0, rank=0, world=1, nnratio=0.7):
+        self.F, self.w, self.h = frames_per_step, width, height
+        self.rank, self.world = rank, world
+        self.dev = torch.device("cuda", device)
+        self.ex = ORBextractor(nfeatures, scale, nlevels, ini_th, min_th, max_width=max(width, 64),
+                               max_height=max(height, 64), max_batch=2 * self.F, device=device)
+        self.cap = self.ex.cap
+        self.matcher = ORBmatcher(nnratio, True, max_features=self.cap, max_batch=self.F, device=device)
+        self.ba_problem = ba_problem
+        self.ba_every = ba_every
+        self.n_ba = (self.F + ba_every - 1) // ba_every if ba_problem is not None else 0
+        self.opt = None
+        if self.n_ba:
+            self.opt = Optimizer(max_kf=max(16, ba_problem["n_kf"]), max_mp=len(ba_problem["points"]),
+                                 max_edges=len(ba_problem["edges"]), max_batch=self.n_ba, device=device)
+        F, cap = self.F, self.cap
+        S = 1 + 2 * F  # slot 0: the frame before this shard; 1..F left images; F+1..2F right images
+        z = dict(device=self.dev)
+        self.kps = torch.zeros((S, cap, KP_BYTES), dtype=torch.uint8, **z)
+        self.desc = torch.zeros((S, cap, 32), dtype=torch.uint8, **z)
+        self.counts = torch.zeros(S, dtype=torch.int32, **z)
+        self.node = torch.zeros((1 + F, cap), dtype=torch.int32, **z)   # every feature in vocabulary node 0
+        self.valid = torch.ones((1 + F, cap), dtype=torch.uint8, **z)
+        self.ang = torch.zeros((1 + F, cap), dtype=torch.float32, **z)
+        self.match = torch.full((F, cap), -1, dtype=torch.int32, **z)
+        self.nmatch = torch.zeros(F, dtype=torch.int32, **z)
+        if world > 1:
+            self.g_kps = torch.zeros((world, F, cap, KP_BYTES), dtype=torch.uint8, **z)
+            self.g_desc = torch.zeros((world, F, cap, 32), dtype=torch.uint8, **z)
+            self.g_counts = torch.zeros((world, F), dtype=torch.int32, **z)
+        self.d_imgs = torch.zeros((2 * F, height, width), dtype=torch.uint8, **z)
+
+    # ------------------------------------------------------------------ device-resident step
+    def upload(self, imgs_host):
+        """imgs_host: uint8 [2F, h, w] (L_0..L_F-1, R_0..R_F-1), ideally pinned."""
+        self.d_imgs.copy_(imgs_host, non_blocking=True)
+
+    def step_device(self, run_ba=True):
+        F, cap = self.F, self.cap
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        self.ex.extract_batch_device(self.d_imgs.data_ptr(), self.w * self.h, 2 * F, self.w, self.h, self.w,
+                                     self.kps[1:].data_ptr(), self.desc[1:].data_ptr(), self.counts[1:].data_ptr(), cap,
+                                     stream=st)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.g_kps, self.kps[1:1 + F])
+            dist.all_gather_into_tensor(self.g_desc, self.desc[1:1 + F])
+            dist.all_gather_into_tensor(self.g_counts, self.counts[1:1 + F])
+            prev = (self.rank - 1) % self.world
+            self.kps[0].copy_(self.g_kps[prev, F - 1])
+            self.desc[0].copy_(self.g_desc[prev, F - 1])
+            self.counts[0:1].copy_(self.g_counts[prev, F - 1:F])
+        else:  # ring inside the shard
+            self.kps[0].copy_(self.kps[F])
+            self.desc[0].copy_(self.desc[F])
+            self.counts[0:1].copy_(self.counts[F:F + 1])
+        # angles of the left images (kpUn.angle), gathered out of the 28-byte records
+        self.ang.copy_(self.kps[:1 + F].view(torch.float32)[:, :, 3])
+        L = lib()
+        _check(L.b2s_search_by_bow_device(self.matcher._h, F, _vp(self.desc.data_ptr()), _vp(self.node.data_ptr()),
+                                          _vp(self.valid.data_ptr()), _vp(self.ang.data_ptr()),
+                                          _vp(self.counts.data_ptr()), cap, _vp(self.desc[1:].data_ptr()),
+                                          _vp(self.node[1:].data_ptr()), None, _vp(self.ang[1:].data_ptr()),
+                                          _vp(self.counts[1:].data_ptr()), cap, 50, float(self.matcher.mfNNratio), 0, 1,
+                                          _vp(self.match.data_ptr()), _vp(self.nmatch.data_ptr()), _vp(st)))
+        ba_out = None
+        if run_ba and self.n_ba:
+            ba_out = self.opt.LocalBundleAdjustmentBatch([self.ba_problem] * self.n_ba)
+        return ba_out
+
+    # ------------------------------------------------------------------ end-to-end step through the host-buffer C ABI
+    def step_host(self, imgs_host_np, run_ba=True):
+        """imgs_host_np: numpy uint8 [2F, h, w]. Returns (counts, nmatches, ba_out); everything ends up in host memory."""
+        F, cap = self.F, self.cap
+        res_kps = np.zeros((2 * F, cap), keypoint_dtype)
+        res_desc = np.zeros((2 * F, cap, 32), np.uint8)
+        n = np.zeros(2 * F, np.int32)
+        ptrs = (_vp * (2 * F))(*[imgs_host_np[i].ctypes.data for i in range(2 * F)])
+        L = lib()
+        _check(L.b2s_extract_batch(self.ex._h, ctypes.cast(ptrs, _vp), 2 * F, self.w, self.h, self.w,
+                                   res_kps.ctypes.data_as(_vp), res_desc.ctypes.data_as(_vp), cap,
+                                   n.ctypes.data_as(_vp)))
+        # ring: pair f = (left f-1, left f)
+        order = [(f - 1) % F for f in range(F)]
+        descA = np.ascontiguousarray(res_desc[order])
+        angA = np.ascontiguousarray(res_kps["angle"][order])
+        nA = np.ascontiguousarray(n[order])
+        descB = res_desc[:F]
+        angB = np.ascontiguousarray(res_kps["angle"][:F])
+        nB = np.ascontiguousarray(n[:F])
+        node = np.zeros((F, cap), np.int32)
+        valid = np.ones((F, cap), np.uint8)
+        match = np.full((F, cap), -1, np.int32)
+        nm = np.zeros(F, np.int32)
+        p = lambda a: a.ctypes.data_as(_vp)
+        _check(L.b2s_search_by_bow_batch(self.matcher._h, F, p(descA), p(node), p(valid), p(angA), p(nA), cap, p(descB),
+                                         p(node), None, p(angB), p(nB), cap, 50, float(self.matcher.mfNNratio), 0, 1,
+                                         p(match), p(nm)))
+        ba_out = None
+        if run_ba and self.n_ba:
+            ba_out = self.opt.LocalBundleAdjustmentBatch([self.ba_problem] * self.n_ba)
+        return n, nm, ba_out, (res_kps, res_desc, match)
+
+    def launch_count(self):
+        c = self.ex.launch_count() + self.matcher.launch_count()
+        if self.opt is not None:
+            c += self.opt.launch_count()
+        return c
+
+    def h2d_bytes_per_step(self):
+        b = 2 * self.F * self.w * self.h
+        b += self.F * self.cap * (32 + 4 + 4 + 1) * 2  # descriptors, nodes, angles, valid for both sides of the matcher
+        if self.n_ba:
+            pr = self.ba_problem
+            b += self.n_ba * (pr["n_kf"] * 64 + len(pr["points"]) * 12 + len(pr["edges"]) * ba_edge_dtype.itemsize)
+        return int(b)
+
+    def d2h_bytes_per_step(self):
+        b = 2 * self.F * self.cap * (KP_BYTES + 32) + 2 * self.F * 4
+        b += self.F * self.cap * 4 + self.F * 4
+        if self.n_ba:
+            pr = self.ba_problem
+            b += self.n_ba * (pr["n_local"] * 64 + len(pr["points"]) * 12 + len(pr["edges"]))
+        return int(b)
