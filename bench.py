@@ -200,10 +200,10 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
-    ev0.record()
+    ev0.record(ss.stream)
     for _ in range(args.steps):
         ss.step_device()
-    ev1.record()
+    ev1.record(ss.stream)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     barrier()

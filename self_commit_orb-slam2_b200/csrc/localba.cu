@@ -48,6 +48,8 @@ struct BaPtrs {  // strided per-window arrays
   double *err, *chi2, *W;
   int *mpStart, *mpEdges, *kfStart, *kfEdges;
   double *Hpp, *Hll, *b, *x, *Dinv, *S;
+  double *db, *Y;      // Dinv*b_l per landmark, W*Dinv per edge
+  int *lmEdge, *freeKf;  // [landmark][free pose] -> edge id or -1 ; free pose index -> keyframe index
   double *partChi, *partScale;
   int* anyActive;
 };
@@ -442,99 +444,161 @@ __global__ void k_control_begin(BaPtrs p, int batch) {
   st.maxDiagBits = 0ull;
 }
 
-// _Hschur = _Hpp (+lambda on the diagonal), augmented with b_p as an extra row so that the Cholesky sweep also does
-// the forward substitution
-__global__ void __launch_bounds__(256) k_schur_init(BaPtrs p) {
+// ---- Schur complement (block_solver.hpp:381-439), atomic-free and deterministic:
+//   k_lm_edge      (once per window)  lmEdge[landmark][free pose] = edge id
+//   k_dinv         per landmark:  Dinv = (Hll + lambda I)^-1,  db = Dinv b_l
+//   k_schur_pose   per free pose: Y_e = W_e Dinv (kept for the block pass), augmented row  b_p - sum_e W_e db
+//   k_schur_blocks per lower block (i1 >= i2): S(i1,i2) = [Hpp + lambda I] - sum_{l seen by both} Y_a W_c^T
+__global__ void __launch_bounds__(256) k_lm_edge(BaPtrs p) {
   const int w = blockIdx.y;
-  const BaState& st = p.st[w];
-  if (!st.active) return;
   const BaWin W = p.win[w];
-  const int n = W.nFree * 6, N1 = n + 1;
-  double* S = p.S + (size_t)w * p.ldS * p.ldS;
-  const double* bvec = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3);
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N1 * N1; idx += gridDim.x * blockDim.x) {
-    const int r = idx / N1, c = idx - r * N1;
-    double v = 0;
-    if (r < n && c < n) {
-      if (r / 6 == c / 6) {
-        v = p.Hpp[((size_t)w * p.capKf + r / 6) * 36 + (r % 6) * 6 + (c % 6)];
-        if (r == c) v += st.lambda;
-      }
-    } else if (r == n && c < n) {
-      v = bvec[c];
-    }
-    S[(size_t)r * p.ldS + c] = v;
-  }
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= W.nEdges) return;
+  const size_t eo = (size_t)w * p.capE + e;
+  const int pi = p.poseIndex[(size_t)w * p.capKf + p.eKf[eo]];
+  if (pi >= 0) p.lmEdge[((size_t)w * p.capMp + p.eMp[eo]) * p.capKf + pi] = e;
 }
 
-// Schur complement (block_solver.hpp:381-439): one warp per landmark
-__global__ void __launch_bounds__(256) k_schur(BaPtrs p) {
+__global__ void __launch_bounds__(128) k_dinv(BaPtrs p) {
   const int w = blockIdx.y;
   const BaState& st = p.st[w];
   if (!st.active) return;
   const BaWin W = p.win[w];
-  const int lane = threadIdx.x & 31;
-  const int l = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= W.nMp) return;
   const size_t mo = (size_t)w * p.capMp + l;
-  const int* ms = p.mpStart + (size_t)w * (p.capMp + 1);
-  const int* me = p.mpEdges + (size_t)w * p.capE;
   double D[9];
 #pragma unroll
   for (int k = 0; k < 9; k++) D[k] = p.Hll[mo * 9 + k];
   D[0] += st.lambda; D[4] += st.lambda; D[8] += st.lambda;
   double Di[9];
-  {
-    const double c00 = D[4] * D[8] - D[5] * D[7], c01 = D[5] * D[6] - D[3] * D[8], c02 = D[3] * D[7] - D[4] * D[6];
-    const double id = 1.0 / (D[0] * c00 + D[1] * c01 + D[2] * c02);
-    Di[0] = c00 * id; Di[1] = (D[2] * D[7] - D[1] * D[8]) * id; Di[2] = (D[1] * D[5] - D[2] * D[4]) * id;
-    Di[3] = c01 * id; Di[4] = (D[0] * D[8] - D[2] * D[6]) * id; Di[5] = (D[2] * D[3] - D[0] * D[5]) * id;
-    Di[6] = c02 * id; Di[7] = (D[1] * D[6] - D[0] * D[7]) * id; Di[8] = (D[0] * D[4] - D[1] * D[3]) * id;
-  }
-  if (lane < 9) p.Dinv[mo * 9 + lane] = Di[lane];
+  const double c00 = D[4] * D[8] - D[5] * D[7], c01 = D[5] * D[6] - D[3] * D[8], c02 = D[3] * D[7] - D[4] * D[6];
+  const double id = 1.0 / (D[0] * c00 + D[1] * c01 + D[2] * c02);
+  Di[0] = c00 * id; Di[1] = (D[2] * D[7] - D[1] * D[8]) * id; Di[2] = (D[1] * D[5] - D[2] * D[4]) * id;
+  Di[3] = c01 * id; Di[4] = (D[0] * D[8] - D[2] * D[6]) * id; Di[5] = (D[2] * D[3] - D[0] * D[5]) * id;
+  Di[6] = c02 * id; Di[7] = (D[1] * D[6] - D[0] * D[7]) * id; Di[8] = (D[0] * D[4] - D[1] * D[3]) * id;
+#pragma unroll
+  for (int k = 0; k < 9; k++) p.Dinv[mo * 9 + k] = Di[k];
   const double* bl = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)W.nFree * 6 + (size_t)l * 3;
-  const double db0 = Di[0] * bl[0] + Di[1] * bl[1] + Di[2] * bl[2];
-  const double db1 = Di[3] * bl[0] + Di[4] * bl[1] + Di[5] * bl[2];
-  const double db2 = Di[6] * bl[0] + Di[7] * bl[1] + Di[8] * bl[2];
-  double* S = p.S + (size_t)w * p.ldS * p.ldS;
-  const int n = W.nFree * 6;
-  const int beg = ms[l], cnt = ms[l + 1] - beg;
-  // items: (a, c, entry) with pose(a) >= pose(c) ; plus the right-hand side rows (a, r)
-  const int items = cnt * cnt * 36;
-  for (int it = lane; it < items; it += 32) {
-    const int pr = it / 36, en = it - pr * 36;
-    const int ia = pr / cnt, ic = pr - ia * cnt;
-    const int ea = me[beg + ia], ec = me[beg + ic];
-    const size_t eoa = (size_t)w * p.capE + ea, eoc = (size_t)w * p.capE + ec;
-    if (p.eLevel[eoa] || p.eLevel[eoc]) continue;
-    const int i1 = p.poseIndex[(size_t)w * p.capKf + p.eKf[eoa]], i2 = p.poseIndex[(size_t)w * p.capKf + p.eKf[eoc]];
-    if (i1 < 0 || i2 < 0 || i1 < i2) continue;  // lower triangle of block rows only
-    const int r = en / 6, c = en - r * 6;
-    if (i1 == i2 && c > r) continue;  // diagonal blocks: only the lower entries are read by the Cholesky
-    const double* Wa = p.W + eoa * 18 + r * 3;
-    const double* Wc = p.W + eoc * 18 + c * 3;
-    // (W_a Dinv W_c^T)(r,c)
-    const double y0 = Wa[0] * Di[0] + Wa[1] * Di[3] + Wa[2] * Di[6];
-    const double y1 = Wa[0] * Di[1] + Wa[1] * Di[4] + Wa[2] * Di[7];
-    const double y2 = Wa[0] * Di[2] + Wa[1] * Di[5] + Wa[2] * Di[8];
-    const double v = y0 * Wc[0] + y1 * Wc[1] + y2 * Wc[2];
-    atomicAdd(&S[(size_t)(i1 * 6 + r) * p.ldS + (i2 * 6 + c)], -v);
+  p.db[mo * 3 + 0] = Di[0] * bl[0] + Di[1] * bl[1] + Di[2] * bl[2];
+  p.db[mo * 3 + 1] = Di[3] * bl[0] + Di[4] * bl[1] + Di[5] * bl[2];
+  p.db[mo * 3 + 2] = Di[6] * bl[0] + Di[7] * bl[1] + Di[8] * bl[2];
+}
+
+__global__ void __launch_bounds__(128) k_schur_pose(BaPtrs p) {
+  __shared__ double sm[32];
+  __shared__ double out[6];
+  const int w = blockIdx.y;
+  const BaState& st = p.st[w];
+  if (!st.active) return;
+  const BaWin W = p.win[w];
+  const int kf = blockIdx.x;
+  if (kf >= W.nKf) return;
+  const int pi = p.poseIndex[(size_t)w * p.capKf + kf];
+  if (pi < 0) return;
+  const int* ks = p.kfStart + (size_t)w * (p.capKf + 1);
+  const int* ke = p.kfEdges + (size_t)w * p.capE;
+  double r[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = ks[kf] + threadIdx.x; k < ks[kf + 1]; k += blockDim.x) {
+    const int e = ke[k];
+    const size_t eo = (size_t)w * p.capE + e;
+    if (p.eLevel[eo]) continue;
+    const size_t mo = (size_t)w * p.capMp + p.eMp[eo];
+    const double* Di = p.Dinv + mo * 9;
+    const double* d3 = p.db + mo * 3;
+    const double* Wb = p.W + eo * 18;
+    double* Yb = p.Y + eo * 18;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const double w0 = Wb[i * 3], w1 = Wb[i * 3 + 1], w2 = Wb[i * 3 + 2];
+      Yb[i * 3 + 0] = w0 * Di[0] + w1 * Di[3] + w2 * Di[6];
+      Yb[i * 3 + 1] = w0 * Di[1] + w1 * Di[4] + w2 * Di[7];
+      Yb[i * 3 + 2] = w0 * Di[2] + w1 * Di[5] + w2 * Di[8];
+      r[i] += w0 * d3[0] + w1 * d3[1] + w2 * d3[2];
+    }
   }
-  for (int it = lane; it < cnt * 6; it += 32) {
-    const int ia = it / 6, r = it - ia * 6;
-    const int ea = me[beg + ia];
-    const size_t eoa = (size_t)w * p.capE + ea;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const double s = block_sum(r[i], sm);
+    if (threadIdx.x == 0) out[i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const int n = W.nFree * 6;
+    const double* bp = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)pi * 6;
+    p.S[(size_t)w * p.ldS * p.ldS + (size_t)n * p.ldS + pi * 6 + threadIdx.x] = bp[threadIdx.x] - out[threadIdx.x];
+  }
+}
+
+__global__ void __launch_bounds__(64) k_schur_blocks(BaPtrs p) {
+  __shared__ double red[2][36];
+  const int w = blockIdx.y;
+  const BaState& st = p.st[w];
+  if (!st.active) return;
+  const BaWin W = p.win[w];
+  // decode lower-triangular block index -> (i1 >= i2)
+  const int t = blockIdx.x;
+  int i1 = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((i1 + 1) * (i1 + 2) / 2 <= t) i1++;
+  while (i1 * (i1 + 1) / 2 > t) i1--;
+  const int i2 = t - i1 * (i1 + 1) / 2;
+  if (i1 >= W.nFree) return;
+  const int kf1 = p.freeKf[(size_t)w * p.capKf + i1];
+  const int* ks = p.kfStart + (size_t)w * (p.capKf + 1);
+  const int* ke = p.kfEdges + (size_t)w * p.capE;
+  const int* lm = p.lmEdge + (size_t)w * p.capMp * p.capKf;
+  double acc[36];
+#pragma unroll
+  for (int k = 0; k < 36; k++) acc[k] = 0;
+  for (int k = ks[kf1] + threadIdx.x; k < ks[kf1 + 1]; k += blockDim.x) {
+    const int a = ke[k];
+    const size_t eoa = (size_t)w * p.capE + a;
     if (p.eLevel[eoa]) continue;
-    const int i1 = p.poseIndex[(size_t)w * p.capKf + p.eKf[eoa]];
-    if (i1 < 0) continue;
-    const double* Wa = p.W + eoa * 18 + r * 3;
-    atomicAdd(&S[(size_t)n * p.ldS + (i1 * 6 + r)], -(Wa[0] * db0 + Wa[1] * db1 + Wa[2] * db2));
+    const int c = lm[(size_t)p.eMp[eoa] * p.capKf + i2];
+    if (c < 0) continue;
+    const size_t eoc = (size_t)w * p.capE + c;
+    if (p.eLevel[eoc]) continue;
+    const double* Ya = p.Y + eoa * 18;
+    const double* Wc = p.W + eoc * 18;
+    double y[18], wc[18];
+#pragma unroll
+    for (int q = 0; q < 18; q++) {
+      y[q] = Ya[q];
+      wc[q] = Wc[q];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int cc = 0; cc < 6; cc++)
+        acc[r * 6 + cc] += y[r * 3] * wc[cc * 3] + y[r * 3 + 1] * wc[cc * 3 + 1] + y[r * 3 + 2] * wc[cc * 3 + 2];
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 36; k++) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 36) {
+    const int r = threadIdx.x / 6, cc = threadIdx.x - r * 6;
+    double base = 0;
+    if (i1 == i2) {
+      base = p.Hpp[((size_t)w * p.capKf + i1) * 36 + r * 6 + cc];
+      if (r == cc) base += st.lambda;
+    }
+    p.S[(size_t)w * p.ldS * p.ldS + (size_t)(i1 * 6 + r) * p.ldS + (i2 * 6 + cc)] = base - (red[0][threadIdx.x] + red[1][threadIdx.x]);
   }
 }
 
 // LinearSolver on the reduced camera system: blocked right-looking Cholesky (lower), one CTA per window.
 // The augmented last row carries b and ends up holding y = L^-1 b; then L^T x = y by blocked back substitution.
-__global__ void __launch_bounds__(1024) k_chol(BaPtrs p) {
+// Diagonal 32x32 blocks are factored by one warp with a row per lane in registers (shuffle broadcast), the panel solve
+// keeps each row in registers, the trailing update is 4x4 register tiled out of the shared-memory panel.
+constexpr int CHOL_T = 512;
+constexpr int CHOL_PP = CHOL_BS + 1;
+__global__ void __launch_bounds__(CHOL_T) k_chol(BaPtrs p) {
   extern __shared__ __align__(16) double dsm[];
   const int w = blockIdx.x;
   BaState& st = p.st[w];
@@ -542,63 +606,112 @@ __global__ void __launch_bounds__(1024) k_chol(BaPtrs p) {
   const BaWin W = p.win[w];
   const int n = W.nFree * 6, N1 = n + 1, ld = p.ldS;
   double* S = p.S + (size_t)w * ld * ld;
-  double* Dblk = dsm;                       // 32 x 33
-  double* panel = dsm + CHOL_BS * 33;       // (ld) x 32
-  double* xs = panel + (size_t)ld * CHOL_BS;  // ld
+  double* Dblk = dsm;                                // 32 x 33
+  double* panel = dsm + CHOL_BS * CHOL_PP;           // ld x 33
+  double* xs = panel + (size_t)(ld + 4) * CHOL_PP;   // ld
   __shared__ int fail;
-  const int tid = threadIdx.x, T = blockDim.x;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
   if (tid == 0) fail = 0;
   __syncthreads();
   for (int kb = 0; kb < n; kb += CHOL_BS) {
     const int wd = min(CHOL_BS, n - kb);
-    for (int idx = tid; idx < wd * wd; idx += T) {
-      const int r = idx / wd, c = idx - r * wd;
-      Dblk[r * 33 + c] = (c <= r) ? S[(size_t)(kb + r) * ld + kb + c] : 0.0;
+    for (int idx = tid; idx < CHOL_BS * CHOL_BS; idx += T) {
+      const int r = idx >> 5, c = idx & 31;
+      double v = (r == c) ? 1.0 : 0.0;  // identity padding for a short last block
+      if (r < wd && c < wd) v = (c <= r) ? S[(size_t)(kb + r) * ld + kb + c] : 0.0;
+      Dblk[r * CHOL_PP + c] = v;
     }
     __syncthreads();
     if (tid < 32) {
-      for (int j = 0; j < wd; j++) {
-        double d = Dblk[j * 33 + j];
-        for (int k = 0; k < j; k++) d -= Dblk[j * 33 + k] * Dblk[j * 33 + k];
-        if (!(d > 0.0) || !isfinite(d)) {
-          if (tid == 0) fail = 1;
-          d = 1.0;
+      double row[CHOL_BS];
+#pragma unroll
+      for (int c = 0; c < CHOL_BS; c++) row[c] = Dblk[lane * CHOL_PP + c];
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < CHOL_BS; j++) {
+        double djj = __shfl_sync(0xffffffffu, row[j], j);
+        if (!(djj > 0.0) || !isfinite(djj)) {
+          bad = true;
+          djj = 1.0;
         }
-        const double ljj = sqrt(d);
-        if (tid > j && tid < wd) {
-          double s = Dblk[tid * 33 + j];
-          for (int k = 0; k < j; k++) s -= Dblk[tid * 33 + k] * Dblk[j * 33 + k];
-          Dblk[tid * 33 + j] = s / ljj;
+        const double ljj = sqrt(djj);
+        if (lane == j) row[j] = ljj;
+        else if (lane > j) row[j] = row[j] / ljj;
+#pragma unroll
+        for (int k = j + 1; k < CHOL_BS; k++) {
+          const double lkj = __shfl_sync(0xffffffffu, row[j], k);  // L[k][j]
+          if (lane >= k) row[k] -= row[j] * lkj;
         }
-        __syncwarp();
-        if (tid == 0) Dblk[j * 33 + j] = ljj;
-        __syncwarp();
       }
+      if (bad && lane == 0) fail = 1;
+#pragma unroll
+      for (int c = 0; c < CHOL_BS; c++) Dblk[lane * CHOL_PP + c] = (c <= lane) ? row[c] : 0.0;
     }
     __syncthreads();
     for (int idx = tid; idx < wd * wd; idx += T) {
       const int r = idx / wd, c = idx - r * wd;
-      if (c <= r) S[(size_t)(kb + r) * ld + kb + c] = Dblk[r * 33 + c];
+      if (c <= r) S[(size_t)(kb + r) * ld + kb + c] = Dblk[r * CHOL_PP + c];
     }
     const int m = N1 - (kb + wd);  // rows below the diagonal block (including the augmented row)
-    for (int row = tid; row < m; row += T) {
-      const int i = kb + wd + row;
-      for (int c = 0; c < wd; c++) {
-        double v = S[(size_t)i * ld + kb + c];
-        for (int k = 0; k < c; k++) v -= panel[row * CHOL_BS + k] * Dblk[c * 33 + k];
-        v /= Dblk[c * 33 + c];
-        panel[row * CHOL_BS + c] = v;
-        S[(size_t)i * ld + kb + c] = v;
+    for (int rowi = tid; rowi < m; rowi += T) {
+      const int i = kb + wd + rowi;
+      double v[CHOL_BS];
+#pragma unroll
+      for (int c = 0; c < CHOL_BS; c++) v[c] = (c < wd) ? S[(size_t)i * ld + kb + c] : 0.0;
+#pragma unroll
+      for (int c = 0; c < CHOL_BS; c++) {
+        double a = v[c];
+#pragma unroll
+        for (int k = 0; k < c; k++) a -= v[k] * Dblk[c * CHOL_PP + k];
+        v[c] = a / Dblk[c * CHOL_PP + c];
+      }
+#pragma unroll
+      for (int c = 0; c < CHOL_BS; c++) {
+        panel[rowi * CHOL_PP + c] = v[c];
+        if (c < wd) S[(size_t)i * ld + kb + c] = v[c];
       }
     }
+    // zero the padding rows read by the 4x4 tiles
+    for (int idx = tid; idx < 4 * CHOL_PP; idx += T) panel[(m + idx / CHOL_PP) * CHOL_PP + idx % CHOL_PP] = 0.0;
     __syncthreads();
-    for (int pidx = tid; pidx < m * m; pidx += T) {
-      const int i = pidx / m, j = pidx - i * m;
-      if (j > i) continue;
-      if (kb + wd + j >= n) continue;  // column n (the augmented corner) is never needed
-      double acc = 0;
-      for (int k = 0; k < wd; k++) acc += panel[i * CHOL_BS + k] * panel[j * CHOL_BS + k];
-      S[(size_t)(kb + wd + i) * ld + kb + wd + j] -= acc;
+    const int mt = (m + 3) >> 2;
+    const int ntile = mt * (mt + 1) / 2;
+    for (int t = tid; t < ntile; t += T) {
+      int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+      while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+      while (ti * (ti + 1) / 2 > t) ti--;
+      const int tj = t - ti * (ti + 1) / 2;
+      double acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b2 = 0; b2 < 4; b2++) acc[a][b2] = 0;
+      const double* pa = panel + (size_t)(4 * ti) * CHOL_PP;
+      const double* pb = panel + (size_t)(4 * tj) * CHOL_PP;
+#pragma unroll 8
+      for (int k = 0; k < CHOL_BS; k++) {
+        double av[4], bv[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          av[a] = pa[a * CHOL_PP + k];
+          bv[a] = pb[a * CHOL_PP + k];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b2 = 0; b2 < 4; b2++) acc[a][b2] += av[a] * bv[b2];
+      }
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int i = 4 * ti + a;
+        if (i >= m) continue;
+#pragma unroll
+        for (int b2 = 0; b2 < 4; b2++) {
+          const int j = 4 * tj + b2;
+          if (j > i || kb + wd + j >= n) continue;  // lower triangle only; column n is never needed
+          S[(size_t)(kb + wd + i) * ld + kb + wd + j] -= acc[a][b2];
+        }
+      }
     }
     __syncthreads();
   }
@@ -608,23 +721,36 @@ __global__ void __launch_bounds__(1024) k_chol(BaPtrs p) {
   const int nblk = (n + CHOL_BS - 1) / CHOL_BS;
   for (int bk = nblk - 1; bk >= 0; bk--) {
     const int kb = bk * CHOL_BS, wd = min(CHOL_BS, n - kb);
-    for (int idx = tid; idx < wd * wd; idx += T) {
-      const int r = idx / wd, c = idx - r * wd;
-      Dblk[r * 33 + c] = (c <= r) ? S[(size_t)(kb + r) * ld + kb + c] : 0.0;
+    for (int idx = tid; idx < CHOL_BS * CHOL_BS; idx += T) {
+      const int r = idx >> 5, c = idx & 31;
+      double v = (r == c) ? 1.0 : 0.0;
+      if (r < wd && c < wd) v = (c <= r) ? S[(size_t)(kb + r) * ld + kb + c] : 0.0;
+      Dblk[r * CHOL_PP + c] = v;
     }
     __syncthreads();
-    if (tid == 0) {
-      for (int j = wd - 1; j >= 0; j--) {
-        double s = xs[kb + j];
-        for (int r = j + 1; r < wd; r++) s -= Dblk[r * 33 + j] * xs[kb + r];
-        xs[kb + j] = s / Dblk[j * 33 + j];
+    if (tid < 32) {
+      double col[CHOL_BS];  // column `lane` of L_D == row `lane` of L_D^T
+#pragma unroll
+      for (int r = 0; r < CHOL_BS; r++) col[r] = Dblk[r * CHOL_PP + lane];
+      double tv = (lane < wd) ? xs[kb + lane] : 0.0;
+#pragma unroll
+      for (int j = CHOL_BS - 1; j >= 0; j--) {
+        double xj = tv / col[j];                      // meaningful on lane j (col[j] = L[j][j])
+        xj = __shfl_sync(0xffffffffu, xj, j);
+        if (lane == j) tv = xj;
+        else if (lane < j) tv -= col[j] * xj;         // L[j][lane] * x_j
       }
+      if (lane < wd) xs[kb + lane] = tv;
     }
     __syncthreads();
     for (int c = tid; c < kb; c += T) {
-      double s = xs[c];
-      for (int r = 0; r < wd; r++) s -= S[(size_t)(kb + r) * ld + c] * xs[kb + r];
-      xs[c] = s;
+      double sacc = xs[c];
+      double lv[CHOL_BS];
+#pragma unroll
+      for (int r = 0; r < CHOL_BS; r++) lv[r] = (r < wd) ? S[(size_t)(kb + r) * ld + c] : 0.0;
+#pragma unroll
+      for (int r = 0; r < CHOL_BS; r++) sacc -= lv[r] * xs[kb + min(r, wd - 1)] * (r < wd ? 1.0 : 0.0);
+      xs[c] = sacc;
     }
     __syncthreads();
   }
@@ -892,10 +1018,12 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   A(&d.Hpp, B * max_kf * 36 * 8); A(&d.Hll, B * max_mp * 9 * 8);
   A(&d.b, B * ((size_t)max_kf * 6 + (size_t)max_mp * 3) * 8); A(&d.x, B * ((size_t)max_kf * 6 + (size_t)max_mp * 3) * 8);
   A(&d.Dinv, B * max_mp * 9 * 8); A(&d.S, B * (size_t)d.ldS * d.ldS * 8);
+  A(&d.db, B * max_mp * 3 * 8); A(&d.Y, B * max_edges * 18 * 8);
+  A(&d.lmEdge, B * (size_t)max_mp * max_kf * 4); A(&d.freeKf, B * max_kf * 4);
   A(&d.partChi, B * d.nPartE * 8); A(&d.partScale, B * d.nPartM * 8);
   A(&d.anyActive, 4);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&h->hAny, 4);
-  h->cholSmem = (size_t)(CHOL_BS * 33 + (size_t)d.ldS * CHOL_BS + d.ldS) * 8;
+  h->cholSmem = (size_t)(CHOL_BS * CHOL_PP + (size_t)(d.ldS + 4) * CHOL_PP + d.ldS) * 8;
   if (e == cudaSuccess && h->cholSmem > 48 * 1024)
     e = cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cholSmem);
   if (e != cudaSuccess) {
@@ -927,7 +1055,7 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
   B2S_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   if (stop && *stop) return B2S_ERR_ABORTED;  // src/Optimizer.cc:858-860: return without write-back
-  int maxE = 0, maxMp = 0, maxKf = 0, maxN = 0;
+  int maxE = 0, maxMp = 0, maxKf = 0, maxN = 0, maxFree = 0;
   std::vector<BaWin> wins(batch);
   std::vector<BaState> states(batch);
   // host staging (pageable -> device); a window is a few MB at most
@@ -943,7 +1071,7 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
       return B2S_ERR_BAD_ARG;
     }
     std::vector<double> pose((size_t)P.n_kf * PSTRIDE, 0.0);
-    std::vector<int> pidx(P.n_kf, -1);
+    std::vector<int> pidx(P.n_kf, -1), freeKf;
     int nFree = 0;
     for (int k = 0; k < P.n_kf; k++) {
       const float* T = P.Tcw + (size_t)k * 16;
@@ -954,7 +1082,10 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
       pose[(size_t)k * PSTRIDE + 4] = T[3];
       pose[(size_t)k * PSTRIDE + 5] = T[7];
       pose[(size_t)k * PSTRIDE + 6] = T[11];
-      if (!P.fixed[k]) pidx[k] = nFree++;
+      if (!P.fixed[k]) {
+        pidx[k] = nFree++;
+        freeKf.push_back(k);
+      }
     }
     std::vector<double> pts((size_t)P.n_mp * 3);
     for (size_t i = 0; i < pts.size(); i++) pts[i] = P.points[i];  // Converter::toVector3d
@@ -996,11 +1127,13 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
     S0.ni = 2;
     maxE = std::max(maxE, P.n_edges); maxMp = std::max(maxMp, P.n_mp); maxKf = std::max(maxKf, P.n_kf);
     maxN = std::max(maxN, nFree * 6 + 1);
+    maxFree = std::max(maxFree, nFree);
 #define UP(dst, vec, stride) \
   if (!(vec).empty()) B2S_CUDA(cudaMemcpyAsync((dst) + (size_t)w * (stride), (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, st))
     UP(d.pose, pose, (size_t)d.capKf * PSTRIDE);
     UP(d.pts, pts, (size_t)d.capMp * 3);
     UP(d.poseIndex, pidx, d.capKf);
+    UP(d.freeKf, freeKf, d.capKf);
     UP(d.eKf, eKf, d.capE); UP(d.eMp, eMp, d.capE);
     UP(d.eObs, eObs, (size_t)d.capE * 3); UP(d.eW, eW, d.capE);
     UP(d.eStereo, eSt, d.capE);
@@ -1008,6 +1141,7 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
     UP(d.kfStart, kfStart, d.capKf + 1); UP(d.kfEdges, kfEdges, d.capE);
 #undef UP
     B2S_CUDA(cudaMemsetAsync(d.eLevel + (size_t)w * d.capE, 0, d.capE, st));
+    B2S_CUDA(cudaMemsetAsync(d.lmEdge + (size_t)w * d.capMp * d.capKf, 0xFF, (size_t)P.n_mp * d.capKf * 4, st));
     B2S_CUDA(cudaMemsetAsync(d.chi2 + (size_t)w * d.capE, 0, (size_t)d.capE * 8, st));
     B2S_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
   }
@@ -1015,6 +1149,8 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
   B2S_CUDA(cudaMemcpyAsync(d.st, states.data(), batch * sizeof(BaState), cudaMemcpyHostToDevice, st));
   const int gE = std::max(1, div_up(maxE, 256)), gM = std::max(1, div_up(maxMp, 128));
   const int gRestore = std::max(1, div_up(std::max(maxMp * 3, maxKf * PSTRIDE), 256));
+  k_lm_edge<<<dim3(gE, batch), 256, 0, st>>>(d);
+  h->launches++;
   bool stopSent = false;
   for (int step = 0; step < 400; step++) {
     if (stop && *stop && !stopSent) {  // asynchronous abort (LocalMapping::InsertKeyFrame sets mbAbortBA)
@@ -1028,9 +1164,10 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
     k_build_landmarks<<<dim3(gM, batch), 128, 0, st>>>(d);
     k_build_poses<<<dim3(maxKf, batch), 128, 0, st>>>(d);
     k_control_begin<<<div_up(batch, 64), 64, 0, st>>>(d, batch);
-    k_schur_init<<<dim3(std::min(64, div_up(maxN * maxN, 256)), batch), 256, 0, st>>>(d);
-    k_schur<<<dim3(std::max(1, div_up(maxMp, 8)), batch), 256, 0, st>>>(d);
-    k_chol<<<batch, 1024, h->cholSmem, st>>>(d);
+    k_dinv<<<dim3(gM, batch), 128, 0, st>>>(d);
+    k_schur_pose<<<dim3(maxKf, batch), 128, 0, st>>>(d);
+    k_schur_blocks<<<dim3(std::max(1, maxFree * (maxFree + 1) / 2), batch), 64, 0, st>>>(d);
+    k_chol<<<batch, CHOL_T, h->cholSmem, st>>>(d);
     k_backsub<<<dim3(gM, batch), 128, 0, st>>>(d);
     k_update_poses<<<batch, 128, 0, st>>>(d);
     k_errors<<<dim3(gE, batch), 256, 0, st>>>(d, 1);
@@ -1039,7 +1176,7 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
     k_outliers<<<dim3(gE, batch), 256, 0, st>>>(d);
     B2S_CUDA(cudaMemsetAsync(d.anyActive, 0, 4, st));
     k_any_active<<<div_up(batch, 64), 64, 0, st>>>(d, batch);
-    h->launches += 14;
+    h->launches += 15;
     B2S_CUDA(cudaMemcpyAsync(h->hAny, d.anyActive, 4, cudaMemcpyDeviceToHost, st));
     B2S_CUDA(cudaStreamSynchronize(st));
     if (!*h->hAny) break;

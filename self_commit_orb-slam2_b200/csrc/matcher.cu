@@ -102,45 +102,65 @@ __global__ void k_rank_by_key(const int32_t* __restrict__ keyBase, const int32_t
 // SearchByBoW, stage 1: per keyframe-side row, K best frame-side candidates of the same vocabulary node
 // key = dist<<16 | j   (j ascending == the reference's candidate iteration order inside a node)
 // ------------------------------------------------------------------------------------------------
+// One thread per keyframe-side row (its descriptor and K-list live in registers); the frame-side descriptors of the pair
+// are staged once per CTA in shared memory and read as warp-wide broadcasts, so every distance costs
+// 8 XOR + 8 POPC + 8 IADD per lane and no cross-lane merge is needed.
+constexpr int BOW_TILE = 1024;  // frame-side descriptors per shared-memory stage (32 KB) + node ids (4 KB) + valid (1 KB)
 __global__ void __launch_bounds__(256) k_bow_topk(const uint8_t* __restrict__ descA, const int32_t* __restrict__ nodeA,
                                                   const uint8_t* __restrict__ validA, const int32_t* __restrict__ nAarr,
                                                   int capA, const uint8_t* __restrict__ descB,
                                                   const int32_t* __restrict__ nodeB, const uint8_t* __restrict__ validB,
                                                   const int32_t* __restrict__ nBarr, int capB,
                                                   uint32_t* __restrict__ topk, int32_t* __restrict__ candCnt) {
+  __shared__ __align__(32) uint32_t sB[BOW_TILE * 8];
+  __shared__ int32_t sNode[BOW_TILE];
+  __shared__ uint8_t sValid[BOW_TILE];
   const int pair = blockIdx.y;
   const int nA = nAarr[pair], nB = nBarr[pair];
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (i >= nA) return;
+  if ((int)(blockIdx.x * blockDim.x) >= nA) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t oa = (size_t)pair * capA, ob = (size_t)pair * capB;
+  const bool rowOk = (i < nA) && (!validA || validA[oa + i]);
+  u256 da;
+  int na = -1;
+  if (rowOk) {
+    da = ld_desc(descA + oa * 32, i);
+    na = nodeA[oa + i];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) da.w[k] = 0;
+  }
   uint32_t t[TOPK];
 #pragma unroll
   for (int k = 0; k < TOPK; k++) t[k] = EMPTY;
   int cnt = 0;
-  if (!validA || validA[oa + i]) {
-    const u256 da = ld_desc(descA + oa * 32, i);
-    const int na = nodeA[oa + i];
-    for (int j = lane; j < nB; j += 32) {
-      if (nodeB[ob + j] != na) continue;
-      if (validB && !validB[ob + j]) continue;
-      const u256 db = ld_desc(descB + ob * 32, j);
-      const int d = hamming256(da, db);
-      cnt++;
-      topk_insert(t, ((uint32_t)d << 16) | (uint32_t)j);
+  for (int j0 = 0; j0 < nB; j0 += BOW_TILE) {
+    const int tn = min(BOW_TILE, nB - j0);
+    __syncthreads();
+    const uint32_t* gB = reinterpret_cast<const uint32_t*>(descB + (ob + j0) * 32);
+    for (int q = threadIdx.x; q < tn * 8; q += blockDim.x) sB[q] = gB[q];
+    for (int q = threadIdx.x; q < tn; q += blockDim.x) {
+      sNode[q] = nodeB[ob + j0 + q];
+      sValid[q] = validB ? validB[ob + j0 + q] : 1;
+    }
+    __syncthreads();
+    if (rowOk) {
+      for (int j = 0; j < tn; j++) {
+        if (sNode[j] != na || !sValid[j]) continue;
+        const uint4 b0 = *reinterpret_cast<const uint4*>(&sB[j * 8]);
+        const uint4 b1 = *reinterpret_cast<const uint4*>(&sB[j * 8 + 4]);
+        const int d = __popc(da.w[0] ^ b0.x) + __popc(da.w[1] ^ b0.y) + __popc(da.w[2] ^ b0.z) + __popc(da.w[3] ^ b0.w) +
+                      __popc(da.w[4] ^ b1.x) + __popc(da.w[5] ^ b1.y) + __popc(da.w[6] ^ b1.z) + __popc(da.w[7] ^ b1.w);
+        cnt++;
+        topk_insert(t, ((uint32_t)d << 16) | (uint32_t)(j0 + j));
+      }
     }
   }
-  uint32_t out[TOPK];
-  topk_warp_merge(t, out);
-  cnt = warp_reduce_sum(cnt);
-  if (lane < TOPK) {
-    uint32_t v = EMPTY;
+  if (i < nA) {
 #pragma unroll
-    for (int k = 0; k < TOPK; k++)
-      if (k == lane) v = out[k];
-    topk[(oa + i) * TOPK + lane] = v;
+    for (int k = 0; k < TOPK; k++) topk[(oa + i) * TOPK + k] = t[k];
+    candCnt[oa + i] = cnt;
   }
-  if (lane == 0) candCnt[oa + i] = cnt;
 }
 
 // full rescan of row i against the still-unmatched candidates (exact fallback when the K-list runs dry)
@@ -150,7 +170,7 @@ __device__ void bow_rescan(const u256& da, int na, const uint8_t* descB, const i
   for (int j = lane; j < nB; j += 32) {
     if (nodeB[j] != na) continue;
     if (validB && !validB[j]) continue;
-    if (matchB[j] >= 0) continue;
+    if (__ldcg(&matchB[j]) >= 0) continue;
     const int d = hamming256(da, ld_desc(descB, j));
     if (d < b1) {
       b2 = b1;
@@ -178,8 +198,11 @@ __device__ void bow_rescan(const u256& da, int na, const uint8_t* descB, const i
   }
 }
 
-// stage 2: one warp per vocabulary node (the warp at the first sorted position of a node owns it); keyframe-side
-// rows of the node are resolved in ascending index order (:268 loop), exactly as the reference's greedy loop.
+// stage 2: one warp per vocabulary node (the warp at the first sorted position of a node owns it).  The reference's
+// greedy loop (:268) is sequential in the keyframe-side rows of a node; here 32 consecutive rows are resolved
+// speculatively, one per lane, against the current `matched` state, and the longest prefix of lanes whose decision
+// cannot have been changed by an earlier lane of the same block is committed — exactly the sequential result, in
+// ~1 round per 32 rows when rows rarely compete for the same frame feature.
 __global__ void __launch_bounds__(128) k_bow_resolve(const uint8_t* __restrict__ descA, const int32_t* __restrict__ nodeA,
                                                      const uint8_t* __restrict__ validA, const float* __restrict__ angA,
                                                      const int32_t* __restrict__ nAarr, int capA,
@@ -188,54 +211,94 @@ __global__ void __launch_bounds__(128) k_bow_resolve(const uint8_t* __restrict__
                                                      const int32_t* __restrict__ nBarr, int capB,
                                                      const int32_t* __restrict__ orderA, const uint32_t* __restrict__ topk,
                                                      const int32_t* __restrict__ candCnt, MatchParams mp,
-                                                     int32_t* __restrict__ matchB, int32_t* __restrict__ binB) {
+                                                     int32_t* matchB, int32_t* __restrict__ binB) {
   const int pair = blockIdx.y;
   const int nA = nAarr[pair], nB = nBarr[pair];
   const int lane = threadIdx.x & 31;
-  int r = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (r >= nA) return;
+  const int r0 = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r0 >= nA) return;
   const size_t oa = (size_t)pair * capA, ob = (size_t)pair * capB;
   const int32_t* order = orderA + oa;
   const int32_t* nodeAp = nodeA + oa;
-  const int node = nodeAp[order[r]];
-  if (r > 0 && nodeAp[order[r - 1]] == node) return;  // not the head of a node segment
+  const int node = nodeAp[order[r0]];
+  if (r0 > 0 && nodeAp[order[r0 - 1]] == node) return;  // not the head of a node segment
   int32_t* mB = matchB + ob;
-  for (; r < nA; r++) {
-    const int i = order[r];
-    if (nodeAp[i] != node) break;
-    if (validA && !validA[oa + i]) continue;  // no MapPoint / bad (:272-277)
-    // walk the K-list: first two entries whose frame feature is still unmatched (:288)
-    const uint32_t e = (lane < TOPK) ? topk[(oa + i) * TOPK + lane] : EMPTY;
-    const bool avail = (e != EMPTY) && (mB[e & 0xffff] < 0);
-    const unsigned am = __ballot_sync(0xffffffffu, avail);
-    const int listed = __popc(__ballot_sync(0xffffffffu, e != EMPTY));
-    int best1 = 256, idx1 = -1, best2 = 256;
-    const int navail = __popc(am);
-    const bool complete = candCnt[oa + i] <= TOPK;  // the list holds every candidate of the row
-    if (navail >= 2 || (complete && navail >= 0)) {
-      if (navail >= 1) {
-        const int l1 = __ffs(am) - 1;
-        const uint32_t e1 = __shfl_sync(0xffffffffu, e, l1);
-        best1 = (int)(e1 >> 16);
-        idx1 = (int)(e1 & 0xffff);
-        if (navail >= 2) {
-          const int l2 = __ffs(am & (am - 1)) - 1;
-          best2 = (int)(__shfl_sync(0xffffffffu, e, l2) >> 16);
+  for (int base = r0; base < nA; base += 32) {
+    // lane <-> row base+lane of the segment
+    const int r = base + lane;
+    int i = -1;
+    bool inSeg = false;
+    if (r < nA) {
+      i = order[r];
+      inSeg = nodeAp[i] == node;
+    }
+    const unsigned segMask = __ballot_sync(0xffffffffu, inSeg);
+    if (segMask == 0) break;
+    const int nrows = __popc(segMask);  // rows of this node are contiguous in sorted order -> a prefix of lanes
+    const bool rowOk = inSeg && (!validA || validA[oa + i]);  // no MapPoint / bad (:272-277)
+    uint32_t e[TOPK];
+#pragma unroll
+    for (int k = 0; k < TOPK; k++) e[k] = rowOk ? topk[(oa + i) * TOPK + k] : EMPTY;
+    const bool complete = rowOk ? (candCnt[oa + i] <= TOPK) : true;
+    int first = 0;  // lanes < first are committed
+    while (first < nrows) {
+      // speculative decision of every uncommitted lane against the current matched state
+      int best1 = 256, idx1 = -1, best2 = 256, idx2 = -1, navail = 0;
+      if (lane >= first && rowOk) {
+#pragma unroll
+        for (int k = 0; k < TOPK; k++) {
+          const uint32_t ek = e[k];
+          if (ek == EMPTY) continue;
+          const int j = (int)(ek & 0xffff);
+          if (__ldcg(&mB[j]) >= 0) continue;  // already matched (:288)
+          if (navail == 0) {
+            best1 = (int)(ek >> 16);
+            idx1 = j;
+          } else if (navail == 1) {
+            best2 = (int)(ek >> 16);
+            idx2 = j;
+          }
+          navail++;
         }
       }
-    } else {
-      const u256 da = ld_desc(descA + oa * 32, i);
-      bow_rescan(da, node, descB + ob * 32, nodeB + ob, validB ? validB + ob : nullptr, mB, nB, lane, best1, idx1, best2);
-    }
-    (void)listed;
-    const bool pass = mp.strictLt ? (best1 < mp.thLow) : (best1 <= mp.thLow);
-    if (pass && (float)best1 < __fmul_rn(mp.nnratio, (float)best2)) {
-      if (lane == 0) {
+      const bool hard = (lane >= first) && rowOk && !(navail >= 2 || complete);  // K-list ran dry: exact rescan
+      bool pass = mp.strictLt ? (best1 < mp.thLow) : (best1 <= mp.thLow);
+      bool accept = (lane >= first) && rowOk && !hard && pass && ((float)best1 < __fmul_rn(mp.nnratio, (float)best2));
+      const int pick = accept ? idx1 : -1;
+      bool dirty = hard;
+      for (int src = first; src < nrows; src++) {
+        const int pk = __shfl_sync(0xffffffffu, pick, src);
+        if (src < lane && pk >= 0 && (pk == idx1 || pk == idx2)) dirty = true;
+      }
+      const unsigned dm = __ballot_sync(0xffffffffu, dirty && lane >= first && lane < nrows);
+      const int d = dm ? (__ffs(dm) - 1) : nrows;  // first lane that must wait
+      if (lane >= first && lane < d && accept) {
         mB[idx1] = i;
         binB[ob + idx1] = mp.checkOri ? rot_bin(angA[oa + i], angB[ob + idx1]) : 0;
       }
       __syncwarp();
+      first = d;
+      if (first < nrows) {
+        const unsigned hm = __ballot_sync(0xffffffffu, hard);
+        if (hm & (1u << first)) {
+          // cooperative exact rescan of that row with all 32 lanes
+          const int ih = __shfl_sync(0xffffffffu, i, first);
+          const u256 da = ld_desc(descA + oa * 32, ih);
+          int b1, i1, b2;
+          bow_rescan(da, node, descB + ob * 32, nodeB + ob, validB ? validB + ob : nullptr, mB, nB, lane, b1, i1, b2);
+          const bool ps = mp.strictLt ? (b1 < mp.thLow) : (b1 <= mp.thLow);
+          if (ps && (float)b1 < __fmul_rn(mp.nnratio, (float)b2)) {
+            if (lane == 0) {
+              mB[i1] = ih;
+              binB[ob + i1] = mp.checkOri ? rot_bin(angA[oa + ih], angB[ob + i1]) : 0;
+            }
+          }
+          __syncwarp();
+          first++;
+        }
+      }
     }
+    if (nrows < 32) break;
   }
 }
 
@@ -709,7 +772,7 @@ extern "C" int b2s_search_by_bow_device(b2s_matcher* h, int batch, const uint8_t
   MatchParams mp{th_low, nnratio, strict_lt, check_ori};
   k_fill_i32<<<div_up(batch * capB, 256), 256, 0, st>>>(d_matchB, -1, (size_t)batch * capB);
   k_rank_by_key<<<dim3(div_up(capA, 128), batch), 128, 0, st>>>(d_nodeA, d_nA, capA, h->dOrder);
-  k_bow_topk<<<dim3(div_up(capA, 8), batch), 256, 0, st>>>(d_descA, d_nodeA, d_validA, d_nA, capA, d_descB, d_nodeB,
+  k_bow_topk<<<dim3(div_up(capA, 256), batch), 256, 0, st>>>(d_descA, d_nodeA, d_validA, d_nA, capA, d_descB, d_nodeB,
                                                            d_validB, d_nB, capB, h->dTopk, h->dCandCnt);
   k_bow_resolve<<<dim3(div_up(capA, 4), batch), 128, 0, st>>>(d_descA, d_nodeA, d_validA, d_angA, d_nA, capA, d_descB,
                                                               d_nodeB, d_validB, d_angB, d_nB, capB, h->dOrder, h->dTopk,

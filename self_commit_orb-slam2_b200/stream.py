@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import (ORBextractor, ORBmatcher, Optimizer, _check, _vp, ba_edge_dtype, keypoint_dtype, lib)
+from . import sharding
 
 KP_BYTES = keypoint_dtype.itemsize  # 28
 
@@ -26,6 +27,8 @@ class StereoStream:
         self.F, self.w, self.h = frames_per_step, width, height
         self.rank, self.world = rank, world
         self.dev = torch.device("cuda", device)
+        # a real (non-default) stream: the C ABI treats stream == NULL as "the handle's own stream"
+        self.stream = torch.cuda.Stream(self.dev)
         self.ex = ORBextractor(nfeatures, scale, nlevels, ini_th, min_th, max_width=max(width, 64),
                                max_height=max(height, 64), max_batch=2 * self.F, device=device)
         self.cap = self.ex.cap
@@ -57,23 +60,28 @@ class StereoStream:
     # ------------------------------------------------------------------ device-resident step
     def upload(self, imgs_host):
         """imgs_host: uint8 [2F, h, w] (L_0..L_F-1, R_0..R_F-1), ideally pinned."""
-        self.d_imgs.copy_(imgs_host, non_blocking=True)
+        with torch.cuda.stream(self.stream):
+            self.d_imgs.copy_(imgs_host, non_blocking=True)
 
     def step_device(self, run_ba=True):
+        with torch.cuda.stream(self.stream):
+            self._enqueue_extract_match()
+        ba_out = None
+        if run_ba and self.n_ba:  # own stream inside the solver; overlaps the work enqueued above
+            ba_out = self.opt.LocalBundleAdjustmentBatch([self.ba_problem] * self.n_ba)
+        return ba_out
+
+    def _enqueue_extract_match(self):
         F, cap = self.F, self.cap
-        st = torch.cuda.current_stream(self.dev).cuda_stream
+        st = self.stream.cuda_stream
         self.ex.extract_batch_device(self.d_imgs.data_ptr(), self.w * self.h, 2 * F, self.w, self.h, self.w,
                                      self.kps[1:].data_ptr(), self.desc[1:].data_ptr(), self.counts[1:].data_ptr(), cap,
                                      stream=st)
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(self.g_kps, self.kps[1:1 + F])
-            dist.all_gather_into_tensor(self.g_desc, self.desc[1:1 + F])
-            dist.all_gather_into_tensor(self.g_counts, self.counts[1:1 + F])
-            prev = (self.rank - 1) % self.world
-            self.kps[0].copy_(self.g_kps[prev, F - 1])
-            self.desc[0].copy_(self.g_desc[prev, F - 1])
-            self.counts[0:1].copy_(self.g_counts[prev, F - 1:F])
+            sharding.gather_records(self.kps[1:1 + F], self.desc[1:1 + F], self.counts[1:1 + F], self.g_kps, self.g_desc,
+                                    self.g_counts)
+            sharding.take_predecessor(self.g_kps, self.g_desc, self.g_counts, self.rank, self.world, self.kps[0],
+                                      self.desc[0], self.counts[0:1])
         else:  # ring inside the shard
             self.kps[0].copy_(self.kps[F])
             self.desc[0].copy_(self.desc[F])
@@ -87,10 +95,6 @@ class StereoStream:
                                           _vp(self.node[1:].data_ptr()), None, _vp(self.ang[1:].data_ptr()),
                                           _vp(self.counts[1:].data_ptr()), cap, 50, float(self.matcher.mfNNratio), 0, 1,
                                           _vp(self.match.data_ptr()), _vp(self.nmatch.data_ptr()), _vp(st)))
-        ba_out = None
-        if run_ba and self.n_ba:
-            ba_out = self.opt.LocalBundleAdjustmentBatch([self.ba_problem] * self.n_ba)
-        return ba_out
 
     # ------------------------------------------------------------------ end-to-end step through the host-buffer C ABI
     def step_host(self, imgs_host_np, run_ba=True):

@@ -89,3 +89,12 @@ def test_sincosf_device_matches_glibc(pkg, oracle):
         os_, oc = oracle.sincosf(x)
         bad += int((s.view(np.uint32) != os_.view(np.uint32)).sum()) + int((c.view(np.uint32) != oc.view(np.uint32)).sum())
     assert bad == 0
+
+
+def test_against_committed_golden(pkg):
+    """CUDA path vs tests/golden (no oracle, no /root/reference at run time)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "extract_640x480_seed3.npz"))
+    ex = pkg.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480)
+    k, d = ex(synth_image(640, 480, 3))
+    assert k.tobytes() == g["kps"].tobytes() and np.array_equal(d, g["desc"])

@@ -86,3 +86,20 @@ def test_search_by_projection(pkg, oracle, mode, cluster, th):
     assert n == on
     assert np.array_equal(match, om)
     assert n > 100
+
+
+def test_against_committed_golden(pkg):
+    import os
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    m = pkg.ORBmatcher(0.7, True)
+    for nodes in (100, 1):
+        g = np.load(os.path.join(G, "bow_2000_nodes%d.npz" % nodes))
+        A, nA, vA, aA, B, nB, aB = synth_descriptors(2000, seed=1234 + nodes, n_nodes=nodes)
+        n, match = m.SearchByBoW(A, nA, vA, aA, B, nB, aB)
+        assert n == int(g["n"]) and np.array_equal(match, g["match"])
+    g = np.load(os.path.join(G, "proj_seed21.npz"))
+    d = synth_projection(seed=21, cluster=False, th=7.0)
+    m9 = pkg.ORBmatcher(0.9, True)
+    n, match = m9.SearchByProjection(d["q"], d["kpx"], d["kpy"], d["octave"], d["angle"], d["uright"], d["occupied"],
+                                     d["desc"], d["geom"], d["th"], mode=0)
+    assert n == int(g["n"]) and np.array_equal(match, g["match"])

@@ -20,8 +20,8 @@ def test_stream_step_matches_oracle(pkg, oracle):
     ss = stream_mod.StereoStream(F, w, h, 2000, ba_problem=ba, ba_every=2)
     ss.upload(torch.from_numpy(imgs))
     ba_out = ss.step_device()
-    ss.ex.check()
     torch.cuda.synchronize()
+    ss.ex.check()
     counts_dev = ss.counts.cpu().numpy()
     nm_dev = ss.nmatch.cpu().numpy()
     match_dev = ss.match.cpu().numpy()
