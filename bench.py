@@ -222,14 +222,40 @@ def run_b200(args, rank, local_rank, world):
     dev_ms = float(t_all.item())
     value = world * F * args.steps / (dev_ms / 1e3)
 
+    # ---------------- phase breakdown (untimed extra passes, for DESIGN.md / profiles): extraction+matching alone, LocalBA alone
+    phase = {}
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(2):
+        ss.step_device(run_ba=False)
+    torch.cuda.synchronize()
+    phase["extract_match_ms"] = (time.perf_counter() - t1) * 500.0
+    # extractor stage timing without LocalBA competing for the SMs
+    L.b2s_extractor_set_timing(ss.ex._h, 1)
+    for _ in range(2):
+        ss.step_device(run_ba=False)
+    torch.cuda.synchronize()
+    stage_iso = (ctypes.c_double * 5)()
+    calls_iso = ctypes.c_longlong(0)
+    L.b2s_extractor_get_timing(ss.ex._h, stage_iso, ctypes.byref(calls_iso))
+    L.b2s_extractor_set_timing(ss.ex._h, 0)
+    phase["extractor_stage_ms_isolated"] = {k: stage_iso[i] / max(1, calls_iso.value) for i, k in enumerate(
+        ["resize_chain", "fast_cells", "quadtree", "blur", "orient_describe"])}
+    if ss.n_ba:
+        t1 = time.perf_counter()
+        ss.opt.LocalBundleAdjustmentBatch([ss.ba_problem] * ss.n_ba)
+        phase["local_ba_batch_ms"] = (time.perf_counter() - t1) * 1e3
+        phase["local_ba_windows"] = ss.n_ba
+
     # ---------------- end to end through the host-buffer C ABI (`e2e`)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    ss.step_host(imgs)  # warm
+    imgs_pinned = pinned.numpy()  # e2e inputs come from pinned host memory
+    ss.step_host(imgs_pinned)  # warm
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        n, nm, ba_out, _ = ss.step_host(imgs)
+        n, nm, ba_out, _ = ss.step_host(imgs_pinned)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -254,10 +280,12 @@ def run_b200(args, rank, local_rank, world):
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": ss.h2d_bytes_per_step(),
                 "d2h_bytes_per_step": ss.d2h_bytes_per_step(), "steps": e2e_steps},
         "gpu_launches": int(launches),
+        "phase_ms": phase,
         "clocks": clocks,
         "roofline": {"kernel": "k_fast_cells (per-cell FAST-9/16 score + NMS + dual threshold)", "bound": "hbm",
                      "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "traffic": None, "peak_source": peak_src, "launch_ms": fast_ms,
+                     "launch_ms_isolated": phase.get("extractor_stage_ms_isolated", {}).get("fast_cells"),
                      "algorithmic_bytes_per_launch": B_FAST_IMAGE * images_per_launch,
                      "extractor_all_stages": {"ms_per_launch_set": ex_ms,
                                               "achieved_GBps": B_STAGE_IMAGE * images_per_launch / (ex_ms * 1e-3) / 1e9

@@ -54,52 +54,86 @@ __global__ void __launch_bounds__(128) k_resize(ExtractGeom g, int l, uint8_t* _
 //     One CTA per 30-px cell of src/ORBextractor.cc:1089-1157 (cv::FAST on the cell ROI, :1126,1135).
 //     M = max over the 16 arcs of min|v-p| (same sign); corner at th <=> M > th; response = M-1.
 // ------------------------------------------------------------------------------------------------
-constexpr int FP = 72;  // smem pitch of the cell ROI (ROI width <= 66)
-constexpr int FR = 68;  // max ROI rows
-// Bresenham circle r=3 offsets (dx,dy) in OpenCV order
-#define B2S_CIRCLE(F) \
-  F(0, 0, 3) F(1, 1, 3) F(2, 2, 2) F(3, 3, 1) F(4, 3, 0) F(5, 3, -1) F(6, 2, -2) F(7, 1, -3) F(8, 0, -3) F(9, -1, -3) \
-      F(10, -2, -2) F(11, -3, -1) F(12, -3, 0) F(13, -3, 1) F(14, -2, 2) F(15, -1, 3)
+constexpr int FP = 80;   // byte pitch of the raw ROI / score map (ROI width <= 66, + alignment slack)
+constexpr int FR = 68;   // max ROI rows
+constexpr int PW = 37;   // word pitch of the packed pixel-pair planes (36 pairs + 1 pad word)
 
-__device__ __forceinline__ int fast_arc_strength(const uint8_t* c, int minTh) {
-  const int v = c[0];
-  int d[16];
-#define LD(k, dx, dy) d[k] = v - (int)c[(dy)*FP + (dx)];
-  B2S_CIRCLE(LD)
-#undef LD
-  // exact quick reject: every 9-arc holds one pixel of each opposite pair (k,k+8)
-  int dk = __vimin3_s32(max(d[0], d[8]), max(d[1], d[9]), max(d[2], d[10]));
-  dk = __vimin3_s32(dk, max(d[3], d[11]), max(d[4], d[12]));
-  dk = __vimin3_s32(dk, max(d[5], d[13]), max(d[6], d[14]));
-  dk = min(dk, max(d[7], d[15]));
-  int br = __vimax3_s32(min(d[0], d[8]), min(d[1], d[9]), min(d[2], d[10]));
-  br = __vimax3_s32(br, min(d[3], d[11]), min(d[4], d[12]));
-  br = __vimax3_s32(br, min(d[5], d[13]), min(d[6], d[14]));
-  br = max(br, min(d[7], d[15]));
-  if (dk <= minTh && -br <= minTh) return 0;
-  int t3n[16], t3x[16];
+// FAST-9/16 arc strength of a horizontal PIXEL PAIR in packed 16-bit lanes (DPX VIMNMX3.U16x2).
+// d'_k = 256 + v - p_k per lane (in [1,511], so one 32-bit subtract never borrows across lanes).
+// dark  strength = max_s min_{j<9} d'_{s+j} - 256 ; bright strength = 256 - min_s max_{j<9} d'_{s+j}.
+// Returns M(lo) | M(hi)<<16, each clamped at 0.  quick: exact reject through the 8 opposite pairs (k,k+8).
+__device__ __forceinline__ void fast_pair_load(const uint32_t* __restrict__ E, const uint32_t* __restrict__ O, int wrd,
+                                               uint32_t (&d)[16]) {
+  // center pair starts at odd ROI x = 2*wrd+1 -> O plane word `wrd`.  Neighbour (dx,dy): dx even -> O[wrd + dx/2],
+  // dx odd -> E[wrd + (dx+1)/2]; row offset dy*PW.
+  const uint32_t vb = O[wrd] + 0x01000100u;
+  d[0] = vb - O[3 * PW + wrd];        // ( 0, 3)
+  d[1] = vb - E[3 * PW + wrd + 1];    // ( 1, 3)
+  d[2] = vb - O[2 * PW + wrd + 1];    // ( 2, 2)
+  d[3] = vb - E[1 * PW + wrd + 2];    // ( 3, 1)
+  d[4] = vb - E[wrd + 2];             // ( 3, 0)
+  d[5] = vb - E[-1 * PW + wrd + 2];   // ( 3,-1)
+  d[6] = vb - O[-2 * PW + wrd + 1];   // ( 2,-2)
+  d[7] = vb - E[-3 * PW + wrd + 1];   // ( 1,-3)
+  d[8] = vb - O[-3 * PW + wrd];       // ( 0,-3)
+  d[9] = vb - E[-3 * PW + wrd];       // (-1,-3)
+  d[10] = vb - O[-2 * PW + wrd - 1];  // (-2,-2)
+  d[11] = vb - E[-1 * PW + wrd - 1];  // (-3,-1)
+  d[12] = vb - E[wrd - 1];            // (-3, 0)
+  d[13] = vb - E[1 * PW + wrd - 1];   // (-3, 1)
+  d[14] = vb - O[2 * PW + wrd - 1];   // (-2, 2)
+  d[15] = vb - E[3 * PW + wrd];       // (-1, 3)
+}
+
+// exact reject through the 8 opposite pairs (k,k+8): true if either lane can still be a corner at minTh
+__device__ __forceinline__ bool fast_pair_quick(const uint32_t (&d)[16], int minTh) {
+  uint32_t dk = __vimin3_u16x2(__vmaxu2(d[0], d[8]), __vmaxu2(d[1], d[9]), __vmaxu2(d[2], d[10]));
+  dk = __vimin3_u16x2(dk, __vmaxu2(d[3], d[11]), __vmaxu2(d[4], d[12]));
+  dk = __vimin3_u16x2(dk, __vmaxu2(d[5], d[13]), __vmaxu2(d[6], d[14]));
+  dk = __vminu2(dk, __vmaxu2(d[7], d[15]));
+  uint32_t br = __vimax3_u16x2(__vminu2(d[0], d[8]), __vminu2(d[1], d[9]), __vminu2(d[2], d[10]));
+  br = __vimax3_u16x2(br, __vminu2(d[3], d[11]), __vminu2(d[4], d[12]));
+  br = __vimax3_u16x2(br, __vminu2(d[5], d[13]), __vminu2(d[6], d[14]));
+  br = __vmaxu2(br, __vminu2(d[7], d[15]));
+  // lane passes if dk-256 > minTh or 256-br > minTh
+  const uint32_t thHi = (uint32_t)(256 + minTh) * 0x00010001u, thLo = (uint32_t)(256 - minTh) * 0x00010001u;
+  return (__vcmpgtu2(dk, thHi) | __vcmpgtu2(thLo, br)) != 0u;
+}
+
+// M(lo) | M(hi)<<16 : max over the 16 arcs of min|v-p| (same sign), clamped at 0
+__device__ __forceinline__ uint32_t fast_pair_full(const uint32_t (&d)[16]) {
+  uint32_t t3n[16], t3x[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) {
-    t3n[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-    t3x[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    t3n[k] = __vimin3_u16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    t3x[k] = __vimax3_u16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
   }
-  int dark = -512, bright = 512;
+  uint32_t dark = 0u, bright = 0xFFFFFFFFu;
 #pragma unroll
-  for (int s = 0; s < 16; s++) {
-    dark = max(dark, __vimin3_s32(t3n[s], t3n[(s + 3) & 15], t3n[(s + 6) & 15]));
-    bright = min(bright, __vimax3_s32(t3x[s], t3x[(s + 3) & 15], t3x[(s + 6) & 15]));
+  for (int sft = 0; sft < 16; sft += 2) {
+    const uint32_t a0 = __vimin3_u16x2(t3n[sft], t3n[(sft + 3) & 15], t3n[(sft + 6) & 15]);
+    const uint32_t a1 = __vimin3_u16x2(t3n[sft + 1], t3n[(sft + 4) & 15], t3n[(sft + 7) & 15]);
+    dark = __vimax3_u16x2(dark, a0, a1);
+    const uint32_t b0 = __vimax3_u16x2(t3x[sft], t3x[(sft + 3) & 15], t3x[(sft + 6) & 15]);
+    const uint32_t b1 = __vimax3_u16x2(t3x[sft + 1], t3x[(sft + 4) & 15], t3x[(sft + 7) & 15]);
+    bright = __vimin3_u16x2(bright, b0, b1);
   }
-  return __vimax3_s32(dark, -bright, 0);
+  const int dl = (int)(dark & 0xffffu) - 256, dh = (int)(dark >> 16) - 256;
+  const int bl = 256 - (int)(bright & 0xffffu), bh = 256 - (int)(bright >> 16);
+  const int Ml = __vimax3_s32(dl, bl, 0), Mh = __vimax3_s32(dh, bh, 0);
+  return (uint32_t)Ml | ((uint32_t)Mh << 16);
 }
 
 __global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t* __restrict__ pyr,
                                                     uint32_t* __restrict__ candXY, uint32_t* __restrict__ candKey,
                                                     uint8_t* __restrict__ candResp, int32_t* __restrict__ candCount,
                                                     int32_t* __restrict__ status) {
-  __shared__ __align__(16) uint8_t tile[FR * FP];
-  __shared__ __align__(16) uint8_t score[FR * FP];
+  __shared__ __align__(16) uint8_t raw[FR * FP];  // staged ROI bytes; reused as the score map once the planes exist
+  uint8_t* score = raw;
+  __shared__ uint32_t planeE[FR * PW];
+  __shared__ uint32_t planeO[FR * PW];
   __shared__ uint32_t list[1024];
-  __shared__ int sN, sHi, sBase, sEmit;
+  __shared__ int sN, sHi, sBase, sEmit, sPass;
   const int b = blockIdx.y;
   const int cid = blockIdx.x;
   int l = 0;
@@ -117,36 +151,98 @@ __global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t
   if (maxX > L.maxBX) maxX = L.maxBX;
   const int rw = maxX - iniX, rh = maxY - iniY;
   if (rw < 7 || rh < 7) return;
-  const int tid = threadIdx.x;
-  const uint8_t* src = pyr + (size_t)b * g.pyrBytes + L.off + (size_t)iniY * L.pitch + iniX;
-  for (int idx = tid; idx < rh * FP; idx += 128) {
-    const int y = idx / FP, x = idx - y * FP;
-    tile[idx] = (x < rw) ? src[(size_t)y * L.pitch + x] : 0;
-    score[idx] = 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- stage the ROI (plus up to 4 columns of slack on the right) with aligned 32-bit loads
+  const int a0 = iniX & 3;                       // ROI pixel x lives at raw column x + a0
+  const int nWords = (a0 + rw + 4 + 3) >> 2;     // <= 18
+  const uint8_t* srcRow = pyr + (size_t)b * g.pyrBytes + L.off + (size_t)iniY * L.pitch + (iniX - a0);
+  for (int r = warp; r < rh; r += 4) {
+    if (lane < nWords) {
+      const int gx = (iniX - a0) + lane * 4;
+      uint32_t wv = 0;
+      if (gx + 3 < L.pitch) wv = *reinterpret_cast<const uint32_t*>(srcRow + (size_t)r * L.pitch + lane * 4);
+      *reinterpret_cast<uint32_t*>(&raw[r * FP + lane * 4]) = wv;
+    }
   }
   if (tid == 0) {
     sN = 0;
     sHi = 0;
+    sPass = 0;
   }
   __syncthreads();
+  // ---- packed pixel-pair planes: E[r][i] = (pix 2i, pix 2i+1), O[r][i] = (pix 2i+1, pix 2i+2)
+  const int nPairW = (rw + 4) >> 1;  // words per plane row that are ever read (<= 35)
+  for (int r = warp; r < rh; r += 4) {
+    for (int i = lane; i < nPairW; i += 32) {
+      const uint8_t* q = &raw[r * FP + a0 + 2 * i];
+      const uint32_t p0 = q[0], p1 = q[1], p2 = q[2];
+      planeE[r * PW + i] = p0 | (p1 << 16);
+      planeO[r * PW + i] = p1 | (p2 << 16);
+    }
+  }
+  __syncthreads();
+  for (int q = tid; q < rh * (FP / 4); q += 128) reinterpret_cast<uint32_t*>(score)[q] = 0u;  // raw -> score map
+  __syncthreads();
+  // ---- arc strength, two pixels per thread.  Pass 1: load the 16 circle pairs and run the exact quick reject on every
+  // pair; survivors (a few percent) go to a compact list.  Pass 2: the full 16-arc evaluation runs densely on the list.
   const int iw = rw - 6, ih = rh - 6;
-  for (int p = tid; p < iw * ih; p += 128) {
-    const int y = p / iw + 3, x = p - (y - 3) * iw + 3;
-    const int M = fast_arc_strength(&tile[y * FP + x], g.minTh);
-    score[y * FP + x] = (uint8_t)min(M, 255);
+  const int npair = (iw + 1) >> 1;            // pairs start at ROI x = 3, 5, 7, ...
+  const int ppr = (npair <= 16) ? 16 : 32;    // lanes per row slot
+  const int rowsPerPass = 4 * (32 / ppr);
+  const int myRow = warp * (32 / ppr) + (ppr == 16 ? (lane >> 4) : 0);
+  const int myPair = (ppr == 16) ? (lane & 15) : lane;
+  for (int y0 = 0; y0 < ih; y0 += rowsPerPass) {
+    const int y = y0 + myRow + 3;
+    if (y < rh - 3 && myPair < npair) {
+      uint32_t d[16];
+      fast_pair_load(&planeE[y * PW], &planeO[y * PW], myPair + 1, d);  // x = 2*wrd+1 = 3 + 2*myPair
+      if (fast_pair_quick(d, g.minTh)) {
+        const int slot = atomicAdd(&sPass, 1);
+        if (slot < 1024) {
+          list[slot] = (uint32_t)myPair | ((uint32_t)y << 8);
+        } else {  // list full (only possible for very large cells): evaluate in place
+          const uint32_t M2 = fast_pair_full(d);
+          const int x = 3 + 2 * myPair;
+          score[y * FP + x] = (uint8_t)min((int)(M2 & 0xffffu), 255);
+          if (x + 1 < rw - 3) score[y * FP + x + 1] = (uint8_t)min((int)(M2 >> 16), 255);
+        }
+      }
+    }
   }
   __syncthreads();
-  // 3x3 NMS inside the cell's detectable area (rim scores are 0 == "not a corner" in OpenCV's buffers)
-  for (int p = tid; p < iw * ih; p += 128) {
-    const int y = p / iw + 3, x = p - (y - 3) * iw + 3;
-    const uint8_t* s = &score[y * FP + x];
-    const int M = s[0];
-    if (M <= g.minTh) continue;
-    const int nb = max(max(max(s[-FP - 1], s[-FP]), max(s[-FP + 1], s[-1])), max(max(s[1], s[FP - 1]), max(s[FP], s[FP + 1])));
-    if (M > nb) {
-      const int slot = atomicAdd(&sN, 1);
-      if (M > g.iniTh) atomicAdd(&sHi, 1);
-      if (slot < 1024) list[slot] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)M << 16);
+  {
+    const int nPass = min(sPass, 1024);
+    for (int k = tid; k < nPass; k += 128) {
+      const uint32_t e = list[k];
+      const int pr = e & 0xff, y = e >> 8;
+      uint32_t d[16];
+      fast_pair_load(&planeE[y * PW], &planeO[y * PW], pr + 1, d);
+      const uint32_t M2 = fast_pair_full(d);
+      const int x = 3 + 2 * pr;
+      score[y * FP + x] = (uint8_t)min((int)(M2 & 0xffffu), 255);
+      if (x + 1 < rw - 3) score[y * FP + x + 1] = (uint8_t)min((int)(M2 >> 16), 255);
+    }
+  }
+  __syncthreads();
+  // ---- 3x3 NMS inside the cell's detectable area (rim scores are 0 == "not a corner" in OpenCV's buffers)
+  for (int y0 = 0; y0 < ih; y0 += rowsPerPass) {
+    const int y = y0 + myRow + 3;
+    if (y < rh - 3 && myPair < npair) {
+#pragma unroll
+      for (int h2 = 0; h2 < 2; h2++) {
+        const int x = 3 + 2 * myPair + h2;
+        if (x >= rw - 3) continue;
+        const uint8_t* sc = &score[y * FP + x];
+        const int M = sc[0];
+        if (M <= g.minTh) continue;
+        const int nb =
+            max(max(max(sc[-FP - 1], sc[-FP]), max(sc[-FP + 1], sc[-1])), max(max(sc[1], sc[FP - 1]), max(sc[FP], sc[FP + 1])));
+        if (M > nb) {
+          const int slot = atomicAdd(&sN, 1);
+          if (M > g.iniTh) atomicAdd(&sHi, 1);
+          if (slot < 1024) list[slot] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)M << 16);
+        }
+      }
     }
   }
   __syncthreads();
@@ -529,48 +625,86 @@ __global__ void __launch_bounds__(256) k_quadtree(ExtractGeom g, int capMax, con
 
 // ------------------------------------------------------------------------------------------------
 // K5a: GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101, OpenCV-4 fixed point (Q8 taps, one final rounding).
-//      src/ORBextractor.cc:1626-1634.  64x32 output tile per CTA, separable through shared memory.
+//      src/ORBextractor.cc:1626-1634.  Each lane owns 4 consecutive columns and marches down a 32-row strip:
+//      one coalesced 32-bit load per input row (+2 shuffles for the neighbours' words), the horizontal 7 taps are
+//      two DP4A per pixel on byte-aligned windows (PRMT), the vertical 7 taps run on a register window of the last
+//      7 horizontal sums, and every output row is one coalesced 32-bit store per lane.
 // ------------------------------------------------------------------------------------------------
-constexpr int BT_W = 64, BT_H = 32, BT_P = 72;
+constexpr int BL_ROWS = 32;        // output rows per warp strip
+constexpr int BL_COLS = 128;       // columns per warp (32 lanes x 4)
 __device__ __forceinline__ int reflect101(int p, int n) {
   if (n == 1) return 0;
   while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * (n - 1) - p;
   return p;
 }
 
-__global__ void __launch_bounds__(256) k_blur(ExtractGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
-  __shared__ __align__(16) uint8_t in[(BT_H + 6) * BT_P];
-  __shared__ __align__(16) uint16_t Hs[(BT_H + 6) * BT_W];
+__global__ void __launch_bounds__(128) k_blur(ExtractGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
   const int b = blockIdx.y;
   int l = 0;
   while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].blurTileStart) l++;
   const LevelGeom& L = g.lv[l];
-  const int t = blockIdx.x - L.blurTileStart;
-  const int ty = t / L.blurTilesX, tx = t - ty * L.blurTilesX;
-  const int ox = tx * BT_W, oy = ty * BT_H;
+  const int lane = threadIdx.x & 31;
+  const int task = (blockIdx.x - L.blurTileStart) * 4 + (threadIdx.x >> 5);
+  if (task >= L.blurTilesX * L.blurTilesY) return;
+  const int ty = task / L.blurTilesX, tx = task - ty * L.blurTilesX;
+  const int x0 = tx * BL_COLS + lane * 4, oy = ty * BL_ROWS;
   const uint8_t* src = pyr + (size_t)b * g.pyrBytes + L.off;
   uint8_t* dst = blur + (size_t)b * g.pyrBytes + L.off;
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < (BT_H + 6) * (BT_W + 6); idx += 256) {
-    const int r = idx / (BT_W + 6), c = idx - r * (BT_W + 6);
-    const int sy = reflect101(oy + r - 3, L.h), sx = reflect101(ox + c - 3, L.w);
-    in[r * BT_P + c] = src[(size_t)sy * L.pitch + sx];
-  }
-  __syncthreads();
-  for (int idx = tid; idx < (BT_H + 6) * BT_W; idx += 256) {
-    const int r = idx / BT_W, c = idx - r * BT_W;
-    const uint8_t* q = &in[r * BT_P + c];
-    Hs[idx] = (uint16_t)(18 * (q[0] + q[6]) + 34 * (q[1] + q[5]) + 48 * (q[2] + q[4]) + 56 * q[3]);
-  }
-  __syncthreads();
-  for (int idx = tid; idx < BT_H * BT_W; idx += 256) {
-    const int r = idx / BT_W, c = idx - r * BT_W;
-    const int x = ox + c, y = oy + r;
-    if (x >= L.w || y >= L.h) continue;
-    const uint16_t* q = &Hs[r * BT_W + c];
-    const uint32_t acc = 18u * (q[0] + q[6 * BT_W]) + 34u * (q[BT_W] + q[5 * BT_W]) + 48u * (q[2 * BT_W] + q[4 * BT_W]) +
-                         56u * q[3 * BT_W];
-    dst[(size_t)y * L.pitch + x] = (uint8_t)((acc + 32768u) >> 16);
+  const int Wd = L.w, Hd = L.h;
+  const bool laneIn = x0 < L.pitch;                    // this lane's own word exists in the padded row
+  int hw[7][4];
+  // left / right border handling without per-byte loops: reflect101 of the 12-byte window x0-4 .. x0+7
+  const bool leftEdge = (x0 == 0);
+  const int nValid = Wd - x0;                  // pixels of this lane's window that exist, counted from x0
+  const bool rightEdge = laneIn && (nValid < 8) && (x0 < Wd);  // x0+7 >= Wd : some of bytes 4..11 are beyond the image
+#pragma unroll 1
+  for (int i0 = 0; i0 < BL_ROWS + 6; i0 += 7) {
+#pragma unroll
+    for (int u = 0; u < 7; u++) {
+      const int i = i0 + u;
+      if (i < BL_ROWS + 6) {  // warp-uniform
+        const int sy = reflect101(oy - 3 + i, Hd);
+        const uint8_t* row = src + (size_t)sy * L.pitch;
+        uint32_t w1 = laneIn ? *reinterpret_cast<const uint32_t*>(row + x0) : 0u;
+        uint32_t w0 = __shfl_up_sync(0xffffffffu, w1, 1);
+        uint32_t w2 = __shfl_down_sync(0xffffffffu, w1, 1);
+        if (lane == 0) w0 = (x0 >= 4) ? *reinterpret_cast<const uint32_t*>(row + x0 - 4) : 0u;
+        if (lane == 31) w2 = (x0 + 4 < L.pitch) ? *reinterpret_cast<const uint32_t*>(row + x0 + 4) : 0u;
+        if (leftEdge) w0 = __byte_perm(w1, w2, 0x1234);  // pixels 4,3,2,1 (reflect101 of -4..-1)
+        if (rightEdge) {                                   // few lanes per row: rebuild bytes 4..11 by reflection
+          uint32_t ww1 = 0u, ww2 = 0u;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            int px = x0 + k;
+            px = (px >= Wd) ? 2 * (Wd - 1) - px : px;
+            ww1 |= (uint32_t)row[px] << (8 * k);
+            int px2 = x0 + 4 + k;
+            px2 = (px2 >= Wd) ? 2 * (Wd - 1) - px2 : px2;
+            ww2 |= (uint32_t)row[px2] << (8 * k);
+          }
+          w1 = ww1;
+          w2 = ww2;
+        }
+        const uint32_t KA = 0x38302212u, KB = 0x00122230u;  // taps (18,34,48,56) and (48,34,18,0)
+        hw[u][0] = (int)__dp4a(__byte_perm(w1, w2, 0x4321), KB, __dp4a(__byte_perm(w0, w1, 0x4321), KA, 0u));
+        hw[u][1] = (int)__dp4a(__byte_perm(w1, w2, 0x5432), KB, __dp4a(__byte_perm(w0, w1, 0x5432), KA, 0u));
+        hw[u][2] = (int)__dp4a(__byte_perm(w1, w2, 0x6543), KB, __dp4a(__byte_perm(w0, w1, 0x6543), KA, 0u));
+        hw[u][3] = (int)__dp4a(w2, KB, __dp4a(w1, KA, 0u));
+        if (i >= 6) {
+          const int y = oy + i - 6;
+          uint32_t outw = 0;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            // the window holds rows i-6..i at slots (u+1)%7 .. u
+            const int q0 = hw[(u + 1) % 7][j], q1 = hw[(u + 2) % 7][j], q2 = hw[(u + 3) % 7][j], q3 = hw[(u + 4) % 7][j],
+                      q4 = hw[(u + 5) % 7][j], q5 = hw[(u + 6) % 7][j], q6 = hw[u][j];
+            const uint32_t acc = 18u * (uint32_t)(q0 + q6) + 34u * (uint32_t)(q1 + q5) + 48u * (uint32_t)(q2 + q4) + 56u * (uint32_t)q3;
+            outw |= ((acc + 32768u) >> 16) << (8 * j);
+          }
+          if (y < Hd && x0 < Wd) *reinterpret_cast<uint32_t*>(dst + (size_t)y * L.pitch + x0) = outw;
+        }
+      }
+    }
   }
 }
 
@@ -819,7 +953,7 @@ static int build_geometry(b2s_extractor* h, int W, int H) {
     }
     L.wCell = (int)ceilf(width / L.nCols);
     L.hCell = (int)ceilf(height / L.nRows);
-    if (L.wCell + 6 > FP - 4 || L.hCell + 6 > FR || L.wCell > 63 || L.hCell > 63) {
+    if (L.wCell + 6 > 66 || L.hCell + 6 > FR || L.wCell > 63 || L.hCell > 63) {
       set_error("cell %dx%d at level %d exceeds the kernel tile", L.wCell, L.hCell, l);
       return B2S_ERR_BAD_ARG;
     }
@@ -841,9 +975,9 @@ static int build_geometry(b2s_extractor* h, int W, int H) {
     L.scale = h->scale[l];
     L.kpsize = (float)(int)(kPatch * h->scale[l]);
     L.blurTileStart = tileStart;
-    L.blurTilesX = div_up(L.w, BT_W);
-    L.blurTilesY = div_up(L.h, BT_H);
-    tileStart += L.blurTilesX * L.blurTilesY;
+    L.blurTilesX = div_up(L.w, BL_COLS);  // warp tasks: 128 columns x 32 rows each, 4 per CTA
+    L.blurTilesY = div_up(L.h, BL_ROWS);
+    tileStart += div_up(L.blurTilesX * L.blurTilesY, 4);
     L.rxOff = rxOff;
     L.ryOff = ryOff;
     if (l > 0) {
@@ -932,7 +1066,7 @@ static int run_pipeline(b2s_extractor* h, int batch, b2s_keypoint* dKps, uint8_t
                                                        d.candCount, d.selXYR, d.selCount, d.status);
   h->launches++;
   if (tm) cudaEventRecord(h->ev[3], st);
-  k_blur<<<dim3(g.totalBlurTiles, batch), 256, 0, st>>>(g, d.pyr, d.blur);
+  k_blur<<<dim3(g.totalBlurTiles, batch), 128, 0, st>>>(g, d.pyr, d.blur);
   h->launches++;
   if (tm) cudaEventRecord(h->ev[4], st);
   k_orient_describe<<<dim3(div_up(g.totalSelCap, 8), batch), 256, 0, st>>>(g, d.pyr, d.blur, d.selXYR, d.selCount, dKps,
@@ -1186,6 +1320,22 @@ extern "C" int b2s_extract_batch(b2s_extractor* h, const uint8_t* const* imgs, i
                                height, cudaMemcpyHostToDevice, h->stream));
   }
   const int icap = h->outCap;
+  if (cap <= icap) {
+    // records are produced with the caller's stride and copied straight into the caller's arrays (fast when those
+    // are pinned; pageable memory is staged by the driver)
+    rc = run_pipeline(h, batch, h->d.outKps, h->d.outDesc, h->d.outCounts, cap, h->stream);
+    if (rc != B2S_OK) return rc;
+    B2S_CUDA(cudaMemcpyAsync(kps, h->d.outKps, (size_t)batch * cap * sizeof(b2s_keypoint), cudaMemcpyDeviceToHost,
+                             h->stream));
+    B2S_CUDA(cudaMemcpyAsync(desc, h->d.outDesc, (size_t)batch * cap * 32, cudaMemcpyDeviceToHost, h->stream));
+    B2S_CUDA(cudaMemcpyAsync(h->hCounts, h->d.outCounts, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
+    B2S_CUDA(cudaMemcpyAsync(h->hStatus, h->d.status, 4, cudaMemcpyDeviceToHost, h->stream));
+    B2S_CUDA(cudaStreamSynchronize(h->stream));
+    rc = check_status(h);
+    if (rc != B2S_OK) return rc;
+    for (int b = 0; b < batch; b++) n_out[b] = h->hCounts[b];
+    return B2S_OK;
+  }
   rc = run_pipeline(h, batch, h->d.outKps, h->d.outDesc, h->d.outCounts, icap, h->stream);
   if (rc != B2S_OK) return rc;
   B2S_CUDA(cudaMemcpyAsync(h->hKps, h->d.outKps, (size_t)batch * icap * sizeof(b2s_keypoint), cudaMemcpyDeviceToHost,
@@ -1198,10 +1348,6 @@ extern "C" int b2s_extract_batch(b2s_extractor* h, const uint8_t* const* imgs, i
   if (rc != B2S_OK) return rc;
   for (int b = 0; b < batch; b++) {
     const int n = h->hCounts[b];
-    if (n > cap) {
-      set_error("b2s_extract: %d keypoints do not fit cap=%d", n, cap);
-      return B2S_ERR_CAPACITY;
-    }
     n_out[b] = n;
     memcpy(kps + (size_t)b * cap, h->hKps + (size_t)b * icap, (size_t)n * sizeof(b2s_keypoint));
     memcpy(desc + (size_t)b * cap * 32, h->hDesc + (size_t)b * icap * 32, (size_t)n * 32);

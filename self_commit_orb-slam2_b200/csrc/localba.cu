@@ -7,13 +7,18 @@
 //   core/block_solver.hpp:354-486        Schur complement + back substitution         -> k_schur / k_chol / k_backsub
 //   core/optimization_algorithm_levenberg.cpp:61-189   LM control                     -> k_control_begin / k_control_end
 //   types/se3quat.h:223-257, types_sba.h:52-56         oplus updates                  -> k_update_poses / k_backsub
-// The LM state machine lives on the device (one record per window); the host only polls one "any window active" word
-// per trial, so a batch of windows advances in lock step without host-side per-window logic.
+// The whole Levenberg-Marquardt loop of a window runs inside ONE persistent kernel: a window owns `nCta` thread blocks
+// that move through the phases (linearise -> Schur -> Cholesky -> back-substitute -> evaluate -> accept/reject) separated
+// by a per-window barrier in global memory; the LM state machine is a device record per window, so a batch of windows
+// needs a single launch and no host round trips.  All reductions have a fixed order (no floating-point atomics).
 #include <float.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -50,8 +55,11 @@ struct BaPtrs {  // strided per-window arrays
   double *Hpp, *Hll, *b, *x, *Dinv, *S;
   double *db, *Y;      // Dinv*b_l per landmark, W*Dinv per edge
   int *lmEdge, *freeKf;  // [landmark][free pose] -> edge id or -1 ; free pose index -> keyframe index
-  double *partChi, *partScale;
-  int* anyActive;
+  int *blkOff, *pairA, *pairC, *usePairs;  // covisibility pair lists per lower block (built once per window)
+  int capPairs, capBlk;
+  double *partChi, *partScale;   // per-CTA partial sums [window][nCta]
+  unsigned int* bar;             // per-window barrier counters
+  long long* prof;               // per-window phase cycle counters (debug): 16 slots
 };
 
 // ---------------------------------------------------------------- small FP64 helpers
@@ -181,67 +189,48 @@ __device__ double block_sum(double v, double* sm) {  // deterministic block redu
   return r;  // valid in thread 0
 }
 
-// ---------------------------------------------------------------- kernels
-// computeActiveErrors + activeRobustChi2 (sparse_optimizer.cpp:61-113).  mode 0: iteration begin, 1: after a trial.
-__global__ void __launch_bounds__(256) k_errors(BaPtrs p, int mode) {
-  __shared__ double sm[32];
-  const int w = blockIdx.y;
-  const BaState& st = p.st[w];
-  if (!st.active) return;
-  if (mode == 0 && !st.needBuild) return;
-  const BaWin W = p.win[w];
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  double contrib = 0;
-  if (e < W.nEdges) {
-    const size_t eo = (size_t)w * p.capE + e;
-    if (!p.eLevel[eo]) {
-      const int kf = p.eKf[eo], mp = p.eMp[eo];
-      double Xc[3];
-      pose_map(p.pose + ((size_t)w * p.capKf + kf) * PSTRIDE, p.pts + ((size_t)w * p.capMp + mp) * 3, Xc);
-      const double wgt = (double)p.eW[eo];
-      const float* ob = p.eObs + eo * 3;
-      double e0, e1, e2 = 0, c2;
-      if (p.eStereo[eo]) {
-        const float invz = (float)(1.0 / Xc[2]);  // const float invz = 1.0f/trans_xyz[2]  (.cpp:151)
-        const double u = Xc[0] * invz * (double)W.fx + (double)W.cx;
-        const double v = Xc[1] * invz * (double)W.fy + (double)W.cy;
-        const double ur = u - (double)__fmul_rn(W.bf, invz);
-        e0 = (double)ob[0] - u;
-        e1 = (double)ob[1] - v;
-        e2 = (double)ob[2] - ur;
-        c2 = e0 * (wgt * e0) + e1 * (wgt * e1) + e2 * (wgt * e2);
-      } else {
-        const double u = Xc[0] / Xc[2] * (double)W.fx + (double)W.cx;
-        const double v = Xc[1] / Xc[2] * (double)W.fy + (double)W.cy;
-        e0 = (double)ob[0] - u;
-        e1 = (double)ob[1] - v;
-        c2 = e0 * (wgt * e0) + e1 * (wgt * e1);
+
+// ---------------------------------------------------------------- per-window barrier
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// All CTAs of a window call this the same number of times; `epoch` counts arrivals expected so far.
+// A bounded spin: if the CTAs of a window ever fail to meet (which would mean they are not co-resident), the window is
+// flagged `hung`, every CTA leaves, and the host reports an error instead of hanging the GPU.
+__device__ __forceinline__ void win_barrier(unsigned int* bar, unsigned int& epoch, int nCta, volatile int* hung) {
+  __syncthreads();
+  epoch += (unsigned int)nCta;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned int spins = 0;
+    while (ld_acquire_u32(bar) < epoch) {
+      __nanosleep(64);
+      if (*hung) break;
+      if (++spins > (1u << 24)) {  // ~1 s
+        *hung = 1;
+        break;
       }
-      p.err[eo * 3] = e0; p.err[eo * 3 + 1] = e1; p.err[eo * 3 + 2] = e2;
-      p.chi2[eo] = c2;
-      if (st.robust) {
-        double r0, r1;
-        huber(c2, delta_of(p.eStereo[eo]), r0, r1);
-        contrib = r0;
-      } else
-        contrib = c2;
     }
+    __threadfence();
   }
-  const double s = block_sum(contrib, sm);
-  if (threadIdx.x == 0) p.partChi[(size_t)w * p.nPartE + blockIdx.x] = s;
+  __syncthreads();
 }
 
 struct EdgeJac {
   double A[3][3], B[3][6];
+  double Xc[3];
   int D;
 };
 // linearizeOplus (types_six_dof_expmap.cpp:103-139 mono, :188-234 stereo)
 __device__ __forceinline__ void edge_jacobians(const double* P, const double* X, bool st, double fx, double fy, double bf,
                                                EdgeJac& J) {
-  double Xc[3], R[3][3];
-  pose_map(P, X, Xc);
+  double R[3][3];
+  pose_map(P, X, J.Xc);
   quat_to_R(P, R);
-  const double x = Xc[0], y = Xc[1], z = Xc[2], z_2 = z * z;
+  const double x = J.Xc[0], y = J.Xc[1], z = J.Xc[2], z_2 = z * z;
   J.D = st ? 3 : 2;
   if (st) {
     for (int c = 0; c < 3; c++) {
@@ -283,152 +272,175 @@ __device__ __forceinline__ void edge_jacobians(const double* P, const double* X,
   }
 }
 
+// computeError (types_six_dof_expmap.h:90-95 mono, :122-127 stereo; cam_project .cpp:141-157) from camera coordinates
+__device__ __forceinline__ double edge_error(const double* Xc, bool stereo, const float* ob, double wgt, const BaWin& W,
+                                             double* e) {
+  if (stereo) {
+    const float invz = (float)(1.0 / Xc[2]);  // const float invz = 1.0f/trans_xyz[2]  (.cpp:151)
+    const double u = Xc[0] * invz * (double)W.fx + (double)W.cx;
+    const double v = Xc[1] * invz * (double)W.fy + (double)W.cy;
+    const double ur = u - (double)__fmul_rn(W.bf, invz);
+    e[0] = (double)ob[0] - u;
+    e[1] = (double)ob[1] - v;
+    e[2] = (double)ob[2] - ur;
+    return e[0] * (wgt * e[0]) + e[1] * (wgt * e[1]) + e[2] * (wgt * e[2]);
+  }
+  const double u = Xc[0] / Xc[2] * (double)W.fx + (double)W.cx;
+  const double v = Xc[1] / Xc[2] * (double)W.fy + (double)W.cy;
+  e[0] = (double)ob[0] - u;
+  e[1] = (double)ob[1] - v;
+  e[2] = 0;
+  return e[0] * (wgt * e[0]) + e[1] * (wgt * e[1]);
+}
+
 __device__ __forceinline__ void atomic_max_pos_double(unsigned long long* addr, double v) {
   atomicMax(addr, (unsigned long long)__double_as_longlong(fabs(v)));  // |v| >= 0: IEEE order == integer order
 }
 
-// buildSystem, landmark side: one thread per landmark walks its edges in insertion order (deterministic sums)
-__global__ void __launch_bounds__(128) k_build_landmarks(BaPtrs p) {
-  const int w = blockIdx.y;
-  const BaState& st = p.st[w];
-  if (!st.active || !st.needBuild) return;
-  const BaWin W = p.win[w];
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= W.nMp) return;
-  const size_t mo = (size_t)w * p.capMp + l;
+struct WinCtx {
+  int w, cta, nCta, gtid, gthreads;  // window id, CTA index inside the window, threads of the window
+};
+
+// ---------------------------------------------------------------- phases (device functions, strided over the window's threads)
+// computeActiveErrors + buildSystem (landmark side): one thread per landmark walks its edges in insertion order:
+// error, chi2, Huber weight, J^T W J -> Hll, b_l and the pose-landmark blocks W_e (block_solver.hpp:502-560).
+__device__ void phase_build_landmarks(const BaPtrs& p, const WinCtx& c, const BaWin& W, int robust, double* sm) {
+  const int w = c.w;
   const int* ms = p.mpStart + (size_t)w * (p.capMp + 1);
   const int* me = p.mpEdges + (size_t)w * p.capE;
-  double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
-  const double* X = p.pts + mo * 3;
-  for (int k = ms[l]; k < ms[l + 1]; k++) {
-    const int e = me[k];
-    const size_t eo = (size_t)w * p.capE + e;
-    if (p.eLevel[eo]) continue;
-    const int kf = p.eKf[eo];
-    const bool stereo = p.eStereo[eo];
-    EdgeJac J;
-    edge_jacobians(p.pose + ((size_t)w * p.capKf + kf) * PSTRIDE, X, stereo, W.fx, W.fy, W.bf, J);
-    const double w0 = (double)p.eW[eo];
-    double rho1 = 1.0;
-    if (st.robust) {
-      double r0;
-      huber(p.chi2[eo], delta_of(stereo), r0, rho1);
-    }
-    const double* er = p.err + eo * 3;
-    double omr[3];
-    for (int r = 0; r < 3; r++) omr[r] = -(w0 * er[r]) * rho1;
-    const double wq = rho1 * w0;
-    for (int i = 0; i < 3; i++) {
-      double s = 0;
-      for (int r = 0; r < J.D; r++) s += J.A[r][i] * omr[r];
-      bl[i] += s;
-      for (int j = 0; j < 3; j++) {
-        double hh = 0;
-        for (int r = 0; r < J.D; r++) hh += J.A[r][i] * wq * J.A[r][j];
-        H[i * 3 + j] += hh;
-      }
-    }
-    if (p.poseIndex[(size_t)w * p.capKf + kf] >= 0) {
-      double* Wb = p.W + eo * 18;
-      for (int i = 0; i < 6; i++)
+  double chi = 0, md = 0;
+  for (int l = c.gtid; l < W.nMp; l += c.gthreads) {
+    const size_t mo = (size_t)w * p.capMp + l;
+    double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+    const double* X = p.pts + mo * 3;
+    for (int k = ms[l]; k < ms[l + 1]; k++) {
+      const int e = me[k];
+      const size_t eo = (size_t)w * p.capE + e;
+      if (p.eLevel[eo]) continue;
+      const int kf = p.eKf[eo];
+      const bool stereo = p.eStereo[eo];
+      EdgeJac J;
+      edge_jacobians(p.pose + ((size_t)w * p.capKf + kf) * PSTRIDE, X, stereo, W.fx, W.fy, W.bf, J);
+      const double w0 = (double)p.eW[eo];
+      double er[3];
+      const double c2 = edge_error(J.Xc, stereo, p.eObs + eo * 3, w0, W, er);
+      p.err[eo * 3] = er[0]; p.err[eo * 3 + 1] = er[1]; p.err[eo * 3 + 2] = er[2];
+      p.chi2[eo] = c2;
+      double rho0 = c2, rho1 = 1.0;
+      if (robust) huber(c2, delta_of(stereo), rho0, rho1);
+      chi += rho0;
+      double omr[3];
+      for (int r = 0; r < 3; r++) omr[r] = -(w0 * er[r]) * rho1;
+      const double wq = rho1 * w0;
+      for (int i = 0; i < 3; i++) {
+        double s = 0;
+        for (int r = 0; r < J.D; r++) s += J.A[r][i] * omr[r];
+        bl[i] += s;
         for (int j = 0; j < 3; j++) {
           double hh = 0;
-          for (int r = 0; r < J.D; r++) hh += J.B[r][i] * wq * J.A[r][j];
-          Wb[i * 3 + j] = hh;
+          for (int r = 0; r < J.D; r++) hh += J.A[r][i] * wq * J.A[r][j];
+          H[i * 3 + j] += hh;
         }
+      }
+      if (p.poseIndex[(size_t)w * p.capKf + kf] >= 0) {
+        double* Wb = p.W + eo * 18;
+        for (int i = 0; i < 6; i++)
+          for (int j = 0; j < 3; j++) {
+            double hh = 0;
+            for (int r = 0; r < J.D; r++) hh += J.B[r][i] * wq * J.A[r][j];
+            Wb[i * 3 + j] = hh;
+          }
+      }
     }
+    for (int k = 0; k < 9; k++) p.Hll[mo * 9 + k] = H[k];
+    double* bb = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)W.nFree * 6 + (size_t)l * 3;
+    bb[0] = bl[0]; bb[1] = bl[1]; bb[2] = bl[2];
+    md = fmax(md, fmax(fabs(H[0]), fmax(fabs(H[4]), fabs(H[8]))));
   }
-  for (int k = 0; k < 9; k++) p.Hll[mo * 9 + k] = H[k];
-  double* bb = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)W.nFree * 6 + (size_t)l * 3;
-  bb[0] = bl[0]; bb[1] = bl[1]; bb[2] = bl[2];
-  atomic_max_pos_double(&p.st[w].maxDiagBits, fmax(fabs(H[0]), fmax(fabs(H[4]), fabs(H[8]))));
+  atomic_max_pos_double(&p.st[w].maxDiagBits, md);
+  const double s = block_sum(chi, sm);
+  if (threadIdx.x == 0) p.partChi[(size_t)w * p.nPartE + c.cta] = s;
 }
 
-// buildSystem, pose side: one CTA per free pose; fixed thread->edge mapping + ordered reduction => deterministic
-__global__ void __launch_bounds__(128) k_build_poses(BaPtrs p) {
-  __shared__ double sm[32];
-  __shared__ double out[27];
-  const int w = blockIdx.y;
-  const BaState& st = p.st[w];
-  if (!st.active || !st.needBuild) return;
-  const BaWin W = p.win[w];
-  const int kf = blockIdx.x;
-  if (kf >= W.nKf) return;
-  const int pi = p.poseIndex[(size_t)w * p.capKf + kf];
-  if (pi < 0) return;
+// buildSystem (pose side): one warp per free pose, lanes stride over the pose's edges, ordered shuffle reduction
+__device__ void phase_build_poses(const BaPtrs& p, const WinCtx& c, const BaWin& W, int robust) {
+  const int w = c.w;
+  const int lane = threadIdx.x & 31;
+  const int nWarps = c.gthreads >> 5, gw = c.gtid >> 5;
   const int* ks = p.kfStart + (size_t)w * (p.capKf + 1);
   const int* ke = p.kfEdges + (size_t)w * p.capE;
-  double acc[27];
+  for (int pi = gw; pi < W.nFree; pi += nWarps) {
+    const int kf = p.freeKf[(size_t)w * p.capKf + pi];
+    double acc[27];
 #pragma unroll
-  for (int k = 0; k < 27; k++) acc[k] = 0;
-  const double* P = p.pose + ((size_t)w * p.capKf + kf) * PSTRIDE;
-  for (int k = ks[kf] + threadIdx.x; k < ks[kf + 1]; k += blockDim.x) {
-    const int e = ke[k];
-    const size_t eo = (size_t)w * p.capE + e;
-    if (p.eLevel[eo]) continue;
-    const bool stereo = p.eStereo[eo];
-    EdgeJac J;
-    edge_jacobians(P, p.pts + ((size_t)w * p.capMp + p.eMp[eo]) * 3, stereo, W.fx, W.fy, W.bf, J);
-    const double w0 = (double)p.eW[eo];
-    double rho1 = 1.0;
-    if (st.robust) {
-      double r0;
-      huber(p.chi2[eo], delta_of(stereo), r0, rho1);
-    }
-    const double* er = p.err + eo * 3;
-    double omr[3];
-    for (int r = 0; r < 3; r++) omr[r] = -(w0 * er[r]) * rho1;
-    const double wq = rho1 * w0;
-    int t = 0;
+    for (int k = 0; k < 27; k++) acc[k] = 0;
+    const double* P = p.pose + ((size_t)w * p.capKf + kf) * PSTRIDE;
+    for (int k = ks[kf] + lane; k < ks[kf + 1]; k += 32) {
+      const int e = ke[k];
+      const size_t eo = (size_t)w * p.capE + e;
+      if (p.eLevel[eo]) continue;
+      const bool stereo = p.eStereo[eo];
+      EdgeJac J;
+      edge_jacobians(P, p.pts + ((size_t)w * p.capMp + p.eMp[eo]) * 3, stereo, W.fx, W.fy, W.bf, J);
+      const double w0 = (double)p.eW[eo];
+      double rho1 = 1.0;
+      if (robust) {
+        double r0;
+        huber(p.chi2[eo], delta_of(stereo), r0, rho1);
+      }
+      const double* er = p.err + eo * 3;
+      double omr[3];
+      for (int r = 0; r < 3; r++) omr[r] = -(w0 * er[r]) * rho1;
+      const double wq = rho1 * w0;
+      int t = 0;
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
+      for (int i = 0; i < 6; i++) {
 #pragma unroll
-      for (int j = i; j < 6; j++) {
-        double hh = 0;
-        for (int r = 0; r < J.D; r++) hh += J.B[r][i] * wq * J.B[r][j];
-        acc[t++] += hh;
+        for (int j = i; j < 6; j++) {
+          double hh = 0;
+          for (int r = 0; r < J.D; r++) hh += J.B[r][i] * wq * J.B[r][j];
+          acc[t++] += hh;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        double s = 0;
+        for (int r = 0; r < J.D; r++) s += J.B[r][i] * omr[r];
+        acc[21 + i] += s;
       }
     }
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-      double s = 0;
-      for (int r = 0; r < J.D; r++) s += J.B[r][i] * omr[r];
-      acc[21 + i] += s;
-    }
-  }
+    for (int k = 0; k < 27; k++) {
 #pragma unroll
-  for (int k = 0; k < 27; k++) {
-    const double s = block_sum(acc[k], sm);
-    if (threadIdx.x == 0) out[k] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double* Hp = p.Hpp + ((size_t)w * p.capKf + pi) * 36;
-    int t = 0;
-    double md = 0;
-    for (int i = 0; i < 6; i++)
-      for (int j = i; j < 6; j++) {
-        Hp[i * 6 + j] = out[t];
-        Hp[j * 6 + i] = out[t];
-        if (i == j) md = fmax(md, fabs(out[t]));
-        t++;
-      }
-    double* bp = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)pi * 6;
-    for (int i = 0; i < 6; i++) bp[i] = out[21 + i];
-    atomic_max_pos_double(&p.st[w].maxDiagBits, md);
+      for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+    }
+    if (lane == 0) {
+      double* Hp = p.Hpp + ((size_t)w * p.capKf + pi) * 36;
+      int t = 0;
+      double md = 0;
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) {
+          Hp[i * 6 + j] = acc[t];
+          Hp[j * 6 + i] = acc[t];
+          if (i == j) md = fmax(md, fabs(acc[t]));
+          t++;
+        }
+      double* bp = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)pi * 6;
+#pragma unroll
+      for (int i = 0; i < 6; i++) bp[i] = acc[21 + i];
+      atomic_max_pos_double(&p.st[w].maxDiagBits, md);
+    }
   }
 }
 
-__global__ void k_control_begin(BaPtrs p, int batch) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= batch) return;
+// iteration begin (levenberg.cpp:83-100): chi2 of the current state, lambda init on the first iteration
+__device__ void control_begin(const BaPtrs& p, int w, int nCta) {
   BaState& st = p.st[w];
-  if (!st.active) return;
   if (st.needBuild) {
-    const BaWin W = p.win[w];
-    const int nb = (W.nEdges + 255) / 256;
     double chi = 0;
-    for (int k = 0; k < nb; k++) chi += p.partChi[(size_t)w * p.nPartE + k];
+    for (int k = 0; k < nCta; k++) chi += p.partChi[(size_t)w * p.nPartE + k];
     st.currentChi = chi;
     st.iniChi = chi;
     st.tempChi = chi;
@@ -444,170 +456,172 @@ __global__ void k_control_begin(BaPtrs p, int batch) {
   st.maxDiagBits = 0ull;
 }
 
-// ---- Schur complement (block_solver.hpp:381-439), atomic-free and deterministic:
-//   k_lm_edge      (once per window)  lmEdge[landmark][free pose] = edge id
-//   k_dinv         per landmark:  Dinv = (Hll + lambda I)^-1,  db = Dinv b_l
-//   k_schur_pose   per free pose: Y_e = W_e Dinv (kept for the block pass), augmented row  b_p - sum_e W_e db
-//   k_schur_blocks per lower block (i1 >= i2): S(i1,i2) = [Hpp + lambda I] - sum_{l seen by both} Y_a W_c^T
-__global__ void __launch_bounds__(256) k_lm_edge(BaPtrs p) {
-  const int w = blockIdx.y;
-  const BaWin W = p.win[w];
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= W.nEdges) return;
-  const size_t eo = (size_t)w * p.capE + e;
-  const int pi = p.poseIndex[(size_t)w * p.capKf + p.eKf[eo]];
-  if (pi >= 0) p.lmEdge[((size_t)w * p.capMp + p.eMp[eo]) * p.capKf + pi] = e;
+// Schur complement (block_solver.hpp:381-439), atomic-free:
+//   phase_dinv         per landmark:  Dinv = (Hll + lambda I)^-1,  db = Dinv b_l
+//   phase_schur_pose   per free pose: Y_e = W_e Dinv, augmented row  b_p - sum_e W_e db
+//   phase_schur_blocks per lower block (i1 >= i2): S(i1,i2) = [Hpp + lambda I] - sum_{l seen by both} Y_a W_c^T
+__device__ void phase_dinv(const BaPtrs& p, const WinCtx& c, const BaWin& W, double lambda) {
+  const int w = c.w;
+  for (int l = c.gtid; l < W.nMp; l += c.gthreads) {
+    const size_t mo = (size_t)w * p.capMp + l;
+    double D[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) D[k] = p.Hll[mo * 9 + k];
+    D[0] += lambda; D[4] += lambda; D[8] += lambda;
+    double Di[9];
+    const double c00 = D[4] * D[8] - D[5] * D[7], c01 = D[5] * D[6] - D[3] * D[8], c02 = D[3] * D[7] - D[4] * D[6];
+    const double id = 1.0 / (D[0] * c00 + D[1] * c01 + D[2] * c02);
+    Di[0] = c00 * id; Di[1] = (D[2] * D[7] - D[1] * D[8]) * id; Di[2] = (D[1] * D[5] - D[2] * D[4]) * id;
+    Di[3] = c01 * id; Di[4] = (D[0] * D[8] - D[2] * D[6]) * id; Di[5] = (D[2] * D[3] - D[0] * D[5]) * id;
+    Di[6] = c02 * id; Di[7] = (D[1] * D[6] - D[0] * D[7]) * id; Di[8] = (D[0] * D[4] - D[1] * D[3]) * id;
+#pragma unroll
+    for (int k = 0; k < 9; k++) p.Dinv[mo * 9 + k] = Di[k];
+    const double* bl = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)W.nFree * 6 + (size_t)l * 3;
+    p.db[mo * 3 + 0] = Di[0] * bl[0] + Di[1] * bl[1] + Di[2] * bl[2];
+    p.db[mo * 3 + 1] = Di[3] * bl[0] + Di[4] * bl[1] + Di[5] * bl[2];
+    p.db[mo * 3 + 2] = Di[6] * bl[0] + Di[7] * bl[1] + Di[8] * bl[2];
+  }
 }
 
-__global__ void __launch_bounds__(128) k_dinv(BaPtrs p) {
-  const int w = blockIdx.y;
-  const BaState& st = p.st[w];
-  if (!st.active) return;
-  const BaWin W = p.win[w];
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= W.nMp) return;
-  const size_t mo = (size_t)w * p.capMp + l;
-  double D[9];
-#pragma unroll
-  for (int k = 0; k < 9; k++) D[k] = p.Hll[mo * 9 + k];
-  D[0] += st.lambda; D[4] += st.lambda; D[8] += st.lambda;
-  double Di[9];
-  const double c00 = D[4] * D[8] - D[5] * D[7], c01 = D[5] * D[6] - D[3] * D[8], c02 = D[3] * D[7] - D[4] * D[6];
-  const double id = 1.0 / (D[0] * c00 + D[1] * c01 + D[2] * c02);
-  Di[0] = c00 * id; Di[1] = (D[2] * D[7] - D[1] * D[8]) * id; Di[2] = (D[1] * D[5] - D[2] * D[4]) * id;
-  Di[3] = c01 * id; Di[4] = (D[0] * D[8] - D[2] * D[6]) * id; Di[5] = (D[2] * D[3] - D[0] * D[5]) * id;
-  Di[6] = c02 * id; Di[7] = (D[1] * D[6] - D[0] * D[7]) * id; Di[8] = (D[0] * D[4] - D[1] * D[3]) * id;
-#pragma unroll
-  for (int k = 0; k < 9; k++) p.Dinv[mo * 9 + k] = Di[k];
-  const double* bl = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)W.nFree * 6 + (size_t)l * 3;
-  p.db[mo * 3 + 0] = Di[0] * bl[0] + Di[1] * bl[1] + Di[2] * bl[2];
-  p.db[mo * 3 + 1] = Di[3] * bl[0] + Di[4] * bl[1] + Di[5] * bl[2];
-  p.db[mo * 3 + 2] = Di[6] * bl[0] + Di[7] * bl[1] + Di[8] * bl[2];
-}
-
-__global__ void __launch_bounds__(128) k_schur_pose(BaPtrs p) {
-  __shared__ double sm[32];
-  __shared__ double out[6];
-  const int w = blockIdx.y;
-  const BaState& st = p.st[w];
-  if (!st.active) return;
-  const BaWin W = p.win[w];
-  const int kf = blockIdx.x;
-  if (kf >= W.nKf) return;
-  const int pi = p.poseIndex[(size_t)w * p.capKf + kf];
-  if (pi < 0) return;
+__device__ void phase_schur_pose(const BaPtrs& p, const WinCtx& c, const BaWin& W) {
+  const int w = c.w;
+  const int lane = threadIdx.x & 31;
+  const int nWarps = c.gthreads >> 5, gw = c.gtid >> 5;
   const int* ks = p.kfStart + (size_t)w * (p.capKf + 1);
   const int* ke = p.kfEdges + (size_t)w * p.capE;
-  double r[6] = {0, 0, 0, 0, 0, 0};
-  for (int k = ks[kf] + threadIdx.x; k < ks[kf + 1]; k += blockDim.x) {
-    const int e = ke[k];
-    const size_t eo = (size_t)w * p.capE + e;
-    if (p.eLevel[eo]) continue;
-    const size_t mo = (size_t)w * p.capMp + p.eMp[eo];
-    const double* Di = p.Dinv + mo * 9;
-    const double* d3 = p.db + mo * 3;
-    const double* Wb = p.W + eo * 18;
-    double* Yb = p.Y + eo * 18;
+  const int n = W.nFree * 6;
+  for (int pi = gw; pi < W.nFree; pi += nWarps) {
+    const int kf = p.freeKf[(size_t)w * p.capKf + pi];
+    double r[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = ks[kf] + lane; k < ks[kf + 1]; k += 32) {
+      const int e = ke[k];
+      const size_t eo = (size_t)w * p.capE + e;
+      if (p.eLevel[eo]) continue;
+      const size_t mo = (size_t)w * p.capMp + p.eMp[eo];
+      const double* Di = p.Dinv + mo * 9;
+      const double* d3 = p.db + mo * 3;
+      const double* Wb = p.W + eo * 18;
+      double* Yb = p.Y + eo * 18;
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        const double w0 = Wb[i * 3], w1 = Wb[i * 3 + 1], w2 = Wb[i * 3 + 2];
+        Yb[i * 3 + 0] = w0 * Di[0] + w1 * Di[3] + w2 * Di[6];
+        Yb[i * 3 + 1] = w0 * Di[1] + w1 * Di[4] + w2 * Di[7];
+        Yb[i * 3 + 2] = w0 * Di[2] + w1 * Di[5] + w2 * Di[8];
+        r[i] += w0 * d3[0] + w1 * d3[1] + w2 * d3[2];
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-      const double w0 = Wb[i * 3], w1 = Wb[i * 3 + 1], w2 = Wb[i * 3 + 2];
-      Yb[i * 3 + 0] = w0 * Di[0] + w1 * Di[3] + w2 * Di[6];
-      Yb[i * 3 + 1] = w0 * Di[1] + w1 * Di[4] + w2 * Di[7];
-      Yb[i * 3 + 2] = w0 * Di[2] + w1 * Di[5] + w2 * Di[8];
-      r[i] += w0 * d3[0] + w1 * d3[1] + w2 * d3[2];
-    }
-  }
 #pragma unroll
-  for (int i = 0; i < 6; i++) {
-    const double s = block_sum(r[i], sm);
-    if (threadIdx.x == 0) out[i] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < 6) {
-    const int n = W.nFree * 6;
-    const double* bp = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)pi * 6;
-    p.S[(size_t)w * p.ldS * p.ldS + (size_t)n * p.ldS + pi * 6 + threadIdx.x] = bp[threadIdx.x] - out[threadIdx.x];
+      for (int o = 16; o > 0; o >>= 1) r[i] += __shfl_down_sync(0xffffffffu, r[i], o);
+    }
+    if (lane == 0) {
+      const double* bp = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)pi * 6;
+      double* aug = p.S + (size_t)w * p.ldS * p.ldS + (size_t)n * p.ldS + pi * 6;
+#pragma unroll
+      for (int i = 0; i < 6; i++) aug[i] = bp[i] - r[i];
+    }
   }
 }
 
-__global__ void __launch_bounds__(64) k_schur_blocks(BaPtrs p) {
-  __shared__ double red[2][36];
-  const int w = blockIdx.y;
-  const BaState& st = p.st[w];
-  if (!st.active) return;
-  const BaWin W = p.win[w];
-  // decode lower-triangular block index -> (i1 >= i2)
-  const int t = blockIdx.x;
-  int i1 = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+__device__ __forceinline__ void decode_block(int t, int& i1, int& i2) {
+  i1 = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
   while ((i1 + 1) * (i1 + 2) / 2 <= t) i1++;
   while (i1 * (i1 + 1) / 2 > t) i1--;
-  const int i2 = t - i1 * (i1 + 1) / 2;
-  if (i1 >= W.nFree) return;
-  const int kf1 = p.freeKf[(size_t)w * p.capKf + i1];
-  const int* ks = p.kfStart + (size_t)w * (p.capKf + 1);
-  const int* ke = p.kfEdges + (size_t)w * p.capE;
-  const int* lm = p.lmEdge + (size_t)w * p.capMp * p.capKf;
-  double acc[36];
+  i2 = t - i1 * (i1 + 1) / 2;
+}
+
+// one warp per lower block; lanes stride over the block's covisibility pairs, ordered shuffle reduction of the 36 sums
+__device__ void phase_schur_blocks(const BaPtrs& p, const WinCtx& c, const BaWin& W, double lambda) {
+  const int w = c.w;
+  const int lane = threadIdx.x & 31;
+  const int nWarps = c.gthreads >> 5, gw = c.gtid >> 5;
+  const int nb = W.nFree * (W.nFree + 1) / 2;
+  const int usePairs = p.usePairs[w];
+  const int* off = p.blkOff + (size_t)w * (p.capBlk + 1);
+  const int* pa = p.pairA + (size_t)w * p.capPairs;
+  const int* pc = p.pairC + (size_t)w * p.capPairs;
+  for (int t = gw; t < nb; t += nWarps) {
+    int i1, i2;
+    decode_block(t, i1, i2);
+    double acc[36];
 #pragma unroll
-  for (int k = 0; k < 36; k++) acc[k] = 0;
-  for (int k = ks[kf1] + threadIdx.x; k < ks[kf1 + 1]; k += blockDim.x) {
-    const int a = ke[k];
-    const size_t eoa = (size_t)w * p.capE + a;
-    if (p.eLevel[eoa]) continue;
-    const int c = lm[(size_t)p.eMp[eoa] * p.capKf + i2];
-    if (c < 0) continue;
-    const size_t eoc = (size_t)w * p.capE + c;
-    if (p.eLevel[eoc]) continue;
-    const double* Ya = p.Y + eoa * 18;
-    const double* Wc = p.W + eoc * 18;
-    double y[18], wc[18];
+    for (int k = 0; k < 36; k++) acc[k] = 0;
+    if (usePairs) {
+      for (int q = off[t] + lane; q < off[t + 1]; q += 32) {
+        const size_t eoa = (size_t)w * p.capE + pa[q], eoc = (size_t)w * p.capE + pc[q];
+        if (p.eLevel[eoa] | p.eLevel[eoc]) continue;
+        const double* Ya = p.Y + eoa * 18;
+        const double* Wc = p.W + eoc * 18;
+        double y[18], wc[18];
 #pragma unroll
-    for (int q = 0; q < 18; q++) {
-      y[q] = Ya[q];
-      wc[q] = Wc[q];
+        for (int z = 0; z < 18; z++) {
+          y[z] = Ya[z];
+          wc[z] = Wc[z];
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int cc = 0; cc < 6; cc++)
+            acc[r * 6 + cc] += y[r * 3] * wc[cc * 3] + y[r * 3 + 1] * wc[cc * 3 + 1] + y[r * 3 + 2] * wc[cc * 3 + 2];
+      }
+    } else {  // pair list did not fit: probe the landmark->edge table (same sums, same order)
+      const int kf1 = p.freeKf[(size_t)w * p.capKf + i1];
+      const int* ks = p.kfStart + (size_t)w * (p.capKf + 1);
+      const int* ke = p.kfEdges + (size_t)w * p.capE;
+      const int* lm = p.lmEdge + (size_t)w * p.capMp * p.capKf;
+      for (int k = ks[kf1] + lane; k < ks[kf1 + 1]; k += 32) {
+        const int a = ke[k];
+        const size_t eoa = (size_t)w * p.capE + a;
+        if (p.eLevel[eoa]) continue;
+        const int cidx = lm[(size_t)p.eMp[eoa] * p.capKf + i2];
+        if (cidx < 0) continue;
+        const size_t eoc = (size_t)w * p.capE + cidx;
+        if (p.eLevel[eoc]) continue;
+        const double* Ya = p.Y + eoa * 18;
+        const double* Wc = p.W + eoc * 18;
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int cc = 0; cc < 6; cc++)
+            acc[r * 6 + cc] += Ya[r * 3] * Wc[cc * 3] + Ya[r * 3 + 1] * Wc[cc * 3 + 1] + Ya[r * 3 + 2] * Wc[cc * 3 + 2];
+      }
     }
 #pragma unroll
-    for (int r = 0; r < 6; r++)
+    for (int k = 0; k < 36; k++) {
 #pragma unroll
-      for (int cc = 0; cc < 6; cc++)
-        acc[r * 6 + cc] += y[r * 3] * wc[cc * 3] + y[r * 3 + 1] * wc[cc * 3 + 1] + y[r * 3 + 2] * wc[cc * 3 + 2];
-  }
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < 36; k++) {
-    double v = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) red[wid][k] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < 36) {
-    const int r = threadIdx.x / 6, cc = threadIdx.x - r * 6;
-    double base = 0;
-    if (i1 == i2) {
-      base = p.Hpp[((size_t)w * p.capKf + i1) * 36 + r * 6 + cc];
-      if (r == cc) base += st.lambda;
+      for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
     }
-    p.S[(size_t)w * p.ldS * p.ldS + (size_t)(i1 * 6 + r) * p.ldS + (i2 * 6 + cc)] = base - (red[0][threadIdx.x] + red[1][threadIdx.x]);
+    if (lane == 0) {
+      double* Sb = p.S + (size_t)w * p.ldS * p.ldS + (size_t)(i1 * 6) * p.ldS + i2 * 6;
+      const double* Hp = p.Hpp + ((size_t)w * p.capKf + i1) * 36;
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int cc = 0; cc < 6; cc++) {
+          double base = 0;
+          if (i1 == i2) {
+            base = Hp[r * 6 + cc];
+            if (r == cc) base += lambda;
+          }
+          Sb[(size_t)r * p.ldS + cc] = base - acc[r * 6 + cc];
+        }
+    }
   }
 }
 
-// LinearSolver on the reduced camera system: blocked right-looking Cholesky (lower), one CTA per window.
+// LinearSolver on the reduced camera system: blocked right-looking Cholesky (lower) by ONE CTA of the window.
 // The augmented last row carries b and ends up holding y = L^-1 b; then L^T x = y by blocked back substitution.
 // Diagonal 32x32 blocks are factored by one warp with a row per lane in registers (shuffle broadcast), the panel solve
 // keeps each row in registers, the trailing update is 4x4 register tiled out of the shared-memory panel.
-constexpr int CHOL_T = 512;
 constexpr int CHOL_PP = CHOL_BS + 1;
-__global__ void __launch_bounds__(CHOL_T) k_chol(BaPtrs p) {
-  extern __shared__ __align__(16) double dsm[];
-  const int w = blockIdx.x;
+__device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) {
   BaState& st = p.st[w];
-  if (!st.active) return;
-  const BaWin W = p.win[w];
   const int n = W.nFree * 6, N1 = n + 1, ld = p.ldS;
   double* S = p.S + (size_t)w * ld * ld;
-  double* Dblk = dsm;                                // 32 x 33
-  double* panel = dsm + CHOL_BS * CHOL_PP;           // ld x 33
+  double* Dblk = dsm;                                // 33 x 33 (last row: reciprocal diagonal)
+  double* panel = dsm + (CHOL_BS + 1) * CHOL_PP;     // (ld+4) x 33
   double* xs = panel + (size_t)(ld + 4) * CHOL_PP;   // ld
   __shared__ int fail;
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
@@ -616,17 +630,18 @@ __global__ void __launch_bounds__(CHOL_T) k_chol(BaPtrs p) {
   for (int kb = 0; kb < n; kb += CHOL_BS) {
     const int wd = min(CHOL_BS, n - kb);
     for (int idx = tid; idx < CHOL_BS * CHOL_BS; idx += T) {
-      const int r = idx >> 5, c = idx & 31;
-      double v = (r == c) ? 1.0 : 0.0;  // identity padding for a short last block
-      if (r < wd && c < wd) v = (c <= r) ? S[(size_t)(kb + r) * ld + kb + c] : 0.0;
-      Dblk[r * CHOL_PP + c] = v;
+      const int r = idx >> 5, cc = idx & 31;
+      double v = (r == cc) ? 1.0 : 0.0;  // identity padding for a short last block
+      if (r < wd && cc < wd) v = (cc <= r) ? S[(size_t)(kb + r) * ld + kb + cc] : 0.0;
+      Dblk[r * CHOL_PP + cc] = v;
     }
     __syncthreads();
     if (tid < 32) {
       double row[CHOL_BS];
 #pragma unroll
-      for (int c = 0; c < CHOL_BS; c++) row[c] = Dblk[lane * CHOL_PP + c];
+      for (int cc = 0; cc < CHOL_BS; cc++) row[cc] = Dblk[lane * CHOL_PP + cc];
       bool bad = false;
+      double mydinv = 1.0;
 #pragma unroll
       for (int j = 0; j < CHOL_BS; j++) {
         double djj = __shfl_sync(0xffffffffu, row[j], j);
@@ -634,53 +649,55 @@ __global__ void __launch_bounds__(CHOL_T) k_chol(BaPtrs p) {
           bad = true;
           djj = 1.0;
         }
-        const double ljj = sqrt(djj);
-        if (lane == j) row[j] = ljj;
-        else if (lane > j) row[j] = row[j] / ljj;
+        const double rinv = rsqrt(djj);
+        const double ljj = djj * rinv;
+        mydinv = (lane == j) ? rinv : mydinv;  // 1 / L[j][j]
+        // branch-free on purpose: entries above the diagonal (k > lane) hold don't-care values that are never read;
+        // lane-dependent control flow here makes the compiler index `row` dynamically and spill it to local memory
+        row[j] = (lane == j) ? ljj : row[j] * rinv;
 #pragma unroll
         for (int k = j + 1; k < CHOL_BS; k++) {
           const double lkj = __shfl_sync(0xffffffffu, row[j], k);  // L[k][j]
-          if (lane >= k) row[k] -= row[j] * lkj;
+          row[k] = fma(-row[j], lkj, row[k]);
         }
       }
       if (bad && lane == 0) fail = 1;
 #pragma unroll
-      for (int c = 0; c < CHOL_BS; c++) Dblk[lane * CHOL_PP + c] = (c <= lane) ? row[c] : 0.0;
+      for (int cc = 0; cc < CHOL_BS; cc++) Dblk[lane * CHOL_PP + cc] = (cc <= lane) ? row[cc] : 0.0;
+      Dblk[CHOL_BS * CHOL_PP + lane] = mydinv;
     }
     __syncthreads();
     for (int idx = tid; idx < wd * wd; idx += T) {
-      const int r = idx / wd, c = idx - r * wd;
-      if (c <= r) S[(size_t)(kb + r) * ld + kb + c] = Dblk[r * CHOL_PP + c];
+      const int r = idx / wd, cc = idx - r * wd;
+      if (cc <= r) S[(size_t)(kb + r) * ld + kb + cc] = Dblk[r * CHOL_PP + cc];
     }
     const int m = N1 - (kb + wd);  // rows below the diagonal block (including the augmented row)
     for (int rowi = tid; rowi < m; rowi += T) {
       const int i = kb + wd + rowi;
       double v[CHOL_BS];
+      const double* dinv = Dblk + CHOL_BS * CHOL_PP;
 #pragma unroll
-      for (int c = 0; c < CHOL_BS; c++) v[c] = (c < wd) ? S[(size_t)i * ld + kb + c] : 0.0;
+      for (int cc = 0; cc < CHOL_BS; cc++) v[cc] = (cc < wd) ? S[(size_t)i * ld + kb + cc] : 0.0;
 #pragma unroll
-      for (int c = 0; c < CHOL_BS; c++) {
-        double a = v[c];
+      for (int cc = 0; cc < CHOL_BS; cc++) {
+        double a = v[cc];
 #pragma unroll
-        for (int k = 0; k < c; k++) a -= v[k] * Dblk[c * CHOL_PP + k];
-        v[c] = a / Dblk[c * CHOL_PP + c];
+        for (int k = 0; k < cc; k++) a -= v[k] * Dblk[cc * CHOL_PP + k];
+        v[cc] = a * dinv[cc];
       }
 #pragma unroll
-      for (int c = 0; c < CHOL_BS; c++) {
-        panel[rowi * CHOL_PP + c] = v[c];
-        if (c < wd) S[(size_t)i * ld + kb + c] = v[c];
+      for (int cc = 0; cc < CHOL_BS; cc++) {
+        panel[rowi * CHOL_PP + cc] = v[cc];
+        if (cc < wd) S[(size_t)i * ld + kb + cc] = v[cc];
       }
     }
-    // zero the padding rows read by the 4x4 tiles
     for (int idx = tid; idx < 4 * CHOL_PP; idx += T) panel[(m + idx / CHOL_PP) * CHOL_PP + idx % CHOL_PP] = 0.0;
     __syncthreads();
     const int mt = (m + 3) >> 2;
     const int ntile = mt * (mt + 1) / 2;
     for (int t = tid; t < ntile; t += T) {
-      int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-      while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-      while (ti * (ti + 1) / 2 > t) ti--;
-      const int tj = t - ti * (ti + 1) / 2;
+      int ti, tj;
+      decode_block(t, ti, tj);
       double acc[4][4];
 #pragma unroll
       for (int a = 0; a < 4; a++)
@@ -722,10 +739,10 @@ __global__ void __launch_bounds__(CHOL_T) k_chol(BaPtrs p) {
   for (int bk = nblk - 1; bk >= 0; bk--) {
     const int kb = bk * CHOL_BS, wd = min(CHOL_BS, n - kb);
     for (int idx = tid; idx < CHOL_BS * CHOL_BS; idx += T) {
-      const int r = idx >> 5, c = idx & 31;
-      double v = (r == c) ? 1.0 : 0.0;
-      if (r < wd && c < wd) v = (c <= r) ? S[(size_t)(kb + r) * ld + kb + c] : 0.0;
-      Dblk[r * CHOL_PP + c] = v;
+      const int r = idx >> 5, cc = idx & 31;
+      double v = (r == cc) ? 1.0 : 0.0;
+      if (r < wd && cc < wd) v = (cc <= r) ? S[(size_t)(kb + r) * ld + kb + cc] : 0.0;
+      Dblk[r * CHOL_PP + cc] = v;
     }
     __syncthreads();
     if (tid < 32) {
@@ -735,44 +752,44 @@ __global__ void __launch_bounds__(CHOL_T) k_chol(BaPtrs p) {
       double tv = (lane < wd) ? xs[kb + lane] : 0.0;
 #pragma unroll
       for (int j = CHOL_BS - 1; j >= 0; j--) {
-        double xj = tv / col[j];                      // meaningful on lane j (col[j] = L[j][j])
+        double xj = tv / col[j];  // meaningful on lane j (col[j] = L[j][j])
         xj = __shfl_sync(0xffffffffu, xj, j);
-        if (lane == j) tv = xj;
-        else if (lane < j) tv -= col[j] * xj;         // L[j][lane] * x_j
+        tv = (lane == j) ? xj : ((lane < j) ? fma(-col[j], xj, tv) : tv);
       }
       if (lane < wd) xs[kb + lane] = tv;
     }
     __syncthreads();
-    for (int c = tid; c < kb; c += T) {
-      double sacc = xs[c];
-      double lv[CHOL_BS];
-#pragma unroll
-      for (int r = 0; r < CHOL_BS; r++) lv[r] = (r < wd) ? S[(size_t)(kb + r) * ld + c] : 0.0;
-#pragma unroll
-      for (int r = 0; r < CHOL_BS; r++) sacc -= lv[r] * xs[kb + min(r, wd - 1)] * (r < wd ? 1.0 : 0.0);
-      xs[c] = sacc;
+    for (int cc = tid; cc < kb; cc += T) {
+      double sacc = xs[cc];
+#pragma unroll 8
+      for (int r = 0; r < CHOL_BS; r++)
+        if (r < wd) sacc -= S[(size_t)(kb + r) * ld + cc] * xs[kb + r];
+      xs[cc] = sacc;
     }
     __syncthreads();
   }
   double* x = p.x + (size_t)w * (p.capKf * 6 + p.capMp * 3);
   for (int i = tid; i < n; i += T) x[i] = xs[i];
   if (tid == 0) st.solveOk = fail ? 0 : 1;
+  __syncthreads();
 }
 
-// landmark back-substitution (block_solver.hpp:461-481) + update (types_sba.h:52-56) + computeScale partials
-__global__ void __launch_bounds__(128) k_backsub(BaPtrs p) {
-  __shared__ double sm[32];
-  const int w = blockIdx.y;
-  const BaState& st = p.st[w];
-  if (!st.active) return;
-  const BaWin W = p.win[w];
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+// landmark back-substitution (block_solver.hpp:461-481) + updates (types_sba.h:52-56, se3quat oplus) + computeScale
+__device__ void phase_backsub_update(const BaPtrs& p, const WinCtx& c, const BaWin& W, double lambda, int solveOk,
+                                     double* sm) {
+  const int w = c.w;
+  const int* ms = p.mpStart + (size_t)w * (p.capMp + 1);
+  const int* me = p.mpEdges + (size_t)w * p.capE;
+  const size_t xo = (size_t)w * (p.capKf * 6 + p.capMp * 3);
   double sc = 0;
-  if (l < W.nMp && st.solveOk) {
+  for (int l = c.gtid; l < W.nMp; l += c.gthreads) {
     const size_t mo = (size_t)w * p.capMp + l;
-    const int* ms = p.mpStart + (size_t)w * (p.capMp + 1);
-    const int* me = p.mpEdges + (size_t)w * p.capE;
-    const size_t xo = (size_t)w * (p.capKf * 6 + p.capMp * 3);
+    double* X = p.pts + mo * 3;
+    double* Xb = p.ptsBak + mo * 3;
+    if (!solveOk) {
+      for (int i = 0; i < 3; i++) Xb[i] = X[i];
+      continue;
+    }
     const double* bl = p.b + xo + (size_t)W.nFree * 6 + (size_t)l * 3;
     double cl[3] = {bl[0], bl[1], bl[2]};
     for (int k = ms[l]; k < ms[l + 1]; k++) {
@@ -783,68 +800,68 @@ __global__ void __launch_bounds__(128) k_backsub(BaPtrs p) {
       if (pi < 0) continue;
       const double* Wb = p.W + eo * 18;
       const double* xp = p.x + xo + (size_t)pi * 6;
-      for (int c = 0; c < 3; c++)
-        for (int r = 0; r < 6; r++) cl[c] -= Wb[r * 3 + c] * xp[r];
+      for (int cc = 0; cc < 3; cc++)
+        for (int r = 0; r < 6; r++) cl[cc] -= Wb[r * 3 + cc] * xp[r];
     }
     const double* Di = p.Dinv + mo * 9;
-    double xl[3];
-    for (int i = 0; i < 3; i++) xl[i] = Di[i * 3] * cl[0] + Di[i * 3 + 1] * cl[1] + Di[i * 3 + 2] * cl[2];
     double* xout = p.x + xo + (size_t)W.nFree * 6 + (size_t)l * 3;
-    double* X = p.pts + mo * 3;
-    double* Xb = p.ptsBak + mo * 3;
     for (int i = 0; i < 3; i++) {
-      xout[i] = xl[i];
+      const double xl = Di[i * 3] * cl[0] + Di[i * 3 + 1] * cl[1] + Di[i * 3 + 2] * cl[2];
+      xout[i] = xl;
       Xb[i] = X[i];
-      X[i] += xl[i];
-      sc += xl[i] * (st.lambda * xl[i] + bl[i]);
+      X[i] += xl;
+      sc += xl * (lambda * xl + bl[i]);
     }
-  } else if (l < W.nMp) {
-    const size_t mo = (size_t)w * p.capMp + l;
-    for (int i = 0; i < 3; i++) p.ptsBak[mo * 3 + i] = p.pts[mo * 3 + i];
+  }
+  // poses: the last CTA of the window also backs up and updates the keyframe poses
+  if (c.cta == c.nCta - 1) {
+    for (int kf = threadIdx.x; kf < W.nKf; kf += blockDim.x) {
+      double* P = p.pose + ((size_t)w * p.capKf + kf) * PSTRIDE;
+      double* Pb = p.poseBak + ((size_t)w * p.capKf + kf) * PSTRIDE;
+      for (int k = 0; k < 7; k++) Pb[k] = P[k];
+      const int pi = p.poseIndex[(size_t)w * p.capKf + kf];
+      if (pi >= 0 && solveOk) {
+        const double* xp = p.x + xo + (size_t)pi * 6;
+        const double* bp = p.b + xo + (size_t)pi * 6;
+        pose_oplus(P, xp);
+        for (int i = 0; i < 6; i++) sc += xp[i] * (lambda * xp[i] + bp[i]);
+      }
+    }
   }
   const double s = block_sum(sc, sm);
-  if (threadIdx.x == 0) p.partScale[(size_t)w * p.nPartM + blockIdx.x] = s;
+  if (threadIdx.x == 0) p.partScale[(size_t)w * p.nPartM + c.cta] = s;
 }
 
-__global__ void __launch_bounds__(128) k_update_poses(BaPtrs p) {
-  __shared__ double sm[32];
-  const int w = blockIdx.x;
-  BaState& st = p.st[w];
-  if (!st.active) return;
-  const BaWin W = p.win[w];
-  double sc = 0;
-  for (int kf = threadIdx.x; kf < W.nKf; kf += blockDim.x) {
-    double* P = p.pose + ((size_t)w * p.capKf + kf) * PSTRIDE;
-    double* Pb = p.poseBak + ((size_t)w * p.capKf + kf) * PSTRIDE;
-    for (int k = 0; k < 7; k++) Pb[k] = P[k];
-    const int pi = p.poseIndex[(size_t)w * p.capKf + kf];
-    if (pi >= 0 && st.solveOk) {
-      const size_t xo = (size_t)w * (p.capKf * 6 + p.capMp * 3);
-      const double* xp = p.x + xo + (size_t)pi * 6;
-      const double* bp = p.b + xo + (size_t)pi * 6;
-      pose_oplus(P, xp);
-      for (int i = 0; i < 6; i++) sc += xp[i] * (st.lambda * xp[i] + bp[i]);
-    }
+// computeActiveErrors + activeRobustChi2 after the update (sparse_optimizer.cpp:61-113), one thread per edge
+__device__ void phase_errors(const BaPtrs& p, const WinCtx& c, const BaWin& W, int robust, double* sm) {
+  const int w = c.w;
+  double chi = 0;
+  for (int e = c.gtid; e < W.nEdges; e += c.gthreads) {
+    const size_t eo = (size_t)w * p.capE + e;
+    if (p.eLevel[eo]) continue;
+    double Xc[3], er[3];
+    pose_map(p.pose + ((size_t)w * p.capKf + p.eKf[eo]) * PSTRIDE, p.pts + ((size_t)w * p.capMp + p.eMp[eo]) * 3, Xc);
+    const bool stereo = p.eStereo[eo];
+    const double c2 = edge_error(Xc, stereo, p.eObs + eo * 3, (double)p.eW[eo], W, er);
+    p.err[eo * 3] = er[0]; p.err[eo * 3 + 1] = er[1]; p.err[eo * 3 + 2] = er[2];
+    p.chi2[eo] = c2;
+    double rho0 = c2, rho1;
+    if (robust) huber(c2, delta_of(stereo), rho0, rho1);
+    chi += rho0;
   }
-  const double s = block_sum(sc, sm);
-  if (threadIdx.x == 0) p.partScale[(size_t)w * p.nPartM + (p.nPartM - 1)] = s;  // last slot is reserved for the poses
+  const double s = block_sum(chi, sm);
+  if (threadIdx.x == 0) p.partChi[(size_t)w * p.nPartE + c.cta] = s;
 }
 
 // LM accept/reject + iteration/round bookkeeping (levenberg.cpp:102-161, sparse_optimizer.cpp:376-412,
 // src/Optimizer.cc:863-917)
-__global__ void k_control_end(BaPtrs p, int batch) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= batch) return;
+__device__ void control_end(const BaPtrs& p, int w, int nCta) {
   BaState& st = p.st[w];
   st.restore = 0;
   st.doOutlier = 0;
-  if (!st.active) return;
-  const BaWin W = p.win[w];
-  const int nbE = (W.nEdges + 255) / 256, nbM = (W.nMp + 127) / 128;
-  double tempChi = 0;
-  for (int k = 0; k < nbE; k++) tempChi += p.partChi[(size_t)w * p.nPartE + k];
-  double scale = p.partScale[(size_t)w * p.nPartM + (p.nPartM - 1)];
-  for (int k = 0; k < nbM; k++) scale += p.partScale[(size_t)w * p.nPartM + k];
+  double tempChi = 0, scale = 0;
+  for (int k = 0; k < nCta; k++) tempChi += p.partChi[(size_t)w * p.nPartE + k];
+  for (int k = 0; k < nCta; k++) scale += p.partScale[(size_t)w * p.nPartM + k];
   st.chi2Final = tempChi;  // activeRobustChi2() of the last evaluated state (diagnostic)
   if (!st.solveOk) {
     tempChi = DBL_MAX;
@@ -870,7 +887,8 @@ __global__ void k_control_end(BaPtrs p, int batch) {
   st.rho = rho;
   st.tempChi = tempChi;
   st.qmax++;
-  if (rho < 0 && st.qmax < 10 && !st.stop) return;  // another trial with the larger lambda
+  const int stop = *((volatile int*)&st.stop);
+  if (rho < 0 && st.qmax < 10 && !stop) return;  // another trial with the larger lambda
   bool roundEnd = false;
   if (st.qmax == 10 || rho == 0) {
     roundEnd = true;
@@ -880,71 +898,215 @@ __global__ void k_control_end(BaPtrs p, int batch) {
     if (st.nBad >= 3) roundEnd = true;
   }
   st.it++;
-  if (st.it >= st.its[st.round] || st.stop) roundEnd = true;
+  if (st.it >= st.its[st.round] || stop) roundEnd = true;
   if (!roundEnd) {
     st.needBuild = 1;
     return;
   }
-  if (st.round == 0 && !st.stop && st.its[1] > 0) {
+  if (st.round == 0 && !stop && st.its[1] > 0) {
     st.doOutlier = 1;  // setLevel(1) on outliers, drop the robust kernels, second round
     st.round = 1;
     st.it = 0;
     st.robust = 0;
     st.needBuild = 1;
   } else {
-    // its2 == 0 or stop after round 1: the final outlier test still runs (:921-958)
-    st.doOutlier = 2;
+    st.doOutlier = 2;  // final outlier test (:921-958); it also runs when round 2 is skipped
     st.active = 0;
   }
 }
 
-// pop(): restore the state of a rejected trial; then the chi2/depth outlier tests (src/Optimizer.cc:880-958)
-__global__ void __launch_bounds__(256) k_restore_outliers(BaPtrs p) {
-  const int w = blockIdx.y;
-  const BaState& st = p.st[w];
-  const BaWin W = p.win[w];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (st.restore) {
-    if (i < W.nMp * 3) p.pts[(size_t)w * p.capMp * 3 + i] = p.ptsBak[(size_t)w * p.capMp * 3 + i];
-    if (i < W.nKf * PSTRIDE) p.pose[(size_t)w * p.capKf * PSTRIDE + i] = p.poseBak[(size_t)w * p.capKf * PSTRIDE + i];
+__device__ void phase_restore(const BaPtrs& p, const WinCtx& c, const BaWin& W) {
+  const int w = c.w;
+  for (int i = c.gtid; i < W.nMp * 3; i += c.gthreads) p.pts[(size_t)w * p.capMp * 3 + i] = p.ptsBak[(size_t)w * p.capMp * 3 + i];
+  for (int i = c.gtid; i < W.nKf * PSTRIDE; i += c.gthreads)
+    p.pose[(size_t)w * p.capKf * PSTRIDE + i] = p.poseBak[(size_t)w * p.capKf * PSTRIDE + i];
+}
+
+// chi2 / depth outlier tests (src/Optimizer.cc:880-958)
+__device__ void phase_outliers(const BaPtrs& p, const WinCtx& c, const BaWin& W, int mode) {
+  const int w = c.w;
+  for (int e = c.gtid; e < W.nEdges; e += c.gthreads) {
+    const size_t eo = (size_t)w * p.capE + e;
+    double Xc[3];
+    pose_map(p.pose + ((size_t)w * p.capKf + p.eKf[eo]) * PSTRIDE, p.pts + ((size_t)w * p.capMp + p.eMp[eo]) * 3, Xc);
+    const double th = p.eStereo[eo] ? 7.815 : 5.991;
+    const bool out = p.chi2[eo] > th || !(Xc[2] > 0.0);
+    if (mode == 1) {
+      if (out) p.eLevel[eo] = 1;
+    } else
+      p.eOutlier[eo] = out ? 1 : 0;
   }
 }
-__global__ void __launch_bounds__(256) k_outliers(BaPtrs p) {
+
+// ---------------------------------------------------------------- the persistent kernel: grid = batch * nCta CTAs
+constexpr int BA_T = 384;
+__global__ void __launch_bounds__(BA_T) k_local_ba(BaPtrs p, int nCta, int wBase) {
+  extern __shared__ __align__(16) double dsm[];
+  __shared__ double red[32];
+  WinCtx c;
+  c.w = blockIdx.x / nCta;
+  c.cta = blockIdx.x - c.w * nCta;
+  c.w += wBase;
+  c.nCta = nCta;
+  c.gtid = c.cta * blockDim.x + threadIdx.x;
+  c.gthreads = nCta * blockDim.x;
+  const int w = c.w;
+  const BaWin W = p.win[w];
+  unsigned int* bar = p.bar + w;
+  unsigned int epoch = 0;
+  volatile BaState* vst = p.st + w;
+  volatile int* hung = &(p.st + w)->finishedRound0;  // (field reused as the barrier-timeout flag)
+  const bool profOn = (c.cta == 0 && threadIdx.x == 0);
+  long long tPrev = clock64();
+#define BA_PROF(slot)                                   \
+  if (profOn) {                                         \
+    const long long tn = clock64();                     \
+    p.prof[(size_t)w * 16 + (slot)] += tn - tPrev;      \
+    tPrev = tn;                                         \
+  }
+  for (int guard = 0; guard < 4096; guard++) {
+    if (!vst->active || *hung) break;
+    const int needBuild = vst->needBuild, robust = vst->robust;
+    if (needBuild) {
+      phase_build_landmarks(p, c, W, robust, red);
+      win_barrier(bar, epoch, nCta, hung);
+      BA_PROF(0)
+      phase_build_poses(p, c, W, robust);
+      win_barrier(bar, epoch, nCta, hung);
+      BA_PROF(1)
+    }
+    if (c.cta == 0 && threadIdx.x == 0) control_begin(p, w, nCta);
+    win_barrier(bar, epoch, nCta, hung);
+    BA_PROF(2)
+    const double lambda = vst->lambda;
+    phase_dinv(p, c, W, lambda);
+    win_barrier(bar, epoch, nCta, hung);
+    BA_PROF(3)
+    phase_schur_pose(p, c, W);
+    win_barrier(bar, epoch, nCta, hung);
+    BA_PROF(4)
+    phase_schur_blocks(p, c, W, lambda);
+    win_barrier(bar, epoch, nCta, hung);
+    BA_PROF(5)
+    if (c.cta == 0) phase_chol(p, w, W, dsm);
+    win_barrier(bar, epoch, nCta, hung);
+    BA_PROF(6)
+    phase_backsub_update(p, c, W, lambda, vst->solveOk, red);
+    win_barrier(bar, epoch, nCta, hung);
+    BA_PROF(7)
+    phase_errors(p, c, W, robust, red);
+    win_barrier(bar, epoch, nCta, hung);
+    BA_PROF(8)
+    if (c.cta == 0 && threadIdx.x == 0) control_end(p, w, nCta);
+    win_barrier(bar, epoch, nCta, hung);
+    BA_PROF(9)
+    if (vst->restore) phase_restore(p, c, W);
+    const int doOutlier = vst->doOutlier;
+    if (doOutlier) {
+      win_barrier(bar, epoch, nCta, hung);  // the depth test reads the restored state
+      phase_outliers(p, c, W, doOutlier);
+    }
+    win_barrier(bar, epoch, nCta, hung);
+    BA_PROF(10)
+  }
+#undef BA_PROF
+}
+
+// ---------------------------------------------------------------- structure kernels (once per window)
+__global__ void __launch_bounds__(256) k_lm_edge(BaPtrs p) {
   const int w = blockIdx.y;
-  const BaState& st = p.st[w];
-  if (!st.doOutlier) return;
   const BaWin W = p.win[w];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= W.nEdges) return;
   const size_t eo = (size_t)w * p.capE + e;
-  double Xc[3];
-  pose_map(p.pose + ((size_t)w * p.capKf + p.eKf[eo]) * PSTRIDE, p.pts + ((size_t)w * p.capMp + p.eMp[eo]) * 3, Xc);
-  const double th = p.eStereo[eo] ? 7.815 : 5.991;
-  const bool out = p.chi2[eo] > th || !(Xc[2] > 0.0);
-  if (st.doOutlier == 1) p.eLevel[eo] = out ? 1 : p.eLevel[eo];
-  else p.eOutlier[eo] = out ? 1 : 0;
+  const int pi = p.poseIndex[(size_t)w * p.capKf + p.eKf[eo]];
+  if (pi >= 0) p.lmEdge[((size_t)w * p.capMp + p.eMp[eo]) * p.capKf + pi] = e;
 }
 
-__global__ void k_any_active(BaPtrs p, int batch) {
+// covisibility pair lists: for every lower block (i1 >= i2) the (edge of pose i1, edge of pose i2) pairs that share a
+// landmark, in the order of pose i1's edge list (count -> scan -> ordered fill)
+__global__ void __launch_bounds__(64) k_pair_build(BaPtrs p, int fill) {
+  __shared__ int wsum[2];
+  __shared__ int running;
+  const int w = blockIdx.y;
+  if (!p.usePairs[w]) return;
+  const BaWin W = p.win[w];
+  int i1, i2;
+  decode_block(blockIdx.x, i1, i2);
+  if (i1 >= W.nFree) return;
+  const int kf1 = p.freeKf[(size_t)w * p.capKf + i1];
+  const int* ks = p.kfStart + (size_t)w * (p.capKf + 1);
+  const int* ke = p.kfEdges + (size_t)w * p.capE;
+  const int* lm = p.lmEdge + (size_t)w * p.capMp * p.capKf;
+  int* off = p.blkOff + (size_t)w * (p.capBlk + 1);
+  const int beg = ks[kf1], end = ks[kf1 + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  int total = 0;
+  for (int k0 = beg; k0 < end; k0 += 64) {
+    const int k = k0 + threadIdx.x;
+    int a = -1, cidx = -1;
+    if (k < end) {
+      a = ke[k];
+      cidx = lm[(size_t)p.eMp[(size_t)w * p.capE + a] * p.capKf + i2];
+    }
+    const bool hit = cidx >= 0;
+    const unsigned bm = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) wsum[wid] = __popc(bm);
+    __syncthreads();
+    if (fill && hit) {
+      const int pos = off[blockIdx.x] + running + (wid ? wsum[0] : 0) + __popc(bm & ((1u << lane) - 1u));
+      p.pairA[(size_t)w * p.capPairs + pos] = a;
+      p.pairC[(size_t)w * p.capPairs + pos] = cidx;
+    }
+    total += wsum[0] + wsum[1];
+    __syncthreads();
+    if (threadIdx.x == 0) running = total;
+    __syncthreads();
+  }
+  if (!fill && threadIdx.x == 0) off[blockIdx.x + 1] = total;  // counts, scanned by k_pair_scan
+}
+
+__global__ void k_pair_scan(BaPtrs p, int batch) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w < batch && p.st[w].active) atomicOr(p.anyActive, 1);
+  if (w >= batch || !p.usePairs[w]) return;
+  const BaWin W = p.win[w];
+  int* off = p.blkOff + (size_t)w * (p.capBlk + 1);
+  const int nb = W.nFree * (W.nFree + 1) / 2;
+  off[0] = 0;
+  int run = 0;
+  for (int t = 0; t < nb; t++) {
+    run += off[t + 1];
+    off[t + 1] = run;
+  }
+  if (run > p.capPairs) p.usePairs[w] = 0;  // does not fit: fall back to probing every trial
 }
-
-// final robust/plain chi2 of the active edges (diagnostic) comes from st.tempChi/currentChi; nothing else to do.
 
 }  // namespace b2s
 
 using namespace b2s;
 
+// ================================================================================================ host side
+struct BaHostStage {  // pinned mirror of the uploaded per-window arrays (same strides as the device arrays)
+  double *pose = nullptr, *pts = nullptr;
+  int *pidx = nullptr, *freeKf = nullptr, *eKf = nullptr, *eMp = nullptr, *mpStart = nullptr, *kfStart = nullptr,
+      *mpEdges = nullptr, *kfEdges = nullptr, *usePairs = nullptr;
+  float *eObs = nullptr, *eW = nullptr;
+  uint8_t *eSt = nullptr, *eOutlier = nullptr;
+  BaWin* win = nullptr;
+  BaState* st = nullptr;
+};
+
 struct b2s_ba_solver {
   int maxKf, maxMp, maxE, maxBatch, device;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
   long long launches = 0;
   BaPtrs d;
-  std::vector<void*> allocs;
-  // pinned staging
-  int* hAny = nullptr;
-  size_t cholSmem = 0;
+  std::vector<void*> allocs, hostAllocs;
+  BaHostStage hs;
+  size_t smemBytes = 0;
+  int numSMs = 0;
 };
 
 static void quat_from_R_host(const double m[3][3], double* q) {
@@ -987,14 +1149,18 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   if (rc != B2S_OK) return rc;
   b2s_ba_solver* h = new b2s_ba_solver();
   h->maxKf = max_kf; h->maxMp = max_mp; h->maxE = max_edges; h->maxBatch = max_batch; h->device = device;
+  cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, device);
   BaPtrs& d = h->d;
   memset(&d, 0, sizeof(d));
   d.capKf = max_kf; d.capMp = max_mp; d.capE = max_edges;
   d.ldS = max_kf * 6 + 1;
-  d.nPartE = div_up(max_edges, 256);
-  d.nPartM = div_up(max_mp, 128) + 1;
+  d.nPartE = 16;  // >= CTAs per window
+  d.nPartM = 16;
+  d.capBlk = max_kf * (max_kf + 1) / 2;
+  d.capPairs = 8 * max_edges;
   const size_t B = max_batch;
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
   auto A = [&](void* pp, size_t bytes) {
     void** p = (void**)pp;
     if (e == cudaSuccess) {
@@ -1003,6 +1169,13 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
         h->allocs.push_back(*p);
         e = cudaMemset(*p, 0, bytes);
       }
+    }
+  };
+  auto HA = [&](void* pp, size_t bytes) {
+    void** p = (void**)pp;
+    if (e == cudaSuccess) {
+      e = cudaMallocHost(p, bytes);
+      if (e == cudaSuccess) h->hostAllocs.push_back(*p);
     }
   };
   A(&d.win, B * sizeof(BaWin)); A(&d.st, B * sizeof(BaState));
@@ -1020,12 +1193,24 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   A(&d.Dinv, B * max_mp * 9 * 8); A(&d.S, B * (size_t)d.ldS * d.ldS * 8);
   A(&d.db, B * max_mp * 3 * 8); A(&d.Y, B * max_edges * 18 * 8);
   A(&d.lmEdge, B * (size_t)max_mp * max_kf * 4); A(&d.freeKf, B * max_kf * 4);
+  A(&d.blkOff, B * (size_t)(d.capBlk + 1) * 4); A(&d.pairA, B * (size_t)d.capPairs * 4); A(&d.pairC, B * (size_t)d.capPairs * 4);
+  A(&d.usePairs, B * 4);
   A(&d.partChi, B * d.nPartE * 8); A(&d.partScale, B * d.nPartM * 8);
-  A(&d.anyActive, 4);
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->hAny, 4);
-  h->cholSmem = (size_t)(CHOL_BS * CHOL_PP + (size_t)(d.ldS + 4) * CHOL_PP + d.ldS) * 8;
-  if (e == cudaSuccess && h->cholSmem > 48 * 1024)
-    e = cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cholSmem);
+  A(&d.bar, B * 4);
+  A(&d.prof, B * 16 * 8);
+  BaHostStage& s = h->hs;
+  HA(&s.pose, B * max_kf * PSTRIDE * 8); HA(&s.pts, B * max_mp * 3 * 8);
+  HA(&s.pidx, B * max_kf * 4); HA(&s.freeKf, B * max_kf * 4);
+  HA(&s.eKf, B * max_edges * 4); HA(&s.eMp, B * max_edges * 4);
+  HA(&s.mpStart, B * (max_mp + 1) * 4); HA(&s.kfStart, B * (max_kf + 1) * 4);
+  HA(&s.mpEdges, B * max_edges * 4); HA(&s.kfEdges, B * max_edges * 4);
+  HA(&s.usePairs, B * 4);
+  HA(&s.eObs, B * max_edges * 12); HA(&s.eW, B * max_edges * 4);
+  HA(&s.eSt, B * max_edges); HA(&s.eOutlier, B * max_edges);
+  HA(&s.win, B * sizeof(BaWin)); HA(&s.st, B * sizeof(BaState));
+  h->smemBytes = (size_t)((CHOL_BS + 1) * CHOL_PP + (size_t)(d.ldS + 4) * CHOL_PP + d.ldS) * 8;
+  if (e == cudaSuccess && h->smemBytes > 48 * 1024)
+    e = cudaFuncSetAttribute(k_local_ba, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes);
   if (e != cudaSuccess) {
     set_error("b2s_ba_create: %s", cudaGetErrorString(e));
     b2s_ba_destroy(h);
@@ -1039,11 +1224,73 @@ extern "C" void b2s_ba_destroy(b2s_ba_solver* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
-  if (h->hAny) cudaFreeHost(h->hAny);
+  for (void* p : h->hostAllocs) cudaFreeHost(p);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   delete h;
 }
 extern "C" long long b2s_ba_launch_count(const b2s_ba_solver* h) { return h ? h->launches : 0; }
+
+// Converter::toSE3Quat / toVector3d + CSR structure of one window, written into the pinned staging area
+static int ba_prepare_window(b2s_ba_solver* h, int w, const b2s_ba_problem& P, int* nFreeOut) {
+  const BaPtrs& d = h->d;
+  BaHostStage& s = h->hs;
+  double* pose = s.pose + (size_t)w * d.capKf * PSTRIDE;
+  int* pidx = s.pidx + (size_t)w * d.capKf;
+  int* freeKf = s.freeKf + (size_t)w * d.capKf;
+  int nFree = 0;
+  for (int k = 0; k < P.n_kf; k++) {
+    const float* T = P.Tcw + (size_t)k * 16;
+    double R[3][3];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) R[i][j] = T[i * 4 + j];  // Converter::toSE3Quat (src/Converter.cc:57-66)
+    quat_from_R_host(R, pose + (size_t)k * PSTRIDE);
+    pose[(size_t)k * PSTRIDE + 4] = T[3];
+    pose[(size_t)k * PSTRIDE + 5] = T[7];
+    pose[(size_t)k * PSTRIDE + 6] = T[11];
+    pose[(size_t)k * PSTRIDE + 7] = 0;
+    if (!P.fixed[k]) {
+      pidx[k] = nFree;
+      freeKf[nFree++] = k;
+    } else
+      pidx[k] = -1;
+  }
+  double* pts = s.pts + (size_t)w * d.capMp * 3;
+  for (size_t i = 0; i < (size_t)P.n_mp * 3; i++) pts[i] = P.points[i];  // Converter::toVector3d
+  int* eKf = s.eKf + (size_t)w * d.capE;
+  int* eMp = s.eMp + (size_t)w * d.capE;
+  float* eObs = s.eObs + (size_t)w * d.capE * 3;
+  float* eW = s.eW + (size_t)w * d.capE;
+  uint8_t* eSt = s.eSt + (size_t)w * d.capE;
+  int* mpStart = s.mpStart + (size_t)w * (d.capMp + 1);
+  int* kfStart = s.kfStart + (size_t)w * (d.capKf + 1);
+  int* mpEdges = s.mpEdges + (size_t)w * d.capE;
+  int* kfEdges = s.kfEdges + (size_t)w * d.capE;
+  for (int i = 0; i <= P.n_mp; i++) mpStart[i] = 0;
+  for (int i = 0; i <= P.n_kf; i++) kfStart[i] = 0;
+  for (int e = 0; e < P.n_edges; e++) {
+    const b2s_ba_edge& E = P.edges[e];
+    if (E.kf < 0 || E.kf >= P.n_kf || E.mp < 0 || E.mp >= P.n_mp) return -1;
+    eKf[e] = E.kf;
+    eMp[e] = E.mp;
+    eObs[(size_t)e * 3] = E.obs[0]; eObs[(size_t)e * 3 + 1] = E.obs[1]; eObs[(size_t)e * 3 + 2] = E.obs[2];
+    eW[e] = E.inv_sigma2;
+    eSt[e] = !(E.obs[2] < 0);  // mvuRight<0 -> monocular edge (src/Optimizer.cc:794)
+    mpStart[E.mp + 1]++;
+    kfStart[E.kf + 1]++;
+  }
+  for (int i = 0; i < P.n_mp; i++) mpStart[i + 1] += mpStart[i];
+  for (int i = 0; i < P.n_kf; i++) kfStart[i + 1] += kfStart[i];
+  {
+    std::vector<int> cm(mpStart, mpStart + P.n_mp), ck(kfStart, kfStart + P.n_kf);
+    for (int e = 0; e < P.n_edges; e++) {
+      mpEdges[cm[eMp[e]]++] = e;
+      kfEdges[ck[eKf[e]]++] = e;
+    }
+  }
+  *nFreeOut = nFree;
+  return 0;
+}
 
 static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, const volatile uint8_t* stop,
                   b2s_ba_result* res) {
@@ -1052,13 +1299,12 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
     return B2S_ERR_BAD_ARG;
   }
   BaPtrs& d = h->d;
+  BaHostStage& s = h->hs;
   B2S_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   if (stop && *stop) return B2S_ERR_ABORTED;  // src/Optimizer.cc:858-860: return without write-back
-  int maxE = 0, maxMp = 0, maxKf = 0, maxN = 0, maxFree = 0;
-  std::vector<BaWin> wins(batch);
-  std::vector<BaState> states(batch);
-  // host staging (pageable -> device); a window is a few MB at most
+  const bool dbg = getenv("B2S_DEBUG_TIMING") != nullptr;
+  const auto tStart = std::chrono::steady_clock::now();
   for (int w = 0; w < batch; w++) {
     const b2s_ba_problem& P = probs[w];
     if (P.its1 < 1 || P.its2 < 0) {
@@ -1070,152 +1316,160 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
       set_error("b2s_local_ba: window %d exceeds the solver's capacity or has null arrays", w);
       return B2S_ERR_BAD_ARG;
     }
-    std::vector<double> pose((size_t)P.n_kf * PSTRIDE, 0.0);
-    std::vector<int> pidx(P.n_kf, -1), freeKf;
-    int nFree = 0;
-    for (int k = 0; k < P.n_kf; k++) {
-      const float* T = P.Tcw + (size_t)k * 16;
-      double R[3][3];
-      for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) R[i][j] = T[i * 4 + j];  // Converter::toSE3Quat (src/Converter.cc:57-66)
-      quat_from_R_host(R, &pose[(size_t)k * PSTRIDE]);
-      pose[(size_t)k * PSTRIDE + 4] = T[3];
-      pose[(size_t)k * PSTRIDE + 5] = T[7];
-      pose[(size_t)k * PSTRIDE + 6] = T[11];
-      if (!P.fixed[k]) {
-        pidx[k] = nFree++;
-        freeKf.push_back(k);
-      }
+  }
+  // ---- host preparation of all windows in parallel (pinned staging), then one H2D per array
+  std::vector<int> nFree(batch, 0), prc(batch, 0);
+  {
+    const int nth = std::max(1, std::min(batch, std::min(16, (int)std::thread::hardware_concurrency())));
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; t++)
+      th.emplace_back([&, t]() {
+        for (int w = t; w < batch; w += nth) prc[w] = ba_prepare_window(h, w, probs[w], &nFree[w]);
+      });
+    for (auto& t : th) t.join();
+  }
+  int maxE = 0, maxMp = 0, maxFree = 0;
+  for (int w = 0; w < batch; w++) {
+    if (prc[w]) {
+      set_error("b2s_local_ba: window %d: an edge references a vertex out of range", w);
+      return B2S_ERR_BAD_ARG;
     }
-    std::vector<double> pts((size_t)P.n_mp * 3);
-    for (size_t i = 0; i < pts.size(); i++) pts[i] = P.points[i];  // Converter::toVector3d
-    std::vector<int> eKf(P.n_edges), eMp(P.n_edges), mpStart(P.n_mp + 1, 0), kfStart(P.n_kf + 1, 0), mpEdges(P.n_edges),
-        kfEdges(P.n_edges);
-    std::vector<float> eObs((size_t)P.n_edges * 3), eW(P.n_edges);
-    std::vector<uint8_t> eSt(P.n_edges);
-    for (int e = 0; e < P.n_edges; e++) {
-      const b2s_ba_edge& E = P.edges[e];
-      if (E.kf < 0 || E.kf >= P.n_kf || E.mp < 0 || E.mp >= P.n_mp) {
-        set_error("b2s_local_ba: edge %d references a vertex out of range", e);
-        return B2S_ERR_BAD_ARG;
-      }
-      eKf[e] = E.kf; eMp[e] = E.mp;
-      eObs[(size_t)e * 3] = E.obs[0]; eObs[(size_t)e * 3 + 1] = E.obs[1]; eObs[(size_t)e * 3 + 2] = E.obs[2];
-      eW[e] = E.inv_sigma2;
-      eSt[e] = !(E.obs[2] < 0);  // mvuRight<0 -> monocular edge (src/Optimizer.cc:794)
-      mpStart[E.mp + 1]++;
-      kfStart[E.kf + 1]++;
-    }
-    for (int i = 0; i < P.n_mp; i++) mpStart[i + 1] += mpStart[i];
-    for (int i = 0; i < P.n_kf; i++) kfStart[i + 1] += kfStart[i];
-    {
-      std::vector<int> cm(mpStart.begin(), mpStart.end() - 1), ck(kfStart.begin(), kfStart.end() - 1);
-      for (int e = 0; e < P.n_edges; e++) {
-        mpEdges[cm[eMp[e]]++] = e;
-        kfEdges[ck[eKf[e]]++] = e;
-      }
-    }
-    BaWin& Wn = wins[w];
-    Wn.nKf = P.n_kf; Wn.nLocal = P.n_local; Wn.nMp = P.n_mp; Wn.nEdges = P.n_edges; Wn.nFree = nFree;
+    const b2s_ba_problem& P = probs[w];
+    BaWin& Wn = s.win[w];
+    Wn.nKf = P.n_kf; Wn.nLocal = P.n_local; Wn.nMp = P.n_mp; Wn.nEdges = P.n_edges; Wn.nFree = nFree[w];
     Wn.fx = P.fx; Wn.fy = P.fy; Wn.cx = P.cx; Wn.cy = P.cy; Wn.bf = P.bf;
-    BaState& S0 = states[w];
+    BaState& S0 = s.st[w];
     memset(&S0, 0, sizeof(S0));
-    S0.active = (P.its1 > 0) ? 1 : 0;
+    S0.active = 1;
     S0.needBuild = 1;
     S0.robust = 1;
     S0.its[0] = P.its1; S0.its[1] = P.its2;
     S0.ni = 2;
-    maxE = std::max(maxE, P.n_edges); maxMp = std::max(maxMp, P.n_mp); maxKf = std::max(maxKf, P.n_kf);
-    maxN = std::max(maxN, nFree * 6 + 1);
-    maxFree = std::max(maxFree, nFree);
-#define UP(dst, vec, stride) \
-  if (!(vec).empty()) B2S_CUDA(cudaMemcpyAsync((dst) + (size_t)w * (stride), (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, st))
-    UP(d.pose, pose, (size_t)d.capKf * PSTRIDE);
-    UP(d.pts, pts, (size_t)d.capMp * 3);
-    UP(d.poseIndex, pidx, d.capKf);
-    UP(d.freeKf, freeKf, d.capKf);
-    UP(d.eKf, eKf, d.capE); UP(d.eMp, eMp, d.capE);
-    UP(d.eObs, eObs, (size_t)d.capE * 3); UP(d.eW, eW, d.capE);
-    UP(d.eStereo, eSt, d.capE);
-    UP(d.mpStart, mpStart, d.capMp + 1); UP(d.mpEdges, mpEdges, d.capE);
-    UP(d.kfStart, kfStart, d.capKf + 1); UP(d.kfEdges, kfEdges, d.capE);
-#undef UP
-    B2S_CUDA(cudaMemsetAsync(d.eLevel + (size_t)w * d.capE, 0, d.capE, st));
-    B2S_CUDA(cudaMemsetAsync(d.lmEdge + (size_t)w * d.capMp * d.capKf, 0xFF, (size_t)P.n_mp * d.capKf * 4, st));
-    B2S_CUDA(cudaMemsetAsync(d.chi2 + (size_t)w * d.capE, 0, (size_t)d.capE * 8, st));
-    B2S_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
+    s.usePairs[w] = 1;
+    maxE = std::max(maxE, P.n_edges); maxMp = std::max(maxMp, P.n_mp); maxFree = std::max(maxFree, nFree[w]);
   }
-  B2S_CUDA(cudaMemcpyAsync(d.win, wins.data(), batch * sizeof(BaWin), cudaMemcpyHostToDevice, st));
-  B2S_CUDA(cudaMemcpyAsync(d.st, states.data(), batch * sizeof(BaState), cudaMemcpyHostToDevice, st));
-  const int gE = std::max(1, div_up(maxE, 256)), gM = std::max(1, div_up(maxMp, 128));
-  const int gRestore = std::max(1, div_up(std::max(maxMp * 3, maxKf * PSTRIDE), 256));
+  const size_t nb = (size_t)batch;
+#define UPALL(dst, src, stride, type) \
+  B2S_CUDA(cudaMemcpyAsync((dst), (src), nb * (size_t)(stride) * sizeof(type), cudaMemcpyHostToDevice, st))
+  UPALL(d.pose, s.pose, d.capKf * PSTRIDE, double);
+  UPALL(d.pts, s.pts, (size_t)d.capMp * 3, double);
+  UPALL(d.poseIndex, s.pidx, d.capKf, int);
+  UPALL(d.freeKf, s.freeKf, d.capKf, int);
+  UPALL(d.eKf, s.eKf, d.capE, int);
+  UPALL(d.eMp, s.eMp, d.capE, int);
+  UPALL(d.eObs, s.eObs, (size_t)d.capE * 3, float);
+  UPALL(d.eW, s.eW, d.capE, float);
+  UPALL(d.eStereo, s.eSt, d.capE, uint8_t);
+  UPALL(d.mpStart, s.mpStart, d.capMp + 1, int);
+  UPALL(d.mpEdges, s.mpEdges, d.capE, int);
+  UPALL(d.kfStart, s.kfStart, d.capKf + 1, int);
+  UPALL(d.kfEdges, s.kfEdges, d.capE, int);
+  UPALL(d.usePairs, s.usePairs, 1, int);
+  UPALL(d.win, s.win, 1, BaWin);
+  UPALL(d.st, s.st, 1, BaState);
+#undef UPALL
+  B2S_CUDA(cudaMemsetAsync(d.eLevel, 0, nb * d.capE, st));
+  B2S_CUDA(cudaMemsetAsync(d.chi2, 0, nb * d.capE * 8, st));
+  B2S_CUDA(cudaMemsetAsync(d.lmEdge, 0xFF, nb * (size_t)d.capMp * d.capKf * 4, st));
+  B2S_CUDA(cudaMemsetAsync(d.bar, 0, nb * 4, st));
+  B2S_CUDA(cudaMemsetAsync(d.prof, 0, nb * 16 * 8, st));
+  const auto tPrep = std::chrono::steady_clock::now();
+  const int gE = std::max(1, div_up(maxE, 256));
   k_lm_edge<<<dim3(gE, batch), 256, 0, st>>>(d);
-  h->launches++;
-  bool stopSent = false;
-  for (int step = 0; step < 400; step++) {
-    if (stop && *stop && !stopSent) {  // asynchronous abort (LocalMapping::InsertKeyFrame sets mbAbortBA)
-      for (int w = 0; w < batch; w++) {
-        const int one = 1;
-        B2S_CUDA(cudaMemcpyAsync((char*)(d.st + w) + offsetof(BaState, stop), &one, 4, cudaMemcpyHostToDevice, st));
-      }
-      stopSent = true;
-    }
-    k_errors<<<dim3(gE, batch), 256, 0, st>>>(d, 0);
-    k_build_landmarks<<<dim3(gM, batch), 128, 0, st>>>(d);
-    k_build_poses<<<dim3(maxKf, batch), 128, 0, st>>>(d);
-    k_control_begin<<<div_up(batch, 64), 64, 0, st>>>(d, batch);
-    k_dinv<<<dim3(gM, batch), 128, 0, st>>>(d);
-    k_schur_pose<<<dim3(maxKf, batch), 128, 0, st>>>(d);
-    k_schur_blocks<<<dim3(std::max(1, maxFree * (maxFree + 1) / 2), batch), 64, 0, st>>>(d);
-    k_chol<<<batch, CHOL_T, h->cholSmem, st>>>(d);
-    k_backsub<<<dim3(gM, batch), 128, 0, st>>>(d);
-    k_update_poses<<<batch, 128, 0, st>>>(d);
-    k_errors<<<dim3(gE, batch), 256, 0, st>>>(d, 1);
-    k_control_end<<<div_up(batch, 64), 64, 0, st>>>(d, batch);
-    k_restore_outliers<<<dim3(gRestore, batch), 256, 0, st>>>(d);
-    k_outliers<<<dim3(gE, batch), 256, 0, st>>>(d);
-    B2S_CUDA(cudaMemsetAsync(d.anyActive, 0, 4, st));
-    k_any_active<<<div_up(batch, 64), 64, 0, st>>>(d, batch);
-    h->launches += 15;
-    B2S_CUDA(cudaMemcpyAsync(h->hAny, d.anyActive, 4, cudaMemcpyDeviceToHost, st));
-    B2S_CUDA(cudaStreamSynchronize(st));
-    if (!*h->hAny) break;
+  const int nblk = std::max(1, maxFree * (maxFree + 1) / 2);
+  k_pair_build<<<dim3(nblk, batch), 64, 0, st>>>(d, 0);
+  k_pair_scan<<<div_up(batch, 64), 64, 0, st>>>(d, batch);
+  k_pair_build<<<dim3(nblk, batch), 64, 0, st>>>(d, 1);
+  // ---- the whole LM loop of every window: one persistent launch, nCta co-resident CTAs per window
+  const int chunk = std::min(batch, h->numSMs);  // windows per cooperative launch (all their CTAs must be co-resident)
+  int nCta = std::max(1, std::min(8, h->numSMs / chunk));
+  if (const char* ev = getenv("B2S_BA_NCTA")) nCta = std::max(1, std::min(nCta, atoi(ev)));  // tuning knob
+  for (int wBase = 0; wBase < batch; wBase += chunk) {
+    int nw = std::min(chunk, batch - wBase);
+    void* args[] = {(void*)&d, (void*)&nCta, (void*)&wBase};
+    B2S_CUDA(cudaLaunchCooperativeKernel((const void*)k_local_ba, dim3(nw * nCta), dim3(BA_T), args, h->smemBytes, st));
+    h->launches++;
   }
-  B2S_CUDA(cudaGetLastError());
-  // write-back values (src/Optimizer.cc:961-996): SetPose(toCvMat(SE3quat)), SetWorldPos(toCvMat(estimate))
-  B2S_CUDA(cudaMemcpyAsync(states.data(), d.st, batch * sizeof(BaState), cudaMemcpyDeviceToHost, st));
-  for (int w = 0; w < batch; w++) {
-    const b2s_ba_problem& P = probs[w];
-    b2s_ba_result& R = res[w];
-    std::vector<double> pose((size_t)P.n_kf * PSTRIDE), pts((size_t)P.n_mp * 3);
-    B2S_CUDA(cudaMemcpyAsync(pose.data(), d.pose + (size_t)w * d.capKf * PSTRIDE, pose.size() * 8, cudaMemcpyDeviceToHost, st));
-    if (P.n_mp) B2S_CUDA(cudaMemcpyAsync(pts.data(), d.pts + (size_t)w * d.capMp * 3, pts.size() * 8, cudaMemcpyDeviceToHost, st));
-    if (R.edge_outlier && P.n_edges)
-      B2S_CUDA(cudaMemcpyAsync(R.edge_outlier, d.eOutlier + (size_t)w * d.capE, P.n_edges, cudaMemcpyDeviceToHost, st));
-    B2S_CUDA(cudaStreamSynchronize(st));
-    if (R.Tcw_out) {
-      for (int k = 0; k < P.n_local; k++) {
-        const double* q = &pose[(size_t)k * PSTRIDE];
-        const double tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
-        const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
-        const double txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
-        const double tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
-        float* T = R.Tcw_out + (size_t)k * 16;
-        T[0] = (float)(1 - (tyy + tzz)); T[1] = (float)(txy - twz); T[2] = (float)(txz + twy); T[3] = (float)q[4];
-        T[4] = (float)(txy + twz); T[5] = (float)(1 - (txx + tzz)); T[6] = (float)(tyz - twx); T[7] = (float)q[5];
-        T[8] = (float)(txz - twy); T[9] = (float)(tyz + twx); T[10] = (float)(1 - (txx + tyy)); T[11] = (float)q[6];
-        T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
+  h->launches += 4;
+  // asynchronous abort (LocalMapping::InsertKeyFrame sets mbAbortBA): forward the flag while the kernel runs
+  if (stop) {
+    bool sent = false;
+    while (cudaStreamQuery(st) == cudaErrorNotReady) {
+      if (*stop && !sent) {
+        const int one = 1;
+        for (int w = 0; w < batch; w++)
+          cudaMemcpyAsync((char*)(d.st + w) + offsetof(BaState, stop), &one, 4, cudaMemcpyHostToDevice, h->stream2);
+        cudaStreamSynchronize(h->stream2);
+        sent = true;
       }
+      std::this_thread::yield();
     }
-    if (R.points_out)
-      for (size_t i = 0; i < pts.size(); i++) R.points_out[i] = (float)pts[i];
-    R.chi2_final = states[w].chi2Final;
-    R.n_trials = states[w].nTrials;
-    if (R.trace) {
-      const int n = std::min(states[w].nTrials, 255);
-      for (int i = 0; i < n; i++) R.trace[i] = states[w].trace[i];
-      R.trace[n] = -1;
+  }
+  // write-back values (src/Optimizer.cc:961-996): SetPose(toCvMat(SE3quat)), SetWorldPos(toCvMat(estimate))
+  B2S_CUDA(cudaMemcpyAsync(s.pose, d.pose, nb * d.capKf * PSTRIDE * 8, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(s.pts, d.pts, nb * (size_t)d.capMp * 3 * 8, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(s.eOutlier, d.eOutlier, nb * d.capE, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(s.st, d.st, nb * sizeof(BaState), cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  B2S_CUDA(cudaGetLastError());
+  for (int w = 0; w < batch; w++)
+    if (s.st[w].finishedRound0) {
+      set_error("b2s_local_ba: window %d: LM kernel barrier timed out (CTAs not co-resident?)", w);
+      return B2S_ERR_CUDA;
     }
+  const auto tLoop = std::chrono::steady_clock::now();
+  {
+    const int nth = std::max(1, std::min(batch, std::min(16, (int)std::thread::hardware_concurrency())));
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; t++)
+      th.emplace_back([&, t]() {
+        for (int w = t; w < batch; w += nth) {
+          const b2s_ba_problem& P = probs[w];
+          b2s_ba_result& R = res[w];
+          const double* pose = s.pose + (size_t)w * d.capKf * PSTRIDE;
+          const double* pts = s.pts + (size_t)w * d.capMp * 3;
+          if (R.Tcw_out) {
+            for (int k = 0; k < P.n_local; k++) {
+              const double* q = pose + (size_t)k * PSTRIDE;
+              const double tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
+              const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+              const double txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+              const double tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+              float* T = R.Tcw_out + (size_t)k * 16;
+              T[0] = (float)(1 - (tyy + tzz)); T[1] = (float)(txy - twz); T[2] = (float)(txz + twy); T[3] = (float)q[4];
+              T[4] = (float)(txy + twz); T[5] = (float)(1 - (txx + tzz)); T[6] = (float)(tyz - twx); T[7] = (float)q[5];
+              T[8] = (float)(txz - twy); T[9] = (float)(tyz + twx); T[10] = (float)(1 - (txx + tyy)); T[11] = (float)q[6];
+              T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
+            }
+          }
+          if (R.points_out)
+            for (size_t i = 0; i < (size_t)P.n_mp * 3; i++) R.points_out[i] = (float)pts[i];
+          if (R.edge_outlier && P.n_edges) memcpy(R.edge_outlier, s.eOutlier + (size_t)w * d.capE, P.n_edges);
+          R.chi2_final = s.st[w].chi2Final;
+          R.n_trials = s.st[w].nTrials;
+          if (R.trace) {
+            const int n = std::min(s.st[w].nTrials, 255);
+            for (int i = 0; i < n; i++) R.trace[i] = s.st[w].trace[i];
+            R.trace[n] = -1;
+          }
+        }
+      });
+    for (auto& t : th) t.join();
+  }
+  if (dbg) {
+    const auto tEnd = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    long long prof[16];
+    cudaMemcpy(prof, d.prof, sizeof(prof), cudaMemcpyDeviceToHost);
+    static const char* names[11] = {"build_lm", "build_pose", "ctl_begin", "dinv", "schur_pose", "schur_blk", "chol",
+                                    "backsub", "errors", "ctl_end", "restore/outl"};
+    fprintf(stderr, "[b2s_local_ba] window 0 phase Mcycles:");
+    for (int k = 0; k < 11; k++) fprintf(stderr, " %s=%.2f", names[k], prof[k] / 1e6);
+    fprintf(stderr, "\n");
+    fprintf(stderr, "[b2s_local_ba] batch=%d nCta=%d prep+upload %.2f ms, structure+LM kernel %.2f ms, write-back %.2f ms\n",
+            batch, nCta, ms(tStart, tPrep), ms(tPrep, tLoop), ms(tLoop, tEnd));
   }
   return B2S_OK;
 }

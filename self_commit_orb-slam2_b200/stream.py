@@ -100,8 +100,12 @@ class StereoStream:
     def step_host(self, imgs_host_np, run_ba=True):
         """imgs_host_np: numpy uint8 [2F, h, w]. Returns (counts, nmatches, ba_out); everything ends up in host memory."""
         F, cap = self.F, self.cap
-        res_kps = np.zeros((2 * F, cap), keypoint_dtype)
-        res_desc = np.zeros((2 * F, cap, 32), np.uint8)
+        if getattr(self, "_h_kps", None) is None:  # pinned result buffers, allocated once
+            self._h_kps_t = torch.zeros((2 * F, cap, KP_BYTES), dtype=torch.uint8).pin_memory()
+            self._h_desc_t = torch.zeros((2 * F, cap, 32), dtype=torch.uint8).pin_memory()
+            self._h_kps = self._h_kps_t.numpy().view(keypoint_dtype).reshape(2 * F, cap)
+            self._h_desc = self._h_desc_t.numpy()
+        res_kps, res_desc = self._h_kps, self._h_desc
         n = np.zeros(2 * F, np.int32)
         ptrs = (_vp * (2 * F))(*[imgs_host_np[i].ctypes.data for i in range(2 * F)])
         L = lib()
