@@ -220,56 +220,44 @@ __device__ __forceinline__ void win_barrier(unsigned int* bar, unsigned int& epo
 }
 
 struct EdgeJac {
-  double A[3][3], B[3][6];
+  double A[3][3], B[3][6];  // a monocular edge has an all-zero third row (adds exact zeros to every product)
   double Xc[3];
-  int D;
 };
-// linearizeOplus (types_six_dof_expmap.cpp:103-139 mono, :188-234 stereo)
+// linearizeOplus (types_six_dof_expmap.cpp:103-139 mono, :188-234 stereo).  The reference divides by z and z^2 in
+// every entry; here 1/z is formed once (differences ~1 ulp, far inside the 1e-5 bar).
 __device__ __forceinline__ void edge_jacobians(const double* P, const double* X, bool st, double fx, double fy, double bf,
                                                EdgeJac& J) {
   double R[3][3];
   pose_map(P, X, J.Xc);
   quat_to_R(P, R);
-  const double x = J.Xc[0], y = J.Xc[1], z = J.Xc[2], z_2 = z * z;
-  J.D = st ? 3 : 2;
-  if (st) {
-    for (int c = 0; c < 3; c++) {
-      J.A[0][c] = -fx * R[0][c] / z + fx * x * R[2][c] / z_2;
-      J.A[1][c] = -fy * R[1][c] / z + fy * y * R[2][c] / z_2;
-      J.A[2][c] = J.A[0][c] - bf * R[2][c] / z_2;
-    }
-  } else {
-    const double tmp[2][3] = {{fx, 0, -x / z * fx}, {0, fy, -y / z * fy}};
-    for (int r = 0; r < 2; r++)
-      for (int c = 0; c < 3; c++) {
-        double s = 0;
-        for (int k = 0; k < 3; k++) s += (-1. / z * tmp[r][k]) * R[k][c];
-        J.A[r][c] = s;
-      }
-    J.A[2][0] = J.A[2][1] = J.A[2][2] = 0;
+  const double x = J.Xc[0], y = J.Xc[1], z = J.Xc[2];
+  const double iz = 1.0 / z, iz2 = iz * iz;
+  const double fxz = fx * iz, fyz = fy * iz, fxx = fx * x * iz2, fyy = fy * y * iz2;
+  const double bz = st ? bf * iz2 : 0.0;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    J.A[0][c] = -fxz * R[0][c] + fxx * R[2][c];
+    J.A[1][c] = -fyz * R[1][c] + fyy * R[2][c];
+    J.A[2][c] = st ? (J.A[0][c] - bz * R[2][c]) : 0.0;
   }
-  J.B[0][0] = x * y / z_2 * fx;
-  J.B[0][1] = -(1 + (x * x / z_2)) * fx;
-  J.B[0][2] = y / z * fx;
-  J.B[0][3] = -1. / z * fx;
+  J.B[0][0] = x * y * iz2 * fx;
+  J.B[0][1] = -(1 + (x * x * iz2)) * fx;
+  J.B[0][2] = y * iz * fx;
+  J.B[0][3] = -iz * fx;
   J.B[0][4] = 0;
-  J.B[0][5] = x / z_2 * fx;
-  J.B[1][0] = (1 + y * y / z_2) * fy;
-  J.B[1][1] = -x * y / z_2 * fy;
-  J.B[1][2] = -x / z * fy;
+  J.B[0][5] = x * iz2 * fx;
+  J.B[1][0] = (1 + y * y * iz2) * fy;
+  J.B[1][1] = -x * y * iz2 * fy;
+  J.B[1][2] = -x * iz * fy;
   J.B[1][3] = 0;
-  J.B[1][4] = -1. / z * fy;
-  J.B[1][5] = y / z_2 * fy;
-  if (st) {
-    J.B[2][0] = J.B[0][0] - bf * y / z_2;
-    J.B[2][1] = J.B[0][1] + bf * x / z_2;
-    J.B[2][2] = J.B[0][2];
-    J.B[2][3] = J.B[0][3];
-    J.B[2][4] = 0;
-    J.B[2][5] = J.B[0][5] - bf / z_2;
-  } else {
-    for (int c = 0; c < 6; c++) J.B[2][c] = 0;
-  }
+  J.B[1][4] = -iz * fy;
+  J.B[1][5] = y * iz2 * fy;
+  J.B[2][0] = st ? (J.B[0][0] - bz * y) : 0.0;
+  J.B[2][1] = st ? (J.B[0][1] + bz * x) : 0.0;
+  J.B[2][2] = st ? J.B[0][2] : 0.0;
+  J.B[2][3] = st ? J.B[0][3] : 0.0;
+  J.B[2][4] = 0;
+  J.B[2][5] = st ? (J.B[0][5] - bz) : 0.0;
 }
 
 // computeError (types_six_dof_expmap.h:90-95 mono, :122-127 stereo; cam_project .cpp:141-157) from camera coordinates
@@ -330,24 +318,32 @@ __device__ void phase_build_landmarks(const BaPtrs& p, const WinCtx& c, const Ba
       if (robust) huber(c2, delta_of(stereo), rho0, rho1);
       chi += rho0;
       double omr[3];
+#pragma unroll
       for (int r = 0; r < 3; r++) omr[r] = -(w0 * er[r]) * rho1;
       const double wq = rho1 * w0;
+#pragma unroll
       for (int i = 0; i < 3; i++) {
         double s = 0;
-        for (int r = 0; r < J.D; r++) s += J.A[r][i] * omr[r];
+#pragma unroll
+        for (int r = 0; r < 3; r++) s += J.A[r][i] * omr[r];
         bl[i] += s;
+#pragma unroll
         for (int j = 0; j < 3; j++) {
           double hh = 0;
-          for (int r = 0; r < J.D; r++) hh += J.A[r][i] * wq * J.A[r][j];
+#pragma unroll
+          for (int r = 0; r < 3; r++) hh += J.A[r][i] * wq * J.A[r][j];
           H[i * 3 + j] += hh;
         }
       }
       if (p.poseIndex[(size_t)w * p.capKf + kf] >= 0) {
         double* Wb = p.W + eo * 18;
+#pragma unroll
         for (int i = 0; i < 6; i++)
+#pragma unroll
           for (int j = 0; j < 3; j++) {
             double hh = 0;
-            for (int r = 0; r < J.D; r++) hh += J.B[r][i] * wq * J.A[r][j];
+#pragma unroll
+            for (int r = 0; r < 3; r++) hh += J.B[r][i] * wq * J.A[r][j];
             Wb[i * 3 + j] = hh;
           }
       }
@@ -390,6 +386,7 @@ __device__ void phase_build_poses(const BaPtrs& p, const WinCtx& c, const BaWin&
       }
       const double* er = p.err + eo * 3;
       double omr[3];
+#pragma unroll
       for (int r = 0; r < 3; r++) omr[r] = -(w0 * er[r]) * rho1;
       const double wq = rho1 * w0;
       int t = 0;
@@ -398,14 +395,16 @@ __device__ void phase_build_poses(const BaPtrs& p, const WinCtx& c, const BaWin&
 #pragma unroll
         for (int j = i; j < 6; j++) {
           double hh = 0;
-          for (int r = 0; r < J.D; r++) hh += J.B[r][i] * wq * J.B[r][j];
+#pragma unroll
+          for (int r = 0; r < 3; r++) hh += J.B[r][i] * wq * J.B[r][j];
           acc[t++] += hh;
         }
       }
 #pragma unroll
       for (int i = 0; i < 6; i++) {
         double s = 0;
-        for (int r = 0; r < J.D; r++) s += J.B[r][i] * omr[r];
+#pragma unroll
+        for (int r = 0; r < 3; r++) s += J.B[r][i] * omr[r];
         acc[21 + i] += s;
       }
     }
@@ -458,7 +457,6 @@ __device__ void control_begin(const BaPtrs& p, int w, int nCta) {
 
 // Schur complement (block_solver.hpp:381-439), atomic-free:
 //   phase_dinv         per landmark:  Dinv = (Hll + lambda I)^-1,  db = Dinv b_l
-//   phase_schur_pose   per free pose: Y_e = W_e Dinv, augmented row  b_p - sum_e W_e db
 //   phase_schur_blocks per lower block (i1 >= i2): S(i1,i2) = [Hpp + lambda I] - sum_{l seen by both} Y_a W_c^T
 __device__ void phase_dinv(const BaPtrs& p, const WinCtx& c, const BaWin& W, double lambda) {
   const int w = c.w;
@@ -483,48 +481,6 @@ __device__ void phase_dinv(const BaPtrs& p, const WinCtx& c, const BaWin& W, dou
   }
 }
 
-__device__ void phase_schur_pose(const BaPtrs& p, const WinCtx& c, const BaWin& W) {
-  const int w = c.w;
-  const int lane = threadIdx.x & 31;
-  const int nWarps = c.gthreads >> 5, gw = c.gtid >> 5;
-  const int* ks = p.kfStart + (size_t)w * (p.capKf + 1);
-  const int* ke = p.kfEdges + (size_t)w * p.capE;
-  const int n = W.nFree * 6;
-  for (int pi = gw; pi < W.nFree; pi += nWarps) {
-    const int kf = p.freeKf[(size_t)w * p.capKf + pi];
-    double r[6] = {0, 0, 0, 0, 0, 0};
-    for (int k = ks[kf] + lane; k < ks[kf + 1]; k += 32) {
-      const int e = ke[k];
-      const size_t eo = (size_t)w * p.capE + e;
-      if (p.eLevel[eo]) continue;
-      const size_t mo = (size_t)w * p.capMp + p.eMp[eo];
-      const double* Di = p.Dinv + mo * 9;
-      const double* d3 = p.db + mo * 3;
-      const double* Wb = p.W + eo * 18;
-      double* Yb = p.Y + eo * 18;
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        const double w0 = Wb[i * 3], w1 = Wb[i * 3 + 1], w2 = Wb[i * 3 + 2];
-        Yb[i * 3 + 0] = w0 * Di[0] + w1 * Di[3] + w2 * Di[6];
-        Yb[i * 3 + 1] = w0 * Di[1] + w1 * Di[4] + w2 * Di[7];
-        Yb[i * 3 + 2] = w0 * Di[2] + w1 * Di[5] + w2 * Di[8];
-        r[i] += w0 * d3[0] + w1 * d3[1] + w2 * d3[2];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) r[i] += __shfl_down_sync(0xffffffffu, r[i], o);
-    }
-    if (lane == 0) {
-      const double* bp = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)pi * 6;
-      double* aug = p.S + (size_t)w * p.ldS * p.ldS + (size_t)n * p.ldS + pi * 6;
-#pragma unroll
-      for (int i = 0; i < 6; i++) aug[i] = bp[i] - r[i];
-    }
-  }
-}
-
 __device__ __forceinline__ void decode_block(int t, int& i1, int& i2) {
   i1 = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
   while ((i1 + 1) * (i1 + 2) / 2 <= t) i1++;
@@ -532,81 +488,158 @@ __device__ __forceinline__ void decode_block(int t, int& i1, int& i2) {
   i2 = t - i1 * (i1 + 1) / 2;
 }
 
-// one warp per lower block; lanes stride over the block's covisibility pairs, ordered shuffle reduction of the 36 sums
+// Butterfly reduce-scatter of 32 per-lane values across the warp: lane L ends with the warp-wide sum of element L
+// (31 double shuffles instead of 32 x 5; fixed summation tree => deterministic).
+__device__ __forceinline__ double warp_reduce_scatter32(double (&v)[32], int lane) {
+  double a16[16];
+  const bool h16 = lane & 16;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const double keep = h16 ? v[k + 16] : v[k], send = h16 ? v[k] : v[k + 16];
+    a16[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  double a8[8];
+  const bool h8 = lane & 8;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const double keep = h8 ? a16[k + 8] : a16[k], send = h8 ? a16[k] : a16[k + 8];
+    a8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  double a4[4];
+  const bool h4 = lane & 4;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const double keep = h4 ? a8[k + 4] : a8[k], send = h4 ? a8[k] : a8[k + 4];
+    a4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  double a2[2];
+  const bool h2 = lane & 2;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const double keep = h2 ? a4[k + 2] : a4[k], send = h2 ? a4[k] : a4[k + 2];
+    a2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const bool h1 = lane & 1;
+  const double keep = h1 ? a2[1] : a2[0], send = h1 ? a2[0] : a2[1];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+// Schur complement (block_solver.hpp:381-439): one warp per lower block (i1 >= i2); lanes stride over the block's
+// covisibility pairs (edge a of pose i1, edge c of pose i2, same landmark l) and accumulate (W_a Dinv_l) W_c^T; the
+// diagonal blocks also accumulate W_a (Dinv_l b_l) for the right-hand side.  S(i1,i2) = [Hpp + lambda I] - sum.
 __device__ void phase_schur_blocks(const BaPtrs& p, const WinCtx& c, const BaWin& W, double lambda) {
   const int w = c.w;
   const int lane = threadIdx.x & 31;
   const int nWarps = c.gthreads >> 5, gw = c.gtid >> 5;
   const int nb = W.nFree * (W.nFree + 1) / 2;
+  const int n = W.nFree * 6;
   const int usePairs = p.usePairs[w];
   const int* off = p.blkOff + (size_t)w * (p.capBlk + 1);
   const int* pa = p.pairA + (size_t)w * p.capPairs;
   const int* pc = p.pairC + (size_t)w * p.capPairs;
+  const int* ks = p.kfStart + (size_t)w * (p.capKf + 1);
+  const int* ke = p.kfEdges + (size_t)w * p.capE;
+  const int* lm = p.lmEdge + (size_t)w * p.capMp * p.capKf;
   for (int t = gw; t < nb; t += nWarps) {
     int i1, i2;
     decode_block(t, i1, i2);
-    double acc[36];
+    const bool diag = (i1 == i2);
+    double acc[32], tail[10];  // entries 0..31, entries 32..35 + the 6 right-hand-side sums
 #pragma unroll
-    for (int k = 0; k < 36; k++) acc[k] = 0;
+    for (int k = 0; k < 32; k++) acc[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 10; k++) tail[k] = 0;
+    int qBeg, qEnd;
     if (usePairs) {
-      for (int q = off[t] + lane; q < off[t + 1]; q += 32) {
-        const size_t eoa = (size_t)w * p.capE + pa[q], eoc = (size_t)w * p.capE + pc[q];
-        if (p.eLevel[eoa] | p.eLevel[eoc]) continue;
-        const double* Ya = p.Y + eoa * 18;
-        const double* Wc = p.W + eoc * 18;
-        double y[18], wc[18];
-#pragma unroll
-        for (int z = 0; z < 18; z++) {
-          y[z] = Ya[z];
-          wc[z] = Wc[z];
-        }
-#pragma unroll
-        for (int r = 0; r < 6; r++)
-#pragma unroll
-          for (int cc = 0; cc < 6; cc++)
-            acc[r * 6 + cc] += y[r * 3] * wc[cc * 3] + y[r * 3 + 1] * wc[cc * 3 + 1] + y[r * 3 + 2] * wc[cc * 3 + 2];
-      }
-    } else {  // pair list did not fit: probe the landmark->edge table (same sums, same order)
+      qBeg = off[t];
+      qEnd = off[t + 1];
+    } else {  // pair list did not fit: walk pose i1's edges and probe the landmark->edge table (same order)
       const int kf1 = p.freeKf[(size_t)w * p.capKf + i1];
-      const int* ks = p.kfStart + (size_t)w * (p.capKf + 1);
-      const int* ke = p.kfEdges + (size_t)w * p.capE;
-      const int* lm = p.lmEdge + (size_t)w * p.capMp * p.capKf;
-      for (int k = ks[kf1] + lane; k < ks[kf1 + 1]; k += 32) {
-        const int a = ke[k];
-        const size_t eoa = (size_t)w * p.capE + a;
-        if (p.eLevel[eoa]) continue;
-        const int cidx = lm[(size_t)p.eMp[eoa] * p.capKf + i2];
-        if (cidx < 0) continue;
-        const size_t eoc = (size_t)w * p.capE + cidx;
-        if (p.eLevel[eoc]) continue;
-        const double* Ya = p.Y + eoa * 18;
-        const double* Wc = p.W + eoc * 18;
-#pragma unroll
-        for (int r = 0; r < 6; r++)
-#pragma unroll
-          for (int cc = 0; cc < 6; cc++)
-            acc[r * 6 + cc] += Ya[r * 3] * Wc[cc * 3] + Ya[r * 3 + 1] * Wc[cc * 3 + 1] + Ya[r * 3 + 2] * Wc[cc * 3 + 2];
+      qBeg = ks[kf1];
+      qEnd = ks[kf1 + 1];
+    }
+    for (int q = qBeg + lane; q < qEnd; q += 32) {
+      int ea, ec;
+      if (usePairs) {
+        ea = pa[q];
+        ec = pc[q];
+      } else {
+        ea = ke[q];
+        ec = lm[(size_t)p.eMp[(size_t)w * p.capE + ea] * p.capKf + i2];
+        if (ec < 0) continue;
       }
-    }
+      const size_t eoa = (size_t)w * p.capE + ea, eoc = (size_t)w * p.capE + ec;
+      if (p.eLevel[eoa] | p.eLevel[eoc]) continue;
+      const size_t mo = (size_t)w * p.capMp + p.eMp[eoa];
+      const double* Di = p.Dinv + mo * 9;
+      const double* Wa = p.W + eoa * 18;
+      const double* Wc = p.W + eoc * 18;
+      double di[9], wc[18];
 #pragma unroll
-    for (int k = 0; k < 36; k++) {
+      for (int z = 0; z < 9; z++) di[z] = Di[z];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
-    }
-    if (lane == 0) {
-      double* Sb = p.S + (size_t)w * p.ldS * p.ldS + (size_t)(i1 * 6) * p.ldS + i2 * 6;
-      const double* Hp = p.Hpp + ((size_t)w * p.capKf + i1) * 36;
+      for (int z = 0; z < 18; z++) wc[z] = Wc[z];
+      double d0 = 0, d1 = 0, d2 = 0;
+      if (diag) {
+        const double* d3 = p.db + mo * 3;
+        d0 = d3[0]; d1 = d3[1]; d2 = d3[2];
+      }
 #pragma unroll
-      for (int r = 0; r < 6; r++)
+      for (int r = 0; r < 6; r++) {
+        const double w0 = Wa[r * 3], w1 = Wa[r * 3 + 1], w2 = Wa[r * 3 + 2];  // one row of W_a at a time (register budget)
+        const double y0 = w0 * di[0] + w1 * di[3] + w2 * di[6];
+        const double y1 = w0 * di[1] + w1 * di[4] + w2 * di[7];
+        const double y2 = w0 * di[2] + w1 * di[5] + w2 * di[8];
 #pragma unroll
         for (int cc = 0; cc < 6; cc++) {
-          double base = 0;
-          if (i1 == i2) {
-            base = Hp[r * 6 + cc];
-            if (r == cc) base += lambda;
-          }
-          Sb[(size_t)r * p.ldS + cc] = base - acc[r * 6 + cc];
+          const double v = y0 * wc[cc * 3] + y1 * wc[cc * 3 + 1] + y2 * wc[cc * 3 + 2];
+          const int en = r * 6 + cc;
+          if (en < 32) acc[en] += v;
+          else tail[en - 32] += v;
         }
+        if (diag) tail[4 + r] += w0 * d0 + w1 * d1 + w2 * d2;
+      }
+    }
+    const double mine = warp_reduce_scatter32(acc, lane);
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tail[k] += __shfl_xor_sync(0xffffffffu, tail[k], o);
+    }
+    double* Sb = p.S + (size_t)w * p.ldS * p.ldS + (size_t)(i1 * 6) * p.ldS + i2 * 6;
+    const double* Hp = p.Hpp + ((size_t)w * p.capKf + i1) * 36;
+    {
+      const int r = lane / 6, cc = lane - r * 6;
+      double base = 0;
+      if (diag) {
+        base = Hp[lane];
+        if (r == cc) base += lambda;
+      }
+      Sb[(size_t)r * p.ldS + cc] = base - mine;
+    }
+    if (lane < 4) {  // entries 32..35 = row 5, columns 2..5
+      const int cc = 2 + lane;
+      double base = 0;
+      if (diag) {
+        base = Hp[32 + lane];
+        if (cc == 5) base += lambda;
+      }
+      double tv = tail[0];
+      if (lane == 1) tv = tail[1];
+      if (lane == 2) tv = tail[2];
+      if (lane == 3) tv = tail[3];
+      Sb[(size_t)5 * p.ldS + cc] = base - tv;
+    }
+    if (diag && lane >= 8 && lane < 14) {  // augmented row: b_p - sum_e W_e (Dinv b_l)
+      const int r = lane - 8;
+      double tv = tail[4];
+      if (r == 1) tv = tail[5];
+      if (r == 2) tv = tail[6];
+      if (r == 3) tv = tail[7];
+      if (r == 4) tv = tail[8];
+      if (r == 5) tv = tail[9];
+      const double* bp = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)i1 * 6;
+      p.S[(size_t)w * p.ldS * p.ldS + (size_t)n * p.ldS + i1 * 6 + r] = bp[r] - tv;
     }
   }
 }
@@ -617,6 +650,9 @@ __device__ void phase_schur_blocks(const BaPtrs& p, const WinCtx& c, const BaWin
 // keeps each row in registers, the trailing update is 4x4 register tiled out of the shared-memory panel.
 constexpr int CHOL_PP = CHOL_BS + 1;
 __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) {
+  long long tc = clock64();
+  long long* prof = p.prof + (size_t)w * 16;
+#define CH_PROF(slot) if (threadIdx.x == 0) { const long long tn = clock64(); prof[slot] += tn - tc; tc = tn; }
   BaState& st = p.st[w];
   const int n = W.nFree * 6, N1 = n + 1, ld = p.ldS;
   double* S = p.S + (size_t)w * ld * ld;
@@ -667,6 +703,7 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
       Dblk[CHOL_BS * CHOL_PP + lane] = mydinv;
     }
     __syncthreads();
+    CH_PROF(11)
     for (int idx = tid; idx < wd * wd; idx += T) {
       const int r = idx / wd, cc = idx - r * wd;
       if (cc <= r) S[(size_t)(kb + r) * ld + kb + cc] = Dblk[r * CHOL_PP + cc];
@@ -693,6 +730,7 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
     }
     for (int idx = tid; idx < 4 * CHOL_PP; idx += T) panel[(m + idx / CHOL_PP) * CHOL_PP + idx % CHOL_PP] = 0.0;
     __syncthreads();
+    CH_PROF(12)
     const int mt = (m + 3) >> 2;
     const int ntile = mt * (mt + 1) / 2;
     for (int t = tid; t < ntile; t += T) {
@@ -731,6 +769,7 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
       }
     }
     __syncthreads();
+    CH_PROF(13)
   }
   // back substitution L^T x = y
   for (int i = tid; i < n; i += T) xs[i] = S[(size_t)n * ld + i];
@@ -750,9 +789,12 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
 #pragma unroll
       for (int r = 0; r < CHOL_BS; r++) col[r] = Dblk[r * CHOL_PP + lane];
       double tv = (lane < wd) ? xs[kb + lane] : 0.0;
+      double myrcp = 1.0;
+#pragma unroll
+      for (int j = 0; j < CHOL_BS; j++) myrcp = (lane == j) ? 1.0 / col[j] : myrcp;  // 1 / L[lane][lane], off the chain
 #pragma unroll
       for (int j = CHOL_BS - 1; j >= 0; j--) {
-        double xj = tv / col[j];  // meaningful on lane j (col[j] = L[j][j])
+        double xj = tv * myrcp;  // meaningful on lane j
         xj = __shfl_sync(0xffffffffu, xj, j);
         tv = (lane == j) ? xj : ((lane < j) ? fma(-col[j], xj, tv) : tv);
       }
@@ -772,6 +814,8 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
   for (int i = tid; i < n; i += T) x[i] = xs[i];
   if (tid == 0) st.solveOk = fail ? 0 : 1;
   __syncthreads();
+  CH_PROF(14)
+#undef CH_PROF
 }
 
 // landmark back-substitution (block_solver.hpp:461-481) + updates (types_sba.h:52-56, se3quat oplus) + computeScale
@@ -939,7 +983,7 @@ __device__ void phase_outliers(const BaPtrs& p, const WinCtx& c, const BaWin& W,
 }
 
 // ---------------------------------------------------------------- the persistent kernel: grid = batch * nCta CTAs
-constexpr int BA_T = 384;
+constexpr int BA_T = 256;
 __global__ void __launch_bounds__(BA_T) k_local_ba(BaPtrs p, int nCta, int wBase) {
   extern __shared__ __align__(16) double dsm[];
   __shared__ double red[32];
@@ -982,9 +1026,6 @@ __global__ void __launch_bounds__(BA_T) k_local_ba(BaPtrs p, int nCta, int wBase
     phase_dinv(p, c, W, lambda);
     win_barrier(bar, epoch, nCta, hung);
     BA_PROF(3)
-    phase_schur_pose(p, c, W);
-    win_barrier(bar, epoch, nCta, hung);
-    BA_PROF(4)
     phase_schur_blocks(p, c, W, lambda);
     win_barrier(bar, epoch, nCta, hung);
     BA_PROF(5)
@@ -1154,8 +1195,8 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   memset(&d, 0, sizeof(d));
   d.capKf = max_kf; d.capMp = max_mp; d.capE = max_edges;
   d.ldS = max_kf * 6 + 1;
-  d.nPartE = 16;  // >= CTAs per window
-  d.nPartM = 16;
+  d.nPartE = 32;  // >= CTAs per window
+  d.nPartM = 32;
   d.capBlk = max_kf * (max_kf + 1) / 2;
   d.capPairs = 8 * max_edges;
   const size_t B = max_batch;
@@ -1381,8 +1422,9 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
   k_pair_scan<<<div_up(batch, 64), 64, 0, st>>>(d, batch);
   k_pair_build<<<dim3(nblk, batch), 64, 0, st>>>(d, 1);
   // ---- the whole LM loop of every window: one persistent launch, nCta co-resident CTAs per window
-  const int chunk = std::min(batch, h->numSMs);  // windows per cooperative launch (all their CTAs must be co-resident)
-  int nCta = std::max(1, std::min(8, h->numSMs / chunk));
+  int chunk = std::min(batch, h->numSMs);  // windows per cooperative launch (all their CTAs must be co-resident)
+  if (const char* ev = getenv("B2S_BA_CHUNK")) chunk = std::max(1, std::min(chunk, atoi(ev)));  // tuning knob
+  int nCta = std::max(1, std::min(16, h->numSMs / chunk));
   if (const char* ev = getenv("B2S_BA_NCTA")) nCta = std::max(1, std::min(nCta, atoi(ev)));  // tuning knob
   for (int wBase = 0; wBase < batch; wBase += chunk) {
     int nw = std::min(chunk, batch - wBase);
@@ -1463,10 +1505,11 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
     };
     long long prof[16];
     cudaMemcpy(prof, d.prof, sizeof(prof), cudaMemcpyDeviceToHost);
-    static const char* names[11] = {"build_lm", "build_pose", "ctl_begin", "dinv", "schur_pose", "schur_blk", "chol",
-                                    "backsub", "errors", "ctl_end", "restore/outl"};
+    static const char* names[15] = {"build_lm", "build_pose", "ctl_begin", "dinv", "-", "schur_blk", "chol",
+                                    "backsub", "errors", "ctl_end", "restore/outl", "chol.diag", "chol.panel",
+                                    "chol.trail", "chol.backsub"};
     fprintf(stderr, "[b2s_local_ba] window 0 phase Mcycles:");
-    for (int k = 0; k < 11; k++) fprintf(stderr, " %s=%.2f", names[k], prof[k] / 1e6);
+    for (int k = 0; k < 15; k++) fprintf(stderr, " %s=%.2f", names[k], prof[k] / 1e6);
     fprintf(stderr, "\n");
     fprintf(stderr, "[b2s_local_ba] batch=%d nCta=%d prep+upload %.2f ms, structure+LM kernel %.2f ms, write-back %.2f ms\n",
             batch, nCta, ms(tStart, tPrep), ms(tPrep, tLoop), ms(tLoop, tEnd));

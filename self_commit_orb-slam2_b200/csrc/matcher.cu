@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(256) k_bow_topk(const uint8_t* __restrict__ de
                                                   const int32_t* __restrict__ nBarr, int capB,
                                                   uint32_t* __restrict__ topk, int32_t* __restrict__ candCnt) {
   __shared__ __align__(32) uint32_t sB[BOW_TILE * 8];
-  __shared__ int32_t sNode[BOW_TILE];
-  __shared__ uint8_t sValid[BOW_TILE];
+  __shared__ __align__(16) int32_t sNode[BOW_TILE];
+  __shared__ __align__(16) uint8_t sValid[BOW_TILE];
   const int pair = blockIdx.y;
   const int nA = nAarr[pair], nB = nBarr[pair];
   if ((int)(blockIdx.x * blockDim.x) >= nA) return;
@@ -145,14 +145,22 @@ __global__ void __launch_bounds__(256) k_bow_topk(const uint8_t* __restrict__ de
     }
     __syncthreads();
     if (rowOk) {
-      for (int j = 0; j < tn; j++) {
-        if (sNode[j] != na || !sValid[j]) continue;
-        const uint4 b0 = *reinterpret_cast<const uint4*>(&sB[j * 8]);
-        const uint4 b1 = *reinterpret_cast<const uint4*>(&sB[j * 8 + 4]);
-        const int d = __popc(da.w[0] ^ b0.x) + __popc(da.w[1] ^ b0.y) + __popc(da.w[2] ^ b0.z) + __popc(da.w[3] ^ b0.w) +
-                      __popc(da.w[4] ^ b1.x) + __popc(da.w[5] ^ b1.y) + __popc(da.w[6] ^ b1.z) + __popc(da.w[7] ^ b1.w);
-        cnt++;
-        topk_insert(t, ((uint32_t)d << 16) | (uint32_t)(j0 + j));
+      // four frame-side descriptors per iteration, branch-free distance; only the (rare) K-list insertion branches
+      for (int j = 0; j < tn; j += 4) {
+        const int4 nd = *reinterpret_cast<const int4*>(&sNode[j]);
+        const uint32_t vv = *reinterpret_cast<const uint32_t*>(&sValid[j]);
+        const int nds[4] = {nd.x, nd.y, nd.z, nd.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const uint4 b0 = *reinterpret_cast<const uint4*>(&sB[(j + q) * 8]);
+          const uint4 b1 = *reinterpret_cast<const uint4*>(&sB[(j + q) * 8 + 4]);
+          const int d = __popc(da.w[0] ^ b0.x) + __popc(da.w[1] ^ b0.y) + __popc(da.w[2] ^ b0.z) + __popc(da.w[3] ^ b0.w) +
+                        __popc(da.w[4] ^ b1.x) + __popc(da.w[5] ^ b1.y) + __popc(da.w[6] ^ b1.z) + __popc(da.w[7] ^ b1.w);
+          const bool ok = (nds[q] == na) && ((vv >> (8 * q)) & 0xffu) && (j + q < tn);
+          cnt += ok ? 1 : 0;
+          const uint32_t key = ok ? (((uint32_t)d << 16) | (uint32_t)(j0 + j + q)) : EMPTY;
+          if (key < t[TOPK - 1]) topk_insert(t, key);
+        }
       }
     }
   }

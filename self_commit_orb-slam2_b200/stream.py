@@ -56,6 +56,8 @@ class StereoStream:
             self.g_desc = torch.zeros((world, F, cap, 32), dtype=torch.uint8, **z)
             self.g_counts = torch.zeros((world, F), dtype=torch.int32, **z)
         self.d_imgs = torch.zeros((2 * F, height, width), dtype=torch.uint8, **z)
+        self._pool = None
+        self._ba_future = None
 
     # ------------------------------------------------------------------ device-resident step
     def upload(self, imgs_host):
@@ -63,13 +65,34 @@ class StereoStream:
         with torch.cuda.stream(self.stream):
             self.d_imgs.copy_(imgs_host, non_blocking=True)
 
-    def step_device(self, run_ba=True):
+    def step_device(self, run_ba=True, pipelined=False):
+        """Enqueue extraction (+ all-gather) + matching on the stream, then LocalBA of this step's windows.
+
+        pipelined=True runs the LocalBA batch on a worker thread (the C call releases the GIL and uses the solver's own
+        CUDA streams), so the caller can already enqueue the next step while it runs; at most one batch is in flight
+        (finish() joins the last one).  This also keeps ranks from waiting on each other's host-blocking LocalBA inside
+        the all-gather."""
         with torch.cuda.stream(self.stream):
             self._enqueue_extract_match()
         ba_out = None
         if run_ba and self.n_ba:  # own stream inside the solver; overlaps the work enqueued above
-            ba_out = self.opt.LocalBundleAdjustmentBatch([self.ba_problem] * self.n_ba)
+            if pipelined:
+                self.finish()
+                if self._pool is None:
+                    from concurrent.futures import ThreadPoolExecutor
+                    self._pool = ThreadPoolExecutor(max_workers=1)
+                self._ba_future = self._pool.submit(self.opt.LocalBundleAdjustmentBatch, [self.ba_problem] * self.n_ba)
+            else:
+                ba_out = self.opt.LocalBundleAdjustmentBatch([self.ba_problem] * self.n_ba)
         return ba_out
+
+    def finish(self):
+        """Join the LocalBA batch still in flight (pipelined mode); returns its result or None."""
+        out = None
+        if self._ba_future is not None:
+            out = self._ba_future.result()
+            self._ba_future = None
+        return out
 
     def _enqueue_extract_match(self):
         F, cap = self.F, self.cap
@@ -97,7 +120,7 @@ class StereoStream:
                                           _vp(self.match.data_ptr()), _vp(self.nmatch.data_ptr()), _vp(st)))
 
     # ------------------------------------------------------------------ end-to-end step through the host-buffer C ABI
-    def step_host(self, imgs_host_np, run_ba=True):
+    def step_host(self, imgs_host_np, run_ba=True, pipelined=False):
         """imgs_host_np: numpy uint8 [2F, h, w]. Returns (counts, nmatches, ba_out); everything ends up in host memory."""
         F, cap = self.F, self.cap
         if getattr(self, "_h_kps", None) is None:  # pinned result buffers, allocated once
@@ -130,7 +153,14 @@ class StereoStream:
                                          p(match), p(nm)))
         ba_out = None
         if run_ba and self.n_ba:
-            ba_out = self.opt.LocalBundleAdjustmentBatch([self.ba_problem] * self.n_ba)
+            if pipelined:  # results of the previous step's windows are returned; finish() joins the last batch
+                ba_out = self.finish()
+                if self._pool is None:
+                    from concurrent.futures import ThreadPoolExecutor
+                    self._pool = ThreadPoolExecutor(max_workers=1)
+                self._ba_future = self._pool.submit(self.opt.LocalBundleAdjustmentBatch, [self.ba_problem] * self.n_ba)
+            else:
+                ba_out = self.opt.LocalBundleAdjustmentBatch([self.ba_problem] * self.n_ba)
         return n, nm, ba_out, (res_kps, res_desc, match)
 
     def launch_count(self):
