@@ -27,26 +27,36 @@ __constant__ int c_umax[16];
 __global__ void __launch_bounds__(128) k_resize(ExtractGeom g, int l, uint8_t* __restrict__ pyr,
                                                 const int16_t* __restrict__ rxOfs, const uint32_t* __restrict__ rxAlpha,
                                                 const int16_t* __restrict__ ryOfs, const uint32_t* __restrict__ ryBeta) {
+  // four destination pixels per thread: one 8-byte + one 16-byte table load, one 32-bit store (the x tables of every
+  // level are padded to a multiple of 4 entries; rows are padded to 16 bytes, padding bytes are written as 0)
   const LevelGeom& S = g.lv[l - 1];
   const LevelGeom& D = g.lv[l];
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y;
-  if (x >= D.w) return;
+  const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;  // block = 32 x 4 threads = 128 pixels x 4 rows
+  const int y = blockIdx.y * 4 + threadIdx.y;
+  if (x0 >= D.w || y >= D.h) return;
   const uint8_t* src = pyr + (size_t)blockIdx.z * g.pyrBytes + S.off;
   uint8_t* dst = pyr + (size_t)blockIdx.z * g.pyrBytes + D.off;
   const int sy = ryOfs[D.ryOff + y];
   const uint32_t bb = ryBeta[D.ryOff + y];
   const int b0 = (int16_t)(bb & 0xffffu), b1 = (int16_t)(bb >> 16);
   const int sy0 = min(max(sy, 0), S.h - 1), sy1 = min(max(sy + 1, 0), S.h - 1);
-  const int sx = rxOfs[D.rxOff + x];
-  const uint32_t aa = rxAlpha[D.rxOff + x];
-  const int a0 = (int16_t)(aa & 0xffffu), a1 = (int16_t)(aa >> 16);
-  const int sx1 = min(sx + 1, S.w - 1);
   const uint8_t* r0 = src + (size_t)sy0 * S.pitch;
   const uint8_t* r1 = src + (size_t)sy1 * S.pitch;
-  const int h0 = r0[sx] * a0 + r0[sx1] * a1;
-  const int h1 = r1[sx] * a0 + r1[sx1] * a1;
-  dst[(size_t)y * D.pitch + x] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+  const short4 sx4 = *reinterpret_cast<const short4*>(rxOfs + D.rxOff + x0);
+  const uint4 aa4 = *reinterpret_cast<const uint4*>(rxAlpha + D.rxOff + x0);
+  const int sxs[4] = {sx4.x, sx4.y, sx4.z, sx4.w};
+  const uint32_t aas[4] = {aa4.x, aa4.y, aa4.z, aa4.w};
+  uint32_t word = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int sx = sxs[i], sx1 = min(sx + 1, S.w - 1);
+    const int a0 = (int16_t)(aas[i] & 0xffffu), a1 = (int16_t)(aas[i] >> 16);
+    const int h0 = r0[sx] * a0 + r0[sx1] * a1;
+    const int h1 = r1[sx] * a0 + r1[sx1] * a1;
+    const uint32_t v = (uint32_t)(uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+    if (x0 + i < D.w) word |= v << (8 * i);
+  }
+  *reinterpret_cast<uint32_t*>(dst + (size_t)y * D.pitch + x0) = word;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -56,7 +66,7 @@ __global__ void __launch_bounds__(128) k_resize(ExtractGeom g, int l, uint8_t* _
 // ------------------------------------------------------------------------------------------------
 constexpr int FP = 80;   // byte pitch of the raw ROI / score map (ROI width <= 66, + alignment slack)
 constexpr int FR = 68;   // max ROI rows
-constexpr int PW = 37;   // word pitch of the packed pixel-pair planes (36 pairs + 1 pad word)
+constexpr int PW = 40;   // word pitch of the packed pixel-pair planes (<= 38 pair words per row, even => 8-byte stores)
 
 // FAST-9/16 arc strength of a horizontal PIXEL PAIR in packed 16-bit lanes (DPX VIMNMX3.U16x2).
 // d'_k = 256 + v - p_k per lane (in [1,511], so one 32-bit subtract never borrows across lanes).
@@ -125,22 +135,21 @@ __device__ __forceinline__ uint32_t fast_pair_full(const uint32_t (&d)[16]) {
 }
 
 __global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t* __restrict__ pyr,
+                                                    const uint32_t* __restrict__ cellInfo,
                                                     uint32_t* __restrict__ candXY, uint32_t* __restrict__ candKey,
                                                     uint8_t* __restrict__ candResp, int32_t* __restrict__ candCount,
                                                     int32_t* __restrict__ status) {
-  __shared__ __align__(16) uint8_t raw[FR * FP];  // staged ROI bytes; reused as the score map once the planes exist
-  uint8_t* score = raw;
-  __shared__ uint32_t planeE[FR * PW];
-  __shared__ uint32_t planeO[FR * PW];
+  __shared__ __align__(16) uint8_t score[FR * FP];   // arc strength M per pixel, indexed by the ALIGNED column X
+  __shared__ __align__(16) uint32_t planeE[FR * PW];  // (P[2i], P[2i+1])   P = pixels of the 4-byte aligned row
+  __shared__ __align__(16) uint32_t planeO[FR * PW];  // (P[2i+1], P[2i+2])
   __shared__ uint32_t list[1024];
   __shared__ int sN, sHi, sBase, sEmit, sPass;
   const int b = blockIdx.y;
   const int cid = blockIdx.x;
-  int l = 0;
-  while (l + 1 < g.nlevels && cid >= g.lv[l + 1].cellStart) l++;
+  const uint32_t info = cellInfo[cid];  // level | cell row | cell column (built with the geometry)
+  const int l = info >> 28, ci = (info >> 14) & 0x3fff, cj = info & 0x3fff;
   const LevelGeom& L = g.lv[l];
-  const int c = cid - L.cellStart;
-  const int ci = c / L.nCols, cj = c - ci * L.nCols;
+  const int c = ci * L.nCols + cj;
   const int iniY = kMinBorder + ci * L.hCell;
   int maxY = iniY + L.hCell + 6;
   if (iniY >= L.maxBY - 3) return;  // :1099
@@ -152,17 +161,26 @@ __global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t
   const int rw = maxX - iniX, rh = maxY - iniY;
   if (rw < 7 || rh < 7) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // ---- stage the ROI (plus up to 4 columns of slack on the right) with aligned 32-bit loads
-  const int a0 = iniX & 3;                       // ROI pixel x lives at raw column x + a0
-  const int nWords = (a0 + rw + 4 + 3) >> 2;     // <= 18
+  // ---- pixel-pair planes straight from aligned 32-bit global loads (one word per lane, PRMT unpack, 8-byte stores).
+  // Column coordinates below are ALIGNED columns X = x_roi + a0, with a0 = iniX & 3.
+  const int a0 = iniX & 3;
+  const int nWords = (a0 + rw + 4 + 3) >> 2;  // <= 19
   const uint8_t* srcRow = pyr + (size_t)b * g.pyrBytes + L.off + (size_t)iniY * L.pitch + (iniX - a0);
   for (int r = warp; r < rh; r += 4) {
+    uint32_t wv = 0;
+    if (lane < nWords && (iniX - a0) + lane * 4 + 3 < L.pitch)
+      wv = *reinterpret_cast<const uint32_t*>(srcRow + (size_t)r * L.pitch + lane * 4);
+    const uint32_t wn = __shfl_down_sync(0xffffffffu, wv, 1);
     if (lane < nWords) {
-      const int gx = (iniX - a0) + lane * 4;
-      uint32_t wv = 0;
-      if (gx + 3 < L.pitch) wv = *reinterpret_cast<const uint32_t*>(srcRow + (size_t)r * L.pitch + lane * 4);
-      *reinterpret_cast<uint32_t*>(&raw[r * FP + lane * 4]) = wv;
+      uint2 e2, o2;
+      e2.x = __byte_perm(wv, 0u, 0x4140);                     // (b0, b1)
+      e2.y = __byte_perm(wv, 0u, 0x4342);                     // (b2, b3)
+      o2.x = __byte_perm(wv, 0u, 0x4241);                     // (b1, b2)
+      o2.y = (wv >> 24) | ((wn & 0xffu) << 16);               // (b3, next b0)
+      *reinterpret_cast<uint2*>(&planeE[r * PW + 2 * lane]) = e2;
+      *reinterpret_cast<uint2*>(&planeO[r * PW + 2 * lane]) = o2;
     }
+    if (lane < FP / 4) *reinterpret_cast<uint32_t*>(&score[r * FP + lane * 4]) = 0u;
   }
   if (tid == 0) {
     sN = 0;
@@ -170,41 +188,38 @@ __global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t
     sPass = 0;
   }
   __syncthreads();
-  // ---- packed pixel-pair planes: E[r][i] = (pix 2i, pix 2i+1), O[r][i] = (pix 2i+1, pix 2i+2)
-  const int nPairW = (rw + 4) >> 1;  // words per plane row that are ever read (<= 35)
-  for (int r = warp; r < rh; r += 4) {
-    for (int i = lane; i < nPairW; i += 32) {
-      const uint8_t* q = &raw[r * FP + a0 + 2 * i];
-      const uint32_t p0 = q[0], p1 = q[1], p2 = q[2];
-      planeE[r * PW + i] = p0 | (p1 << 16);
-      planeO[r * PW + i] = p1 | (p2 << 16);
-    }
-  }
-  __syncthreads();
-  for (int q = tid; q < rh * (FP / 4); q += 128) reinterpret_cast<uint32_t*>(score)[q] = 0u;  // raw -> score map
-  __syncthreads();
   // ---- arc strength, two pixels per thread.  Pass 1: load the 16 circle pairs and run the exact quick reject on every
-  // pair; survivors (a few percent) go to a compact list.  Pass 2: the full 16-arc evaluation runs densely on the list.
-  const int iw = rw - 6, ih = rh - 6;
-  const int npair = (iw + 1) >> 1;            // pairs start at ROI x = 3, 5, 7, ...
-  const int ppr = (npair <= 16) ? 16 : 32;    // lanes per row slot
+  // pair; survivors go to a compact list.  Pass 2: the full 16-arc evaluation runs densely on the list.
+  const int xLo = a0 + 3, xHi = a0 + rw - 3;        // interior columns [xLo, xHi)
+  const int xFirst = (xLo & 1) ? xLo : xLo - 1;     // pairs start at odd aligned columns
+  const int ih = rh - 6;
+  const int npair = (xHi - xFirst + 1) >> 1;
+  const int ppr = (npair <= 16) ? 16 : 32;          // lanes per row slot
   const int rowsPerPass = 4 * (32 / ppr);
   const int myRow = warp * (32 / ppr) + (ppr == 16 ? (lane >> 4) : 0);
   const int myPair = (ppr == 16) ? (lane & 15) : lane;
   for (int y0 = 0; y0 < ih; y0 += rowsPerPass) {
     const int y = y0 + myRow + 3;
+    bool pass = false;
+    uint32_t d[16];
     if (y < rh - 3 && myPair < npair) {
-      uint32_t d[16];
-      fast_pair_load(&planeE[y * PW], &planeO[y * PW], myPair + 1, d);  // x = 2*wrd+1 = 3 + 2*myPair
-      if (fast_pair_quick(d, g.minTh)) {
-        const int slot = atomicAdd(&sPass, 1);
+      fast_pair_load(&planeE[y * PW], &planeO[y * PW], (xFirst - 1) / 2 + myPair, d);  // X = xFirst + 2*myPair
+      pass = fast_pair_quick(d, g.minTh);
+    }
+    const unsigned pm = __ballot_sync(0xffffffffu, pass);
+    if (pm) {  // warp-aggregated append
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&sPass, __popc(pm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (pass) {
+        const int slot = base + __popc(pm & ((1u << lane) - 1u));
         if (slot < 1024) {
           list[slot] = (uint32_t)myPair | ((uint32_t)y << 8);
         } else {  // list full (only possible for very large cells): evaluate in place
           const uint32_t M2 = fast_pair_full(d);
-          const int x = 3 + 2 * myPair;
-          score[y * FP + x] = (uint8_t)min((int)(M2 & 0xffffu), 255);
-          if (x + 1 < rw - 3) score[y * FP + x + 1] = (uint8_t)min((int)(M2 >> 16), 255);
+          const int X = xFirst + 2 * myPair;
+          if (X >= xLo) score[y * FP + X] = (uint8_t)min((int)(M2 & 0xffffu), 255);
+          if (X + 1 < xHi) score[y * FP + X + 1] = (uint8_t)min((int)(M2 >> 16), 255);
         }
       }
     }
@@ -216,32 +231,50 @@ __global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t
       const uint32_t e = list[k];
       const int pr = e & 0xff, y = e >> 8;
       uint32_t d[16];
-      fast_pair_load(&planeE[y * PW], &planeO[y * PW], pr + 1, d);
+      fast_pair_load(&planeE[y * PW], &planeO[y * PW], (xFirst - 1) / 2 + pr, d);
       const uint32_t M2 = fast_pair_full(d);
-      const int x = 3 + 2 * pr;
-      score[y * FP + x] = (uint8_t)min((int)(M2 & 0xffffu), 255);
-      if (x + 1 < rw - 3) score[y * FP + x + 1] = (uint8_t)min((int)(M2 >> 16), 255);
+      const int X = xFirst + 2 * pr;
+      if (X >= xLo) score[y * FP + X] = (uint8_t)min((int)(M2 & 0xffffu), 255);
+      if (X + 1 < xHi) score[y * FP + X + 1] = (uint8_t)min((int)(M2 >> 16), 255);
     }
   }
   __syncthreads();
   // ---- 3x3 NMS inside the cell's detectable area (rim scores are 0 == "not a corner" in OpenCV's buffers)
   for (int y0 = 0; y0 < ih; y0 += rowsPerPass) {
     const int y = y0 + myRow + 3;
+    uint32_t found = 0;  // up to two survivors per thread: (X | y<<8 | M<<16), 0 = none
+    uint32_t found2 = 0;
     if (y < rh - 3 && myPair < npair) {
 #pragma unroll
       for (int h2 = 0; h2 < 2; h2++) {
-        const int x = 3 + 2 * myPair + h2;
-        if (x >= rw - 3) continue;
-        const uint8_t* sc = &score[y * FP + x];
+        const int X = xFirst + 2 * myPair + h2;
+        if (X < xLo || X >= xHi) continue;
+        const uint8_t* sc = &score[y * FP + X];
         const int M = sc[0];
         if (M <= g.minTh) continue;
         const int nb =
             max(max(max(sc[-FP - 1], sc[-FP]), max(sc[-FP + 1], sc[-1])), max(max(sc[1], sc[FP - 1]), max(sc[FP], sc[FP + 1])));
         if (M > nb) {
-          const int slot = atomicAdd(&sN, 1);
-          if (M > g.iniTh) atomicAdd(&sHi, 1);
-          if (slot < 1024) list[slot] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)M << 16);
+          const uint32_t ent = (uint32_t)X | ((uint32_t)y << 8) | ((uint32_t)M << 16);
+          if (h2 == 0) found = ent;
+          else found2 = ent;
         }
+      }
+    }
+    // warp-aggregated append of the survivors (two adjacent pixels can never both survive a strict 3x3 NMS)
+    const uint32_t ent = found ? found : found2;
+    const unsigned sm = __ballot_sync(0xffffffffu, ent != 0u);
+    if (sm) {
+      const unsigned hm = __ballot_sync(0xffffffffu, ent != 0u && (int)(ent >> 16) > g.iniTh);
+      int base = 0;
+      if (lane == 0) {
+        base = atomicAdd(&sN, __popc(sm));
+        if (hm) atomicAdd(&sHi, __popc(hm));
+      }
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (ent) {
+        const int slot = base + __popc(sm & ((1u << lane) - 1u));
+        if (slot < 1024) list[slot] = ent;
       }
     }
   }
@@ -258,7 +291,7 @@ __global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t
   const size_t cbase = (size_t)b * g.totalCandCap + L.candOff;
   for (int k = tid; k < nList; k += 128) {
     const uint32_t e = list[k];
-    const int x = e & 0xff, y = (e >> 8) & 0xff, M = e >> 16;
+    const int x = (int)(e & 0xff) - a0, y = (e >> 8) & 0xff, M = e >> 16;  // back to ROI columns
     if (useHi && M <= g.iniTh) continue;
     const int slot = sBase + atomicAdd(&sEmit, 1);
     if (slot >= L.candCap) continue;
@@ -1001,12 +1034,28 @@ static int build_geometry(b2s_extractor* h, int W, int H) {
         const int16_t b0 = (int16_t)cv_roundf((1.f - fy) * 2048.f), b1 = (int16_t)cv_roundf(fy * 2048.f);
         ryBeta.push_back((uint32_t)(uint16_t)b0 | ((uint32_t)(uint16_t)b1 << 16));
       }
-      rxOff += L.w;
+      for (int dx = L.w; dx & 3; dx++) {  // pad to 4 entries (k_resize loads the x tables four at a time)
+        rxOfs.push_back(rxOfs.back());
+        rxAlpha.push_back(rxAlpha.back());
+      }
+      rxOff += (uint32_t)align_up((size_t)L.w, 4);
       ryOff += L.h;
     }
   }
   g.pyrBytes = off;
   g.totalCells = cellStart;
+  {
+    std::vector<uint32_t> info(cellStart);
+    for (int l = 0; l < g.nlevels; l++)
+      for (int ci = 0; ci < g.lv[l].nRows; ci++)
+        for (int cj = 0; cj < g.lv[l].nCols; cj++)
+          info[g.lv[l].cellStart + ci * g.lv[l].nCols + cj] = ((uint32_t)l << 28) | ((uint32_t)ci << 14) | (uint32_t)cj;
+    if ((size_t)cellStart > h->cellAlloc) {
+      set_error("image %dx%d needs %d FAST cells, more than allocated", W, H, cellStart);
+      return B2S_ERR_BAD_ARG;
+    }
+    B2S_CUDA(cudaMemcpy(h->d.cellInfo, info.data(), info.size() * 4, cudaMemcpyHostToDevice));
+  }
   g.totalCandCap = candOff;
   g.totalSelCap = selOff;
   g.totalBlurTiles = tileStart;
@@ -1039,24 +1088,82 @@ static int build_geometry(b2s_extractor* h, int W, int H) {
 
 static void b2s_extractor_timing_collect(b2s_extractor* h);
 
-// Enqueue the whole pipeline for `batch` images whose level-0 pixels are already in d.pyr.
-static int run_pipeline(b2s_extractor* h, int batch, b2s_keypoint* dKps, uint8_t* dDesc, int32_t* dCounts, int cap,
-                        cudaStream_t st) {
+// per-image arrays advanced by `off` images (a chunk of a batch uses a disjoint slice of every buffer)
+static DeviceBuffers shifted(const DeviceBuffers& d, const ExtractGeom& g, int off) {
+  DeviceBuffers r = d;
+  r.pyr += (size_t)off * g.pyrBytes;
+  r.blur += (size_t)off * g.pyrBytes;
+  r.candXY += (size_t)off * g.totalCandCap;
+  r.candKey += (size_t)off * g.totalCandCap;
+  r.candResp += (size_t)off * g.totalCandCap;
+  r.candNode += (size_t)off * g.totalCandCap;
+  r.candQ += (size_t)off * g.totalCandCap;
+  r.candCount += (size_t)off * kMaxLevels;
+  r.selXYR += (size_t)off * g.totalSelCap * 2;
+  r.selCount += (size_t)off * kMaxLevels;
+  return r;
+}
+
+// Dense host layout [image][row][width bytes] (one 1-D H2D copy per contiguous run of images; 2-D copies of 1241-byte
+// rows run far below PCIe speed) -> level 0 of the pyramid (rows padded to 16 bytes, padding written as 0).
+__global__ void __launch_bounds__(128) k_repitch(const uint8_t* __restrict__ raw, uint8_t* __restrict__ pyr, size_t pyrBytes,
+                                                 uint32_t off0, int w, int h, int pitch, int bBase) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;  // destination word of the row
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (4 * k >= pitch) return;
+  const int rem = w - 4 * k;
+  uint32_t v = 0;
+  if (rem > 0) {
+    const size_t o = ((size_t)(bBase + b) * h + y) * (size_t)w + 4 * (size_t)k;  // `raw` itself is 256-byte aligned
+    const uint32_t* W = reinterpret_cast<const uint32_t*>(raw);
+    const size_t a = o >> 2;
+    v = __funnelshift_r(W[a], W[a + 1], (unsigned)(o & 3) * 8);
+    if (rem < 4) v &= (1u << (8 * rem)) - 1u;
+  }
+  *reinterpret_cast<uint32_t*>(pyr + (size_t)b * pyrBytes + off0 + (size_t)y * pitch + 4 * k) = v;
+}
+
+// Upload `n` host images (each `height` rows of `width` bytes, row stride `stride`) into level 0 of images [b0, b0+n).
+static int upload_level0(b2s_extractor* h, const uint8_t* const* imgs, int b0, int n, int width, int height, int stride,
+                         cudaStream_t st) {
   const ExtractGeom& g = h->geom;
-  DeviceBuffers& d = h->d;
+  if (stride != width || !h->d.raw) {
+    for (int b = b0; b < b0 + n; b++)
+      B2S_CUDA(cudaMemcpy2DAsync(h->d.pyr + (size_t)b * g.pyrBytes + g.lv[0].off, g.lv[0].pitch, imgs[b], stride, width,
+                                 height, cudaMemcpyHostToDevice, st));
+    return B2S_OK;
+  }
+  const size_t img = (size_t)width * height;
+  for (int b = b0; b < b0 + n;) {
+    int e = b + 1;
+    while (e < b0 + n && imgs[e] == imgs[e - 1] + img) e++;  // contiguous run on the host
+    B2S_CUDA(cudaMemcpyAsync(h->d.raw + (size_t)b * img, imgs[b], (size_t)(e - b) * img, cudaMemcpyHostToDevice, st));
+    b = e;
+  }
+  k_repitch<<<dim3(div_up(g.lv[0].pitch / 4, 128), height, n), 128, 0, st>>>(
+      h->d.raw, h->d.pyr + (size_t)b0 * g.pyrBytes, g.pyrBytes, g.lv[0].off, width, height, g.lv[0].pitch, b0);
+  h->launches++;
+  return B2S_OK;
+}
+
+// Enqueue the whole pipeline for `batch` images whose level-0 pixels are already in d.pyr.
+static int run_pipeline(b2s_extractor* h, const DeviceBuffers& d, int batch, b2s_keypoint* dKps, uint8_t* dDesc,
+                        int32_t* dCounts, int cap, cudaStream_t st, bool allowTiming = true) {
+  const ExtractGeom& g = h->geom;
   B2S_CUDA(cudaMemsetAsync(d.candCount, 0, sizeof(int32_t) * kMaxLevels * batch, st));
-  const bool tm = h->timing != 0;
+  const bool tm = allowTiming && h->timing != 0;
   if (tm) {
     if (h->evPending) b2s_extractor_timing_collect(h);
     cudaEventRecord(h->ev[0], st);
   }
   for (int l = 1; l < g.nlevels; l++) {
-    dim3 grid(div_up(g.lv[l].w, 128), g.lv[l].h, batch);
-    k_resize<<<grid, 128, 0, st>>>(g, l, d.pyr, d.rxOfs, d.rxAlpha, d.ryOfs, d.ryBeta);
+    dim3 grid(div_up(g.lv[l].w, 128), div_up(g.lv[l].h, 4), batch);
+    k_resize<<<grid, dim3(32, 4), 0, st>>>(g, l, d.pyr, d.rxOfs, d.rxAlpha, d.ryOfs, d.ryBeta);
     h->launches++;
   }
   if (tm) cudaEventRecord(h->ev[1], st);
-  k_fast_cells<<<dim3(g.totalCells, batch), 128, 0, st>>>(g, d.pyr, d.candXY, d.candKey, d.candResp, d.candCount, d.status);
+  k_fast_cells<<<dim3(g.totalCells, batch), 128, 0, st>>>(g, d.pyr, d.cellInfo, d.candXY, d.candKey, d.candResp, d.candCount,
+                                                          d.status);
   h->launches++;
   if (tm) cudaEventRecord(h->ev[2], st);
   int capMax = 0;
@@ -1171,7 +1278,8 @@ extern "C" int b2s_extractor_create(int nfeatures, float scaleFactor, int nlevel
     }
     h->nFeat[nlevels - 1] = std::max(nfeatures - sum, 0);
   }
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("cudaStreamCreate failed");
     delete h;
     return B2S_ERR_CUDA;
@@ -1206,6 +1314,7 @@ extern "C" int b2s_extractor_create(int nfeatures, float scaleFactor, int nlevel
   };
   A((void**)&d.pyr, B * pyrBytes);
   A((void**)&d.blur, B * pyrBytes);
+  if (max_batch > 1) A((void**)&d.raw, B * (size_t)max_width * max_height + 64);  // dense upload staging (batch path)
   A((void**)&d.candXY, B * candCap * 4);
   A((void**)&d.candKey, B * candCap * 4);
   A((void**)&d.candResp, B * candCap);
@@ -1215,6 +1324,8 @@ extern "C" int b2s_extractor_create(int nfeatures, float scaleFactor, int nlevel
   A((void**)&d.selXYR, B * selCap * 8);
   A((void**)&d.selCount, B * kMaxLevels * 4);
   A((void**)&d.status, 4);
+  h->cellAlloc = (size_t)(div_up(max_width, 28) + 2) * (size_t)(div_up(max_height, 28) + 2) * 4 + 64;
+  A((void**)&d.cellInfo, h->cellAlloc * 4);
   A((void**)&d.rxOfs, h->rxAlloc * 2);
   A((void**)&d.rxAlpha, h->rxAlloc * 4);
   A((void**)&d.ryOfs, h->ryAlloc * 2);
@@ -1252,7 +1363,8 @@ extern "C" void b2s_extractor_destroy(b2s_extractor* h) {
   cudaSetDevice(h->device);
   DeviceBuffers& d = h->d;
   void* ptrs[] = {d.pyr, d.blur, d.candXY, d.candKey, d.candResp, d.candNode, d.candQ, d.candCount, d.selXYR,
-                  d.selCount, d.status, d.rxOfs, d.rxAlpha, d.ryOfs, d.ryBeta, d.outKps, d.outDesc, d.outCounts};
+                  d.selCount, d.status, d.rxOfs, d.rxAlpha, d.ryOfs, d.ryBeta, d.outKps, d.outDesc, d.outCounts, d.cellInfo,
+                  d.raw};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->hKps) cudaFreeHost(h->hKps);
@@ -1260,6 +1372,7 @@ extern "C" void b2s_extractor_destroy(b2s_extractor* h) {
   if (h->hCounts) cudaFreeHost(h->hCounts);
   if (h->hStatus) cudaFreeHost(h->hStatus);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   delete h;
 }
 
@@ -1314,21 +1427,31 @@ extern "C" int b2s_extract_batch(b2s_extractor* h, const uint8_t* const* imgs, i
   int rc = ensure_geometry(h, width, height);
   if (rc != B2S_OK) return rc;
   const ExtractGeom& g = h->geom;
-  for (int b = 0; b < batch; b++) {
+  for (int b = 0; b < batch; b++)
     if (!imgs[b]) return B2S_ERR_BAD_ARG;
-    B2S_CUDA(cudaMemcpy2DAsync(h->d.pyr + (size_t)b * g.pyrBytes + g.lv[0].off, g.lv[0].pitch, imgs[b], stride, width,
-                               height, cudaMemcpyHostToDevice, h->stream));
-  }
   const int icap = h->outCap;
   if (cap <= icap) {
-    // records are produced with the caller's stride and copied straight into the caller's arrays (fast when those
-    // are pinned; pageable memory is staged by the driver)
-    rc = run_pipeline(h, batch, h->d.outKps, h->d.outDesc, h->d.outCounts, cap, h->stream);
-    if (rc != B2S_OK) return rc;
-    B2S_CUDA(cudaMemcpyAsync(kps, h->d.outKps, (size_t)batch * cap * sizeof(b2s_keypoint), cudaMemcpyDeviceToHost,
-                             h->stream));
-    B2S_CUDA(cudaMemcpyAsync(desc, h->d.outDesc, (size_t)batch * cap * 32, cudaMemcpyDeviceToHost, h->stream));
-    B2S_CUDA(cudaMemcpyAsync(h->hCounts, h->d.outCounts, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
+    // Records are produced with the caller's stride and copied straight into the caller's arrays (full PCIe speed when
+    // those are pinned).  Large batches are cut into chunks on two streams so that the H2D copy of chunk k+1, the kernels
+    // of chunk k and the D2H copy of chunk k-1 overlap.
+    const int nChunks = (batch >= 16 && h->stream2) ? 4 : 1;
+    for (int c = 0; c < nChunks; c++) {
+      const int b0 = (int)((long long)batch * c / nChunks), b1 = (int)((long long)batch * (c + 1) / nChunks);
+      if (b1 <= b0) continue;
+      cudaStream_t st = (nChunks > 1 && (c & 1)) ? h->stream2 : h->stream;
+      rc = upload_level0(h, imgs, b0, b1 - b0, width, height, stride, st);
+      if (rc != B2S_OK) return rc;
+      const DeviceBuffers dc = shifted(h->d, g, b0);
+      rc = run_pipeline(h, dc, b1 - b0, h->d.outKps + (size_t)b0 * cap, h->d.outDesc + (size_t)b0 * cap * 32,
+                        h->d.outCounts + b0, cap, st, nChunks == 1);
+      if (rc != B2S_OK) return rc;
+      B2S_CUDA(cudaMemcpyAsync(kps + (size_t)b0 * cap, h->d.outKps + (size_t)b0 * cap,
+                               (size_t)(b1 - b0) * cap * sizeof(b2s_keypoint), cudaMemcpyDeviceToHost, st));
+      B2S_CUDA(cudaMemcpyAsync(desc + (size_t)b0 * cap * 32, h->d.outDesc + (size_t)b0 * cap * 32,
+                               (size_t)(b1 - b0) * cap * 32, cudaMemcpyDeviceToHost, st));
+      B2S_CUDA(cudaMemcpyAsync(h->hCounts + b0, h->d.outCounts + b0, (size_t)(b1 - b0) * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (nChunks > 1) B2S_CUDA(cudaStreamSynchronize(h->stream2));
     B2S_CUDA(cudaMemcpyAsync(h->hStatus, h->d.status, 4, cudaMemcpyDeviceToHost, h->stream));
     B2S_CUDA(cudaStreamSynchronize(h->stream));
     rc = check_status(h);
@@ -1336,7 +1459,9 @@ extern "C" int b2s_extract_batch(b2s_extractor* h, const uint8_t* const* imgs, i
     for (int b = 0; b < batch; b++) n_out[b] = h->hCounts[b];
     return B2S_OK;
   }
-  rc = run_pipeline(h, batch, h->d.outKps, h->d.outDesc, h->d.outCounts, icap, h->stream);
+  rc = upload_level0(h, imgs, 0, batch, width, height, stride, h->stream);
+  if (rc != B2S_OK) return rc;
+  rc = run_pipeline(h, h->d, batch, h->d.outKps, h->d.outDesc, h->d.outCounts, icap, h->stream);
   if (rc != B2S_OK) return rc;
   B2S_CUDA(cudaMemcpyAsync(h->hKps, h->d.outKps, (size_t)batch * icap * sizeof(b2s_keypoint), cudaMemcpyDeviceToHost,
                            h->stream));
@@ -1394,7 +1519,7 @@ extern "C" int b2s_extract_batch_device(b2s_extractor* h, const uint8_t* d_imgs,
   for (int b = 0; b < batch; b++)
     B2S_CUDA(cudaMemcpy2DAsync(h->d.pyr + (size_t)b * g.pyrBytes + g.lv[0].off, g.lv[0].pitch,
                                d_imgs + (size_t)b * img_pitch_bytes, stride, width, height, cudaMemcpyDeviceToDevice, st));
-  return run_pipeline(h, batch, d_kps, d_desc, d_counts, cap, st);
+  return run_pipeline(h, h->d, batch, d_kps, d_desc, d_counts, cap, st);
 }
 
 extern "C" int b2s_extractor_check(b2s_extractor* h) {

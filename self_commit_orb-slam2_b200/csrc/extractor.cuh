@@ -41,6 +41,7 @@ struct ExtractGeom {
 struct DeviceBuffers {
   uint8_t* pyr = nullptr;      // B x pyrBytes
   uint8_t* blur = nullptr;     // B x pyrBytes
+  uint8_t* raw = nullptr;      // B x width*height dense upload staging (host-buffer batch path)
   uint32_t* candXY = nullptr;  // B x totalCandCap   (x | y<<16, border-relative)
   uint32_t* candKey = nullptr; // B x totalCandCap   (order key: cell<<12 | ylocal<<6 | xlocal)
   uint8_t* candResp = nullptr; // B x totalCandCap
@@ -49,6 +50,7 @@ struct DeviceBuffers {
   int32_t* candCount = nullptr;  // B x kMaxLevels
   uint32_t* selXYR = nullptr;    // B x totalSelCap x 2 (x|y<<16 level coords, response)
   int32_t* selCount = nullptr;   // B x kMaxLevels
+  uint32_t* cellInfo = nullptr;  // per FAST cell: level<<28 | cell row<<14 | cell column
   int32_t* status = nullptr;     // 1 int: bit0 cand overflow, bit1 output overflow, bit2 node overflow
   int16_t* rxOfs = nullptr;      // resize tables
   uint32_t* rxAlpha = nullptr;
@@ -72,8 +74,8 @@ struct b2s_extractor {
   int curW = 0, curH = 0;
   b2s::ExtractGeom geom;
   b2s::DeviceBuffers d;
-  size_t pyrBytesAlloc = 0, candCapAlloc = 0, selCapAlloc = 0, rxAlloc = 0, ryAlloc = 0;
-  cudaStream_t stream = nullptr;
+  size_t pyrBytesAlloc = 0, candCapAlloc = 0, selCapAlloc = 0, rxAlloc = 0, ryAlloc = 0, cellAlloc = 0;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
   // pinned staging for the host-buffer entry points
   b2s_keypoint* hKps = nullptr;
   uint8_t* hDesc = nullptr;

@@ -53,9 +53,13 @@ struct BaPtrs {  // strided per-window arrays
   double *err, *chi2, *W;
   int *mpStart, *mpEdges, *kfStart, *kfEdges;
   double *Hpp, *Hll, *b, *x, *Dinv, *S;
-  double *db, *Y;      // Dinv*b_l per landmark, W*Dinv per edge
+  double *db, *Y;      // Dinv*b_l per landmark, (Y unused)
+  double* DinvP;       // per landmark, 16-byte items: {d00,d01,d02,d11,d12,d22, db0,db1,db2, pad} (Schur gather record)
+  double* hl;          // landmark-side contributions {H00,H01,H02,H11,H12,H22, b0,b1,b2}, layout [window][term][edge]
   int *lmEdge, *freeKf;  // [landmark][free pose] -> edge id or -1 ; free pose index -> keyframe index
-  int *blkOff, *pairA, *pairC, *usePairs;  // covisibility pair lists per lower block (built once per window)
+  int *blkOff, *usePairs;  // covisibility pair lists per lower block (built once per window): offsets, fits-flag
+  int4* pairRec;           // pair record {edge of pose i1, edge of pose i2, landmark, 0}
+  int *blkOrder, *blkNZ;   // lower blocks sorted by descending pair count; number of non-empty blocks
   int capPairs, capBlk;
   double *partChi, *partScale;   // per-CTA partial sums [window][nCta]
   unsigned int* bar;             // per-window barrier counters
@@ -290,72 +294,120 @@ struct WinCtx {
 };
 
 // ---------------------------------------------------------------- phases (device functions, strided over the window's threads)
-// computeActiveErrors + buildSystem (landmark side): one thread per landmark walks its edges in insertion order:
-// error, chi2, Huber weight, J^T W J -> Hll, b_l and the pose-landmark blocks W_e (block_solver.hpp:502-560).
-__device__ void phase_build_landmarks(const BaPtrs& p, const WinCtx& c, const BaWin& W, int robust, double* sm) {
+// computeActiveErrors + buildSystem, edge side (block_solver.hpp:502-560): one thread per edge in edge order — error,
+// chi2, Huber weight, the landmark-side products {A^T W A, A^T W e} and the pose-landmark block W_e = B^T W A.  The
+// per-edge records are written through a per-warp shared-memory transpose so that 32 consecutive edges leave the SM as
+// contiguous 4.6 KB / 2.3 KB / 0.8 KB bursts instead of 30 scattered 8-byte stores per lane.
+__device__ void phase_build_edges(const BaPtrs& p, const WinCtx& c, const BaWin& W, int robust, double* stage, double* sm) {
   const int w = c.w;
-  const int* ms = p.mpStart + (size_t)w * (p.capMp + 1);
-  const int* me = p.mpEdges + (size_t)w * p.capE;
-  double chi = 0, md = 0;
-  for (int l = c.gtid; l < W.nMp; l += c.gthreads) {
-    const size_t mo = (size_t)w * p.capMp + l;
-    double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
-    const double* X = p.pts + mo * 3;
-    for (int k = ms[l]; k < ms[l + 1]; k++) {
-      const int e = me[k];
-      const size_t eo = (size_t)w * p.capE + e;
-      if (p.eLevel[eo]) continue;
+  const int lane = threadIdx.x & 31;
+  double* tile = stage + (size_t)(threadIdx.x >> 5) * (30 * 33);
+  const int nE = W.nEdges;
+  double chi = 0;
+  for (int base = c.gtid - lane; base < nE; base += c.gthreads) {
+    const int e = base + lane;
+    const size_t eo = (size_t)w * p.capE + e;
+    double rec[30];
+#pragma unroll
+    for (int k = 0; k < 30; k++) rec[k] = 0;
+    if (e < nE && !p.eLevel[eo]) {
       const int kf = p.eKf[eo];
       const bool stereo = p.eStereo[eo];
       EdgeJac J;
-      edge_jacobians(p.pose + ((size_t)w * p.capKf + kf) * PSTRIDE, X, stereo, W.fx, W.fy, W.bf, J);
+      edge_jacobians(p.pose + ((size_t)w * p.capKf + kf) * PSTRIDE, p.pts + ((size_t)w * p.capMp + p.eMp[eo]) * 3, stereo,
+                     W.fx, W.fy, W.bf, J);
       const double w0 = (double)p.eW[eo];
       double er[3];
       const double c2 = edge_error(J.Xc, stereo, p.eObs + eo * 3, w0, W, er);
-      p.err[eo * 3] = er[0]; p.err[eo * 3 + 1] = er[1]; p.err[eo * 3 + 2] = er[2];
       p.chi2[eo] = c2;
       double rho0 = c2, rho1 = 1.0;
       if (robust) huber(c2, delta_of(stereo), rho0, rho1);
       chi += rho0;
       double omr[3];
 #pragma unroll
-      for (int r = 0; r < 3; r++) omr[r] = -(w0 * er[r]) * rho1;
+      for (int r = 0; r < 3; r++) {
+        omr[r] = -(w0 * er[r]) * rho1;
+        rec[27 + r] = er[r];
+      }
       const double wq = rho1 * w0;
+      // W_e (6x3)
 #pragma unroll
-      for (int i = 0; i < 3; i++) {
-        double s = 0;
-#pragma unroll
-        for (int r = 0; r < 3; r++) s += J.A[r][i] * omr[r];
-        bl[i] += s;
+      for (int i = 0; i < 6; i++)
 #pragma unroll
         for (int j = 0; j < 3; j++) {
           double hh = 0;
 #pragma unroll
-          for (int r = 0; r < 3; r++) hh += J.A[r][i] * wq * J.A[r][j];
-          H[i * 3 + j] += hh;
+          for (int r = 0; r < 3; r++) hh += J.B[r][i] * wq * J.A[r][j];
+          rec[i * 3 + j] = hh;
         }
-      }
-      if (p.poseIndex[(size_t)w * p.capKf + kf] >= 0) {
-        double* Wb = p.W + eo * 18;
+      // A^T (wq) A upper triangle, A^T omega_r
+      int t = 18;
 #pragma unroll
-        for (int i = 0; i < 6; i++)
+      for (int i = 0; i < 3; i++)
 #pragma unroll
-          for (int j = 0; j < 3; j++) {
-            double hh = 0;
+        for (int j = i; j < 3; j++) {
+          double hh = 0;
 #pragma unroll
-            for (int r = 0; r < 3; r++) hh += J.B[r][i] * wq * J.A[r][j];
-            Wb[i * 3 + j] = hh;
-          }
+          for (int r = 0; r < 3; r++) hh += J.A[r][i] * wq * J.A[r][j];
+          rec[t++] = hh;
+        }
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        double s2 = 0;
+#pragma unroll
+        for (int r = 0; r < 3; r++) s2 += J.A[r][i] * omr[r];
+        rec[24 + i] = s2;
       }
     }
-    for (int k = 0; k < 9; k++) p.Hll[mo * 9 + k] = H[k];
-    double* bb = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)W.nFree * 6 + (size_t)l * 3;
-    bb[0] = bl[0]; bb[1] = bl[1]; bb[2] = bl[2];
-    md = fmax(md, fmax(fabs(H[0]), fmax(fabs(H[4]), fabs(H[8]))));
+#pragma unroll
+    for (int k = 0; k < 30; k++)
+      if (k < 18 || k >= 27) tile[k * 33 + lane] = rec[k];
+    __syncwarp();
+    double* Wout = p.W + ((size_t)w * p.capE + base) * 18;
+    const int nv = min(32, nE - base);
+    for (int idx = lane; idx < nv * 18; idx += 32) {
+      const int ed = idx / 18, k = idx - ed * 18;
+      Wout[idx] = tile[k * 33 + ed];
+    }
+    if (e < nE) {  // landmark-side terms: structure-of-arrays [term][edge], written straight from registers
+#pragma unroll
+      for (int k = 0; k < 9; k++) p.hl[((size_t)w * 9 + k) * p.capE + e] = rec[18 + k];
+    }
+    double* Eout = p.err + ((size_t)w * p.capE + base) * 3;
+    for (int idx = lane; idx < nv * 3; idx += 32) {
+      const int ed = idx / 3, k = idx - ed * 3;
+      Eout[idx] = tile[(27 + k) * 33 + ed];
+    }
+    __syncwarp();
   }
-  atomic_max_pos_double(&p.st[w].maxDiagBits, md);
   const double s = block_sum(chi, sm);
   if (threadIdx.x == 0) p.partChi[(size_t)w * p.nPartE + c.cta] = s;
+}
+
+// landmark side of buildSystem: one thread per landmark sums its edges' contributions in insertion order
+__device__ void phase_reduce_landmarks(const BaPtrs& p, const WinCtx& c, const BaWin& W) {
+  const int w = c.w;
+  const int* ms = p.mpStart + (size_t)w * (p.capMp + 1);
+  const int* me = p.mpEdges + (size_t)w * p.capE;
+  double md = 0;
+  for (int l = c.gtid; l < W.nMp; l += c.gthreads) {
+    const size_t mo = (size_t)w * p.capMp + l;
+    double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = ms[l]; k < ms[l + 1]; k++) {
+      const size_t eo = (size_t)w * p.capE + me[k];
+      if (p.eLevel[eo]) continue;
+#pragma unroll
+      for (int q = 0; q < 9; q++) h[q] += p.hl[((size_t)w * 9 + q) * p.capE + me[k]];
+    }
+    double* H = p.Hll + mo * 9;
+    H[0] = h[0]; H[1] = h[1]; H[2] = h[2];
+    H[3] = h[1]; H[4] = h[3]; H[5] = h[4];
+    H[6] = h[2]; H[7] = h[4]; H[8] = h[5];
+    double* bb = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)W.nFree * 6 + (size_t)l * 3;
+    bb[0] = h[6]; bb[1] = h[7]; bb[2] = h[8];
+    md = fmax(md, fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5]))));
+  }
+  atomic_max_pos_double(&p.st[w].maxDiagBits, md);
 }
 
 // buildSystem (pose side): one warp per free pose, lanes stride over the pose's edges, ordered shuffle reduction
@@ -384,7 +436,7 @@ __device__ void phase_build_poses(const BaPtrs& p, const WinCtx& c, const BaWin&
         double r0;
         huber(p.chi2[eo], delta_of(stereo), r0, rho1);
       }
-      const double* er = p.err + eo * 3;
+      const double* er = p.err + eo * 3;  // written by phase_build_edges
       double omr[3];
 #pragma unroll
       for (int r = 0; r < 3; r++) omr[r] = -(w0 * er[r]) * rho1;
@@ -478,6 +530,12 @@ __device__ void phase_dinv(const BaPtrs& p, const WinCtx& c, const BaWin& W, dou
     p.db[mo * 3 + 0] = Di[0] * bl[0] + Di[1] * bl[1] + Di[2] * bl[2];
     p.db[mo * 3 + 1] = Di[3] * bl[0] + Di[4] * bl[1] + Di[5] * bl[2];
     p.db[mo * 3 + 2] = Di[6] * bl[0] + Di[7] * bl[1] + Di[8] * bl[2];
+    double2* rec = reinterpret_cast<double2*>(p.DinvP + mo * 10);  // Hll is exactly symmetric, so is the cofactor inverse
+    rec[0] = make_double2(Di[0], Di[1]);
+    rec[1] = make_double2(Di[2], Di[4]);
+    rec[2] = make_double2(Di[5], Di[8]);
+    rec[3] = make_double2(p.db[mo * 3 + 0], p.db[mo * 3 + 1]);
+    rec[4] = make_double2(p.db[mo * 3 + 2], 0.0);
   }
 }
 
@@ -524,10 +582,140 @@ __device__ __forceinline__ double warp_reduce_scatter32(double (&v)[32], int lan
   return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
+
+// Warp-cooperative gather of one record per lane (REC16 16-byte items each, record index `rec` held by the lane) into a
+// shared-memory tile laid out [lane][N16]: consecutive lanes fetch consecutive 16-byte items, so one load instruction
+// touches ~32*16/128 lines per record run instead of 32 lines (a lane reading its own record costs one LSU wavefront
+// per lane per instruction; that wavefront rate, not HBM, is what bounded the Schur and back-substitution phases).
+// Only the first N16 items of each record are fetched.  Tile reads by the owning lane (stride N16*16 B, N16 odd) are
+// bank-conflict free for 128-bit accesses.
+template <int N16, int REC16>
+__device__ __forceinline__ void warp_gather16(double2* tile, const double2* base, int rec, int lane) {
+#pragma unroll
+  for (int r = 0; r < N16; r++) {
+    const int idx = lane + 32 * r;
+    const int pr = idx / N16, el = idx - pr * N16;
+    const int src = __shfl_sync(0xffffffffu, rec, pr);
+    tile[idx] = base[(size_t)src * REC16 + el];
+  }
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// the same gather as an asynchronous global->shared copy (no registers held across the memory latency)
+template <int N16, int REC16>
+__device__ __forceinline__ void warp_gather16_async(double2* tile, const double2* base, int rec, int lane) {
+#pragma unroll
+  for (int r = 0; r < N16; r++) {
+    const int idx = lane + 32 * r;
+    const int pr = idx / N16, el = idx - pr * N16;
+    const int src = __shfl_sync(0xffffffffu, rec, pr);
+    cp_async16(tile + idx, base + (size_t)src * REC16 + el);
+  }
+}
+constexpr int GATHER_TILE16 = 32 * 9 * 2 + 32 * 5;  // per-warp staging: two W records + one packed Dinv record per lane
+
+// One covisibility pair per lane out of the staged records: acc += (W_a Dinv_l) W_c^T (36 entries: 32 in acc, 4 in
+// tail[0..3]); diagonal blocks also accumulate W_a (Dinv_l b_l) into tail[4..9].
+template <bool DIAG>
+__device__ __forceinline__ void schur_accumulate(const double2* tA, const double2* tC, const double2* tD, int lane,
+                                                 double (&acc)[32], double (&tail)[10]) {
+  const double2* ra = tA + lane * 9;
+  const double2* rc = DIAG ? ra : tC + lane * 9;
+  const double2* rd = tD + lane * (DIAG ? 5 : 3);
+  double wc[18];
+#pragma unroll
+  for (int z = 0; z < 9; z++) {
+    const double2 v = rc[z];
+    wc[2 * z] = v.x;
+    wc[2 * z + 1] = v.y;
+  }
+  const double2 dA = rd[0], dB = rd[1], dC = rd[2];
+  const double d00 = dA.x, d01 = dA.y, d02 = dB.x, d11 = dB.y, d12 = dC.x, d22 = dC.y;
+  double b0 = 0, b1 = 0, b2 = 0;
+  if (DIAG) {
+    const double2 e0 = rd[3], e1 = rd[4];
+    b0 = e0.x; b1 = e0.y; b2 = e1.x;
+  }
+#pragma unroll
+  for (int r2 = 0; r2 < 3; r2++) {  // two rows of W_a at a time (register budget)
+    const double2 u0 = ra[3 * r2], u1 = ra[3 * r2 + 1], u2 = ra[3 * r2 + 2];
+    const double wr[2][3] = {{u0.x, u0.y, u1.x}, {u1.y, u2.x, u2.y}};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int r = 2 * r2 + h;
+      const double w0 = wr[h][0], w1 = wr[h][1], w2 = wr[h][2];
+      const double y0 = w0 * d00 + w1 * d01 + w2 * d02;
+      const double y1 = w0 * d01 + w1 * d11 + w2 * d12;
+      const double y2 = w0 * d02 + w1 * d12 + w2 * d22;
+#pragma unroll
+      for (int cc = 0; cc < 6; cc++) {
+        const double v = y0 * wc[cc * 3] + y1 * wc[cc * 3 + 1] + y2 * wc[cc * 3 + 2];
+        const int en = r * 6 + cc;
+        if (en < 32) acc[en] += v;
+        else tail[en - 32] += v;
+      }
+      if (DIAG) tail[4 + r] += w0 * b0 + w1 * b1 + w2 * b2;
+    }
+  }
+}
+
+// Pair-list Schur accumulation of one block, software pipelined: while the lanes multiply the records of iteration i,
+// the cp.async gathers of iteration i+1 are in flight and the pair records of iteration i+2 are being loaded.  (At
+// 8 warps per SM the phase is bound by the index -> record -> arithmetic dependency chain, not by bandwidth.)
+// Edges excluded from the optimisation (level 1) carry W_e = 0 (phase_build_edges), so they need no test here.
+template <bool DIAG>
+__device__ __forceinline__ void schur_block_pairs(const int4* prs, int qBeg, int qEnd, const double2* Wb, const double2* Db,
+                                                  double2* buf, int lane, double (&acc)[32], double (&tail)[10]) {
+  const int nIt = (qEnd - qBeg + 31) >> 5;
+  auto issue = [&](double2* t, const int4& r) {
+    warp_gather16_async<9, 9>(t, Wb, r.x, lane);
+    if (!DIAG) {
+      warp_gather16_async<9, 9>(t + 32 * 9, Wb, r.y, lane);
+      warp_gather16_async<3, 5>(t + 32 * 18, Db, r.z, lane);
+    } else {
+      warp_gather16_async<5, 5>(t + 32 * 18, Db, r.z, lane);
+    }
+  };
+  auto loadRec = [&](int it, int4& r, bool& v) {
+    const int q = qBeg + it * 32 + lane;
+    v = q < qEnd;
+    r = v ? prs[q] : make_int4(0, 0, 0, 0);
+  };
+  int4 r0, r1 = make_int4(0, 0, 0, 0);
+  bool v0, v1 = false;
+  loadRec(0, r0, v0);
+  issue(buf, r0);
+  cp_async_commit();
+  if (nIt > 1) loadRec(1, r1, v1);
+  for (int it = 0; it < nIt; it++) {
+    double2* cur = buf + (size_t)(it & 1) * GATHER_TILE16;
+    double2* nxt = buf + (size_t)((it & 1) ^ 1) * GATHER_TILE16;
+    if (it + 1 < nIt) issue(nxt, r1);
+    cp_async_commit();
+    int4 r2 = make_int4(0, 0, 0, 0);
+    bool v2 = false;
+    if (it + 2 < nIt) loadRec(it + 2, r2, v2);
+    cp_async_wait<1>();
+    __syncwarp();
+    if (v0) schur_accumulate<DIAG>(cur, cur + 32 * 9, cur + 32 * 18, lane, acc, tail);
+    __syncwarp();
+    v0 = v1;
+    r1 = r2;
+    v1 = v2;
+  }
+  cp_async_wait<0>();
+}
+
 // Schur complement (block_solver.hpp:381-439): one warp per lower block (i1 >= i2); lanes stride over the block's
 // covisibility pairs (edge a of pose i1, edge c of pose i2, same landmark l) and accumulate (W_a Dinv_l) W_c^T; the
 // diagonal blocks also accumulate W_a (Dinv_l b_l) for the right-hand side.  S(i1,i2) = [Hpp + lambda I] - sum.
-__device__ void phase_schur_blocks(const BaPtrs& p, const WinCtx& c, const BaWin& W, double lambda) {
+// Blocks are dealt to the warps of the window in snake order over the list sorted by descending pair count.
+__device__ void phase_schur_blocks(const BaPtrs& p, const WinCtx& c, const BaWin& W, double lambda, double* stage) {
   const int w = c.w;
   const int lane = threadIdx.x & 31;
   const int nWarps = c.gthreads >> 5, gw = c.gtid >> 5;
@@ -535,76 +723,75 @@ __device__ void phase_schur_blocks(const BaPtrs& p, const WinCtx& c, const BaWin
   const int n = W.nFree * 6;
   const int usePairs = p.usePairs[w];
   const int* off = p.blkOff + (size_t)w * (p.capBlk + 1);
-  const int* pa = p.pairA + (size_t)w * p.capPairs;
-  const int* pc = p.pairC + (size_t)w * p.capPairs;
+  const int* order = p.blkOrder + (size_t)w * p.capBlk;
+  const int4* prs = p.pairRec + (size_t)w * p.capPairs;
   const int* ks = p.kfStart + (size_t)w * (p.capKf + 1);
   const int* ke = p.kfEdges + (size_t)w * p.capE;
   const int* lm = p.lmEdge + (size_t)w * p.capMp * p.capKf;
-  for (int t = gw; t < nb; t += nWarps) {
+  const int* eMp = p.eMp + (size_t)w * p.capE;
+  const double2* Wb = reinterpret_cast<const double2*>(p.W + (size_t)w * p.capE * 18);
+  const double2* Db = reinterpret_cast<const double2*>(p.DinvP + (size_t)w * p.capMp * 10);
+  double2* buf = reinterpret_cast<double2*>(stage) + (size_t)(threadIdx.x >> 5) * (2 * GATHER_TILE16);
+  for (int k0 = 0; k0 < nb; k0 += nWarps) {
+    const int k = k0 + (((k0 / nWarps) & 1) ? nWarps - 1 - gw : gw);
+    if (k >= nb) continue;
+    const int t = usePairs ? order[k] : k;
     int i1, i2;
     decode_block(t, i1, i2);
     const bool diag = (i1 == i2);
     double acc[32], tail[10];  // entries 0..31, entries 32..35 + the 6 right-hand-side sums
 #pragma unroll
-    for (int k = 0; k < 32; k++) acc[k] = 0;
+    for (int z = 0; z < 32; z++) acc[z] = 0;
 #pragma unroll
-    for (int k = 0; k < 10; k++) tail[k] = 0;
-    int qBeg, qEnd;
+    for (int z = 0; z < 10; z++) tail[z] = 0;
+    bool any = true;
     if (usePairs) {
-      qBeg = off[t];
-      qEnd = off[t + 1];
+      const int qBeg = off[t], qEnd = off[t + 1];
+      any = qEnd > qBeg;
+      if (any) {
+        if (diag) schur_block_pairs<true>(prs, qBeg, qEnd, Wb, Db, buf, lane, acc, tail);
+        else schur_block_pairs<false>(prs, qBeg, qEnd, Wb, Db, buf, lane, acc, tail);
+      }
     } else {  // pair list did not fit: walk pose i1's edges and probe the landmark->edge table (same order)
       const int kf1 = p.freeKf[(size_t)w * p.capKf + i1];
-      qBeg = ks[kf1];
-      qEnd = ks[kf1 + 1];
-    }
-    for (int q = qBeg + lane; q < qEnd; q += 32) {
-      int ea, ec;
-      if (usePairs) {
-        ea = pa[q];
-        ec = pc[q];
-      } else {
-        ea = ke[q];
-        ec = lm[(size_t)p.eMp[(size_t)w * p.capE + ea] * p.capKf + i2];
-        if (ec < 0) continue;
-      }
-      const size_t eoa = (size_t)w * p.capE + ea, eoc = (size_t)w * p.capE + ec;
-      if (p.eLevel[eoa] | p.eLevel[eoc]) continue;
-      const size_t mo = (size_t)w * p.capMp + p.eMp[eoa];
-      const double* Di = p.Dinv + mo * 9;
-      const double* Wa = p.W + eoa * 18;
-      const double* Wc = p.W + eoc * 18;
-      double di[9], wc[18];
-#pragma unroll
-      for (int z = 0; z < 9; z++) di[z] = Di[z];
-#pragma unroll
-      for (int z = 0; z < 18; z++) wc[z] = Wc[z];
-      double d0 = 0, d1 = 0, d2 = 0;
-      if (diag) {
-        const double* d3 = p.db + mo * 3;
-        d0 = d3[0]; d1 = d3[1]; d2 = d3[2];
-      }
-#pragma unroll
-      for (int r = 0; r < 6; r++) {
-        const double w0 = Wa[r * 3], w1 = Wa[r * 3 + 1], w2 = Wa[r * 3 + 2];  // one row of W_a at a time (register budget)
-        const double y0 = w0 * di[0] + w1 * di[3] + w2 * di[6];
-        const double y1 = w0 * di[1] + w1 * di[4] + w2 * di[7];
-        const double y2 = w0 * di[2] + w1 * di[5] + w2 * di[8];
-#pragma unroll
-        for (int cc = 0; cc < 6; cc++) {
-          const double v = y0 * wc[cc * 3] + y1 * wc[cc * 3 + 1] + y2 * wc[cc * 3 + 2];
-          const int en = r * 6 + cc;
-          if (en < 32) acc[en] += v;
-          else tail[en - 32] += v;
+      const int qBeg = ks[kf1], qEnd = ks[kf1 + 1];
+      for (int q0 = qBeg; q0 < qEnd; q0 += 32) {
+        const int q = q0 + lane;
+        bool valid = q < qEnd;
+        int ea = 0, ec = 0, mp = 0;
+        if (valid) {
+          ea = ke[q];
+          mp = eMp[ea];
+          ec = lm[(size_t)mp * p.capKf + i2];
+          if (ec < 0) {
+            valid = false;
+            ec = 0;
+          }
         }
-        if (diag) tail[4 + r] += w0 * d0 + w1 * d1 + w2 * d2;
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        warp_gather16<9, 9>(buf, Wb, ea, lane);
+        if (!diag) {
+          warp_gather16<9, 9>(buf + 32 * 9, Wb, ec, lane);
+          warp_gather16<3, 5>(buf + 32 * 18, Db, mp, lane);
+        } else {
+          warp_gather16<5, 5>(buf + 32 * 18, Db, mp, lane);
+        }
+        __syncwarp();
+        if (valid) {
+          if (diag) schur_accumulate<true>(buf, buf + 32 * 9, buf + 32 * 18, lane, acc, tail);
+          else schur_accumulate<false>(buf, buf + 32 * 9, buf + 32 * 18, lane, acc, tail);
+        }
+        __syncwarp();
       }
     }
-    const double mine = warp_reduce_scatter32(acc, lane);
+    double mine = 0;
+    if (any) {  // (warp-uniform) a block without pairs is just its Hpp part
+      mine = warp_reduce_scatter32(acc, lane);
 #pragma unroll
-    for (int k = 0; k < 10; k++) {
+      for (int z = 0; z < 10; z++) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) tail[k] += __shfl_xor_sync(0xffffffffu, tail[k], o);
+        for (int o = 16; o > 0; o >>= 1) tail[z] += __shfl_xor_sync(0xffffffffu, tail[z], o);
+      }
     }
     double* Sb = p.S + (size_t)w * p.ldS * p.ldS + (size_t)(i1 * 6) * p.ldS + i2 * 6;
     const double* Hp = p.Hpp + ((size_t)w * p.capKf + i1) * 36;
@@ -659,6 +846,7 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
   double* Dblk = dsm;                                // 33 x 33 (last row: reciprocal diagonal)
   double* panel = dsm + (CHOL_BS + 1) * CHOL_PP;     // (ld+4) x 33
   double* xs = panel + (size_t)(ld + 4) * CHOL_PP;   // ld
+  double* rdiag = xs + ld;                           // ld: 1 / L[i][i], kept for the back substitution
   __shared__ int fail;
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
   if (tid == 0) fail = 0;
@@ -701,6 +889,7 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
 #pragma unroll
       for (int cc = 0; cc < CHOL_BS; cc++) Dblk[lane * CHOL_PP + cc] = (cc <= lane) ? row[cc] : 0.0;
       Dblk[CHOL_BS * CHOL_PP + lane] = mydinv;
+      if (lane < wd) rdiag[kb + lane] = mydinv;
     }
     __syncthreads();
     CH_PROF(11)
@@ -789,9 +978,7 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
 #pragma unroll
       for (int r = 0; r < CHOL_BS; r++) col[r] = Dblk[r * CHOL_PP + lane];
       double tv = (lane < wd) ? xs[kb + lane] : 0.0;
-      double myrcp = 1.0;
-#pragma unroll
-      for (int j = 0; j < CHOL_BS; j++) myrcp = (lane == j) ? 1.0 / col[j] : myrcp;  // 1 / L[lane][lane], off the chain
+      const double myrcp = (lane < wd) ? rdiag[kb + lane] : 1.0;  // 1 / L[lane][lane] from the factorisation
 #pragma unroll
       for (int j = CHOL_BS - 1; j >= 0; j--) {
         double xj = tv * myrcp;  // meaningful on lane j
@@ -820,33 +1007,86 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
 
 // landmark back-substitution (block_solver.hpp:461-481) + updates (types_sba.h:52-56, se3quat oplus) + computeScale
 __device__ void phase_backsub_update(const BaPtrs& p, const WinCtx& c, const BaWin& W, double lambda, int solveOk,
-                                     double* sm) {
+                                     double* sm, double* stage) {
   const int w = c.w;
   const int* ms = p.mpStart + (size_t)w * (p.capMp + 1);
   const int* me = p.mpEdges + (size_t)w * p.capE;
   const size_t xo = (size_t)w * (p.capKf * 6 + p.capMp * 3);
   double sc = 0;
-  for (int l = c.gtid; l < W.nMp; l += c.gthreads) {
-    const size_t mo = (size_t)w * p.capMp + l;
+  const int lane = threadIdx.x & 31;
+  const int* eKf = p.eKf + (size_t)w * p.capE;
+  const int* pidx = p.poseIndex + (size_t)w * p.capKf;
+  const double2* Wb2 = reinterpret_cast<const double2*>(p.W + (size_t)w * p.capE * 18);
+  double2* tA = reinterpret_cast<double2*>(stage) + (size_t)(threadIdx.x >> 5) * (2 * GATHER_TILE16);
+  for (int l0 = c.gtid - lane; l0 < W.nMp; l0 += c.gthreads) {  // 32 consecutive landmarks per warp, one per lane
+    const int l = l0 + lane;
+    const bool live = l < W.nMp;
+    const size_t mo = (size_t)w * p.capMp + (live ? l : 0);
     double* X = p.pts + mo * 3;
     double* Xb = p.ptsBak + mo * 3;
     if (!solveOk) {
-      for (int i = 0; i < 3; i++) Xb[i] = X[i];
+      if (live)
+        for (int i = 0; i < 3; i++) Xb[i] = X[i];
       continue;
     }
-    const double* bl = p.b + xo + (size_t)W.nFree * 6 + (size_t)l * 3;
+    const double* bl = p.b + xo + (size_t)W.nFree * 6 + (size_t)(live ? l : 0) * 3;
     double cl[3] = {bl[0], bl[1], bl[2]};
-    for (int k = ms[l]; k < ms[l + 1]; k++) {
-      const int e = me[k];
-      const size_t eo = (size_t)w * p.capE + e;
-      if (p.eLevel[eo]) continue;
-      const int pi = p.poseIndex[(size_t)w * p.capKf + p.eKf[eo]];
-      if (pi < 0) continue;
-      const double* Wb = p.W + eo * 18;
-      const double* xp = p.x + xo + (size_t)pi * 6;
-      for (int cc = 0; cc < 3; cc++)
-        for (int r = 0; r < 6; r++) cl[cc] -= Wb[r * 3 + cc] * xp[r];
+    const int kBeg = live ? ms[l] : 0, deg = live ? ms[l + 1] - kBeg : 0;
+    int maxDeg = deg;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxDeg = max(maxDeg, __shfl_xor_sync(0xffffffffu, maxDeg, o));
+    // k-th edge of every landmark of the group; W records gathered cooperatively, one iteration ahead (cp.async).
+    // Level-1 edges carry W_e = 0 and subtract exact zeros.
+    auto edgeOf = [&](int k, int& e, int& pi, bool& v) {
+      v = k < deg;
+      e = 0;
+      pi = -1;
+      if (v) {
+        e = me[kBeg + k];
+        pi = pidx[eKf[e]];
+        v = pi >= 0;
+      }
+    };
+    int e0, pi0, e1 = 0, pi1 = -1;
+    bool v0, v1 = false;
+    edgeOf(0, e0, pi0, v0);
+    if (maxDeg > 0) warp_gather16_async<9, 9>(tA, Wb2, e0, lane);
+    cp_async_commit();
+    if (maxDeg > 1) edgeOf(1, e1, pi1, v1);
+    for (int k = 0; k < maxDeg; k++) {
+      double2* cur = tA + (size_t)(k & 1) * GATHER_TILE16;
+      double2* nxt = tA + (size_t)((k & 1) ^ 1) * GATHER_TILE16;
+      if (k + 1 < maxDeg) warp_gather16_async<9, 9>(nxt, Wb2, e1, lane);
+      cp_async_commit();
+      int e2 = 0, pi2 = -1;
+      bool v2 = false;
+      if (k + 2 < maxDeg) edgeOf(k + 2, e2, pi2, v2);
+      cp_async_wait<1>();
+      __syncwarp();
+      if (v0) {
+        const double2* ra = cur + lane * 9;
+        double wb[18];
+#pragma unroll
+        for (int z = 0; z < 9; z++) {
+          const double2 t2 = ra[z];
+          wb[2 * z] = t2.x;
+          wb[2 * z + 1] = t2.y;
+        }
+        const double* xp = p.x + xo + (size_t)pi0 * 6;
+        double xv[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) xv[r] = xp[r];
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+          for (int r = 0; r < 6; r++) cl[cc] -= wb[r * 3 + cc] * xv[r];
+      }
+      __syncwarp();
+      v0 = v1; pi0 = pi1;
+      e1 = e2; pi1 = pi2; v1 = v2;
     }
+    cp_async_wait<0>();
+    if (!live) continue;
     const double* Di = p.Dinv + mo * 9;
     double* xout = p.x + xo + (size_t)W.nFree * 6 + (size_t)l * 3;
     for (int i = 0; i < 3; i++) {
@@ -877,21 +1117,49 @@ __device__ void phase_backsub_update(const BaPtrs& p, const WinCtx& c, const BaW
 }
 
 // computeActiveErrors + activeRobustChi2 after the update (sparse_optimizer.cpp:61-113), one thread per edge
+struct EdgeIn {  // operands of one edge, loaded ahead of the arithmetic
+  double P[7], X[3];
+  float ob[3], wgt;
+  bool stereo, live;
+};
+__device__ __forceinline__ void load_edge(const BaPtrs& p, int w, int e, int nE, EdgeIn& in) {
+  in.live = false;
+  if (e >= nE) return;
+  const size_t eo = (size_t)w * p.capE + e;
+  if (p.eLevel[eo]) return;
+  in.live = true;
+  const double* P = p.pose + ((size_t)w * p.capKf + p.eKf[eo]) * PSTRIDE;
+  const double* X = p.pts + ((size_t)w * p.capMp + p.eMp[eo]) * 3;
+#pragma unroll
+  for (int k = 0; k < 7; k++) in.P[k] = P[k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    in.X[k] = X[k];
+    in.ob[k] = p.eObs[eo * 3 + k];
+  }
+  in.wgt = p.eW[eo];
+  in.stereo = p.eStereo[eo];
+}
 __device__ void phase_errors(const BaPtrs& p, const WinCtx& c, const BaWin& W, int robust, double* sm) {
   const int w = c.w;
   double chi = 0;
-  for (int e = c.gtid; e < W.nEdges; e += c.gthreads) {
-    const size_t eo = (size_t)w * p.capE + e;
-    if (p.eLevel[eo]) continue;
-    double Xc[3], er[3];
-    pose_map(p.pose + ((size_t)w * p.capKf + p.eKf[eo]) * PSTRIDE, p.pts + ((size_t)w * p.capMp + p.eMp[eo]) * 3, Xc);
-    const bool stereo = p.eStereo[eo];
-    const double c2 = edge_error(Xc, stereo, p.eObs + eo * 3, (double)p.eW[eo], W, er);
-    p.err[eo * 3] = er[0]; p.err[eo * 3 + 1] = er[1]; p.err[eo * 3 + 2] = er[2];
-    p.chi2[eo] = c2;
-    double rho0 = c2, rho1;
-    if (robust) huber(c2, delta_of(stereo), rho0, rho1);
-    chi += rho0;
+  // two edges per thread and iteration: at 8 warps per SM the phase is bound by the dependent index -> operand load
+  // chain, so the second edge's loads are issued before the first edge's arithmetic
+  for (int e = c.gtid; e < W.nEdges; e += 2 * c.gthreads) {
+    EdgeIn in[2];
+    load_edge(p, w, e, W.nEdges, in[0]);
+    load_edge(p, w, e + c.gthreads, W.nEdges, in[1]);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      if (!in[h].live) continue;
+      double Xc[3], er[3];
+      pose_map(in[h].P, in[h].X, Xc);
+      const double c2 = edge_error(Xc, in[h].stereo, in[h].ob, (double)in[h].wgt, W, er);
+      p.chi2[(size_t)w * p.capE + e + h * c.gthreads] = c2;
+      double rho0 = c2, rho1;
+      if (robust) huber(c2, delta_of(in[h].stereo), rho0, rho1);
+      chi += rho0;
+    }
   }
   const double s = block_sum(chi, sm);
   if (threadIdx.x == 0) p.partChi[(size_t)w * p.nPartE + c.cta] = s;
@@ -984,7 +1252,7 @@ __device__ void phase_outliers(const BaPtrs& p, const WinCtx& c, const BaWin& W,
 
 // ---------------------------------------------------------------- the persistent kernel: grid = batch * nCta CTAs
 constexpr int BA_T = 256;
-__global__ void __launch_bounds__(BA_T) k_local_ba(BaPtrs p, int nCta, int wBase) {
+__global__ void __launch_bounds__(BA_T) k_local_ba(BaPtrs p, int nCta, int wBase, int dbgRepeat) {
   extern __shared__ __align__(16) double dsm[];
   __shared__ double red[32];
   WinCtx c;
@@ -1012,12 +1280,15 @@ __global__ void __launch_bounds__(BA_T) k_local_ba(BaPtrs p, int nCta, int wBase
     if (!vst->active || *hung) break;
     const int needBuild = vst->needBuild, robust = vst->robust;
     if (needBuild) {
-      phase_build_landmarks(p, c, W, robust, red);
-      win_barrier(bar, epoch, nCta, hung);
-      BA_PROF(0)
-      phase_build_poses(p, c, W, robust);
-      win_barrier(bar, epoch, nCta, hung);
-      BA_PROF(1)
+      for (int rr = ((dbgRepeat >> 8) == 2 ? (dbgRepeat & 255) : 1); rr > 0; rr--) {
+        phase_build_edges(p, c, W, robust, dsm, red);
+        win_barrier(bar, epoch, nCta, hung);
+        BA_PROF(0)
+        phase_reduce_landmarks(p, c, W);
+        phase_build_poses(p, c, W, robust);
+        win_barrier(bar, epoch, nCta, hung);
+        BA_PROF(1)
+      }
     }
     if (c.cta == 0 && threadIdx.x == 0) control_begin(p, w, nCta);
     win_barrier(bar, epoch, nCta, hung);
@@ -1026,17 +1297,23 @@ __global__ void __launch_bounds__(BA_T) k_local_ba(BaPtrs p, int nCta, int wBase
     phase_dinv(p, c, W, lambda);
     win_barrier(bar, epoch, nCta, hung);
     BA_PROF(3)
-    phase_schur_blocks(p, c, W, lambda);
-    win_barrier(bar, epoch, nCta, hung);
+    // dbgRepeat (profiling only, B2S_BA_REPEAT=phase*256+count): re-run one idempotent phase so that a whole-kernel
+    // ncu capture is dominated by it; 0 in production
+    for (int rr = ((dbgRepeat >> 8) == 1 ? (dbgRepeat & 255) : 1); rr > 0; rr--) {
+      phase_schur_blocks(p, c, W, lambda, dsm);
+      win_barrier(bar, epoch, nCta, hung);
+    }
     BA_PROF(5)
     if (c.cta == 0) phase_chol(p, w, W, dsm);
     win_barrier(bar, epoch, nCta, hung);
     BA_PROF(6)
-    phase_backsub_update(p, c, W, lambda, vst->solveOk, red);
+    phase_backsub_update(p, c, W, lambda, vst->solveOk, red, dsm);
     win_barrier(bar, epoch, nCta, hung);
     BA_PROF(7)
-    phase_errors(p, c, W, robust, red);
-    win_barrier(bar, epoch, nCta, hung);
+    for (int rr = ((dbgRepeat >> 8) == 3 ? (dbgRepeat & 255) : 1); rr > 0; rr--) {
+      phase_errors(p, c, W, robust, red);
+      win_barrier(bar, epoch, nCta, hung);
+    }
     BA_PROF(8)
     if (c.cta == 0 && threadIdx.x == 0) control_end(p, w, nCta);
     win_barrier(bar, epoch, nCta, hung);
@@ -1098,8 +1375,7 @@ __global__ void __launch_bounds__(64) k_pair_build(BaPtrs p, int fill) {
     __syncthreads();
     if (fill && hit) {
       const int pos = off[blockIdx.x] + running + (wid ? wsum[0] : 0) + __popc(bm & ((1u << lane) - 1u));
-      p.pairA[(size_t)w * p.capPairs + pos] = a;
-      p.pairC[(size_t)w * p.capPairs + pos] = cidx;
+      p.pairRec[(size_t)w * p.capPairs + pos] = make_int4(a, cidx, p.eMp[(size_t)w * p.capE + a], 0);
     }
     total += wsum[0] + wsum[1];
     __syncthreads();
@@ -1122,6 +1398,32 @@ __global__ void k_pair_scan(BaPtrs p, int batch) {
     off[t + 1] = run;
   }
   if (run > p.capPairs) p.usePairs[w] = 0;  // does not fit: fall back to probing every trial
+}
+
+// lower blocks sorted by descending pair count (ties by block id): the Schur phase deals them to its warps in this order
+__global__ void __launch_bounds__(256) k_block_order(BaPtrs p) {
+  const int w = blockIdx.x;
+  const BaWin W = p.win[w];
+  const int nb = W.nFree * (W.nFree + 1) / 2;
+  const int* off = p.blkOff + (size_t)w * (p.capBlk + 1);
+  int* order = p.blkOrder + (size_t)w * p.capBlk;
+  if (!p.usePairs[w]) {
+    for (int t = threadIdx.x; t < nb; t += blockDim.x) order[t] = t;
+    if (threadIdx.x == 0) p.blkNZ[w] = nb;
+    return;
+  }
+  int nz = 0;
+  for (int t = threadIdx.x; t < nb; t += blockDim.x) {
+    const int mine = off[t + 1] - off[t];
+    int rank = 0;
+    for (int u = 0; u < nb; u++) {
+      const int cu = off[u + 1] - off[u];
+      rank += (cu > mine) || (cu == mine && u < t);
+    }
+    order[rank] = t;
+    nz += mine > 0;
+  }
+  if (nz) atomicAdd(&p.blkNZ[w], nz);
 }
 
 }  // namespace b2s
@@ -1232,9 +1534,10 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   A(&d.Hpp, B * max_kf * 36 * 8); A(&d.Hll, B * max_mp * 9 * 8);
   A(&d.b, B * ((size_t)max_kf * 6 + (size_t)max_mp * 3) * 8); A(&d.x, B * ((size_t)max_kf * 6 + (size_t)max_mp * 3) * 8);
   A(&d.Dinv, B * max_mp * 9 * 8); A(&d.S, B * (size_t)d.ldS * d.ldS * 8);
-  A(&d.db, B * max_mp * 3 * 8); A(&d.Y, B * max_edges * 18 * 8);
+  A(&d.db, B * max_mp * 3 * 8); A(&d.DinvP, B * max_mp * 10 * 8); A(&d.hl, B * (size_t)max_edges * 9 * 8);
   A(&d.lmEdge, B * (size_t)max_mp * max_kf * 4); A(&d.freeKf, B * max_kf * 4);
-  A(&d.blkOff, B * (size_t)(d.capBlk + 1) * 4); A(&d.pairA, B * (size_t)d.capPairs * 4); A(&d.pairC, B * (size_t)d.capPairs * 4);
+  A(&d.blkOff, B * (size_t)(d.capBlk + 1) * 4); A(&d.pairRec, B * (size_t)d.capPairs * 16);
+  A(&d.blkOrder, B * (size_t)d.capBlk * 4); A(&d.blkNZ, B * 4);
   A(&d.usePairs, B * 4);
   A(&d.partChi, B * d.nPartE * 8); A(&d.partScale, B * d.nPartM * 8);
   A(&d.bar, B * 4);
@@ -1249,7 +1552,9 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   HA(&s.eObs, B * max_edges * 12); HA(&s.eW, B * max_edges * 4);
   HA(&s.eSt, B * max_edges); HA(&s.eOutlier, B * max_edges);
   HA(&s.win, B * sizeof(BaWin)); HA(&s.st, B * sizeof(BaState));
-  h->smemBytes = (size_t)((CHOL_BS + 1) * CHOL_PP + (size_t)(d.ldS + 4) * CHOL_PP + d.ldS) * 8;
+  h->smemBytes = (size_t)((CHOL_BS + 1) * CHOL_PP + (size_t)(d.ldS + 4) * CHOL_PP + 2 * d.ldS) * 8;
+  h->smemBytes = std::max(h->smemBytes, (size_t)(BA_T / 32) * 30 * 33 * 8);  // per-warp staging tiles of phase_build_edges
+  h->smemBytes = std::max(h->smemBytes, (size_t)(BA_T / 32) * 2 * GATHER_TILE16 * 16);  // double-buffered gather tiles (Schur)
   if (e == cudaSuccess && h->smemBytes > 48 * 1024)
     e = cudaFuncSetAttribute(k_local_ba, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes);
   if (e != cudaSuccess) {
@@ -1421,6 +1726,8 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
   k_pair_build<<<dim3(nblk, batch), 64, 0, st>>>(d, 0);
   k_pair_scan<<<div_up(batch, 64), 64, 0, st>>>(d, batch);
   k_pair_build<<<dim3(nblk, batch), 64, 0, st>>>(d, 1);
+  B2S_CUDA(cudaMemsetAsync(d.blkNZ, 0, nb * 4, st));
+  k_block_order<<<batch, 256, 0, st>>>(d);
   // ---- the whole LM loop of every window: one persistent launch, nCta co-resident CTAs per window
   int chunk = std::min(batch, h->numSMs);  // windows per cooperative launch (all their CTAs must be co-resident)
   if (const char* ev = getenv("B2S_BA_CHUNK")) chunk = std::max(1, std::min(chunk, atoi(ev)));  // tuning knob
@@ -1428,11 +1735,13 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
   if (const char* ev = getenv("B2S_BA_NCTA")) nCta = std::max(1, std::min(nCta, atoi(ev)));  // tuning knob
   for (int wBase = 0; wBase < batch; wBase += chunk) {
     int nw = std::min(chunk, batch - wBase);
-    void* args[] = {(void*)&d, (void*)&nCta, (void*)&wBase};
+    int dbgRepeat = 0;
+    if (const char* ev = getenv("B2S_BA_REPEAT")) dbgRepeat = atoi(ev);  // profiling aid, see k_local_ba
+    void* args[] = {(void*)&d, (void*)&nCta, (void*)&wBase, (void*)&dbgRepeat};
     B2S_CUDA(cudaLaunchCooperativeKernel((const void*)k_local_ba, dim3(nw * nCta), dim3(BA_T), args, h->smemBytes, st));
     h->launches++;
   }
-  h->launches += 4;
+  h->launches += 5;
   // asynchronous abort (LocalMapping::InsertKeyFrame sets mbAbortBA): forward the flag while the kernel runs
   if (stop) {
     bool sent = false;

@@ -124,33 +124,38 @@ class StereoStream:
         """imgs_host_np: numpy uint8 [2F, h, w]. Returns (counts, nmatches, ba_out); everything ends up in host memory."""
         F, cap = self.F, self.cap
         if getattr(self, "_h_kps", None) is None:  # pinned result buffers, allocated once
-            self._h_kps_t = torch.zeros((2 * F, cap, KP_BYTES), dtype=torch.uint8).pin_memory()
-            self._h_desc_t = torch.zeros((2 * F, cap, 32), dtype=torch.uint8).pin_memory()
-            self._h_kps = self._h_kps_t.numpy().view(keypoint_dtype).reshape(2 * F, cap)
+            # slot 0 = the frame before the shard's first one (ring), slots 1..2F = this step's images: both sides of the
+            # temporal matcher are then contiguous views, exactly like the device-resident layout
+            self._h_kps_t = torch.zeros((1 + 2 * F, cap, KP_BYTES), dtype=torch.uint8).pin_memory()
+            self._h_desc_t = torch.zeros((1 + 2 * F, cap, 32), dtype=torch.uint8).pin_memory()
+            self._h_kps = self._h_kps_t.numpy().view(keypoint_dtype).reshape(1 + 2 * F, cap)
             self._h_desc = self._h_desc_t.numpy()
-        res_kps, res_desc = self._h_kps, self._h_desc
-        n = np.zeros(2 * F, np.int32)
-        ptrs = (_vp * (2 * F))(*[imgs_host_np[i].ctypes.data for i in range(2 * F)])
+            self._h_n = np.zeros(1 + 2 * F, np.int32)
+            self._h_ang = torch.zeros((1 + F, cap), dtype=torch.float32).pin_memory().numpy()
+            self._h_node = torch.zeros((1 + F, cap), dtype=torch.int32).pin_memory().numpy()
+            self._h_valid = torch.ones((1 + F, cap), dtype=torch.uint8).pin_memory().numpy()
+            self._h_match = torch.zeros((F, cap), dtype=torch.int32).pin_memory().numpy()
+            self._h_nm = np.zeros(F, np.int32)
+            self._h_ptrs = (_vp * (2 * F))()
+        all_kps, all_desc, all_n = self._h_kps, self._h_desc, self._h_n
+        res_kps, res_desc, n = all_kps[1:], all_desc[1:], all_n[1:]
+        base, stride0 = imgs_host_np.ctypes.data, imgs_host_np.strides[0]
+        for i in range(2 * F):
+            self._h_ptrs[i] = base + i * stride0
         L = lib()
-        _check(L.b2s_extract_batch(self.ex._h, ctypes.cast(ptrs, _vp), 2 * F, self.w, self.h, self.w,
+        _check(L.b2s_extract_batch(self.ex._h, ctypes.cast(self._h_ptrs, _vp), 2 * F, self.w, self.h, self.w,
                                    res_kps.ctypes.data_as(_vp), res_desc.ctypes.data_as(_vp), cap,
                                    n.ctypes.data_as(_vp)))
-        # ring: pair f = (left f-1, left f)
-        order = [(f - 1) % F for f in range(F)]
-        descA = np.ascontiguousarray(res_desc[order])
-        angA = np.ascontiguousarray(res_kps["angle"][order])
-        nA = np.ascontiguousarray(n[order])
-        descB = res_desc[:F]
-        angB = np.ascontiguousarray(res_kps["angle"][:F])
-        nB = np.ascontiguousarray(n[:F])
-        node = np.zeros((F, cap), np.int32)
-        valid = np.ones((F, cap), np.uint8)
-        match = np.full((F, cap), -1, np.int32)
-        nm = np.zeros(F, np.int32)
+        # ring: pair f = (left f-1, left f); slot 0 <- the last left image
+        all_kps[0] = all_kps[F]
+        all_desc[0] = all_desc[F]
+        all_n[0] = all_n[F]
+        np.copyto(self._h_ang, all_kps["angle"][:1 + F])
+        ang, node, valid, match, nm = self._h_ang, self._h_node, self._h_valid, self._h_match, self._h_nm
         p = lambda a: a.ctypes.data_as(_vp)
-        _check(L.b2s_search_by_bow_batch(self.matcher._h, F, p(descA), p(node), p(valid), p(angA), p(nA), cap, p(descB),
-                                         p(node), None, p(angB), p(nB), cap, 50, float(self.matcher.mfNNratio), 0, 1,
-                                         p(match), p(nm)))
+        _check(L.b2s_search_by_bow_batch(self.matcher._h, F, p(all_desc), p(node), p(valid), p(ang), p(all_n), cap,
+                                         p(all_desc[1:]), p(node[1:]), None, p(ang[1:]), p(all_n[1:]), cap, 50,
+                                         float(self.matcher.mfNNratio), 0, 1, p(match), p(nm)))
         ba_out = None
         if run_ba and self.n_ba:
             if pipelined:  # results of the previous step's windows are returned; finish() joins the last batch
