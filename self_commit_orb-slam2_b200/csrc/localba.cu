@@ -59,6 +59,8 @@ struct BaPtrs {  // strided per-window arrays
   int *lmEdge, *freeKf;  // [landmark][free pose] -> edge id or -1 ; free pose index -> keyframe index
   int *blkOff, *usePairs;  // covisibility pair lists per lower block (built once per window): offsets, fits-flag
   int4* pairRec;           // pair record {edge of pose i1, edge of pose i2, landmark, 0}
+  int2* lmRec;             // landmark-CSR order: {edge, free pose index of its keyframe or -1}
+  int* blkFirst;           // per block row: first non-empty block column (envelope of the reduced system)
   int *blkOrder, *blkNZ;   // lower blocks sorted by descending pair count; number of non-empty blocks
   int capPairs, capBlk;
   double *partChi, *partScale;   // per-CTA partial sums [window][nCta]
@@ -293,6 +295,37 @@ struct WinCtx {
   int w, cta, nCta, gtid, gthreads;  // window id, CTA index inside the window, threads of the window
 };
 
+// Branch-free operand loads of one edge in two waves (everything indexed by the edge id, then the gathered pose and
+// landmark): callers issue the waves of several edges back to back so that the memory latencies overlap.  With 8 warps
+// per SM and three dependent loads per edge (level -> indices -> operands) these phases were bound by that chain.
+struct EdgeIdx {
+  int kf, mp;
+  float ob[3], wgt;
+  bool stereo, live;
+};
+struct EdgeOps {
+  double P[7], X[3];
+};
+__device__ __forceinline__ void load_edge_idx(const BaPtrs& p, int w, int e, int nE, EdgeIdx& x) {
+  const bool ok = e < nE;
+  const size_t eo = (size_t)w * p.capE + (ok ? e : 0);
+  x.live = ok & (p.eLevel[eo] == 0);
+  x.kf = p.eKf[eo];
+  x.mp = p.eMp[eo];
+#pragma unroll
+  for (int k = 0; k < 3; k++) x.ob[k] = p.eObs[eo * 3 + k];
+  x.wgt = p.eW[eo];
+  x.stereo = p.eStereo[eo] != 0;
+}
+__device__ __forceinline__ void load_edge_ops(const BaPtrs& p, int w, const EdgeIdx& x, EdgeOps& o) {
+  const double* P = p.pose + ((size_t)w * p.capKf + x.kf) * PSTRIDE;
+  const double* X = p.pts + ((size_t)w * p.capMp + x.mp) * 3;
+#pragma unroll
+  for (int k = 0; k < 7; k++) o.P[k] = P[k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) o.X[k] = X[k];
+}
+
 // ---------------------------------------------------------------- phases (device functions, strided over the window's threads)
 // computeActiveErrors + buildSystem, edge side (block_solver.hpp:502-560): one thread per edge in edge order — error,
 // chi2, Huber weight, the landmark-side products {A^T W A, A^T W e} and the pose-landmark block W_e = B^T W A.  The
@@ -304,81 +337,90 @@ __device__ void phase_build_edges(const BaPtrs& p, const WinCtx& c, const BaWin&
   double* tile = stage + (size_t)(threadIdx.x >> 5) * (30 * 33);
   const int nE = W.nEdges;
   double chi = 0;
-  for (int base = c.gtid - lane; base < nE; base += c.gthreads) {
-    const int e = base + lane;
-    const size_t eo = (size_t)w * p.capE + e;
-    double rec[30];
+  for (int base0 = c.gtid - lane; base0 < nE; base0 += 2 * c.gthreads) {
+    EdgeIdx ix[2];
+    EdgeOps op[2];
 #pragma unroll
-    for (int k = 0; k < 30; k++) rec[k] = 0;
-    if (e < nE && !p.eLevel[eo]) {
-      const int kf = p.eKf[eo];
-      const bool stereo = p.eStereo[eo];
-      EdgeJac J;
-      edge_jacobians(p.pose + ((size_t)w * p.capKf + kf) * PSTRIDE, p.pts + ((size_t)w * p.capMp + p.eMp[eo]) * 3, stereo,
-                     W.fx, W.fy, W.bf, J);
-      const double w0 = (double)p.eW[eo];
-      double er[3];
-      const double c2 = edge_error(J.Xc, stereo, p.eObs + eo * 3, w0, W, er);
-      p.chi2[eo] = c2;
-      double rho0 = c2, rho1 = 1.0;
-      if (robust) huber(c2, delta_of(stereo), rho0, rho1);
-      chi += rho0;
-      double omr[3];
+    for (int h = 0; h < 2; h++) load_edge_idx(p, w, base0 + h * c.gthreads + lane, nE, ix[h]);
 #pragma unroll
-      for (int r = 0; r < 3; r++) {
-        omr[r] = -(w0 * er[r]) * rho1;
-        rec[27 + r] = er[r];
-      }
-      const double wq = rho1 * w0;
-      // W_e (6x3)
+    for (int h = 0; h < 2; h++) load_edge_ops(p, w, ix[h], op[h]);
 #pragma unroll
-      for (int i = 0; i < 6; i++)
+    for (int h = 0; h < 2; h++) {
+      const int base = base0 + h * c.gthreads;
+      if (base >= nE) break;  // (warp-uniform)
+      const int e = base + lane;
+      const size_t eo = (size_t)w * p.capE + e;
+      double rec[30];
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-          double hh = 0;
+      for (int k = 0; k < 30; k++) rec[k] = 0;
+      if (ix[h].live) {
+        const bool stereo = ix[h].stereo;
+        EdgeJac J;
+        edge_jacobians(op[h].P, op[h].X, stereo, W.fx, W.fy, W.bf, J);
+        const double w0 = (double)ix[h].wgt;
+        double er[3];
+        const double c2 = edge_error(J.Xc, stereo, ix[h].ob, w0, W, er);
+        p.chi2[eo] = c2;
+        double rho0 = c2, rho1 = 1.0;
+        if (robust) huber(c2, delta_of(stereo), rho0, rho1);
+        chi += rho0;
+        double omr[3];
 #pragma unroll
-          for (int r = 0; r < 3; r++) hh += J.B[r][i] * wq * J.A[r][j];
-          rec[i * 3 + j] = hh;
+        for (int r = 0; r < 3; r++) {
+          omr[r] = -(w0 * er[r]) * rho1;
+          rec[27 + r] = er[r];
         }
-      // A^T (wq) A upper triangle, A^T omega_r
-      int t = 18;
+        const double wq = rho1 * w0;
+        // W_e (6x3)
 #pragma unroll
-      for (int i = 0; i < 3; i++)
+        for (int i = 0; i < 6; i++)
 #pragma unroll
-        for (int j = i; j < 3; j++) {
-          double hh = 0;
+          for (int j = 0; j < 3; j++) {
+            double hh = 0;
 #pragma unroll
-          for (int r = 0; r < 3; r++) hh += J.A[r][i] * wq * J.A[r][j];
-          rec[t++] = hh;
+            for (int r = 0; r < 3; r++) hh += J.B[r][i] * wq * J.A[r][j];
+            rec[i * 3 + j] = hh;
+          }
+        // A^T (wq) A upper triangle, A^T omega_r
+        int t = 18;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = i; j < 3; j++) {
+            double hh = 0;
+#pragma unroll
+            for (int r = 0; r < 3; r++) hh += J.A[r][i] * wq * J.A[r][j];
+            rec[t++] = hh;
+          }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          double s2 = 0;
+#pragma unroll
+          for (int r = 0; r < 3; r++) s2 += J.A[r][i] * omr[r];
+          rec[24 + i] = s2;
         }
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        double s2 = 0;
-#pragma unroll
-        for (int r = 0; r < 3; r++) s2 += J.A[r][i] * omr[r];
-        rec[24 + i] = s2;
       }
-    }
 #pragma unroll
-    for (int k = 0; k < 30; k++)
-      if (k < 18 || k >= 27) tile[k * 33 + lane] = rec[k];
-    __syncwarp();
-    double* Wout = p.W + ((size_t)w * p.capE + base) * 18;
-    const int nv = min(32, nE - base);
-    for (int idx = lane; idx < nv * 18; idx += 32) {
-      const int ed = idx / 18, k = idx - ed * 18;
-      Wout[idx] = tile[k * 33 + ed];
-    }
-    if (e < nE) {  // landmark-side terms: structure-of-arrays [term][edge], written straight from registers
+      for (int k = 0; k < 30; k++)
+        if (k < 18 || k >= 27) tile[k * 33 + lane] = rec[k];
+      __syncwarp();
+      double* Wout = p.W + ((size_t)w * p.capE + base) * 18;
+      const int nv = min(32, nE - base);
+      for (int idx = lane; idx < nv * 18; idx += 32) {
+        const int ed = idx / 18, k = idx - ed * 18;
+        Wout[idx] = tile[k * 33 + ed];
+      }
+      if (e < nE) {  // landmark-side terms: structure-of-arrays [term][edge], written straight from registers
 #pragma unroll
-      for (int k = 0; k < 9; k++) p.hl[((size_t)w * 9 + k) * p.capE + e] = rec[18 + k];
+        for (int k = 0; k < 9; k++) p.hl[((size_t)w * 9 + k) * p.capE + e] = rec[18 + k];
+      }
+      double* Eout = p.err + ((size_t)w * p.capE + base) * 3;
+      for (int idx = lane; idx < nv * 3; idx += 32) {
+        const int ed = idx / 3, k = idx - ed * 3;
+        Eout[idx] = tile[(27 + k) * 33 + ed];
+      }
+      __syncwarp();
     }
-    double* Eout = p.err + ((size_t)w * p.capE + base) * 3;
-    for (int idx = lane; idx < nv * 3; idx += 32) {
-      const int ed = idx / 3, k = idx - ed * 3;
-      Eout[idx] = tile[(27 + k) * 33 + ed];
-    }
-    __syncwarp();
   }
   const double s = block_sum(chi, sm);
   if (threadIdx.x == 0) p.partChi[(size_t)w * p.nPartE + c.cta] = s;
@@ -423,41 +465,71 @@ __device__ void phase_build_poses(const BaPtrs& p, const WinCtx& c, const BaWin&
 #pragma unroll
     for (int k = 0; k < 27; k++) acc[k] = 0;
     const double* P = p.pose + ((size_t)w * p.capKf + kf) * PSTRIDE;
-    for (int k = ks[kf] + lane; k < ks[kf + 1]; k += 32) {
-      const int e = ke[k];
-      const size_t eo = (size_t)w * p.capE + e;
-      if (p.eLevel[eo]) continue;
-      const bool stereo = p.eStereo[eo];
-      EdgeJac J;
-      edge_jacobians(P, p.pts + ((size_t)w * p.capMp + p.eMp[eo]) * 3, stereo, W.fx, W.fy, W.bf, J);
-      const double w0 = (double)p.eW[eo];
-      double rho1 = 1.0;
-      if (robust) {
-        double r0;
-        huber(p.chi2[eo], delta_of(stereo), r0, rho1);
+    double Pv[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) Pv[k] = P[k];
+    const int kBeg = ks[kf], kEnd = ks[kf + 1];
+    for (int k0 = kBeg; k0 < kEnd; k0 += 64) {  // two edges per lane and iteration, loads in three waves up front
+      int ee[2], mp[2];
+      bool live[2], stereo[2];
+      float wgt[2];
+      double c2v[2], er[2][3], X[2][3];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int kk = k0 + h * 32 + lane;
+        live[h] = kk < kEnd;
+        ee[h] = ke[live[h] ? kk : kBeg];
       }
-      const double* er = p.err + eo * 3;  // written by phase_build_edges
-      double omr[3];
 #pragma unroll
-      for (int r = 0; r < 3; r++) omr[r] = -(w0 * er[r]) * rho1;
-      const double wq = rho1 * w0;
-      int t = 0;
+      for (int h = 0; h < 2; h++) {
+        const size_t eo = (size_t)w * p.capE + ee[h];
+        live[h] = live[h] & (p.eLevel[eo] == 0);
+        stereo[h] = p.eStereo[eo] != 0;
+        mp[h] = p.eMp[eo];
+        wgt[h] = p.eW[eo];
+        c2v[h] = p.chi2[eo];
 #pragma unroll
-      for (int i = 0; i < 6; i++) {
+        for (int r = 0; r < 3; r++) er[h][r] = p.err[eo * 3 + r];  // written by phase_build_edges
+      }
 #pragma unroll
-        for (int j = i; j < 6; j++) {
-          double hh = 0;
+      for (int h = 0; h < 2; h++) {
+        const double* Xp = p.pts + ((size_t)w * p.capMp + mp[h]) * 3;
 #pragma unroll
-          for (int r = 0; r < 3; r++) hh += J.B[r][i] * wq * J.B[r][j];
-          acc[t++] += hh;
+        for (int r = 0; r < 3; r++) X[h][r] = Xp[r];
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        if (!live[h]) continue;
+        EdgeJac J;
+        edge_jacobians(Pv, X[h], stereo[h], W.fx, W.fy, W.bf, J);
+        const double w0 = (double)wgt[h];
+        double rho1 = 1.0;
+        if (robust) {
+          double r0;
+          huber(c2v[h], delta_of(stereo[h]), r0, rho1);
         }
-      }
+        double omr[3];
 #pragma unroll
-      for (int i = 0; i < 6; i++) {
-        double s = 0;
+        for (int r = 0; r < 3; r++) omr[r] = -(w0 * er[h][r]) * rho1;
+        const double wq = rho1 * w0;
+        int t = 0;
 #pragma unroll
-        for (int r = 0; r < 3; r++) s += J.B[r][i] * omr[r];
-        acc[21 + i] += s;
+        for (int i = 0; i < 6; i++) {
+#pragma unroll
+          for (int j = i; j < 6; j++) {
+            double hh = 0;
+#pragma unroll
+            for (int r = 0; r < 3; r++) hh += J.B[r][i] * wq * J.B[r][j];
+            acc[t++] += hh;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          double s2 = 0;
+#pragma unroll
+          for (int r = 0; r < 3; r++) s2 += J.B[r][i] * omr[r];
+          acc[21 + i] += s2;
+        }
       }
     }
 #pragma unroll
@@ -841,13 +913,16 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
   long long* prof = p.prof + (size_t)w * 16;
 #define CH_PROF(slot) if (threadIdx.x == 0) { const long long tn = clock64(); prof[slot] += tn - tc; tc = tn; }
   BaState& st = p.st[w];
-  const int n = W.nFree * 6, N1 = n + 1, ld = p.ldS;
+  const int n = W.nFree * 6, ld = p.ldS;
   double* S = p.S + (size_t)w * ld * ld;
   double* Dblk = dsm;                                // 33 x 33 (last row: reciprocal diagonal)
   double* panel = dsm + (CHOL_BS + 1) * CHOL_PP;     // (ld+4) x 33
   double* xs = panel + (size_t)(ld + 4) * CHOL_PP;   // ld
   double* rdiag = xs + ld;                           // ld: 1 / L[i][i], kept for the back substitution
-  __shared__ int fail;
+  int* rowList = reinterpret_cast<int*>(rdiag + ld);  // ld + 4 ints: compacted row list of the current block column
+  int* bfirst = rowList + ld + 4;                     // nFree ints: first non-empty block of every block row (envelope)
+  __shared__ int fail, mRows;
+  for (int i = threadIdx.x; i < W.nFree; i += blockDim.x) bfirst[i] = p.blkFirst[(size_t)w * p.capKf + i];
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
   if (tid == 0) fail = 0;
   __syncthreads();
@@ -890,6 +965,15 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
       for (int cc = 0; cc < CHOL_BS; cc++) Dblk[lane * CHOL_PP + cc] = (cc <= lane) ? row[cc] : 0.0;
       Dblk[CHOL_BS * CHOL_PP + lane] = mydinv;
       if (lane < wd) rdiag[kb + lane] = mydinv;
+    } else if (tid == 32) {  // meanwhile: the rows this block column reaches (envelope), in ascending order
+      int cnt = 0;
+      const int rEnd = kb + wd;
+      for (int pr = rEnd / 6; pr < W.nFree; pr++) {
+        if (bfirst[pr] * 6 >= rEnd) continue;
+        for (int i = max(pr * 6, rEnd); i < pr * 6 + 6; i++) rowList[cnt++] = i;
+      }
+      rowList[cnt++] = n;
+      mRows = cnt;
     }
     __syncthreads();
     CH_PROF(11)
@@ -897,9 +981,11 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
       const int r = idx / wd, cc = idx - r * wd;
       if (cc <= r) S[(size_t)(kb + r) * ld + kb + cc] = Dblk[r * CHOL_PP + cc];
     }
-    const int m = N1 - (kb + wd);  // rows below the diagonal block (including the augmented row)
+    // rows below the diagonal block whose envelope reaches into this block column (rowList, built during the factor
+    // step; the augmented row n is always among them); all other rows hold zeros here and stay untouched
+    const int m = mRows;
     for (int rowi = tid; rowi < m; rowi += T) {
-      const int i = kb + wd + rowi;
+      const int i = rowList[rowi];
       double v[CHOL_BS];
       const double* dinv = Dblk + CHOL_BS * CHOL_PP;
 #pragma unroll
@@ -947,13 +1033,16 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
       }
 #pragma unroll
       for (int a = 0; a < 4; a++) {
-        const int i = 4 * ti + a;
-        if (i >= m) continue;
+        const int ia = 4 * ti + a;
+        if (ia >= m) continue;
+        const int i = rowList[ia];
 #pragma unroll
         for (int b2 = 0; b2 < 4; b2++) {
-          const int j = 4 * tj + b2;
-          if (j > i || kb + wd + j >= n) continue;  // lower triangle only; column n is never needed
-          S[(size_t)(kb + wd + i) * ld + kb + wd + j] -= acc[a][b2];
+          const int jb = 4 * tj + b2;
+          if (jb > ia) continue;  // lower triangle only (the list is ascending)
+          const int j = rowList[jb];
+          if (j >= n) continue;   // column n is never needed
+          S[(size_t)i * ld + j] -= acc[a][b2];
         }
       }
     }
@@ -988,7 +1077,9 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
       if (lane < wd) xs[kb + lane] = tv;
     }
     __syncthreads();
-    for (int cc = tid; cc < kb; cc += T) {
+    int cmin = kb;  // leftmost column any row of this block reaches
+    for (int pr = kb / 6; pr <= min((kb + wd - 1) / 6, W.nFree - 1); pr++) cmin = min(cmin, bfirst[pr] * 6);
+    for (int cc = cmin + tid; cc < kb; cc += T) {
       double sacc = xs[cc];
 #pragma unroll 8
       for (int r = 0; r < CHOL_BS; r++)
@@ -1010,12 +1101,10 @@ __device__ void phase_backsub_update(const BaPtrs& p, const WinCtx& c, const BaW
                                      double* sm, double* stage) {
   const int w = c.w;
   const int* ms = p.mpStart + (size_t)w * (p.capMp + 1);
-  const int* me = p.mpEdges + (size_t)w * p.capE;
   const size_t xo = (size_t)w * (p.capKf * 6 + p.capMp * 3);
   double sc = 0;
   const int lane = threadIdx.x & 31;
-  const int* eKf = p.eKf + (size_t)w * p.capE;
-  const int* pidx = p.poseIndex + (size_t)w * p.capKf;
+  const int2* lrec = p.lmRec + (size_t)w * p.capE;
   const double2* Wb2 = reinterpret_cast<const double2*>(p.W + (size_t)w * p.capE * 18);
   double2* tA = reinterpret_cast<double2*>(stage) + (size_t)(threadIdx.x >> 5) * (2 * GATHER_TILE16);
   for (int l0 = c.gtid - lane; l0 < W.nMp; l0 += c.gthreads) {  // 32 consecutive landmarks per warp, one per lane
@@ -1035,36 +1124,29 @@ __device__ void phase_backsub_update(const BaPtrs& p, const WinCtx& c, const BaW
     int maxDeg = deg;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxDeg = max(maxDeg, __shfl_xor_sync(0xffffffffu, maxDeg, o));
-    // k-th edge of every landmark of the group; W records gathered cooperatively, one iteration ahead (cp.async).
-    // Level-1 edges carry W_e = 0 and subtract exact zeros.
-    auto edgeOf = [&](int k, int& e, int& pi, bool& v) {
-      v = k < deg;
-      e = 0;
-      pi = -1;
-      if (v) {
-        e = me[kBeg + k];
-        pi = pidx[eKf[e]];
-        v = pi >= 0;
+    // Edges k .. k+4 of every landmark of the group at once: their {edge, pose} records, then their W records (gathered
+    // cooperatively with cp.async into five tiles) are all in flight together, so a group costs two memory latencies
+    // instead of three per edge.  Level-1 edges carry W_e = 0 and subtract exact zeros.
+    constexpr int NBUF = 5, TILE = 32 * 9;
+    for (int kb0 = 0; kb0 < maxDeg; kb0 += NBUF) {
+      int ee[NBUF], pp[NBUF];
+#pragma unroll
+      for (int j = 0; j < NBUF; j++) {
+        const int k = kb0 + j;
+        const int2 r = (k < deg) ? lrec[kBeg + k] : make_int2(0, -1);
+        ee[j] = r.x;
+        pp[j] = r.y;
       }
-    };
-    int e0, pi0, e1 = 0, pi1 = -1;
-    bool v0, v1 = false;
-    edgeOf(0, e0, pi0, v0);
-    if (maxDeg > 0) warp_gather16_async<9, 9>(tA, Wb2, e0, lane);
-    cp_async_commit();
-    if (maxDeg > 1) edgeOf(1, e1, pi1, v1);
-    for (int k = 0; k < maxDeg; k++) {
-      double2* cur = tA + (size_t)(k & 1) * GATHER_TILE16;
-      double2* nxt = tA + (size_t)((k & 1) ^ 1) * GATHER_TILE16;
-      if (k + 1 < maxDeg) warp_gather16_async<9, 9>(nxt, Wb2, e1, lane);
+#pragma unroll
+      for (int j = 0; j < NBUF; j++)
+        if (kb0 + j < maxDeg) warp_gather16_async<9, 9>(tA + j * TILE, Wb2, ee[j], lane);
       cp_async_commit();
-      int e2 = 0, pi2 = -1;
-      bool v2 = false;
-      if (k + 2 < maxDeg) edgeOf(k + 2, e2, pi2, v2);
-      cp_async_wait<1>();
+      cp_async_wait<0>();
       __syncwarp();
-      if (v0) {
-        const double2* ra = cur + lane * 9;
+#pragma unroll
+      for (int j = 0; j < NBUF; j++) {
+        if (pp[j] < 0) continue;
+        const double2* ra = tA + j * TILE + lane * 9;
         double wb[18];
 #pragma unroll
         for (int z = 0; z < 9; z++) {
@@ -1072,7 +1154,7 @@ __device__ void phase_backsub_update(const BaPtrs& p, const WinCtx& c, const BaW
           wb[2 * z] = t2.x;
           wb[2 * z + 1] = t2.y;
         }
-        const double* xp = p.x + xo + (size_t)pi0 * 6;
+        const double* xp = p.x + xo + (size_t)pp[j] * 6;
         double xv[6];
 #pragma unroll
         for (int r = 0; r < 6; r++) xv[r] = xp[r];
@@ -1082,10 +1164,7 @@ __device__ void phase_backsub_update(const BaPtrs& p, const WinCtx& c, const BaW
           for (int r = 0; r < 6; r++) cl[cc] -= wb[r * 3 + cc] * xv[r];
       }
       __syncwarp();
-      v0 = v1; pi0 = pi1;
-      e1 = e2; pi1 = pi2; v1 = v2;
     }
-    cp_async_wait<0>();
     if (!live) continue;
     const double* Di = p.Dinv + mo * 9;
     double* xout = p.x + xo + (size_t)W.nFree * 6 + (size_t)l * 3;
@@ -1117,47 +1196,26 @@ __device__ void phase_backsub_update(const BaPtrs& p, const WinCtx& c, const BaW
 }
 
 // computeActiveErrors + activeRobustChi2 after the update (sparse_optimizer.cpp:61-113), one thread per edge
-struct EdgeIn {  // operands of one edge, loaded ahead of the arithmetic
-  double P[7], X[3];
-  float ob[3], wgt;
-  bool stereo, live;
-};
-__device__ __forceinline__ void load_edge(const BaPtrs& p, int w, int e, int nE, EdgeIn& in) {
-  in.live = false;
-  if (e >= nE) return;
-  const size_t eo = (size_t)w * p.capE + e;
-  if (p.eLevel[eo]) return;
-  in.live = true;
-  const double* P = p.pose + ((size_t)w * p.capKf + p.eKf[eo]) * PSTRIDE;
-  const double* X = p.pts + ((size_t)w * p.capMp + p.eMp[eo]) * 3;
-#pragma unroll
-  for (int k = 0; k < 7; k++) in.P[k] = P[k];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    in.X[k] = X[k];
-    in.ob[k] = p.eObs[eo * 3 + k];
-  }
-  in.wgt = p.eW[eo];
-  in.stereo = p.eStereo[eo];
-}
 __device__ void phase_errors(const BaPtrs& p, const WinCtx& c, const BaWin& W, int robust, double* sm) {
   const int w = c.w;
   double chi = 0;
-  // two edges per thread and iteration: at 8 warps per SM the phase is bound by the dependent index -> operand load
-  // chain, so the second edge's loads are issued before the first edge's arithmetic
-  for (int e = c.gtid; e < W.nEdges; e += 2 * c.gthreads) {
-    EdgeIn in[2];
-    load_edge(p, w, e, W.nEdges, in[0]);
-    load_edge(p, w, e + c.gthreads, W.nEdges, in[1]);
+  // four edges per thread and iteration, loaded in two waves ahead of the arithmetic (see load_edge_idx)
+  for (int e = c.gtid; e < W.nEdges; e += 4 * c.gthreads) {
+    EdgeIdx ix[4];
+    EdgeOps op[4];
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      if (!in[h].live) continue;
+    for (int h = 0; h < 4; h++) load_edge_idx(p, w, e + h * c.gthreads, W.nEdges, ix[h]);
+#pragma unroll
+    for (int h = 0; h < 4; h++) load_edge_ops(p, w, ix[h], op[h]);
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+      if (!ix[h].live) continue;
       double Xc[3], er[3];
-      pose_map(in[h].P, in[h].X, Xc);
-      const double c2 = edge_error(Xc, in[h].stereo, in[h].ob, (double)in[h].wgt, W, er);
+      pose_map(op[h].P, op[h].X, Xc);
+      const double c2 = edge_error(Xc, ix[h].stereo, ix[h].ob, (double)ix[h].wgt, W, er);
       p.chi2[(size_t)w * p.capE + e + h * c.gthreads] = c2;
       double rho0 = c2, rho1;
-      if (robust) huber(c2, delta_of(in[h].stereo), rho0, rho1);
+      if (robust) huber(c2, delta_of(ix[h].stereo), rho0, rho1);
       chi += rho0;
     }
   }
@@ -1339,6 +1397,8 @@ __global__ void __launch_bounds__(256) k_lm_edge(BaPtrs p) {
   const size_t eo = (size_t)w * p.capE + e;
   const int pi = p.poseIndex[(size_t)w * p.capKf + p.eKf[eo]];
   if (pi >= 0) p.lmEdge[((size_t)w * p.capMp + p.eMp[eo]) * p.capKf + pi] = e;
+  const int ek = p.mpEdges[eo];  // position e of the landmark-ordered edge list
+  p.lmRec[eo] = make_int2(ek, p.poseIndex[(size_t)w * p.capKf + p.eKf[(size_t)w * p.capE + ek]]);
 }
 
 // covisibility pair lists: for every lower block (i1 >= i2) the (edge of pose i1, edge of pose i2) pairs that share a
@@ -1407,10 +1467,22 @@ __global__ void __launch_bounds__(256) k_block_order(BaPtrs p) {
   const int nb = W.nFree * (W.nFree + 1) / 2;
   const int* off = p.blkOff + (size_t)w * (p.capBlk + 1);
   int* order = p.blkOrder + (size_t)w * p.capBlk;
+  int* first = p.blkFirst + (size_t)w * p.capKf;
   if (!p.usePairs[w]) {
     for (int t = threadIdx.x; t < nb; t += blockDim.x) order[t] = t;
+    for (int i = threadIdx.x; i < W.nFree; i += blockDim.x) first[i] = 0;  // structure unknown: dense
     if (threadIdx.x == 0) p.blkNZ[w] = nb;
     return;
+  }
+  for (int i1 = threadIdx.x; i1 < W.nFree; i1 += blockDim.x) {
+    int f = i1;
+    const int t0 = i1 * (i1 + 1) / 2;
+    for (int i2 = 0; i2 < i1; i2++)
+      if (off[t0 + i2 + 1] > off[t0 + i2]) {
+        f = i2;
+        break;
+      }
+    first[i1] = f;
   }
   int nz = 0;
   for (int t = threadIdx.x; t < nb; t += blockDim.x) {
@@ -1537,7 +1609,7 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   A(&d.db, B * max_mp * 3 * 8); A(&d.DinvP, B * max_mp * 10 * 8); A(&d.hl, B * (size_t)max_edges * 9 * 8);
   A(&d.lmEdge, B * (size_t)max_mp * max_kf * 4); A(&d.freeKf, B * max_kf * 4);
   A(&d.blkOff, B * (size_t)(d.capBlk + 1) * 4); A(&d.pairRec, B * (size_t)d.capPairs * 16);
-  A(&d.blkOrder, B * (size_t)d.capBlk * 4); A(&d.blkNZ, B * 4);
+  A(&d.lmRec, B * (size_t)max_edges * 8); A(&d.blkFirst, B * (size_t)max_kf * 4); A(&d.blkOrder, B * (size_t)d.capBlk * 4); A(&d.blkNZ, B * 4);
   A(&d.usePairs, B * 4);
   A(&d.partChi, B * d.nPartE * 8); A(&d.partScale, B * d.nPartM * 8);
   A(&d.bar, B * 4);
@@ -1552,7 +1624,7 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   HA(&s.eObs, B * max_edges * 12); HA(&s.eW, B * max_edges * 4);
   HA(&s.eSt, B * max_edges); HA(&s.eOutlier, B * max_edges);
   HA(&s.win, B * sizeof(BaWin)); HA(&s.st, B * sizeof(BaState));
-  h->smemBytes = (size_t)((CHOL_BS + 1) * CHOL_PP + (size_t)(d.ldS + 4) * CHOL_PP + 2 * d.ldS) * 8;
+  h->smemBytes = (size_t)((CHOL_BS + 1) * CHOL_PP + (size_t)(d.ldS + 4) * CHOL_PP + 2 * d.ldS) * 8 + (size_t)(d.ldS + 8 + max_kf) * 4;
   h->smemBytes = std::max(h->smemBytes, (size_t)(BA_T / 32) * 30 * 33 * 8);  // per-warp staging tiles of phase_build_edges
   h->smemBytes = std::max(h->smemBytes, (size_t)(BA_T / 32) * 2 * GATHER_TILE16 * 16);  // double-buffered gather tiles (Schur)
   if (e == cudaSuccess && h->smemBytes > 48 * 1024)

@@ -91,3 +91,29 @@ def test_local_ba_batch(pkg, oracle):
     outs = opt.LocalBundleAdjustmentBatch(ds)
     for d, out in zip(ds, outs):
         _check(out, oracle.local_ba(d), d)
+
+
+def test_local_ba_shuffled_keyframes(pkg, oracle):
+    """Keyframe ids permuted: the covisibility pattern of the reduced system is scattered instead of banded, so the
+    envelope logic of the Cholesky and the sorted Schur block order see a general structure."""
+    d = synth_local_ba(n_kf=30, n_fixed=6, n_mp=1500, obs_per_mp=5, seed=21)
+    rng = np.random.RandomState(5)
+    nl = d["n_local"]
+    perm = np.arange(d["n_kf"])
+    perm[1:nl] = 1 + rng.permutation(nl - 1)  # new index -> old index (index 0 stays the fixed origin)
+    inv = np.argsort(perm)
+    d["Tcw"] = np.ascontiguousarray(d["Tcw"][perm])
+    d["fixed"] = np.ascontiguousarray(d["fixed"][perm])
+    d["edges"]["kf"] = inv[d["edges"]["kf"]].astype(np.int32)
+    opt = pkg.Optimizer(max_kf=32, max_mp=2048, max_edges=8192)
+    _check(opt.LocalBundleAdjustment(d), oracle.local_ba(d), d)
+
+
+def test_local_ba_pair_list_overflow(pkg, oracle):
+    """High-degree landmarks with a tight edge capacity: the covisibility pair list does not fit (8 x max_edges) and the
+    Schur phase falls back to probing the landmark -> edge table."""
+    d = synth_local_ba(n_kf=24, n_fixed=2, n_mp=150, obs_per_mp=20, seed=31)
+    deg = np.bincount(d["edges"]["mp"][d["fixed"][d["edges"]["kf"]] == 0])
+    assert (deg * (deg + 1) // 2).sum() > 8 * len(d["edges"])
+    opt = pkg.Optimizer(max_kf=24, max_mp=150, max_edges=len(d["edges"]))
+    _check(opt.LocalBundleAdjustment(d), oracle.local_ba(d), d)
