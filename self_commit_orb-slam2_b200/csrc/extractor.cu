@@ -868,15 +868,15 @@ __global__ void __launch_bounds__(256) k_orient_describe(ExtractGeom g, const ui
   // IC_Angle: m10 = sum u*I, m01 = sum v*I over the 31-row circular patch (lane = column)
   const uint8_t* img = pyr + (size_t)b * g.pyrBytes + L.off;
   int m01 = 0, m10 = 0;
-#pragma unroll 1
+  // all 31 row loads are independent: fully unrolled so that they are in flight together (integer sums: any order)
+  const uint8_t* ctr = img + (size_t)cy * L.pitch + cx;
+#pragma unroll
   for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
     const int d = c_umax[v < 0 ? -v : v];
     const int u = lane - d;
-    if (u <= d) {
-      const int val = img[(size_t)(cy + v) * L.pitch + cx + u];
-      m10 += u * val;
-      m01 += v * val;
-    }
+    const int val = (u <= d) ? (int)ctr[v * L.pitch + u] : 0;
+    m10 += u * val;
+    m01 += v * val;
   }
   m01 = warp_reduce_sum(m01);
   m10 = warp_reduce_sum(m10);

@@ -435,11 +435,23 @@ __device__ void phase_reduce_landmarks(const BaPtrs& p, const WinCtx& c, const B
   for (int l = c.gtid; l < W.nMp; l += c.gthreads) {
     const size_t mo = (size_t)w * p.capMp + l;
     double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = ms[l]; k < ms[l + 1]; k++) {
-      const size_t eo = (size_t)w * p.capE + me[k];
-      if (p.eLevel[eo]) continue;
+    // level-1 edges carry zero terms (phase_build_edges); four edges' loads are issued together, summed in list order
+    const int kBeg = ms[l], kEnd = ms[l + 1];
+    for (int k0 = kBeg; k0 < kEnd; k0 += 4) {
+      int ee[4];
+      double v[4][9];
 #pragma unroll
-      for (int q = 0; q < 9; q++) h[q] += p.hl[((size_t)w * 9 + q) * p.capE + me[k]];
+      for (int j = 0; j < 4; j++) ee[j] = me[min(k0 + j, kEnd - 1)];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int q = 0; q < 9; q++) v[j][q] = p.hl[((size_t)w * 9 + q) * p.capE + ee[j]];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (k0 + j < kEnd) {
+#pragma unroll
+          for (int q = 0; q < 9; q++) h[q] += v[j][q];
+        }
     }
     double* H = p.Hll + mo * 9;
     H[0] = h[0]; H[1] = h[1]; H[2] = h[2];
@@ -1792,6 +1804,11 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
   B2S_CUDA(cudaMemsetAsync(d.bar, 0, nb * 4, st));
   B2S_CUDA(cudaMemsetAsync(d.prof, 0, nb * 16 * 8, st));
   const auto tPrep = std::chrono::steady_clock::now();
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (dbg) {
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], st);  // uploads + memsets enqueued before this point
+  }
   const int gE = std::max(1, div_up(maxE, 256));
   k_lm_edge<<<dim3(gE, batch), 256, 0, st>>>(d);
   const int nblk = std::max(1, maxFree * (maxFree + 1) / 2);
@@ -1801,6 +1818,7 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
   B2S_CUDA(cudaMemsetAsync(d.blkNZ, 0, nb * 4, st));
   k_block_order<<<batch, 256, 0, st>>>(d);
   // ---- the whole LM loop of every window: one persistent launch, nCta co-resident CTAs per window
+  if (dbg) cudaEventRecord(ev[1], st);
   int chunk = std::min(batch, h->numSMs);  // windows per cooperative launch (all their CTAs must be co-resident)
   if (const char* ev = getenv("B2S_BA_CHUNK")) chunk = std::max(1, std::min(chunk, atoi(ev)));  // tuning knob
   int nCta = std::max(1, std::min(16, h->numSMs / chunk));
@@ -1814,6 +1832,7 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
     h->launches++;
   }
   h->launches += 5;
+  if (dbg) cudaEventRecord(ev[2], st);
   // asynchronous abort (LocalMapping::InsertKeyFrame sets mbAbortBA): forward the flag while the kernel runs
   if (stop) {
     bool sent = false;
@@ -1833,6 +1852,7 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
   B2S_CUDA(cudaMemcpyAsync(s.pts, d.pts, nb * (size_t)d.capMp * 3 * 8, cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaMemcpyAsync(s.eOutlier, d.eOutlier, nb * d.capE, cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaMemcpyAsync(s.st, d.st, nb * sizeof(BaState), cudaMemcpyDeviceToHost, st));
+  if (dbg) cudaEventRecord(ev[3], st);
   B2S_CUDA(cudaStreamSynchronize(st));
   B2S_CUDA(cudaGetLastError());
   for (int w = 0; w < batch; w++)
@@ -1894,6 +1914,12 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
     fprintf(stderr, "\n");
     fprintf(stderr, "[b2s_local_ba] batch=%d nCta=%d prep+upload %.2f ms, structure+LM kernel %.2f ms, write-back %.2f ms\n",
             batch, nCta, ms(tStart, tPrep), ms(tPrep, tLoop), ms(tLoop, tEnd));
+    float e01 = 0, e12 = 0, e23 = 0;
+    cudaEventElapsedTime(&e01, ev[0], ev[1]);
+    cudaEventElapsedTime(&e12, ev[1], ev[2]);
+    cudaEventElapsedTime(&e23, ev[2], ev[3]);
+    fprintf(stderr, "[b2s_local_ba] device: structure kernels %.2f ms, LM kernel %.2f ms, D2H %.2f ms\n", e01, e12, e23);
+    for (auto& e : ev) cudaEventDestroy(e);
   }
   return B2S_OK;
 }
