@@ -68,6 +68,14 @@ constexpr int FP = 80;   // byte pitch of the raw ROI / score map (ROI width <= 
 constexpr int FR = 68;   // max ROI rows
 constexpr int PW = 40;   // word pitch of the packed pixel-pair planes (<= 38 pair words per row, even => 8-byte stores)
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts_v2(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts_zero16(uint32_t a) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
+}
+
 // FAST-9/16 arc strength of a horizontal PIXEL PAIR in packed 16-bit lanes (DPX VIMNMX3.U16x2).
 // d'_k = 256 + v - p_k per lane (in [1,511], so one 32-bit subtract never borrows across lanes).
 // dark  strength = max_s min_{j<9} d'_{s+j} - 256 ; bright strength = 256 - min_s max_{j<9} d'_{s+j}.
@@ -165,22 +173,37 @@ __global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t
   // Column coordinates below are ALIGNED columns X = x_roi + a0, with a0 = iniX & 3.
   const int a0 = iniX & 3;
   const int nWords = (a0 + rw + 4 + 3) >> 2;  // <= 19
-  const uint8_t* srcRow = pyr + (size_t)b * g.pyrBytes + L.off + (size_t)iniY * L.pitch + (iniX - a0);
-  for (int r = warp; r < rh; r += 4) {
-    uint32_t wv = 0;
-    if (lane < nWords && (iniX - a0) + lane * 4 + 3 < L.pitch)
-      wv = *reinterpret_cast<const uint32_t*>(srcRow + (size_t)r * L.pitch + lane * 4);
-    const uint32_t wn = __shfl_down_sync(0xffffffffu, wv, 1);
-    if (lane < nWords) {
-      uint2 e2, o2;
-      e2.x = __byte_perm(wv, 0u, 0x4140);                     // (b0, b1)
-      e2.y = __byte_perm(wv, 0u, 0x4342);                     // (b2, b3)
-      o2.x = __byte_perm(wv, 0u, 0x4241);                     // (b1, b2)
-      o2.y = (wv >> 24) | ((wn & 0xffu) << 16);               // (b3, next b0)
-      *reinterpret_cast<uint2*>(&planeE[r * PW + 2 * lane]) = e2;
-      *reinterpret_cast<uint2*>(&planeO[r * PW + 2 * lane]) = o2;
+  const int pitch = L.pitch;
+  {
+    // each warp owns rows warp, warp+4, ...; the (up to) nine global loads of a chunk are issued before any is
+    // consumed, shared addresses are plain 32-bit offsets (one memory latency per chunk instead of one per row)
+    const bool colOK = lane < nWords && (iniX - a0) + lane * 4 + 3 < pitch;
+    const uint8_t* p0 = pyr + (size_t)b * g.pyrBytes + L.off + (size_t)(iniY + warp) * pitch + (iniX - a0) + lane * 4;
+    const uint32_t eA = smem_u32(planeE) + (uint32_t)(warp * PW + 2 * lane) * 4u;
+    const uint32_t oA = smem_u32(planeO) + (uint32_t)(warp * PW + 2 * lane) * 4u;
+    for (int r0 = warp; r0 < rh; r0 += 36) {
+      uint32_t wv[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) {
+        const int r = r0 + 4 * i;
+        wv[i] = 0u;
+        if (colOK && r < rh) wv[i] = __ldg(reinterpret_cast<const uint32_t*>(p0 + (size_t)(r - warp) * pitch));
+      }
+#pragma unroll
+      for (int i = 0; i < 9; i++) {
+        const int r = r0 + 4 * i;
+        if (r >= rh) break;  // (warp-uniform)
+        const uint32_t w0 = wv[i];
+        const uint32_t wn = __shfl_down_sync(0xffffffffu, w0, 1);
+        if (lane < nWords) {
+          const uint32_t rowOff = (uint32_t)(r - warp) * (PW * 4u);
+          sts_v2(eA + rowOff, __byte_perm(w0, 0u, 0x4140), __byte_perm(w0, 0u, 0x4342));             // (b0,b1) (b2,b3)
+          sts_v2(oA + rowOff, __byte_perm(w0, 0u, 0x4241), (w0 >> 24) | ((wn & 0xffu) << 16));        // (b1,b2) (b3,b4)
+        }
+      }
     }
-    if (lane < FP / 4) *reinterpret_cast<uint32_t*>(&score[r * FP + lane * 4]) = 0u;
+    const uint32_t sA = smem_u32(score);
+    for (int k = tid; k < (rh * FP) / 16; k += 128) sts_zero16(sA + (uint32_t)k * 16u);
   }
   if (tid == 0) {
     sN = 0;
@@ -239,33 +262,30 @@ __global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t
     }
   }
   __syncthreads();
-  // ---- 3x3 NMS inside the cell's detectable area (rim scores are 0 == "not a corner" in OpenCV's buffers)
-  for (int y0 = 0; y0 < ih; y0 += rowsPerPass) {
-    const int y = y0 + myRow + 3;
-    uint32_t found = 0;  // up to two survivors per thread: (X | y<<8 | M<<16), 0 = none
-    uint32_t found2 = 0;
-    if (y < rh - 3 && myPair < npair) {
+  // ---- 3x3 NMS inside the cell's detectable area (rim scores are 0 == "not a corner" in OpenCV's buffers).
+  // Only pixels of pairs that passed the quick test can have a non-zero score, so the NMS walks the pass list; the
+  // survivors (X | y<<8 | M<<16) go to `surv`, which reuses the pixel-pair plane E (dead after pass 2).
+  uint32_t* surv = planeE;
+  const int minTh = g.minTh, iniTh = g.iniTh;
+  auto nms_pair = [&](int pr, int y) -> uint32_t {  // two adjacent pixels can never both survive a strict 3x3 NMS
+    uint32_t ent = 0;
 #pragma unroll
-      for (int h2 = 0; h2 < 2; h2++) {
-        const int X = xFirst + 2 * myPair + h2;
-        if (X < xLo || X >= xHi) continue;
-        const uint8_t* sc = &score[y * FP + X];
-        const int M = sc[0];
-        if (M <= g.minTh) continue;
-        const int nb =
-            max(max(max(sc[-FP - 1], sc[-FP]), max(sc[-FP + 1], sc[-1])), max(max(sc[1], sc[FP - 1]), max(sc[FP], sc[FP + 1])));
-        if (M > nb) {
-          const uint32_t ent = (uint32_t)X | ((uint32_t)y << 8) | ((uint32_t)M << 16);
-          if (h2 == 0) found = ent;
-          else found2 = ent;
-        }
-      }
+    for (int h2 = 0; h2 < 2; h2++) {
+      const int X = xFirst + 2 * pr + h2;
+      if (X < xLo || X >= xHi) continue;
+      const uint8_t* sc = &score[y * FP + X];
+      const int M = sc[0];
+      if (M <= minTh) continue;
+      const int nb =
+          max(max(max(sc[-FP - 1], sc[-FP]), max(sc[-FP + 1], sc[-1])), max(max(sc[1], sc[FP - 1]), max(sc[FP], sc[FP + 1])));
+      if (M > nb) ent = (uint32_t)X | ((uint32_t)y << 8) | ((uint32_t)M << 16);
     }
-    // warp-aggregated append of the survivors (two adjacent pixels can never both survive a strict 3x3 NMS)
-    const uint32_t ent = found ? found : found2;
+    return ent;
+  };
+  auto append = [&](uint32_t ent) {  // warp-aggregated append of the survivors (all lanes call)
     const unsigned sm = __ballot_sync(0xffffffffu, ent != 0u);
     if (sm) {
-      const unsigned hm = __ballot_sync(0xffffffffu, ent != 0u && (int)(ent >> 16) > g.iniTh);
+      const unsigned hm = __ballot_sync(0xffffffffu, ent != 0u && (int)(ent >> 16) > iniTh);
       int base = 0;
       if (lane == 0) {
         base = atomicAdd(&sN, __popc(sm));
@@ -274,8 +294,27 @@ __global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t
       base = __shfl_sync(0xffffffffu, base, 0);
       if (ent) {
         const int slot = base + __popc(sm & ((1u << lane) - 1u));
-        if (slot < 1024) list[slot] = ent;
+        if (slot < 1024) surv[slot] = ent;
       }
+    }
+  };
+  if (sPass <= 1024) {
+    const int nPass = sPass;
+    for (int k0 = 0; k0 < nPass; k0 += 128) {
+      const int k = k0 + tid;
+      uint32_t ent = 0;
+      if (k < nPass) {
+        const uint32_t e = list[k];
+        ent = nms_pair((int)(e & 0xff), (int)(e >> 8));
+      }
+      append(ent);
+    }
+  } else {  // pass list overflowed (very large cells only): dense NMS over every pixel pair
+    for (int y0 = 0; y0 < ih; y0 += rowsPerPass) {
+      const int y = y0 + myRow + 3;
+      uint32_t ent = 0;
+      if (y < rh - 3 && myPair < npair) ent = nms_pair(myPair, y);
+      append(ent);
     }
   }
   __syncthreads();
@@ -290,9 +329,9 @@ __global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t
   __syncthreads();
   const size_t cbase = (size_t)b * g.totalCandCap + L.candOff;
   for (int k = tid; k < nList; k += 128) {
-    const uint32_t e = list[k];
+    const uint32_t e = surv[k];
     const int x = (int)(e & 0xff) - a0, y = (e >> 8) & 0xff, M = e >> 16;  // back to ROI columns
-    if (useHi && M <= g.iniTh) continue;
+    if (useHi && M <= iniTh) continue;
     const int slot = sBase + atomicAdd(&sEmit, 1);
     if (slot >= L.candCap) continue;
     candXY[cbase + slot] = (uint32_t)(x + cj * L.wCell) | ((uint32_t)(y + ci * L.hCell) << 16);  // :1150-1151
@@ -869,12 +908,13 @@ __global__ void __launch_bounds__(256) k_orient_describe(ExtractGeom g, const ui
   const uint8_t* img = pyr + (size_t)b * g.pyrBytes + L.off;
   int m01 = 0, m10 = 0;
   // all 31 row loads are independent: fully unrolled so that they are in flight together (integer sums: any order)
-  const uint8_t* ctr = img + (size_t)cy * L.pitch + cx;
+  const int pitch = L.pitch;
+  const uint8_t* ctr = img + (size_t)cy * pitch + cx;
 #pragma unroll
   for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
     const int d = c_umax[v < 0 ? -v : v];
     const int u = lane - d;
-    const int val = (u <= d) ? (int)ctr[v * L.pitch + u] : 0;
+    const int val = (u <= d) ? (int)ctr[v * pitch + u] : 0;
     m10 += u * val;
     m01 += v * val;
   }
@@ -885,7 +925,7 @@ __global__ void __launch_bounds__(256) k_orient_describe(ExtractGeom g, const ui
   const float factorPI = (float)(3.14159265358979323846 / 180.f);
   float a, bsn;
   dev_sincosf(__fmul_rn(angle, factorPI), &bsn, &a);  // a = cos, b = sin (:181)
-  const uint8_t* bl = blur + (size_t)b * g.pyrBytes + L.off + (size_t)cy * L.pitch + cx;
+  const uint8_t* bl = blur + (size_t)b * g.pyrBytes + L.off + (size_t)cy * pitch + cx;
   uint32_t val = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -896,8 +936,8 @@ __global__ void __launch_bounds__(256) k_orient_describe(ExtractGeom g, const ui
     const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bsn)));
     const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bsn), __fmul_rn(y1, a)));
     const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, bsn)));
-    const int t0 = bl[r0 * L.pitch + c0];
-    const int t1 = bl[r1 * L.pitch + c1];
+    const int t0 = bl[r0 * pitch + c0];
+    const int t1 = bl[r1 * pitch + c1];
     val |= (uint32_t)(t0 < t1) << k;
   }
   // gather the 32 bytes into 8 words on lanes 0..7, then one 256-bit store from lane 0
