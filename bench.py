@@ -31,6 +31,9 @@ W_IMG, H_IMG, NFEAT = 1241, 376, 2000
 # algorithmic bytes per 1241x376 image
 B_STAGE_IMAGE = 9359539          # all extractor stages
 B_FAST_IMAGE = 1444097           # FAST stage: every pyramid pixel read once (sum of the 8 level sizes)
+# dram__bytes_read.sum + dram__bytes_write.sum of one 320-image k_fast_cells launch (ncu --set full,
+# profiles/r1_ncu_full_k_fast_cells_v15.csv: 408.31 MB + 46.83 MB), per image
+TRAFFIC_FAST_IMAGE = (408313600 + 46831616) / 320.0
 BA_EVERY = 5
 
 
@@ -287,7 +290,9 @@ def run_b200(args, rank, local_rank, world):
         "clocks": clocks,
         "roofline": {"kernel": "k_fast_cells (per-cell FAST-9/16 score + NMS + dual threshold)", "bound": "hbm",
                      "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": None, "peak_source": peak_src, "launch_ms": fast_ms,
+                     "traffic": TRAFFIC_FAST_IMAGE * images_per_launch,
+                     "traffic_source": "profiles/r1_ncu_full_k_fast_cells_v15.csv (ncu --set full, 320-image launch)",
+                     "peak_source": peak_src, "launch_ms": fast_ms,
                      "launch_ms_isolated": phase.get("extractor_stage_ms_isolated", {}).get("fast_cells"),
                      "algorithmic_bytes_per_launch": B_FAST_IMAGE * images_per_launch,
                      "extractor_all_stages": {"ms_per_launch_set": ex_ms,

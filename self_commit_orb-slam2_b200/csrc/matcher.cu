@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(256) k_bow_topk(const uint8_t* __restrict__ de
         for (int q = 0; q < 4; q++) {
           const uint4 b0 = *reinterpret_cast<const uint4*>(&sB[(j + q) * 8]);
           const uint4 b1 = *reinterpret_cast<const uint4*>(&sB[(j + q) * 8 + 4]);
-          const int d = __popc(da.w[0] ^ b0.x) + __popc(da.w[1] ^ b0.y) + __popc(da.w[2] ^ b0.z) + __popc(da.w[3] ^ b0.w) +
-                        __popc(da.w[4] ^ b1.x) + __popc(da.w[5] ^ b1.y) + __popc(da.w[6] ^ b1.z) + __popc(da.w[7] ^ b1.w);
+          const int d = hamming256_words(da.w[0] ^ b0.x, da.w[1] ^ b0.y, da.w[2] ^ b0.z, da.w[3] ^ b0.w, da.w[4] ^ b1.x,
+                                         da.w[5] ^ b1.y, da.w[6] ^ b1.z, da.w[7] ^ b1.w);
           const bool ok = (nds[q] == na) && ((vv >> (8 * q)) & 0xffu) && (j + q < tn);
           cnt += ok ? 1 : 0;
           const uint32_t key = ok ? (((uint32_t)d << 16) | (uint32_t)(j0 + j + q)) : EMPTY;
