@@ -687,6 +687,7 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -783,7 +784,20 @@ __device__ __forceinline__ void schur_block_pairs(const int4* prs, int qBeg, int
     cp_async_commit();
     int4 r2 = make_int4(0, 0, 0, 0);
     bool v2 = false;
-    if (it + 2 < nIt) loadRec(it + 2, r2, v2);
+    if (it + 2 < nIt) {
+      loadRec(it + 2, r2, v2);
+      // 32 windows' records (~10 MB each) do not stay in L2: pull the lines of step it+2 into L2 now so that its
+      // cp.async gathers (issued one step later) see L2 latency instead of DRAM latency
+      if (v2) {
+        prefetch_l2(Wb + (size_t)r2.x * 9);
+        prefetch_l2(Wb + (size_t)r2.x * 9 + 8);
+        if (!DIAG) {
+          prefetch_l2(Wb + (size_t)r2.y * 9);
+          prefetch_l2(Wb + (size_t)r2.y * 9 + 8);
+        }
+        prefetch_l2(Db + (size_t)r2.z * 5);
+      }
+    }
     cp_async_wait<1>();
     __syncwarp();
     if (v0) schur_accumulate<DIAG>(cur, cur + 32 * 9, cur + 32 * 18, lane, acc, tail);
