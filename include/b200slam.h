@@ -151,6 +151,27 @@ int b2s_search_by_projection_last(b2s_matcher* h, const b2s_proj_query* q, int n
                                   const uint8_t* occupied, const uint8_t* desc, int nf, const b2s_frame_geom* g, float th,
                                   int mode, int th_high, int check_ori, int32_t* match_cur, int* nmatches);
 
+/* SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, float th) (src/ORBmatcher.cc:70-175), the local-map
+ * matcher of Tracking::SearchLocalPoints; queries are the map points after Frame::isInFrustum (src/Frame.cc:608-735). */
+typedef struct {
+  float u, v, ur;    /* mTrackProjX, mTrackProjY, mTrackProjXR */
+  float view_cos;    /* mTrackViewCos (RadiusByViewingCos, :178-185) */
+  int32_t level;     /* mnTrackScaleLevel */
+  uint8_t in_view;   /* mbTrackInView && !isBad() (:83-87) */
+  uint8_t has_obs;   /* pMP->Observations()>0 */
+  uint8_t pad[2];
+  uint8_t desc[32];  /* pMP->GetDescriptor() */
+} b2s_map_query;
+
+/* Levels [level-1, level], radius RadiusByViewingCos(view_cos) (x th when th != 1) x scale[level], stereo gate on `ur`,
+ * best <= th_high (TH_HIGH), ratio test `best > nnratio*second` only when both candidates share the pyramid level.
+ * occupied[j] = the feature already holds a MapPoint with Observations()>0 (:123-125; may be NULL).
+ * match_cur[j] = query index or -1 (last writer wins); *nmatches as the reference counts them. HOST buffers. */
+int b2s_search_by_projection_map(b2s_matcher* h, const b2s_map_query* q, int nq, const float* kpx, const float* kpy,
+                                 const int32_t* octave, const float* uright, const uint8_t* occupied, const uint8_t* desc,
+                                 int nf, const b2s_frame_geom* g, float th, int th_high, float nnratio, int32_t* match_cur,
+                                 int* nmatches);
+
 /* ------------------------------------------------------------------ LocalBA */
 typedef struct {
   int32_t kf;       /* index into Tcw[] */

@@ -245,3 +245,55 @@ extern "C" int orc_search_by_projection_last(const orc_proj_query* q, int nq, co
   delete grid;
   return nmatches;
 }
+
+// SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th) — src/ORBmatcher.cc:70-175.
+extern "C" int orc_search_by_projection_map(const orc_map_query* q, int nq, const float* kpx, const float* kpy,
+                                            const int32_t* octave, const float* uright, const uint8_t* occupied_in,
+                                            const uint8_t* desc, int nf, const orc_frame_geom* g, float th, int th_high,
+                                            float nnratio, int32_t* match_cur) {
+  Grid* grid = new Grid();
+  grid->build(kpx, kpy, nf, g);
+  std::vector<uint8_t> occupied(nf, 0);
+  if (occupied_in) std::copy(occupied_in, occupied_in + nf, occupied.begin());
+  for (int j = 0; j < nf; j++) match_cur[j] = -1;
+  int nmatches = 0;
+  const bool bFactor = th != 1.0;  // :76 (float compared with a double literal)
+  std::vector<int> cand;
+  for (int i = 0; i < nq; i++) {
+    if (!q[i].in_view) continue;  // :83-87
+    const int nPredictedLevel = q[i].level;
+    float r = (q[i].view_cos > 0.998) ? 2.5f : 4.0f;  // RadiusByViewingCos :178-185 (float vs double literal)
+    if (bFactor) r *= th;
+    const float rwin = r * g->scale_factors[nPredictedLevel];
+    grid->in_area(q[i].u, q[i].v, rwin, nPredictedLevel - 1, nPredictedLevel, kpx, kpy, octave, cand);  // :99-103
+    if (cand.empty()) continue;
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (size_t c = 0; c < cand.size(); c++) {
+      const int idx = cand[c];
+      if (occupied[idx]) continue;  // :123-125
+      if (uright[idx] > 0) {        // :128-139
+        const float er = std::fabs(q[i].ur - uright[idx]);
+        if (er > r * g->scale_factors[nPredictedLevel]) continue;
+      }
+      const int dist = orc_descriptor_distance(q[i].desc, desc + (size_t)idx * 32);
+      if (dist < bestDist) {  // :147-160
+        bestDist2 = bestDist;
+        bestDist = dist;
+        bestLevel2 = bestLevel;
+        bestLevel = octave[idx];
+        bestIdx = idx;
+      } else if (dist < bestDist2) {
+        bestLevel2 = octave[idx];
+        bestDist2 = dist;
+      }
+    }
+    if (bestDist <= th_high) {  // :164-171
+      if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+      match_cur[bestIdx] = i;
+      occupied[bestIdx] = q[i].has_obs ? 1 : 0;
+      nmatches++;
+    }
+  }
+  delete grid;
+  return nmatches;
+}

@@ -94,6 +94,25 @@ int orc_search_by_projection_last(const orc_proj_query* q, int nq, const float* 
                                   const uint8_t* occupied, const uint8_t* desc, int nf, const orc_frame_geom* g,
                                   float th, int mode, int th_high, int check_ori, int32_t* match_cur);
 
+/* SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, float th) — src/ORBmatcher.cc:70-175: the local-map
+ * matcher of Tracking::SearchLocalPoints.  Queries are the local map points after Frame::isInFrustum
+ * (src/Frame.cc:608-735) filled mTrackProjX/Y/XR, mnTrackScaleLevel, mTrackViewCos. */
+typedef struct {
+  float u, v, ur;      /* mTrackProjX, mTrackProjY, mTrackProjXR */
+  float view_cos;      /* mTrackViewCos -> RadiusByViewingCos (:178-185) */
+  int32_t level;       /* mnTrackScaleLevel (predicted level) */
+  uint8_t in_view;     /* mbTrackInView && !isBad()  (:83-87) */
+  uint8_t has_obs;     /* pMP->Observations()>0: the feature it is assigned to becomes occupied (:123-125) */
+  uint8_t pad[2];
+  uint8_t desc[32];    /* pMP->GetDescriptor() */
+} orc_map_query;
+
+/* match_cur[j] = query index or -1 (last writer wins, :168). Returns nmatches as the reference counts them. */
+int orc_search_by_projection_map(const orc_map_query* q, int nq, const float* kpx, const float* kpy,
+                                 const int32_t* octave, const float* uright, const uint8_t* occupied,
+                                 const uint8_t* desc, int nf, const orc_frame_geom* g, float th, int th_high,
+                                 float nnratio, int32_t* match_cur);
+
 /* ---------------- LocalBA (src/Optimizer.cc:629-997 + vendored g2o) ---------------- */
 typedef struct {
   int32_t kf;        /* index into poses[] */

@@ -21,6 +21,8 @@ OK, ERR_NO_DEVICE, ERR_BAD_ARG, ERR_CUDA, ERR_CAPACITY, ERR_ABORTED = range(6)
 
 keypoint_dtype = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                            ("octave", "<i4"), ("class_id", "<i4")])
+map_query_dtype = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("view_cos", "<f4"), ("level", "<i4"),
+                            ("in_view", "u1"), ("has_obs", "u1"), ("pad", "u1", 2), ("desc", "u1", 32)])
 proj_query_dtype = np.dtype([("u", "<f4"), ("v", "<f4"), ("invz", "<f4"), ("angle", "<f4"), ("octave", "<i4"),
                              ("has_obs", "<i4"), ("desc", "u1", 32)])
 ba_edge_dtype = np.dtype([("kf", "<i4"), ("mp", "<i4"), ("obs", "<f4", 3), ("inv_sigma2", "<f4")])
@@ -100,6 +102,8 @@ def lib():
             L.b2s_search_by_projection_last.argtypes = [_vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                                         ctypes.c_int, _vp, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                                         ctypes.c_int, _vp, _vp]
+            L.b2s_search_by_projection_map.argtypes = [_vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,
+                                                       _vp, ctypes.c_float, ctypes.c_int, ctypes.c_float, _vp, _vp]
         if hasattr(L, "b2s_ba_create"):
             L.b2s_ba_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
             L.b2s_ba_destroy.argtypes = [_vp]
@@ -283,6 +287,19 @@ class ORBmatcher:
                                                    _p(angle), _p(uright), _p(occupied), _p(desc), nf, ctypes.byref(g),
                                                    float(th), mode, th_high, int(self.mbCheckOrientation), _p(match),
                                                    ctypes.byref(nm)))
+        return nm.value, match
+
+
+    def SearchByProjectionMap(self, queries, kpx, kpy, octave, uright, occupied, desc, geom, th=1.0, th_high=TH_HIGH):
+        """SearchByProjection(Frame&, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:70-175); queries: map_query_dtype."""
+        nf = len(kpx)
+        sf = np.ascontiguousarray(geom["scale_factors"], np.float32)
+        g = _FrameGeom(geom["mnMinX"], geom["mnMinY"], geom["mnMaxX"], geom["mnMaxY"], geom["bf"], sf.ctypes.data, len(sf))
+        match = np.full(nf, -1, np.int32)
+        nm = ctypes.c_int(0)
+        _check(lib().b2s_search_by_projection_map(self._h, _p(queries), len(queries), _p(kpx), _p(kpy), _p(octave),
+                                                  _p(uright), _p(occupied), _p(desc), nf, ctypes.byref(g), float(th),
+                                                  th_high, float(self.mfNNratio), _p(match), ctypes.byref(nm)))
         return nm.value, match
 
 

@@ -723,27 +723,49 @@ __global__ void __launch_bounds__(128) k_blur(ExtractGeom g, const uint8_t* __re
   const uint8_t* src = pyr + (size_t)b * g.pyrBytes + L.off;
   uint8_t* dst = blur + (size_t)b * g.pyrBytes + L.off;
   const int Wd = L.w, Hd = L.h;
-  const bool laneIn = x0 < L.pitch;                    // this lane's own word exists in the padded row
+  const bool laneIn = x0 < L.pitch;  // this lane's own word exists in the padded row
   int hw[7][4];
   // left / right border handling without per-byte loops: reflect101 of the 12-byte window x0-4 .. x0+7
   const bool leftEdge = (x0 == 0);
   const int nValid = Wd - x0;                  // pixels of this lane's window that exist, counted from x0
   const bool rightEdge = laneIn && (nValid < 8) && (x0 < Wd);  // x0+7 >= Wd : some of bytes 4..11 are beyond the image
+  const int pitch = L.pitch;
+  const uint8_t* colBase = src + x0;
+  // lanes 0 and 31 fetch the word left / right of the warp's 128-byte span (one predicated load, no branches)
+  const bool wantExtra = (lane == 0 && x0 >= 4) || (lane == 31 && x0 + 4 < pitch);
+  const int extraOff = (lane == 0) ? -4 : 4;
 #pragma unroll 1
   for (int i0 = 0; i0 < BL_ROWS + 6; i0 += 7) {
+    // the seven row loads of the body are issued together (one exposed memory latency per seven rows)
+    uint32_t w1v[7], exv[7];
+    int syv[7];
+#pragma unroll
+    for (int u = 0; u < 7; u++) {
+      int sy = oy - 3 + i0 + u;
+      if (Hd >= 8) {  // (uniform) one reflection is enough
+        sy = sy < 0 ? -sy : sy;
+        sy = sy >= Hd ? 2 * (Hd - 1) - sy : sy;
+      } else {
+        sy = reflect101(sy, Hd);
+      }
+      sy = min(max(sy, 0), Hd - 1);  // rows of a partial last tile that are never stored
+      syv[u] = sy;
+      const uint8_t* rp = colBase + (size_t)sy * pitch;
+      w1v[u] = laneIn ? __ldg(reinterpret_cast<const uint32_t*>(rp)) : 0u;
+      exv[u] = wantExtra ? __ldg(reinterpret_cast<const uint32_t*>(rp + extraOff)) : 0u;
+    }
 #pragma unroll
     for (int u = 0; u < 7; u++) {
       const int i = i0 + u;
       if (i < BL_ROWS + 6) {  // warp-uniform
-        const int sy = reflect101(oy - 3 + i, Hd);
-        const uint8_t* row = src + (size_t)sy * L.pitch;
-        uint32_t w1 = laneIn ? *reinterpret_cast<const uint32_t*>(row + x0) : 0u;
+        uint32_t w1 = w1v[u];
         uint32_t w0 = __shfl_up_sync(0xffffffffu, w1, 1);
         uint32_t w2 = __shfl_down_sync(0xffffffffu, w1, 1);
-        if (lane == 0) w0 = (x0 >= 4) ? *reinterpret_cast<const uint32_t*>(row + x0 - 4) : 0u;
-        if (lane == 31) w2 = (x0 + 4 < L.pitch) ? *reinterpret_cast<const uint32_t*>(row + x0 + 4) : 0u;
+        if (lane == 0) w0 = exv[u];
+        if (lane == 31) w2 = exv[u];
         if (leftEdge) w0 = __byte_perm(w1, w2, 0x1234);  // pixels 4,3,2,1 (reflect101 of -4..-1)
         if (rightEdge) {                                   // few lanes per row: rebuild bytes 4..11 by reflection
+          const uint8_t* row = src + (size_t)syv[u] * pitch;
           uint32_t ww1 = 0u, ww2 = 0u;
 #pragma unroll
           for (int k = 0; k < 4; k++) {
@@ -773,7 +795,7 @@ __global__ void __launch_bounds__(128) k_blur(ExtractGeom g, const uint8_t* __re
             const uint32_t acc = 18u * (uint32_t)(q0 + q6) + 34u * (uint32_t)(q1 + q5) + 48u * (uint32_t)(q2 + q4) + 56u * (uint32_t)q3;
             outw |= ((acc + 32768u) >> 16) << (8 * j);
           }
-          if (y < Hd && x0 < Wd) *reinterpret_cast<uint32_t*>(dst + (size_t)y * L.pitch + x0) = outw;
+          if (y < Hd && x0 < Wd) *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch + x0) = outw;
         }
       }
     }

@@ -419,11 +419,73 @@ struct __align__(8) ProjQuery {  // == b2s_proj_query
   int32_t octave, has_obs;
   uint8_t desc[32];
 };
+struct __align__(8) MapQuery {  // == b2s_map_query (SearchByProjection(Frame&, vector<MapPoint*>&, th), :70-175)
+  float u, v, ur, view_cos;
+  int32_t level;
+  uint8_t in_view, has_obs, pad[2];
+  uint8_t desc[32];
+};
+
+// search window of one query: centre, radius, level range of GetFeaturesInArea and the right-image coordinate of the
+// stereo gate
+struct Win {
+  bool ok;
+  float u, v, r, ur;
+  int minL, maxL;
+};
+__device__ __forceinline__ Win make_win(const ProjQuery& Q, const ProjGeom& g) {  // :1607-1646
+  Win w;
+  w.u = Q.u; w.v = Q.v;
+  w.ok = !(Q.invz < 0) && !(Q.u < g.minX || Q.u > g.maxX) && !(Q.v < g.minY || Q.v > g.maxY);  // :1616-1626
+  const int oct = Q.octave;
+  w.r = w.ok ? __fmul_rn(g.th, g.scale[oct]) : 0.f;
+  if (g.mode == 1) { w.minL = oct; w.maxL = -1; }
+  else if (g.mode == 2) { w.minL = 0; w.maxL = oct; }
+  else { w.minL = oct - 1; w.maxL = oct + 1; }
+  w.ur = __fsub_rn(Q.u, __fmul_rn(g.bf, Q.invz));
+  return w;
+}
+__device__ __forceinline__ Win make_win(const MapQuery& Q, const ProjGeom& g) {  // :83-103
+  Win w;
+  w.u = Q.u; w.v = Q.v;
+  w.ok = Q.in_view != 0;
+  float r = ((double)Q.view_cos > 0.998) ? 2.5f : 4.0f;  // RadiusByViewingCos (:178-185)
+  if (g.th != 1.0f) r = __fmul_rn(r, g.th);              // bFactor (:76,93-94)
+  const int lv = min(max(Q.level, 0), 15);
+  w.r = __fmul_rn(r, g.scale[lv]);
+  w.minL = Q.level - 1;
+  w.maxL = Q.level;
+  w.ur = Q.ur;
+  return w;
+}
+// cell range of GetFeaturesInArea (src/Frame.cc:752-770); false = empty result
+__device__ __forceinline__ bool win_cells(const Win& w, const ProjGeom& g, int& c0x, int& c1x, int& c0y, int& c1y) {
+  c0x = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.u, g.minX), w.r), g.invW)));
+  c1x = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(w.u, g.minX), w.r), g.invW)));
+  c0y = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.v, g.minY), w.r), g.invH)));
+  c1y = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(w.v, g.minY), w.r), g.invH)));
+  return !(c0x >= GRID_COLS || c1x < 0 || c0y >= GRID_ROWS || c1y < 0);
+}
+// one candidate of the window: level gate, |dx|,|dy| < r, occupancy, stereo gate (:1648-1669 / :117-139)
+__device__ __forceinline__ bool win_take(const Win& w, int id, const float* __restrict__ kpx, const float* __restrict__ kpy,
+                                         const int32_t* __restrict__ octave, const float* __restrict__ uright) {
+  if ((w.minL > 0) || (w.maxL >= 0)) {
+    const int o = octave[id];
+    if (o < w.minL) return false;
+    if (w.maxL >= 0 && o > w.maxL) return false;
+  }
+  const float dx = __fsub_rn(kpx[id], w.u), dy = __fsub_rn(kpy[id], w.v);
+  if (!(fabsf(dx) < w.r && fabsf(dy) < w.r)) return false;
+  const float urr = uright[id];
+  if (urr > 0 && fabsf(__fsub_rn(w.ur, urr)) > w.r) return false;
+  return true;
+}
 
 // stage 1: one warp per query; candidates are enumerated in GetFeaturesInArea order (src/Frame.cc:741-850:
 // ix outer, iy inner, insertion order inside a cell) and the K best by (distance, order) are kept.
 // key = dist<<20 | ord  (ord < 2^20 = running index in enumeration order); cand index stored alongside.
-__global__ void __launch_bounds__(256) k_proj_topk(const ProjQuery* __restrict__ q, int nq, const float* __restrict__ kpx,
+template <class QT>
+__global__ void __launch_bounds__(256) k_proj_topk(const QT* __restrict__ q, int nq, const float* __restrict__ kpx,
                                                    const float* __restrict__ kpy, const int32_t* __restrict__ octave,
                                                    const float* __restrict__ uright, const uint8_t* __restrict__ occupied,
                                                    const uint8_t* __restrict__ desc, const int32_t* __restrict__ order,
@@ -437,51 +499,21 @@ __global__ void __launch_bounds__(256) k_proj_topk(const ProjQuery* __restrict__
 #pragma unroll
   for (int k = 0; k < TOPK; k++) t[k] = EMPTY;
   int cnt = 0;
-  const ProjQuery& Q = q[i];
-  const float u = Q.u, v = Q.v, invz = Q.invz;
-  bool ok = !(invz < 0) && !(u < g.minX || u > g.maxX) && !(v < g.minY || v > g.maxY);  // :1616-1626
-  int oct = Q.octave;
-  float r = 0.f;
-  int c0x = 0, c1x = -1, c0y = 0, c1y = -1, minL = 0, maxL = -1;
+  const QT& Q = q[i];
+  Win w = make_win(Q, g);
+  int c0x = 0, c1x = -1, c0y = 0, c1y = -1;
+  bool ok = w.ok;
+  if (ok) ok = win_cells(w, g, c0x, c1x, c0y, c1y);
   if (ok) {
-    r = __fmul_rn(g.th, g.scale[oct]);
-    if (g.mode == 1) { minL = oct; maxL = -1; }
-    else if (g.mode == 2) { minL = 0; maxL = oct; }
-    else { minL = oct - 1; maxL = oct + 1; }
-    c0x = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, g.minX), r), g.invW)));
-    c1x = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, g.minX), r), g.invW)));
-    c0y = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, g.minY), r), g.invH)));
-    c1y = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, g.minY), r), g.invH)));
-    if (c0x >= GRID_COLS || c1x < 0 || c0y >= GRID_ROWS || c1y < 0) ok = false;
-  }
-  if (ok) {
-    const bool checkLevels = (minL > 0) || (maxL >= 0);
     const u256 dq = ld_desc_w(Q.desc);
-    const float ur = __fsub_rn(u, __fmul_rn(g.bf, invz));
     // columns of cells ix; inside a column the cells iy=c0y..c1y are contiguous in the sorted array
     int ord = 0;
     for (int ix = c0x; ix <= c1x; ix++) {
       const int beg = cellStart[ix * GRID_ROWS + c0y], end = cellStart[ix * GRID_ROWS + c1y + 1];
       for (int p = beg + lane; p < end; p += 32) {
         const int id = order[p];
-        bool take = true;
-        if (checkLevels) {
-          const int o = octave[id];
-          if (o < minL) take = false;
-          if (maxL >= 0 && o > maxL) take = false;
-        }
-        if (take) {
-          const float dx = __fsub_rn(kpx[id], u), dy = __fsub_rn(kpy[id], v);
-          if (!(fabsf(dx) < r && fabsf(dy) < r)) take = false;
-        }
+        bool take = win_take(w, id, kpx, kpy, octave, uright);
         if (take && occupied && occupied[id]) take = false;  // initially occupied features are never candidates
-        if (take) {
-          const float urr = uright[id];
-          if (urr > 0) {
-            const float er = fabsf(__fsub_rn(ur, urr));
-            if (er > r) take = false;
-          }
-        }
         if (take) {
           const int d = hamming256(dq, ld_desc(desc, id));
           cnt++;
@@ -517,6 +549,65 @@ __global__ void __launch_bounds__(256) k_proj_topk(const ProjQuery* __restrict__
     topkIdx[(size_t)i * TOPK + lane] = id;
   }
   if (lane == 0) candCnt[i] = ok ? cnt : -1;
+}
+
+// Exact rescan of one query's window in enumeration order against the CURRENT occupancy: the two smallest
+// (distance, order) keys over the warp (key2/id2 = EMPTY/-1 when there is no second candidate).
+template <class QT>
+__device__ __forceinline__ void win_rescan_top2(const QT& Q, const ProjGeom& g, int lane, const float* __restrict__ kpx,
+                                                const float* __restrict__ kpy, const int32_t* __restrict__ octave,
+                                                const float* __restrict__ uright, const uint8_t* __restrict__ occupied,
+                                                const uint8_t* __restrict__ taken, const uint8_t* __restrict__ desc,
+                                                const int32_t* __restrict__ order, const int32_t* __restrict__ cellStart,
+                                                uint32_t& key1, int& id1, uint32_t& key2, int& id2) {
+  const Win w = make_win(Q, g);
+  int c0x, c1x, c0y, c1y;
+  win_cells(w, g, c0x, c1x, c0y, c1y);
+  const u256 dq = ld_desc_w(Q.desc);
+  uint32_t k1 = EMPTY, k2 = EMPTY;
+  int i1 = -1, i2 = -1;
+  int ord = 0;
+  for (int ix = c0x; ix <= c1x; ix++) {
+    const int beg = cellStart[ix * GRID_ROWS + c0y], end = cellStart[ix * GRID_ROWS + c1y + 1];
+    for (int p = beg + lane; p < end; p += 32) {
+      const int fid = order[p];
+      bool take = win_take(w, fid, kpx, kpy, octave, uright);
+      if (take && ((occupied && occupied[fid]) || taken[fid])) take = false;
+      if (take) {
+        const uint32_t key = ((uint32_t)hamming256(dq, ld_desc(desc, fid)) << 20) | (uint32_t)(ord + (p - beg));
+        if (key < k1) {
+          k2 = k1; i2 = i1;
+          k1 = key; i1 = fid;
+        } else if (key < k2) {
+          k2 = key; i2 = fid;
+        }
+      }
+    }
+    ord += end - beg;
+  }
+  // warp top-2 of the per-lane pairs (keys are unique: the order part differs)
+  uint32_t m1 = k1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m1 = min(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+  key1 = m1;
+  id1 = -1;
+  key2 = EMPTY;
+  id2 = -1;
+  if (m1 == EMPTY) return;
+  const unsigned who = __ballot_sync(0xffffffffu, k1 == m1);
+  const int wl = __ffs(who) - 1;
+  id1 = __shfl_sync(0xffffffffu, i1, wl);
+  // second: the winner lane contributes its own runner-up, every other lane its best
+  const uint32_t cand2 = (lane == wl) ? k2 : k1;
+  const int cid2 = (lane == wl) ? i2 : i1;
+  uint32_t m2 = cand2;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m2 = min(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+  if (m2 != EMPTY) {
+    const unsigned who2 = __ballot_sync(0xffffffffu, cand2 == m2);
+    key2 = m2;
+    id2 = __shfl_sync(0xffffffffu, cid2, __ffs(who2) - 1);
+  }
 }
 
 // stage 2: the greedy loop of :1600-1706 — one warp walks the queries in order; `taken[j]` = feature j now holds a
@@ -624,6 +715,61 @@ __global__ void __launch_bounds__(32) k_proj_resolve(const ProjQuery* __restrict
   __syncwarp();
   if (lane == 0) accepted[0] = nAccepted;
   if (lane < HISTO) histOut[lane] = hist[lane];
+}
+
+// SearchByProjection(Frame&, vector<MapPoint*>&, th) greedy loop (:78-172): one warp walks the map points in order.
+// Best and second best among the features that are not occupied NOW (:123-125) are the first two available entries of
+// the query's K-list (sorted by distance, then enumeration order — exactly the order in which the reference's
+// best/second bookkeeping of :147-160 ranks them); if the list cannot supply two, the window is rescanned exactly.
+// Ratio test only when both are on the same pyramid level (:164-166); no rotation check in this matcher.
+__global__ void __launch_bounds__(32) k_map_resolve(const MapQuery* __restrict__ q, int nq, const float* __restrict__ kpx,
+                                                    const float* __restrict__ kpy, const int32_t* __restrict__ octave,
+                                                    const float* __restrict__ uright, const uint8_t* __restrict__ occupied,
+                                                    const uint8_t* __restrict__ desc, const int32_t* __restrict__ order,
+                                                    const int32_t* __restrict__ cellStart, ProjGeom g, float nnratio,
+                                                    const uint32_t* __restrict__ topk, const int32_t* __restrict__ topkIdx,
+                                                    const int32_t* __restrict__ candCnt, uint8_t* __restrict__ taken,
+                                                    int32_t* __restrict__ matchCur, int32_t* __restrict__ nmatches) {
+  const int lane = threadIdx.x;
+  int nAccepted = 0;
+  for (int i = 0; i < nq; i++) {
+    const int cc = candCnt[i];
+    if (cc <= 0) continue;
+    const uint32_t e = (lane < TOPK) ? topk[(size_t)i * TOPK + lane] : EMPTY;
+    const int id = (lane < TOPK) ? topkIdx[(size_t)i * TOPK + lane] : -1;
+    const bool avail = (e != EMPTY) && !taken[id];
+    unsigned am = __ballot_sync(0xffffffffu, avail);
+    uint32_t key1 = EMPTY, key2 = EMPTY;
+    int id1 = -1, id2 = -1;
+    if (__popc(am) >= 2 || (am != 0u && cc <= TOPK)) {
+      const int l1 = __ffs(am) - 1;
+      key1 = __shfl_sync(0xffffffffu, e, l1);
+      id1 = __shfl_sync(0xffffffffu, id, l1);
+      am &= am - 1;
+      if (am) {
+        const int l2 = __ffs(am) - 1;
+        key2 = __shfl_sync(0xffffffffu, e, l2);
+        id2 = __shfl_sync(0xffffffffu, id, l2);
+      }
+    } else if (cc > TOPK) {
+      win_rescan_top2(q[i], g, lane, kpx, kpy, octave, uright, occupied, taken, desc, order, cellStart, key1, id1, key2,
+                      id2);
+    }
+    if (id1 < 0) continue;
+    const int bestDist = (int)(key1 >> 20);
+    if (bestDist > g.thHigh) continue;  // :164
+    if (id2 >= 0) {
+      const int bestDist2 = (int)(key2 >> 20);
+      if (octave[id1] == octave[id2] && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;  // :166
+    }
+    if (lane == 0) {
+      matchCur[id1] = i;                       // :168 (last writer wins)
+      taken[id1] = q[i].has_obs ? 1 : 0;       // the feature now holds a MapPoint; occupied iff Observations()>0
+    }
+    nAccepted++;
+    __syncwarp();
+  }
+  if (lane == 0) nmatches[0] = nAccepted;
 }
 
 // rotation culling for SearchByProjection: the histogram holds every accepted push (a feature may have been pushed more
@@ -897,7 +1043,7 @@ extern "C" int b2s_search_by_projection_last(b2s_matcher* h, const b2s_proj_quer
   k_proj_cell_key<<<div_up(nf, 256), 256, 0, st>>>(h->dKpx, h->dKpy, nf, pg, h->dCellKey);
   k_rank_by_key<<<dim3(div_up(nf, 128), 1), 128, 0, st>>>(h->dCellKey, h->dNB, nf, h->dOrder);
   k_proj_cell_start<<<div_up(nf + 1, 256), 256, 0, st>>>(h->dCellKey, h->dOrder, nf, h->dCellStart);
-  k_proj_topk<<<div_up(nq, 8), 256, 0, st>>>(h->dQueries, nq, h->dKpx, h->dKpy, h->dOct, h->dURight,
+  k_proj_topk<ProjQuery><<<div_up(nq, 8), 256, 0, st>>>(h->dQueries, nq, h->dKpx, h->dKpy, h->dOct, h->dURight,
                                              occupied ? h->dOcc : nullptr, h->dDescB, h->dOrder, h->dCellStart, pg,
                                              h->dTopk, h->dTopkIdx, h->dCandCnt);
   k_proj_resolve<<<1, 32, 0, st>>>(h->dQueries, nq, h->dKpx, h->dKpy, h->dOct, h->dAngB, h->dURight,
@@ -905,6 +1051,62 @@ extern "C" int b2s_search_by_projection_last(b2s_matcher* h, const b2s_proj_quer
                                    h->dTopkIdx, h->dCandCnt, h->dTaken, h->dMatch, h->dPush, h->dExtra, h->dHist);
   k_proj_cull<<<1, 256, 0, st>>>(check_ori, h->dHist, h->dExtra, h->dMatch, h->dPush, h->dNMatches);
   h->launches += 7;
+  B2S_CUDA(cudaGetLastError());
+  B2S_CUDA(cudaMemcpyAsync(match_cur, h->dMatch, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  return B2S_OK;
+}
+
+extern "C" int b2s_search_by_projection_map(b2s_matcher* h, const b2s_map_query* q, int nq, const float* kpx,
+                                            const float* kpy, const int32_t* octave, const float* uright,
+                                            const uint8_t* occupied, const uint8_t* desc, int nf, const b2s_frame_geom* g,
+                                            float th, int th_high, float nnratio, int32_t* match_cur, int* nmatches) {
+  static_assert(sizeof(MapQuery) == sizeof(b2s_map_query), "query layout");
+  static_assert(sizeof(MapQuery) == sizeof(ProjQuery), "the query staging buffer is shared");
+  if (!h || nq < 0 || nf < 0 || nq > h->maxF || nf > h->maxF || !match_cur || !nmatches || !g || !g->scale_factors ||
+      g->nlevels < 1 || g->nlevels > 16) {
+    set_error("b2s_search_by_projection_map: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  *nmatches = 0;
+  for (int j = 0; j < nf; j++) match_cur[j] = -1;
+  if (nq == 0 || nf == 0) return B2S_OK;
+  if (!q || !kpx || !kpy || !octave || !uright || !desc) return B2S_ERR_BAD_ARG;
+  for (int i = 0; i < nq; i++)
+    if (q[i].in_view && (q[i].level < 0 || q[i].level >= g->nlevels)) {
+      set_error("b2s_search_by_projection_map: query %d has a predicted level outside the scale table", i);
+      return B2S_ERR_BAD_ARG;
+    }
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  ProjGeom pg;
+  pg.minX = g->mnMinX; pg.minY = g->mnMinY; pg.maxX = g->mnMaxX; pg.maxY = g->mnMaxY;
+  pg.invW = (float)GRID_COLS / (g->mnMaxX - g->mnMinX);  // src/Frame.cc:213-214
+  pg.invH = (float)GRID_ROWS / (g->mnMaxY - g->mnMinY);
+  pg.bf = g->bf; pg.th = th; pg.mode = 0; pg.thHigh = th_high; pg.checkOri = 0; pg.nlevels = g->nlevels;
+  for (int i = 0; i < 16; i++) pg.scale[i] = i < g->nlevels ? g->scale_factors[i] : 0.f;
+  MapQuery* dQ = reinterpret_cast<MapQuery*>(h->dQueries);
+  B2S_CUDA(cudaMemcpyAsync(dQ, q, (size_t)nq * sizeof(MapQuery), cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dKpx, kpx, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dKpy, kpy, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dOct, octave, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dURight, uright, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  if (occupied) B2S_CUDA(cudaMemcpyAsync(h->dOcc, occupied, (size_t)nf, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dDescB, desc, (size_t)nf * 32, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNB, &nf, 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemsetAsync(h->dTaken, 0, (size_t)nf, st));
+  k_fill_i32<<<div_up(nf, 256), 256, 0, st>>>(h->dMatch, -1, (size_t)nf);
+  k_proj_cell_key<<<div_up(nf, 256), 256, 0, st>>>(h->dKpx, h->dKpy, nf, pg, h->dCellKey);
+  k_rank_by_key<<<dim3(div_up(nf, 128), 1), 128, 0, st>>>(h->dCellKey, h->dNB, nf, h->dOrder);
+  k_proj_cell_start<<<div_up(nf + 1, 256), 256, 0, st>>>(h->dCellKey, h->dOrder, nf, h->dCellStart);
+  k_proj_topk<MapQuery><<<div_up(nq, 8), 256, 0, st>>>(dQ, nq, h->dKpx, h->dKpy, h->dOct, h->dURight,
+                                                       occupied ? h->dOcc : nullptr, h->dDescB, h->dOrder, h->dCellStart,
+                                                       pg, h->dTopk, h->dTopkIdx, h->dCandCnt);
+  k_map_resolve<<<1, 32, 0, st>>>(dQ, nq, h->dKpx, h->dKpy, h->dOct, h->dURight, occupied ? h->dOcc : nullptr, h->dDescB,
+                                  h->dOrder, h->dCellStart, pg, nnratio, h->dTopk, h->dTopkIdx, h->dCandCnt, h->dTaken,
+                                  h->dMatch, h->dNMatches);
+  h->launches += 6;
   B2S_CUDA(cudaGetLastError());
   B2S_CUDA(cudaMemcpyAsync(match_cur, h->dMatch, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));

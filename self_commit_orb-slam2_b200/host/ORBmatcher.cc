@@ -72,4 +72,17 @@ int ORBmatcher::SearchByProjection(const std::vector<b2s_proj_query>& q, const f
   return nm;
 }
 
+int ORBmatcher::SearchByProjection(const std::vector<b2s_map_query>& mp, const float* kpx, const float* kpy,
+                                   const int32_t* octave, const float* uright, const uint8_t* occupied,
+                                   const uint8_t* descriptors, int nF, const b2s_frame_geom& geom, float th,
+                                   std::vector<int32_t>& matchF) {
+  Ensure((int)mp.size() > nF ? (int)mp.size() : nF);
+  matchF.assign(nF, -1);
+  int nm = 0;
+  int rc = b2s_search_by_projection_map(mpHandle, mp.data(), (int)mp.size(), kpx, kpy, octave, uright, occupied,
+                                        descriptors, nF, &geom, th, TH_HIGH, mfNNratio, matchF.data(), &nm);
+  if (rc != B2S_OK) fail("ORBmatcher::SearchByProjection(map points)", rc);
+  return nm;
+}
+
 }  // namespace ORB_SLAM2

@@ -39,6 +39,11 @@ class ORBmatcher {
                          const int32_t* octave, const float* angle, const float* uright, const uint8_t* occupied,
                          const uint8_t* descriptors, int nFeatures, const b2s_frame_geom& geom, float th, int mode,
                          std::vector<int32_t>& matchCur);
+  // SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, float th) (src/ORBmatcher.cc:70) after
+  // Frame::isInFrustum filled the track fields of the local map points
+  int SearchByProjection(const std::vector<b2s_map_query>& mapPoints, const float* kpx, const float* kpy,
+                         const int32_t* octave, const float* uright, const uint8_t* occupied, const uint8_t* descriptors,
+                         int nFeatures, const b2s_frame_geom& geom, float th, std::vector<int32_t>& matchF);
 
  protected:
   void Ensure(int n);

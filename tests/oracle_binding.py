@@ -66,6 +66,8 @@ class Oracle:
                                         ctypes.c_float, ctypes.c_int, ctypes.c_int, vp]
         L.orc_search_by_projection_last.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp,
                                                     ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+        L.orc_search_by_projection_map.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp,
+                                                   ctypes.c_float, ctypes.c_int, ctypes.c_float, vp]
         L.orc_local_ba.argtypes = [vp, vp, vp]
         L.orc_sincosf_batch.argtypes = [vp, ctypes.c_long, vp, vp, ctypes.c_int]
         L.orc_extract_many.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
@@ -135,6 +137,15 @@ class Oracle:
         n = self.L.orc_search_by_projection_last(P(queries), len(queries), P(kpx), P(kpy), P(octave), P(angle), P(uright),
                                                  P(occupied), P(desc), len(kpx), ctypes.byref(g), th, mode, th_high,
                                                  int(check_ori), P(m))
+        return n, m
+
+    def search_by_projection_map(self, queries, kpx, kpy, octave, uright, occupied, desc, geom, th=1.0, th_high=100,
+                                 nnratio=0.8):
+        sf = np.ascontiguousarray(geom["scale_factors"], np.float32)
+        g = FrameGeom(geom["mnMinX"], geom["mnMinY"], geom["mnMaxX"], geom["mnMaxY"], geom["bf"], sf.ctypes.data, len(sf))
+        m = np.full(len(kpx), -1, np.int32)
+        n = self.L.orc_search_by_projection_map(P(queries), len(queries), P(kpx), P(kpy), P(octave), P(uright),
+                                                P(occupied), P(desc), len(kpx), ctypes.byref(g), th, th_high, nnratio, P(m))
         return n, m
 
     # ---- LocalBA ----

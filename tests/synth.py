@@ -203,3 +203,25 @@ def synth_projection(nf=2000, nq=1800, seed=7, w=1241, h=376, cluster=False, th=
                 scale_factors=scale)
     return dict(q=q, kpx=kpx, kpy=kpy, octave=octave, angle=angle, uright=uright, occupied=occupied, desc=desc,
                 geom=geom, th=np.float32(th))
+
+
+def synth_projection_map(nf=2000, nq=2500, seed=9, w=1241, h=376, cluster=False):
+    """Current-frame features + local map points after isInFrustum (SURVEY M4 / src/ORBmatcher.cc:70-175)."""
+    d = synth_projection(nf=nf, nq=nq, seed=seed, w=w, h=h, cluster=cluster)
+    rng = np.random.RandomState(seed + 77)
+    q0 = d["q"]
+    qdt = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("view_cos", "<f4"), ("level", "<i4"), ("in_view", "u1"),
+                    ("has_obs", "u1"), ("pad", "u1", 2), ("desc", "u1", 32)])
+    q = np.zeros(nq, qdt)
+    q["u"], q["v"], q["desc"] = q0["u"], q0["v"], q0["desc"]
+    q["u"][:5] = np.float32(-30.0)  # far outside: GetFeaturesInArea returns nothing
+    invz = np.where(q0["invz"] > 0, q0["invz"], np.float32(0.05)).astype(np.float32)
+    q["ur"] = (q0["u"] - d["geom"]["bf"] * invz + rng.randint(-30, 31, size=nq).astype(np.float32) / np.float32(10.0)).astype(np.float32)
+    q["view_cos"] = np.where(rng.randint(0, 100, size=nq) < 50, np.float32(0.9995), np.float32(0.99)).astype(np.float32)
+    q["view_cos"][::17] = np.float32(0.998)  # exactly at the (double) threshold of RadiusByViewingCos
+    q["level"] = q0["octave"]
+    q["in_view"] = (rng.randint(0, 100, size=nq) < 90).astype(np.uint8)
+    q["has_obs"] = (rng.randint(0, 100, size=nq) < 85).astype(np.uint8)
+    d = dict(d)
+    d["q"] = q
+    return d

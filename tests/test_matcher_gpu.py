@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from synth import synth_descriptors, synth_projection
+from synth import synth_descriptors, synth_projection, synth_projection_map
 
 pytestmark = pytest.mark.gpu
 
@@ -103,3 +103,39 @@ def test_against_committed_golden(pkg):
     n, match = m9.SearchByProjection(d["q"], d["kpx"], d["kpy"], d["octave"], d["angle"], d["uright"], d["occupied"],
                                      d["desc"], d["geom"], d["th"], mode=0)
     assert n == int(g["n"]) and np.array_equal(match, g["match"])
+
+
+@pytest.mark.parametrize("th", [1.0, 3.0])
+@pytest.mark.parametrize("cluster", [False, True])
+@pytest.mark.parametrize("nnratio", [0.8, 0.6])
+def test_search_by_projection_map(pkg, oracle, th, cluster, nnratio):
+    """SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:70-175): bit-exact match array and count,
+    including the level-gated ratio test, the dynamic occupancy and K-list exhaustion (clustered descriptors)."""
+    d = synth_projection_map(seed=31 + int(th), cluster=cluster)
+    m = pkg.ORBmatcher(nnratio, True)
+    n, match = m.SearchByProjectionMap(d["q"], d["kpx"], d["kpy"], d["octave"], d["uright"], d["occupied"], d["desc"],
+                                       d["geom"], th=th)
+    on, om = oracle.search_by_projection_map(d["q"], d["kpx"], d["kpy"], d["octave"], d["uright"], d["occupied"],
+                                             d["desc"], d["geom"], th=th, nnratio=nnratio)
+    assert n == on
+    assert np.array_equal(match, om)
+    assert n > 100
+
+
+def test_search_by_projection_map_edge_cases(pkg, oracle):
+    d = synth_projection_map(seed=5)
+    m = pkg.ORBmatcher(0.8, True)
+    n, match = m.SearchByProjectionMap(d["q"][:0], d["kpx"], d["kpy"], d["octave"], d["uright"], d["occupied"], d["desc"],
+                                       d["geom"])
+    assert n == 0 and (match == -1).all()
+    q = d["q"].copy()
+    q["in_view"] = 0  # nothing in view: no match
+    n, match = m.SearchByProjectionMap(q, d["kpx"], d["kpy"], d["octave"], d["uright"], d["occupied"], d["desc"], d["geom"])
+    assert n == 0 and (match == -1).all()
+    occ = np.ones_like(d["occupied"])  # every feature already holds a map point
+    n, match = m.SearchByProjectionMap(d["q"], d["kpx"], d["kpy"], d["octave"], d["uright"], occ, d["desc"], d["geom"])
+    assert n == 0 and (match == -1).all()
+    n, match = m.SearchByProjectionMap(d["q"], d["kpx"], d["kpy"], d["octave"], d["uright"], None, d["desc"], d["geom"])
+    on, om = oracle.search_by_projection_map(d["q"], d["kpx"], d["kpy"], d["octave"], d["uright"], None, d["desc"],
+                                             d["geom"], nnratio=0.8)
+    assert n == on and np.array_equal(match, om)

@@ -15,7 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_binding  # noqa: E402
-from synth import synth_descriptors, synth_image, synth_local_ba, synth_projection  # noqa: E402
+from synth import synth_descriptors, synth_image, synth_local_ba, synth_projection, synth_projection_map  # noqa: E402
 
 out = os.path.join(ROOT, "tests", "golden")
 os.makedirs(out, exist_ok=True)
@@ -48,6 +48,11 @@ pd = synth_projection(seed=21, cluster=False, th=7.0)
 n, m = o.search_by_projection_last(pd["q"], pd["kpx"], pd["kpy"], pd["octave"], pd["angle"], pd["uright"], pd["occupied"],
                                    pd["desc"], pd["geom"], float(pd["th"]), mode=0)
 np.savez_compressed(os.path.join(out, "proj_seed21.npz"), n=n, match=m)
+# SearchByProjection (local map points)
+pm = synth_projection_map(seed=31)
+n, m = o.search_by_projection_map(pm["q"], pm["kpx"], pm["kpy"], pm["octave"], pm["uright"], pm["occupied"], pm["desc"],
+                                  pm["geom"], th=1.0, nnratio=0.8)
+np.savez_compressed(os.path.join(out, "projmap_seed31.npz"), n=n, match=m)
 # LocalBA (small window: exact float outputs; KITTI-shaped window: hashes of flags + trace)
 ba = synth_local_ba(n_kf=8, n_fixed=2, n_mp=200, obs_per_mp=4, seed=5)
 r = o.local_ba(ba)
