@@ -94,6 +94,25 @@ int b2s_extractor_debug_level(b2s_extractor* h, int b, int level, int blurred, u
 int b2s_extractor_debug_candidates(b2s_extractor* h, int b, int level, int32_t* xy /*2*cap*/, int32_t* resp, int cap,
                                    int* n);
 
+/* ------------------------------------------------------------------ stereo matching */
+/* Frame::ComputeStereoMatches (src/Frame.cc:1026-1421) for the stereo pairs of the batch this handle extracted last; the
+ * image pyramids (mvImagePyramid, the function's only other input) are still resident, so no image leaves the device.
+ * Pair p = (image first_left+p, image first_right+p) of that batch, p in [0, n_pairs).
+ * bf = Frame::mbf; mb = the baseline the reference sees when the function runs (this fork assigns mb AFTER the call,
+ * src/Frame.cc:125,186,1108, so it sees 0 and the disparity bound maxD = mbf/mb is +inf; pass the real baseline to get
+ * the upstream behaviour).  Outputs per left feature: mvuRight / mvDepth (-1 = no stereo match); n_matched[p] = matches
+ * that survive the median cull (:1395-1415).
+ *
+ * _device: d_kps/d_desc/d_counts are the device record arrays of that batch (e.g. the buffers given to
+ * b2s_extract_batch_device, `cap` records per image, cap <= 4096); d_uright/d_depth: device float [n_pairs][cap];
+ * asynchronous on `stream`.  The host variant uses the records b2s_extract_batch left on the device and writes
+ * [n_pairs][cap_out] host arrays (cap_out >= the cap of that call). */
+int b2s_stereo_match_device(b2s_extractor* h, int first_left, int first_right, int n_pairs, const b2s_keypoint* d_kps,
+                            const uint8_t* d_desc, const int32_t* d_counts, int cap, float bf, float mb, float* d_uright,
+                            float* d_depth, int32_t* d_nmatched, void* stream);
+int b2s_stereo_match(b2s_extractor* h, int first_left, int first_right, int n_pairs, float bf, float mb, float* uright,
+                     float* depth, int cap_out, int32_t* n_matched);
+
 /* ------------------------------------------------------------------ matcher */
 typedef struct b2s_matcher b2s_matcher;
 int b2s_matcher_create(int max_features, int max_batch, int device, b2s_matcher** out);

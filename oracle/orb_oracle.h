@@ -113,6 +113,17 @@ int orc_search_by_projection_map(const orc_map_query* q, int nq, const float* kp
                                  const uint8_t* desc, int nf, const orc_frame_geom* g, float th, int th_high,
                                  float nnratio, int32_t* match_cur);
 
+/* Frame::ComputeStereoMatches (src/Frame.cc:1026-1421): row-band candidates, Hamming best (< (TH_HIGH+TH_LOW)/2),
+ * 11x11 L1 block matching over +-5 px on the keypoint's pyramid level, parabola sub-pixel fit, median*2.1 cull.
+ * kps: level-0 coordinates as produced by the extractor; pyr*: dense level images (stride = width), lvlW/lvlH their
+ * sizes; scale / inv_scale = mvScaleFactors / mvInvScaleFactors; mb = the baseline the reference sees at that point
+ * (0 in this fork: it is assigned after the call, so maxD = +inf).  Outputs mvuRight / mvDepth (-1 = no match).
+ * Returns the number of stereo matches that survive the cull. */
+int orc_compute_stereo_matches(const orc_keypoint* kpsL, const uint8_t* descL, int nL, const orc_keypoint* kpsR,
+                               const uint8_t* descR, int nR, const uint8_t* const* pyrL, const uint8_t* const* pyrR,
+                               const int* lvlW, const int* lvlH, const float* scale, const float* inv_scale, int nlevels,
+                               float mbf, float mb, float* uright, float* depth);
+
 /* ---------------- LocalBA (src/Optimizer.cc:629-997 + vendored g2o) ---------------- */
 typedef struct {
   int32_t kf;        /* index into poses[] */

@@ -213,6 +213,28 @@ class ORBextractor:
                                               _vp(d_kps_ptr), _vp(d_desc_ptr), _vp(d_counts_ptr), cap,
                                               _vp(stream) if stream else None))
 
+    def stereo_match(self, first_left, first_right, n_pairs, bf, mb=0.0):
+        """Frame::ComputeStereoMatches (src/Frame.cc:1026-1421) on the pairs of the batch extracted last with
+        extract_batch(); returns (uright [n_pairs, cap], depth [n_pairs, cap], n_matched [n_pairs])."""
+        ur = np.full((n_pairs, self.cap), -1, np.float32)
+        dp = np.full((n_pairs, self.cap), -1, np.float32)
+        nm = np.zeros(n_pairs, np.int32)
+        L = lib()
+        L.b2s_stereo_match.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, _vp,
+                                       _vp, ctypes.c_int, _vp]
+        _check(L.b2s_stereo_match(self._h, first_left, first_right, n_pairs, float(bf), float(mb), _p(ur), _p(dp),
+                                  self.cap, _p(nm)))
+        return ur, dp, nm
+
+    def stereo_match_device(self, first_left, first_right, n_pairs, d_kps_ptr, d_desc_ptr, d_counts_ptr, cap, bf, mb,
+                            d_uright_ptr, d_depth_ptr, d_nmatched_ptr, stream=0):
+        L = lib()
+        L.b2s_stereo_match_device.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, ctypes.c_int,
+                                              ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp]
+        _check(L.b2s_stereo_match_device(self._h, first_left, first_right, n_pairs, _vp(d_kps_ptr), _vp(d_desc_ptr),
+                                         _vp(d_counts_ptr), cap, float(bf), float(mb), _vp(d_uright_ptr),
+                                         _vp(d_depth_ptr), _vp(d_nmatched_ptr), _vp(stream)))
+
     def check(self):
         _check(lib().b2s_extractor_check(self._h))
 

@@ -1260,6 +1260,229 @@ static void b2s_extractor_timing_collect(b2s_extractor* h) {
   h->evPending = 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Frame::ComputeStereoMatches (src/Frame.cc:1026-1421) on the device-resident pyramids of a batch.
+// ------------------------------------------------------------------------------------------------
+struct StereoParams {
+  float invScale[kMaxLevels];  // mvInvScaleFactors
+  float bf, mb;
+  int firstLeft, firstRight;   // image indices of pair 0 inside the batch (pair p = firstLeft+p, firstRight+p)
+  int cap;
+};
+constexpr int ST_WARPS = 16;      // left keypoints per CTA
+constexpr int ST_MAXR = 4096;     // right keypoints staged per CTA (cap is checked on the host)
+
+// One warp per left keypoint.  Stage 1 (:1169-1219): the right keypoints whose row band [floor(y-r), ceil(y+r)],
+// r = 2*scale[octave] (:1060-1097) contains the left keypoint's row, within one pyramid level and with uR in
+// [uL-maxD, uL], minimum Hamming distance, first minimum in right-keypoint order.  Stage 2 (:1222-1391): 11x11 L1 block
+// matching over +-5 px on the keypoint's own pyramid level, parabola fit, disparity gate.  sad = best SAD or -1.
+__global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(ExtractGeom g, StereoParams sp, const uint8_t* __restrict__ pyr,
+                                                                const b2s_keypoint* __restrict__ kps,
+                                                                const uint8_t* __restrict__ desc,
+                                                                const int32_t* __restrict__ counts,
+                                                                float* __restrict__ uRight, float* __restrict__ depth,
+                                                                int32_t* __restrict__ sad) {
+  __shared__ int16_t sMinr[ST_MAXR], sMaxr[ST_MAXR];
+  __shared__ int8_t sOct[ST_MAXR];
+  __shared__ float sU[ST_MAXR];
+  const int pairI = blockIdx.y;
+  const int imgL = sp.firstLeft + pairI, imgR = sp.firstRight + pairI;
+  const int nL = min(counts[imgL], sp.cap), nR = min(counts[imgR], min(sp.cap, ST_MAXR));
+  if ((int)(blockIdx.x * ST_WARPS) >= nL) {  // beyond the left image's features: "no match"
+    const int i = blockIdx.x * ST_WARPS + (threadIdx.x >> 5);
+    if ((threadIdx.x & 31) == 0 && i < sp.cap) {
+      uRight[(size_t)pairI * sp.cap + i] = -1.0f;
+      depth[(size_t)pairI * sp.cap + i] = -1.0f;
+      sad[(size_t)pairI * sp.cap + i] = -1;
+    }
+    return;
+  }
+  const b2s_keypoint* kR = kps + (size_t)imgR * sp.cap;
+  for (int j = threadIdx.x; j < nR; j += blockDim.x) {
+    const b2s_keypoint k = kR[j];
+    const float r = __fmul_rn(2.0f, g.lv[k.octave].scale);
+    sMaxr[j] = (int16_t)(int)ceilf(__fadd_rn(k.y, r));
+    sMinr[j] = (int16_t)(int)floorf(__fsub_rn(k.y, r));
+    sOct[j] = (int8_t)k.octave;
+    sU[j] = k.x;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * ST_WARPS + (threadIdx.x >> 5);
+  if (i >= nL) {
+    if (lane == 0 && i < sp.cap) {
+      uRight[(size_t)pairI * sp.cap + i] = -1.0f;
+      depth[(size_t)pairI * sp.cap + i] = -1.0f;
+      sad[(size_t)pairI * sp.cap + i] = -1;
+    }
+    return;
+  }
+  const size_t oi = (size_t)pairI * sp.cap + i;
+  const b2s_keypoint kL = kps[(size_t)imgL * sp.cap + i];
+  const int levelL = kL.octave;
+  const float uL = kL.x, vL = kL.y;
+  const int row = (int)vL;  // vRowIndices[vL]
+  const float minD = 0.f, maxD = __fdiv_rn(sp.bf, sp.mb);  // :1108-1112 (mb == 0 -> +inf)
+  const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, minD);
+  float outU = -1.0f, outD = -1.0f;
+  int outSad = -1;
+  // ---- stage 1
+  uint32_t best = 0xFFFFFFFFu;
+  if (!(maxU < 0) && row >= 0 && row < g.lv[0].h) {
+    const u256 dL = ld_u256(desc + ((size_t)imgL * sp.cap + i) * 32);
+    const uint8_t* dR = desc + (size_t)imgR * sp.cap * 32;
+    for (int j = lane; j < nR; j += 32) {
+      const int o = sOct[j];
+      if (row < sMinr[j] || row > sMaxr[j] || o < levelL - 1 || o > levelL + 1) continue;
+      const float uR = sU[j];
+      if (!(uR >= minU && uR <= maxU)) continue;
+      const uint32_t key = ((uint32_t)hamming256(dL, ld_u256(dR + (size_t)j * 32)) << 16) | (uint32_t)j;
+      best = min(best, key);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  const int bestDist = (best == 0xFFFFFFFFu) ? 256 : (int)(best >> 16);
+  // dist < bestDist with bestDist initialised to TH_HIGH (:1166,1205); then bestDist < thOrbDist = (TH_HIGH+TH_LOW)/2
+  if (bestDist < 100 && bestDist < (100 + 50) / 2) {
+    // ---- stage 2
+    const int bestIdxR = (int)(best & 0xFFFFu);
+    const float uR0 = sU[bestIdxR];
+    const float scaleFactor = sp.invScale[levelL];
+    const float scaleduL = roundf(__fmul_rn(uL, scaleFactor));
+    const float scaledvL = roundf(__fmul_rn(vL, scaleFactor));
+    const float scaleduR0 = roundf(__fmul_rn(uR0, scaleFactor));
+    const LevelGeom& LV = g.lv[levelL];
+    const int w = 5, L = 5;
+    const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+    const int cy = (int)scaledvL, cxL = (int)scaleduL, cxR0 = (int)scaleduR0;
+    bool ok = !(iniu < 0 || endu >= (float)LV.w);  // :1290
+    ok = ok && !(cy - w < 0 || cy + w >= LV.h || cxL - w < 0 || cxL + w >= LV.w || cxR0 - L - w < 0);  // cv::Mat range asserts
+    if (ok) {
+      const uint8_t* IL = pyr + (size_t)imgL * g.pyrBytes + LV.off;
+      const uint8_t* IR = pyr + (size_t)imgR * g.pyrBytes + LV.off;
+      const int pitch = LV.pitch;
+      const int cL = IL[(size_t)cy * pitch + cxL];
+      int aL[4], off[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int p = lane + 32 * t;  // pixel of the 11x11 window
+        const int dy = p / 11 - w, dx = p - (p / 11) * 11 - w;
+        off[t] = (p < 121) ? (cy + dy) * pitch + dx : -1;
+        aL[t] = (p < 121) ? (int)IL[off[t] + cxL] - cL : 0;
+      }
+      int bestSad = 0x7fffffff, bestinc = 0;
+      int d0 = 0, d1 = 0, d2 = 0;  // SAD at bestinc-1, bestinc, bestinc+1
+      int prev = 0;
+      bool needNext = false;
+#pragma unroll 1
+      for (int incR = -L; incR <= L; incR++) {
+        const int cxR = cxR0 + incR;
+        const int cR = IR[(size_t)cy * pitch + cxR];
+        int sum = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+          if (off[t] >= 0) sum += abs(aL[t] - ((int)IR[off[t] + cxR] - cR));
+        sum = warp_reduce_sum(sum);
+        sum = __shfl_sync(0xffffffffu, sum, 0);
+        if (needNext) {
+          d2 = sum;
+          needNext = false;
+        }
+        if (sum < bestSad) {  // (float)dist < bestDist, strict: first minimum wins (:1308)
+          bestSad = sum;
+          bestinc = incR;
+          d0 = prev;
+          d1 = sum;
+          needNext = true;
+        }
+        prev = sum;
+      }
+      if (!(bestinc == -L || bestinc == L)) {
+        const float dist1 = (float)d0, dist2 = (float)d1, dist3 = (float)d2;
+        const float deltaR =
+            __fdiv_rn(__fsub_rn(dist1, dist3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(dist1, dist3), __fmul_rn(2.0f, dist2))));
+        if (!(deltaR < -1 || deltaR > 1)) {
+          float bestuR = __fmul_rn(LV.scale, __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
+          float disparity = __fsub_rn(uL, bestuR);
+          if (disparity >= minD && disparity < maxD) {
+            if (disparity <= 0) {
+              disparity = 0.01f;
+              bestuR = (float)((double)uL - 0.01);
+            }
+            outD = __fdiv_rn(sp.bf, disparity);
+            outU = bestuR;
+            outSad = bestSad;
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    uRight[oi] = outU;
+    depth[oi] = outD;
+    sad[oi] = outSad;
+  }
+}
+
+// Median-based cull (:1395-1415): thDist = 1.5f*1.4f*median(SAD) over the accepted matches (element size/2 of the
+// list sorted by (SAD, index)); matches with SAD >= thDist are removed.  One CTA per stereo pair.
+__global__ void __launch_bounds__(1024) k_stereo_cull(StereoParams sp, const int32_t* __restrict__ counts,
+                                                      float* __restrict__ uRight, float* __restrict__ depth,
+                                                      const int32_t* __restrict__ sad, int32_t* __restrict__ nMatched) {
+  __shared__ int32_t sSad[ST_MAXR];
+  __shared__ int sM, sMedian, sKept;
+  const int pairI = blockIdx.x;
+  const int nL = min(counts[sp.firstLeft + pairI], min(sp.cap, ST_MAXR));
+  const size_t base = (size_t)pairI * sp.cap;
+  if (threadIdx.x == 0) {
+    sM = 0;
+    sMedian = 0;
+    sKept = 0;
+  }
+  __syncthreads();
+  int mine = 0;
+  for (int i = threadIdx.x; i < nL; i += blockDim.x) {
+    const int v = sad[base + i];
+    sSad[i] = v;
+    mine += v >= 0;
+  }
+  if (mine) atomicAdd(&sM, mine);
+  __syncthreads();
+  const int M = sM;
+  if (M == 0) {
+    if (threadIdx.x == 0) nMatched[pairI] = 0;
+    return;
+  }
+  const int target = M / 2;
+  for (int i = threadIdx.x; i < nL; i += blockDim.x) {
+    const int v = sSad[i];
+    if (v < 0) continue;
+    int rank = 0;
+    for (int j = 0; j < nL; j++) {
+      const int u = sSad[j];
+      rank += (u >= 0) && (u < v || (u == v && j < i));
+    }
+    if (rank == target) sMedian = v;
+  }
+  __syncthreads();
+  const float thDist = __fmul_rn(__fmul_rn(1.5f, 1.4f), (float)sMedian);
+  int kept = 0;
+  for (int i = threadIdx.x; i < nL; i += blockDim.x) {
+    const int v = sSad[i];
+    if (v < 0) continue;
+    if ((float)v < thDist) {
+      kept++;
+    } else {
+      uRight[base + i] = -1.0f;
+      depth[base + i] = -1.0f;
+    }
+  }
+  if (kept) atomicAdd(&sKept, kept);
+  __syncthreads();
+  if (threadIdx.x == 0) nMatched[pairI] = sKept;
+}
+
 }  // namespace b2s
 
 using namespace b2s;
@@ -1433,6 +1656,10 @@ extern "C" void b2s_extractor_destroy(b2s_extractor* h) {
   if (h->hDesc) cudaFreeHost(h->hDesc);
   if (h->hCounts) cudaFreeHost(h->hCounts);
   if (h->hStatus) cudaFreeHost(h->hStatus);
+  if (h->dStereoSad) cudaFree(h->dStereoSad);
+  if (h->dStereoU) cudaFree(h->dStereoU);
+  if (h->dStereoD) cudaFree(h->dStereoD);
+  if (h->dStereoN) cudaFree(h->dStereoN);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   delete h;
@@ -1519,6 +1746,8 @@ extern "C" int b2s_extract_batch(b2s_extractor* h, const uint8_t* const* imgs, i
     rc = check_status(h);
     if (rc != B2S_OK) return rc;
     for (int b = 0; b < batch; b++) n_out[b] = h->hCounts[b];
+    h->lastCap = cap;  // the records of this call stay on the device (b2s_stereo_match)
+    h->lastBatch = batch;
     return B2S_OK;
   }
   rc = upload_level0(h, imgs, 0, batch, width, height, stride, h->stream);
@@ -1539,6 +1768,8 @@ extern "C" int b2s_extract_batch(b2s_extractor* h, const uint8_t* const* imgs, i
     memcpy(kps + (size_t)b * cap, h->hKps + (size_t)b * icap, (size_t)n * sizeof(b2s_keypoint));
     memcpy(desc + (size_t)b * cap * 32, h->hDesc + (size_t)b * icap * 32, (size_t)n * 32);
   }
+  h->lastCap = icap;
+  h->lastBatch = batch;
   return B2S_OK;
 }
 
@@ -1651,5 +1882,80 @@ extern "C" int b2s_debug_sincosf(const float* in, int n, float* s, float* c) {
   cudaFree(din);
   cudaFree(ds);
   cudaFree(dc);
+  return B2S_OK;
+}
+
+
+// ---------------------------------------------------------------- stereo matching on the resident pyramids
+static int stereo_launch(b2s_extractor* h, int first_left, int first_right, int n_pairs, const b2s_keypoint* d_kps,
+                         const uint8_t* d_desc, const int32_t* d_counts, int cap, float bf, float mb, float* d_uright,
+                         float* d_depth, int32_t* d_nmatched, cudaStream_t st) {
+  const ExtractGeom& g = h->geom;
+  StereoParams sp;
+  for (int l = 0; l < kMaxLevels; l++) sp.invScale[l] = l < h->nlevels ? h->invScale[l] : 0.f;
+  sp.bf = bf; sp.mb = mb; sp.firstLeft = first_left; sp.firstRight = first_right; sp.cap = cap;
+  if ((size_t)n_pairs * cap > h->stereoCap) {
+    if (h->dStereoSad) cudaFree(h->dStereoSad);
+    h->dStereoSad = nullptr;
+    h->stereoCap = 0;
+    B2S_CUDA(cudaMalloc((void**)&h->dStereoSad, (size_t)n_pairs * cap * 4));
+    h->stereoCap = (size_t)n_pairs * cap;
+  }
+  k_stereo_match<<<dim3(div_up(cap, ST_WARPS), n_pairs), ST_WARPS * 32, 0, st>>>(g, sp, h->d.pyr, d_kps, d_desc, d_counts,
+                                                                               d_uright, d_depth, h->dStereoSad);
+  k_stereo_cull<<<n_pairs, 1024, 0, st>>>(sp, d_counts, d_uright, d_depth, h->dStereoSad, d_nmatched);
+  h->launches += 2;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+extern "C" int b2s_stereo_match_device(b2s_extractor* h, int first_left, int first_right, int n_pairs,
+                                       const b2s_keypoint* d_kps, const uint8_t* d_desc, const int32_t* d_counts, int cap,
+                                       float bf, float mb, float* d_uright, float* d_depth, int32_t* d_nmatched,
+                                       void* stream) {
+  if (!h || !h->curW || n_pairs < 1 || first_left < 0 || first_right < 0 || first_left + n_pairs > h->maxBatch ||
+      first_right + n_pairs > h->maxBatch || !d_kps || !d_desc || !d_counts || cap < 1 || cap > ST_MAXR || !d_uright ||
+      !d_depth || !d_nmatched) {
+    set_error("b2s_stereo_match_device: bad argument (extract a batch with this handle first; cap <= %d)", ST_MAXR);
+    return B2S_ERR_BAD_ARG;
+  }
+  B2S_CUDA(cudaSetDevice(h->device));
+  return stereo_launch(h, first_left, first_right, n_pairs, d_kps, d_desc, d_counts, cap, bf, mb, d_uright, d_depth,
+                       d_nmatched, stream ? (cudaStream_t)stream : h->stream);
+}
+
+extern "C" int b2s_stereo_match(b2s_extractor* h, int first_left, int first_right, int n_pairs, float bf, float mb,
+                                float* uright, float* depth, int cap_out, int32_t* n_matched) {
+  if (!h || !h->curW || h->lastCap < 1 || n_pairs < 1 || first_left < 0 || first_right < 0 ||
+      first_left + n_pairs > h->lastBatch || first_right + n_pairs > h->lastBatch || !uright || !depth ||
+      cap_out < h->lastCap || h->lastCap > ST_MAXR) {
+    set_error("b2s_stereo_match: call b2s_extract_batch first; cap_out must be >= the cap of that call");
+    return B2S_ERR_BAD_ARG;
+  }
+  B2S_CUDA(cudaSetDevice(h->device));
+  const int cap = h->lastCap;
+  const size_t need = (size_t)n_pairs * cap;
+  if (need > h->stereoOutCap) {
+    if (h->dStereoU) cudaFree(h->dStereoU);
+    if (h->dStereoD) cudaFree(h->dStereoD);
+    if (h->dStereoN) cudaFree(h->dStereoN);
+    h->dStereoU = h->dStereoD = nullptr;
+    h->dStereoN = nullptr;
+    h->stereoOutCap = 0;
+    B2S_CUDA(cudaMalloc((void**)&h->dStereoU, need * 4));
+    B2S_CUDA(cudaMalloc((void**)&h->dStereoD, need * 4));
+    B2S_CUDA(cudaMalloc((void**)&h->dStereoN, (size_t)h->maxBatch * 4));
+    h->stereoOutCap = need;
+  }
+  cudaStream_t st = h->stream;
+  int rc = stereo_launch(h, first_left, first_right, n_pairs, h->d.outKps, h->d.outDesc, h->d.outCounts, cap, bf, mb,
+                         h->dStereoU, h->dStereoD, h->dStereoN, st);
+  if (rc != B2S_OK) return rc;
+  B2S_CUDA(cudaMemcpy2DAsync(uright, (size_t)cap_out * 4, h->dStereoU, (size_t)cap * 4, (size_t)cap * 4, n_pairs,
+                             cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpy2DAsync(depth, (size_t)cap_out * 4, h->dStereoD, (size_t)cap * 4, (size_t)cap * 4, n_pairs,
+                             cudaMemcpyDeviceToHost, st));
+  if (n_matched) B2S_CUDA(cudaMemcpyAsync(n_matched, h->dStereoN, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
   return B2S_OK;
 }

@@ -76,6 +76,12 @@ struct b2s_extractor {
   b2s::DeviceBuffers d;
   size_t pyrBytesAlloc = 0, candCapAlloc = 0, selCapAlloc = 0, rxAlloc = 0, ryAlloc = 0, cellAlloc = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;
+  // stereo matching scratch + bookkeeping of the last host-buffer batch extraction (b2s_stereo_match)
+  int32_t* dStereoSad = nullptr;
+  size_t stereoCap = 0, stereoOutCap = 0;
+  float *dStereoU = nullptr, *dStereoD = nullptr;
+  int32_t* dStereoN = nullptr;
+  int lastCap = 0, lastBatch = 0;
   // pinned staging for the host-buffer entry points
   b2s_keypoint* hKps = nullptr;
   uint8_t* hDesc = nullptr;

@@ -148,6 +148,26 @@ class Oracle:
                                                 P(occupied), P(desc), len(kpx), ctypes.byref(g), th, th_high, nnratio, P(m))
         return n, m
 
+    def compute_stereo_matches(self, exL, exR, kpsL, descL, kpsR, descR, bf, mb=0.0):
+        """exL / exR: OracleExtractor objects that just extracted the left / right image (their pyramids are used)."""
+        nl = exL.nlevels
+        lv_l = [exL.level(l) for l in range(nl)]
+        lv_r = [exR.level(l) for l in range(nl)]
+        W = np.array([a.shape[1] for a in lv_l], np.int32)
+        H = np.array([a.shape[0] for a in lv_l], np.int32)
+        pl = (vp * nl)(*[a.ctypes.data for a in lv_l])
+        pr = (vp * nl)(*[a.ctypes.data for a in lv_r])
+        (sc, isc, _, _), _, _ = exL.tables()
+        kpsL, descL = np.ascontiguousarray(kpsL), np.ascontiguousarray(descL)
+        kpsR, descR = np.ascontiguousarray(kpsR), np.ascontiguousarray(descR)
+        ur = np.zeros(len(kpsL), np.float32)
+        dp = np.zeros(len(kpsL), np.float32)
+        self.L.orc_compute_stereo_matches.argtypes = [vp, vp, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp,
+                                                      ctypes.c_int, ctypes.c_float, ctypes.c_float, vp, vp]
+        n = self.L.orc_compute_stereo_matches(P(kpsL), P(descL), len(kpsL), P(kpsR), P(descR), len(kpsR), pl, pr, P(W), P(H),
+                                              P(sc), P(isc), nl, bf, mb, P(ur), P(dp))
+        return n, ur, dp
+
     # ---- LocalBA ----
     def local_ba(self, d, stop=None, its1=5, its2=10):
         Tcw = np.ascontiguousarray(d["Tcw"], np.float32)

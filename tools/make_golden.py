@@ -59,3 +59,7 @@ r = o.local_ba(ba)
 np.savez_compressed(os.path.join(out, "localba_small_seed5.npz"), Tcw=r["Tcw"], points=r["points"], outlier=r["outlier"],
                     trace=r["trace"], n_trials=r["n_trials"], chi2=r["chi2"])
 print("golden fixtures written to", out)
+# ComputeStereoMatches (written by tests/test_oracle_stereo.py::_run with the same arguments)
+from test_oracle_stereo import _run as _stereo_run  # noqa: E402
+_, n, ur, dp = _stereo_run(o, 640, 480, 1000, 9, 0.0)
+np.savez_compressed(os.path.join(out, "stereo_640x480_seed9.npz"), n=n, uright=ur, depth=dp)
