@@ -246,6 +246,27 @@ def run_b200(args, rank, local_rank, world):
     L.b2s_extractor_set_timing(ss.ex._h, 0)
     phase["extractor_stage_ms_isolated"] = {k: stage_iso[i] / max(1, calls_iso.value) for i, k in enumerate(
         ["resize_chain", "fast_cells", "quadtree", "blur", "orient_describe"])}
+    # Frame::ComputeStereoMatches for the F pairs of the step, on the resident pyramids (reported next to
+    # the step, not part of the metric): left image i <-> right image F+i
+    try:
+        ur = torch.zeros((F, ss.cap), dtype=torch.float32, device="cuda")
+        dp = torch.zeros((F, ss.cap), dtype=torch.float32, device="cuda")
+        nmt = torch.zeros(F, dtype=torch.int32, device="cuda")
+        st = ss.stream
+        with torch.cuda.stream(st):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for rep in range(2):
+                if rep == 1:
+                    e0.record(st)
+                ss.ex.stereo_match_device(0, F, F, ss.kps[1:].data_ptr(), ss.desc[1:].data_ptr(),
+                                          ss.counts[1:].data_ptr(), ss.cap, 386.1448, 0.0, ur.data_ptr(), dp.data_ptr(),
+                                          nmt.data_ptr(), stream=st.cuda_stream)
+            e1.record(st)
+        torch.cuda.synchronize()
+        phase["stereo_match_ms_isolated"] = e0.elapsed_time(e1)
+        phase["stereo_matches_per_frame"] = float(nmt.float().mean().item())
+    except Exception as ex:  # never let the side measurement break the bench line
+        phase["stereo_match_error"] = str(ex)[:200]
     if ss.n_ba:
         t1 = time.perf_counter()
         ss.opt.LocalBundleAdjustmentBatch([ss.ba_problem] * ss.n_ba)
