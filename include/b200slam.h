@@ -191,6 +191,32 @@ int b2s_search_by_projection_map(b2s_matcher* h, const b2s_map_query* q, int nq,
                                  int nf, const b2s_frame_geom* g, float th, int th_high, float nnratio, int32_t* match_cur,
                                  int* nmatches);
 
+/* Windowed best-match search on a KeyFrame's feature grid: the search core shared by
+ *   ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th)                        src/ORBmatcher.cc:1020-1174 (B2S_WIN_CHI2)
+ *   ORBmatcher::Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint)          :1179-1310                  (no flag)
+ *   ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) :388-512                    (B2S_WIN_GREEDY)
+ * The caller keeps the projection (Rcw/tcw or Sim3), the visibility / distance / normal tests and the map bookkeeping
+ * (Replace / AddObservation) and passes one query per surviving map point, in the reference's iteration order. */
+typedef struct {
+  float u, v, ur;      /* projection into the keyframe (ur = u - bf*invz; only the chi-square gate reads it) */
+  float radius;        /* th * pKF->mvScaleFactors[nPredictedLevel] */
+  int32_t min_level;   /* nPredictedLevel-1 */
+  int32_t max_level;   /* nPredictedLevel   */
+  uint8_t valid;       /* 0: skipped by the reference before the search (bad / behind the camera / out of range ...) */
+  uint8_t pad[3];
+  uint8_t desc[32];    /* pMP->GetDescriptor() */
+} b2s_win_query;
+#define B2S_WIN_CHI2 1   /* reprojection gate e2*mvInvLevelSigma2[level] <= 7.8 (mvuRight >= 0) / 5.99 (:1097-1124) */
+#define B2S_WIN_GREEDY 2 /* features with occupied[j] != 0 or chosen by an earlier query are skipped (:462-463,498-502) */
+
+/* best_idx[i] = keyframe feature with the smallest descriptor distance (first minimum in GetFeaturesInArea order,
+ * src/KeyFrame.cc:752-796) if that distance <= th_dist (TH_LOW), else -1; best_dist may be NULL; occupied is only
+ * read with B2S_WIN_GREEDY (may be NULL); inv_level_sigma2 only with B2S_WIN_CHI2.  HOST buffers. */
+int b2s_search_windows(b2s_matcher* h, const b2s_win_query* q, int nq, const float* kpx, const float* kpy,
+                       const int32_t* octave, const float* uright, const float* inv_level_sigma2, const uint8_t* occupied,
+                       const uint8_t* desc, int nf, const b2s_frame_geom* g, int flags, int th_dist, int32_t* best_idx,
+                       int32_t* best_dist, int* n_accepted);
+
 /* ------------------------------------------------------------------ LocalBA */
 typedef struct {
   int32_t kf;       /* index into Tcw[] */

@@ -297,3 +297,56 @@ extern "C" int orc_search_by_projection_map(const orc_map_query* q, int nq, cons
   delete grid;
   return nmatches;
 }
+
+// Common search core of Fuse (:1020-1174, :1179-1310) and SearchByProjection(KeyFrame*, Scw, ...) (:388-512); see orb_oracle.h.
+extern "C" int orc_search_windows(const orc_win_query* q, int nq, const float* kpx, const float* kpy, const int32_t* octave,
+                                  const float* uright, const float* inv_level_sigma2, const uint8_t* occupied_in,
+                                  const uint8_t* desc, int nf, const orc_frame_geom* g, int flags, int th_dist,
+                                  int32_t* best_idx, int32_t* best_dist) {
+  Grid* grid = new Grid();
+  grid->build(kpx, kpy, nf, g);
+  std::vector<uint8_t> occupied(nf, 0);
+  if (occupied_in) std::copy(occupied_in, occupied_in + nf, occupied.begin());
+  const bool chi2 = flags & ORC_WIN_CHI2, greedy = flags & ORC_WIN_GREEDY;
+  int n = 0;
+  std::vector<int> cand;
+  for (int i = 0; i < nq; i++) {
+    best_idx[i] = -1;
+    if (best_dist) best_dist[i] = 256;
+    if (!q[i].valid) continue;
+    const float u = q[i].u, v = q[i].v, ur = q[i].ur;
+    grid->in_area(u, v, q[i].radius, -1, -1, kpx, kpy, octave, cand);  // KeyFrame::GetFeaturesInArea: no level filter
+    if (cand.empty()) continue;
+    int bestDist = 256, bestIdx = -1;
+    for (size_t c = 0; c < cand.size(); c++) {
+      const int idx = cand[c];
+      if (greedy && occupied[idx]) continue;  // :462-463
+      const int kpLevel = octave[idx];
+      if (kpLevel < q[i].min_level || kpLevel > q[i].max_level) continue;  // :1093-1094
+      if (chi2) {  // :1097-1124
+        if (uright[idx] >= 0) {
+          const float ex = u - kpx[idx], ey = v - kpy[idx], er = ur - uright[idx];
+          const float e2 = ex * ex + ey * ey + er * er;
+          if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+        } else {
+          const float ex = u - kpx[idx], ey = v - kpy[idx];
+          const float e2 = ex * ex + ey * ey;
+          if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+        }
+      }
+      const int dist = orc_descriptor_distance(q[i].desc, desc + (size_t)idx * 32);
+      if (dist < bestDist) {
+        bestDist = dist;
+        bestIdx = idx;
+      }
+    }
+    if (best_dist) best_dist[i] = bestDist;
+    if (bestDist <= th_dist) {  // :1137 / :498
+      best_idx[i] = bestIdx;
+      if (greedy) occupied[bestIdx] = 1;
+      n++;
+    }
+  }
+  delete grid;
+  return n;
+}

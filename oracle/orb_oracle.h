@@ -113,6 +113,27 @@ int orc_search_by_projection_map(const orc_map_query* q, int nq, const float* kp
                                  const uint8_t* desc, int nf, const orc_frame_geom* g, float th, int th_high,
                                  float nnratio, int32_t* match_cur);
 
+/* Windowed best-match search on a KeyFrame's grid — the common core of
+ *   ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th)                      src/ORBmatcher.cc:1020-1174  (flags = CHI2)
+ *   ORBmatcher::Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint)        :1179-1310                   (flags = 0)
+ *   ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) :388-512                    (flags = GREEDY)
+ * after the caller projected the map points (u, v, ur), predicted the level and computed radius = th*scale[level].
+ * Candidates: KeyFrame::GetFeaturesInArea(u, v, radius) (src/KeyFrame.cc:752-796), level in [min_level, max_level];
+ * CHI2: reprojection gate e2*invSigma2[level] <= 7.8 (stereo feature, mvuRight >= 0) / 5.99 (mono) (:1097-1124);
+ * GREEDY: a feature with occupied[idx] != 0 or chosen by an earlier query is skipped (:462-463,498-502).
+ * best_idx[i] = feature with the smallest distance (first minimum) if that distance <= th_dist, else -1. */
+typedef struct {
+  float u, v, ur, radius;
+  int32_t min_level, max_level;
+  uint8_t valid, pad[3];
+  uint8_t desc[32];
+} orc_win_query;
+#define ORC_WIN_CHI2 1
+#define ORC_WIN_GREEDY 2
+int orc_search_windows(const orc_win_query* q, int nq, const float* kpx, const float* kpy, const int32_t* octave,
+                       const float* uright, const float* inv_level_sigma2, const uint8_t* occupied, const uint8_t* desc,
+                       int nf, const orc_frame_geom* g, int flags, int th_dist, int32_t* best_idx, int32_t* best_dist);
+
 /* Frame::ComputeStereoMatches (src/Frame.cc:1026-1421): row-band candidates, Hamming best (< (TH_HIGH+TH_LOW)/2),
  * 11x11 L1 block matching over +-5 px on the keypoint's pyramid level, parabola sub-pixel fit, median*2.1 cull.
  * kps: level-0 coordinates as produced by the extractor; pyr*: dense level images (stride = width), lvlW/lvlH their

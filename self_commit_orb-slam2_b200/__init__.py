@@ -21,6 +21,8 @@ OK, ERR_NO_DEVICE, ERR_BAD_ARG, ERR_CUDA, ERR_CAPACITY, ERR_ABORTED = range(6)
 
 keypoint_dtype = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                            ("octave", "<i4"), ("class_id", "<i4")])
+win_query_dtype = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("radius", "<f4"), ("min_level", "<i4"),
+                            ("max_level", "<i4"), ("valid", "u1"), ("pad", "u1", 3), ("desc", "u1", 32)])
 map_query_dtype = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("view_cos", "<f4"), ("level", "<i4"),
                             ("in_view", "u1"), ("has_obs", "u1"), ("pad", "u1", 2), ("desc", "u1", 32)])
 proj_query_dtype = np.dtype([("u", "<f4"), ("v", "<f4"), ("invz", "<f4"), ("angle", "<f4"), ("octave", "<i4"),
@@ -323,6 +325,26 @@ class ORBmatcher:
                                                   _p(uright), _p(occupied), _p(desc), nf, ctypes.byref(g), float(th),
                                                   th_high, float(self.mfNNratio), _p(match), ctypes.byref(nm)))
         return nm.value, match
+
+
+    def SearchWindows(self, queries, kpx, kpy, octave, uright, inv_level_sigma2, occupied, desc, geom, chi2=False,
+                      greedy=False, th_dist=TH_LOW):
+        """Search core of Fuse (src/ORBmatcher.cc:1020-1174, :1179-1310) and SearchByProjection(KeyFrame*, Scw, ...)
+        (:388-512); queries: win_query_dtype.  Returns (n_accepted, best_idx, best_dist)."""
+        nq, nf = len(queries), len(kpx)
+        sf = np.ascontiguousarray(geom["scale_factors"], np.float32)
+        g = _FrameGeom(geom["mnMinX"], geom["mnMinY"], geom["mnMaxX"], geom["mnMaxY"], geom["bf"], sf.ctypes.data, len(sf))
+        best = np.full(nq, -1, np.int32)
+        bdist = np.full(nq, 256, np.int32)
+        nacc = ctypes.c_int(0)
+        L = lib()
+        L.b2s_search_windows.argtypes = [_vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp,
+                                         ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]
+        is2 = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+        _check(L.b2s_search_windows(self._h, _p(queries), nq, _p(kpx), _p(kpy), _p(octave), _p(uright), _p(is2),
+                                    _p(occupied), _p(desc), nf, ctypes.byref(g), (1 if chi2 else 0) | (2 if greedy else 0),
+                                    th_dist, _p(best), _p(bdist), ctypes.byref(nacc)))
+        return nacc.value, best, bdist
 
 
 class Optimizer:

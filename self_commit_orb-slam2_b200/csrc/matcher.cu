@@ -392,6 +392,8 @@ struct ProjGeom {
   float minX, minY, maxX, maxY, invW, invH, bf, th;
   int mode, thHigh, checkOri, nlevels;
   float scale[16];
+  float invSigma2[16];  // mvInvLevelSigma2 (only the chi-square gate of the window search reads it)
+  int winFlags;         // B2S_WIN_* of b2s_search_windows
 };
 
 // PosInGrid (src/Frame.cc:863-877): cell = round(), features outside the grid get key = big (sorted last, ignored)
@@ -426,12 +428,21 @@ struct __align__(8) MapQuery {  // == b2s_map_query (SearchByProjection(Frame&, 
   uint8_t desc[32];
 };
 
+struct __align__(4) WinQuery {  // == b2s_win_query (Fuse / SearchByProjection(KeyFrame*, Scw, ...) search core)
+  float u, v, ur, radius;
+  int32_t min_level, max_level;
+  uint8_t valid, pad[3];
+  uint8_t desc[32];
+};
+
 // search window of one query: centre, radius, level range of GetFeaturesInArea and the right-image coordinate of the
 // stereo gate
 struct Win {
   bool ok;
   float u, v, r, ur;
   int minL, maxL;
+  bool stereoGate = true;  // |ur - uRight| <= r on stereo features (:1662-1669 / :128-139)
+  bool chi2Gate = false;   // Fuse reprojection gate (:1097-1124)
 };
 __device__ __forceinline__ Win make_win(const ProjQuery& Q, const ProjGeom& g) {  // :1607-1646
   Win w;
@@ -458,6 +469,17 @@ __device__ __forceinline__ Win make_win(const MapQuery& Q, const ProjGeom& g) { 
   w.ur = Q.ur;
   return w;
 }
+__device__ __forceinline__ Win make_win(const WinQuery& Q, const ProjGeom& g) {
+  Win w;
+  w.u = Q.u; w.v = Q.v; w.ur = Q.ur;
+  w.ok = Q.valid != 0;
+  w.r = Q.radius;
+  w.minL = Q.min_level;  // max_level >= 0, so the GetFeaturesInArea-style test below is the plain range test
+  w.maxL = max(Q.max_level, 0);
+  w.stereoGate = false;
+  w.chi2Gate = (g.winFlags & 1) != 0;
+  return w;
+}
 // cell range of GetFeaturesInArea (src/Frame.cc:752-770); false = empty result
 __device__ __forceinline__ bool win_cells(const Win& w, const ProjGeom& g, int& c0x, int& c1x, int& c0y, int& c1y) {
   c0x = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.u, g.minX), w.r), g.invW)));
@@ -477,8 +499,23 @@ __device__ __forceinline__ bool win_take(const Win& w, int id, const float* __re
   const float dx = __fsub_rn(kpx[id], w.u), dy = __fsub_rn(kpy[id], w.v);
   if (!(fabsf(dx) < w.r && fabsf(dy) < w.r)) return false;
   const float urr = uright[id];
-  if (urr > 0 && fabsf(__fsub_rn(w.ur, urr)) > w.r) return false;
+  if (w.stereoGate && urr > 0 && fabsf(__fsub_rn(w.ur, urr)) > w.r) return false;
   return true;
+}
+// Fuse: reprojection error gate with the candidate's level sigma (src/ORBmatcher.cc:1097-1124)
+__device__ __forceinline__ bool win_chi2_ok(const Win& w, int id, const float* __restrict__ kpx, const float* __restrict__ kpy,
+                                            const int32_t* __restrict__ octave, const float* __restrict__ uright,
+                                            const ProjGeom& g) {
+  const float ex = __fsub_rn(w.u, kpx[id]), ey = __fsub_rn(w.v, kpy[id]);
+  const float is2 = g.invSigma2[min(max(octave[id], 0), 15)];
+  const float urr = uright[id];
+  if (urr >= 0) {
+    const float er = __fsub_rn(w.ur, urr);
+    const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
+    return !((double)__fmul_rn(e2, is2) > 7.8);
+  }
+  const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+  return !((double)__fmul_rn(e2, is2) > 5.99);
 }
 
 // stage 1: one warp per query; candidates are enumerated in GetFeaturesInArea order (src/Frame.cc:741-850:
@@ -513,6 +550,7 @@ __global__ void __launch_bounds__(256) k_proj_topk(const QT* __restrict__ q, int
       for (int p = beg + lane; p < end; p += 32) {
         const int id = order[p];
         bool take = win_take(w, id, kpx, kpy, octave, uright);
+        if (take && w.chi2Gate) take = win_chi2_ok(w, id, kpx, kpy, octave, uright, g);
         if (take && occupied && occupied[id]) take = false;  // initially occupied features are never candidates
         if (take) {
           const int d = hamming256(dq, ld_desc(desc, id));
@@ -572,6 +610,7 @@ __device__ __forceinline__ void win_rescan_top2(const QT& Q, const ProjGeom& g, 
     for (int p = beg + lane; p < end; p += 32) {
       const int fid = order[p];
       bool take = win_take(w, fid, kpx, kpy, octave, uright);
+      if (take && w.chi2Gate) take = win_chi2_ok(w, fid, kpx, kpy, octave, uright, g);
       if (take && ((occupied && occupied[fid]) || taken[fid])) take = false;
       if (take) {
         const uint32_t key = ((uint32_t)hamming256(dq, ld_desc(desc, fid)) << 20) | (uint32_t)(ord + (p - beg));
@@ -715,6 +754,72 @@ __global__ void __launch_bounds__(32) k_proj_resolve(const ProjQuery* __restrict
   __syncwarp();
   if (lane == 0) accepted[0] = nAccepted;
   if (lane < HISTO) histOut[lane] = hist[lane];
+}
+
+// Window search without occupancy (Fuse): the queries are independent, the answer is the head of each K-list.
+__global__ void __launch_bounds__(256) k_win_pick(int nq, int thDist, const uint32_t* __restrict__ topk,
+                                                  const int32_t* __restrict__ topkIdx, int32_t* __restrict__ bestIdx,
+                                                  int32_t* __restrict__ bestDist, int32_t* __restrict__ nAccepted) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool acc = false;
+  if (i < nq) {
+    const uint32_t e = topk[(size_t)i * TOPK];
+    const int d = (e == EMPTY) ? 256 : (int)(e >> 20);
+    acc = d <= thDist;
+    bestDist[i] = d;
+    bestIdx[i] = acc ? topkIdx[(size_t)i * TOPK] : -1;
+  }
+  const int c = __syncthreads_count(acc);
+  if (threadIdx.x == 0 && c) atomicAdd(nAccepted, c);
+}
+
+// Window search with greedy occupancy (SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th), :388-512): a
+// feature chosen by an earlier query (or occupied on entry) is skipped; one warp walks the queries in order.
+__global__ void __launch_bounds__(32) k_win_resolve(const WinQuery* __restrict__ q, int nq, int thDist,
+                                                    const float* __restrict__ kpx, const float* __restrict__ kpy,
+                                                    const int32_t* __restrict__ octave, const float* __restrict__ uright,
+                                                    const uint8_t* __restrict__ occupied, const uint8_t* __restrict__ desc,
+                                                    const int32_t* __restrict__ order, const int32_t* __restrict__ cellStart,
+                                                    ProjGeom g, const uint32_t* __restrict__ topk,
+                                                    const int32_t* __restrict__ topkIdx, const int32_t* __restrict__ candCnt,
+                                                    uint8_t* __restrict__ taken, int32_t* __restrict__ bestIdx,
+                                                    int32_t* __restrict__ bestDist, int32_t* __restrict__ nAccepted) {
+  const int lane = threadIdx.x;
+  int nAcc = 0;
+  for (int i = 0; i < nq; i++) {
+    const int cc = candCnt[i];
+    int outIdx = -1, outDist = 256;
+    if (cc > 0) {
+      const uint32_t e = (lane < TOPK) ? topk[(size_t)i * TOPK + lane] : EMPTY;
+      const int id = (lane < TOPK) ? topkIdx[(size_t)i * TOPK + lane] : -1;
+      const bool avail = (e != EMPTY) && !taken[id];
+      const unsigned am = __ballot_sync(0xffffffffu, avail);
+      uint32_t key1 = EMPTY, key2;
+      int id1 = -1, id2;
+      if (am) {
+        const int l1 = __ffs(am) - 1;
+        key1 = __shfl_sync(0xffffffffu, e, l1);
+        id1 = __shfl_sync(0xffffffffu, id, l1);
+      } else if (cc > TOPK) {
+        win_rescan_top2(q[i], g, lane, kpx, kpy, octave, uright, occupied, taken, desc, order, cellStart, key1, id1, key2,
+                        id2);
+      }
+      if (id1 >= 0) {
+        outDist = (int)(key1 >> 20);
+        if (outDist <= thDist) {
+          outIdx = id1;
+          if (lane == 0) taken[id1] = 1;
+          nAcc++;
+        }
+      }
+    }
+    if (lane == 0) {
+      bestIdx[i] = outIdx;
+      bestDist[i] = outDist;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) nAccepted[0] = nAcc;
 }
 
 // SearchByProjection(Frame&, vector<MapPoint*>&, th) greedy loop (:78-172): one warp walks the map points in order.
@@ -871,7 +976,7 @@ extern "C" int b2s_matcher_create(int max_features, int max_batch, int device, b
   A((void**)&h->dAngA, F * 4); A((void**)&h->dAngB, F * 4);
   A((void**)&h->dKpx, F * 4); A((void**)&h->dKpy, F * 4); A((void**)&h->dURight, F * 4);
   A((void**)&h->dTopk, F * TOPK * 4);
-  A((void**)&h->dQueries, F * sizeof(ProjQuery));
+  A((void**)&h->dQueries, F * 64);  // ProjQuery / MapQuery (56 B) or WinQuery (60 B)
   if (e != cudaSuccess) {
     set_error("b2s_matcher_create: %s", cudaGetErrorString(e));
     b2s_matcher_destroy(h);
@@ -1024,6 +1129,7 @@ extern "C" int b2s_search_by_projection_last(b2s_matcher* h, const b2s_proj_quer
   B2S_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   ProjGeom pg;
+  memset(&pg, 0, sizeof(pg));
   pg.minX = g->mnMinX; pg.minY = g->mnMinY; pg.maxX = g->mnMaxX; pg.maxY = g->mnMaxY;
   pg.invW = (float)GRID_COLS / (g->mnMaxX - g->mnMinX);  // src/Frame.cc:213-214
   pg.invH = (float)GRID_ROWS / (g->mnMaxY - g->mnMinY);
@@ -1081,6 +1187,7 @@ extern "C" int b2s_search_by_projection_map(b2s_matcher* h, const b2s_map_query*
   B2S_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   ProjGeom pg;
+  memset(&pg, 0, sizeof(pg));
   pg.minX = g->mnMinX; pg.minY = g->mnMinY; pg.maxX = g->mnMaxX; pg.maxY = g->mnMaxY;
   pg.invW = (float)GRID_COLS / (g->mnMaxX - g->mnMinX);  // src/Frame.cc:213-214
   pg.invH = (float)GRID_ROWS / (g->mnMaxY - g->mnMinY);
@@ -1111,5 +1218,72 @@ extern "C" int b2s_search_by_projection_map(b2s_matcher* h, const b2s_map_query*
   B2S_CUDA(cudaMemcpyAsync(match_cur, h->dMatch, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaStreamSynchronize(st));
+  return B2S_OK;
+}
+
+extern "C" int b2s_search_windows(b2s_matcher* h, const b2s_win_query* q, int nq, const float* kpx, const float* kpy,
+                                  const int32_t* octave, const float* uright, const float* inv_level_sigma2,
+                                  const uint8_t* occupied, const uint8_t* desc, int nf, const b2s_frame_geom* g, int flags,
+                                  int th_dist, int32_t* best_idx, int32_t* best_dist, int* n_accepted) {
+  static_assert(sizeof(WinQuery) == sizeof(b2s_win_query), "query layout");
+  if (!h || nq < 0 || nf < 0 || nq > h->maxF || nf > h->maxF || !best_idx || !g || g->nlevels < 1 || g->nlevels > 16 ||
+      ((flags & B2S_WIN_CHI2) && !inv_level_sigma2)) {
+    set_error("b2s_search_windows: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  if (n_accepted) *n_accepted = 0;
+  for (int i = 0; i < nq; i++) {
+    best_idx[i] = -1;
+    if (best_dist) best_dist[i] = 256;
+  }
+  if (nq == 0 || nf == 0) return B2S_OK;
+  if (!q || !kpx || !kpy || !octave || !uright || !desc) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  ProjGeom pg;
+  memset(&pg, 0, sizeof(pg));
+  pg.minX = g->mnMinX; pg.minY = g->mnMinY; pg.maxX = g->mnMaxX; pg.maxY = g->mnMaxY;
+  pg.invW = (float)GRID_COLS / (g->mnMaxX - g->mnMinX);  // KeyFrame::mfGridElementWidthInv (copied from the Frame)
+  pg.invH = (float)GRID_ROWS / (g->mnMaxY - g->mnMinY);
+  pg.bf = g->bf; pg.th = 1.f; pg.mode = 0; pg.thHigh = th_dist; pg.checkOri = 0; pg.nlevels = g->nlevels;
+  pg.winFlags = flags;
+  for (int i = 0; i < 16; i++) {
+    pg.scale[i] = (g->scale_factors && i < g->nlevels) ? g->scale_factors[i] : 0.f;
+    pg.invSigma2[i] = (inv_level_sigma2 && i < g->nlevels) ? inv_level_sigma2[i] : 0.f;
+  }
+  const bool greedy = (flags & B2S_WIN_GREEDY) != 0;
+  const bool useOcc = greedy && occupied;
+  WinQuery* dQ = reinterpret_cast<WinQuery*>(h->dQueries);
+  B2S_CUDA(cudaMemcpyAsync(dQ, q, (size_t)nq * sizeof(WinQuery), cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dKpx, kpx, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dKpy, kpy, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dOct, octave, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dURight, uright, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  if (useOcc) B2S_CUDA(cudaMemcpyAsync(h->dOcc, occupied, (size_t)nf, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dDescB, desc, (size_t)nf * 32, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNB, &nf, 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemsetAsync(h->dTaken, 0, (size_t)nf, st));
+  B2S_CUDA(cudaMemsetAsync(h->dNMatches, 0, 4, st));
+  k_proj_cell_key<<<div_up(nf, 256), 256, 0, st>>>(h->dKpx, h->dKpy, nf, pg, h->dCellKey);
+  k_rank_by_key<<<dim3(div_up(nf, 128), 1), 128, 0, st>>>(h->dCellKey, h->dNB, nf, h->dOrder);
+  k_proj_cell_start<<<div_up(nf + 1, 256), 256, 0, st>>>(h->dCellKey, h->dOrder, nf, h->dCellStart);
+  k_proj_topk<WinQuery><<<div_up(nq, 8), 256, 0, st>>>(dQ, nq, h->dKpx, h->dKpy, h->dOct, h->dURight,
+                                                       useOcc ? h->dOcc : nullptr, h->dDescB, h->dOrder, h->dCellStart, pg,
+                                                       h->dTopk, h->dTopkIdx, h->dCandCnt);
+  // results: dMatch holds best_idx (nq <= maxF entries), dPush holds best_dist
+  if (greedy)
+    k_win_resolve<<<1, 32, 0, st>>>(dQ, nq, th_dist, h->dKpx, h->dKpy, h->dOct, h->dURight, useOcc ? h->dOcc : nullptr,
+                                    h->dDescB, h->dOrder, h->dCellStart, pg, h->dTopk, h->dTopkIdx, h->dCandCnt, h->dTaken,
+                                    h->dMatch, h->dPush, h->dNMatches);
+  else
+    k_win_pick<<<div_up(nq, 256), 256, 0, st>>>(nq, th_dist, h->dTopk, h->dTopkIdx, h->dMatch, h->dPush, h->dNMatches);
+  h->launches += 5;
+  B2S_CUDA(cudaGetLastError());
+  B2S_CUDA(cudaMemcpyAsync(best_idx, h->dMatch, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  if (best_dist) B2S_CUDA(cudaMemcpyAsync(best_dist, h->dPush, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  int acc = 0;
+  B2S_CUDA(cudaMemcpyAsync(&acc, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  if (n_accepted) *n_accepted = acc;
   return B2S_OK;
 }

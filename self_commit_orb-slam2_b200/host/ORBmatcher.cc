@@ -85,4 +85,17 @@ int ORBmatcher::SearchByProjection(const std::vector<b2s_map_query>& mp, const f
   return nm;
 }
 
+int ORBmatcher::SearchWindows(const std::vector<b2s_win_query>& mp, const float* kpx, const float* kpy, const int32_t* octave,
+                              const float* uright, const float* invLevelSigma2, const uint8_t* occupied,
+                              const uint8_t* descriptors, int nF, const b2s_frame_geom& geom, int flags,
+                              std::vector<int32_t>& bestIdx) {
+  Ensure((int)mp.size() > nF ? (int)mp.size() : nF);
+  bestIdx.assign(mp.size(), -1);
+  int n = 0;
+  int rc = b2s_search_windows(mpHandle, mp.data(), (int)mp.size(), kpx, kpy, octave, uright, invLevelSigma2, occupied,
+                              descriptors, nF, &geom, flags, TH_LOW, bestIdx.data(), nullptr, &n);
+  if (rc != B2S_OK) fail("ORBmatcher::SearchWindows", rc);
+  return n;
+}
+
 }  // namespace ORB_SLAM2

@@ -44,6 +44,11 @@ class ORBmatcher {
   int SearchByProjection(const std::vector<b2s_map_query>& mapPoints, const float* kpx, const float* kpy,
                          const int32_t* octave, const float* uright, const uint8_t* occupied, const uint8_t* descriptors,
                          int nFeatures, const b2s_frame_geom& geom, float th, std::vector<int32_t>& matchF);
+  // search core of Fuse(KeyFrame*, vpMapPoints, th) (B2S_WIN_CHI2), Fuse(KeyFrame*, Scw, ...) (no flag) and
+  // SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (B2S_WIN_GREEDY): best keyframe feature per map point
+  int SearchWindows(const std::vector<b2s_win_query>& mapPoints, const float* kpx, const float* kpy, const int32_t* octave,
+                    const float* uright, const float* invLevelSigma2, const uint8_t* occupied, const uint8_t* descriptors,
+                    int nFeatures, const b2s_frame_geom& geom, int flags, std::vector<int32_t>& bestIdx);
 
  protected:
   void Ensure(int n);

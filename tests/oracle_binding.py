@@ -148,6 +148,20 @@ class Oracle:
                                                 P(occupied), P(desc), len(kpx), ctypes.byref(g), th, th_high, nnratio, P(m))
         return n, m
 
+    def search_windows(self, queries, kpx, kpy, octave, uright, inv_level_sigma2, occupied, desc, geom, chi2=False,
+                       greedy=False, th_dist=50):
+        sf = np.ascontiguousarray(geom["scale_factors"], np.float32)
+        g = FrameGeom(geom["mnMinX"], geom["mnMinY"], geom["mnMaxX"], geom["mnMaxY"], geom["bf"], sf.ctypes.data, len(sf))
+        best = np.full(len(queries), -1, np.int32)
+        bdist = np.full(len(queries), 256, np.int32)
+        self.L.orc_search_windows.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp, ctypes.c_int,
+                                              ctypes.c_int, vp, vp]
+        is2 = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+        n = self.L.orc_search_windows(P(queries), len(queries), P(kpx), P(kpy), P(octave), P(uright), P(is2), P(occupied),
+                                      P(desc), len(kpx), ctypes.byref(g), (1 if chi2 else 0) | (2 if greedy else 0), th_dist,
+                                      P(best), P(bdist))
+        return n, best, bdist
+
     def compute_stereo_matches(self, exL, exR, kpsL, descL, kpsR, descR, bf, mb=0.0):
         """exL / exR: OracleExtractor objects that just extracted the left / right image (their pyramids are used)."""
         nl = exL.nlevels

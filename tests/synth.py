@@ -225,3 +225,27 @@ def synth_projection_map(nf=2000, nq=2500, seed=9, w=1241, h=376, cluster=False)
     d = dict(d)
     d["q"] = q
     return d
+
+
+def synth_windows(nf=2000, nq=2500, seed=13, th=3.0, cluster=False):
+    """Keyframe features + projected map points for the Fuse / SearchByProjection(KeyFrame*, Scw, ...) search core."""
+    d = synth_projection(nf=nf, nq=nq, seed=seed, cluster=cluster)
+    rng = np.random.RandomState(seed + 5)
+    q0 = d["q"]
+    qdt = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("radius", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"),
+                    ("valid", "u1"), ("pad", "u1", 3), ("desc", "u1", 32)])
+    q = np.zeros(nq, qdt)
+    # small reprojection offsets so that the chi-square gate passes for some candidates and fails for others
+    q["u"] = (q0["u"] + rng.randint(-15, 16, size=nq).astype(np.float32) / np.float32(10.0)).astype(np.float32)
+    q["v"] = q0["v"]
+    q["desc"] = q0["desc"]
+    invz = np.where(q0["invz"] > 0, q0["invz"], np.float32(0.05)).astype(np.float32)
+    q["ur"] = (q["u"] - d["geom"]["bf"] * invz).astype(np.float32)
+    lvl = q0["octave"].astype(np.int32)
+    q["radius"] = (np.float32(th) * d["geom"]["scale_factors"][lvl]).astype(np.float32)
+    q["min_level"], q["max_level"] = lvl - 1, lvl
+    q["valid"] = (rng.randint(0, 100, size=nq) < 92).astype(np.uint8)
+    d = dict(d)
+    d["q"] = q
+    d["inv_sigma2"] = (np.float32(1.0) / (d["geom"]["scale_factors"] * d["geom"]["scale_factors"])).astype(np.float32)
+    return d

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from synth import synth_descriptors, synth_projection, synth_projection_map
+from synth import synth_descriptors, synth_projection, synth_projection_map, synth_windows
 
 pytestmark = pytest.mark.gpu
 
@@ -139,3 +139,25 @@ def test_search_by_projection_map_edge_cases(pkg, oracle):
     on, om = oracle.search_by_projection_map(d["q"], d["kpx"], d["kpy"], d["octave"], d["uright"], None, d["desc"],
                                              d["geom"], nnratio=0.8)
     assert n == on and np.array_equal(match, om)
+
+
+@pytest.mark.parametrize("chi2,greedy", [(True, False), (False, False), (False, True)])
+@pytest.mark.parametrize("cluster", [False, True])
+def test_search_windows(pkg, oracle, chi2, greedy, cluster):
+    """Search core of Fuse (src/ORBmatcher.cc:1020-1174 with the chi-square gate, :1179-1310 without) and of
+    SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (:388-512, greedy occupancy): identical best feature per
+    map point, distance and accepted count."""
+    d = synth_windows(seed=13 + int(chi2) + 2 * int(greedy), th=3.0 if not cluster else 6.0, cluster=cluster)
+    occ = d["occupied"] if greedy else None
+    m = pkg.ORBmatcher(0.8, True)
+    n, best, bd = m.SearchWindows(d["q"], d["kpx"], d["kpy"], d["octave"], d["uright"], d["inv_sigma2"], occ, d["desc"],
+                                  d["geom"], chi2=chi2, greedy=greedy)
+    on, obest, obd = oracle.search_windows(d["q"], d["kpx"], d["kpy"], d["octave"], d["uright"], d["inv_sigma2"], occ,
+                                           d["desc"], d["geom"], chi2=chi2, greedy=greedy)
+    assert n == on
+    assert np.array_equal(best, obest)
+    assert np.array_equal(bd, obd)
+    assert n > 100
+    if greedy:  # every feature is given to at most one map point
+        used = best[best >= 0]
+        assert len(np.unique(used)) == len(used)

@@ -63,3 +63,12 @@ print("golden fixtures written to", out)
 from test_oracle_stereo import _run as _stereo_run  # noqa: E402
 _, n, ur, dp = _stereo_run(o, 640, 480, 1000, 9, 0.0)
 np.savez_compressed(os.path.join(out, "stereo_640x480_seed9.npz"), n=n, uright=ur, depth=dp)
+# search core of Fuse / SearchByProjection(KeyFrame*, Scw, ...)
+from synth import synth_windows  # noqa: E402
+wout = {}
+for name, (chi2, greedy) in dict(fuse=(True, False), fuse_sim3=(False, False), kf_sim3_greedy=(False, True)).items():
+    wd = synth_windows(seed=13)
+    n, b, bd = o.search_windows(wd["q"], wd["kpx"], wd["kpy"], wd["octave"], wd["uright"], wd["inv_sigma2"],
+                                wd["occupied"] if greedy else None, wd["desc"], wd["geom"], chi2=chi2, greedy=greedy)
+    wout[name + "_n"], wout[name + "_best"], wout[name + "_dist"] = n, b, bd
+np.savez_compressed(os.path.join(out, "windows_seed13.npz"), **wout)
