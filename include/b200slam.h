@@ -217,6 +217,26 @@ int b2s_search_windows(b2s_matcher* h, const b2s_win_query* q, int nq, const flo
                        const uint8_t* desc, int nf, const b2s_frame_geom* g, int flags, int th_dist, int32_t* best_idx,
                        int32_t* best_dist, int* n_accepted);
 
+/* ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, vMatchedPairs, bOnlyStereo)
+ * (src/ORBmatcher.cc:810-1009, CheckDistEpipolarLine :186-215) on flattened keyframes (LocalMapping::CreateNewMapPoints). */
+typedef struct {
+  const uint8_t* desc;    /* mDescriptors, n x 32 */
+  const int32_t* node;    /* DBoW2 FeatureVector node id per feature (mFeatVec) */
+  const uint8_t* has_mp;  /* GetMapPoint(idx) != NULL */
+  const uint8_t* stereo;  /* mvuRight[idx] >= 0 */
+  const float* x;         /* mvKeysUn[idx].pt.x */
+  const float* y;
+  const int32_t* octave;  /* mvKeysUn[idx].octave */
+  const float* angle;     /* mvKeysUn[idx].angle */
+  int32_t n;
+} b2s_kf_features;
+
+/* F12: 3x3 row-major float; (ex, ey): epipole of camera 1 in image 2 (:815-823); scale_factors / level_sigma2:
+ * pKF2->mvScaleFactors / mvLevelSigma2.  match12[idx1] = idx2 or -1 (vMatchedPairs in ascending idx1). HOST buffers. */
+int b2s_search_for_triangulation(b2s_matcher* h, const b2s_kf_features* kf1, const b2s_kf_features* kf2, const float* F12,
+                                 float ex, float ey, const float* scale_factors, const float* level_sigma2, int nlevels,
+                                 int only_stereo, int check_ori, int32_t* match12, int* nmatches);
+
 /* ------------------------------------------------------------------ LocalBA */
 typedef struct {
   int32_t kf;       /* index into Tcw[] */

@@ -350,3 +350,94 @@ extern "C" int orc_search_windows(const orc_win_query* q, int nq, const float* k
   delete grid;
   return n;
 }
+
+// CheckDistEpipolarLine (src/ORBmatcher.cc:186-215)
+static bool check_dist_epipolar_line(float x1, float y1, float x2, float y2, int oct2, const float* F12,
+                                     const float* level_sigma2) {
+  const float a = x1 * F12[0] + y1 * F12[3] + F12[6];
+  const float b = x1 * F12[1] + y1 * F12[4] + F12[7];
+  const float c = x1 * F12[2] + y1 * F12[5] + F12[8];
+  const float num = a * x2 + b * y2 + c;
+  const float den = a * a + b * b;
+  if (den == 0) return false;
+  const float dsqr = num * num / den;
+  return dsqr < 3.84 * level_sigma2[oct2];
+}
+
+// SearchForTriangulation (src/ORBmatcher.cc:810-1009)
+extern "C" int orc_search_for_triangulation(const orc_kf_features* kf1, const orc_kf_features* kf2, const float* F12,
+                                            float ex, float ey, const float* scale_factors, const float* level_sigma2,
+                                            int only_stereo, int check_ori, int32_t* match12) {
+  const int N1 = kf1->n, N2 = kf2->n;
+  const int TH_LOW = 50;  // include/ORBmatcher.h:199
+  // FeatureVector = std::map<NodeId, std::vector<unsigned>> filled in ascending feature index
+  std::map<int, std::vector<int> > fv1, fv2;
+  for (int i = 0; i < N1; i++) fv1[kf1->node[i]].push_back(i);
+  for (int i = 0; i < N2; i++) fv2[kf2->node[i]].push_back(i);
+  int nmatches = 0;
+  std::vector<bool> vbMatched2(N2, false);
+  std::vector<int> vMatches12(N1, -1);
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = HISTO_LENGTH / 360.0f;
+  auto f1it = fv1.begin(), f2it = fv2.begin();
+  while (f1it != fv1.end() && f2it != fv2.end()) {
+    if (f1it->first == f2it->first) {
+      for (size_t i1 = 0; i1 < f1it->second.size(); i1++) {
+        const int idx1 = f1it->second[i1];
+        if (kf1->has_mp[idx1]) continue;  // :852-855
+        const bool bStereo1 = kf1->stereo[idx1] != 0;
+        if (only_stereo && !bStereo1) continue;
+        int bestDist = TH_LOW, bestIdx2 = -1;
+        for (size_t i2 = 0; i2 < f2it->second.size(); i2++) {
+          const int idx2 = f2it->second[i2];
+          if (vbMatched2[idx2] || kf2->has_mp[idx2]) continue;  // :877-878
+          const bool bStereo2 = kf2->stereo[idx2] != 0;
+          if (only_stereo && !bStereo2) continue;
+          const int dist = orc_descriptor_distance(kf1->desc + (size_t)idx1 * 32, kf2->desc + (size_t)idx2 * 32);
+          if (dist > TH_LOW || dist > bestDist) continue;  // :893
+          if (!bStereo1 && !bStereo2) {                    // :899-906
+            const float distex = ex - kf2->x[idx2];
+            const float distey = ey - kf2->y[idx2];
+            if (distex * distex + distey * distey < 100 * scale_factors[kf2->octave[idx2]]) continue;
+          }
+          if (check_dist_epipolar_line(kf1->x[idx1], kf1->y[idx1], kf2->x[idx2], kf2->y[idx2], kf2->octave[idx2], F12,
+                                       level_sigma2)) {
+            bestIdx2 = idx2;
+            bestDist = dist;
+          }
+        }
+        if (bestIdx2 >= 0) {
+          vMatches12[idx1] = bestIdx2;
+          vbMatched2[bestIdx2] = true;
+          nmatches++;
+          if (check_ori) {
+            float rot = kf1->angle[idx1] - kf2->angle[bestIdx2];
+            if (rot < 0.0) rot += 360.0f;
+            int bin = (int)std::round(rot * factor);
+            if (bin == HISTO_LENGTH) bin = 0;
+            rotHist[bin].push_back(idx1);
+          }
+        }
+      }
+      ++f1it;
+      ++f2it;
+    } else if (f1it->first < f2it->first) {
+      f1it = fv1.lower_bound(f2it->first);
+    } else {
+      f2it = fv2.lower_bound(f1it->first);
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (size_t j = 0; j < rotHist[i].size(); j++) {
+        vMatches12[rotHist[i][j]] = -1;
+        nmatches--;
+      }
+    }
+  }
+  for (int i = 0; i < N1; i++) match12[i] = vMatches12[i];
+  return nmatches;
+}

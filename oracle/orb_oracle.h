@@ -134,6 +134,28 @@ int orc_search_windows(const orc_win_query* q, int nq, const float* kpx, const f
                        const float* uright, const float* inv_level_sigma2, const uint8_t* occupied, const uint8_t* desc,
                        int nf, const orc_frame_geom* g, int flags, int th_dist, int32_t* best_idx, int32_t* best_dist);
 
+/* ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, vMatchedPairs, bOnlyStereo)
+ * (src/ORBmatcher.cc:810-1009) + CheckDistEpipolarLine (:186-215) on flattened keyframes.
+ * node: DBoW2 FeatureVector node id per feature (features of a node are visited in ascending feature index, nodes in
+ * ascending id); has_mp: pKF->GetMapPoint(idx) != NULL; stereo: mvuRight[idx] >= 0; x, y, octave, angle: mvKeysUn.
+ * F12: 3x3 row-major float (F12.at<float>(r,c)); ex, ey: epipole of camera 1 in image 2 (:821-823);
+ * scale_factors / level_sigma2: pKF2->mvScaleFactors / mvLevelSigma2.
+ * match12[idx1] = idx2 or -1 (the vMatchedPairs list in ascending idx1). Returns nmatches. */
+typedef struct {
+  const uint8_t* desc;
+  const int32_t* node;
+  const uint8_t* has_mp;
+  const uint8_t* stereo;
+  const float* x;
+  const float* y;
+  const int32_t* octave;
+  const float* angle;
+  int32_t n;
+} orc_kf_features;
+int orc_search_for_triangulation(const orc_kf_features* kf1, const orc_kf_features* kf2, const float* F12, float ex, float ey,
+                                 const float* scale_factors, const float* level_sigma2, int only_stereo, int check_ori,
+                                 int32_t* match12);
+
 /* Frame::ComputeStereoMatches (src/Frame.cc:1026-1421): row-band candidates, Hamming best (< (TH_HIGH+TH_LOW)/2),
  * 11x11 L1 block matching over +-5 px on the keypoint's pyramid level, parabola sub-pixel fit, median*2.1 cull.
  * kps: level-0 coordinates as produced by the extractor; pyr*: dense level images (stride = width), lvlW/lvlH their

@@ -47,6 +47,12 @@ class _FrameGeom(ctypes.Structure):
                 ("mnMaxY", ctypes.c_float), ("bf", ctypes.c_float), ("scale_factors", _vp), ("nlevels", ctypes.c_int)]
 
 
+class _KfFeatures(ctypes.Structure):
+    _fields_ = [("desc", ctypes.c_void_p), ("node", ctypes.c_void_p), ("has_mp", ctypes.c_void_p),
+                ("stereo", ctypes.c_void_p), ("x", ctypes.c_void_p), ("y", ctypes.c_void_p), ("octave", ctypes.c_void_p),
+                ("angle", ctypes.c_void_p), ("n", ctypes.c_int32)]
+
+
 class _BaProblem(ctypes.Structure):
     _fields_ = [("n_kf", ctypes.c_int), ("n_local", ctypes.c_int), ("Tcw", _vp), ("fixed", _vp), ("n_mp", ctypes.c_int),
                 ("points", _vp), ("n_edges", ctypes.c_int), ("edges", _vp), ("fx", ctypes.c_float),
@@ -345,6 +351,34 @@ class ORBmatcher:
                                     _p(occupied), _p(desc), nf, ctypes.byref(g), (1 if chi2 else 0) | (2 if greedy else 0),
                                     th_dist, _p(best), _p(bdist), ctypes.byref(nacc)))
         return nacc.value, best, bdist
+
+
+    def SearchForTriangulation(self, kf1, kf2, F12, ex, ey, scale_factors, level_sigma2, only_stereo=False):
+        """ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:810-1009). kf1/kf2: dicts with desc, node, has_mp, stereo,
+        x, y, octave, angle.  Returns (nmatches, match12)."""
+        keep = []
+
+        def side(k):
+            arrs = [np.ascontiguousarray(k["desc"], np.uint8), np.ascontiguousarray(k["node"], np.int32),
+                    np.ascontiguousarray(k["has_mp"], np.uint8), np.ascontiguousarray(k["stereo"], np.uint8),
+                    np.ascontiguousarray(k["x"], np.float32), np.ascontiguousarray(k["y"], np.float32),
+                    np.ascontiguousarray(k["octave"], np.int32), np.ascontiguousarray(k["angle"], np.float32)]
+            keep.append(arrs)
+            return _KfFeatures(*[a.ctypes.data for a in arrs], len(arrs[0]))
+
+        a, b = side(kf1), side(kf2)
+        F = np.ascontiguousarray(F12, np.float32).reshape(9)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        s2 = np.ascontiguousarray(level_sigma2, np.float32)
+        match12 = np.full(a.n, -1, np.int32)
+        nm = ctypes.c_int(0)
+        L = lib()
+        L.b2s_search_for_triangulation.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp,
+                                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]
+        _check(L.b2s_search_for_triangulation(self._h, ctypes.byref(a), ctypes.byref(b), _p(F), float(ex), float(ey), _p(sf),
+                                              _p(s2), len(sf), int(only_stereo), int(self.mbCheckOrientation),
+                                              _p(match12), ctypes.byref(nm)))
+        return nm.value, match12
 
 
 class Optimizer:

@@ -756,6 +756,92 @@ __global__ void __launch_bounds__(32) k_proj_resolve(const ProjQuery* __restrict
   if (lane < HISTO) histOut[lane] = hist[lane];
 }
 
+// ------------------------------------------------------------------------------------------------
+// SearchForTriangulation (src/ORBmatcher.cc:810-1009): per vocabulary node, greedy in keyframe-1 feature order; the
+// candidates of a row are the unmatched keyframe-2 features of the node without a MapPoint that pass the distance,
+// epipole and epipolar-line gates; `dist > bestDist -> continue` (:893) makes the LAST minimum win.
+// One warp per node: rows sequential, lanes over the node's keyframe-2 features (a node holds tens of features with a
+// real vocabulary; nothing here is shared between nodes).
+// ------------------------------------------------------------------------------------------------
+struct TriParams {
+  float F12[9];
+  float ex, ey;
+  float scale[16], sigma2[16];
+  int thLow, checkOri;
+};
+__device__ __forceinline__ bool tri_epipolar_ok(float x1, float y1, float x2, float y2, int oct2, const TriParams& tp) {
+  // CheckDistEpipolarLine (:186-215), float arithmetic in source order (this file is built with --fmad=false)
+  const float a = __fadd_rn(__fadd_rn(__fmul_rn(x1, tp.F12[0]), __fmul_rn(y1, tp.F12[3])), tp.F12[6]);
+  const float b = __fadd_rn(__fadd_rn(__fmul_rn(x1, tp.F12[1]), __fmul_rn(y1, tp.F12[4])), tp.F12[7]);
+  const float c = __fadd_rn(__fadd_rn(__fmul_rn(x1, tp.F12[2]), __fmul_rn(y1, tp.F12[5])), tp.F12[8]);
+  const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, x2), __fmul_rn(b, y2)), c);
+  const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+  if (den == 0) return false;
+  const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+  return (double)dsqr < 3.84 * (double)tp.sigma2[min(max(oct2, 0), 15)];
+}
+__global__ void __launch_bounds__(128) k_tri_match(const uint8_t* __restrict__ descA, const int32_t* __restrict__ nodeA,
+                                                   const uint8_t* __restrict__ eligA, const uint8_t* __restrict__ stereoA,
+                                                   const float* __restrict__ xA, const float* __restrict__ yA,
+                                                   const float* __restrict__ angA, int nA,
+                                                   const int32_t* __restrict__ orderA, const uint8_t* __restrict__ descB,
+                                                   const int32_t* __restrict__ nodeB, const uint8_t* __restrict__ eligB,
+                                                   const uint8_t* __restrict__ stereoB, const float* __restrict__ xB,
+                                                   const float* __restrict__ yB, const int32_t* __restrict__ octB,
+                                                   const float* __restrict__ angB, int nB,
+                                                   const int32_t* __restrict__ orderB, TriParams tp, int32_t* matchB,
+                                                   int32_t* __restrict__ binB) {
+  const int lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r0 >= nA) return;
+  const int node = nodeA[orderA[r0]];
+  if (r0 > 0 && nodeA[orderA[r0 - 1]] == node) return;  // not the head of a node segment
+  // keyframe-2 segment of the node: lower bound in the (node, index)-sorted order
+  int lo = 0, hi = nB;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (nodeB[orderB[mid]] < node) lo = mid + 1;
+    else hi = mid;
+  }
+  const int bBeg = lo;
+  int bEnd = bBeg;
+  while (bEnd < nB && nodeB[orderB[bEnd]] == node) bEnd++;
+  if (bEnd == bBeg) return;
+  for (int r = r0; r < nA; r++) {
+    const int i = orderA[r];
+    if (nodeA[i] != node) break;
+    if (!eligA[i]) continue;  // has a MapPoint / not stereo when bOnlyStereo (:852-861)
+    const u256 da = ld_desc(descA, i);
+    const bool st1 = stereoA[i] != 0;
+    const float x1 = xA[i], y1 = yA[i];
+    uint32_t best = EMPTY;
+    for (int p = bBeg + lane; p < bEnd; p += 32) {
+      const int j = orderB[p];
+      if (!eligB[j] || __ldcg(&matchB[j]) >= 0) continue;  // :877-885
+      const int d = hamming256(da, ld_desc(descB, j));
+      if (d > tp.thLow) continue;  // :893
+      const float x2 = xB[j], y2 = yB[j];
+      const int o2 = octB[j];
+      if (!st1 && !stereoB[j]) {  // :899-906
+        const float dx = __fsub_rn(tp.ex, x2), dy = __fsub_rn(tp.ey, y2);
+        if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, tp.scale[min(max(o2, 0), 15)])) continue;
+      }
+      if (!tri_epipolar_ok(x1, y1, x2, y2, o2, tp)) continue;
+      best = min(best, ((uint32_t)d << 16) | (uint32_t)(0xFFFF - (p - bBeg)));  // smallest distance, LAST in node order
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (best != EMPTY) {
+      const int j = orderB[bBeg + (0xFFFF - (int)(best & 0xFFFFu))];
+      if (lane == 0) {
+        matchB[j] = i;  // vMatches12[idx1] = bestIdx2; vbMatched2[bestIdx2] = true (:913-916)
+        binB[j] = tp.checkOri ? rot_bin(angA[i], angB[j]) : 0;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // Window search without occupancy (Fuse): the queries are independent, the answer is the head of each K-list.
 __global__ void __launch_bounds__(256) k_win_pick(int nq, int thDist, const uint32_t* __restrict__ topk,
                                                   const int32_t* __restrict__ topkIdx, int32_t* __restrict__ bestIdx,
@@ -1285,5 +1371,68 @@ extern "C" int b2s_search_windows(b2s_matcher* h, const b2s_win_query* q, int nq
   B2S_CUDA(cudaMemcpyAsync(&acc, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaStreamSynchronize(st));
   if (n_accepted) *n_accepted = acc;
+  return B2S_OK;
+}
+
+extern "C" int b2s_search_for_triangulation(b2s_matcher* h, const b2s_kf_features* kf1, const b2s_kf_features* kf2,
+                                            const float* F12, float ex, float ey, const float* scale_factors,
+                                            const float* level_sigma2, int nlevels, int only_stereo, int check_ori,
+                                            int32_t* match12, int* nmatches) {
+  if (!h || !kf1 || !kf2 || !F12 || !scale_factors || !level_sigma2 || nlevels < 1 || nlevels > 16 || !match12 ||
+      !nmatches || kf1->n < 0 || kf2->n < 0 || kf1->n > h->maxF || kf2->n > h->maxF) {
+    set_error("b2s_search_for_triangulation: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  const int nA = kf1->n, nB = kf2->n;
+  *nmatches = 0;
+  for (int i = 0; i < nA; i++) match12[i] = -1;
+  if (nA == 0 || nB == 0) return B2S_OK;
+  for (const b2s_kf_features* k : {kf1, kf2})
+    if (!k->desc || !k->node || !k->has_mp || !k->stereo || !k->x || !k->y || !k->octave || !k->angle) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  // eligibility on the host: no MapPoint, and a stereo observation when bOnlyStereo (:852-861, :877-885)
+  std::vector<uint8_t> eA(nA), eB(nB);
+  for (int i = 0; i < nA; i++) eA[i] = !kf1->has_mp[i] && (!only_stereo || kf1->stereo[i]);
+  for (int j = 0; j < nB; j++) eB[j] = !kf2->has_mp[j] && (!only_stereo || kf2->stereo[j]);
+  TriParams tp;
+  memset(&tp, 0, sizeof(tp));
+  for (int k = 0; k < 9; k++) tp.F12[k] = F12[k];
+  tp.ex = ex; tp.ey = ey; tp.thLow = 50; tp.checkOri = check_ori;
+  for (int l = 0; l < nlevels; l++) {
+    tp.scale[l] = scale_factors[l];
+    tp.sigma2[l] = level_sigma2[l];
+  }
+  const size_t F = (size_t)h->maxF * h->maxBatch;
+  float* scratch = reinterpret_cast<float*>(h->dQueries);  // 16 floats per feature slot
+  float *dxA = scratch, *dyA = scratch + F, *dxB = scratch + 2 * F, *dyB = scratch + 3 * F;
+  uint8_t* dStA = reinterpret_cast<uint8_t*>(scratch + 4 * F);
+  uint8_t* dStB = dStA + F;
+  int32_t* dOrderB = h->dCandCnt;
+  auto up = [&](void* d, const void* s, size_t bytes) { return cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, st); };
+  B2S_CUDA(up(h->dDescA, kf1->desc, (size_t)nA * 32)); B2S_CUDA(up(h->dDescB, kf2->desc, (size_t)nB * 32));
+  B2S_CUDA(up(h->dNodeA, kf1->node, (size_t)nA * 4)); B2S_CUDA(up(h->dNodeB, kf2->node, (size_t)nB * 4));
+  B2S_CUDA(up(h->dValidA, eA.data(), nA)); B2S_CUDA(up(h->dValidB, eB.data(), nB));
+  B2S_CUDA(up(dStA, kf1->stereo, nA)); B2S_CUDA(up(dStB, kf2->stereo, nB));
+  B2S_CUDA(up(dxA, kf1->x, (size_t)nA * 4)); B2S_CUDA(up(dyA, kf1->y, (size_t)nA * 4));
+  B2S_CUDA(up(dxB, kf2->x, (size_t)nB * 4)); B2S_CUDA(up(dyB, kf2->y, (size_t)nB * 4));
+  B2S_CUDA(up(h->dOct, kf2->octave, (size_t)nB * 4));
+  B2S_CUDA(up(h->dAngA, kf1->angle, (size_t)nA * 4)); B2S_CUDA(up(h->dAngB, kf2->angle, (size_t)nB * 4));
+  B2S_CUDA(up(h->dNA, &nA, 4)); B2S_CUDA(up(h->dNB, &nB, 4));
+  k_fill_i32<<<div_up(nB, 256), 256, 0, st>>>(h->dMatch, -1, (size_t)nB);
+  k_rank_by_key<<<dim3(div_up(nA, 128), 1), 128, 0, st>>>(h->dNodeA, h->dNA, nA, h->dOrder);
+  k_rank_by_key<<<dim3(div_up(nB, 128), 1), 128, 0, st>>>(h->dNodeB, h->dNB, nB, dOrderB);
+  k_tri_match<<<div_up(nA, 4), 128, 0, st>>>(h->dDescA, h->dNodeA, h->dValidA, dStA, dxA, dyA, h->dAngA, nA, h->dOrder,
+                                            h->dDescB, h->dNodeB, h->dValidB, dStB, dxB, dyB, h->dOct, h->dAngB, nB,
+                                            dOrderB, tp, h->dMatch, h->dBin);
+  k_rot_cull<<<1, 256, 0, st>>>(h->dNB, nB, check_ori, h->dMatch, h->dBin, nullptr, h->dNMatches);
+  h->launches += 5;
+  B2S_CUDA(cudaGetLastError());
+  std::vector<int32_t> mB(nB);
+  B2S_CUDA(cudaMemcpyAsync(mB.data(), h->dMatch, (size_t)nB * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  for (int j = 0; j < nB; j++)
+    if (mB[j] >= 0) match12[mB[j]] = j;  // every keyframe-2 feature is matched at most once (vbMatched2)
   return B2S_OK;
 }

@@ -98,4 +98,20 @@ int ORBmatcher::SearchWindows(const std::vector<b2s_win_query>& mp, const float*
   return n;
 }
 
+int ORBmatcher::SearchForTriangulation(const b2s_kf_features& kf1, const b2s_kf_features& kf2, const float F12[9], float ex,
+                                       float ey, const float* scaleFactors2, const float* levelSigma2_2, int nLevels,
+                                       bool bOnlyStereo, std::vector<std::pair<size_t, size_t> >& vMatchedPairs) {
+  Ensure(kf1.n > kf2.n ? kf1.n : kf2.n);
+  std::vector<int32_t> m12(kf1.n > 0 ? kf1.n : 1, -1);
+  int nm = 0;
+  int rc = b2s_search_for_triangulation(mpHandle, &kf1, &kf2, F12, ex, ey, scaleFactors2, levelSigma2_2, nLevels,
+                                        bOnlyStereo, mbCheckOrientation, m12.data(), &nm);
+  if (rc != B2S_OK) fail("ORBmatcher::SearchForTriangulation", rc);
+  vMatchedPairs.clear();
+  vMatchedPairs.reserve(nm);
+  for (int i = 0; i < kf1.n; i++)
+    if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m12[i]));  // :999-1005
+  return nm;
+}
+
 }  // namespace ORB_SLAM2

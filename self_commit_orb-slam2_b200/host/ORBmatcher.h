@@ -2,6 +2,7 @@
 // views (the Frame/KeyFrame/MapPoint pointer graph is gathered by the caller-side adapters shown in INTEGRATION.md).
 #pragma once
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200slam.h"
@@ -49,6 +50,11 @@ class ORBmatcher {
   int SearchWindows(const std::vector<b2s_win_query>& mapPoints, const float* kpx, const float* kpy, const int32_t* octave,
                     const float* uright, const float* invLevelSigma2, const uint8_t* occupied, const uint8_t* descriptors,
                     int nFeatures, const b2s_frame_geom& geom, int flags, std::vector<int32_t>& bestIdx);
+  // SearchForTriangulation(KeyFrame*, KeyFrame*, F12, vMatchedPairs, bOnlyStereo) on flattened keyframes; returns the
+  // pairs (idx1, idx2) in ascending idx1 like the reference's vMatchedPairs
+  int SearchForTriangulation(const b2s_kf_features& kf1, const b2s_kf_features& kf2, const float F12[9], float ex, float ey,
+                             const float* scaleFactors2, const float* levelSigma2_2, int nLevels, bool bOnlyStereo,
+                             std::vector<std::pair<size_t, size_t> >& vMatchedPairs);
 
  protected:
   void Ensure(int n);

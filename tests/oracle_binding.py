@@ -148,6 +148,32 @@ class Oracle:
                                                 P(occupied), P(desc), len(kpx), ctypes.byref(g), th, th_high, nnratio, P(m))
         return n, m
 
+    def search_for_triangulation(self, kf1, kf2, F12, ex, ey, scale_factors, level_sigma2, only_stereo=False,
+                                 check_ori=True):
+        class KF(ctypes.Structure):
+            _fields_ = [("desc", vp), ("node", vp), ("has_mp", vp), ("stereo", vp), ("x", vp), ("y", vp), ("octave", vp),
+                        ("angle", vp), ("n", ctypes.c_int32)]
+        keep = []
+
+        def side(k):
+            arrs = [np.ascontiguousarray(k["desc"], np.uint8), np.ascontiguousarray(k["node"], np.int32),
+                    np.ascontiguousarray(k["has_mp"], np.uint8), np.ascontiguousarray(k["stereo"], np.uint8),
+                    np.ascontiguousarray(k["x"], np.float32), np.ascontiguousarray(k["y"], np.float32),
+                    np.ascontiguousarray(k["octave"], np.int32), np.ascontiguousarray(k["angle"], np.float32)]
+            keep.append(arrs)
+            return KF(*[a.ctypes.data for a in arrs], len(arrs[0]))
+
+        a, b = side(kf1), side(kf2)
+        F = np.ascontiguousarray(F12, np.float32).reshape(9)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        s2 = np.ascontiguousarray(level_sigma2, np.float32)
+        m = np.full(a.n, -1, np.int32)
+        self.L.orc_search_for_triangulation.argtypes = [vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, ctypes.c_int,
+                                                        ctypes.c_int, vp]
+        n = self.L.orc_search_for_triangulation(ctypes.byref(a), ctypes.byref(b), P(F), ex, ey, P(sf), P(s2),
+                                                int(only_stereo), int(check_ori), P(m))
+        return n, m
+
     def search_windows(self, queries, kpx, kpy, octave, uright, inv_level_sigma2, occupied, desc, geom, chi2=False,
                        greedy=False, th_dist=50):
         sf = np.ascontiguousarray(geom["scale_factors"], np.float32)

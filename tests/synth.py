@@ -249,3 +249,66 @@ def synth_windows(nf=2000, nq=2500, seed=13, th=3.0, cluster=False):
     d["q"] = q
     d["inv_sigma2"] = (np.float32(1.0) / (d["geom"]["scale_factors"] * d["geom"]["scale_factors"])).astype(np.float32)
     return d
+
+
+def synth_triangulation(n=2000, seed=17, n_nodes=100, w=1241, h=376):
+    """Two keyframes observing the same 3-D points (SearchForTriangulation, src/ORBmatcher.cc:810): keypoints scattered
+    around the true projections, F12 / epipole computed like LocalMapping::ComputeF12 (src/LocalMapping.cc:1009-1035)."""
+    rng = np.random.RandomState(seed)
+    fx = fy = 718.856
+    cx, cy = 607.1928, 185.2157
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    scale = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+    sigma2 = (scale * scale).astype(np.float32)
+    yaw = np.deg2rad(3.0)
+    R2 = np.array([[np.cos(yaw), 0, -np.sin(yaw)], [0, 1, 0], [np.sin(yaw), 0, np.cos(yaw)]])
+    c2 = np.array([0.6, 0.02, 1.1])  # camera-2 centre in the frame of camera 1 (= world)
+    t2 = -R2 @ c2
+    R1, t1 = np.eye(3), np.zeros(3)
+    R12 = R1 @ R2.T
+    t12 = -R1 @ R2.T @ t2 + t1
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+    F12 = (np.linalg.inv(K).T @ tx @ R12 @ np.linalg.inv(K)).astype(np.float32)
+    C2 = R2 @ np.zeros(3) + t2  # camera-1 centre in camera-2 coordinates
+    ex = np.float32(fx * C2[0] / C2[2] + cx)
+    ey = np.float32(fy * C2[1] / C2[2] + cy)
+    z = rng.uniform(4, 60, size=n)
+    u = rng.uniform(20, w - 20, size=n)
+    v = rng.uniform(20, h - 20, size=n)
+    X = np.stack([(u - cx) * z / fx, (v - cy) * z / fy, z], 1)
+    X2 = (R2 @ X.T).T + t2
+    u2 = fx * X2[:, 0] / X2[:, 2] + cx
+    v2 = fy * X2[:, 1] / X2[:, 2] + cy
+    octv = rng.randint(0, 8, size=n).astype(np.int32)
+    noise = scale[octv].astype(np.float64)
+
+    def kf(uu, vv, perm, flip_max):
+        d = dict()
+        d["x"] = (uu + rng.normal(0, 0.7, n) * noise).astype(np.float32)[perm]
+        d["y"] = (vv + rng.normal(0, 0.7, n) * noise).astype(np.float32)[perm]
+        # a fraction of gross outliers off the epipolar line
+        bad = rng.randint(0, 100, size=n) < 15
+        d["y"] = np.where(bad, d["y"] + np.float32(25.0), d["y"]).astype(np.float32)
+        d["octave"] = np.clip(octv + rng.randint(-1, 2, size=n), 0, 7).astype(np.int32)[perm]
+        d["angle"] = ((base_angle + rng.normal(0, 4, n)) % 360.0).astype(np.float32)[perm]
+        dd = base_desc.copy()
+        for i in range(n):
+            for b in rng.choice(256, size=int(rng.randint(0, flip_max)), replace=False):
+                dd[i, b >> 3] ^= np.uint8(1 << (b & 7))
+        d["desc"] = dd[perm]
+        d["node"] = base_node[perm].astype(np.int32)
+        d["has_mp"] = (rng.randint(0, 100, size=n) < 35).astype(np.uint8)
+        d["stereo"] = (rng.randint(0, 100, size=n) < 70).astype(np.uint8)
+        return d
+
+    base_angle = rng.uniform(0, 360, n)
+    base_desc = rng.randint(0, 256, size=(n, 32)).astype(np.uint8)
+    base_node = rng.randint(0, n_nodes, size=n)
+    # near-duplicate descriptors inside a node so that ties and contention for the same feature occur
+    dup = rng.randint(0, 100, size=n) < 20
+    for i in np.nonzero(dup)[0]:
+        same = np.nonzero(base_node == base_node[i])[0]
+        base_desc[i] = base_desc[same[0]]
+    kf1 = kf(u, v, np.arange(n), 20)
+    kf2 = kf(u2, v2, rng.permutation(n), 25)
+    return dict(kf1=kf1, kf2=kf2, F12=F12, ex=ex, ey=ey, scale=scale, sigma2=sigma2)

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from synth import synth_descriptors, synth_projection, synth_projection_map, synth_windows
+from synth import synth_descriptors, synth_projection, synth_projection_map, synth_triangulation, synth_windows
 
 pytestmark = pytest.mark.gpu
 
@@ -161,3 +161,21 @@ def test_search_windows(pkg, oracle, chi2, greedy, cluster):
     if greedy:  # every feature is given to at most one map point
         used = best[best >= 0]
         assert len(np.unique(used)) == len(used)
+
+
+@pytest.mark.parametrize("only_stereo", [False, True])
+@pytest.mark.parametrize("n_nodes", [100, 7])
+def test_search_for_triangulation(pkg, oracle, only_stereo, n_nodes):
+    """ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:810-1009): identical vMatches12 and count (greedy per node,
+    last-minimum tie rule, epipole and epipolar-line gates, rotation consistency)."""
+    d = synth_triangulation(seed=17 + n_nodes, n_nodes=n_nodes)
+    m = pkg.ORBmatcher(0.6, True)
+    n, m12 = m.SearchForTriangulation(d["kf1"], d["kf2"], d["F12"], d["ex"], d["ey"], d["scale"], d["sigma2"],
+                                      only_stereo=only_stereo)
+    on, om12 = oracle.search_for_triangulation(d["kf1"], d["kf2"], d["F12"], float(d["ex"]), float(d["ey"]), d["scale"],
+                                               d["sigma2"], only_stereo=only_stereo)
+    assert n == on
+    assert np.array_equal(m12, om12)
+    assert n > 100
+    used = m12[m12 >= 0]
+    assert len(np.unique(used)) == len(used)

@@ -72,3 +72,8 @@ for name, (chi2, greedy) in dict(fuse=(True, False), fuse_sim3=(False, False), k
                                 wd["occupied"] if greedy else None, wd["desc"], wd["geom"], chi2=chi2, greedy=greedy)
     wout[name + "_n"], wout[name + "_best"], wout[name + "_dist"] = n, b, bd
 np.savez_compressed(os.path.join(out, "windows_seed13.npz"), **wout)
+# SearchForTriangulation
+from synth import synth_triangulation  # noqa: E402
+td = synth_triangulation(seed=117, n_nodes=100)
+n, m = o.search_for_triangulation(td["kf1"], td["kf2"], td["F12"], float(td["ex"]), float(td["ey"]), td["scale"], td["sigma2"])
+np.savez_compressed(os.path.join(out, "triangulation_seed117.npz"), n=n, match12=m)
