@@ -276,6 +276,30 @@ int b2s_local_ba(b2s_ba_solver* h, const b2s_ba_problem* p, const volatile uint8
 /* `batch` independent windows solved concurrently (replicas). */
 int b2s_local_ba_batch(b2s_ba_solver* h, int batch, const b2s_ba_problem* p, b2s_ba_result* r);
 
+/* ------------------------------------------------------------------ PoseOptimization */
+/* Optimizer::PoseOptimization(Frame*) (src/Optimizer.cc:363-605) from graph construction to SetPose / mvbOutlier. */
+typedef struct {
+  const float* Tcw;        /* pFrame->mTcw, 16 floats row-major */
+  int32_t n;               /* pFrame->N */
+  const uint8_t* has_mp;   /* pFrame->mvpMapPoints[i] != NULL */
+  const float* Xw;         /* pMP->GetWorldPos(), n x 3 (ignored where has_mp == 0) */
+  const float* kpx;        /* mvKeysUn[i].pt.x */
+  const float* kpy;
+  const float* uright;     /* mvuRight[i]; < 0: monocular edge (:418) */
+  const float* inv_sigma2; /* mvInvLevelSigma2[mvKeysUn[i].octave] */
+  float fx, fy, cx, cy, bf;
+} b2s_pose_problem;
+typedef struct {
+  float* Tcw_out;     /* 16 floats: the pose handed to pFrame->SetPose (:600-603) */
+  uint8_t* outlier;   /* n: pFrame->mvbOutlier */
+  int32_t* trace;     /* optional (>= 256): accept(1)/reject(0) per LM trial, -1 terminated */
+  int32_t n_inliers;  /* return value: nInitialCorrespondences - nBad (:605) */
+  int32_t n_trials;
+} b2s_pose_result;
+/* The handle is the LocalBA solver handle (b2s_ba_create); frames of a batch are independent (one CTA each). */
+int b2s_pose_optimization(b2s_ba_solver* h, const b2s_pose_problem* p, b2s_pose_result* r);
+int b2s_pose_optimization_batch(b2s_ba_solver* h, int batch, const b2s_pose_problem* p, b2s_pose_result* r);
+
 #ifdef __cplusplus
 }
 #endif

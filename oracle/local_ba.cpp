@@ -595,7 +595,269 @@ struct BA {
     return 0;
   }
 };
+
+// ------------------------------------------------------------------------------------------------
+// Optimizer::PoseOptimization (src/Optimizer.cc:363-605): one free SE3 vertex, unary edges
+// EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose (types_six_dof_expmap.h:143-205, .cpp:266-364) with fixed
+// map points, BlockSolver_6_3 + LinearSolverDense (6x6 LDLT), Levenberg; 4 rounds of 10 iterations from the SAME
+// initial pose, inlier/outlier re-classification after every round, Huber kernels dropped after round 2.
+// ------------------------------------------------------------------------------------------------
+struct PO {
+  const orc_pose_problem* P;
+  Pose pose;
+  std::vector<int> edges;      // feature index per edge (insertion order = ascending feature index, :414-487)
+  std::vector<uint8_t> level;  // per edge
+  std::vector<double> err, chi2;
+  bool robust = true;
+  double delta_mono, delta_stereo;
+  double H[36], b[6], x[6];
+  double lambda = -1, ni = 2;
+  int nBadLM = 0;
+  std::vector<int32_t> trace;
+  int n_trials = 0;
+
+  bool is_stereo(int f) const { return !(P->uright[f] < 0); }  // :418 mvuRight<0 => monocular edge
+
+  void compute_error(int e) {  // computeError, types_six_dof_expmap.h:153-157 / :184-188; cam_project .cpp:295-312
+    const int f = edges[e];
+    const double Xw[3] = {(double)P->Xw[f * 3], (double)P->Xw[f * 3 + 1], (double)P->Xw[f * 3 + 2]};
+    double Xc[3];
+    pose_map(pose, Xw, Xc);
+    double* er = &err[(size_t)e * 3];
+    const double w = (double)P->inv_sigma2[f];
+    if (is_stereo(f)) {
+      const float invz = (float)(1.0f / Xc[2]);
+      const double u = Xc[0] * invz * (double)P->fx + (double)P->cx;
+      const double v = Xc[1] * invz * (double)P->fy + (double)P->cy;
+      const double ur = u - (double)P->bf * invz;  // `double bf` member times float invz (.cpp:310)
+      er[0] = (double)P->kpx[f] - u;
+      er[1] = (double)P->kpy[f] - v;
+      er[2] = (double)P->uright[f] - ur;
+      chi2[e] = er[0] * (w * er[0]) + er[1] * (w * er[1]) + er[2] * (w * er[2]);
+    } else {
+      const double u = Xc[0] / Xc[2] * (double)P->fx + (double)P->cx;
+      const double v = Xc[1] / Xc[2] * (double)P->fy + (double)P->cy;
+      er[0] = (double)P->kpx[f] - u;
+      er[1] = (double)P->kpy[f] - v;
+      er[2] = 0;
+      chi2[e] = er[0] * (w * er[0]) + er[1] * (w * er[1]);
+    }
+  }
+  void compute_active_errors() {
+    for (size_t e = 0; e < edges.size(); e++)
+      if (!level[e]) compute_error((int)e);
+  }
+  static void huber(double e, double delta, double& rho0, double& rho1) {
+    const double dsqr = delta * delta;
+    if (e <= dsqr) {
+      rho0 = e;
+      rho1 = 1.;
+    } else {
+      const double sqrte = std::sqrt(e);
+      rho0 = 2 * sqrte * delta - dsqr;
+      rho1 = delta / sqrte;
+    }
+  }
+  double active_robust_chi2() const {
+    double chi = 0;
+    for (size_t e = 0; e < edges.size(); e++) {
+      if (level[e]) continue;
+      if (robust) {
+        double r0, r1;
+        huber(chi2[e], is_stereo(edges[e]) ? delta_stereo : delta_mono, r0, r1);
+        chi += r0;
+      } else
+        chi += chi2[e];
+    }
+    return chi;
+  }
+  void build_system() {  // linearizeOplus (.cpp:266-290, :335-364) + BaseUnaryEdge::constructQuadraticForm
+    for (double& v : H) v = 0;
+    for (double& v : b) v = 0;
+    const double fx = P->fx, fy = P->fy, bf = P->bf;
+    for (size_t e = 0; e < edges.size(); e++) {
+      if (level[e]) continue;
+      const int f = edges[e];
+      const double Xw[3] = {(double)P->Xw[f * 3], (double)P->Xw[f * 3 + 1], (double)P->Xw[f * 3 + 2]};
+      double Xc[3];
+      pose_map(pose, Xw, Xc);
+      const double x = Xc[0], y = Xc[1];
+      const double invz = 1.0 / Xc[2], invz_2 = invz * invz;
+      const bool st = is_stereo(f);
+      const int D = st ? 3 : 2;
+      double B[3][6];
+      B[0][0] = x * y * invz_2 * fx;
+      B[0][1] = -(1 + (x * x * invz_2)) * fx;
+      B[0][2] = y * invz * fx;
+      B[0][3] = -invz * fx;
+      B[0][4] = 0;
+      B[0][5] = x * invz_2 * fx;
+      B[1][0] = (1 + y * y * invz_2) * fy;
+      B[1][1] = -x * y * invz_2 * fy;
+      B[1][2] = -x * invz * fy;
+      B[1][3] = 0;
+      B[1][4] = -invz * fy;
+      B[1][5] = y * invz_2 * fy;
+      if (st) {
+        B[2][0] = B[0][0] - bf * y * invz_2;
+        B[2][1] = B[0][1] + bf * x * invz_2;
+        B[2][2] = B[0][2];
+        B[2][3] = B[0][3];
+        B[2][4] = 0;
+        B[2][5] = B[0][5] - bf * invz_2;
+      } else {
+        for (int c = 0; c < 6; c++) B[2][c] = 0;
+      }
+      const double w0 = (double)P->inv_sigma2[f];
+      double rho1 = 1.0;
+      if (robust) {
+        double r0;
+        huber(chi2[e], st ? delta_stereo : delta_mono, r0, rho1);
+      }
+      const double* er = &err[e * 3];
+      double omega_r[3];
+      for (int r = 0; r < 3; r++) omega_r[r] = -(w0 * er[r]) * rho1;
+      const double w = rho1 * w0;
+      for (int i = 0; i < 6; i++) {
+        double s = 0;
+        for (int r = 0; r < D; r++) s += B[r][i] * omega_r[r];
+        b[i] += s;
+        for (int j = 0; j < 6; j++) {
+          double h = 0;
+          for (int r = 0; r < D; r++) h += B[r][i] * w * B[r][j];
+          H[i * 6 + j] += h;
+        }
+      }
+    }
+  }
+  bool solve(double lam) {
+    std::vector<double> S(36);
+    for (int r = 0; r < 6; r++)
+      for (int c = 0; c < 6; c++) S[r * 6 + c] = H[r * 6 + c] + (r == c ? lam : 0.0);
+    return chol_solve(S, 6, b, x);
+  }
+  int n_active() const {
+    int n = 0;
+    for (uint8_t l : level) n += !l;
+    return n;
+  }
+  void optimize(int iterations) {  // SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve (as in BA::optimize)
+    if (n_active() == 0) return;
+    bool ok = true;
+    for (int it = 0; it < iterations && ok; it++) {
+      compute_active_errors();
+      double currentChi = active_robust_chi2();
+      double tempChi = currentChi;
+      const double iniChi = currentChi;
+      build_system();
+      if (it == 0) {
+        double mx = 0;
+        for (int j = 0; j < 6; j++) mx = std::max(std::fabs(H[j * 7]), mx);
+        lambda = 1e-5 * mx;
+        ni = 2;
+        nBadLM = 0;
+      }
+      double rho = 0;
+      int qmax = 0;
+      do {
+        const Pose backup = pose;
+        const bool ok2 = solve(lambda);
+        if (ok2) pose_oplus(pose, x);
+        compute_active_errors();
+        tempChi = active_robust_chi2();
+        if (!ok2) tempChi = DBL_MAX;
+        rho = (currentChi - tempChi);
+        double scale = 0;
+        if (ok2)
+          for (int j = 0; j < 6; j++) scale += x[j] * (lambda * x[j] + b[j]);
+        scale += 1e-3;
+        rho /= scale;
+        if (!ok2) rho = -1;
+        const bool good = rho > 0 && std::isfinite(tempChi);
+        if (n_trials < 250) trace.push_back(good ? 1 : 0);
+        n_trials++;
+        if (good) {
+          double alpha = 1. - std::pow((2 * rho - 1), 3);
+          alpha = std::min(alpha, 2. / 3.);
+          lambda *= std::max(1. / 3., alpha);
+          ni = 2;
+          currentChi = tempChi;
+        } else {
+          lambda *= ni;
+          ni *= 2;
+          pose = backup;
+        }
+        qmax++;
+      } while (rho < 0 && qmax < 10);
+      if (qmax == 10 || rho == 0) {
+        ok = false;
+        continue;
+      }
+      if ((iniChi - currentChi) * 1e3 < iniChi) nBadLM++;
+      else nBadLM = 0;
+      if (nBadLM >= 3) ok = false;
+    }
+  }
+  int run(orc_pose_result* r) {
+    const int N = P->n;
+    for (int i = 0; i < N; i++) {
+      r->outlier[i] = 0;  // pFrame->mvbOutlier[i] = false for every feature with a MapPoint (:421,457)
+      if (P->has_mp[i]) edges.push_back(i);
+    }
+    const int nInitialCorrespondences = (int)edges.size();
+    const Pose initial = pose_from_Tcw(P->Tcw);
+    pose = initial;
+    r->n_trials = 0;
+    if (r->trace) r->trace[0] = -1;
+    if (nInitialCorrespondences < 3) {  // :492-493 (the frame pose is left untouched)
+      for (int k = 0; k < 16; k++) r->Tcw_out[k] = P->Tcw[k];
+      return 0;
+    }
+    level.assign(edges.size(), 0);
+    err.assign(edges.size() * 3, 0.0);
+    chi2.assign(edges.size(), 0.0);
+    delta_mono = (double)(float)std::sqrt(5.991);    // const float deltaMono = sqrt(5.991) (:406)
+    delta_stereo = (double)(float)std::sqrt(7.815);  // :407
+    const float chi2Mono = 5.991f, chi2Stereo = 7.815f;  // :496-497 (float arrays)
+    int nBad = 0;
+    robust = true;
+    for (int it = 0; it < 4; it++) {
+      pose = initial;  // vSE3->setEstimate(Converter::toSE3Quat(pFrame->mTcw)) (:505)
+      optimize(10);
+      nBad = 0;
+      for (size_t e = 0; e < edges.size(); e++) {  // :510-567 (mono and stereo lists; per-edge logic is identical)
+        const int f = edges[e];
+        if (r->outlier[f]) compute_error((int)e);  // inactive edges are not refreshed by the optimizer
+        const float c = (float)chi2[e];
+        if (c > (is_stereo(f) ? chi2Stereo : chi2Mono)) {
+          r->outlier[f] = 1;
+          level[e] = 1;
+          nBad++;
+        } else {
+          r->outlier[f] = 0;
+          level[e] = 0;
+        }
+      }
+      if (it == 2) robust = false;  // e->setRobustKernel(0)
+      if (edges.size() < 10) break;  // optimizer.edges().size()<10 (:569-570)
+    }
+    pose_to_Tcw(pose, r->Tcw_out);
+    r->n_trials = n_trials;
+    if (r->trace) {
+      size_t n = std::min<size_t>(trace.size(), 255);
+      for (size_t i = 0; i < n; i++) r->trace[i] = trace[i];
+      r->trace[n] = -1;
+    }
+    return nInitialCorrespondences - nBad;
+  }
+};
 }  // namespace
+
+extern "C" int orc_pose_optimization(const orc_pose_problem* p, orc_pose_result* r) {
+  PO po;
+  po.P = p;
+  return po.run(r);
+}
 
 extern "C" int orc_local_ba(const orc_ba_problem* p, const volatile uint8_t* stop, orc_ba_result* r) {
   BA ba;

@@ -167,6 +167,27 @@ int orc_compute_stereo_matches(const orc_keypoint* kpsL, const uint8_t* descL, i
                                const int* lvlW, const int* lvlH, const float* scale, const float* inv_scale, int nlevels,
                                float mbf, float mb, float* uright, float* depth);
 
+/* ---------------- PoseOptimization (src/Optimizer.cc:363-605 + vendored g2o) ---------------- */
+typedef struct {
+  const float* Tcw;        /* pFrame->mTcw, 16 floats row-major */
+  int32_t n;               /* pFrame->N */
+  const uint8_t* has_mp;   /* pFrame->mvpMapPoints[i] != NULL */
+  const float* Xw;         /* pMP->GetWorldPos(), n x 3 (ignored where has_mp == 0) */
+  const float* kpx;        /* mvKeysUn[i].pt.x */
+  const float* kpy;
+  const float* uright;     /* mvuRight[i]; < 0: monocular edge (:418) */
+  const float* inv_sigma2; /* mvInvLevelSigma2[mvKeysUn[i].octave] */
+  float fx, fy, cx, cy, bf;
+} orc_pose_problem;
+typedef struct {
+  float* Tcw_out;     /* 16 floats: pFrame->SetPose(...) (:600-603) */
+  uint8_t* outlier;   /* n: pFrame->mvbOutlier */
+  int32_t* trace;     /* optional: accept(1)/reject(0) of every LM trial, -1 terminated, >= 256 entries */
+  int32_t n_trials;
+} orc_pose_result;
+/* returns nInitialCorrespondences - nBad (:605) */
+int orc_pose_optimization(const orc_pose_problem* p, orc_pose_result* r);
+
 /* ---------------- LocalBA (src/Optimizer.cc:629-997 + vendored g2o) ---------------- */
 typedef struct {
   int32_t kf;        /* index into poses[] */

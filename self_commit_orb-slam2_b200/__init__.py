@@ -431,6 +431,42 @@ class Optimizer:
         out["n_trials"] = r.n_trials
         return out
 
+    def PoseOptimizationBatch(self, ds):
+        """Optimizer::PoseOptimization (src/Optimizer.cc:363-605) for a batch of independent frames; ds: dicts with Tcw,
+        has_mp, Xw, kpx, kpy, uright, inv_sigma2, fx, fy, cx, cy, bf.  Returns a list of result dicts."""
+        class PP(ctypes.Structure):
+            _fields_ = [("Tcw", _vp), ("n", ctypes.c_int32), ("has_mp", _vp), ("Xw", _vp), ("kpx", _vp), ("kpy", _vp),
+                        ("uright", _vp), ("inv_sigma2", _vp), ("fx", ctypes.c_float), ("fy", ctypes.c_float),
+                        ("cx", ctypes.c_float), ("cy", ctypes.c_float), ("bf", ctypes.c_float)]
+
+        class PR(ctypes.Structure):
+            _fields_ = [("Tcw_out", _vp), ("outlier", _vp), ("trace", _vp), ("n_inliers", ctypes.c_int32),
+                        ("n_trials", ctypes.c_int32)]
+        B = len(ds)
+        probs, ress, keep, outs = (PP * B)(), (PR * B)(), [], []
+        for i, d in enumerate(ds):
+            a = dict(Tcw=np.ascontiguousarray(d["Tcw"], np.float32).reshape(16),
+                     has_mp=np.ascontiguousarray(d["has_mp"], np.uint8), Xw=np.ascontiguousarray(d["Xw"], np.float32),
+                     kpx=np.ascontiguousarray(d["kpx"], np.float32), kpy=np.ascontiguousarray(d["kpy"], np.float32),
+                     uright=np.ascontiguousarray(d["uright"], np.float32),
+                     inv_sigma2=np.ascontiguousarray(d["inv_sigma2"], np.float32))
+            n = len(a["has_mp"])
+            o = dict(Tcw=np.zeros(16, np.float32), outlier=np.zeros(max(n, 1), np.uint8), trace=np.full(256, -1, np.int32))
+            keep.append((a, o))
+            probs[i] = PP(a["Tcw"].ctypes.data, n, a["has_mp"].ctypes.data, a["Xw"].ctypes.data, a["kpx"].ctypes.data,
+                          a["kpy"].ctypes.data, a["uright"].ctypes.data, a["inv_sigma2"].ctypes.data, float(d["fx"]),
+                          float(d["fy"]), float(d["cx"]), float(d["cy"]), float(d["bf"]))
+            ress[i] = PR(o["Tcw"].ctypes.data, o["outlier"].ctypes.data, o["trace"].ctypes.data, 0, 0)
+            outs.append((o, n))
+        L = lib()
+        L.b2s_pose_optimization_batch.argtypes = [_vp, ctypes.c_int, _vp, _vp]
+        _check(L.b2s_pose_optimization_batch(self._h, B, ctypes.cast(probs, _vp), ctypes.cast(ress, _vp)))
+        return [dict(n_inliers=ress[i].n_inliers, n_trials=ress[i].n_trials, Tcw=o["Tcw"], outlier=o["outlier"][:n],
+                     trace=o["trace"]) for i, (o, n) in enumerate(outs)]
+
+    def PoseOptimization(self, d):
+        return self.PoseOptimizationBatch([d])[0]
+
     def LocalBundleAdjustmentBatch(self, ds, its1=5, its2=10):
         B = len(ds)
         probs = (_BaProblem * B)()

@@ -1524,6 +1524,348 @@ __global__ void __launch_bounds__(256) k_block_order(BaPtrs p) {
   if (nz) atomicAdd(&p.blkNZ[w], nz);
 }
 
+// ================================================================================================
+// Optimizer::PoseOptimization (src/Optimizer.cc:363-605): one CTA per frame.  One free pose, unary edges with fixed map
+// points; 4 rounds x 10 Levenberg iterations from the same initial pose, inlier/outlier re-classification after every
+// round with the chi2 of the LAST evaluated state (g2o semantics, also after a rejected trial), Huber kernels dropped
+// after round 2.  Edge loops are strided over the CTA's threads, sums are fixed-tree block reductions (deterministic),
+// the 6x6 solve and the LM bookkeeping run on thread 0.
+// ================================================================================================
+struct PoFrame {
+  int nEdges, edgeOff;        // this frame's edges are [edgeOff, edgeOff+nEdges) of the packed arrays
+  float fx, fy, cx, cy, bf;
+};
+struct PoPtrs {
+  const PoFrame* frames;
+  const double* poseInit;     // [frame][8]
+  const float* Xw;            // [edge][3]
+  const float* obs;           // [edge][3] (x, y, uRight; uRight < 0: monocular)
+  const float* invSigma2;     // [edge]
+  double* err;                // [edge][3] scratch
+  double* chi2;               // [edge]
+  uint8_t* level;             // [edge]
+  uint8_t* outlier;           // [edge] out
+  double* poseOut;            // [frame][8]
+  int* nInliers;              // [frame]
+  int* nTrials;               // [frame]
+  int* trace;                 // [frame][256]
+};
+
+__device__ __forceinline__ double po_edge_error(const double* P, const float* Xwf, const float* ob, double w,
+                                                const PoFrame& F, double* er) {
+  const double X[3] = {(double)Xwf[0], (double)Xwf[1], (double)Xwf[2]};
+  double Xc[3];
+  pose_map(P, X, Xc);
+  if (!(ob[2] < 0)) {  // stereo: cam_project with `const float invz` (types_six_dof_expmap.cpp:304-312), double bf
+    const float invz = (float)(1.0 / Xc[2]);
+    const double u = Xc[0] * invz * (double)F.fx + (double)F.cx;
+    const double v = Xc[1] * invz * (double)F.fy + (double)F.cy;
+    const double ur = u - (double)F.bf * invz;
+    er[0] = (double)ob[0] - u;
+    er[1] = (double)ob[1] - v;
+    er[2] = (double)ob[2] - ur;
+    return er[0] * (w * er[0]) + er[1] * (w * er[1]) + er[2] * (w * er[2]);
+  }
+  const double u = Xc[0] / Xc[2] * (double)F.fx + (double)F.cx;
+  const double v = Xc[1] / Xc[2] * (double)F.fy + (double)F.cy;
+  er[0] = (double)ob[0] - u;
+  er[1] = (double)ob[1] - v;
+  er[2] = 0;
+  return er[0] * (w * er[0]) + er[1] * (w * er[1]);
+}
+
+// dense 6x6 Cholesky solve (LinearSolverDense uses Eigen LDLT; same solution up to rounding), thread 0 only
+__device__ bool po_solve6(const double* H, double lambda, const double* b, double* x) {
+  double L[36];
+  for (int i = 0; i < 36; i++) L[i] = H[i];
+  for (int i = 0; i < 6; i++) L[i * 7] += lambda;
+  for (int j = 0; j < 6; j++) {
+    double d = L[j * 6 + j];
+    for (int k = 0; k < j; k++) d -= L[j * 6 + k] * L[j * 6 + k];
+    if (!(d > 0.0) || !isfinite(d)) return false;
+    d = sqrt(d);
+    L[j * 6 + j] = d;
+    for (int i = j + 1; i < 6; i++) {
+      double sacc = L[i * 6 + j];
+      for (int k = 0; k < j; k++) sacc -= L[i * 6 + k] * L[j * 6 + k];
+      L[i * 6 + j] = sacc / d;
+    }
+  }
+  double y[6];
+  for (int i = 0; i < 6; i++) {
+    double sacc = b[i];
+    for (int k = 0; k < i; k++) sacc -= L[i * 6 + k] * y[k];
+    y[i] = sacc / L[i * 6 + i];
+  }
+  for (int i = 5; i >= 0; i--) {
+    double sacc = y[i];
+    for (int k = i + 1; k < 6; k++) sacc -= L[k * 6 + i] * x[k];
+    x[i] = sacc / L[i * 6 + i];
+  }
+  return true;
+}
+
+constexpr int PO_T = 256;
+__global__ void __launch_bounds__(PO_T) k_pose_opt(PoPtrs p) {
+  __shared__ double sPose[8], sInit[8], sBackup[8], sH[27], sX[6], sRed[32];
+  __shared__ double sCur, sTemp, sLambda, sNi, sIni, sRho;
+  __shared__ int sOk, sAgain, sRobust, sNBadLM, sTrials, sQmax, sNActive, sNBad;
+  const int fr = blockIdx.x;
+  const PoFrame F = p.frames[fr];
+  const int tid = threadIdx.x;
+  const int nE = F.nEdges, e0 = F.edgeOff;
+  if (tid < 8) {
+    sInit[tid] = p.poseInit[(size_t)fr * 8 + tid];
+    sPose[tid] = sInit[tid];
+  }
+  if (tid == 0) {
+    sRobust = 1;
+    sTrials = 0;
+    sNBad = 0;
+  }
+  for (int e = tid; e < nE; e += PO_T) {
+    p.level[e0 + e] = 0;
+    p.outlier[e0 + e] = 0;
+  }
+  __syncthreads();
+  if (nE < 3) {  // :492-493: return 0, pose untouched
+    if (tid < 8) p.poseOut[(size_t)fr * 8 + tid] = sInit[tid];
+    if (tid == 0) {
+      p.nInliers[fr] = 0;
+      p.nTrials[fr] = 0;
+    }
+    return;
+  }
+  const double dMono = (double)(float)2.4476519360399226, dStereo = (double)(float)2.795532150593156;  // (float)sqrt(5.991|7.815)
+  auto eval_errors = [&]() -> void {  // computeActiveErrors + activeRobustChi2 -> sTemp
+    double chi = 0;
+    const int robust = sRobust;
+    for (int e = tid; e < nE; e += PO_T) {
+      const int ge = e0 + e;
+      if (p.level[ge]) continue;
+      double er[3];
+      const double c2 = po_edge_error(sPose, p.Xw + (size_t)ge * 3, p.obs + (size_t)ge * 3, (double)p.invSigma2[ge], F, er);
+      p.err[(size_t)ge * 3] = er[0];
+      p.err[(size_t)ge * 3 + 1] = er[1];
+      p.err[(size_t)ge * 3 + 2] = er[2];
+      p.chi2[ge] = c2;
+      double r0 = c2, r1;
+      if (robust) huber(c2, (p.obs[(size_t)ge * 3 + 2] < 0) ? dMono : dStereo, r0, r1);
+      chi += r0;
+    }
+    const double tot = block_sum(chi, sRed);
+    if (tid == 0) sTemp = tot;
+    __syncthreads();
+  };
+  for (int round = 0; round < 4; round++) {
+    if (tid < 8) sPose[tid] = sInit[tid];  // vSE3->setEstimate(Converter::toSE3Quat(pFrame->mTcw)) (:505)
+    int act = 0;
+    for (int e = tid; e < nE; e += PO_T) act += p.level[e0 + e] == 0;
+    __syncthreads();
+    {
+      const double a = block_sum((double)act, sRed);
+      if (tid == 0) {
+        sNActive = (int)a;
+        sOk = 1;
+        sNBadLM = 0;
+      }
+      __syncthreads();
+    }
+    if (sNActive > 0) {
+      for (int it = 0; it < 10; it++) {
+        if (!sOk) break;
+        eval_errors();
+        if (tid == 0) {
+          sCur = sTemp;
+          sIni = sTemp;
+        }
+        // buildSystem: J^T (rho' Omega) J (upper triangle, 21) and -J^T Omega e rho' (6)
+        double acc[27];
+#pragma unroll
+        for (int k = 0; k < 27; k++) acc[k] = 0;
+        const int robust = sRobust;
+        for (int e = tid; e < nE; e += PO_T) {
+          const int ge = e0 + e;
+          if (p.level[ge]) continue;
+          const float* Xwf = p.Xw + (size_t)ge * 3;
+          const double X[3] = {(double)Xwf[0], (double)Xwf[1], (double)Xwf[2]};
+          double Xc[3];
+          pose_map(sPose, X, Xc);
+          const bool st = !(p.obs[(size_t)ge * 3 + 2] < 0);
+          const double fx = F.fx, fy = F.fy, bf = F.bf;
+          const double x = Xc[0], y = Xc[1], invz = 1.0 / Xc[2], invz_2 = invz * invz;
+          double B[3][6];
+          B[0][0] = x * y * invz_2 * fx;
+          B[0][1] = -(1 + (x * x * invz_2)) * fx;
+          B[0][2] = y * invz * fx;
+          B[0][3] = -invz * fx;
+          B[0][4] = 0;
+          B[0][5] = x * invz_2 * fx;
+          B[1][0] = (1 + y * y * invz_2) * fy;
+          B[1][1] = -x * y * invz_2 * fy;
+          B[1][2] = -x * invz * fy;
+          B[1][3] = 0;
+          B[1][4] = -invz * fy;
+          B[1][5] = y * invz_2 * fy;
+          B[2][0] = st ? B[0][0] - bf * y * invz_2 : 0.0;
+          B[2][1] = st ? B[0][1] + bf * x * invz_2 : 0.0;
+          B[2][2] = st ? B[0][2] : 0.0;
+          B[2][3] = st ? B[0][3] : 0.0;
+          B[2][4] = 0;
+          B[2][5] = st ? B[0][5] - bf * invz_2 : 0.0;
+          const double w0 = (double)p.invSigma2[ge];
+          double rho1 = 1.0;
+          if (robust) {
+            double r0;
+            huber(p.chi2[ge], st ? dStereo : dMono, r0, rho1);
+          }
+          const double* er = p.err + (size_t)ge * 3;
+          double omr[3];
+#pragma unroll
+          for (int r = 0; r < 3; r++) omr[r] = -(w0 * er[r]) * rho1;
+          const double wq = rho1 * w0;
+          int t = 0;
+#pragma unroll
+          for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int j = i; j < 6; j++) {
+              double hh = 0;
+#pragma unroll
+              for (int r = 0; r < 3; r++) hh += B[r][i] * wq * B[r][j];
+              acc[t++] += hh;
+            }
+#pragma unroll
+          for (int i = 0; i < 6; i++) {
+            double s2 = 0;
+#pragma unroll
+            for (int r = 0; r < 3; r++) s2 += B[r][i] * omr[r];
+            acc[21 + i] += s2;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 27; k++) {
+          const double tot = block_sum(acc[k], sRed);
+          if (tid == 0) sH[k] = tot;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          if (it == 0) {  // computeLambdaInit (levenberg.cpp:166-180)
+            double mx = 0;
+            int t = 0;
+            for (int i = 0; i < 6; i++)
+              for (int j = i; j < 6; j++) {
+                if (i == j) mx = fmax(fabs(sH[t]), mx);
+                t++;
+              }
+            sLambda = 1e-5 * mx;
+            sNi = 2;
+            sNBadLM = 0;
+          }
+          sQmax = 0;
+        }
+        __syncthreads();
+        do {
+          if (tid == 0) {
+            for (int k = 0; k < 8; k++) sBackup[k] = sPose[k];
+            double Hf[36], bb[6];
+            int t = 0;
+            for (int i = 0; i < 6; i++)
+              for (int j = i; j < 6; j++) {
+                Hf[i * 6 + j] = sH[t];
+                Hf[j * 6 + i] = sH[t];
+                t++;
+              }
+            for (int i = 0; i < 6; i++) bb[i] = sH[21 + i];
+            double xx[6];
+            const bool ok2 = po_solve6(Hf, sLambda, bb, xx);
+            sAgain = ok2 ? 1 : 0;  // (temporarily: solve status)
+            if (ok2) {
+              for (int i = 0; i < 6; i++) sX[i] = xx[i];
+              pose_oplus(sPose, xx);
+            }
+          }
+          __syncthreads();
+          const int ok2 = sAgain;
+          eval_errors();
+          if (tid == 0) {
+            double tempChi = ok2 ? sTemp : DBL_MAX;
+            double rho = sCur - tempChi;
+            double scale = 0;
+            if (ok2)
+              for (int j = 0; j < 6; j++) scale += sX[j] * (sLambda * sX[j] + sH[21 + j]);
+            scale += 1e-3;
+            rho /= scale;
+            if (!ok2) rho = -1;
+            const bool good = rho > 0 && isfinite(tempChi);
+            if (sTrials < 255) p.trace[(size_t)fr * 256 + sTrials] = good ? 1 : 0;
+            sTrials++;
+            if (good) {
+              double alpha = 1. - pow((2 * rho - 1), 3);
+              alpha = fmin(alpha, 2. / 3.);
+              sLambda *= fmax(1. / 3., alpha);
+              sNi = 2;
+              sCur = tempChi;
+            } else {
+              sLambda *= sNi;
+              sNi *= 2;
+              for (int k = 0; k < 8; k++) sPose[k] = sBackup[k];
+            }
+            sRho = rho;
+            sQmax++;
+            sAgain = (rho < 0 && sQmax < 10) ? 1 : 0;
+          }
+          __syncthreads();
+        } while (sAgain);
+        if (tid == 0) {
+          if (sQmax == 10 || sRho == 0) {
+            sOk = 0;
+          } else {
+            if ((sIni - sCur) * 1e3 < sIni) sNBadLM++;
+            else sNBadLM = 0;
+            if (sNBadLM >= 3) sOk = 0;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // re-classification (:510-567): chi2 of the last evaluated state for active edges, recomputed for current outliers
+    int bad = 0;
+    for (int e = tid; e < nE; e += PO_T) {
+      const int ge = e0 + e;
+      const bool st = !(p.obs[(size_t)ge * 3 + 2] < 0);
+      double c2 = p.chi2[ge];
+      if (p.outlier[ge]) {
+        double er[3];
+        c2 = po_edge_error(sPose, p.Xw + (size_t)ge * 3, p.obs + (size_t)ge * 3, (double)p.invSigma2[ge], F, er);
+        p.err[(size_t)ge * 3] = er[0];
+        p.err[(size_t)ge * 3 + 1] = er[1];
+        p.err[(size_t)ge * 3 + 2] = er[2];
+        p.chi2[ge] = c2;
+      }
+      const bool out = (float)c2 > (st ? 7.815f : 5.991f);
+      p.outlier[ge] = out ? 1 : 0;
+      p.level[ge] = out ? 1 : 0;
+      bad += out;
+    }
+    __syncthreads();
+    {
+      const double nb = block_sum((double)bad, sRed);
+      if (tid == 0) {
+        sNBad = (int)nb;
+        if (round == 2) sRobust = 0;  // e->setRobustKernel(0)
+      }
+      __syncthreads();
+    }
+    if (nE < 10) break;  // optimizer.edges().size() < 10 (:569-570)
+  }
+  if (tid < 8) p.poseOut[(size_t)fr * 8 + tid] = sPose[tid];
+  if (tid == 0) {
+    p.nInliers[fr] = nE - sNBad;
+    p.nTrials[fr] = sTrials;
+    if (sTrials < 256) p.trace[(size_t)fr * 256 + min(sTrials, 255)] = -1;
+  }
+}
+
 }  // namespace b2s
 
 using namespace b2s;
@@ -1539,8 +1881,11 @@ struct BaHostStage {  // pinned mirror of the uploaded per-window arrays (same s
   BaState* st = nullptr;
 };
 
+struct b2s_pose_scratch;
+static void pose_scratch_free(b2s_pose_scratch* s);
 struct b2s_ba_solver {
   int maxKf, maxMp, maxE, maxBatch, device;
+  b2s_pose_scratch* pose = nullptr;  // PoseOptimization buffers (allocated on first use)
   cudaStream_t stream = nullptr, stream2 = nullptr;
   long long launches = 0;
   BaPtrs d;
@@ -1667,6 +2012,7 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
 extern "C" void b2s_ba_destroy(b2s_ba_solver* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  pose_scratch_free(h->pose);
   for (void* p : h->allocs) cudaFree(p);
   for (void* p : h->hostAllocs) cudaFreeHost(p);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1943,4 +2289,149 @@ extern "C" int b2s_local_ba(b2s_ba_solver* h, const b2s_ba_problem* p, const vol
 }
 extern "C" int b2s_local_ba_batch(b2s_ba_solver* h, int batch, const b2s_ba_problem* p, b2s_ba_result* r) {
   return ba_run(h, batch, p, nullptr, r);
+}
+
+
+// ================================================================================================ PoseOptimization host side
+struct b2s_pose_scratch {
+  size_t capE = 0;
+  int capF = 0;
+  PoFrame* dFrames = nullptr;
+  double *dPoseInit = nullptr, *dPoseOut = nullptr, *dErr = nullptr, *dChi2 = nullptr;
+  float *dXw = nullptr, *dObs = nullptr, *dInvS = nullptr;
+  uint8_t *dLevel = nullptr, *dOutlier = nullptr;
+  int *dNInl = nullptr, *dNTr = nullptr, *dTrace = nullptr;
+};
+
+static void pose_scratch_free(b2s_pose_scratch* s) {
+  if (!s) return;
+  void* ptrs[] = {s->dFrames, s->dPoseInit, s->dPoseOut, s->dErr, s->dChi2, s->dXw, s->dObs, s->dInvS, s->dLevel,
+                  s->dOutlier, s->dNInl, s->dNTr, s->dTrace};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete s;
+}
+
+extern "C" int b2s_pose_optimization_batch(b2s_ba_solver* h, int batch, const b2s_pose_problem* probs, b2s_pose_result* res) {
+  if (!h || !probs || !res || batch < 1) {
+    set_error("b2s_pose_optimization_batch: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  // pack the edges (features with a MapPoint, ascending feature index = g2o insertion order, :411-487)
+  std::vector<PoFrame> frames(batch);
+  std::vector<double> poseInit((size_t)batch * 8);
+  size_t totalE = 0;
+  for (int f = 0; f < batch; f++) {
+    const b2s_pose_problem& P = probs[f];
+    if (P.n < 0 || !P.Tcw || !res[f].Tcw_out || (P.n && (!P.has_mp || !P.Xw || !P.kpx || !P.kpy || !P.uright ||
+                                                         !P.inv_sigma2 || !res[f].outlier))) {
+      set_error("b2s_pose_optimization_batch: frame %d has null arrays", f);
+      return B2S_ERR_BAD_ARG;
+    }
+    int ne = 0;
+    for (int i = 0; i < P.n; i++) ne += P.has_mp[i] != 0;
+    frames[f].nEdges = ne;
+    frames[f].edgeOff = (int)totalE;
+    frames[f].fx = P.fx; frames[f].fy = P.fy; frames[f].cx = P.cx; frames[f].cy = P.cy; frames[f].bf = P.bf;
+    totalE += ne;
+    double R[3][3];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) R[i][j] = P.Tcw[i * 4 + j];  // Converter::toSE3Quat (src/Converter.cc:57-66)
+    double* q = &poseInit[(size_t)f * 8];
+    quat_from_R_host(R, q);
+    q[4] = P.Tcw[3]; q[5] = P.Tcw[7]; q[6] = P.Tcw[11]; q[7] = 0;
+  }
+  std::vector<float> Xw(totalE * 3 + 3), obs(totalE * 3 + 3), invS(totalE + 1);
+  std::vector<int> featOf(totalE + 1);
+  {
+    size_t e = 0;
+    for (int f = 0; f < batch; f++) {
+      const b2s_pose_problem& P = probs[f];
+      for (int i = 0; i < P.n; i++) {
+        if (!P.has_mp[i]) continue;
+        Xw[e * 3] = P.Xw[i * 3]; Xw[e * 3 + 1] = P.Xw[i * 3 + 1]; Xw[e * 3 + 2] = P.Xw[i * 3 + 2];
+        obs[e * 3] = P.kpx[i]; obs[e * 3 + 1] = P.kpy[i]; obs[e * 3 + 2] = P.uright[i];
+        invS[e] = P.inv_sigma2[i];
+        featOf[e] = i;
+        e++;
+      }
+    }
+  }
+  if (!h->pose) h->pose = new b2s_pose_scratch();
+  b2s_pose_scratch* s = h->pose;
+  if (totalE + 1 > s->capE || batch > s->capF) {
+    pose_scratch_free(s);
+    h->pose = s = new b2s_pose_scratch();
+    s->capE = std::max<size_t>(totalE + 1, 4096) * 2;
+    s->capF = std::max(batch, 16) * 2;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void* pp, size_t bytes) {
+      if (e == cudaSuccess) e = cudaMalloc((void**)pp, bytes);
+    };
+    A(&s->dFrames, s->capF * sizeof(PoFrame)); A(&s->dPoseInit, (size_t)s->capF * 64); A(&s->dPoseOut, (size_t)s->capF * 64);
+    A(&s->dErr, s->capE * 24); A(&s->dChi2, s->capE * 8); A(&s->dXw, s->capE * 12); A(&s->dObs, s->capE * 12);
+    A(&s->dInvS, s->capE * 4); A(&s->dLevel, s->capE); A(&s->dOutlier, s->capE);
+    A(&s->dNInl, (size_t)s->capF * 4); A(&s->dNTr, (size_t)s->capF * 4); A(&s->dTrace, (size_t)s->capF * 256 * 4);
+    if (e != cudaSuccess) {
+      set_error("b2s_pose_optimization_batch: %s", cudaGetErrorString(e));
+      return B2S_ERR_CUDA;
+    }
+  }
+  B2S_CUDA(cudaMemcpyAsync(s->dFrames, frames.data(), batch * sizeof(PoFrame), cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(s->dPoseInit, poseInit.data(), (size_t)batch * 64, cudaMemcpyHostToDevice, st));
+  if (totalE) {
+    B2S_CUDA(cudaMemcpyAsync(s->dXw, Xw.data(), totalE * 12, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(s->dObs, obs.data(), totalE * 12, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(s->dInvS, invS.data(), totalE * 4, cudaMemcpyHostToDevice, st));
+  }
+  PoPtrs pp;
+  pp.frames = s->dFrames; pp.poseInit = s->dPoseInit; pp.Xw = s->dXw; pp.obs = s->dObs; pp.invSigma2 = s->dInvS;
+  pp.err = s->dErr; pp.chi2 = s->dChi2; pp.level = s->dLevel; pp.outlier = s->dOutlier; pp.poseOut = s->dPoseOut;
+  pp.nInliers = s->dNInl; pp.nTrials = s->dNTr; pp.trace = s->dTrace;
+  k_pose_opt<<<batch, PO_T, 0, st>>>(pp);
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  std::vector<double> poseOut((size_t)batch * 8);
+  std::vector<uint8_t> outl(totalE + 1);
+  std::vector<int> nInl(batch), nTr(batch), trace((size_t)batch * 256);
+  B2S_CUDA(cudaMemcpyAsync(poseOut.data(), s->dPoseOut, (size_t)batch * 64, cudaMemcpyDeviceToHost, st));
+  if (totalE) B2S_CUDA(cudaMemcpyAsync(outl.data(), s->dOutlier, totalE, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(nInl.data(), s->dNInl, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(nTr.data(), s->dNTr, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(trace.data(), s->dTrace, (size_t)batch * 256 * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  for (int f = 0; f < batch; f++) {
+    const b2s_pose_problem& P = probs[f];
+    b2s_pose_result& R = res[f];
+    for (int i = 0; i < P.n; i++) R.outlier[i] = 0;
+    for (int e = 0; e < frames[f].nEdges; e++) R.outlier[featOf[frames[f].edgeOff + e]] = outl[frames[f].edgeOff + e];
+    R.n_inliers = nInl[f];
+    R.n_trials = nTr[f];
+    if (frames[f].nEdges < 3) {
+      for (int k = 0; k < 16; k++) R.Tcw_out[k] = P.Tcw[k];  // untouched (:492-493)
+    } else {
+      const double* q = &poseOut[(size_t)f * 8];  // Converter::toCvMat(SE3Quat) (src/Converter.cc:96-107)
+      const double tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
+      const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+      const double txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+      const double tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+      float* T = R.Tcw_out;
+      T[0] = (float)(1 - (tyy + tzz)); T[1] = (float)(txy - twz); T[2] = (float)(txz + twy); T[3] = (float)q[4];
+      T[4] = (float)(txy + twz); T[5] = (float)(1 - (txx + tzz)); T[6] = (float)(tyz - twx); T[7] = (float)q[5];
+      T[8] = (float)(txz - twy); T[9] = (float)(tyz + twx); T[10] = (float)(1 - (txx + tyy)); T[11] = (float)q[6];
+      T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
+    }
+    if (R.trace) {
+      const int n = std::min(nTr[f], 255);
+      for (int i = 0; i < n; i++) R.trace[i] = trace[(size_t)f * 256 + i];
+      R.trace[n] = -1;
+    }
+  }
+  return B2S_OK;
+}
+
+extern "C" int b2s_pose_optimization(b2s_ba_solver* h, const b2s_pose_problem* p, b2s_pose_result* r) {
+  return b2s_pose_optimization_batch(h, 1, p, r);
 }

@@ -63,4 +63,35 @@ void Optimizer::LocalBundleAdjustment(const LocalBAWindow& w, bool* pbStopFlag, 
   }
 }
 
+// PoseOptimization runs on the Tracking thread: its own solver handle (handles are not shared between threads)
+static b2s_ba_solver* g_poseSolver = nullptr;
+static std::mutex g_poseMutex;
+
+int Optimizer::PoseOptimization(const PoseProblem& f, float TcwOut[16], std::vector<uint8_t>& outlier) {
+  std::lock_guard<std::mutex> lock(g_poseMutex);
+  if (!g_poseSolver) {
+    const char* e = getenv("B2S_DEVICE");
+    int rc = b2s_ba_create(4, 16, 64, 1, e ? atoi(e) : 0, &g_poseSolver);
+    if (rc != B2S_OK) {
+      fprintf(stderr, "Optimizer::PoseOptimization: libb200slam error %d: %s\n", rc, b2s_last_error());
+      throw std::runtime_error(b2s_last_error());
+    }
+  }
+  const int N = (int)f.hasMapPoint.size();
+  outlier.assign(N > 0 ? N : 1, 0);
+  b2s_pose_problem p;
+  p.Tcw = f.Tcw; p.n = N; p.has_mp = f.hasMapPoint.data(); p.Xw = f.Xw.data(); p.kpx = f.kpx.data(); p.kpy = f.kpy.data();
+  p.uright = f.uRight.data(); p.inv_sigma2 = f.invSigma2.data();
+  p.fx = f.fx; p.fy = f.fy; p.cx = f.cx; p.cy = f.cy; p.bf = f.bf;
+  b2s_pose_result r;
+  r.Tcw_out = TcwOut; r.outlier = outlier.data(); r.trace = nullptr; r.n_inliers = 0; r.n_trials = 0;
+  int rc = b2s_pose_optimization(g_poseSolver, &p, &r);
+  if (rc != B2S_OK) {
+    fprintf(stderr, "Optimizer::PoseOptimization: libb200slam error %d: %s\n", rc, b2s_last_error());
+    throw std::runtime_error(b2s_last_error());
+  }
+  outlier.resize(N);
+  return r.n_inliers;
+}
+
 }  // namespace ORB_SLAM2

@@ -25,8 +25,21 @@ struct LocalBAResult {
   bool aborted = false;              // stop flag was set before round 1: nothing to write back (:858-860)
 };
 
+struct PoseProblem {                 // Optimizer::PoseOptimization(Frame*) on the flattened frame
+  float Tcw[16];                     // pFrame->mTcw
+  std::vector<uint8_t> hasMapPoint;  // N: mvpMapPoints[i] != NULL
+  std::vector<float> Xw;             // N x 3: pMP->GetWorldPos() (ignored where hasMapPoint == 0)
+  std::vector<float> kpx, kpy;       // N: mvKeysUn[i].pt
+  std::vector<float> uRight;         // N: mvuRight[i] (< 0: monocular observation)
+  std::vector<float> invSigma2;      // N: mvInvLevelSigma2[mvKeysUn[i].octave]
+  float fx = 0, fy = 0, cx = 0, cy = 0, bf = 0;
+};
+
 class Optimizer {
  public:
+  // int static PoseOptimization(Frame* pFrame) (include/Optimizer.h:100, src/Optimizer.cc:363-605): fills TcwOut (the
+  // pose for pFrame->SetPose) and outlier (pFrame->mvbOutlier), returns nInitialCorrespondences - nBad
+  static int PoseOptimization(const PoseProblem& f, float TcwOut[16], std::vector<uint8_t>& outlier);
   // void static LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap) on the flattened window
   static void LocalBundleAdjustment(const LocalBAWindow& w, bool* pbStopFlag, LocalBAResult& out);
 };

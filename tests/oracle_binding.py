@@ -208,6 +208,28 @@ class Oracle:
                                               P(sc), P(isc), nl, bf, mb, P(ur), P(dp))
         return n, ur, dp
 
+    # ---- PoseOptimization ----
+    def pose_optimization(self, d):
+        class PP(ctypes.Structure):
+            _fields_ = [("Tcw", vp), ("n", ctypes.c_int32), ("has_mp", vp), ("Xw", vp), ("kpx", vp), ("kpy", vp),
+                        ("uright", vp), ("inv_sigma2", vp), ("fx", ctypes.c_float), ("fy", ctypes.c_float),
+                        ("cx", ctypes.c_float), ("cy", ctypes.c_float), ("bf", ctypes.c_float)]
+
+        class PR(ctypes.Structure):
+            _fields_ = [("Tcw_out", vp), ("outlier", vp), ("trace", vp), ("n_trials", ctypes.c_int32)]
+        arrs = pose_problem_arrays(d)
+        n = len(arrs["has_mp"])
+        p = PP(arrs["Tcw"].ctypes.data, n, arrs["has_mp"].ctypes.data, arrs["Xw"].ctypes.data, arrs["kpx"].ctypes.data,
+               arrs["kpy"].ctypes.data, arrs["uright"].ctypes.data, arrs["inv_sigma2"].ctypes.data, d["fx"], d["fy"],
+               d["cx"], d["cy"], d["bf"])
+        Tout = np.zeros(16, np.float32)
+        outl = np.zeros(n, np.uint8)
+        trace = np.full(256, -1, np.int32)
+        r = PR(Tout.ctypes.data, outl.ctypes.data, trace.ctypes.data, 0)
+        self.L.orc_pose_optimization.argtypes = [vp, vp]
+        ninl = self.L.orc_pose_optimization(ctypes.byref(p), ctypes.byref(r))
+        return dict(n_inliers=ninl, Tcw=Tout, outlier=outl, trace=trace, n_trials=r.n_trials)
+
     # ---- LocalBA ----
     def local_ba(self, d, stop=None, its1=5, its2=10):
         Tcw = np.ascontiguousarray(d["Tcw"], np.float32)
@@ -233,6 +255,14 @@ class Oracle:
         c = np.zeros_like(x)
         self.L.orc_sincosf_batch(P(x), len(x), P(s), P(c), threads)
         return s, c
+
+
+def pose_problem_arrays(d):
+    return dict(Tcw=np.ascontiguousarray(d["Tcw"], np.float32).reshape(16),
+                has_mp=np.ascontiguousarray(d["has_mp"], np.uint8), Xw=np.ascontiguousarray(d["Xw"], np.float32),
+                kpx=np.ascontiguousarray(d["kpx"], np.float32), kpy=np.ascontiguousarray(d["kpy"], np.float32),
+                uright=np.ascontiguousarray(d["uright"], np.float32),
+                inv_sigma2=np.ascontiguousarray(d["inv_sigma2"], np.float32))
 
 
 class OracleExtractor:

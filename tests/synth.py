@@ -312,3 +312,41 @@ def synth_triangulation(n=2000, seed=17, n_nodes=100, w=1241, h=376):
     kf1 = kf(u, v, np.arange(n), 20)
     kf2 = kf(u2, v2, rng.permutation(n), 25)
     return dict(kf1=kf1, kf2=kf2, F12=F12, ex=ex, ey=ey, scale=scale, sigma2=sigma2)
+
+
+def synth_pose_problem(n=2000, seed=23, mp_frac=0.6, mono_frac=0.2, outlier_frac=0.1, pert_t=0.05, pert_deg=0.5):
+    """One tracked frame for Optimizer::PoseOptimization (src/Optimizer.cc:363): map points seen from a true pose,
+    noisy observations (sigma = 1 px * 1.2^octave), gross outliers, initial pose = motion-model prediction."""
+    rng = np.random.RandomState(seed)
+    fx = fy = np.float32(718.856)
+    cx, cy, bf = np.float32(607.1928), np.float32(185.2157), np.float32(386.1448)
+    W, H = 1241, 376
+    yaw = np.deg2rad(rng.uniform(-3, 3))
+    R = np.array([[np.cos(yaw), 0, -np.sin(yaw)], [0, 1, 0], [np.sin(yaw), 0, np.cos(yaw)]])
+    c = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.05, 0.05), rng.uniform(0, 2.0)])
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = -R @ c
+    z = rng.uniform(4, 60, size=n)
+    u = rng.uniform(5, W - 5, size=n)
+    v = rng.uniform(5, H - 5, size=n)
+    Xc = np.stack([(u - cx) * z / fx, (v - cy) * z / fy, z], 1)
+    Xw = (R.T @ (Xc - T[:3, 3]).T).T
+    octv = rng.randint(0, 8, size=n)
+    sig = 1.2 ** octv
+    kpx = u + rng.normal(0, 1, n) * sig
+    kpy = v + rng.normal(0, 1, n) * sig
+    ur = u - bf / z + rng.normal(0, 1, n) * sig
+    bad = rng.uniform(size=n) < outlier_frac
+    kpx = np.where(bad, kpx + rng.choice([-1, 1], n) * rng.uniform(15, 60, n), kpx)
+    mono = rng.uniform(size=n) < mono_frac
+    ur = np.where(mono, -1.0, ur)
+    has_mp = (rng.uniform(size=n) < mp_frac).astype(np.uint8)
+    dyaw = np.deg2rad(rng.normal(0, pert_deg))
+    dR = np.array([[np.cos(dyaw), 0, -np.sin(dyaw)], [0, 1, 0], [np.sin(dyaw), 0, np.cos(dyaw)]])
+    T0 = np.eye(4)
+    T0[:3, :3] = dR @ R
+    T0[:3, 3] = dR @ T[:3, 3] + rng.normal(0, pert_t, 3)
+    return dict(Tcw=T0.astype(np.float32).reshape(16), Tcw_true=T, has_mp=has_mp, Xw=Xw.astype(np.float32),
+                kpx=kpx.astype(np.float32), kpy=kpy.astype(np.float32), uright=ur.astype(np.float32),
+                inv_sigma2=(1.0 / (1.2 ** (2 * octv))).astype(np.float32), fx=fx, fy=fy, cx=cx, cy=cy, bf=bf)

@@ -77,3 +77,8 @@ from synth import synth_triangulation  # noqa: E402
 td = synth_triangulation(seed=117, n_nodes=100)
 n, m = o.search_for_triangulation(td["kf1"], td["kf2"], td["F12"], float(td["ex"]), float(td["ey"]), td["scale"], td["sigma2"])
 np.savez_compressed(os.path.join(out, "triangulation_seed117.npz"), n=n, match12=m)
+# PoseOptimization
+from synth import synth_pose_problem  # noqa: E402
+pr = o.pose_optimization(synth_pose_problem(seed=23))
+np.savez_compressed(os.path.join(out, "poseopt_seed23.npz"), n_inliers=pr["n_inliers"], Tcw=pr["Tcw"], outlier=pr["outlier"],
+                    trace=pr["trace"], n_trials=pr["n_trials"])
