@@ -267,6 +267,22 @@ def run_b200(args, rank, local_rank, world):
         phase["stereo_matches_per_frame"] = float(nmt.float().mean().item())
     except Exception as ex:  # never let the side measurement break the bench line
         phase["stereo_match_error"] = str(ex)[:200]
+    # Optimizer::PoseOptimization for the F frames of the step (side measurement through the host-buffer
+    # C ABI: packing, H2D, one CTA per frame, D2H)
+    try:
+        from synth import synth_pose_problem
+        pp = [synth_pose_problem(seed=1000 + (i % 8)) for i in range(8)]
+        frames_pp = [pp[i % 8] for i in range(F)]
+        popt = ss.opt if ss.opt is not None else None
+        if popt is not None:
+            popt.PoseOptimizationBatch(frames_pp)
+            t1 = time.perf_counter()
+            pr = popt.PoseOptimizationBatch(frames_pp)
+            phase["pose_optimization_batch_ms"] = (time.perf_counter() - t1) * 1e3
+            phase["pose_optimization_frames"] = F
+            phase["pose_optimization_inliers_per_frame"] = float(np.mean([r["n_inliers"] for r in pr]))
+    except Exception as ex:
+        phase["pose_optimization_error"] = str(ex)[:200]
     if ss.n_ba:
         t1 = time.perf_counter()
         ss.opt.LocalBundleAdjustmentBatch([ss.ba_problem] * ss.n_ba)
