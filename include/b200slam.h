@@ -237,6 +237,32 @@ int b2s_search_for_triangulation(b2s_matcher* h, const b2s_kf_features* kf1, con
                                  float ex, float ey, const float* scale_factors, const float* level_sigma2, int nlevels,
                                  int only_stereo, int check_ori, int32_t* match12, int* nmatches);
 
+/* ------------------------------------------------------------------ DBoW2 vocabulary */
+/* TemplatedVocabulary<FORB>::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1256) as used by
+ * Frame::ComputeBoW / KeyFrame::ComputeBoW (src/Frame.cc:880-896, src/KeyFrame.cc, levelsup = 4): it produces the word
+ * ids / weights of mBowVec and the node ids of mFeatVec that SearchByBoW and SearchForTriangulation consume.
+ * The vocabulary is passed flattened: node 0 = root, nodes 1..n-1 in the order of the text file (loadFromTextFile
+ * :1338-1425: "parent isLeaf d0..d31 weight" per line); children keep the file order, word ids go to the flagged leaves in
+ * file order. */
+typedef struct {
+  int32_t k, L, n_nodes;
+  const int32_t* parent;    /* [n_nodes], parent[0] = -1; parents precede their children */
+  const uint8_t* leaf_flag; /* [n_nodes] */
+  const uint8_t* desc;      /* [n_nodes][32] */
+  const double* weight;     /* [n_nodes] */
+} b2s_vocabulary_desc;
+typedef struct b2s_vocabulary b2s_vocabulary;
+int b2s_vocabulary_create(const b2s_vocabulary_desc* d, int device, b2s_vocabulary** out);
+void b2s_vocabulary_destroy(b2s_vocabulary* v);
+int b2s_vocabulary_words(const b2s_vocabulary* v);
+/* Per feature: word id, word weight (0 = stopped word, skipped by DBoW2; may be NULL), node id `levelsup` levels above the
+ * leaves (0 = root when L - levelsup <= 0).  The host composes BowVector (sum of weights per word, L1-normalised) and
+ * FeatureVector (features per node) from these arrays; the device variant feeds b2s_search_by_bow_device directly. */
+int b2s_bow_transform(b2s_vocabulary* v, const uint8_t* features, int n, int levelsup, int32_t* word_id, double* weight,
+                      int32_t* node_id);
+int b2s_bow_transform_device(b2s_vocabulary* v, const uint8_t* d_features, int n, int levelsup, int32_t* d_word_id,
+                             double* d_weight, int32_t* d_node_id, void* stream);
+
 /* ------------------------------------------------------------------ LocalBA */
 typedef struct {
   int32_t kf;       /* index into Tcw[] */

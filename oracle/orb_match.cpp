@@ -441,3 +441,61 @@ extern "C" int orc_search_for_triangulation(const orc_kf_features* kf1, const or
   for (int i = 0; i < N1; i++) match12[i] = vMatches12[i];
   return nmatches;
 }
+
+// FORB::distance (Thirdparty/DBoW2/DBoW2/FORB.cpp:81-101): the bit-trick popcount of the 8 XOR words
+static int forb_distance(const uint8_t* a, const uint8_t* b) {
+  const int32_t* pa = reinterpret_cast<const int32_t*>(a);
+  const int32_t* pb = reinterpret_cast<const int32_t*>(b);
+  int dist = 0;
+  for (int i = 0; i < 8; i++, pa++, pb++) {
+    unsigned int v = *pa ^ *pb;
+    v = v - ((v >> 1) & 0x55555555);
+    v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+    dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+  }
+  return dist;
+}
+
+// TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup) (:1211-1256) for every feature
+extern "C" int orc_bow_transform(const orc_vocabulary* v, const uint8_t* features, int n, int levelsup, int32_t* word_id,
+                                 double* weight, int32_t* node_id) {
+  const int N = v->n_nodes;
+  std::vector<std::vector<int> > children(N);
+  std::vector<int> word(N, 0);
+  int nWords = 0;
+  for (int nid = 1; nid < N; nid++) {  // loadFromTextFile :1378-1418
+    children[v->parent[nid]].push_back(nid);
+    if (v->leaf_flag[nid]) word[nid] = nWords++;
+  }
+  const int nid_level = v->L - levelsup;
+  for (int i = 0; i < n; i++) {
+    const uint8_t* feature = features + (size_t)i * 32;
+    int nid = 0;  // if(nid_level <= 0 && nid != NULL) *nid = 0
+    int final_id = 0, current_level = 0;
+    if (children[0].empty()) {  // empty vocabulary
+      word_id[i] = 0;
+      weight[i] = 0;
+      node_id[i] = 0;
+      continue;
+    }
+    do {
+      ++current_level;
+      const std::vector<int>& nodes = children[final_id];
+      final_id = nodes[0];
+      double best_d = forb_distance(feature, v->desc + (size_t)final_id * 32);
+      for (size_t c = 1; c < nodes.size(); c++) {
+        const int id = nodes[c];
+        const double d = forb_distance(feature, v->desc + (size_t)id * 32);
+        if (d < best_d) {
+          best_d = d;
+          final_id = id;
+        }
+      }
+      if (current_level == nid_level) nid = final_id;
+    } while (!children[final_id].empty());
+    word_id[i] = word[final_id];
+    weight[i] = v->weight[final_id];
+    node_id[i] = nid;
+  }
+  return nWords;
+}

@@ -156,6 +156,21 @@ int orc_search_for_triangulation(const orc_kf_features* kf1, const orc_kf_featur
                                  const float* scale_factors, const float* level_sigma2, int only_stereo, int check_ori,
                                  int32_t* match12);
 
+/* DBoW2 TemplatedVocabulary<FORB>::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1256) as used by
+ * Frame::ComputeBoW / KeyFrame::ComputeBoW (src/Frame.cc:880-896, levelsup = 4) on a flattened vocabulary:
+ * node 0 is the root; nodes 1..n-1 in the order of the text file (loadFromTextFile :1338-1425): parent id, leaf flag,
+ * 32-byte descriptor, weight; children are visited in file order, word ids are assigned to the leaves in file order. */
+typedef struct {
+  int32_t k, L, n_nodes;
+  const int32_t* parent;    /* [n_nodes], parent[0] = -1 */
+  const uint8_t* leaf_flag; /* [n_nodes] nIsLeaf > 0 */
+  const uint8_t* desc;      /* [n_nodes][32] */
+  const double* weight;     /* [n_nodes] */
+} orc_vocabulary;
+/* per feature: word id, word weight (0 = stopped word: DBoW2 skips it), id of the node `levelsup` levels above the leaves */
+int orc_bow_transform(const orc_vocabulary* v, const uint8_t* features, int n, int levelsup, int32_t* word_id, double* weight,
+                      int32_t* node_id);
+
 /* Frame::ComputeStereoMatches (src/Frame.cc:1026-1421): row-band candidates, Hamming best (< (TH_HIGH+TH_LOW)/2),
  * 11x11 L1 block matching over +-5 px on the keypoint's pyramid level, parabola sub-pixel fit, median*2.1 cull.
  * kps: level-0 coordinates as produced by the extractor; pyr*: dense level images (stride = width), lvlW/lvlH their

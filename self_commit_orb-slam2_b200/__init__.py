@@ -381,6 +381,66 @@ class ORBmatcher:
         return nm.value, match12
 
 
+class _VocDesc(ctypes.Structure):
+    _fields_ = [("k", ctypes.c_int32), ("L", ctypes.c_int32), ("n_nodes", ctypes.c_int32), ("parent", ctypes.c_void_p),
+                ("leaf_flag", ctypes.c_void_p), ("desc", ctypes.c_void_p), ("weight", ctypes.c_void_p)]
+
+
+class ORBVocabulary:
+    """Mirror of ORBVocabulary::transform (DBoW2 TemplatedVocabulary.h:1127-1256) on a flattened vocabulary."""
+
+    def __init__(self, k, L, parent, leaf_flag, desc, weight, device=0):
+        self._h = _vp()
+        self._keep = [np.ascontiguousarray(parent, np.int32), np.ascontiguousarray(leaf_flag, np.uint8),
+                      np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(weight, np.float64)]
+        d = _VocDesc(k, L, len(self._keep[0]), *[a.ctypes.data for a in self._keep])
+        L_ = lib()
+        L_.b2s_vocabulary_create.argtypes = [_vp, ctypes.c_int, _vp]
+        L_.b2s_vocabulary_destroy.argtypes = [_vp]
+        L_.b2s_vocabulary_destroy.restype = None
+        L_.b2s_bow_transform.argtypes = [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]
+        L_.b2s_bow_transform_device.argtypes = [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp]
+        _check(L_.b2s_vocabulary_create(ctypes.byref(d), device, ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().b2s_vocabulary_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def transform_features(self, features, levelsup=4):
+        """Per feature (word_id, weight, node_id)."""
+        features = np.ascontiguousarray(features, np.uint8)
+        n = len(features)
+        word = np.zeros(n, np.int32)
+        w = np.zeros(n, np.float64)
+        node = np.zeros(n, np.int32)
+        _check(lib().b2s_bow_transform(self._h, _p(features), n, levelsup, _p(word), _p(w), _p(node)))
+        return word, w, node
+
+    def transform(self, features, levelsup=4):
+        """transform(features, BowVector&, FeatureVector&, levelsup) (:1127-1187) for TF_IDF / L1: returns
+        (bow: dict word -> value, feat: dict node -> [feature indices])."""
+        word, w, node = self.transform_features(features, levelsup)
+        bow, feat = {}, {}
+        for i in range(len(word)):
+            if w[i] > 0:  # not stopped
+                bow[int(word[i])] = bow.get(int(word[i]), 0.0) + float(w[i])  # BowVector::addWeight, feature order
+                feat.setdefault(int(node[i]), []).append(i)                   # FeatureVector::addFeature
+        norm = 0.0
+        for k in sorted(bow):  # BowVector::normalize(L1) iterates the std::map in key order
+            norm += abs(bow[k])
+        if norm > 0.0:
+            for k in bow:
+                bow[k] /= norm
+        return bow, feat
+
+
 class Optimizer:
     """Mirror of ORB_SLAM2::Optimizer::LocalBundleAdjustment (include/Optimizer.h:112) on a flattened window."""
 

@@ -842,6 +842,44 @@ __global__ void __launch_bounds__(128) k_tri_match(const uint8_t* __restrict__ d
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// DBoW2 TemplatedVocabulary<FORB>::transform (TemplatedVocabulary.h:1211-1256): descend the k-ary tree, at every level the
+// child with the smallest Hamming distance (first minimum in file order); word id / weight of the leaf and the id of the
+// node `levelsup` levels above the leaves.  One thread per feature; the children of a node are contiguous in cDesc.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_bow_transform(const uint8_t* __restrict__ feat, int n,
+                                                       const int32_t* __restrict__ childStart,
+                                                       const int32_t* __restrict__ childCount,
+                                                       const int32_t* __restrict__ cNode, const uint8_t* __restrict__ cDesc,
+                                                       const int32_t* __restrict__ wordOf, const double* __restrict__ wgt,
+                                                       int nidLevel, int32_t* __restrict__ wordId,
+                                                       double* __restrict__ weight, int32_t* __restrict__ nodeId) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u256 f = ld_desc(feat, i);
+  int finalId = 0, level = 0, nid = 0;
+  if (childCount[0] == 0) {
+    wordId[i] = 0;
+    if (weight) weight[i] = 0;
+    nodeId[i] = 0;
+    return;
+  }
+  do {
+    ++level;
+    const int beg = childStart[finalId], cnt = childCount[finalId];
+    uint32_t best = 0xFFFFFFFFu;
+    for (int c = 0; c < cnt; c++) {
+      const uint32_t key = ((uint32_t)hamming256(f, ld_desc(cDesc, beg + c)) << 16) | (uint32_t)c;  // d < best_d: first minimum
+      best = min(best, key);
+    }
+    finalId = cNode[beg + (int)(best & 0xFFFFu)];
+    if (level == nidLevel) nid = finalId;
+  } while (childCount[finalId] != 0);
+  wordId[i] = wordOf[finalId];
+  if (weight) weight[i] = wgt[finalId];
+  nodeId[i] = nid;
+}
+
 // Window search without occupancy (Fuse): the queries are independent, the answer is the head of each K-list.
 __global__ void __launch_bounds__(256) k_win_pick(int nq, int thDist, const uint32_t* __restrict__ topk,
                                                   const int32_t* __restrict__ topkIdx, int32_t* __restrict__ bestIdx,
@@ -1434,5 +1472,130 @@ extern "C" int b2s_search_for_triangulation(b2s_matcher* h, const b2s_kf_feature
   B2S_CUDA(cudaStreamSynchronize(st));
   for (int j = 0; j < nB; j++)
     if (mB[j] >= 0) match12[mB[j]] = j;  // every keyframe-2 feature is matched at most once (vbMatched2)
+  return B2S_OK;
+}
+
+// ---------------------------------------------------------------- DBoW2 vocabulary
+struct b2s_vocabulary {
+  int k = 0, L = 0, nNodes = 0, nWords = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  int32_t *dChildStart = nullptr, *dChildCount = nullptr, *dCNode = nullptr, *dWordOf = nullptr;
+  uint8_t* dCDesc = nullptr;
+  double* dWeight = nullptr;
+  // scratch of the host-buffer entry point
+  size_t cap = 0;
+  uint8_t* dFeat = nullptr;
+  int32_t *dWord = nullptr, *dNode = nullptr;
+  double* dW = nullptr;
+};
+
+extern "C" void b2s_vocabulary_destroy(b2s_vocabulary* v) {
+  if (!v) return;
+  cudaSetDevice(v->device);
+  void* ptrs[] = {v->dChildStart, v->dChildCount, v->dCNode, v->dWordOf, v->dCDesc, v->dWeight, v->dFeat, v->dWord, v->dNode,
+                  v->dW};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (v->stream) cudaStreamDestroy(v->stream);
+  delete v;
+}
+
+extern "C" int b2s_vocabulary_create(const b2s_vocabulary_desc* d, int device, b2s_vocabulary** out) {
+  if (!out || !d || d->n_nodes < 1 || !d->parent || !d->leaf_flag || !d->desc || !d->weight || d->k < 1 || d->L < 1) {
+    set_error("b2s_vocabulary_create: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  *out = nullptr;
+  int rc = select_device(device);
+  if (rc != B2S_OK) return rc;
+  const int N = d->n_nodes;
+  // children in file order (loadFromTextFile :1378-1418), word ids to the flagged leaves in file order
+  std::vector<int32_t> cnt(N, 0), start(N + 1, 0), wordOf(N, 0);
+  int nWords = 0;
+  for (int nid = 1; nid < N; nid++) {
+    const int p = d->parent[nid];
+    if (p < 0 || p >= nid) {
+      set_error("b2s_vocabulary_create: node %d has parent %d (parents must precede their children)", nid, p);
+      return B2S_ERR_BAD_ARG;
+    }
+    cnt[p]++;
+    if (d->leaf_flag[nid]) wordOf[nid] = nWords++;
+  }
+  for (int i = 0; i < N; i++) start[i + 1] = start[i] + cnt[i];
+  std::vector<int32_t> fill(start.begin(), start.end() - 1), cNode(std::max(N - 1, 1));
+  std::vector<uint8_t> cDesc((size_t)std::max(N - 1, 1) * 32);
+  for (int nid = 1; nid < N; nid++) {
+    const int pos = fill[d->parent[nid]]++;
+    cNode[pos] = nid;
+    memcpy(&cDesc[(size_t)pos * 32], d->desc + (size_t)nid * 32, 32);
+  }
+  b2s_vocabulary* v = new b2s_vocabulary();
+  v->k = d->k; v->L = d->L; v->nNodes = N; v->nWords = nWords; v->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking);
+  auto A = [&](void* pp, size_t bytes, const void* src) {
+    if (e == cudaSuccess) e = cudaMalloc((void**)pp, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(*(void**)pp, src, bytes, cudaMemcpyHostToDevice);
+  };
+  A(&v->dChildStart, (size_t)N * 4, start.data());
+  A(&v->dChildCount, (size_t)N * 4, cnt.data());
+  A(&v->dCNode, cNode.size() * 4, cNode.data());
+  A(&v->dCDesc, cDesc.size(), cDesc.data());
+  A(&v->dWordOf, (size_t)N * 4, wordOf.data());
+  A(&v->dWeight, (size_t)N * 8, d->weight);
+  if (e != cudaSuccess) {
+    set_error("b2s_vocabulary_create: %s", cudaGetErrorString(e));
+    b2s_vocabulary_destroy(v);
+    return B2S_ERR_CUDA;
+  }
+  *out = v;
+  return B2S_OK;
+}
+
+extern "C" int b2s_vocabulary_words(const b2s_vocabulary* v) { return v ? v->nWords : 0; }
+
+extern "C" int b2s_bow_transform_device(b2s_vocabulary* v, const uint8_t* d_features, int n, int levelsup, int32_t* d_word_id,
+                                        double* d_weight, int32_t* d_node_id, void* stream) {
+  if (!v || n < 0 || !d_word_id || !d_node_id || (n && !d_features)) {
+    set_error("b2s_bow_transform_device: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  if (n == 0) return B2S_OK;
+  B2S_CUDA(cudaSetDevice(v->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : v->stream;
+  k_bow_transform<<<div_up(n, 128), 128, 0, st>>>(d_features, n, v->dChildStart, v->dChildCount, v->dCNode, v->dCDesc,
+                                                v->dWordOf, v->dWeight, v->L - levelsup, d_word_id, d_weight, d_node_id);
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+extern "C" int b2s_bow_transform(b2s_vocabulary* v, const uint8_t* features, int n, int levelsup, int32_t* word_id,
+                                 double* weight, int32_t* node_id) {
+  if (!v || n < 0 || !word_id || !node_id || (n && !features)) {
+    set_error("b2s_bow_transform: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  if (n == 0) return B2S_OK;
+  B2S_CUDA(cudaSetDevice(v->device));
+  if ((size_t)n > v->cap) {
+    void* ptrs[] = {v->dFeat, v->dWord, v->dNode, v->dW};
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+    v->dFeat = nullptr; v->dWord = nullptr; v->dNode = nullptr; v->dW = nullptr;
+    v->cap = 0;
+    const size_t c = std::max<size_t>(n, 4096);
+    B2S_CUDA(cudaMalloc((void**)&v->dFeat, c * 32));
+    B2S_CUDA(cudaMalloc((void**)&v->dWord, c * 4));
+    B2S_CUDA(cudaMalloc((void**)&v->dNode, c * 4));
+    B2S_CUDA(cudaMalloc((void**)&v->dW, c * 8));
+    v->cap = c;
+  }
+  cudaStream_t st = v->stream;
+  B2S_CUDA(cudaMemcpyAsync(v->dFeat, features, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+  int rc = b2s_bow_transform_device(v, v->dFeat, n, levelsup, v->dWord, v->dW, v->dNode, st);
+  if (rc != B2S_OK) return rc;
+  B2S_CUDA(cudaMemcpyAsync(word_id, v->dWord, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (weight) B2S_CUDA(cudaMemcpyAsync(weight, v->dW, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(node_id, v->dNode, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
   return B2S_OK;
 }

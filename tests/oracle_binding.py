@@ -208,6 +208,21 @@ class Oracle:
                                               P(sc), P(isc), nl, bf, mb, P(ur), P(dp))
         return n, ur, dp
 
+    # ---- DBoW2 transform ----
+    def bow_transform(self, voc, features, levelsup=4):
+        class V(ctypes.Structure):
+            _fields_ = [("k", ctypes.c_int32), ("L", ctypes.c_int32), ("n_nodes", ctypes.c_int32), ("parent", vp),
+                        ("leaf_flag", vp), ("desc", vp), ("weight", vp)]
+        arrs = [np.ascontiguousarray(voc["parent"], np.int32), np.ascontiguousarray(voc["leaf_flag"], np.uint8),
+                np.ascontiguousarray(voc["desc"], np.uint8), np.ascontiguousarray(voc["weight"], np.float64)]
+        v = V(voc["k"], voc["L"], len(arrs[0]), *[a.ctypes.data for a in arrs])
+        features = np.ascontiguousarray(features, np.uint8)
+        n = len(features)
+        word, w, node = np.zeros(n, np.int32), np.zeros(n, np.float64), np.zeros(n, np.int32)
+        self.L.orc_bow_transform.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]
+        nw = self.L.orc_bow_transform(ctypes.byref(v), P(features), n, levelsup, P(word), P(w), P(node))
+        return nw, word, w, node
+
     # ---- PoseOptimization ----
     def pose_optimization(self, d):
         class PP(ctypes.Structure):

@@ -350,3 +350,46 @@ def synth_pose_problem(n=2000, seed=23, mp_frac=0.6, mono_frac=0.2, outlier_frac
     return dict(Tcw=T0.astype(np.float32).reshape(16), Tcw_true=T, has_mp=has_mp, Xw=Xw.astype(np.float32),
                 kpx=kpx.astype(np.float32), kpy=kpy.astype(np.float32), uright=ur.astype(np.float32),
                 inv_sigma2=(1.0 / (1.2 ** (2 * octv))).astype(np.float32), fx=fx, fy=fy, cx=cx, cy=cy, bf=bf)
+
+
+def synth_vocabulary(k=10, L=4, seed=3, stop_frac=0.05, ragged=True):
+    """A DBoW2-shaped vocabulary tree (k children per node, L levels) in text-file order (breadth-first like the k-means
+    training writes it): children descriptors are noisy copies of their parent so the descent is meaningful; a few
+    branches stop early (leaves above level L) when `ragged`."""
+    rng = np.random.RandomState(seed)
+    parent, leaf, desc, weight, level = [-1], [0], [np.zeros(32, np.uint8)], [0.0], [0]
+    frontier = [0]
+    for lv in range(1, L + 1):
+        nxt = []
+        for p in frontier:
+            nchild = k if not ragged else int(rng.choice([k, k, k, k - 3]))
+            for c in range(nchild):
+                d = desc[p].copy() if lv > 1 else rng.randint(0, 256, 32).astype(np.uint8)
+                flips = rng.choice(256, size=int(256 // (2 ** lv)), replace=False)
+                for b in flips:
+                    d[b >> 3] ^= np.uint8(1 << (b & 7))
+                nid = len(parent)
+                parent.append(p)
+                is_leaf = lv == L or (ragged and lv >= 2 and rng.uniform() < 0.03)
+                leaf.append(1 if is_leaf else 0)
+                desc.append(d)
+                weight.append(0.0 if (is_leaf and rng.uniform() < stop_frac) else float(rng.uniform(0.5, 9.0)))
+                level.append(lv)
+                if not is_leaf:
+                    nxt.append(nid)
+        frontier = nxt
+    return dict(k=k, L=L, parent=np.array(parent, np.int32), leaf_flag=np.array(leaf, np.uint8),
+                desc=np.stack(desc).astype(np.uint8), weight=np.array(weight, np.float64))
+
+
+def synth_voc_features(voc, n=2000, seed=5):
+    """Features near random leaves of the vocabulary (plus pure-noise features)."""
+    rng = np.random.RandomState(seed)
+    leaves = np.nonzero(voc["leaf_flag"])[0]
+    f = voc["desc"][rng.choice(leaves, size=n)].copy()
+    for i in range(n):
+        for b in rng.choice(256, size=int(rng.randint(0, 40)), replace=False):
+            f[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    noise = rng.uniform(size=n) < 0.1
+    f[noise] = rng.randint(0, 256, size=(int(noise.sum()), 32)).astype(np.uint8)
+    return f

@@ -82,3 +82,8 @@ from synth import synth_pose_problem  # noqa: E402
 pr = o.pose_optimization(synth_pose_problem(seed=23))
 np.savez_compressed(os.path.join(out, "poseopt_seed23.npz"), n_inliers=pr["n_inliers"], Tcw=pr["Tcw"], outlier=pr["outlier"],
                     trace=pr["trace"], n_trials=pr["n_trials"])
+# DBoW2 transform
+from synth import synth_voc_features, synth_vocabulary  # noqa: E402
+voc = synth_vocabulary(k=10, L=4, seed=7)
+nw, word, w, node = o.bow_transform(voc, synth_voc_features(voc, 2000, 5), 2)
+np.savez_compressed(os.path.join(out, "bow_transform_seed7.npz"), nw=nw, word=word, weight=w, node=node)
