@@ -177,7 +177,7 @@ def run_b200(args, rank, local_rank, world):
     F = args.frames
     ba = ba_window()
     ss = stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, ba_problem=ba, ba_every=BA_EVERY, device=local_rank, rank=rank,
-                                 world=world)
+                                 world=world, ba_depth=args.ba_depth)
     imgs = make_images(min(F, 16), F, seed0=1000 * rank)
     pinned = torch.from_numpy(imgs).pin_memory()
     ss.upload(pinned)
@@ -383,6 +383,8 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=24, help="stereo frames per step of the CPU reference arm")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ba-depth", type=int, default=int(os.environ.get("B2S_BA_DEPTH", "1")),
+                    help="LocalBA solver handles used round-robin by the pipelined stream (host work of batch i+1 overlaps the kernel of batch i)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

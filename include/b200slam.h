@@ -237,6 +237,12 @@ int b2s_search_for_triangulation(b2s_matcher* h, const b2s_kf_features* kf1, con
                                  float ex, float ey, const float* scale_factors, const float* level_sigma2, int nlevels,
                                  int only_stereo, int check_ori, int32_t* match12, int* nmatches);
 
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:359-440) for a batch of map points:
+ * point p owns descriptors [offsets[p], offsets[p+1]) (its observations in map order, bad keyframes removed);
+ * best_idx[p] = descriptor (relative index) with the least median distance to the others, -1 without descriptors. */
+int b2s_distinctive_descriptors(b2s_matcher* h, const uint8_t* desc, const int32_t* offsets, int n_points,
+                                int32_t* best_idx);
+
 /* ------------------------------------------------------------------ DBoW2 vocabulary */
 /* TemplatedVocabulary<FORB>::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1256) as used by
  * Frame::ComputeBoW / KeyFrame::ComputeBoW (src/Frame.cc:880-896, src/KeyFrame.cc, levelsup = 4): it produces the word

@@ -6,6 +6,7 @@
 #include "orb_oracle.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -498,4 +499,34 @@ extern "C" int orc_bow_transform(const orc_vocabulary* v, const uint8_t* feature
     node_id[i] = nid;
   }
   return nWords;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:359-440)
+extern "C" void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best_idx) {
+  for (int p = 0; p < n_points; p++) {
+    const int beg = offsets[p];
+    const size_t N = (size_t)(offsets[p + 1] - beg);
+    best_idx[p] = -1;
+    if (N == 0) continue;  // :378-379
+    std::vector<std::vector<float> > Distances(N, std::vector<float>(N, 0));
+    for (size_t i = 0; i < N; i++) {
+      Distances[i][i] = 0;
+      for (size_t j = i + 1; j < N; j++) {
+        const int distij = orc_descriptor_distance(desc + (size_t)(beg + i) * 32, desc + (size_t)(beg + j) * 32);
+        Distances[i][j] = (float)distij;
+        Distances[j][i] = (float)distij;
+      }
+    }
+    int BestMedian = INT_MAX, BestIdx = 0;
+    for (size_t i = 0; i < N; i++) {
+      std::vector<int> vDists(Distances[i].begin(), Distances[i].end());
+      std::sort(vDists.begin(), vDists.end());
+      const int median = vDists[(size_t)(0.5 * (N - 1))];
+      if (median < BestMedian) {
+        BestMedian = median;
+        BestIdx = (int)i;
+      }
+    }
+    best_idx[p] = BestIdx;
+  }
 }

@@ -171,6 +171,12 @@ typedef struct {
 int orc_bow_transform(const orc_vocabulary* v, const uint8_t* features, int n, int levelsup, int32_t* word_id, double* weight,
                       int32_t* node_id);
 
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:359-440) for a batch of map points: point p owns the
+ * descriptors [offsets[p], offsets[p+1]) (its observations in std::map<KeyFrame*,size_t> order, bad keyframes removed).
+ * best_idx[p] = index (relative to offsets[p]) of the descriptor with the least median distance to the others
+ * (median = sorted row [0.5*(N-1)], first minimum wins), or -1 for a point without descriptors. */
+void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best_idx);
+
 /* Frame::ComputeStereoMatches (src/Frame.cc:1026-1421): row-band candidates, Hamming best (< (TH_HIGH+TH_LOW)/2),
  * 11x11 L1 block matching over +-5 px on the keypoint's pyramid level, parabola sub-pixel fit, median*2.1 cull.
  * kps: level-0 coordinates as produced by the extractor; pyr*: dense level images (stride = width), lvlW/lvlH their

@@ -353,6 +353,16 @@ class ORBmatcher:
         return nacc.value, best, bdist
 
 
+    def DistinctiveDescriptors(self, desc, offsets):
+        """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:359-440) for a batch of map points."""
+        desc = np.ascontiguousarray(desc, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        best = np.full(len(offsets) - 1, -1, np.int32)
+        L = lib()
+        L.b2s_distinctive_descriptors.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp]
+        _check(L.b2s_distinctive_descriptors(self._h, _p(desc), _p(offsets), len(offsets) - 1, _p(best)))
+        return best
+
     def SearchForTriangulation(self, kf1, kf2, F12, ex, ey, scale_factors, level_sigma2, only_stereo=False):
         """ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:810-1009). kf1/kf2: dicts with desc, node, has_mp, stereo,
         x, y, octave, angle.  Returns (nmatches, match12)."""

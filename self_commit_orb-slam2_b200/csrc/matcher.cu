@@ -880,6 +880,62 @@ __global__ void __launch_bounds__(128) k_bow_transform(const uint8_t* __restrict
   nodeId[i] = nid;
 }
 
+// ------------------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:359-440): one warp per map point.  For every observation i the
+// median (sorted row element floor(0.5*(N-1))) of its distances to all observations is read off a 257-bin histogram
+// built by the warp; the first row with the smallest median wins.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_distinctive(const uint8_t* __restrict__ desc, const int32_t* __restrict__ offsets,
+                                                     int nPoints, int32_t* __restrict__ bestIdx) {
+  __shared__ int hist[8][264];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int p = blockIdx.x * 8 + wid;
+  if (p >= nPoints) return;
+  const int beg = offsets[p], N = offsets[p + 1] - beg;
+  if (N <= 0) {
+    if (lane == 0) bestIdx[p] = -1;
+    return;
+  }
+  int* h = hist[wid];
+  const int kth = (int)(0.5 * (double)(N - 1));
+  int bestMedian = 0x7fffffff, best = 0;
+  for (int i = 0; i < N; i++) {
+    for (int b = lane; b < 257; b += 32) h[b] = 0;
+    __syncwarp();
+    const u256 di = ld_desc(desc, beg + i);
+    for (int j = lane; j < N; j += 32) atomicAdd(&h[(j == i) ? 0 : hamming256(di, ld_desc(desc, beg + j))], 1);
+    __syncwarp();
+    // smallest value v with #(distances <= v) > kth: warp scan over 257 bins (9 per lane)
+    int local[9], sum = 0;
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      const int b = lane * 9 + t;
+      local[t] = (b < 257) ? h[b] : 0;
+      sum += local[t];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int run = incl - sum, med = 0x7fffffff;
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      run += local[t];
+      if (med == 0x7fffffff && run > kth && lane * 9 + t < 257) med = lane * 9 + t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) med = min(med, __shfl_xor_sync(0xffffffffu, med, o));
+    if (med < bestMedian) {  // strict: the first minimum wins (:424-428)
+      bestMedian = med;
+      best = i;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) bestIdx[p] = best;
+}
+
 // Window search without occupancy (Fuse): the queries are independent, the answer is the head of each K-list.
 __global__ void __launch_bounds__(256) k_win_pick(int nq, int thDist, const uint32_t* __restrict__ topk,
                                                   const int32_t* __restrict__ topkIdx, int32_t* __restrict__ bestIdx,
@@ -1597,5 +1653,40 @@ extern "C" int b2s_bow_transform(b2s_vocabulary* v, const uint8_t* features, int
   if (weight) B2S_CUDA(cudaMemcpyAsync(weight, v->dW, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaMemcpyAsync(node_id, v->dNode, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaStreamSynchronize(st));
+  return B2S_OK;
+}
+
+extern "C" int b2s_distinctive_descriptors(b2s_matcher* h, const uint8_t* desc, const int32_t* offsets, int n_points,
+                                           int32_t* best_idx) {
+  if (!h || n_points < 0 || !best_idx || (n_points && !offsets)) {
+    set_error("b2s_distinctive_descriptors: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  if (n_points == 0) return B2S_OK;
+  const int total = offsets[n_points];
+  if (total < 0 || (total && !desc)) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  uint8_t* dDesc = nullptr;
+  int32_t *dOff = nullptr, *dBest = nullptr;
+  B2S_CUDA(cudaMalloc((void**)&dDesc, (size_t)std::max(total, 1) * 32));
+  cudaError_t e = cudaMalloc((void**)&dOff, (size_t)(n_points + 1) * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dBest, (size_t)n_points * 4);
+  if (e == cudaSuccess && total) e = cudaMemcpyAsync(dDesc, desc, (size_t)total * 32, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dOff, offsets, (size_t)(n_points + 1) * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    k_distinctive<<<div_up(n_points, 8), 256, 0, st>>>(dDesc, dOff, n_points, dBest);
+    h->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(best_idx, dBest, (size_t)n_points * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(dDesc);
+  if (dOff) cudaFree(dOff);
+  if (dBest) cudaFree(dBest);
+  if (e != cudaSuccess) {
+    set_error("b2s_distinctive_descriptors: %s", cudaGetErrorString(e));
+    return B2S_ERR_CUDA;
+  }
   return B2S_OK;
 }

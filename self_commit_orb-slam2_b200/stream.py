@@ -23,7 +23,7 @@ KP_BYTES = keypoint_dtype.itemsize  # 28
 
 class StereoStream:
     def __init__(self, frames_per_step, width, height, nfeatures=2000, scale=1.2, nlevels=8, ini_th=20, min_th=7,
-                 ba_problem=None, ba_every=5, device=0, rank=0, world=1, nnratio=0.7):
+                 ba_problem=None, ba_every=5, device=0, rank=0, world=1, nnratio=0.7, ba_depth=1):
         self.F, self.w, self.h = frames_per_step, width, height
         self.rank, self.world = rank, world
         self.dev = torch.device("cuda", device)
@@ -37,9 +37,14 @@ class StereoStream:
         self.ba_every = ba_every
         self.n_ba = (self.F + ba_every - 1) // ba_every if ba_problem is not None else 0
         self.opt = None
+        self.opts = []
         if self.n_ba:
-            self.opt = Optimizer(max_kf=max(16, ba_problem["n_kf"]), max_mp=len(ba_problem["points"]),
-                                 max_edges=len(ba_problem["edges"]), max_batch=self.n_ba, device=device)
+            # ba_depth solver handles: with depth 2 the host preparation / upload / write-back of one LocalBA batch
+            # overlaps the LM kernel of the previous one (pipelined mode only)
+            for _ in range(max(1, int(ba_depth))):
+                self.opts.append(Optimizer(max_kf=max(16, ba_problem["n_kf"]), max_mp=len(ba_problem["points"]),
+                                           max_edges=len(ba_problem["edges"]), max_batch=self.n_ba, device=device))
+            self.opt = self.opts[0]
         F, cap = self.F, self.cap
         S = 1 + 2 * F  # slot 0: the frame before this shard; 1..F left images; F+1..2F right images
         z = dict(device=self.dev)
@@ -58,6 +63,8 @@ class StereoStream:
         self.d_imgs = torch.zeros((2 * F, height, width), dtype=torch.uint8, **z)
         self._pool = None
         self._ba_future = None
+        self._ba_futures = []  # (pipelined) in-flight LocalBA batches, oldest first; at most len(self.opts)
+        self._ba_next = 0
 
     # ------------------------------------------------------------------ device-resident step
     def upload(self, imgs_host):
@@ -77,21 +84,30 @@ class StereoStream:
         ba_out = None
         if run_ba and self.n_ba:  # own stream inside the solver; overlaps the work enqueued above
             if pipelined:
-                self.finish()
-                if self._pool is None:
-                    from concurrent.futures import ThreadPoolExecutor
-                    self._pool = ThreadPoolExecutor(max_workers=1)
-                self._ba_future = self._pool.submit(self.opt.LocalBundleAdjustmentBatch, [self.ba_problem] * self.n_ba)
+                ba_out = self._submit_ba()
             else:
                 ba_out = self.opt.LocalBundleAdjustmentBatch([self.ba_problem] * self.n_ba)
         return ba_out
 
-    def finish(self):
-        """Join the LocalBA batch still in flight (pipelined mode); returns its result or None."""
+    def _submit_ba(self):
+        """Queue this step's LocalBA batch on the next solver handle; returns the result of the batch that used that
+        handle before (or None)."""
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=len(self.opts))
         out = None
-        if self._ba_future is not None:
-            out = self._ba_future.result()
-            self._ba_future = None
+        if len(self._ba_futures) >= len(self.opts):
+            out = self._ba_futures.pop(0).result()
+        opt = self.opts[self._ba_next % len(self.opts)]
+        self._ba_next += 1
+        self._ba_futures.append(self._pool.submit(opt.LocalBundleAdjustmentBatch, [self.ba_problem] * self.n_ba))
+        return out
+
+    def finish(self):
+        """Join the LocalBA batches still in flight (pipelined mode); returns the last result or None."""
+        out = None
+        while self._ba_futures:
+            out = self._ba_futures.pop(0).result()
         return out
 
     def _enqueue_extract_match(self):
@@ -158,20 +174,16 @@ class StereoStream:
                                          float(self.matcher.mfNNratio), 0, 1, p(match), p(nm)))
         ba_out = None
         if run_ba and self.n_ba:
-            if pipelined:  # results of the previous step's windows are returned; finish() joins the last batch
-                ba_out = self.finish()
-                if self._pool is None:
-                    from concurrent.futures import ThreadPoolExecutor
-                    self._pool = ThreadPoolExecutor(max_workers=1)
-                self._ba_future = self._pool.submit(self.opt.LocalBundleAdjustmentBatch, [self.ba_problem] * self.n_ba)
+            if pipelined:  # results of an earlier step's windows are returned; finish() joins the rest
+                ba_out = self._submit_ba()
             else:
                 ba_out = self.opt.LocalBundleAdjustmentBatch([self.ba_problem] * self.n_ba)
         return n, nm, ba_out, (res_kps, res_desc, match)
 
     def launch_count(self):
         c = self.ex.launch_count() + self.matcher.launch_count()
-        if self.opt is not None:
-            c += self.opt.launch_count()
+        for o in self.opts:
+            c += o.launch_count()
         return c
 
     def h2d_bytes_per_step(self):

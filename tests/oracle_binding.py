@@ -208,6 +208,15 @@ class Oracle:
                                               P(sc), P(isc), nl, bf, mb, P(ur), P(dp))
         return n, ur, dp
 
+    def distinctive_descriptors(self, desc, offsets):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        best = np.full(len(offsets) - 1, -1, np.int32)
+        self.L.orc_distinctive_descriptors.argtypes = [vp, vp, ctypes.c_int, vp]
+        self.L.orc_distinctive_descriptors.restype = None
+        self.L.orc_distinctive_descriptors(P(desc), P(offsets), len(offsets) - 1, P(best))
+        return best
+
     # ---- DBoW2 transform ----
     def bow_transform(self, voc, features, levelsup=4):
         class V(ctypes.Structure):

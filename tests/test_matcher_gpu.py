@@ -196,3 +196,26 @@ def test_search_by_sim3_directions(pkg, oracle):
         assert n == on and np.array_equal(best, obest) and np.array_equal(bd, obd)
         assert (bd[best >= 0] <= 100).all() and n > 200
         res.append(best)
+
+
+def test_distinctive_descriptors(pkg, oracle):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:359-440): same representative descriptor per map point
+    (median of the distance rows, first minimum), including points with 0, 1, 2 and >32 observations and ties."""
+    rng = np.random.RandomState(8)
+    counts = np.concatenate([[0, 1, 2, 2, 3, 40, 97], rng.randint(1, 25, size=3000)]).astype(np.int32)
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    desc = np.zeros((offsets[-1], 32), np.uint8)
+    for p in range(len(counts)):
+        base = rng.randint(0, 256, 32).astype(np.uint8)
+        for i in range(counts[p]):
+            d = base.copy()
+            for b in rng.choice(256, size=int(rng.randint(0, 30)), replace=False):
+                d[b >> 3] ^= np.uint8(1 << (b & 7))
+            desc[offsets[p] + i] = d
+        if counts[p] >= 3 and p % 7 == 0:  # exact duplicates -> ties between medians
+            desc[offsets[p] + 1] = desc[offsets[p]]
+    m = pkg.ORBmatcher(0.6, True)
+    best = m.DistinctiveDescriptors(desc, offsets)
+    obest = oracle.distinctive_descriptors(desc, offsets)
+    assert np.array_equal(best, obest)
+    assert best[0] == -1 and best[1] == 0
