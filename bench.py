@@ -158,7 +158,7 @@ def workload_config(frames_per_gpu, world):
     return {"workload": "batched KITTI-shape stereo stream 1241x376, 2000 feat/img, 8 levels, FAST 20/7: extract L+R, "
                         "temporal SearchByBoW 2000x2000 (one vocabulary node), LocalBA 50KF/5000MP/30k edges every 5th frame",
             "frames_per_step_per_gpu": frames_per_gpu, "images_per_step_per_gpu": 2 * frames_per_gpu,
-            "parallelism": "frames sharded x%d, NCCL all-gather of left-image feature records" % world,
+            "parallelism": "frames sharded x%d, NCCL all-gather of the shard-boundary left-image feature records" % world,
             "l2": "inputs per step (%.0f MB of images per GPU) exceed the 126 MB L2"
                   % (2 * frames_per_gpu * W_IMG * H_IMG / 1e6)}
 
@@ -177,7 +177,7 @@ def run_b200(args, rank, local_rank, world):
     F = args.frames
     ba = ba_window()
     ss = stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, ba_problem=ba, ba_every=BA_EVERY, device=local_rank, rank=rank,
-                                 world=world, ba_depth=args.ba_depth)
+                                 world=world, ba_depth=args.ba_depth, exchange=args.exchange)
     imgs = make_images(min(F, 16), F, seed0=1000 * rank)
     pinned = torch.from_numpy(imgs).pin_memory()
     ss.upload(pinned)
@@ -383,6 +383,8 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=24, help="stereo frames per step of the CPU reference arm")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="boundary", choices=["boundary", "all"],
+                    help="NCCL all-gather of the shard-boundary left-image record only, or of every left-image record")
     ap.add_argument("--ba-depth", type=int, default=int(os.environ.get("B2S_BA_DEPTH", "1")),
                     help="LocalBA solver handles used round-robin by the pipelined stream (host work of batch i+1 overlaps the kernel of batch i)")
     args = ap.parse_args()

@@ -23,7 +23,8 @@ KP_BYTES = keypoint_dtype.itemsize  # 28
 
 class StereoStream:
     def __init__(self, frames_per_step, width, height, nfeatures=2000, scale=1.2, nlevels=8, ini_th=20, min_th=7,
-                 ba_problem=None, ba_every=5, device=0, rank=0, world=1, nnratio=0.7, ba_depth=1):
+                 ba_problem=None, ba_every=5, device=0, rank=0, world=1, nnratio=0.7, ba_depth=1,
+                 exchange="boundary"):
         self.F, self.w, self.h = frames_per_step, width, height
         self.rank, self.world = rank, world
         self.dev = torch.device("cuda", device)
@@ -56,10 +57,15 @@ class StereoStream:
         self.ang = torch.zeros((1 + F, cap), dtype=torch.float32, **z)
         self.match = torch.full((F, cap), -1, dtype=torch.int32, **z)
         self.nmatch = torch.zeros(F, dtype=torch.int32, **z)
+        # exchange: "boundary" all-gathers only each rank's LAST left-image record (the only frame another rank's temporal
+        # matcher reads: 123 KB per rank); "all" gathers every left-image record of the step (any rank can then
+        # match any frame pair; 20 MB per rank and step)
+        self.exchange = exchange
+        self.G = F if exchange == "all" else 1
         if world > 1:
-            self.g_kps = torch.zeros((world, F, cap, KP_BYTES), dtype=torch.uint8, **z)
-            self.g_desc = torch.zeros((world, F, cap, 32), dtype=torch.uint8, **z)
-            self.g_counts = torch.zeros((world, F), dtype=torch.int32, **z)
+            self.g_kps = torch.zeros((world, self.G, cap, KP_BYTES), dtype=torch.uint8, **z)
+            self.g_desc = torch.zeros((world, self.G, cap, 32), dtype=torch.uint8, **z)
+            self.g_counts = torch.zeros((world, self.G), dtype=torch.int32, **z)
         self.d_imgs = torch.zeros((2 * F, height, width), dtype=torch.uint8, **z)
         self._pool = None
         self._ba_future = None
@@ -117,7 +123,8 @@ class StereoStream:
                                      self.kps[1:].data_ptr(), self.desc[1:].data_ptr(), self.counts[1:].data_ptr(), cap,
                                      stream=st)
         if self.world > 1:
-            sharding.gather_records(self.kps[1:1 + F], self.desc[1:1 + F], self.counts[1:1 + F], self.g_kps, self.g_desc,
+            lo = 1 + F - self.G  # first gathered slot: all F left images, or just the last one
+            sharding.gather_records(self.kps[lo:1 + F], self.desc[lo:1 + F], self.counts[lo:1 + F], self.g_kps, self.g_desc,
                                     self.g_counts)
             sharding.take_predecessor(self.g_kps, self.g_desc, self.g_counts, self.rank, self.world, self.kps[0],
                                       self.desc[0], self.counts[0:1])
