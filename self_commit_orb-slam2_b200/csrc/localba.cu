@@ -2022,6 +2022,14 @@ extern "C" void b2s_ba_destroy(b2s_ba_solver* h) {
 extern "C" long long b2s_ba_launch_count(const b2s_ba_solver* h) { return h ? h->launches : 0; }
 
 // Converter::toSE3Quat / toVector3d + CSR structure of one window, written into the pinned staging area
+// host threads for window preparation / write-back: min(batch, 16, cores), or B2S_BA_HOST_THREADS (several ranks per box
+// share the host cores)
+static int ba_host_threads(int batch) {
+  int cap = 16;
+  if (const char* ev = getenv("B2S_BA_HOST_THREADS")) cap = std::max(1, atoi(ev));
+  return std::max(1, std::min(batch, std::min(cap, (int)std::thread::hardware_concurrency())));
+}
+
 static int ba_prepare_window(b2s_ba_solver* h, int w, const b2s_ba_problem& P, int* nFreeOut) {
   const BaPtrs& d = h->d;
   BaHostStage& s = h->hs;
@@ -2110,7 +2118,7 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
   // ---- host preparation of all windows in parallel (pinned staging), then one H2D per array
   std::vector<int> nFree(batch, 0), prc(batch, 0);
   {
-    const int nth = std::max(1, std::min(batch, std::min(16, (int)std::thread::hardware_concurrency())));
+    const int nth = ba_host_threads(batch);
     std::vector<std::thread> th;
     for (int t = 0; t < nth; t++)
       th.emplace_back([&, t]() {
@@ -2222,7 +2230,7 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
     }
   const auto tLoop = std::chrono::steady_clock::now();
   {
-    const int nth = std::max(1, std::min(batch, std::min(16, (int)std::thread::hardware_concurrency())));
+    const int nth = ba_host_threads(batch);
     std::vector<std::thread> th;
     for (int t = 0; t < nth; t++)
       th.emplace_back([&, t]() {
