@@ -177,7 +177,7 @@ def run_b200(args, rank, local_rank, world):
     F = args.frames
     ba = ba_window()
     if world > 1:  # several ranks share the host cores: split them for the LocalBA window preparation threads
-        os.environ.setdefault("B2S_BA_HOST_THREADS", str(max(2, min(16, (os.cpu_count() or 16) // (2 * world)))))
+        os.environ.setdefault("B2S_BA_HOST_THREADS", str(max(2, min(16, (os.cpu_count() or 16) // world))))
     ss = stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, ba_problem=ba, ba_every=BA_EVERY, device=local_rank, rank=rank,
                                  world=world, ba_depth=args.ba_depth, exchange=args.exchange)
     imgs = make_images(min(F, 16), F, seed0=1000 * rank)

@@ -213,7 +213,7 @@ __device__ __forceinline__ void win_barrier(unsigned int* bar, unsigned int& epo
     atomicAdd(bar, 1u);
     unsigned int spins = 0;
     while (ld_acquire_u32(bar) < epoch) {
-      __nanosleep(64);
+      __nanosleep(20);
       if (*hung) break;
       if (++spins > (1u << 24)) {  // ~1 s
         *hung = 1;
