@@ -98,3 +98,24 @@ def test_against_committed_golden(pkg):
     ex = pkg.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480)
     k, d = ex(synth_image(640, 480, 3))
     assert k.tobytes() == g["kps"].tobytes() and np.array_equal(d, g["desc"])
+
+
+def test_batch_upload_paths(pkg, oracle):
+    """Host-buffer batch entry point: >= 16 images take the chunked two-stream path; images in one contiguous block are
+    uploaded with one 1-D copy per chunk and re-pitched on the device (odd width x height: unaligned image starts),
+    separately allocated images take one copy each.  All of it must equal the per-image oracle result."""
+    w, h, nf, B = 321, 243, 500, 18
+    imgs = [synth_image(w, h, 40 + i) for i in range(B)]
+    ex = pkg.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    res_sep = ex.extract_batch(imgs)
+    block = np.stack(imgs)
+    res_blk = ex.extract_batch([block[i] for i in range(B)])
+    oex = oracle.extractor(nf, 1.2, 8, 20, 7)
+    for i in range(B):
+        ok, od = oex(imgs[i])
+        for res in (res_sep, res_blk):
+            k, d = res[i]
+            assert len(k) == len(ok), i
+            for f in ("x", "y", "size", "angle", "response", "octave", "class_id"):
+                assert np.array_equal(k[f], ok[f]), (i, f)
+            assert np.array_equal(d, od), i
