@@ -7,12 +7,15 @@
  * cpu_baseline / --impl reference legs may load it.  The product (libb200slam.so) never links,
  * loads or calls anything in this directory.
  *
- * PARITY PINNING: the reference ships no tests or golden vectors and cannot be
- * built here (needs OpenCV C++/Eigen3/Pangolin, all absent), so the oracle is pinned where it can
- * be: its OpenCV-owned stages (resize, FAST, GaussianBlur, fastAtan2) are checked bit-for-bit
- * against Python cv2 4.13 (the same OpenCV code the reference links) in tests/test_oracle_cv2.py;
- * the stages that are the reference's own code (quadtree, IC_Angle, rBRIEF, matchers, LocalBA)
- * have no independent pin -> "parity unpinned" for those.
+ * PARITY PINNING: the reference ships no tests or golden vectors and its build
+ * needs OpenCV C++/Eigen3/Pangolin (all absent).  The oracle is pinned where it can be:
+ *  - OpenCV-owned stages (resize, FAST, GaussianBlur, fastAtan2): bit-for-bit against Python cv2
+ *    4.13 (the same OpenCV code the reference links), tests/test_oracle_cv2.py;
+ *  - the whole extractor (cell loop, quadtree, IC_Angle, rBRIEF): bit-for-bit against the
+ *    reference's OWN src/ORBextractor.cc compiled in place against oracle/refshim (oracle/_ref,
+ *    tests/test_oracle_reference_extractor.py);
+ *  - matchers, ComputeStereoMatches, LocalBA, PoseOptimization: no independent pin ("parity
+ *    unpinned"); some are cross-checked against a second Python restatement.
  */
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H

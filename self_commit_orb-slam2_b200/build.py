@@ -65,7 +65,18 @@ def build_oracle(force=False):
     return ORACLE_LIB
 
 
+def build_oracle_ref():
+    """oracle/_ref: the reference's own sources compiled in place against oracle/refshim (only where /root/reference is
+    mounted, i.e. in the build container; the GPU box uses the prebuilt files).  Checker infrastructure, never product."""
+    ref = os.environ.get("B2S_REFERENCE_ROOT", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "src")):
+        return None
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref", "REF=" + ref])
+    return os.path.join(ORACLE_DIR, "_ref")
+
+
 if __name__ == "__main__":
     build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv)
     build_oracle(force="--force" in sys.argv)
+    build_oracle_ref()
     print("built", LIB, ORACLE_LIB)
