@@ -14,8 +14,13 @@
  *  - the whole extractor (cell loop, quadtree, IC_Angle, rBRIEF): bit-for-bit against the
  *    reference's OWN src/ORBextractor.cc compiled in place against oracle/refshim (oracle/_ref,
  *    tests/test_oracle_reference_extractor.py);
- *  - matchers, ComputeStereoMatches, LocalBA, PoseOptimization: no independent pin ("parity
- *    unpinned"); some are cross-checked against a second Python restatement.
+ *  - every matcher (SearchByBoW x2, SearchByProjection x3, SearchForTriangulation, Fuse x2,
+ *    SearchBySim3): match-for-match against the reference's OWN src/ORBmatcher.cc compiled in
+ *    place against oracle/refshim (cv stand-in + Frame/KeyFrame/MapPoint data holders),
+ *    oracle/_ref/libref_matcher.so, tests/test_oracle_reference_matcher.py;
+ *  - ComputeStereoMatches, LocalBA, PoseOptimization, DBoW2 transform: no independent pin
+ *    ("parity unpinned"); cross-checked against a second Python restatement
+ *    where one exists.
  */
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H

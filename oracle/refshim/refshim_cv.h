@@ -20,6 +20,8 @@ typedef unsigned char uchar;
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
+#define CV_32FC1 5
 
 inline int cvRound(double v) { return (int)std::nearbyint(v); }  // round half to even (default rounding mode)
 inline int cvFloor(double v) { return (int)std::floor(v); }
@@ -71,20 +73,23 @@ class Mat {
   };
   int rows = 0, cols = 0;
   uchar* data = nullptr;
-  Step step;
+  Step step;  // bytes per row
+  int type_ = CV_8UC1;
+  size_t elemSize() const { return type_ == CV_32F ? 4 : 1; }
 
   Mat() {}
   Mat(int r, int c, int type) { create(r, c, type); }
   Mat(Size s, int type) { create(s.height, s.width, type); }
   // user-data constructor (no copy), as cv::Mat(rows, cols, type, data, step)
   Mat(int r, int c, int, void* d, size_t st) : rows(r), cols(c), data((uchar*)d) { step.v = st; }
-  void create(int r, int c, int) {
-    if (r == rows && c == cols && data) return;
-    buf_.reset(new std::vector<uchar>((size_t)r * c));
+  void create(int r, int c, int type) {
+    if (r == rows && c == cols && data && type == type_) return;
+    type_ = type;
+    buf_.reset(new std::vector<uchar>((size_t)r * c * elemSize()));
     rows = r;
     cols = c;
     data = buf_->data();
-    step.v = (size_t)c;
+    step.v = (size_t)c * elemSize();
   }
   void release() {
     buf_.reset();
@@ -104,15 +109,15 @@ class Mat {
       release();
       create(z.rows, z.cols, z.type);
     }
-    for (int r = 0; r < rows; r++) std::memset(data + (size_t)r * step.v, 0, cols);
+    for (int r = 0; r < rows; r++) std::memset(data + (size_t)r * step.v, 0, cols * elemSize());
     return *this;
   }
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
-  int type() const { return CV_8UC1; }
-  size_t step1() const { return step.v; }
+  int type() const { return type_; }
+  size_t step1() const { return step.v / elemSize(); }
   Mat operator()(const Rect& r) const {
     Mat m = *this;  // shares the buffer
-    m.data = data + (size_t)r.y * step.v + r.x;
+    m.data = data + (size_t)r.y * step.v + (size_t)r.x * elemSize();
     m.rows = r.height;
     m.cols = r.width;
     return m;
@@ -120,9 +125,41 @@ class Mat {
   Mat rowRange(int a, int b) const { return (*this)(Rect(0, a, cols, b - a)); }
   Mat colRange(int a, int b) const { return (*this)(Rect(a, 0, b - a, rows)); }
   Mat clone() const {
-    Mat m(rows, cols, CV_8UC1);
-    for (int r = 0; r < rows; r++) std::memcpy(m.data + (size_t)r * m.step.v, data + (size_t)r * step.v, cols);
+    Mat m(rows, cols, type_);
+    for (int r = 0; r < rows; r++) std::memcpy(m.data + (size_t)r * m.step.v, data + (size_t)r * step.v, cols * elemSize());
     return m;
+  }
+  Mat row(int r) const { return rowRange(r, r + 1); }
+  Mat col(int c) const { return colRange(c, c + 1); }
+  template <typename T>
+  T* ptr(int r = 0) {
+    return (T*)(data + (size_t)r * step.v);
+  }
+  template <typename T>
+  const T* ptr(int r = 0) const {
+    return (const T*)(data + (size_t)r * step.v);
+  }
+  // single-index access of a vector (n x 1 or 1 x n), as cv::Mat::at<T>(int)
+  template <typename T>
+  T& at(int i) {
+    return rows == 1 ? at<T>(0, i) : at<T>(i, 0);
+  }
+  template <typename T>
+  const T& at(int i) const {
+    return rows == 1 ? at<T>(0, i) : at<T>(i, 0);
+  }
+  float f(int r, int c) const { return at<float>(r, c); }
+  Mat t() const {
+    Mat m(cols, rows, type_);
+    for (int r = 0; r < rows; r++)
+      for (int c = 0; c < cols; c++) m.at<float>(c, r) = at<float>(r, c);
+    return m;
+  }
+  double dot(const Mat& b) const {  // cv::Mat::dot: double accumulation of the float products
+    double s = 0;
+    for (int r = 0; r < rows; r++)
+      for (int c = 0; c < cols; c++) s += (double)at<float>(r, c) * (double)b.at<float>(r, c);
+    return s;
   }
   template <typename T>
   T& at(int r, int c) {
@@ -138,6 +175,46 @@ class Mat {
  private:
   std::shared_ptr<std::vector<uchar> > buf_;
 };
+
+// ---- CV_32F matrix expressions as OpenCV evaluates them: gemm with double accumulators, scaling by a double alpha
+inline Mat operator*(const Mat& a, const Mat& b) {
+  Mat m(a.rows, b.cols, CV_32F);
+  for (int r = 0; r < a.rows; r++)
+    for (int c = 0; c < b.cols; c++) {
+      double s = 0;
+      for (int k = 0; k < a.cols; k++) s += (double)a.f(r, k) * (double)b.f(k, c);
+      m.at<float>(r, c) = (float)s;
+    }
+  return m;
+}
+inline Mat scaled(const Mat& a, double alpha) {
+  Mat m(a.rows, a.cols, CV_32F);
+  for (int r = 0; r < a.rows; r++)
+    for (int c = 0; c < a.cols; c++) m.at<float>(r, c) = (float)((double)a.f(r, c) * alpha);
+  return m;
+}
+inline Mat operator*(double s, const Mat& a) { return scaled(a, s); }
+inline Mat operator*(const Mat& a, double s) { return scaled(a, s); }
+inline Mat operator/(const Mat& a, double s) { return scaled(a, 1.0 / s); }
+inline Mat operator-(const Mat& a) { return scaled(a, -1.0); }
+inline Mat operator+(const Mat& a, const Mat& b) {
+  Mat m(a.rows, a.cols, CV_32F);
+  for (int r = 0; r < a.rows; r++)
+    for (int c = 0; c < a.cols; c++) m.at<float>(r, c) = a.f(r, c) + b.f(r, c);
+  return m;
+}
+inline Mat operator-(const Mat& a, const Mat& b) {
+  Mat m(a.rows, a.cols, CV_32F);
+  for (int r = 0; r < a.rows; r++)
+    for (int c = 0; c < a.cols; c++) m.at<float>(r, c) = a.f(r, c) - b.f(r, c);
+  return m;
+}
+inline double norm(const Mat& a) {  // NORM_L2
+  double s = 0;
+  for (int r = 0; r < a.rows; r++)
+    for (int c = 0; c < a.cols; c++) s += (double)a.f(r, c) * (double)a.f(r, c);
+  return std::sqrt(s);
+}
 
 class _InputArray {
  public:
