@@ -18,9 +18,11 @@
  *    SearchBySim3): match-for-match against the reference's OWN src/ORBmatcher.cc compiled in
  *    place against oracle/refshim (cv stand-in + Frame/KeyFrame/MapPoint data holders),
  *    oracle/_ref/libref_matcher.so, tests/test_oracle_reference_matcher.py;
- *  - ComputeStereoMatches, LocalBA, PoseOptimization, DBoW2 transform: no independent pin
- *    ("parity unpinned"); cross-checked against a second Python restatement
- *    where one exists.
+ *  - the DBoW2 transform: exact (doubles included) against the reference's vendored
+ *    Thirdparty/DBoW2 compiled in place (oracle/_ref/libref_dbow2.so,
+ *    tests/test_oracle_reference_dbow2.py);
+ *  - ComputeStereoMatches, LocalBA, PoseOptimization: no independent pin ("parity unpinned",
+ *    see DESIGN.md); cross-checked against a second Python restatement where one exists.
  */
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H
