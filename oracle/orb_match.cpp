@@ -183,6 +183,20 @@ struct Grid {
 };
 }  // namespace
 
+// Frame::GetFeaturesInArea (src/Frame.cc:741-852) on the grid of Frame::AssignFeaturesToGrid (:461-491): test hook for the
+// candidate enumeration every projection matcher above relies on (order included).
+extern "C" int orc_features_in_area(const float* kpx, const float* kpy, const int32_t* octave, int nf, const orc_frame_geom* g,
+                                    float x, float y, float r, int min_level, int max_level, int32_t* out, int cap) {
+  Grid* grid = new Grid();
+  grid->build(kpx, kpy, nf, g);
+  std::vector<int> cand;
+  grid->in_area(x, y, r, min_level, max_level, kpx, kpy, octave, cand);
+  delete grid;
+  if ((int)cand.size() > cap) return -1;
+  std::copy(cand.begin(), cand.end(), out);
+  return (int)cand.size();
+}
+
 // SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) — src/ORBmatcher.cc:1569-1728, from the
 // point where the last frame's map points have been projected (u, v, invzc computed by the shim at :1607-1626).
 extern "C" int orc_search_by_projection_last(const orc_proj_query* q, int nq, const float* kpx, const float* kpy,

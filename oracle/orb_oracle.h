@@ -21,8 +21,11 @@
  *  - the DBoW2 transform: exact (doubles included) against the reference's vendored
  *    Thirdparty/DBoW2 compiled in place (oracle/_ref/libref_dbow2.so,
  *    tests/test_oracle_reference_dbow2.py);
- *  - ComputeStereoMatches, LocalBA, PoseOptimization: no independent pin ("parity unpinned",
- *    see DESIGN.md); cross-checked against a second Python restatement where one exists.
+ *  - ComputeStereoMatches, the Frame feature grid, the isInFrustum -> SearchByProjection chain:
+ *    against the reference's OWN src/Frame.cc compiled in place with its extractor and matcher
+ *    (oracle/_ref/libref_frame.so, tests/test_oracle_reference_frame.py), float for float;
+ *  - LocalBA, PoseOptimization: no independent pin ("parity unpinned") —
+ *    src/Optimizer.cc needs g2o + Eigen, and Eigen is not in this image.
  */
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H
@@ -94,6 +97,10 @@ typedef struct {
   const float* scale_factors; /* mvScaleFactors[nlevels] */
   int nlevels;
 } orc_frame_geom;
+
+/* Frame::GetFeaturesInArea (src/Frame.cc:741-852): indices in the reference's order; returns the count, -1 if > cap */
+int orc_features_in_area(const float* kpx, const float* kpy, const int32_t* octave, int nf, const orc_frame_geom* g, float x,
+                         float y, float r, int min_level, int max_level, int32_t* out, int cap);
 
 /* feats: current frame; kpx,kpy,octave,angle from mvKeysUn; uright = mvuRight; occupied = feature already holds a
  * MapPoint with Observations()>0 (src/ORBmatcher.cc:1658-1660).

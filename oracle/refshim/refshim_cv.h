@@ -6,6 +6,7 @@
 // containers (Mat with ROI views, KeyPoint, Point, ...) only reproduce OpenCV's semantics, not its code.
 #pragma once
 #include <algorithm>
+#include <climits>
 #include <cassert>
 #include <cstdlib>
 #include <cmath>
@@ -129,6 +130,27 @@ class Mat {
     for (int r = 0; r < rows; r++) std::memcpy(m.data + (size_t)r * m.step.v, data + (size_t)r * step.v, cols * elemSize());
     return m;
   }
+  Mat reshape(int) const { return *this; }  // only reached on the distortion path, which the pinning tests do not take
+  static Mat ones(int r, int c, int type) {
+    Mat m(r, c, type);
+    for (int i = 0; i < r; i++)
+      for (int j = 0; j < c; j++) m.at<float>(i, j) = 1.0f;
+    return m;
+  }
+  // u8 -> f32 (the only conversion the reference asks for); a differently-typed destination is reallocated, so
+  // converting a pyramid ROI "in place" leaves the pyramid untouched, as in OpenCV
+  void convertTo(Mat& dst, int type) const {
+    Mat m(rows, cols, type);
+    for (int r = 0; r < rows; r++)
+      for (int c = 0; c < cols; c++) {
+        const float v = type_ == CV_32F ? at<float>(r, c) : (float)at<uchar>(r, c);
+        if (type == CV_32F)
+          m.at<float>(r, c) = v;
+        else
+          m.at<uchar>(r, c) = (uchar)v;
+      }
+    dst = m;
+  }
   Mat row(int r) const { return rowRange(r, r + 1); }
   Mat col(int c) const { return colRange(c, c + 1); }
   template <typename T>
@@ -216,6 +238,35 @@ inline double norm(const Mat& a) {  // NORM_L2
   return std::sqrt(s);
 }
 
+enum { NORM_L1 = 2, NORM_L2 = 4 };
+inline double norm(const Mat& a, const Mat& b, int type) {  // NORM_L1 of a CV_32F difference, double accumulator
+  double s = 0;
+  for (int r = 0; r < a.rows; r++)
+    for (int c = 0; c < a.cols; c++) {
+      const double d = (double)a.f(r, c) - (double)b.f(r, c);
+      s += type == NORM_L1 ? std::fabs(d) : d * d;
+    }
+  return type == NORM_L1 ? s : std::sqrt(s);
+}
+// cv::Mat_<float>(r, c) << a, b, c
+template <typename T>
+class Mat_ : public Mat {
+ public:
+  Mat_(int r, int c) : Mat(r, c, CV_32F) {}
+  struct Comma {
+    Mat m;
+    int i;
+    Comma operator,(T v) {
+      m.at<T>(i / m.cols, i % m.cols) = v;
+      return Comma{m, i + 1};
+    }
+    operator Mat() const { return m; }
+  };
+  Comma operator<<(T v) {
+    at<T>(0, 0) = v;
+    return Comma{*this, 1};
+  }
+};
 class _InputArray {
  public:
   _InputArray() : m_(nullptr) {}
@@ -235,6 +286,9 @@ class _OutputArray : public _InputArray {
 typedef const _InputArray& InputArray;
 typedef const _OutputArray& OutputArray;
 
+inline void undistortPoints(const Mat&, Mat&, const Mat&, const Mat&, const Mat&, const Mat&) {
+  std::abort();  // Frame::UndistortKeyPoints returns before this when mDistCoef[0] == 0 (src/Frame.cc:905-909)
+}
 inline float fastAtan2(float y, float x) { return orc_fast_atan2(y, x); }
 
 inline void resize(const Mat& src, Mat& dst, Size dsize, double, double, int interpolation) {

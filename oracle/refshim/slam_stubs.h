@@ -10,10 +10,19 @@
 // Mutating calls (AddObservation, AddMapPoint, Replace) are recorded in a log the glue reads back.
 #ifndef B2S_REF_SLAM_STUBS_H
 #define B2S_REF_SLAM_STUBS_H
+//
+// Two modes.  Default: Frame is a stand-in too (ORBmatcher.cc alone).  With -DB2S_STUB_REAL_FRAME the reference's own
+// Frame.h / Frame.cc and the vendored DBoW2 BowVector / FeatureVector are used, and only MapPoint, KeyFrame, Converter
+// and ORBVocabulary are stand-ins (src/Frame.cc compiled in place: ComputeStereoMatches, isInFrustum, the feature grid).
 #define MAPPOINT_H
 #define KEYFRAME_H
+#ifdef B2S_STUB_REAL_FRAME
+#define CONVERTER_H
+#define ORBVOCABULARY_H
+#else
 #define FRAME_H
 #define __D_T_FEATURE_VECTOR__
+#endif
 
 #include <opencv2/core/core.hpp>
 
@@ -26,10 +35,15 @@
 
 using namespace std;  // the reference headers rely on it (ORBmatcher.h uses unqualified vector / pair)
 
+#ifdef B2S_STUB_REAL_FRAME
+#include "Thirdparty/DBoW2/DBoW2/BowVector.h"
+#include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
+#else
 namespace DBoW2 {
 typedef unsigned int NodeId;
 class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
 }  // namespace DBoW2
+#endif
 
 namespace ORB_SLAM2 {
 
@@ -74,8 +88,8 @@ class MapPoint {
   int GetIndexInKeyFrame(KeyFrame* kf) { return mObservations.count(kf) ? (int)mObservations[kf] : -1; }
   void AddObservation(KeyFrame* kf, size_t idx) { stub_log().push_back({0, this, kf, (long)idx}); }
   void Replace(MapPoint* other) { stub_log().push_back({2, this, other, -1}); }
-  template <class F>
-  int PredictScaleT(const float& currentDist, F* f) {
+  template <class F>  // F = KeyFrame or Frame (instantiated at the call, when the type is complete)
+  int PredictScale(const float& currentDist, F* f) {
     float ratio = mfMaxDistance / currentDist;
     int nScale = ceil(log(ratio) / f->mfLogScaleFactor);
     if (nScale < 0)
@@ -84,8 +98,6 @@ class MapPoint {
       nScale = f->mnScaleLevels - 1;
     return nScale;
   }
-  int PredictScale(const float& d, KeyFrame* kf) { return PredictScaleT(d, kf); }
-  int PredictScale(const float& d, Frame* f) { return PredictScaleT(d, f); }
 };
 
 // what Frame and KeyFrame share for the matcher
@@ -144,6 +156,22 @@ class FeatureHolder {
   }
 };
 
+#ifdef B2S_STUB_REAL_FRAME
+// Converter::toDescriptorVector (src/Converter.cc:37-47) and an ORBVocabulary whose transform records nothing: Frame.cc
+// only needs them to compile (ComputeBoW is pinned separately through the vendored DBoW2, ref_dbow2_glue.cpp)
+class Converter {
+ public:
+  static std::vector<cv::Mat> toDescriptorVector(const cv::Mat& Descriptors) {
+    std::vector<cv::Mat> v;
+    for (int j = 0; j < Descriptors.rows; j++) v.push_back(Descriptors.row(j));
+    return v;
+  }
+};
+class ORBVocabulary {
+ public:
+  void transform(const std::vector<cv::Mat>&, DBoW2::BowVector&, DBoW2::FeatureVector&, int) {}
+};
+#else
 class Frame : public FeatureHolder {
  public:
   static float fx, fy, cx, cy, invfx, invfy;
@@ -156,6 +184,7 @@ class Frame : public FeatureHolder {
     return Area(mnMinX, mnMinY, x, y, r, minLevel, maxLevel);
   }
 };
+#endif
 
 class KeyFrame : public FeatureHolder {
  public:
