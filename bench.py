@@ -34,6 +34,11 @@ B_FAST_IMAGE = 1444097           # FAST stage: every pyramid pixel read once (su
 # dram__bytes_read.sum + dram__bytes_write.sum of one 320-image k_fast_cells launch (ncu --set full,
 # profiles/r1_ncu_full_k_fast_cells_v15.csv: 408.31 MB + 46.83 MB), per image
 TRAFFIC_FAST_IMAGE = (408313600 + 46831616) / 320.0
+# SURVEY.md §8(d), LocalBA 50 keyframes / 5000 points / 30 k stereo edges, per LM trial: buildSystem 6.1 MB + Schur 5.4 MB +
+# back-substitution 4.3 MB ~= 16 MB, ~= 64 MFLOP (FP64)
+BA_BYTES_TRIAL = 16.0e6
+BA_FLOP_TRIAL = 64.0e6
+FP64_NOMINAL_TFLOPS = 37.0       # B200 data sheet (HGX B200: 296 TFLOP/s FP64 over 8 GPUs); not in MEASURED_PEAKS.json
 BA_EVERY = 5
 
 
@@ -290,6 +295,10 @@ def run_b200(args, rank, local_rank, world):
         ss.opt.LocalBundleAdjustmentBatch([ss.ba_problem] * ss.n_ba)
         phase["local_ba_batch_ms"] = (time.perf_counter() - t1) * 1e3
         phase["local_ba_windows"] = ss.n_ba
+        try:
+            ba_kernel_ms, ba_trials = ss.opt.last_kernel_ms()
+        except Exception:
+            ba_kernel_ms, ba_trials = 0.0, 0
 
     # ---------------- end to end through the host-buffer C ABI (`e2e`)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -313,6 +322,19 @@ def run_b200(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
     peaks, peak_src = load_peaks()
+    roofline_ba = None
+    if ss.n_ba and ba_kernel_ms > 0:
+        ba_gbs = BA_BYTES_TRIAL * ba_trials / (ba_kernel_ms * 1e-3) / 1e9
+        roofline_ba = {"kernel": "k_local_ba (persistent LM loop: %d windows x 4 CTAs, one launch per LocalBA batch)" % ss.n_ba,
+                       "bound": "hbm", "achieved": ba_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": ba_gbs / peaks["hbm_gbs"], "traffic": None,
+                       "launch_ms": ba_kernel_ms, "launch_ms_source": "CUDA events on the solver stream, batch run alone",
+                       "lm_trials": ba_trials, "algorithmic_bytes_per_launch": BA_BYTES_TRIAL * ba_trials,
+                       "fp64": {"achieved_tflops": BA_FLOP_TRIAL * ba_trials / (ba_kernel_ms * 1e-3) / 1e12,
+                                "nominal_peak_tflops": FP64_NOMINAL_TFLOPS},
+                       "note": "latency-bound (dependent index->operand chains at 8 warps/SM), see profiles/README.md; "
+                               "the window state (6 MB) lives in L2, so DRAM traffic is far below the algorithmic bytes"}
+
     fast_ms = stage[1] / max(1, calls.value)
     images_per_launch = 2 * F
     achieved = B_FAST_IMAGE * images_per_launch / (fast_ms * 1e-3) / 1e9 if fast_ms > 0 else 0.0
@@ -343,6 +365,8 @@ def run_b200(args, rank, local_rank, world):
                                                            "blur": stage[3] / max(1, calls.value),
                                                            "orient_describe": stage[4] / max(1, calls.value)}}},
     }
+    if roofline_ba is not None:
+        line["roofline_local_ba"] = roofline_ba
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line), flush=True)

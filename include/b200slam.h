@@ -303,6 +303,9 @@ typedef struct b2s_ba_solver b2s_ba_solver;
 int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batch, int device, b2s_ba_solver** out);
 void b2s_ba_destroy(b2s_ba_solver* h);
 long long b2s_ba_launch_count(const b2s_ba_solver* h);
+/* Duration (CUDA events on the solver's stream) of the persistent LM kernel of the last b2s_local_ba(_batch) call and the
+ * number of LM trials (accepted + rejected, all windows) it ran — measurement hook for bench.py's roofline. */
+float b2s_ba_last_kernel_ms(const b2s_ba_solver* h, long long* lm_trials);
 /* Optimizer::LocalBundleAdjustment from graph construction to write-back values. stop: pbStopFlag (may be NULL). */
 int b2s_local_ba(b2s_ba_solver* h, const b2s_ba_problem* p, const volatile uint8_t* stop, b2s_ba_result* r);
 /* `batch` independent windows solved concurrently (replicas). */

@@ -545,7 +545,7 @@ struct BA {
     return Xc[2] > 0.0;
   }
 
-  int run(orc_ba_result* r) {
+  void init() {
     const int ne = P->n_edges;
     poses.resize(P->n_kf);
     pose_index.assign(P->n_kf, -1);
@@ -566,6 +566,11 @@ struct BA {
     Hpl.assign((size_t)ne * 18, 0.0);
     b.assign((size_t)n_free * 6 + (size_t)P->n_mp * 3, 0.0);
     x.assign(b.size(), 0.0);
+  }
+
+  int run(orc_ba_result* r) {
+    const int ne = P->n_edges;
+    init();
     if (terminate()) return 1;  // src/Optimizer.cc:858-860
     robust = true;
     optimize(P->its1);
@@ -857,6 +862,44 @@ extern "C" int orc_pose_optimization(const orc_pose_problem* p, orc_pose_result*
   PO po;
   po.P = p;
   return po.run(r);
+}
+
+// ---- test hooks (tests/test_oracle_ba_math.py): the linear system of the first LM iteration and one damped solve, and
+// the pose retraction, exposed so that they can be checked against first principles (numeric differentiation of the
+// projection, a dense solve of the full normal equations, the matrix exponential of the twist).
+extern "C" int orc_ba_debug_linear_system(const orc_ba_problem* p, int robust, double lambda, double* Hpp, double* Hll,
+                                          double* Hpl, double* b, double* err, double* chi2, int32_t* pose_index, double* x) {
+  BA ba;
+  ba.P = p;
+  ba.stop = nullptr;
+  ba.init();
+  ba.robust = robust != 0;
+  ba.rebuild_structure();
+  ba.compute_errors();
+  ba.build_system();
+  std::copy(ba.Hpp.begin(), ba.Hpp.end(), Hpp);
+  std::copy(ba.Hll.begin(), ba.Hll.end(), Hll);
+  std::copy(ba.Hpl.begin(), ba.Hpl.end(), Hpl);
+  std::copy(ba.b.begin(), ba.b.end(), b);
+  std::copy(ba.err.begin(), ba.err.end(), err);
+  std::copy(ba.chi2.begin(), ba.chi2.end(), chi2);
+  std::copy(ba.pose_index.begin(), ba.pose_index.end(), pose_index);
+  if (x) {
+    if (!ba.solve(lambda)) return -1;
+    std::copy(ba.x.begin(), ba.x.end(), x);
+  }
+  return ba.n_free;
+}
+
+extern "C" void orc_se3_oplus(const float* Tcw16, const double* upd6, double* R9, double* t3) {
+  Pose T = pose_from_Tcw(Tcw16);
+  pose_oplus(T, upd6);
+  double R[3][3];
+  quat_to_R(T.r, R);
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) R9[i * 3 + j] = R[i][j];
+    t3[i] = T.t[i];
+  }
 }
 
 extern "C" int orc_local_ba(const orc_ba_problem* p, const volatile uint8_t* stop, orc_ba_result* r) {

@@ -259,6 +259,13 @@ typedef struct {
 /* stop: optional async abort flag (pbStopFlag). Returns 0 ok, 1 aborted before round 1 (no write-back). */
 int orc_local_ba(const orc_ba_problem* p, const volatile uint8_t* stop, orc_ba_result* r);
 
+/* test hooks (tests/test_oracle_ba_math.py): the linear system of the first LM iteration at the initial estimate
+ * (Hpp n_free x 36, Hll n_mp x 9, Hpl n_edges x 18 = per-edge 6x3 block, b = [poses | points]), its damped Schur solve
+ * x for (H + lambda I) x = b, and the pose retraction exp(upd) * T (upd = [omega, upsilon]).  Returns n_free. */
+int orc_ba_debug_linear_system(const orc_ba_problem* p, int robust, double lambda, double* Hpp, double* Hll, double* Hpl,
+                               double* b, double* err, double* chi2, int32_t* pose_index, double* x);
+void orc_se3_oplus(const float* Tcw16, const double* upd6, double* R9, double* t3);
+
 /* ---------------- helpers (orb_misc.cpp) ---------------- */
 void orc_sincosf_batch(const float* in, long n, float* s, float* c, int threads); /* glibc sinf/cosf */
 int orc_extract_many(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t* imgs, int count,

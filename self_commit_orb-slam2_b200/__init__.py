@@ -118,6 +118,8 @@ def lib():
             L.b2s_ba_destroy.restype = None
             L.b2s_ba_launch_count.restype = ctypes.c_longlong
             L.b2s_ba_launch_count.argtypes = [_vp]
+            L.b2s_ba_last_kernel_ms.restype = ctypes.c_float
+            L.b2s_ba_last_kernel_ms.argtypes = [_vp, _vp]
             L.b2s_local_ba.argtypes = [_vp, _vp, _vp, _vp]
             L.b2s_local_ba_batch.argtypes = [_vp, ctypes.c_int, _vp, _vp]
         _lib = L
@@ -471,6 +473,13 @@ class Optimizer:
 
     def launch_count(self):
         return lib().b2s_ba_launch_count(self._h)
+
+    def last_kernel_ms(self):
+        """(ms, trials): duration of the persistent LM kernel of the last LocalBundleAdjustment(Batch) call, measured with
+        CUDA events on the solver's stream, and the LM trials it ran over all windows."""
+        n = ctypes.c_longlong(0)
+        ms = lib().b2s_ba_last_kernel_ms(self._h, ctypes.byref(n))
+        return float(ms), int(n.value)
 
     @staticmethod
     def _problem(d, its1=5, its2=10):

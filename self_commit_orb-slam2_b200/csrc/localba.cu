@@ -1893,6 +1893,9 @@ struct b2s_ba_solver {
   BaHostStage hs;
   size_t smemBytes = 0;
   int numSMs = 0;
+  cudaEvent_t evLm[2] = {nullptr, nullptr};  // around the persistent LM kernel of the last batch (b2s_ba_last_kernel_ms)
+  float lastLmMs = 0.f;
+  long long lastTrials = 0;
 };
 
 static void quat_from_R_host(const double m[3][3], double* q) {
@@ -2015,6 +2018,8 @@ extern "C" void b2s_ba_destroy(b2s_ba_solver* h) {
   pose_scratch_free(h->pose);
   for (void* p : h->allocs) cudaFree(p);
   for (void* p : h->hostAllocs) cudaFreeHost(p);
+  for (auto& e : h->evLm)
+    if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   delete h;
@@ -2187,6 +2192,11 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
   k_block_order<<<batch, 256, 0, st>>>(d);
   // ---- the whole LM loop of every window: one persistent launch, nCta co-resident CTAs per window
   if (dbg) cudaEventRecord(ev[1], st);
+  if (!h->evLm[0]) {
+    B2S_CUDA(cudaEventCreate(&h->evLm[0]));
+    B2S_CUDA(cudaEventCreate(&h->evLm[1]));
+  }
+  B2S_CUDA(cudaEventRecord(h->evLm[0], st));
   int chunk = std::min(batch, h->numSMs);  // windows per cooperative launch (all their CTAs must be co-resident)
   if (const char* ev = getenv("B2S_BA_CHUNK")) chunk = std::max(1, std::min(chunk, atoi(ev)));  // tuning knob
   int nCta = std::max(1, std::min(16, h->numSMs / chunk));
@@ -2200,6 +2210,7 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
     h->launches++;
   }
   h->launches += 5;
+  B2S_CUDA(cudaEventRecord(h->evLm[1], st));
   if (dbg) cudaEventRecord(ev[2], st);
   // asynchronous abort (LocalMapping::InsertKeyFrame sets mbAbortBA): forward the flag while the kernel runs
   if (stop) {
@@ -2223,6 +2234,9 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
   if (dbg) cudaEventRecord(ev[3], st);
   B2S_CUDA(cudaStreamSynchronize(st));
   B2S_CUDA(cudaGetLastError());
+  cudaEventElapsedTime(&h->lastLmMs, h->evLm[0], h->evLm[1]);
+  h->lastTrials = 0;
+  for (int w = 0; w < batch; w++) h->lastTrials += s.st[w].nTrials;
   for (int w = 0; w < batch; w++)
     if (s.st[w].finishedRound0) {
       set_error("b2s_local_ba: window %d: LM kernel barrier timed out (CTAs not co-resident?)", w);
@@ -2290,6 +2304,12 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
     for (auto& e : ev) cudaEventDestroy(e);
   }
   return B2S_OK;
+}
+
+extern "C" float b2s_ba_last_kernel_ms(const b2s_ba_solver* h, long long* lm_trials) {
+  if (!h) return 0.f;
+  if (lm_trials) *lm_trials = h->lastTrials;
+  return h->lastLmMs;
 }
 
 extern "C" int b2s_local_ba(b2s_ba_solver* h, const b2s_ba_problem* p, const volatile uint8_t* stop, b2s_ba_result* r) {
