@@ -24,6 +24,8 @@
  *  - ComputeStereoMatches, the Frame feature grid, the isInFrustum -> SearchByProjection chain:
  *    against the reference's OWN src/Frame.cc compiled in place with its extractor and matcher
  *    (oracle/_ref/libref_frame.so, tests/test_oracle_reference_frame.py), float for float;
+ *  - ComputeDistinctiveDescriptors: against the reference's OWN src/MapPoint.cc compiled in place
+ *    (oracle/_ref/libref_mappoint.so, tests/test_oracle_reference_mappoint.py);
  *  - LocalBA, PoseOptimization: no independent pin ("parity unpinned") —
  *    src/Optimizer.cc needs g2o + Eigen, and Eigen is not in this image.
  */

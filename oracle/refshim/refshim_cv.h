@@ -151,6 +151,10 @@ class Mat {
       }
     dst = m;
   }
+  void copyTo(Mat& dst) const {  // deep copy into a (re)allocated destination
+    Mat m = clone();
+    dst = m;
+  }
   Mat row(int r) const { return rowRange(r, r + 1); }
   Mat col(int c) const { return colRange(c, c + 1); }
   template <typename T>
