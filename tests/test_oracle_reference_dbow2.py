@@ -63,7 +63,7 @@ def assemble(word, w, node):
 
 @pytest.mark.parametrize("k,L,seed,levelsup,ragged", [(10, 4, 7, 4, True), (10, 4, 7, 2, True), (6, 5, 9, 4, False), (10, 3, 11, 1, True),
                                                        (10, 6, 13, 4, True)])
-def test_transform_equals_reference_dbow2(oracle, tmp_path, k, L, seed, levelsup, ragged):
+def test_transform_equals_reference_dbow2(checker, tmp_path, k, L, seed, levelsup, ragged):
     if L == 6:
         k = 4  # keep the node count moderate
     voc = synth_vocabulary(k=k, L=L, seed=seed, ragged=ragged)
@@ -71,7 +71,7 @@ def test_transform_equals_reference_dbow2(oracle, tmp_path, k, L, seed, levelsup
     path = str(tmp_path / "voc.txt")
     write_vocabulary_txt(voc, path)
     r = run_reference(path, feats, levelsup)
-    nw, word, w, node = oracle.bow_transform(voc, feats, levelsup)
+    nw, word, w, node = checker.bow_transform(voc, feats, levelsup)
     assert r["n_words"] == int(voc["leaf_flag"].sum())
     assert np.array_equal(r["word"], word)
     assert np.array_equal(r["weight"], w)          # doubles, exact

@@ -40,12 +40,12 @@ def _run(R, img, nf):
 
 @pytest.mark.parametrize("w,h,nf,seed", [(640, 480, 1000, 3), (1241, 376, 2000, 3), (1241, 376, 2000, 5), (321, 243, 500, 7),
                                          (752, 480, 1200, 9)])
-def test_reference_source_equals_oracle(oracle, w, h, nf, seed):
+def test_reference_source_equals_oracle(checker, w, h, nf, seed):
     R = _ref()
     R.ref_set_monotonic_allocator(1)
     img = synth_image(w, h, seed) if seed != 5 else synth_stereo(w, h, seed)[1]
     rk, rd = _run(R, img, nf)
-    ok, od = oracle.extractor(nf, 1.2, 8, 20, 7)(img)
+    ok, od = checker.extractor(nf, 1.2, 8, 20, 7)(img)  # the oracle (CPU suite) or the CUDA extractor (-m gpu)
     assert len(rk) == len(ok)
     for i, f in enumerate(FIELDS):
         assert np.array_equal(rk[:, i], ok[f].astype(np.float32)), f

@@ -129,7 +129,7 @@ def test_features_in_area_equals_reference_frame(oracle):
 
 
 @pytest.mark.parametrize("seed,th", [(5, 1.0), (6, 3.0)])
-def test_search_local_points_chain_equals_reference(oracle, seed, th):
+def test_search_local_points_chain_equals_reference(oracle, checker, seed, th):
     imL, imR = synth_stereo(1241, 376, seed)
     F = RefFrame(imL, imR, 2000)
     rng = np.random.RandomState(seed)
@@ -178,8 +178,40 @@ def test_search_local_points_chain_equals_reference(oracle, seed, th):
     q["level"], q["in_view"], q["has_obs"], q["desc"] = level, inview, 1, desc
     geom = dict(mnMinX=np.float32(0), mnMinY=np.float32(0), mnMaxX=np.float32(F.w), mnMaxY=np.float32(F.h), bf=np.float32(BF),
                 scale_factors=sc)
-    no, mo = oracle.search_by_projection_map(q, np.ascontiguousarray(F.kpsL["x"]), np.ascontiguousarray(F.kpsL["y"]),
+    no, mo = checker.search_by_projection_map(q, np.ascontiguousarray(F.kpsL["x"]), np.ascontiguousarray(F.kpsL["y"]),
                                              np.ascontiguousarray(F.kpsL["octave"]), F.uright, np.zeros(F.N, np.uint8), F.descL,
                                              geom, th=th, th_high=100, nnratio=0.8)
     assert nr == no and nr > 300
     assert np.array_equal(match, mo)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,nf,seed", [(640, 480, 1000, 9), (1241, 376, 2000, 3)])
+def test_cuda_stereo_matches_equal_reference_frame(pkg, w, h, nf, seed):
+    """The CUDA ComputeStereoMatches kernel against the reference Frame directly: the device extracts the same stereo pair
+    (its resident pyramids are the reference's, bit for bit), is handed the REFERENCE frame's keypoints and descriptors, and
+    must return the reference frame's mvuRight / mvDepth."""
+    import torch
+    imL, imR = synth_stereo(w, h, seed)
+    F = RefFrame(imL, imR, nf)
+    ex = pkg.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=2)
+    ex.extract_batch([imL, imR])
+    cap = ex.cap
+    assert F.N <= cap and F.NR <= cap
+    kps = np.zeros((2, cap), kp_dtype)
+    desc = np.zeros((2, cap, 32), np.uint8)
+    kps[0, :F.N], kps[1, :F.NR] = F.kpsL, F.kpsR
+    desc[0, :F.N], desc[1, :F.NR] = F.descL, F.descR
+    d_kps = torch.from_numpy(kps.view(np.uint8).reshape(2, cap, 28)).cuda()
+    d_desc = torch.from_numpy(desc).cuda()
+    d_cnt = torch.tensor([F.N, F.NR], dtype=torch.int32).cuda()
+    ur = torch.full((1, cap), -2.0, dtype=torch.float32, device="cuda")
+    dp = torch.full((1, cap), -2.0, dtype=torch.float32, device="cuda")
+    nm = torch.zeros(1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ex.stereo_match_device(0, 1, 1, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), cap, BF, 0.0, ur.data_ptr(),
+                           dp.data_ptr(), nm.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(nm.item()) == int((F.uright >= 0).sum()) and int(nm.item()) > 100
+    assert np.array_equal(ur.cpu().numpy()[0, :F.N], F.uright)
+    assert np.array_equal(dp.cpu().numpy()[0, :F.N], F.depth)

@@ -16,7 +16,7 @@ vp, c_i, c_f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 
 
 @pytest.mark.parametrize("seed,near_dup", [(1, False), (2, True), (3, True)])
-def test_distinctive_descriptor_equals_reference_mappoint(oracle, seed, near_dup):
+def test_distinctive_descriptor_equals_reference_mappoint(checker, seed, near_dup):
     rng = np.random.RandomState(seed)
     n_kf, per_kf, n_pts = 40, 300, 600
     kf_off = (np.arange(n_kf + 1) * per_kf).astype(np.int32)
@@ -61,7 +61,7 @@ def test_distinctive_descriptor_equals_reference_mappoint(oracle, seed, near_dup
         lists.append(kf_desc[obs_kf[q] * per_kf + obs_idx[q]])
         offs.append(offs[-1] + len(q))
     flat = np.concatenate([l for l in lists if len(l)]) if offs[-1] else np.zeros((0, 32), np.uint8)
-    best = oracle.distinctive_descriptors(flat, np.array(offs, np.int32))
+    best = checker.distinctive_descriptors(flat, np.array(offs, np.int32))
     n_checked = 0
     for p in range(n_pts):
         if len(lists[p]) == 0:

@@ -16,7 +16,10 @@ the oracle function the GPU parity tests use:
 
 Where the reference projects the map points itself, the glue exports the post-projection queries (same expressions on
 the same cv stand-in) and the oracle consumes those — so the comparison covers candidate enumeration, gates, distances,
-tie-breaking, greedy state and the rotation-histogram cull, bit for bit."""
+tie-breaking, greedy state and the rotation-histogram cull, bit for bit.
+
+Every case runs twice (conftest.py `checker`): oracle vs reference source in the CPU suite, and — marked gpu — the CUDA
+kernels vs the reference source directly."""
 import ctypes
 import os
 
@@ -141,7 +144,7 @@ def _bow_inputs(n, seed, match_frac):
 
 
 @pytest.mark.parametrize("n,seed,match_frac,check_ori", [(1500, 11, 0.7, 1), (1500, 12, 0.3, 1), (600, 13, 0.9, 0)])
-def test_search_by_bow_keyframe_frame(ref, oracle, n, seed, match_frac, check_ori):
+def test_search_by_bow_keyframe_frame(ref, checker, n, seed, match_frac, check_ori):
     A, nodeA, validA, angA, Bd, nodeB, angB, xy, octv, ur, rng = _bow_inputs(n, seed, match_frac)
     k = Keep()
     # invalid keyframe features: half without a map point, half with a bad one
@@ -156,14 +159,14 @@ def test_search_by_bow_keyframe_frame(ref, oracle, n, seed, match_frac, check_or
     m = np.full(n, -1, np.int32)
     c = cam()
     nr = ref.ref_search_by_bow_kf_f(B(c), B(kf), B(pts), B(fr), 0.7, check_ori, m.ctypes.data)
-    no, mo = oracle.search_by_bow(A, nodeA, validA, angA, Bd, nodeB, angB, th_low=50, nnratio=0.7, strict_lt=False,
+    no, mo = checker.search_by_bow(A, nodeA, validA, angA, Bd, nodeB, angB, th_low=50, nnratio=0.7, strict_lt=False,
                                   check_ori=bool(check_ori))
     assert nr == no and nr > n * match_frac * 0.3
     assert np.array_equal(m, mo)
 
 
 @pytest.mark.parametrize("n,seed,match_frac,check_ori", [(1500, 21, 0.7, 1), (800, 22, 0.5, 0)])
-def test_search_by_bow_keyframe_keyframe(ref, oracle, n, seed, match_frac, check_ori):
+def test_search_by_bow_keyframe_keyframe(ref, checker, n, seed, match_frac, check_ori):
     A, nodeA, validA, angA, Bd, nodeB, angB, xy, octv, ur, rng = _bow_inputs(n, seed, match_frac)
     validB = (rng.randint(0, 100, size=n) < 90).astype(np.uint8)
     k = Keep()
@@ -179,7 +182,7 @@ def test_search_by_bow_keyframe_keyframe(ref, oracle, n, seed, match_frac, check
     m12 = np.full(n, -1, np.int32)
     c = cam()
     nr = ref.ref_search_by_bow_kf_kf(B(c), B(kf1), B(kf2), B(pts), 0.75, check_ori, m12.ctypes.data)
-    no, mB = oracle.search_by_bow(A, nodeA, validA, angA, Bd, nodeB, angB, validB=validB, th_low=50, nnratio=0.75,
+    no, mB = checker.search_by_bow(A, nodeA, validA, angA, Bd, nodeB, angB, validB=validB, th_low=50, nnratio=0.75,
                                   strict_lt=True, check_ori=bool(check_ori))
     assert nr == no and nr > 50
     # the oracle reports per kf2 feature, the reference per kf1 feature
@@ -191,7 +194,7 @@ def test_search_by_bow_keyframe_keyframe(ref, oracle, n, seed, match_frac, check
 
 # ---------------------------------------------------------------- SearchByProjection(Frame&, local map points)
 @pytest.mark.parametrize("seed,cluster,th", [(31, False, 1.0), (32, True, 3.0), (33, False, 5.0)])
-def test_search_by_projection_map(ref, oracle, seed, cluster, th):
+def test_search_by_projection_map(ref, checker, seed, cluster, th):
     d = synth_projection_map(nf=1500, nq=1800, seed=seed, cluster=cluster)
     sf, _ = scale_tables()
     q, nf, nq = d["q"], len(d["kpx"]), len(d["q"])
@@ -225,7 +228,7 @@ def test_search_by_projection_map(ref, oracle, seed, cluster, th):
     nr = ref.ref_search_by_projection_map(B(c), B(fr), B(pts), qi.ctypes.data, nq, th, 0.8, m.ctypes.data)
     g = dict(d["geom"])
     g["scale_factors"] = sf
-    no, mo = oracle.search_by_projection_map(q, d["kpx"], d["kpy"], d["octave"], d["uright"], d["occupied"], d["desc"], g, th=th,
+    no, mo = checker.search_by_projection_map(q, d["kpx"], d["kpy"], d["octave"], d["uright"], d["occupied"], d["desc"], g, th=th,
                                              th_high=100, nnratio=0.8)
     assert nr == no and nr > 200
     assert np.array_equal(m, mo)
@@ -313,7 +316,7 @@ def _points_seen_from(rng, f, Tcw, n, sf, px_noise=1.5, flips=30, S=None, src=No
 # ---------------------------------------------------------------- SearchByProjection(Current, Last)
 @pytest.mark.parametrize("seed,dz,mono,want_mode,check_ori", [(41, 0.9, 0, 1, 1), (42, -0.9, 0, 2, 1), (43, 0.1, 0, 0, 1),
                                                                (44, 0.9, 1, 0, 1), (45, 0.9, 0, 1, 0)])
-def test_search_by_projection_last(ref, oracle, seed, dz, mono, want_mode, check_ori):
+def test_search_by_projection_last(ref, checker, seed, dz, mono, want_mode, check_ori):
     rng = np.random.RandomState(seed)
     sf, _ = scale_tables()
     nf = 1500
@@ -355,7 +358,7 @@ def test_search_by_projection_last(ref, oracle, seed, dz, mono, want_mode, check
     keep = np.nonzero(q["octave"] >= 0)[0]
     g = dict(mnMinX=np.float32(0), mnMinY=np.float32(0), mnMaxX=np.float32(W), mnMaxY=np.float32(H), bf=np.float32(BF),
              scale_factors=sf)
-    no, mo = oracle.search_by_projection_last(np.ascontiguousarray(q[keep]), cur["x"], cur["y"], cur["octave"], cur["angle"],
+    no, mo = checker.search_by_projection_last(np.ascontiguousarray(q[keep]), cur["x"], cur["y"], cur["octave"], cur["angle"],
                                               cur["uright"], occupied, cur["desc"], g, th, mode=mode.value, th_high=100,
                                               check_ori=bool(check_ori))
     assert nr == no and nr > 150
@@ -365,7 +368,7 @@ def test_search_by_projection_last(ref, oracle, seed, dz, mono, want_mode, check
 
 # ---------------------------------------------------------------- SearchForTriangulation
 @pytest.mark.parametrize("seed,only_stereo,check_ori", [(117, 0, 1), (118, 1, 1), (119, 0, 0)])
-def test_search_for_triangulation(ref, oracle, seed, only_stereo, check_ori):
+def test_search_for_triangulation(ref, checker, seed, only_stereo, check_ori):
     d = synth_triangulation(n=1500, seed=seed)
     sf, s2 = scale_tables()
     n = len(d["kf1"]["x"])
@@ -388,7 +391,7 @@ def test_search_for_triangulation(ref, oracle, seed, only_stereo, check_ori):
     nr = ref.ref_search_for_triangulation(B(c), B(f1), B(f2), B(pts), F12.ctypes.data, only_stereo, check_ori, m.ctypes.data,
                                           ep.ctypes.data)
     assert abs(float(ep[0]) - float(d["ex"])) < 0.05 and abs(float(ep[1]) - float(d["ey"])) < 0.05
-    no, mo = oracle.search_for_triangulation(d["kf1"], d["kf2"], F12, float(ep[0]), float(ep[1]), sf, s2,
+    no, mo = checker.search_for_triangulation(d["kf1"], d["kf2"], F12, float(ep[0]), float(ep[1]), sf, s2,
                                              only_stereo=bool(only_stereo), check_ori=bool(check_ori))
     assert nr == no and nr > 100
     assert np.array_equal(m, mo)
@@ -420,7 +423,7 @@ def _sim3(rng):
 
 @pytest.mark.parametrize("seed,cluster,use_scw,th", [(51, False, False, 3.0), (52, True, False, 3.0), (53, False, True, 4.0),
                                                      (54, True, True, 6.0)])
-def test_fuse(ref, oracle, seed, cluster, use_scw, th):
+def test_fuse(ref, checker, seed, cluster, use_scw, th):
     S = _sim3(None) if use_scw else None
     rng, sf, s2, f, T, P3 = _keyframe_world(seed, cluster=cluster, S=S)
     nf, nq = len(f["x"]), len(P3["pos"])
@@ -452,14 +455,14 @@ def test_fuse(ref, oracle, seed, cluster, use_scw, th):
     nr = ref.ref_fuse(B(c), B(kf), B(pts), qp.ctypes.data, nq, None if Sp is None else Sp.ctypes.data, th, best.ctypes.data,
                       q.ctypes.data)
     assert q["valid"].sum() > nq * 0.5
-    no, bo, _ = oracle.search_windows(q, f["x"], f["y"], f["octave"], f["uright"], (np.float32(1.0) / s2).astype(np.float32), None,
+    no, bo, _ = checker.search_windows(q, f["x"], f["y"], f["octave"], f["uright"], (np.float32(1.0) / s2).astype(np.float32), None,
                                       f["desc"], _geom(sf), chi2=not use_scw, greedy=False, th_dist=50)
     assert nr == no and nr > 150
     assert np.array_equal(best, bo)
 
 
 @pytest.mark.parametrize("seed,cluster,th", [(61, False, 10), (62, True, 10), (63, False, 4)])
-def test_search_by_projection_scw(ref, oracle, seed, cluster, th):
+def test_search_by_projection_scw(ref, checker, seed, cluster, th):
     S = _sim3(None)
     rng, sf, s2, f, T, P3 = _keyframe_world(seed, cluster=cluster, S=S)
     nf, nq = len(f["x"]), len(P3["pos"])
@@ -487,14 +490,14 @@ def test_search_by_projection_scw(ref, oracle, seed, cluster, th):
     c = cam()
     nr = ref.ref_search_by_projection_scw(B(c), B(kf), B(pts), qp.ctypes.data, nq, matched_in.ctypes.data, Sp.ctypes.data, th,
                                           best.ctypes.data, q.ctypes.data)
-    no, bo, _ = oracle.search_windows(q, f["x"], f["y"], f["octave"], f["uright"], None, occupied, f["desc"], _geom(sf),
+    no, bo, _ = checker.search_windows(q, f["x"], f["y"], f["octave"], f["uright"], None, occupied, f["desc"], _geom(sf),
                                       chi2=False, greedy=True, th_dist=50)
     assert nr == no and nr > 150
     assert np.array_equal(best, bo)
 
 
 @pytest.mark.parametrize("seed,th", [(71, 7.5), (72, 3.0)])
-def test_search_by_sim3(ref, oracle, seed, th):
+def test_search_by_sim3(ref, checker, seed, th):
     rng = np.random.RandomState(seed)
     sf, s2 = scale_tables()
     n = 1200
@@ -553,9 +556,9 @@ def test_search_by_sim3(ref, oracle, seed, th):
     nr = ref.ref_search_by_sim3(B(c), B(kf1), B(kf2), B(pts), prior.ctypes.data, s12, R12f.ctypes.data, t12f.ctypes.data, th,
                                 m12.ctypes.data, q12.ctypes.data, q21.ctypes.data)
     assert q12["valid"].sum() > n * 0.4 and q21["valid"].sum() > n * 0.4
-    _, b12, _ = oracle.search_windows(q12, f2["x"], f2["y"], f2["octave"], f2["uright"], None, None, f2["desc"], _geom(sf),
+    _, b12, _ = checker.search_windows(q12, f2["x"], f2["y"], f2["octave"], f2["uright"], None, None, f2["desc"], _geom(sf),
                                       th_dist=100)
-    _, b21, _ = oracle.search_windows(q21, f1["x"], f1["y"], f1["octave"], f1["uright"], None, None, f1["desc"], _geom(sf),
+    _, b21, _ = checker.search_windows(q21, f1["x"], f1["y"], f1["octave"], f1["uright"], None, None, f1["desc"], _geom(sf),
                                       th_dist=100)
     want = np.full(n, -1, np.int32)
     for i1 in range(n):
