@@ -346,6 +346,62 @@ int ref_search_by_projection_last(const ref_cam* c, const ref_feats* cur, const 
   return n;
 }
 
+/* SearchByProjection(CurrentFrame, KeyFrame*, sAlreadyFound, th, ORBdist) — :1731-1862 (Tracking::Relocalization).
+ * already_found[i] != 0: the keyframe's i-th map point is in sAlreadyFound.  match_cur[j] = keyframe feature index whose
+ * map point the frame feature j received, -1.  queries[i] (one per keyframe feature; octave = predicted level, -1 where
+ * the reference skips the point before the search) are what orc_search_by_projection_last takes with mode 0, every
+ * query has_obs = 1, occupied = "holds any map point", no stereo gate (uright = -1) and th_high = ORBdist. */
+int ref_search_by_projection_reloc(const ref_cam* c, const ref_feats* cur, const ref_feats* kf, const ref_points* pts,
+                                   const uint8_t* already_found, float th, int orb_dist, int check_ori, int32_t* match_cur,
+                                   ref_proj_query* queries) {
+  World w;
+  w.build(pts);
+  std::unique_ptr<Frame> C(new Frame());
+  std::unique_ptr<KeyFrame> K(new KeyFrame());
+  fill_frame(*C, cur, c, &w);
+  fill_keyframe(*K, kf, c, &w, 0);
+  std::set<MapPoint*> found;
+  for (int i = 0; i < kf->n; i++)
+    if (already_found[i] && K->mvpMapPoints[i]) found.insert(K->mvpMapPoints[i]);
+  {
+    const cv::Mat Rcw = C->mTcw.rowRange(0, 3).colRange(0, 3);
+    const cv::Mat tcw = C->mTcw.rowRange(0, 3).col(3);
+    const cv::Mat Ow = -Rcw.t() * tcw;
+    for (int i = 0; i < kf->n; i++) {
+      ref_proj_query* q = queries + i;
+      std::memset(q, 0, sizeof(*q));
+      q->octave = -1;
+      MapPoint* pMP = K->mvpMapPoints[i];
+      if (!pMP || pMP->isBad() || found.count(pMP)) continue;
+      cv::Mat x3Dw = pMP->GetWorldPos();
+      cv::Mat x3Dc = Rcw * x3Dw + tcw;
+      const float xc = x3Dc.at<float>(0);
+      const float yc = x3Dc.at<float>(1);
+      const float invzc = 1.0 / x3Dc.at<float>(2);
+      const float u = Frame::fx * xc * invzc + Frame::cx;
+      const float v = Frame::fy * yc * invzc + Frame::cy;
+      cv::Mat PO = x3Dw - Ow;
+      float dist3D = cv::norm(PO);
+      if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+      q->u = u;
+      q->v = v;
+      q->invz = 1.0f;  // the reference neither tests the sign of the depth nor uses it here
+      q->angle = K->mvKeysUn[i].angle;
+      q->octave = pMP->PredictScale(dist3D, C.get());
+      q->has_obs = 1;
+      std::memcpy(q->desc, pMP->mDescriptor.data, 32);
+    }
+  }
+  ORBmatcher m(0.75f, check_ori != 0);
+  int n = m.SearchByProjection(*C, K.get(), found, th, orb_dist);
+  for (int j = 0; j < cur->n; j++) {
+    MapPoint* p = C->mvpMapPoints[j];
+    match_cur[j] = -1;
+    if (p && (cur->mp == NULL || cur->mp[j] < 0)) match_cur[j] = (int)p->mObservations.at(K.get());
+  }
+  return n;
+}
+
 /* SearchForTriangulation — :810-1009.  match12[i1] = i2 or -1; epipole[2] = (ex, ey) of :821-823. */
 int ref_search_for_triangulation(const ref_cam* c, const ref_feats* kf1, const ref_feats* kf2, const ref_points* pts,
                                  const float* F12, int only_stereo, int check_ori, int32_t* match12, float* epipole) {

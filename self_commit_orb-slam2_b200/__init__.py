@@ -322,6 +322,16 @@ class ORBmatcher:
         return nm.value, match
 
 
+    def SearchByProjectionReloc(self, queries, kpx, kpy, octave, angle, occupied, desc, geom, th, orb_dist):
+        """SearchByProjection(Frame& Cur, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1731-1862, relocalisation):
+        queries = the keyframe's projected map points with octave = predicted level; occupied[j] = the frame feature holds
+        any map point.  Same kernel as the last-frame search: levels [l-1, l+1], no stereo gate, th_high = ORBdist."""
+        q = np.ascontiguousarray(queries).copy()
+        q["invz"] = 1.0
+        q["has_obs"] = 1
+        return self.SearchByProjection(q, kpx, kpy, octave, angle, np.full(len(kpx), -1, np.float32), occupied, desc, geom, th,
+                                       mode=0, th_high=orb_dist)
+
     def SearchByProjectionMap(self, queries, kpx, kpy, octave, uright, occupied, desc, geom, th=1.0, th_high=TH_HIGH):
         """SearchByProjection(Frame&, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:70-175); queries: map_query_dtype."""
         nf = len(kpx)

@@ -72,6 +72,25 @@ int ORBmatcher::SearchByProjection(const std::vector<b2s_proj_query>& q, const f
   return nm;
 }
 
+int ORBmatcher::SearchByProjectionReloc(std::vector<b2s_proj_query> q, const float* kpx, const float* kpy,
+                                        const int32_t* octave, const float* angle, const uint8_t* occupied,
+                                        const uint8_t* descriptors, int nF, const b2s_frame_geom& geom, float th, int ORBdist,
+                                        std::vector<int32_t>& matchCur) {
+  Ensure((int)q.size() > nF ? (int)q.size() : nF);
+  matchCur.assign(nF, -1);
+  for (size_t i = 0; i < q.size(); i++) {
+    q[i].invz = 1.0f;   // src/ORBmatcher.cc:1766-1772 neither tests the sign of the depth nor uses it
+    q[i].has_obs = 1;   // :1817 skips any feature that holds a map point, so every assignment occupies its feature
+  }
+  const std::vector<float> noStereo((size_t)nF, -1.0f);  // no |ur - uR| gate in this overload
+  int nm = 0;
+  int rc = b2s_search_by_projection_last(mpHandle, q.data(), (int)q.size(), kpx, kpy, octave, angle, noStereo.data(), occupied,
+                                         descriptors, nF, &geom, th, /*mode: levels [l-1, l+1]*/ 0, ORBdist, mbCheckOrientation,
+                                         matchCur.data(), &nm);
+  if (rc != B2S_OK) fail("ORBmatcher::SearchByProjection(relocalisation)", rc);
+  return nm;
+}
+
 int ORBmatcher::SearchByProjection(const std::vector<b2s_map_query>& mp, const float* kpx, const float* kpy,
                                    const int32_t* octave, const float* uright, const uint8_t* occupied,
                                    const uint8_t* descriptors, int nF, const b2s_frame_geom& geom, float th,

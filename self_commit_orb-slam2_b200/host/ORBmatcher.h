@@ -40,6 +40,14 @@ class ORBmatcher {
                          const int32_t* octave, const float* angle, const float* uright, const uint8_t* occupied,
                          const uint8_t* descriptors, int nFeatures, const b2s_frame_geom& geom, float th, int mode,
                          std::vector<int32_t>& matchCur);
+  // SearchByProjection(Frame& Cur, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1731,
+  // Tracking::Relocalization) after the projection of the keyframe's map points that are neither bad nor already found
+  // and lie in the distance-invariance range: query.octave = MapPoint::PredictScale(dist3D, &Cur), query.angle =
+  // pKF->mvKeysUn[i].angle.  It is the last-frame search with levels [l-1, l+1], no stereo gate, every assignment
+  // occupying its feature and occupied[j] = (Cur.mvpMapPoints[j] != NULL); matchCur[j] = query index or -1.
+  int SearchByProjectionReloc(std::vector<b2s_proj_query> queries, const float* kpx, const float* kpy, const int32_t* octave,
+                              const float* angle, const uint8_t* occupied, const uint8_t* descriptors, int nFeatures,
+                              const b2s_frame_geom& geom, float th, int ORBdist, std::vector<int32_t>& matchCur);
   // SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, float th) (src/ORBmatcher.cc:70) after
   // Frame::isInFrustum filled the track fields of the local map points
   int SearchByProjection(const std::vector<b2s_map_query>& mapPoints, const float* kpx, const float* kpy,

@@ -8,6 +8,7 @@ the oracle function the GPU parity tests use:
   SearchByBoW(KeyFrame*, KeyFrame*)                :656                     <-> orc_search_by_bow (accept <  TH_LOW)
   SearchByProjection(Frame&, vpMapPoints, th)      :70                      <-> orc_search_by_projection_map
   SearchByProjection(Current, Last, th, bMono)     :1569                    <-> orc_search_by_projection_last
+  SearchByProjection(Current, KeyFrame*, found,..) :1731 (relocalisation)   <-> orc_search_by_projection_last, mode 0, no stereo gate
   SearchForTriangulation                           :810                     <-> orc_search_for_triangulation
   Fuse(KeyFrame*, vpMapPoints, th)                 :1020                    <-> orc_search_windows (CHI2)
   Fuse(KeyFrame*, Scw, vpPoints, th, vpReplace)    :1179                    <-> orc_search_windows
@@ -113,6 +114,8 @@ def ref():
     R.ref_search_by_projection_map.argtypes = [vp, vp, vp, vp, c_i, c_f, c_f, vp]
     R.ref_search_by_projection_last.argtypes = [vp, vp, vp, vp, c_f, c_i, c_i, vp, vp, vp]
     R.ref_search_for_triangulation.argtypes = [vp, vp, vp, vp, vp, c_i, c_i, vp, vp]
+    R.ref_search_by_projection_reloc.restype = ctypes.c_int
+    R.ref_search_by_projection_reloc.argtypes = [vp, vp, vp, vp, vp, c_f, c_i, c_i, vp, vp]
     R.ref_fuse.argtypes = [vp, vp, vp, vp, c_i, vp, c_f, vp, vp]
     R.ref_search_by_projection_scw.argtypes = [vp, vp, vp, vp, c_i, vp, vp, c_i, vp, vp]
     R.ref_search_by_sim3.argtypes = [vp, vp, vp, vp, vp, c_f, vp, vp, c_f, vp, vp, vp]
@@ -364,6 +367,60 @@ def test_search_by_projection_last(ref, checker, seed, dz, mono, want_mode, chec
     assert nr == no and nr > 150
     mo_last = np.where(mo >= 0, keep[np.maximum(mo, 0)], -1)
     assert np.array_equal(m, mo_last)
+
+
+# ---------------------------------------------------------------- SearchByProjection(Current, KeyFrame*, sAlreadyFound, th, ORBdist)
+@pytest.mark.parametrize("seed,th,orb_dist,check_ori,cluster", [(81, 10.0, 100, 1, False), (82, 3.0, 64, 1, False), (83, 10.0, 100, 0, True)])
+def test_search_by_projection_relocalisation(ref, checker, seed, th, orb_dist, check_ori, cluster):
+    """Tracking::Relocalization's projection search has no kernel of its own: it IS the last-frame search with the window
+    levels [l-1, l+1] around the predicted level, every assignment occupying its feature, features that hold any map point
+    occupied, no stereo gate and th_high = ORBdist.  The reference's function and that call must agree."""
+    rng = np.random.RandomState(seed)
+    sf, _ = scale_tables()
+    nf, nk = 1500, 1400
+    cur = _features(rng, nf, cluster=cluster)
+    Tc = _pose(_rot(-0.01, 0.03, 0.002), np.array([-0.2, 0.05, 0.5]))
+    P3 = _points_seen_from(rng, cur, Tc, nk, sf, px_noise=3.0)
+    kf = _features(rng, nk)
+    kf["angle"] = ((cur["angle"][P3["src"]].astype(np.float64) + rng.normal(0, 6, nk)) % 360.0).astype(np.float32)
+    mp_kf = np.arange(nk, dtype=np.int32)
+    mp_kf[rng.randint(0, 100, size=nk) < 8] = -1
+    bad = np.zeros(nk, np.uint8)
+    bad[rng.randint(0, 100, size=nk) < 4] = 1
+    already = (rng.randint(0, 100, size=nk) < 10).astype(np.uint8)
+    occupied = (rng.randint(0, 100, size=nf) < 8).astype(np.uint8)
+    occ = np.nonzero(occupied)[0]
+    mp_cur = np.full(nf, -1, np.int32)
+    mp_cur[occ] = nk + np.arange(len(occ))
+    z = len(occ)
+    k = Keep()
+    pts = k.points(np.concatenate([P3["pos"], np.zeros((z, 3), np.float32)]), np.concatenate([P3["desc"], np.zeros((z, 32), np.uint8)]),
+                   bad=np.concatenate([bad, np.zeros(z, np.uint8)]), nobs=np.concatenate([np.ones(nk, np.int32), np.zeros(z, np.int32)]),
+                   minDist=np.concatenate([P3["minDist"], np.zeros(z, np.float32)]),
+                   maxDist=np.concatenate([P3["maxDist"], np.zeros(z, np.float32)]))
+    fc = k.feats(cur["x"], cur["y"], cur["angle"], cur["octave"], cur["uright"], cur["desc"], mp=mp_cur, Tcw=Tc)
+    fk = k.feats(kf["x"], kf["y"], kf["angle"], kf["octave"], kf["uright"], kf["desc"], mp=mp_kf, Tcw=Tc)
+    m = np.full(nf, -1, np.int32)
+    q = np.zeros(nk, proj_query_dtype)
+    c = cam()
+    nr = ref.ref_search_by_projection_reloc(B(c), B(fc), B(fk), B(pts), already.ctypes.data, th, orb_dist, check_ori,
+                                            m.ctypes.data, q.ctypes.data)
+    keep = np.nonzero(q["octave"] >= 0)[0]
+    assert len(keep) > 0.5 * nk
+    g = dict(mnMinX=np.float32(0), mnMinY=np.float32(0), mnMaxX=np.float32(W), mnMaxY=np.float32(H), bf=np.float32(BF),
+             scale_factors=sf)
+    if getattr(checker, "name", "") == "cuda":  # through the host mirror of the overload
+        qq = np.ascontiguousarray(q[keep]).copy()
+        qq["invz"], qq["has_obs"] = -5.0, 0  # the wrapper must override both
+        no, mo = checker.pkg.ORBmatcher(0.9, bool(check_ori)).SearchByProjectionReloc(qq, cur["x"], cur["y"], cur["octave"],
+                                                                                      cur["angle"], occupied, cur["desc"], g, th,
+                                                                                      orb_dist)
+    else:
+        no, mo = checker.search_by_projection_last(np.ascontiguousarray(q[keep]), cur["x"], cur["y"], cur["octave"], cur["angle"],
+                                                   np.full(nf, -1, np.float32), occupied, cur["desc"], g, th, mode=0,
+                                                   th_high=orb_dist, check_ori=bool(check_ori))
+    assert nr == no and nr > 150
+    assert np.array_equal(m, np.where(mo >= 0, keep[np.maximum(mo, 0)], -1))
 
 
 # ---------------------------------------------------------------- SearchForTriangulation
