@@ -231,6 +231,18 @@ typedef struct {
   int32_t n;
 } b2s_kf_features;
 
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) — src/ORBmatcher.cc:515-643
+ * (Tracking::MonocularInitialization, src/Tracking.cc:937-944).  prevx / prevy = vbPrevMatched; octave1 / angle1 / desc1 =
+ * F1.mvKeysUn / F1.mDescriptors (only level-0 keypoints search, :537); the F2 side as for the other projection matchers;
+ * window = windowSize; th_low = TH_LOW; nnratio / check_ori = the matcher's constructor arguments.
+ * match12[i1] = F2 feature or -1 (vnMatches12); the caller then sets vbPrevMatched[i1] = F2.mvKeysUn[match12[i1]].pt
+ * (:636-638). */
+int b2s_search_for_initialization(b2s_matcher* h, const float* prevx, const float* prevy, const int32_t* octave1,
+                                  const float* angle1, const uint8_t* desc1, int n1, const float* kpx2, const float* kpy2,
+                                  const int32_t* octave2, const float* angle2, const uint8_t* desc2, int n2,
+                                  const b2s_frame_geom* g, int window, int th_low, float nnratio, int check_ori,
+                                  int32_t* match12, int* nmatches);
+
 /* F12: 3x3 row-major float; (ex, ey): epipole of camera 1 in image 2 (:815-823); scale_factors / level_sigma2:
  * pKF2->mvScaleFactors / mvLevelSigma2.  match12[idx1] = idx2 or -1 (vMatchedPairs in ascending idx1). HOST buffers. */
 int b2s_search_for_triangulation(b2s_matcher* h, const b2s_kf_features* kf1, const b2s_kf_features* kf2, const float* F12,

@@ -183,6 +183,70 @@ struct Grid {
 };
 }  // namespace
 
+// SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) — src/ORBmatcher.cc:515-643 (monocular
+// initialisation): level-0 keypoints of F1 search a fixed window around their previous match in F2; a candidate already
+// matched with a distance <= the new one is skipped (vMatchedDistance), a better match steals the feature.
+extern "C" int orc_search_for_initialization(const float* prevx, const float* prevy, const int32_t* octave1, const float* angle1,
+                                             const uint8_t* desc1, int n1, const float* kpx2, const float* kpy2,
+                                             const int32_t* octave2, const float* angle2, const uint8_t* desc2, int n2,
+                                             const orc_frame_geom* g, int window, int th_low, float nnratio, int check_ori,
+                                             int32_t* match12) {
+  Grid* grid = new Grid();
+  grid->build(kpx2, kpy2, n2, g);
+  int nmatches = 0;
+  for (int i = 0; i < n1; i++) match12[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  std::vector<int> vMatchedDistance(n2, INT_MAX), vnMatches21(n2, -1), cand;
+  for (int i1 = 0; i1 < n1; i1++) {
+    const int level1 = octave1[i1];
+    if (level1 > 0) continue;  // :537
+    grid->in_area(prevx[i1], prevy[i1], (float)window, level1, level1, kpx2, kpy2, octave2, cand);
+    if (cand.empty()) continue;
+    int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+    for (size_t c = 0; c < cand.size(); c++) {
+      const int i2 = cand[c];
+      const int dist = orc_descriptor_distance(desc1 + (size_t)i1 * 32, desc2 + (size_t)i2 * 32);
+      if (vMatchedDistance[i2] <= dist) continue;  // :563
+      if (dist < bestDist) {
+        bestDist2 = bestDist;
+        bestDist = dist;
+        bestIdx2 = i2;
+      } else if (dist < bestDist2) {
+        bestDist2 = dist;
+      }
+    }
+    if (bestDist <= th_low) {
+      if (bestDist < (float)bestDist2 * nnratio) {  // :581
+        if (vnMatches21[bestIdx2] >= 0) {
+          match12[vnMatches21[bestIdx2]] = -1;
+          nmatches--;
+        }
+        match12[i1] = bestIdx2;
+        vnMatches21[bestIdx2] = i1;
+        vMatchedDistance[bestIdx2] = bestDist;
+        nmatches++;
+        if (check_ori) rotHist[rot_bin(angle1[i1], angle2[bestIdx2])].push_back(i1);
+      }
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (size_t j = 0; j < rotHist[i].size(); j++) {
+        const int idx1 = rotHist[i][j];
+        if (match12[idx1] >= 0) {  // a stolen match is already gone (:624-628)
+          match12[idx1] = -1;
+          nmatches--;
+        }
+      }
+    }
+  }
+  delete grid;
+  return nmatches;  // the caller updates vbPrevMatched[i1] = F2.mvKeysUn[match12[i1]].pt (:636-638)
+}
+
 // Frame::GetFeaturesInArea (src/Frame.cc:741-852) on the grid of Frame::AssignFeaturesToGrid (:461-491): test hook for the
 // candidate enumeration every projection matcher above relies on (order included).
 extern "C" int orc_features_in_area(const float* kpx, const float* kpy, const int32_t* octave, int nf, const orc_frame_geom* g,

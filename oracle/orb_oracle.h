@@ -100,6 +100,14 @@ typedef struct {
   int nlevels;
 } orc_frame_geom;
 
+/* ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:515-643): prev = vbPrevMatched; octave1/angle1/desc1 = F1's
+ * undistorted keypoints; F2 side like the other projection matchers; window = windowSize (Tracking uses 100).
+ * match12[i1] = F2 feature or -1; returns nmatches.  The caller then sets vbPrevMatched[i1] = F2 keypoint (:636-638). */
+int orc_search_for_initialization(const float* prevx, const float* prevy, const int32_t* octave1, const float* angle1,
+                                  const uint8_t* desc1, int n1, const float* kpx2, const float* kpy2, const int32_t* octave2,
+                                  const float* angle2, const uint8_t* desc2, int n2, const orc_frame_geom* g, int window,
+                                  int th_low, float nnratio, int check_ori, int32_t* match12);
+
 /* Frame::GetFeaturesInArea (src/Frame.cc:741-852): indices in the reference's order; returns the count, -1 if > cap */
 int orc_features_in_area(const float* kpx, const float* kpy, const int32_t* octave, int nf, const orc_frame_geom* g, float x,
                          float y, float r, int min_level, int max_level, int32_t* out, int cap);

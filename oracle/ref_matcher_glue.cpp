@@ -402,6 +402,25 @@ int ref_search_by_projection_reloc(const ref_cam* c, const ref_feats* cur, const
   return n;
 }
 
+/* SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) — :515-643.  prev: n1 x 2, updated in place. */
+int ref_search_for_initialization(const ref_cam* c, const ref_feats* f1, const ref_feats* f2, float* prev, int window,
+                                  float nnratio, int check_ori, int32_t* match12) {
+  std::unique_ptr<Frame> F1(new Frame()), F2(new Frame());
+  fill_frame(*F1, f1, c, NULL);
+  fill_frame(*F2, f2, c, NULL);
+  std::vector<cv::Point2f> vprev(f1->n);
+  for (int i = 0; i < f1->n; i++) vprev[i] = cv::Point2f(prev[2 * i], prev[2 * i + 1]);
+  std::vector<int> m12;
+  ORBmatcher m(nnratio, check_ori != 0);
+  int n = m.SearchForInitialization(*F1, *F2, vprev, m12, window);
+  for (int i = 0; i < f1->n; i++) {
+    match12[i] = m12[i];
+    prev[2 * i] = vprev[i].x;
+    prev[2 * i + 1] = vprev[i].y;
+  }
+  return n;
+}
+
 /* SearchForTriangulation — :810-1009.  match12[i1] = i2 or -1; epipole[2] = (ex, ey) of :821-823. */
 int ref_search_for_triangulation(const ref_cam* c, const ref_feats* kf1, const ref_feats* kf2, const ref_points* pts,
                                  const float* F12, int only_stereo, int check_ori, int32_t* match12, float* epipole) {

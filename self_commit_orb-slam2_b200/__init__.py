@@ -322,6 +322,34 @@ class ORBmatcher:
         return nm.value, match
 
 
+    def SearchForInitialization(self, prev, octave1, angle1, desc1, kpx2, kpy2, octave2, angle2, desc2, geom, window=10,
+                                th_low=TH_LOW):
+        """ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:515-643).  prev: [n1, 2] vbPrevMatched (updated in place
+        like the reference does, :636-638).  Returns (nmatches, vnMatches12)."""
+        n1, n2 = len(octave1), len(kpx2)
+        prev_in = np.ascontiguousarray(prev, np.float32)
+        px, py = np.ascontiguousarray(prev_in[:, 0]), np.ascontiguousarray(prev_in[:, 1])
+        sf = np.ascontiguousarray(geom["scale_factors"], np.float32)
+        g = _FrameGeom(geom["mnMinX"], geom["mnMinY"], geom["mnMaxX"], geom["mnMaxY"], geom["bf"], sf.ctypes.data, len(sf))
+        keep = [np.ascontiguousarray(octave1, np.int32), np.ascontiguousarray(angle1, np.float32),
+                np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(kpx2, np.float32),
+                np.ascontiguousarray(kpy2, np.float32), np.ascontiguousarray(octave2, np.int32),
+                np.ascontiguousarray(angle2, np.float32), np.ascontiguousarray(desc2, np.uint8)]
+        m12 = np.full(n1, -1, np.int32)
+        nm = ctypes.c_int(0)
+        L = lib()
+        L.b2s_search_for_initialization.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp,
+                                                    ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                                    ctypes.c_int, _vp, _vp]
+        _check(L.b2s_search_for_initialization(self._h, _p(px), _p(py), _p(keep[0]), _p(keep[1]), _p(keep[2]), n1, _p(keep[3]),
+                                               _p(keep[4]), _p(keep[5]), _p(keep[6]), _p(keep[7]), n2, ctypes.byref(g),
+                                               int(window), int(th_low), float(self.mfNNratio),
+                                               int(self.mbCheckOrientation), _p(m12), ctypes.byref(nm)))
+        hit = m12 >= 0
+        prev[hit, 0] = keep[3][m12[hit]]
+        prev[hit, 1] = keep[4][m12[hit]]
+        return nm.value, m12
+
     def SearchByProjectionReloc(self, queries, kpx, kpy, octave, angle, occupied, desc, geom, th, orb_dist):
         """SearchByProjection(Frame& Cur, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1731-1862, relocalisation):
         queries = the keyframe's projected map points with octave = predicted level; occupied[j] = the frame feature holds

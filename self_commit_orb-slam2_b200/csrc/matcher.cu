@@ -1108,6 +1108,167 @@ __global__ void __launch_bounds__(256) k_proj_cull(int checkOri, const int32_t* 
   if (threadIdx.x == 0) nmatches[0] = accepted[0] - culled;
 }
 
+// ---------------------------------------------------------------- SearchForInitialization (src/ORBmatcher.cc:515-643)
+// Exact rescan of one query's window against the CURRENT vMatchedDistance (:563): the two smallest (distance, order)
+// keys among the candidates whose feature is not already matched with a distance <= the candidate's.
+__device__ __forceinline__ void init_rescan_top2(const WinQuery& Q, const ProjGeom& g, int lane, const float* __restrict__ kpx,
+                                                 const float* __restrict__ kpy, const int32_t* __restrict__ octave,
+                                                 const float* __restrict__ uright, const int32_t* __restrict__ matchedDist,
+                                                 const uint8_t* __restrict__ desc, const int32_t* __restrict__ order,
+                                                 const int32_t* __restrict__ cellStart, uint32_t& key1, int& id1,
+                                                 uint32_t& key2) {
+  const Win w = make_win(Q, g);
+  int c0x, c1x, c0y, c1y;
+  win_cells(w, g, c0x, c1x, c0y, c1y);
+  const u256 dq = ld_desc_w(Q.desc);
+  uint32_t k1 = EMPTY, k2 = EMPTY;
+  int i1 = -1;
+  int ord = 0;
+  for (int ix = c0x; ix <= c1x; ix++) {
+    const int beg = cellStart[ix * GRID_ROWS + c0y], end = cellStart[ix * GRID_ROWS + c1y + 1];
+    for (int p = beg + lane; p < end; p += 32) {
+      const int fid = order[p];
+      if (!win_take(w, fid, kpx, kpy, octave, uright)) continue;
+      const int d = hamming256(dq, ld_desc(desc, fid));
+      if (matchedDist[fid] <= d) continue;
+      const uint32_t key = ((uint32_t)d << 20) | (uint32_t)(ord + (p - beg));
+      if (key < k1) {
+        k2 = k1;
+        k1 = key; i1 = fid;
+      } else if (key < k2) {
+        k2 = key;
+      }
+    }
+    ord += end - beg;
+  }
+  uint32_t m1 = k1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m1 = min(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+  key1 = m1;
+  id1 = -1;
+  key2 = EMPTY;
+  if (m1 == EMPTY) return;
+  const int wl = __ffs(__ballot_sync(0xffffffffu, k1 == m1)) - 1;
+  id1 = __shfl_sync(0xffffffffu, i1, wl);
+  uint32_t m2 = (lane == wl) ? k2 : k1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m2 = min(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+  key2 = m2;
+}
+
+// The sequential loop of :527-610 — one warp walks F1's keypoints in order over their K-lists (sorted by distance, then
+// enumeration order).  matchedDist / match21 are the reference's vMatchedDistance / vnMatches21; a query whose list cannot
+// prove its best two remaining candidates is rescanned exactly.  Every accepted match is pushed to the rotation histogram
+// with its F1 index; pushes of matches that are stolen later stay in the histogram, as in the reference.
+__global__ void __launch_bounds__(32) k_init_resolve(const WinQuery* __restrict__ q, int nq, const float* __restrict__ angle1,
+                                                     const float* __restrict__ kpx, const float* __restrict__ kpy,
+                                                     const int32_t* __restrict__ octave, const float* __restrict__ angle2,
+                                                     const float* __restrict__ uright, const uint8_t* __restrict__ desc,
+                                                     const int32_t* __restrict__ order, const int32_t* __restrict__ cellStart,
+                                                     ProjGeom g, int thLow, float nnratio,
+                                                     const uint32_t* __restrict__ topk, const int32_t* __restrict__ topkIdx,
+                                                     const int32_t* __restrict__ candCnt, int32_t* __restrict__ matchedDist,
+                                                     int32_t* __restrict__ match21, int32_t* __restrict__ match12,
+                                                     int32_t* __restrict__ pushList, int32_t* __restrict__ accepted,
+                                                     int32_t* __restrict__ histOut) {
+  const int lane = threadIdx.x;
+  __shared__ int hist[HISTO];
+  if (lane < HISTO) hist[lane] = 0;
+  __syncwarp();
+  int nPush = 0;
+  for (int i = 0; i < nq; i++) {
+    const int cc = candCnt[i];
+    if (cc <= 0) continue;
+    const uint32_t e = (lane < TOPK) ? topk[(size_t)i * TOPK + lane] : EMPTY;
+    const int id = (lane < TOPK) ? topkIdx[(size_t)i * TOPK + lane] : -1;
+    const bool avail = (e != EMPTY) && !(matchedDist[id] <= (int)(e >> 20));
+    unsigned am = __ballot_sync(0xffffffffu, avail);
+    uint32_t key1 = EMPTY, key2 = EMPTY;
+    int id1 = -1;
+    if (__popc(am) >= 2 || cc <= TOPK) {  // the list holds the best two remaining candidates (or all candidates)
+      if (am) {
+        const int l1 = __ffs(am) - 1;
+        key1 = __shfl_sync(0xffffffffu, e, l1);
+        id1 = __shfl_sync(0xffffffffu, id, l1);
+        am &= am - 1;
+        if (am) key2 = __shfl_sync(0xffffffffu, e, __ffs(am) - 1);
+      }
+    } else {
+      init_rescan_top2(q[i], g, lane, kpx, kpy, octave, uright, matchedDist, desc, order, cellStart, key1, id1, key2);
+    }
+    if (id1 < 0) continue;
+    const int bestDist = (int)(key1 >> 20);
+    const int bestDist2 = key2 == EMPTY ? 2147483647 : (int)(key2 >> 20);
+    if (bestDist > thLow) continue;                                         // :579
+    if (!((float)bestDist < __fmul_rn((float)bestDist2, nnratio))) continue;  // :581
+    if (lane == 0) {
+      const int prev = match21[id1];
+      if (prev >= 0) match12[prev] = -1;  // :583-587: the better match steals the feature
+      match12[i] = id1;
+      match21[id1] = i;
+      matchedDist[id1] = bestDist;
+      if (g.checkOri) {
+        const int bn = rot_bin(angle1[i], angle2[id1]);
+        hist[bn]++;
+        pushList[nPush] = (bn << 20) | i;
+      }
+    }
+    __syncwarp();
+    nPush++;  // (the match count is taken from match12 by k_init_cull: it equals the reference's running nmatches)
+  }
+  __syncwarp();
+  if (lane < HISTO) histOut[lane] = hist[lane];
+  if (lane == 0) accepted[0] = nPush;
+}
+
+// Rotation cull (:612-633): pushes in bins outside the three maxima lose their match if they still hold one; nmatches =
+// the surviving matches (the reference's running count equals the number of non-negative entries at every point).
+__global__ void __launch_bounds__(256) k_init_cull(int checkOri, int n1, const int32_t* __restrict__ hist,
+                                                   const int32_t* __restrict__ accepted, int32_t* __restrict__ match12,
+                                                   const int32_t* __restrict__ pushBins, int32_t* __restrict__ nmatches) {
+  __shared__ int keep[3];
+  __shared__ int total;
+  if (threadIdx.x == 0) {
+    total = 0;
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+    for (int i = 0; i < HISTO; i++) {
+      const int s = hist[i];
+      if (s > max1) {
+        max3 = max2; max2 = max1; max1 = s;
+        ind3 = ind2; ind2 = ind1; ind1 = i;
+      } else if (s > max2) {
+        max3 = max2; max2 = s;
+        ind3 = ind2; ind2 = i;
+      } else if (s > max3) {
+        max3 = s;
+        ind3 = i;
+      }
+    }
+    if ((float)max2 < 0.1f * (float)max1) {
+      ind2 = -1;
+      ind3 = -1;
+    } else if ((float)max3 < 0.1f * (float)max1) {
+      ind3 = -1;
+    }
+    keep[0] = ind1; keep[1] = ind2; keep[2] = ind3;
+  }
+  __syncthreads();
+  if (checkOri) {
+    const int nPush = accepted[0];
+    for (int k = threadIdx.x; k < nPush; k += blockDim.x) {
+      const int packed = pushBins[k];
+      const int bn = packed >> 20, i1 = packed & 0xFFFFF;
+      if (bn != keep[0] && bn != keep[1] && bn != keep[2]) match12[i1] = -1;  // (each F1 index is pushed at most once)
+    }
+  }
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < n1; i += blockDim.x) c += match12[i] >= 0;
+  atomicAdd(&total, c);
+  __syncthreads();
+  if (threadIdx.x == 0) nmatches[0] = total;
+}
+
 }  // namespace b2s
 
 using namespace b2s;
@@ -1339,6 +1500,75 @@ extern "C" int b2s_search_by_projection_last(b2s_matcher* h, const b2s_proj_quer
   h->launches += 7;
   B2S_CUDA(cudaGetLastError());
   B2S_CUDA(cudaMemcpyAsync(match_cur, h->dMatch, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  return B2S_OK;
+}
+
+extern "C" int b2s_search_for_initialization(b2s_matcher* h, const float* prevx, const float* prevy, const int32_t* octave1,
+                                             const float* angle1, const uint8_t* desc1, int n1, const float* kpx2,
+                                             const float* kpy2, const int32_t* octave2, const float* angle2,
+                                             const uint8_t* desc2, int n2, const b2s_frame_geom* g, int window, int th_low,
+                                             float nnratio, int check_ori, int32_t* match12, int* nmatches) {
+  static_assert(sizeof(WinQuery) == sizeof(b2s_win_query), "query layout");
+  if (!h || n1 < 0 || n2 < 0 || n1 > h->maxF || n2 > h->maxF || !match12 || !nmatches || !g || window < 0) {
+    set_error("b2s_search_for_initialization: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  *nmatches = 0;
+  for (int i = 0; i < n1; i++) match12[i] = -1;
+  if (n1 == 0 || n2 == 0) return B2S_OK;
+  if (!prevx || !prevy || !octave1 || !angle1 || !desc1 || !kpx2 || !kpy2 || !octave2 || !angle2 || !desc2)
+    return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  // one window query per F1 keypoint: level-0 keypoints only (:537), fixed radius, candidates of the same level (:541)
+  std::vector<WinQuery> wq((size_t)n1);
+  for (int i = 0; i < n1; i++) {
+    WinQuery& Q = wq[i];
+    memset(&Q, 0, sizeof(Q));
+    Q.u = prevx[i];
+    Q.v = prevy[i];
+    Q.radius = (float)window;
+    Q.min_level = octave1[i];
+    Q.max_level = octave1[i];
+    Q.valid = octave1[i] > 0 ? 0 : 1;
+    memcpy(Q.desc, desc1 + (size_t)i * 32, 32);
+  }
+  ProjGeom pg;
+  memset(&pg, 0, sizeof(pg));
+  pg.minX = g->mnMinX; pg.minY = g->mnMinY; pg.maxX = g->mnMaxX; pg.maxY = g->mnMaxY;
+  pg.invW = (float)GRID_COLS / (g->mnMaxX - g->mnMinX);
+  pg.invH = (float)GRID_ROWS / (g->mnMaxY - g->mnMinY);
+  pg.checkOri = check_ori;
+  WinQuery* dQ = reinterpret_cast<WinQuery*>(h->dQueries);
+  int32_t* dMatchedDist = h->dNodeA;  // vMatchedDistance
+  int32_t* dMatch21 = h->dBin;        // vnMatches21
+  B2S_CUDA(cudaMemcpyAsync(dQ, wq.data(), (size_t)n1 * sizeof(WinQuery), cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dAngA, angle1, (size_t)n1 * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dKpx, kpx2, (size_t)n2 * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dKpy, kpy2, (size_t)n2 * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dOct, octave2, (size_t)n2 * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dAngB, angle2, (size_t)n2 * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dDescB, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNB, &n2, 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemsetAsync(h->dURight, 0, (size_t)n2 * 4, st));
+  B2S_CUDA(cudaStreamSynchronize(st));  // wq is a stack-owned staging vector
+  k_fill_i32<<<div_up(n1, 256), 256, 0, st>>>(h->dMatch, -1, (size_t)n1);
+  k_fill_i32<<<div_up(n2, 256), 256, 0, st>>>(dMatch21, -1, (size_t)n2);
+  k_fill_i32<<<div_up(n2, 256), 256, 0, st>>>(dMatchedDist, 2147483647, (size_t)n2);
+  k_proj_cell_key<<<div_up(n2, 256), 256, 0, st>>>(h->dKpx, h->dKpy, n2, pg, h->dCellKey);
+  k_rank_by_key<<<dim3(div_up(n2, 128), 1), 128, 0, st>>>(h->dCellKey, h->dNB, n2, h->dOrder);
+  k_proj_cell_start<<<div_up(n2 + 1, 256), 256, 0, st>>>(h->dCellKey, h->dOrder, n2, h->dCellStart);
+  k_proj_topk<WinQuery><<<div_up(n1, 8), 256, 0, st>>>(dQ, n1, h->dKpx, h->dKpy, h->dOct, h->dURight, nullptr, h->dDescB,
+                                                       h->dOrder, h->dCellStart, pg, h->dTopk, h->dTopkIdx, h->dCandCnt);
+  k_init_resolve<<<1, 32, 0, st>>>(dQ, n1, h->dAngA, h->dKpx, h->dKpy, h->dOct, h->dAngB, h->dURight, h->dDescB, h->dOrder,
+                                   h->dCellStart, pg, th_low, nnratio, h->dTopk, h->dTopkIdx, h->dCandCnt, dMatchedDist,
+                                   dMatch21, h->dMatch, h->dPush, h->dExtra, h->dHist);
+  k_init_cull<<<1, 256, 0, st>>>(check_ori, n1, h->dHist, h->dExtra, h->dMatch, h->dPush, h->dNMatches);
+  h->launches += 9;
+  B2S_CUDA(cudaGetLastError());
+  B2S_CUDA(cudaMemcpyAsync(match12, h->dMatch, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaStreamSynchronize(st));
   return B2S_OK;

@@ -72,6 +72,35 @@ int ORBmatcher::SearchByProjection(const std::vector<b2s_proj_query>& q, const f
   return nm;
 }
 
+int ORBmatcher::SearchForInitialization(const float* kpx1, const float* kpy1, const int32_t* octave1, const float* angle1,
+                                        const uint8_t* d1, int n1, const float* kpx2, const float* kpy2,
+                                        const int32_t* octave2, const float* angle2, const uint8_t* d2, int n2,
+                                        const b2s_frame_geom& geom, std::vector<float>& vbPrevMatched,
+                                        std::vector<int>& vnMatches12, int windowSize) {
+  (void)kpx1;
+  (void)kpy1;  // F1's own coordinates only seed vbPrevMatched (done by the caller, src/Tracking.cc:905-907)
+  Ensure(n1 > n2 ? n1 : n2);
+  vnMatches12.assign(n1, -1);
+  if ((int)vbPrevMatched.size() < 2 * n1) fail("ORBmatcher::SearchForInitialization: vbPrevMatched too short", B2S_ERR_BAD_ARG);
+  std::vector<float> px(n1), py(n1);
+  for (int i = 0; i < n1; i++) {
+    px[i] = vbPrevMatched[2 * i];
+    py[i] = vbPrevMatched[2 * i + 1];
+  }
+  int nm = 0;
+  static_assert(sizeof(int) == sizeof(int32_t), "vnMatches12 is vector<int> in the reference");
+  int rc = b2s_search_for_initialization(mpHandle, px.data(), py.data(), octave1, angle1, d1, n1, kpx2, kpy2, octave2, angle2, d2,
+                                         n2, &geom, windowSize, TH_LOW, mfNNratio, mbCheckOrientation,
+                                         reinterpret_cast<int32_t*>(vnMatches12.data()), &nm);
+  if (rc != B2S_OK) fail("ORBmatcher::SearchForInitialization", rc);
+  for (int i = 0; i < n1; i++)
+    if (vnMatches12[i] >= 0) {  // :636-638
+      vbPrevMatched[2 * i] = kpx2[vnMatches12[i]];
+      vbPrevMatched[2 * i + 1] = kpy2[vnMatches12[i]];
+    }
+  return nm;
+}
+
 int ORBmatcher::SearchByProjectionReloc(std::vector<b2s_proj_query> q, const float* kpx, const float* kpy,
                                         const int32_t* octave, const float* angle, const uint8_t* occupied,
                                         const uint8_t* descriptors, int nF, const b2s_frame_geom& geom, float th, int ORBdist,

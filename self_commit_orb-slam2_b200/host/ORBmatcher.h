@@ -53,6 +53,12 @@ class ORBmatcher {
   int SearchByProjection(const std::vector<b2s_map_query>& mapPoints, const float* kpx, const float* kpy,
                          const int32_t* octave, const float* uright, const uint8_t* occupied, const uint8_t* descriptors,
                          int nFeatures, const b2s_frame_geom& geom, float th, std::vector<int32_t>& matchF);
+  // SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:515-643) on
+  // flattened frames; vbPrevMatched (x, y interleaved) is updated in place like the reference does (:636-638)
+  int SearchForInitialization(const float* kpx1, const float* kpy1, const int32_t* octave1, const float* angle1,
+                              const uint8_t* descriptors1, int n1, const float* kpx2, const float* kpy2, const int32_t* octave2,
+                              const float* angle2, const uint8_t* descriptors2, int n2, const b2s_frame_geom& geom,
+                              std::vector<float>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
   // search core of Fuse(KeyFrame*, vpMapPoints, th) (B2S_WIN_CHI2), Fuse(KeyFrame*, Scw, ...) (no flag) and
   // SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (B2S_WIN_GREEDY): best keyframe feature per map point
   int SearchWindows(const std::vector<b2s_win_query>& mapPoints, const float* kpx, const float* kpy, const int32_t* octave,

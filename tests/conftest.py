@@ -60,6 +60,12 @@ class CudaChecker:
     def distinctive_descriptors(self, desc, offsets):
         return self.pkg.ORBmatcher(0.6, True).DistinctiveDescriptors(desc, offsets)
 
+    def search_for_initialization(self, prev, octave1, angle1, desc1, kpx2, kpy2, octave2, angle2, desc2, geom, window=10,
+                                  th_low=50, nnratio=0.9, check_ori=True):
+        m = self.pkg.ORBmatcher(nnratio, check_ori)
+        return m.SearchForInitialization(prev, octave1, angle1, desc1, kpx2, kpy2, octave2, angle2, desc2, geom, window=window,
+                                         th_low=th_low)
+
     def extractor(self, nfeatures, scaleFactor, nlevels, iniTh, minTh):
         pkg = self.pkg
 

@@ -148,6 +148,26 @@ class Oracle:
                                                 P(occupied), P(desc), len(kpx), ctypes.byref(g), th, th_high, nnratio, P(m))
         return n, m
 
+    def search_for_initialization(self, prev, octave1, angle1, desc1, kpx2, kpy2, octave2, angle2, desc2, geom, window=10,
+                                  th_low=50, nnratio=0.9, check_ori=True):
+        prev_in = np.ascontiguousarray(prev, np.float32)
+        px, py = np.ascontiguousarray(prev_in[:, 0]), np.ascontiguousarray(prev_in[:, 1])
+        sf = np.ascontiguousarray(geom["scale_factors"], np.float32)
+        g = FrameGeom(geom["mnMinX"], geom["mnMinY"], geom["mnMaxX"], geom["mnMaxY"], geom["bf"], sf.ctypes.data, len(sf))
+        a = [np.ascontiguousarray(octave1, np.int32), np.ascontiguousarray(angle1, np.float32),
+             np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(kpx2, np.float32), np.ascontiguousarray(kpy2, np.float32),
+             np.ascontiguousarray(octave2, np.int32), np.ascontiguousarray(angle2, np.float32), np.ascontiguousarray(desc2, np.uint8)]
+        m12 = np.full(len(a[0]), -1, np.int32)
+        self.L.orc_search_for_initialization.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp,
+                                                         ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int, vp]
+        n = self.L.orc_search_for_initialization(P(px), P(py), P(a[0]), P(a[1]), P(a[2]), len(a[0]), P(a[3]), P(a[4]), P(a[5]),
+                                                 P(a[6]), P(a[7]), len(a[3]), ctypes.byref(g), int(window), int(th_low),
+                                                 float(nnratio), int(check_ori), P(m12))
+        hit = m12 >= 0
+        prev[hit, 0] = a[3][m12[hit]]
+        prev[hit, 1] = a[4][m12[hit]]
+        return n, m12
+
     def search_for_triangulation(self, kf1, kf2, F12, ex, ey, scale_factors, level_sigma2, only_stereo=False,
                                  check_ori=True):
         class KF(ctypes.Structure):

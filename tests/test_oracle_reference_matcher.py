@@ -9,6 +9,7 @@ the oracle function the GPU parity tests use:
   SearchByProjection(Frame&, vpMapPoints, th)      :70                      <-> orc_search_by_projection_map
   SearchByProjection(Current, Last, th, bMono)     :1569                    <-> orc_search_by_projection_last
   SearchByProjection(Current, KeyFrame*, found,..) :1731 (relocalisation)   <-> orc_search_by_projection_last, mode 0, no stereo gate
+  SearchForInitialization                          :515                     <-> orc_search_for_initialization
   SearchForTriangulation                           :810                     <-> orc_search_for_triangulation
   Fuse(KeyFrame*, vpMapPoints, th)                 :1020                    <-> orc_search_windows (CHI2)
   Fuse(KeyFrame*, Scw, vpPoints, th, vpReplace)    :1179                    <-> orc_search_windows
@@ -114,6 +115,8 @@ def ref():
     R.ref_search_by_projection_map.argtypes = [vp, vp, vp, vp, c_i, c_f, c_f, vp]
     R.ref_search_by_projection_last.argtypes = [vp, vp, vp, vp, c_f, c_i, c_i, vp, vp, vp]
     R.ref_search_for_triangulation.argtypes = [vp, vp, vp, vp, vp, c_i, c_i, vp, vp]
+    R.ref_search_for_initialization.restype = ctypes.c_int
+    R.ref_search_for_initialization.argtypes = [vp, vp, vp, vp, c_i, c_f, c_i, vp]
     R.ref_search_by_projection_reloc.restype = ctypes.c_int
     R.ref_search_by_projection_reloc.argtypes = [vp, vp, vp, vp, vp, c_f, c_i, c_i, vp, vp]
     R.ref_fuse.argtypes = [vp, vp, vp, vp, c_i, vp, c_f, vp, vp]
@@ -421,6 +424,52 @@ def test_search_by_projection_relocalisation(ref, checker, seed, th, orb_dist, c
                                                    th_high=orb_dist, check_ori=bool(check_ori))
     assert nr == no and nr > 150
     assert np.array_equal(m, np.where(mo >= 0, keep[np.maximum(mo, 0)], -1))
+
+
+# ---------------------------------------------------------------- SearchForInitialization
+@pytest.mark.parametrize("seed,window,nnratio,check_ori,dense", [(91, 100, 0.9, 1, False), (92, 100, 0.9, 0, True), (93, 30, 0.8, 1, False),
+                                                                 (94, 100, 0.95, 1, True)])
+def test_search_for_initialization(ref, checker, seed, window, nnratio, check_ori, dense):
+    """Monocular initialisation matcher: two iterations, the second starting from the first one's vbPrevMatched, as
+    Tracking::MonocularInitialization does over consecutive frames.  `dense`: near-duplicate descriptors and many level-0
+    features, so that matches get stolen (vMatchedDistance) and the K-lists of the CUDA path run dry."""
+    rng = np.random.RandomState(seed)
+    sf, _ = scale_tables()
+    n1 = n2 = 1500
+    f1 = _features(rng, n1)
+    if dense:
+        f1["octave"] = np.where(rng.randint(0, 100, size=n1) < 75, 0, f1["octave"]).astype(np.int32)
+        base = rng.randint(0, 256, size=(6, 32)).astype(np.uint8)
+        f1["desc"] = np.stack([_flip(rng, base[rng.randint(0, 6)], 14) for _ in range(n1)])
+        f1["x"] = (400 + rng.randint(0, 3000, size=n1) / 10.0).astype(np.float32)
+        f1["y"] = (100 + rng.randint(0, 1500, size=n1) / 10.0).astype(np.float32)
+    else:
+        f1["octave"] = np.where(rng.randint(0, 100, size=n1) < 45, 0, f1["octave"]).astype(np.int32)
+    perm = rng.permutation(n1)
+    f2 = dict(x=(f1["x"] + rng.normal(8, 6, n1)).astype(np.float32)[perm], y=(f1["y"] + rng.normal(0, 4, n1)).astype(np.float32)[perm],
+              octave=np.where(rng.randint(0, 100, size=n1) < 90, f1["octave"], 1).astype(np.int32)[perm],
+              angle=((f1["angle"].astype(np.float64) + rng.normal(0, 5, n1)) % 360.0).astype(np.float32)[perm],
+              desc=np.stack([_flip(rng, d, 30) for d in f1["desc"]])[perm], uright=np.full(n1, -1, np.float32))
+    g = _geom(sf)
+    k = Keep()
+    F1 = k.feats(f1["x"], f1["y"], f1["angle"], f1["octave"], np.full(n1, -1, np.float32), f1["desc"])
+    F2 = k.feats(f2["x"], f2["y"], f2["angle"], f2["octave"], f2["uright"], f2["desc"])
+    prev_r = np.ascontiguousarray(np.stack([f1["x"], f1["y"]], 1), np.float32)  # vbPrevMatched starts at F1's keypoints
+    prev_c = prev_r.copy()
+    c = cam()
+    total = 0
+    for it in range(2):
+        m = np.full(n1, -1, np.int32)
+        nr = ref.ref_search_for_initialization(B(c), B(F1), B(F2), prev_r.ctypes.data, window, nnratio, check_ori, m.ctypes.data)
+        no, mo = checker.search_for_initialization(prev_c, f1["octave"], f1["angle"], f1["desc"], f2["x"], f2["y"], f2["octave"],
+                                                   f2["angle"], f2["desc"], g, window=window, th_low=50, nnratio=nnratio,
+                                                   check_ori=bool(check_ori))
+        assert nr == no == int((m >= 0).sum())
+        assert np.array_equal(m, mo)
+        assert np.array_equal(prev_r, prev_c)
+        assert (f1["octave"][m >= 0] == 0).all()
+        total += nr
+    assert total > 150
 
 
 # ---------------------------------------------------------------- SearchForTriangulation
