@@ -231,6 +231,35 @@ typedef struct {
   int32_t n;
 } b2s_kf_features;
 
+/* ---- persistent Frame feature grid -------------------------------------------------------------------
+ * Frame::AssignFeaturesToGrid (src/Frame.cc:461-491) once per frame; the frame's keypoints, descriptors and the 64 x 48
+ * cell index then stay on the device, so the consecutive matchers Tracking runs on one frame (SearchByProjection against
+ * the last frame, SearchLocalPoints, relocalisation, Fuse / loop searches on a keyframe) upload only their queries.
+ * The grid belongs to the matcher handle it was created with.  inv_level_sigma2 (mvInvLevelSigma2) may be NULL unless
+ * B2S_WIN_CHI2 searches are made.  _create_device takes the extractor's device-resident records (b2s_extract_batch_device)
+ * and an optional device array of mvuRight (b2s_stereo_match_device); NULL = monocular (-1). */
+typedef struct b2s_frame_grid b2s_frame_grid;
+int b2s_frame_grid_create(b2s_matcher* h, const float* kpx, const float* kpy, const int32_t* octave, const float* angle,
+                          const float* uright, const uint8_t* desc, int nf, const b2s_frame_geom* g,
+                          const float* inv_level_sigma2, b2s_frame_grid** out);
+int b2s_frame_grid_create_device(b2s_matcher* h, const b2s_keypoint* d_kps, const uint8_t* d_desc, int nf,
+                                 const float* d_uright, const b2s_frame_geom* g, const float* inv_level_sigma2, void* stream,
+                                 b2s_frame_grid** out);
+void b2s_frame_grid_destroy(b2s_frame_grid* grid);
+int b2s_frame_grid_size(const b2s_frame_grid* grid);
+/* Frame::GetFeaturesInArea (src/Frame.cc:741-852): indices in the reference's order; *n = count (B2S_ERR_CAPACITY if > cap) */
+int b2s_frame_grid_features_in_area(b2s_frame_grid* grid, float x, float y, float r, int min_level, int max_level,
+                                    int32_t* out, int cap, int* n);
+/* b2s_search_by_projection_last / _map / b2s_search_windows on a resident grid (same semantics, same results) */
+int b2s_search_by_projection_last_grid(b2s_matcher* h, b2s_frame_grid* grid, const b2s_proj_query* q, int nq,
+                                       const uint8_t* occupied, float th, int mode, int th_high, int check_ori,
+                                       int32_t* match_cur, int* nmatches);
+int b2s_search_by_projection_map_grid(b2s_matcher* h, b2s_frame_grid* grid, const b2s_map_query* q, int nq,
+                                      const uint8_t* occupied, float th, int th_high, float nnratio, int32_t* match_cur,
+                                      int* nmatches);
+int b2s_search_windows_grid(b2s_matcher* h, b2s_frame_grid* grid, const b2s_win_query* q, int nq, const uint8_t* occupied,
+                            int flags, int th_dist, int32_t* best_idx, int32_t* best_dist, int* n_accepted);
+
 /* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) — src/ORBmatcher.cc:515-643
  * (Tracking::MonocularInitialization, src/Tracking.cc:937-944).  prevx / prevy = vbPrevMatched; octave1 / angle1 / desc1 =
  * F1.mvKeysUn / F1.mDescriptors (only level-0 keypoints search, :537); the F2 side as for the other projection matchers;

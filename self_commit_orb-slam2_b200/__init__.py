@@ -436,6 +436,90 @@ class _VocDesc(ctypes.Structure):
                 ("leaf_flag", ctypes.c_void_p), ("desc", ctypes.c_void_p), ("weight", ctypes.c_void_p)]
 
 
+class FrameGrid:
+    """Frame::AssignFeaturesToGrid / GetFeaturesInArea (src/Frame.cc:461-491, 741-852) kept on the device: build once per
+    frame, then run several projection matchers that upload only their queries."""
+
+    def __init__(self, matcher, kpx=None, kpy=None, octave=None, angle=None, uright=None, desc=None, geom=None,
+                 inv_level_sigma2=None, d_kps_ptr=None, d_desc_ptr=None, d_uright_ptr=None, nf=None, stream=0):
+        self.matcher = matcher
+        self._h = _vp()
+        L = lib()
+        L.b2s_frame_grid_create.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, _vp]
+        L.b2s_frame_grid_create_device.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]
+        L.b2s_frame_grid_destroy.argtypes = [_vp]
+        L.b2s_frame_grid_destroy.restype = None
+        L.b2s_frame_grid_size.argtypes = [_vp]
+        L.b2s_frame_grid_features_in_area.argtypes = [_vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                                      ctypes.c_int, _vp, ctypes.c_int, _vp]
+        L.b2s_search_by_projection_last_grid.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_float, ctypes.c_int,
+                                                         ctypes.c_int, ctypes.c_int, _vp, _vp]
+        L.b2s_search_by_projection_map_grid.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_float, ctypes.c_int,
+                                                        ctypes.c_float, _vp, _vp]
+        L.b2s_search_windows_grid.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]
+        sf = np.ascontiguousarray(geom["scale_factors"], np.float32)
+        g = _FrameGeom(geom["mnMinX"], geom["mnMinY"], geom["mnMaxX"], geom["mnMaxY"], geom["bf"], sf.ctypes.data, len(sf))
+        is2 = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+        if d_kps_ptr is not None:
+            _check(L.b2s_frame_grid_create_device(matcher._h, _vp(d_kps_ptr), _vp(d_desc_ptr), int(nf),
+                                                  _vp(d_uright_ptr) if d_uright_ptr else None, ctypes.byref(g), _p(is2),
+                                                  _vp(stream), ctypes.byref(self._h)))
+        else:
+            a = [np.ascontiguousarray(kpx, np.float32), np.ascontiguousarray(kpy, np.float32),
+                 np.ascontiguousarray(octave, np.int32), np.ascontiguousarray(angle, np.float32),
+                 np.ascontiguousarray(uright, np.float32), np.ascontiguousarray(desc, np.uint8)]
+            _check(L.b2s_frame_grid_create(matcher._h, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), len(a[0]),
+                                           ctypes.byref(g), _p(is2), ctypes.byref(self._h)))
+        self.n = lib().b2s_frame_grid_size(self._h)
+
+    def close(self):
+        if self._h:
+            lib().b2s_frame_grid_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def GetFeaturesInArea(self, x, y, r, minLevel=-1, maxLevel=-1):
+        out = np.zeros(max(self.n, 1), np.int32)
+        n = ctypes.c_int(0)
+        _check(lib().b2s_frame_grid_features_in_area(self._h, float(x), float(y), float(r), int(minLevel), int(maxLevel),
+                                                     _p(out), len(out), ctypes.byref(n)))
+        return out[:n.value].copy()
+
+    def SearchByProjection(self, queries, occupied, th, mode=0, th_high=TH_HIGH):
+        m = np.full(self.n, -1, np.int32)
+        nm = ctypes.c_int(0)
+        q = np.ascontiguousarray(queries)
+        occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        _check(lib().b2s_search_by_projection_last_grid(self.matcher._h, self._h, _p(q), len(q), _p(occ), float(th), int(mode),
+                                                        int(th_high), int(self.matcher.mbCheckOrientation), _p(m),
+                                                        ctypes.byref(nm)))
+        return nm.value, m
+
+    def SearchByProjectionMap(self, queries, occupied, th=1.0, th_high=TH_HIGH):
+        m = np.full(self.n, -1, np.int32)
+        nm = ctypes.c_int(0)
+        q = np.ascontiguousarray(queries)
+        occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        _check(lib().b2s_search_by_projection_map_grid(self.matcher._h, self._h, _p(q), len(q), _p(occ), float(th), int(th_high),
+                                                       float(self.matcher.mfNNratio), _p(m), ctypes.byref(nm)))
+        return nm.value, m
+
+    def SearchWindows(self, queries, occupied, chi2=False, greedy=False, th_dist=TH_LOW):
+        q = np.ascontiguousarray(queries)
+        best = np.full(len(q), -1, np.int32)
+        bd = np.full(len(q), 256, np.int32)
+        na = ctypes.c_int(0)
+        occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        _check(lib().b2s_search_windows_grid(self.matcher._h, self._h, _p(q), len(q), _p(occ), (1 if chi2 else 0) | (2 if greedy else 0),
+                                             int(th_dist), _p(best), _p(bd), ctypes.byref(na)))
+        return na.value, best, bd
+
+
 class ORBVocabulary:
     """Mirror of ORBVocabulary::transform (DBoW2 TemplatedVocabulary.h:1127-1256) on a flattened vocabulary."""
 

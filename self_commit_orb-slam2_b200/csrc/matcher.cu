@@ -1269,6 +1269,53 @@ __global__ void __launch_bounds__(256) k_init_cull(int checkOri, int n1, const i
   if (threadIdx.x == 0) nmatches[0] = total;
 }
 
+// ---------------------------------------------------------------- persistent Frame feature grid
+// unpack device-resident extractor records (28-byte cv::KeyPoint layout) into the SoA the matchers read
+__global__ void k_unpack_kps(const uint8_t* __restrict__ rec, int nf, float* __restrict__ kpx, float* __restrict__ kpy,
+                             int32_t* __restrict__ oct, float* __restrict__ ang) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nf) return;
+  const float* r = reinterpret_cast<const float*>(rec + (size_t)i * 28);
+  kpx[i] = r[0];
+  kpy[i] = r[1];
+  ang[i] = r[3];
+  oct[i] = reinterpret_cast<const int32_t*>(r)[5];
+}
+
+// Frame::GetFeaturesInArea (src/Frame.cc:741-852) on the resident grid: one warp, output in the reference's order
+__global__ void __launch_bounds__(32) k_grid_query(float x, float y, float r, int minL, int maxL, const float* __restrict__ kpx,
+                                                   const float* __restrict__ kpy, const int32_t* __restrict__ octave,
+                                                   const float* __restrict__ uright, const int32_t* __restrict__ order,
+                                                   const int32_t* __restrict__ cellStart, ProjGeom g, int32_t* __restrict__ out,
+                                                   int cap, int32_t* __restrict__ nOut) {
+  const int lane = threadIdx.x;
+  Win w;
+  w.ok = true; w.u = x; w.v = y; w.r = r; w.ur = 0.f; w.minL = minL; w.maxL = maxL; w.stereoGate = false; w.chi2Gate = false;
+  int c0x, c1x, c0y, c1y;
+  int n = 0;
+  if (win_cells(w, g, c0x, c1x, c0y, c1y)) {
+    for (int ix = c0x; ix <= c1x; ix++) {
+      const int beg = cellStart[ix * GRID_ROWS + c0y], end = cellStart[ix * GRID_ROWS + c1y + 1];
+      for (int p0 = beg; p0 < end; p0 += 32) {
+        const int p = p0 + lane;
+        int id = -1;
+        bool take = false;
+        if (p < end) {
+          id = order[p];
+          take = win_take(w, id, kpx, kpy, octave, uright);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (take) {
+          const int pos = n + __popc(m & ((1u << lane) - 1u));
+          if (pos < cap) out[pos] = id;
+        }
+        n += __popc(m);
+      }
+    }
+  }
+  if (lane == 0) nOut[0] = n;
+}
+
 }  // namespace b2s
 
 using namespace b2s;
@@ -1688,6 +1735,277 @@ extern "C" int b2s_search_windows(b2s_matcher* h, const b2s_win_query* q, int nq
   else
     k_win_pick<<<div_up(nq, 256), 256, 0, st>>>(nq, th_dist, h->dTopk, h->dTopkIdx, h->dMatch, h->dPush, h->dNMatches);
   h->launches += 5;
+  B2S_CUDA(cudaGetLastError());
+  B2S_CUDA(cudaMemcpyAsync(best_idx, h->dMatch, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  if (best_dist) B2S_CUDA(cudaMemcpyAsync(best_dist, h->dPush, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  int acc = 0;
+  B2S_CUDA(cudaMemcpyAsync(&acc, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  if (n_accepted) *n_accepted = acc;
+  return B2S_OK;
+}
+
+// ================================================================================================ persistent feature grid
+struct b2s_frame_grid {
+  b2s_matcher* owner = nullptr;  // identity check only: never dereferenced after creation-time use by destroy
+  int device = 0;
+  int nf = 0;
+  ProjGeom pg;  // geometry + scale tables (th / mode / thresholds are filled per search)
+  float *kpx = nullptr, *kpy = nullptr, *ang = nullptr, *uright = nullptr;
+  int32_t *oct = nullptr, *order = nullptr, *cellStart = nullptr, *cellKey = nullptr, *nB = nullptr, *qOut = nullptr;
+  uint8_t* desc = nullptr;
+};
+
+extern "C" void b2s_frame_grid_destroy(b2s_frame_grid* gr) {
+  if (!gr) return;
+  cudaSetDevice(gr->device);
+  void* ptrs[] = {gr->kpx, gr->kpy, gr->ang, gr->uright, gr->oct, gr->order, gr->cellStart, gr->cellKey, gr->nB, gr->qOut, gr->desc};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete gr;
+}
+
+static int grid_alloc(b2s_matcher* h, int nf, const b2s_frame_geom* g, const float* inv_level_sigma2, b2s_frame_grid** out) {
+  if (!h || !out || nf < 0 || nf > h->maxF || !g || !g->scale_factors || g->nlevels < 1 || g->nlevels > 16) {
+    set_error("b2s_frame_grid_create: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  *out = nullptr;
+  B2S_CUDA(cudaSetDevice(h->device));
+  b2s_frame_grid* gr = new b2s_frame_grid();
+  gr->owner = h;
+  gr->device = h->device;
+  gr->nf = nf;
+  ProjGeom& pg = gr->pg;
+  memset(&pg, 0, sizeof(pg));
+  pg.minX = g->mnMinX; pg.minY = g->mnMinY; pg.maxX = g->mnMaxX; pg.maxY = g->mnMaxY;
+  pg.invW = (float)GRID_COLS / (g->mnMaxX - g->mnMinX);  // src/Frame.cc:213-214
+  pg.invH = (float)GRID_ROWS / (g->mnMaxY - g->mnMinY);
+  pg.bf = g->bf; pg.nlevels = g->nlevels;
+  for (int i = 0; i < 16; i++) {
+    pg.scale[i] = i < g->nlevels ? g->scale_factors[i] : 0.f;
+    pg.invSigma2[i] = (inv_level_sigma2 && i < g->nlevels) ? inv_level_sigma2[i] : 0.f;
+  }
+  const size_t n = (size_t)std::max(nf, 1);
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+  };
+  A((void**)&gr->kpx, n * 4); A((void**)&gr->kpy, n * 4); A((void**)&gr->ang, n * 4); A((void**)&gr->uright, n * 4);
+  A((void**)&gr->oct, n * 4); A((void**)&gr->order, n * 4); A((void**)&gr->cellKey, n * 4);
+  A((void**)&gr->cellStart, (GRID_COLS * GRID_ROWS + 2) * 4); A((void**)&gr->nB, 4); A((void**)&gr->qOut, (n + 1) * 4);
+  A((void**)&gr->desc, n * 32);
+  if (e != cudaSuccess) {
+    set_error("b2s_frame_grid_create: %s", cudaGetErrorString(e));
+    b2s_frame_grid_destroy(gr);
+    return B2S_ERR_CUDA;
+  }
+  *out = gr;
+  return B2S_OK;
+}
+
+// Frame::AssignFeaturesToGrid (src/Frame.cc:461-491) on the arrays already in gr: cell key, stable rank, cell starts
+static int grid_build(b2s_frame_grid* gr, cudaStream_t st) {
+  b2s_matcher* h = gr->owner;
+  const int nf = gr->nf;
+  B2S_CUDA(cudaMemcpyAsync(gr->nB, &gr->nf, 4, cudaMemcpyHostToDevice, st));
+  if (nf > 0) {
+    k_proj_cell_key<<<div_up(nf, 256), 256, 0, st>>>(gr->kpx, gr->kpy, nf, gr->pg, gr->cellKey);
+    k_rank_by_key<<<dim3(div_up(nf, 128), 1), 128, 0, st>>>(gr->cellKey, gr->nB, nf, gr->order);
+  }
+  k_proj_cell_start<<<div_up(nf + 1, 256), 256, 0, st>>>(gr->cellKey, gr->order, nf, gr->cellStart);
+  h->launches += 3;
+  B2S_CUDA(cudaGetLastError());
+  B2S_CUDA(cudaStreamSynchronize(st));
+  return B2S_OK;
+}
+
+extern "C" int b2s_frame_grid_create(b2s_matcher* h, const float* kpx, const float* kpy, const int32_t* octave, const float* angle,
+                                     const float* uright, const uint8_t* desc, int nf, const b2s_frame_geom* g,
+                                     const float* inv_level_sigma2, b2s_frame_grid** out) {
+  if (nf > 0 && (!kpx || !kpy || !octave || !angle || !uright || !desc)) return B2S_ERR_BAD_ARG;
+  int rc = grid_alloc(h, nf, g, inv_level_sigma2, out);
+  if (rc != B2S_OK) return rc;
+  b2s_frame_grid* gr = *out;
+  cudaStream_t st = h->stream;
+  if (nf > 0) {
+    B2S_CUDA(cudaMemcpyAsync(gr->kpx, kpx, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(gr->kpy, kpy, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(gr->oct, octave, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(gr->ang, angle, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(gr->uright, uright, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(gr->desc, desc, (size_t)nf * 32, cudaMemcpyHostToDevice, st));
+  }
+  rc = grid_build(gr, st);
+  if (rc != B2S_OK) {
+    b2s_frame_grid_destroy(gr);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+extern "C" int b2s_frame_grid_create_device(b2s_matcher* h, const b2s_keypoint* d_kps, const uint8_t* d_desc, int nf,
+                                            const float* d_uright, const b2s_frame_geom* g, const float* inv_level_sigma2,
+                                            void* stream, b2s_frame_grid** out) {
+  if (nf > 0 && (!d_kps || !d_desc)) return B2S_ERR_BAD_ARG;
+  int rc = grid_alloc(h, nf, g, inv_level_sigma2, out);
+  if (rc != B2S_OK) return rc;
+  b2s_frame_grid* gr = *out;
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  if (nf > 0) {
+    k_unpack_kps<<<div_up(nf, 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(d_kps), nf, gr->kpx, gr->kpy, gr->oct, gr->ang);
+    h->launches += 1;
+    if (d_uright) B2S_CUDA(cudaMemcpyAsync(gr->uright, d_uright, (size_t)nf * 4, cudaMemcpyDeviceToDevice, st));
+    else k_fill_i32<<<div_up(nf, 256), 256, 0, st>>>(reinterpret_cast<int32_t*>(gr->uright), (int)0xBF800000, (size_t)nf);  // -1.0f
+    B2S_CUDA(cudaMemcpyAsync(gr->desc, d_desc, (size_t)nf * 32, cudaMemcpyDeviceToDevice, st));
+  }
+  rc = grid_build(gr, st);
+  if (rc != B2S_OK) {
+    b2s_frame_grid_destroy(gr);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+extern "C" int b2s_frame_grid_size(const b2s_frame_grid* gr) { return gr ? gr->nf : 0; }
+
+extern "C" int b2s_frame_grid_features_in_area(b2s_frame_grid* gr, float x, float y, float r, int min_level, int max_level,
+                                               int32_t* out, int cap, int* n) {
+  if (!gr || !n || cap < 0 || (cap > 0 && !out)) return B2S_ERR_BAD_ARG;
+  *n = 0;
+  if (gr->nf == 0) return B2S_OK;
+  b2s_matcher* h = gr->owner;
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int c = std::min(cap, gr->nf);
+  k_grid_query<<<1, 32, 0, st>>>(x, y, r, min_level, max_level, gr->kpx, gr->kpy, gr->oct, gr->uright, gr->order, gr->cellStart,
+                                 gr->pg, gr->qOut + 1, c, gr->qOut);
+  h->launches += 1;
+  B2S_CUDA(cudaGetLastError());
+  int cnt = 0;
+  B2S_CUDA(cudaMemcpyAsync(&cnt, gr->qOut, 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  *n = cnt;
+  if (cnt > cap) {
+    set_error("b2s_frame_grid_features_in_area: %d features, capacity %d", cnt, cap);
+    return B2S_ERR_CAPACITY;
+  }
+  if (cnt > 0) B2S_CUDA(cudaMemcpy(out, gr->qOut + 1, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+  return B2S_OK;
+}
+
+// the three projection searches on a resident grid: only the queries (and the occupancy flags) travel
+extern "C" int b2s_search_by_projection_last_grid(b2s_matcher* h, b2s_frame_grid* gr, const b2s_proj_query* q, int nq,
+                                                  const uint8_t* occupied, float th, int mode, int th_high, int check_ori,
+                                                  int32_t* match_cur, int* nmatches) {
+  if (!h || !gr || gr->owner != h || nq < 0 || nq > h->maxF || !match_cur || !nmatches) {
+    set_error("b2s_search_by_projection_last_grid: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  const int nf = gr->nf;
+  *nmatches = 0;
+  for (int j = 0; j < nf; j++) match_cur[j] = -1;
+  if (nq == 0 || nf == 0) return B2S_OK;
+  if (!q) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  ProjGeom pg = gr->pg;
+  pg.th = th; pg.mode = mode; pg.thHigh = th_high; pg.checkOri = check_ori;
+  B2S_CUDA(cudaMemcpyAsync(h->dQueries, q, (size_t)nq * sizeof(ProjQuery), cudaMemcpyHostToDevice, st));
+  if (occupied) B2S_CUDA(cudaMemcpyAsync(h->dOcc, occupied, (size_t)nf, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemsetAsync(h->dTaken, 0, (size_t)nf, st));
+  k_fill_i32<<<div_up(nf, 256), 256, 0, st>>>(h->dMatch, -1, (size_t)nf);
+  k_proj_topk<ProjQuery><<<div_up(nq, 8), 256, 0, st>>>(h->dQueries, nq, gr->kpx, gr->kpy, gr->oct, gr->uright,
+                                                        occupied ? h->dOcc : nullptr, gr->desc, gr->order, gr->cellStart, pg,
+                                                        h->dTopk, h->dTopkIdx, h->dCandCnt);
+  k_proj_resolve<<<1, 32, 0, st>>>(h->dQueries, nq, gr->kpx, gr->kpy, gr->oct, gr->ang, gr->uright,
+                                   occupied ? h->dOcc : nullptr, gr->desc, gr->order, gr->cellStart, pg, h->dTopk, h->dTopkIdx,
+                                   h->dCandCnt, h->dTaken, h->dMatch, h->dPush, h->dExtra, h->dHist);
+  k_proj_cull<<<1, 256, 0, st>>>(check_ori, h->dHist, h->dExtra, h->dMatch, h->dPush, h->dNMatches);
+  h->launches += 4;
+  B2S_CUDA(cudaGetLastError());
+  B2S_CUDA(cudaMemcpyAsync(match_cur, h->dMatch, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  return B2S_OK;
+}
+
+extern "C" int b2s_search_by_projection_map_grid(b2s_matcher* h, b2s_frame_grid* gr, const b2s_map_query* q, int nq,
+                                                 const uint8_t* occupied, float th, int th_high, float nnratio,
+                                                 int32_t* match_cur, int* nmatches) {
+  if (!h || !gr || gr->owner != h || nq < 0 || nq > h->maxF || !match_cur || !nmatches) {
+    set_error("b2s_search_by_projection_map_grid: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  const int nf = gr->nf;
+  *nmatches = 0;
+  for (int j = 0; j < nf; j++) match_cur[j] = -1;
+  if (nq == 0 || nf == 0) return B2S_OK;
+  if (!q) return B2S_ERR_BAD_ARG;
+  for (int i = 0; i < nq; i++)
+    if (q[i].in_view && (q[i].level < 0 || q[i].level >= gr->pg.nlevels)) {
+      set_error("b2s_search_by_projection_map_grid: query %d has a predicted level outside the scale table", i);
+      return B2S_ERR_BAD_ARG;
+    }
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  ProjGeom pg = gr->pg;
+  pg.th = th; pg.mode = 0; pg.thHigh = th_high; pg.checkOri = 0;
+  MapQuery* dQ = reinterpret_cast<MapQuery*>(h->dQueries);
+  B2S_CUDA(cudaMemcpyAsync(dQ, q, (size_t)nq * sizeof(MapQuery), cudaMemcpyHostToDevice, st));
+  if (occupied) B2S_CUDA(cudaMemcpyAsync(h->dOcc, occupied, (size_t)nf, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemsetAsync(h->dTaken, 0, (size_t)nf, st));
+  k_fill_i32<<<div_up(nf, 256), 256, 0, st>>>(h->dMatch, -1, (size_t)nf);
+  k_proj_topk<MapQuery><<<div_up(nq, 8), 256, 0, st>>>(dQ, nq, gr->kpx, gr->kpy, gr->oct, gr->uright,
+                                                       occupied ? h->dOcc : nullptr, gr->desc, gr->order, gr->cellStart, pg,
+                                                       h->dTopk, h->dTopkIdx, h->dCandCnt);
+  k_map_resolve<<<1, 32, 0, st>>>(dQ, nq, gr->kpx, gr->kpy, gr->oct, gr->uright, occupied ? h->dOcc : nullptr, gr->desc,
+                                  gr->order, gr->cellStart, pg, nnratio, h->dTopk, h->dTopkIdx, h->dCandCnt, h->dTaken,
+                                  h->dMatch, h->dNMatches);
+  h->launches += 3;
+  B2S_CUDA(cudaGetLastError());
+  B2S_CUDA(cudaMemcpyAsync(match_cur, h->dMatch, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  return B2S_OK;
+}
+
+extern "C" int b2s_search_windows_grid(b2s_matcher* h, b2s_frame_grid* gr, const b2s_win_query* q, int nq,
+                                       const uint8_t* occupied, int flags, int th_dist, int32_t* best_idx, int32_t* best_dist,
+                                       int* n_accepted) {
+  if (!h || !gr || gr->owner != h || nq < 0 || nq > h->maxF || !best_idx) {
+    set_error("b2s_search_windows_grid: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  const int nf = gr->nf;
+  if (n_accepted) *n_accepted = 0;
+  for (int i = 0; i < nq; i++) {
+    best_idx[i] = -1;
+    if (best_dist) best_dist[i] = 256;
+  }
+  if (nq == 0 || nf == 0) return B2S_OK;
+  if (!q) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  ProjGeom pg = gr->pg;
+  pg.th = 1.f; pg.mode = 0; pg.thHigh = th_dist; pg.checkOri = 0; pg.winFlags = flags;
+  const bool greedy = (flags & B2S_WIN_GREEDY) != 0;
+  const bool useOcc = greedy && occupied;
+  WinQuery* dQ = reinterpret_cast<WinQuery*>(h->dQueries);
+  B2S_CUDA(cudaMemcpyAsync(dQ, q, (size_t)nq * sizeof(WinQuery), cudaMemcpyHostToDevice, st));
+  if (useOcc) B2S_CUDA(cudaMemcpyAsync(h->dOcc, occupied, (size_t)nf, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemsetAsync(h->dTaken, 0, (size_t)nf, st));
+  B2S_CUDA(cudaMemsetAsync(h->dNMatches, 0, 4, st));
+  k_proj_topk<WinQuery><<<div_up(nq, 8), 256, 0, st>>>(dQ, nq, gr->kpx, gr->kpy, gr->oct, gr->uright,
+                                                       useOcc ? h->dOcc : nullptr, gr->desc, gr->order, gr->cellStart, pg,
+                                                       h->dTopk, h->dTopkIdx, h->dCandCnt);
+  if (greedy)
+    k_win_resolve<<<1, 32, 0, st>>>(dQ, nq, th_dist, gr->kpx, gr->kpy, gr->oct, gr->uright, useOcc ? h->dOcc : nullptr,
+                                    gr->desc, gr->order, gr->cellStart, pg, h->dTopk, h->dTopkIdx, h->dCandCnt, h->dTaken,
+                                    h->dMatch, h->dPush, h->dNMatches);
+  else
+    k_win_pick<<<div_up(nq, 256), 256, 0, st>>>(nq, th_dist, h->dTopk, h->dTopkIdx, h->dMatch, h->dPush, h->dNMatches);
+  h->launches += 2;
   B2S_CUDA(cudaGetLastError());
   B2S_CUDA(cudaMemcpyAsync(best_idx, h->dMatch, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
   if (best_dist) B2S_CUDA(cudaMemcpyAsync(best_dist, h->dPush, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));

@@ -72,6 +72,58 @@ int ORBmatcher::SearchByProjection(const std::vector<b2s_proj_query>& q, const f
   return nm;
 }
 
+FrameGrid::FrameGrid(ORBmatcher& matcher, const float* kpx, const float* kpy, const int32_t* octave, const float* angle,
+                     const float* uright, const uint8_t* descriptors, int nFeatures, const b2s_frame_geom& geom,
+                     const float* invLevelSigma2)
+    : mN(nFeatures) {
+  int rc = b2s_frame_grid_create(matcher.handle(nFeatures), kpx, kpy, octave, angle, uright, descriptors, nFeatures, &geom,
+                                 invLevelSigma2, &mpGrid);
+  if (rc != B2S_OK) fail("FrameGrid", rc);
+}
+FrameGrid::~FrameGrid() { b2s_frame_grid_destroy(mpGrid); }
+
+std::vector<size_t> FrameGrid::GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel,
+                                                 const int maxLevel) const {
+  std::vector<int32_t> idx((size_t)(mN > 0 ? mN : 1));
+  int n = 0;
+  int rc = b2s_frame_grid_features_in_area(mpGrid, x, y, r, minLevel, maxLevel, idx.data(), (int)idx.size(), &n);
+  if (rc != B2S_OK) fail("FrameGrid::GetFeaturesInArea", rc);
+  return std::vector<size_t>(idx.begin(), idx.begin() + n);
+}
+
+int ORBmatcher::SearchByProjection(const FrameGrid& grid, const std::vector<b2s_proj_query>& q, const uint8_t* occupied,
+                                   float th, int mode, std::vector<int32_t>& matchCur) {
+  Ensure((int)q.size() > grid.N() ? (int)q.size() : grid.N());
+  matchCur.assign(grid.N(), -1);
+  int nm = 0;
+  int rc = b2s_search_by_projection_last_grid(mpHandle, grid.handle(), q.data(), (int)q.size(), occupied, th, mode, TH_HIGH,
+                                              mbCheckOrientation, matchCur.data(), &nm);
+  if (rc != B2S_OK) fail("ORBmatcher::SearchByProjection(grid)", rc);
+  return nm;
+}
+
+int ORBmatcher::SearchByProjection(const FrameGrid& grid, const std::vector<b2s_map_query>& mp, const uint8_t* occupied,
+                                   float th, std::vector<int32_t>& matchF) {
+  Ensure((int)mp.size() > grid.N() ? (int)mp.size() : grid.N());
+  matchF.assign(grid.N(), -1);
+  int nm = 0;
+  int rc = b2s_search_by_projection_map_grid(mpHandle, grid.handle(), mp.data(), (int)mp.size(), occupied, th, TH_HIGH,
+                                             mfNNratio, matchF.data(), &nm);
+  if (rc != B2S_OK) fail("ORBmatcher::SearchByProjection(grid, map points)", rc);
+  return nm;
+}
+
+int ORBmatcher::SearchWindows(const FrameGrid& grid, const std::vector<b2s_win_query>& mp, const uint8_t* occupied, int flags,
+                              std::vector<int32_t>& bestIdx) {
+  Ensure((int)mp.size() > grid.N() ? (int)mp.size() : grid.N());
+  bestIdx.assign(mp.size(), -1);
+  int na = 0;
+  int rc = b2s_search_windows_grid(mpHandle, grid.handle(), mp.data(), (int)mp.size(), occupied, flags, TH_LOW, bestIdx.data(),
+                                   nullptr, &na);
+  if (rc != B2S_OK) fail("ORBmatcher::SearchWindows(grid)", rc);
+  return na;
+}
+
 int ORBmatcher::SearchForInitialization(const float* kpx1, const float* kpy1, const int32_t* octave1, const float* angle1,
                                         const uint8_t* d1, int n1, const float* kpx2, const float* kpy2,
                                         const int32_t* octave2, const float* angle2, const uint8_t* d2, int n2,

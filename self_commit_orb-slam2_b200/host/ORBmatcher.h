@@ -18,6 +18,28 @@ struct BowSide {
   int n = 0;
 };
 
+class ORBmatcher;
+
+// Frame::AssignFeaturesToGrid / GetFeaturesInArea (src/Frame.cc:461-491, 741-852) kept on the device (b2s_frame_grid_*):
+// built once per Frame / KeyFrame, it lets the consecutive projection matchers upload only their queries.
+class FrameGrid {
+ public:
+  FrameGrid(ORBmatcher& matcher, const float* kpx, const float* kpy, const int32_t* octave, const float* angle,
+            const float* uright, const uint8_t* descriptors, int nFeatures, const b2s_frame_geom& geom,
+            const float* invLevelSigma2 = nullptr);
+  ~FrameGrid();
+  FrameGrid(const FrameGrid&) = delete;
+  FrameGrid& operator=(const FrameGrid&) = delete;
+  std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
+                                        const int maxLevel = -1) const;
+  int N() const { return mN; }
+  b2s_frame_grid* handle() const { return mpGrid; }
+
+ private:
+  b2s_frame_grid* mpGrid = nullptr;
+  int mN = 0;
+};
+
 class ORBmatcher {
  public:
   static const int TH_LOW = 50;        // src/ORBmatcher.cc:49-51
@@ -48,6 +70,13 @@ class ORBmatcher {
   int SearchByProjectionReloc(std::vector<b2s_proj_query> queries, const float* kpx, const float* kpy, const int32_t* octave,
                               const float* angle, const uint8_t* occupied, const uint8_t* descriptors, int nFeatures,
                               const b2s_frame_geom& geom, float th, int ORBdist, std::vector<int32_t>& matchCur);
+  // the same three searches on a resident FrameGrid (only queries and occupancy flags are uploaded)
+  int SearchByProjection(const FrameGrid& grid, const std::vector<b2s_proj_query>& queries, const uint8_t* occupied, float th,
+                         int mode, std::vector<int32_t>& matchCur);
+  int SearchByProjection(const FrameGrid& grid, const std::vector<b2s_map_query>& mapPoints, const uint8_t* occupied, float th,
+                         std::vector<int32_t>& matchF);
+  int SearchWindows(const FrameGrid& grid, const std::vector<b2s_win_query>& mapPoints, const uint8_t* occupied, int flags,
+                    std::vector<int32_t>& bestIdx);
   // SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, float th) (src/ORBmatcher.cc:70) after
   // Frame::isInFrustum filled the track fields of the local map points
   int SearchByProjection(const std::vector<b2s_map_query>& mapPoints, const float* kpx, const float* kpy,
@@ -69,6 +98,11 @@ class ORBmatcher {
   int SearchForTriangulation(const b2s_kf_features& kf1, const b2s_kf_features& kf2, const float F12[9], float ex, float ey,
                              const float* scaleFactors2, const float* levelSigma2_2, int nLevels, bool bOnlyStereo,
                              std::vector<std::pair<size_t, size_t> >& vMatchedPairs);
+
+  b2s_matcher* handle(int nFeatures) {  // (FrameGrid needs the handle sized for the frame)
+    Ensure(nFeatures);
+    return mpHandle;
+  }
 
  protected:
   void Ensure(int n);
