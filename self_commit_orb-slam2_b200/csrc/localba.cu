@@ -63,6 +63,8 @@ struct BaPtrs {  // strided per-window arrays
   int* blkFirst;           // per block row: first non-empty block column (envelope of the reduced system)
   int *blkOrder, *blkNZ;   // lower blocks sorted by descending pair count; number of non-empty blocks
   int capPairs, capBlk;
+  double* eWq;             // per edge: rho' * invSigma2 of the last build (0: edge excluded), for the W_e recomputation
+  int schurRecompute;      // Schur phase recomputes W_e from (pose, landmark, eWq) instead of gathering the stored blocks
   double *partChi, *partScale;   // per-CTA partial sums [window][nCta]
   unsigned int* bar;             // per-window barrier counters
   long long* prof;               // per-window phase cycle counters (debug): 16 slots
@@ -336,6 +338,7 @@ __device__ void phase_build_edges(const BaPtrs& p, const WinCtx& c, const BaWin&
   const int lane = threadIdx.x & 31;
   double* tile = stage + (size_t)(threadIdx.x >> 5) * (30 * 33);
   const int nE = W.nEdges;
+  const bool skipW = p.schurRecompute && p.usePairs[w];  // W_e is recomputed by its two consumers: neither formed nor stored
   double chi = 0;
   for (int base0 = c.gtid - lane; base0 < nE; base0 += 2 * c.gthreads) {
     EdgeIdx ix[2];
@@ -353,6 +356,7 @@ __device__ void phase_build_edges(const BaPtrs& p, const WinCtx& c, const BaWin&
       double rec[30];
 #pragma unroll
       for (int k = 0; k < 30; k++) rec[k] = 0;
+      if (!ix[h].live && e < nE) p.eWq[eo] = 0.0;
       if (ix[h].live) {
         const bool stereo = ix[h].stereo;
         EdgeJac J;
@@ -371,16 +375,19 @@ __device__ void phase_build_edges(const BaPtrs& p, const WinCtx& c, const BaWin&
           rec[27 + r] = er[r];
         }
         const double wq = rho1 * w0;
+        p.eWq[eo] = wq;
         // W_e (6x3)
+        if (!skipW) {
 #pragma unroll
-        for (int i = 0; i < 6; i++)
+          for (int i = 0; i < 6; i++)
 #pragma unroll
-          for (int j = 0; j < 3; j++) {
-            double hh = 0;
+            for (int j = 0; j < 3; j++) {
+              double hh = 0;
 #pragma unroll
-            for (int r = 0; r < 3; r++) hh += J.B[r][i] * wq * J.A[r][j];
-            rec[i * 3 + j] = hh;
-          }
+              for (int r = 0; r < 3; r++) hh += J.B[r][i] * wq * J.A[r][j];
+              rec[i * 3 + j] = hh;
+            }
+        }
         // A^T (wq) A upper triangle, A^T omega_r
         int t = 18;
 #pragma unroll
@@ -402,13 +409,15 @@ __device__ void phase_build_edges(const BaPtrs& p, const WinCtx& c, const BaWin&
       }
 #pragma unroll
       for (int k = 0; k < 30; k++)
-        if (k < 18 || k >= 27) tile[k * 33 + lane] = rec[k];
+        if ((k < 18 && !skipW) || k >= 27) tile[k * 33 + lane] = rec[k];
       __syncwarp();
-      double* Wout = p.W + ((size_t)w * p.capE + base) * 18;
       const int nv = min(32, nE - base);
-      for (int idx = lane; idx < nv * 18; idx += 32) {
-        const int ed = idx / 18, k = idx - ed * 18;
-        Wout[idx] = tile[k * 33 + ed];
+      if (!skipW) {
+        double* Wout = p.W + ((size_t)w * p.capE + base) * 18;
+        for (int idx = lane; idx < nv * 18; idx += 32) {
+          const int ed = idx / 18, k = idx - ed * 18;
+          Wout[idx] = tile[k * 33 + ed];
+        }
       }
       if (e < nE) {  // landmark-side terms: structure-of-arrays [term][edge], written straight from registers
 #pragma unroll
@@ -809,6 +818,126 @@ __device__ __forceinline__ void schur_block_pairs(const int4* prs, int qBeg, int
   cp_async_wait<0>();
 }
 
+// W_e = B^T (rho' Omega) A of one edge from the camera's rotation / translation (Rt: R row-major, then t), the landmark and
+// the edge weight — the same closed forms as edge_jacobians; wq == 0 (excluded edge) gives an exact zero block.
+__device__ __forceinline__ void edge_W_regs(const double* __restrict__ Rt, const double X0, const double X1, const double X2,
+                                            bool st, double wq, double fx, double fy, double bf, double (&wv)[18]) {
+  const double x = Rt[0] * X0 + Rt[1] * X1 + Rt[2] * X2 + Rt[9];
+  const double y = Rt[3] * X0 + Rt[4] * X1 + Rt[5] * X2 + Rt[10];
+  const double z = Rt[6] * X0 + Rt[7] * X1 + Rt[8] * X2 + Rt[11];
+  const double iz = 1.0 / z, iz2 = iz * iz;
+  const double fxz = fx * iz, fyz = fy * iz, fxx = fx * x * iz2, fyy = fy * y * iz2;
+  const double bz = st ? bf * iz2 : 0.0;
+  double A[3][3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    A[0][c] = wq * (-fxz * Rt[c] + fxx * Rt[6 + c]);
+    A[1][c] = wq * (-fyz * Rt[3 + c] + fyy * Rt[6 + c]);
+    A[2][c] = st ? (A[0][c] - wq * bz * Rt[6 + c]) : 0.0;
+  }
+  double B[3][6];
+  B[0][0] = x * y * iz2 * fx;
+  B[0][1] = -(1 + (x * x * iz2)) * fx;
+  B[0][2] = y * iz * fx;
+  B[0][3] = -iz * fx;
+  B[0][4] = 0;
+  B[0][5] = x * iz2 * fx;
+  B[1][0] = (1 + y * y * iz2) * fy;
+  B[1][1] = -x * y * iz2 * fy;
+  B[1][2] = -x * iz * fy;
+  B[1][3] = 0;
+  B[1][4] = -iz * fy;
+  B[1][5] = y * iz2 * fy;
+  B[2][0] = st ? (B[0][0] - bz * y) : 0.0;
+  B[2][1] = st ? (B[0][1] + bz * x) : 0.0;
+  B[2][2] = st ? B[0][2] : 0.0;
+  B[2][3] = st ? B[0][3] : 0.0;
+  B[2][4] = 0;
+  B[2][5] = st ? (B[0][5] - bz) : 0.0;
+  const bool zero = !(wq > 0.0);
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double v = B[0][i] * A[0][j] + B[1][i] * A[1][j] + B[2][i] * A[2][j];
+      wv[i * 3 + j] = zero ? 0.0 : v;
+    }
+}
+__device__ __forceinline__ void edge_W_from_Rt(const double* __restrict__ Rt, const double X0, const double X1, const double X2,
+                                               bool st, double wq, double fx, double fy, double bf, double2* __restrict__ out) {
+  double wv[18];
+  edge_W_regs(Rt, X0, X1, X2, st, wq, fx, fy, bf, wv);
+#pragma unroll
+  for (int k = 0; k < 9; k++) out[k] = make_double2(wv[2 * k], wv[2 * k + 1]);
+}
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+
+// per-warp staging of the recomputing Schur loop (double2 units): W_a | W_c tiles (one 9-double2 record per lane each),
+// two Dinv tiles (5 per lane) and two operand tiles (3 per lane: X0 X1 | X2 wq_a | wq_c -), then R|t of the block's two poses
+constexpr int RC_W = 0, RC_D = 32 * 18, RC_OP = RC_D + 2 * 32 * 5, RC_RT = RC_OP + 2 * 32 * 3, RC_TOTAL = RC_RT + 12;
+static_assert(RC_TOTAL <= 2 * GATHER_TILE16, "the recomputing loop reuses the gather staging area");
+
+// Same accumulation as schur_block_pairs, but W_a / W_c are recomputed per pair from 40 bytes of operands that stay
+// resident in L2 (landmark position, two edge weights) instead of gathering two 144-byte blocks from a 4.3 MB array that
+// 32 concurrent windows push out of L2 (profiles/README.md: the gathers were ~all of the kernel's DRAM reads).
+template <bool DIAG>
+__device__ __forceinline__ void schur_block_pairs_rc(const int4* prs, int qBeg, int qEnd, const double* __restrict__ pts,
+                                                     const double* __restrict__ eWq, const double2* Db, double2* buf, int lane,
+                                                     double fx, double fy, double bf, double (&acc)[32], double (&tail)[10]) {
+  const int nIt = (qEnd - qBeg + 31) >> 5;
+  double2* tW = buf + RC_W;
+  const double* Rt = reinterpret_cast<const double*>(buf + RC_RT);
+  auto issue = [&](int slot, const int4& r, bool v) {
+    double2* op = buf + RC_OP + slot * (32 * 3) + lane * 3;
+    if (v) {
+      const double* X = pts + (size_t)r.z * 3;
+      double* o = reinterpret_cast<double*>(op);
+      cp_async8(o, X);
+      cp_async8(o + 1, X + 1);
+      cp_async8(o + 2, X + 2);
+      cp_async8(o + 3, eWq + r.x);
+      if (!DIAG) cp_async8(o + 4, eWq + r.y);
+    }
+    warp_gather16_async<DIAG ? 5 : 3, 5>(buf + RC_D + slot * (32 * 5), Db, r.z, lane);
+  };
+  auto loadRec = [&](int it, int4& r, bool& v) {
+    const int q = qBeg + it * 32 + lane;
+    v = q < qEnd;
+    r = v ? prs[q] : make_int4(0, 0, 0, 0);
+  };
+  int4 r0, r1 = make_int4(0, 0, 0, 0);
+  bool v0, v1 = false;
+  loadRec(0, r0, v0);
+  issue(0, r0, v0);
+  cp_async_commit();
+  if (nIt > 1) loadRec(1, r1, v1);
+  for (int it = 0; it < nIt; it++) {
+    const int slot = it & 1;
+    if (it + 1 < nIt) issue(slot ^ 1, r1, v1);
+    cp_async_commit();
+    int4 r2 = make_int4(0, 0, 0, 0);
+    bool v2 = false;
+    if (it + 2 < nIt) loadRec(it + 2, r2, v2);
+    cp_async_wait<1>();
+    __syncwarp();
+    if (v0) {
+      const double* o = reinterpret_cast<const double*>(buf + RC_OP + slot * (32 * 3) + lane * 3);
+      const double X0 = o[0], X1 = o[1], X2 = o[2];
+      edge_W_from_Rt(Rt, X0, X1, X2, (r0.w & 1) != 0, o[3], fx, fy, bf, tW + lane * 9);
+      if (!DIAG) edge_W_from_Rt(Rt + 12, X0, X1, X2, (r0.w & 2) != 0, o[4], fx, fy, bf, tW + 32 * 9 + lane * 9);
+      schur_accumulate<DIAG>(tW, tW + 32 * 9, buf + RC_D + slot * (32 * 5), lane, acc, tail);
+    }
+    __syncwarp();
+    r0 = r1; v0 = v1;
+    r1 = r2; v1 = v2;
+  }
+  cp_async_wait<0>();
+}
+
 // Schur complement (block_solver.hpp:381-439): one warp per lower block (i1 >= i2); lanes stride over the block's
 // covisibility pairs (edge a of pose i1, edge c of pose i2, same landmark l) and accumulate (W_a Dinv_l) W_c^T; the
 // diagonal blocks also accumulate W_a (Dinv_l b_l) for the right-hand side.  S(i1,i2) = [Hpp + lambda I] - sum.
@@ -846,7 +975,27 @@ __device__ void phase_schur_blocks(const BaPtrs& p, const WinCtx& c, const BaWin
     if (usePairs) {
       const int qBeg = off[t], qEnd = off[t + 1];
       any = qEnd > qBeg;
-      if (any) {
+      if (any && p.schurRecompute) {
+        // rotation / translation of the block's two cameras, staged once per block for the whole warp
+        __syncwarp();
+        if (lane < 2) {
+          const int kf = p.freeKf[(size_t)w * p.capKf + (lane ? i2 : i1)];
+          const double* P = p.pose + ((size_t)w * p.capKf + kf) * PSTRIDE;
+          double R[3][3];
+          quat_to_R(P, R);
+          double* o = reinterpret_cast<double*>(buf + RC_RT) + lane * 12;
+#pragma unroll
+          for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b2 = 0; b2 < 3; b2++) o[a * 3 + b2] = R[a][b2];
+          o[9] = P[4]; o[10] = P[5]; o[11] = P[6];
+        }
+        __syncwarp();
+        const double* ptsW = p.pts + (size_t)w * p.capMp * 3;
+        const double* wqW = p.eWq + (size_t)w * p.capE;
+        if (diag) schur_block_pairs_rc<true>(prs, qBeg, qEnd, ptsW, wqW, Db, buf, lane, W.fx, W.fy, W.bf, acc, tail);
+        else schur_block_pairs_rc<false>(prs, qBeg, qEnd, ptsW, wqW, Db, buf, lane, W.fx, W.fy, W.bf, acc, tail);
+      } else if (any) {
         if (diag) schur_block_pairs<true>(prs, qBeg, qEnd, Wb, Db, buf, lane, acc, tail);
         else schur_block_pairs<false>(prs, qBeg, qEnd, Wb, Db, buf, lane, acc, tail);
       }
@@ -1133,6 +1282,24 @@ __device__ void phase_backsub_update(const BaPtrs& p, const WinCtx& c, const BaW
   const int2* lrec = p.lmRec + (size_t)w * p.capE;
   const double2* Wb2 = reinterpret_cast<const double2*>(p.W + (size_t)w * p.capE * 18);
   double2* tA = reinterpret_cast<double2*>(stage) + (size_t)(threadIdx.x >> 5) * (2 * GATHER_TILE16);
+  const bool recompute = p.schurRecompute && p.usePairs[w];
+  double* RtTab = stage + (size_t)(blockDim.x >> 5) * (2 * GATHER_TILE16) * 2;  // R | t of every free pose (behind the gather tiles)
+  if (recompute && solveOk) {
+    for (int i = threadIdx.x; i < W.nFree; i += blockDim.x) {
+      const double* P = p.pose + ((size_t)w * p.capKf + p.freeKf[(size_t)w * p.capKf + i]) * PSTRIDE;
+      double R[3][3];
+      quat_to_R(P, R);
+      double* o = RtTab + (size_t)i * 12;
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b2 = 0; b2 < 3; b2++) o[a * 3 + b2] = R[a][b2];
+      o[9] = P[4]; o[10] = P[5]; o[11] = P[6];
+    }
+    __syncthreads();
+  }
+  const double* wqW = p.eWq + (size_t)w * p.capE;
+  const uint8_t* stW = p.eStereo + (size_t)w * p.capE;
   for (int l0 = c.gtid - lane; l0 < W.nMp; l0 += c.gthreads) {  // 32 consecutive landmarks per warp, one per lane
     const int l = l0 + lane;
     const bool live = l < W.nMp;
@@ -1154,6 +1321,38 @@ __device__ void phase_backsub_update(const BaPtrs& p, const WinCtx& c, const BaW
     // cooperatively with cp.async into five tiles) are all in flight together, so a group costs two memory latencies
     // instead of three per edge.  Level-1 edges carry W_e = 0 and subtract exact zeros.
     constexpr int NBUF = 5, TILE = 32 * 9;
+    if (recompute) {
+      // W_e^T x_p with W_e recomputed from (R|t of the pose, this landmark, edge weight): five edges' records, then their
+      // weights and flags, are loaded together; no W block is read
+      const double X0 = live ? X[0] : 0.0, X1 = live ? X[1] : 0.0, X2 = live ? X[2] : 1.0;
+      for (int kb0 = 0; kb0 < deg; kb0 += NBUF) {
+        int ee[NBUF], pp[NBUF];
+        double wq[NBUF];
+        bool st[NBUF];
+#pragma unroll
+        for (int j = 0; j < NBUF; j++) {
+          const int2 r = (kb0 + j < deg) ? lrec[kBeg + kb0 + j] : make_int2(0, -1);
+          ee[j] = r.x;
+          pp[j] = r.y;
+        }
+#pragma unroll
+        for (int j = 0; j < NBUF; j++) {
+          wq[j] = wqW[ee[j]];
+          st[j] = stW[ee[j]] != 0;
+        }
+#pragma unroll
+        for (int j = 0; j < NBUF; j++) {
+          if (pp[j] < 0) continue;
+          double wb[18];
+          edge_W_regs(RtTab + (size_t)pp[j] * 12, X0, X1, X2, st[j], wq[j], W.fx, W.fy, W.bf, wb);
+          const double* xp = p.x + xo + (size_t)pp[j] * 6;
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+            for (int r = 0; r < 6; r++) cl[cc] -= wb[r * 3 + cc] * xp[r];
+        }
+      }
+    } else
     for (int kb0 = 0; kb0 < maxDeg; kb0 += NBUF) {
       int ee[NBUF], pp[NBUF];
 #pragma unroll
@@ -1461,7 +1660,8 @@ __global__ void __launch_bounds__(64) k_pair_build(BaPtrs p, int fill) {
     __syncthreads();
     if (fill && hit) {
       const int pos = off[blockIdx.x] + running + (wid ? wsum[0] : 0) + __popc(bm & ((1u << lane) - 1u));
-      p.pairRec[(size_t)w * p.capPairs + pos] = make_int4(a, cidx, p.eMp[(size_t)w * p.capE + a], 0);
+      const int fl = (p.eStereo[(size_t)w * p.capE + a] ? 1 : 0) | (p.eStereo[(size_t)w * p.capE + cidx] ? 2 : 0);
+      p.pairRec[(size_t)w * p.capPairs + pos] = make_int4(a, cidx, p.eMp[(size_t)w * p.capE + a], fl);
     }
     total += wsum[0] + wsum[1];
     __syncthreads();
@@ -1975,6 +2175,9 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   A(&d.eObs, B * max_edges * 12); A(&d.eW, B * max_edges * 4);
   A(&d.eStereo, B * max_edges); A(&d.eLevel, B * max_edges); A(&d.eOutlier, B * max_edges);
   A(&d.err, B * max_edges * 24); A(&d.chi2, B * max_edges * 8); A(&d.W, B * max_edges * 18 * 8);
+  A(&d.eWq, B * max_edges * 8);
+  d.schurRecompute = 1;
+  if (const char* ev = getenv("B2S_BA_SCHUR_RC")) d.schurRecompute = atoi(ev) != 0;  // 0: gather the stored W blocks
   A(&d.mpStart, B * (max_mp + 1) * 4); A(&d.mpEdges, B * max_edges * 4);
   A(&d.kfStart, B * (max_kf + 1) * 4); A(&d.kfEdges, B * max_edges * 4);
   A(&d.Hpp, B * max_kf * 36 * 8); A(&d.Hll, B * max_mp * 9 * 8);
@@ -2000,7 +2203,8 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   HA(&s.win, B * sizeof(BaWin)); HA(&s.st, B * sizeof(BaState));
   h->smemBytes = (size_t)((CHOL_BS + 1) * CHOL_PP + (size_t)(d.ldS + 4) * CHOL_PP + 2 * d.ldS) * 8 + (size_t)(d.ldS + 8 + max_kf) * 4;
   h->smemBytes = std::max(h->smemBytes, (size_t)(BA_T / 32) * 30 * 33 * 8);  // per-warp staging tiles of phase_build_edges
-  h->smemBytes = std::max(h->smemBytes, (size_t)(BA_T / 32) * 2 * GATHER_TILE16 * 16);  // double-buffered gather tiles (Schur)
+  h->smemBytes = std::max(h->smemBytes, (size_t)(BA_T / 32) * 2 * GATHER_TILE16 * 16  // double-buffered gather tiles (Schur)
+                                            + (size_t)max_kf * 12 * 8);                  // + R|t table (back-substitution)
   if (e == cudaSuccess && h->smemBytes > 48 * 1024)
     e = cudaFuncSetAttribute(k_local_ba, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes);
   if (e != cudaSuccess) {
