@@ -30,6 +30,7 @@ constexpr int CHOL_BS = 32;
 
 struct BaState {
   int active, round, it, qmax, needBuild, restore, doOutlier, solveOk, stop, nTrials, nBad, robust, finishedRound0;
+  int errBuf, errCurrent;  // recompute mode: which err / eWq buffer describes the linearisation state; it is up to date
   int its[2];
   double lambda, ni, currentChi, iniChi, tempChi, rho, chi2Final;
   unsigned long long maxDiagBits;
@@ -50,7 +51,8 @@ struct BaPtrs {  // strided per-window arrays
   int *eKf, *eMp;
   float *eObs, *eW;
   uint8_t *eStereo, *eLevel, *eOutlier;
-  double *err, *chi2, *W;
+  double *err, *chi2, *W;  // err = errB[0]
+  double *errB[2], *eWqB[2];  // recompute mode: double-buffered (phase_errors fills the other one, an accepted step swaps)
   int *mpStart, *mpEdges, *kfStart, *kfEdges;
   double *Hpp, *Hll, *b, *x, *Dinv, *S;
   double *db, *Y;      // Dinv*b_l per landmark, (Y unused)
@@ -356,7 +358,7 @@ __device__ void phase_build_edges(const BaPtrs& p, const WinCtx& c, const BaWin&
       double rec[30];
 #pragma unroll
       for (int k = 0; k < 30; k++) rec[k] = 0;
-      if (!ix[h].live && e < nE) p.eWq[eo] = 0.0;
+      if (!ix[h].live && e < nE) p.eWqB[0][eo] = 0.0;
       if (ix[h].live) {
         const bool stereo = ix[h].stereo;
         EdgeJac J;
@@ -375,7 +377,7 @@ __device__ void phase_build_edges(const BaPtrs& p, const WinCtx& c, const BaWin&
           rec[27 + r] = er[r];
         }
         const double wq = rho1 * w0;
-        p.eWq[eo] = wq;
+        p.eWqB[0][eo] = wq;
         // W_e (6x3)
         if (!skipW) {
 #pragma unroll
@@ -473,8 +475,100 @@ __device__ void phase_reduce_landmarks(const BaPtrs& p, const WinCtx& c, const B
   atomic_max_pos_double(&p.st[w].maxDiagBits, md);
 }
 
+// Recompute mode: the landmark side of buildSystem straight from the stored errors and weights — per edge
+// A = d e / d X (from R|t of its keyframe and the landmark), H_ll += A^T (rho' Omega) A, b_l -= A^T (rho' Omega) e, in list order.
+__device__ void phase_reduce_landmarks_rc(const BaPtrs& p, const WinCtx& c, const BaWin& W, int cur, double* RtTab) {
+  const int w = c.w;
+  for (int k = threadIdx.x; k < W.nKf; k += blockDim.x) {
+    const double* P = p.pose + ((size_t)w * p.capKf + k) * PSTRIDE;
+    double R[3][3];
+    quat_to_R(P, R);
+    double* o = RtTab + (size_t)k * 12;
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b2 = 0; b2 < 3; b2++) o[a * 3 + b2] = R[a][b2];
+    o[9] = P[4]; o[10] = P[5]; o[11] = P[6];
+  }
+  __syncthreads();
+  const int* ms = p.mpStart + (size_t)w * (p.capMp + 1);
+  const int* me = p.mpEdges + (size_t)w * p.capE;
+  const int* eKf = p.eKf + (size_t)w * p.capE;
+  const uint8_t* eSt = p.eStereo + (size_t)w * p.capE;
+  const double* wqW = p.eWqB[cur] + (size_t)w * p.capE;
+  const double* erW = p.errB[cur] + (size_t)w * p.capE * 3;
+  const double fx = W.fx, fy = W.fy, bf = W.bf;
+  double md = 0;
+  for (int l = c.gtid; l < W.nMp; l += c.gthreads) {
+    const size_t mo = (size_t)w * p.capMp + l;
+    const double* Xp = p.pts + mo * 3;
+    const double X0 = Xp[0], X1 = Xp[1], X2 = Xp[2];
+    double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const int kBeg = ms[l], kEnd = ms[l + 1];
+    for (int k0 = kBeg; k0 < kEnd; k0 += 4) {
+      int ee[4], kf[4];
+      double wq[4], er[4][3];
+      bool st[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) ee[j] = me[min(k0 + j, kEnd - 1)];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        kf[j] = eKf[ee[j]];
+        wq[j] = wqW[ee[j]];
+        st[j] = eSt[ee[j]] != 0;
+#pragma unroll
+        for (int r = 0; r < 3; r++) er[j][r] = erW[(size_t)ee[j] * 3 + r];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (k0 + j >= kEnd || !(wq[j] > 0.0)) continue;
+        const double* Rt = RtTab + (size_t)kf[j] * 12;
+        const double x = Rt[0] * X0 + Rt[1] * X1 + Rt[2] * X2 + Rt[9];
+        const double y = Rt[3] * X0 + Rt[4] * X1 + Rt[5] * X2 + Rt[10];
+        const double z = Rt[6] * X0 + Rt[7] * X1 + Rt[8] * X2 + Rt[11];
+        const double iz = 1.0 / z, iz2 = iz * iz;
+        const double fxz = fx * iz, fyz = fy * iz, fxx = fx * x * iz2, fyy = fy * y * iz2;
+        const double bz = st[j] ? bf * iz2 : 0.0;
+        double A[3][3];
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) {
+          A[0][cc] = -fxz * Rt[cc] + fxx * Rt[6 + cc];
+          A[1][cc] = -fyz * Rt[3 + cc] + fyy * Rt[6 + cc];
+          A[2][cc] = st[j] ? (A[0][cc] - bz * Rt[6 + cc]) : 0.0;
+        }
+        const double wv = wq[j];
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int jj = i; jj < 3; jj++) {
+            double hh = 0;
+#pragma unroll
+            for (int r = 0; r < 3; r++) hh += A[r][i] * wv * A[r][jj];
+            h[t++] += hh;
+          }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          double s2 = 0;
+#pragma unroll
+          for (int r = 0; r < 3; r++) s2 += A[r][i] * (-(wv * er[j][r]));
+          h[6 + i] += s2;
+        }
+      }
+    }
+    double* H = p.Hll + mo * 9;
+    H[0] = h[0]; H[1] = h[1]; H[2] = h[2];
+    H[3] = h[1]; H[4] = h[3]; H[5] = h[4];
+    H[6] = h[2]; H[7] = h[4]; H[8] = h[5];
+    double* bb = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)W.nFree * 6 + (size_t)l * 3;
+    bb[0] = h[6]; bb[1] = h[7]; bb[2] = h[8];
+    md = fmax(md, fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5]))));
+  }
+  atomic_max_pos_double(&p.st[w].maxDiagBits, md);
+}
+
 // buildSystem (pose side): one warp per free pose, lanes stride over the pose's edges, ordered shuffle reduction
-__device__ void phase_build_poses(const BaPtrs& p, const WinCtx& c, const BaWin& W, int robust) {
+__device__ void phase_build_poses(const BaPtrs& p, const WinCtx& c, const BaWin& W, int robust, int cur) {
   const int w = c.w;
   const int lane = threadIdx.x & 31;
   const int nWarps = c.gthreads >> 5, gw = c.gtid >> 5;
@@ -510,7 +604,7 @@ __device__ void phase_build_poses(const BaPtrs& p, const WinCtx& c, const BaWin&
         wgt[h] = p.eW[eo];
         c2v[h] = p.chi2[eo];
 #pragma unroll
-        for (int r = 0; r < 3; r++) er[h][r] = p.err[eo * 3 + r];  // written by phase_build_edges
+        for (int r = 0; r < 3; r++) er[h][r] = p.errB[cur][eo * 3 + r];  // phase_build_edges / phase_errors
       }
 #pragma unroll
       for (int h = 0; h < 2; h++) {
@@ -942,7 +1036,7 @@ __device__ __forceinline__ void schur_block_pairs_rc(const int4* prs, int qBeg, 
 // covisibility pairs (edge a of pose i1, edge c of pose i2, same landmark l) and accumulate (W_a Dinv_l) W_c^T; the
 // diagonal blocks also accumulate W_a (Dinv_l b_l) for the right-hand side.  S(i1,i2) = [Hpp + lambda I] - sum.
 // Blocks are dealt to the warps of the window in snake order over the list sorted by descending pair count.
-__device__ void phase_schur_blocks(const BaPtrs& p, const WinCtx& c, const BaWin& W, double lambda, double* stage) {
+__device__ void phase_schur_blocks(const BaPtrs& p, const WinCtx& c, const BaWin& W, double lambda, double* stage, int cur) {
   const int w = c.w;
   const int lane = threadIdx.x & 31;
   const int nWarps = c.gthreads >> 5, gw = c.gtid >> 5;
@@ -992,7 +1086,7 @@ __device__ void phase_schur_blocks(const BaPtrs& p, const WinCtx& c, const BaWin
         }
         __syncwarp();
         const double* ptsW = p.pts + (size_t)w * p.capMp * 3;
-        const double* wqW = p.eWq + (size_t)w * p.capE;
+        const double* wqW = p.eWqB[cur] + (size_t)w * p.capE;
         if (diag) schur_block_pairs_rc<true>(prs, qBeg, qEnd, ptsW, wqW, Db, buf, lane, W.fx, W.fy, W.bf, acc, tail);
         else schur_block_pairs_rc<false>(prs, qBeg, qEnd, ptsW, wqW, Db, buf, lane, W.fx, W.fy, W.bf, acc, tail);
       } else if (any) {
@@ -1273,7 +1367,7 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
 
 // landmark back-substitution (block_solver.hpp:461-481) + updates (types_sba.h:52-56, se3quat oplus) + computeScale
 __device__ void phase_backsub_update(const BaPtrs& p, const WinCtx& c, const BaWin& W, double lambda, int solveOk,
-                                     double* sm, double* stage) {
+                                     double* sm, double* stage, int cur) {
   const int w = c.w;
   const int* ms = p.mpStart + (size_t)w * (p.capMp + 1);
   const size_t xo = (size_t)w * (p.capKf * 6 + p.capMp * 3);
@@ -1298,7 +1392,7 @@ __device__ void phase_backsub_update(const BaPtrs& p, const WinCtx& c, const BaW
     }
     __syncthreads();
   }
-  const double* wqW = p.eWq + (size_t)w * p.capE;
+  const double* wqW = p.eWqB[cur] + (size_t)w * p.capE;
   const uint8_t* stW = p.eStereo + (size_t)w * p.capE;
   for (int l0 = c.gtid - lane; l0 < W.nMp; l0 += c.gthreads) {  // 32 consecutive landmarks per warp, one per lane
     const int l = l0 + lane;
@@ -1421,7 +1515,11 @@ __device__ void phase_backsub_update(const BaPtrs& p, const WinCtx& c, const BaW
 }
 
 // computeActiveErrors + activeRobustChi2 after the update (sparse_optimizer.cpp:61-113), one thread per edge
-__device__ void phase_errors(const BaPtrs& p, const WinCtx& c, const BaWin& W, int robust, double* sm) {
+// storeBuf >= 0 (recompute mode): also keep the error vectors and the edge weights rho' * invSigma2 in buffer storeBuf, so
+// that an accepted step needs no separate error pass before the next buildSystem (the values are the same);
+// zeroDead: excluded edges get weight 0 (first pass of a round).
+__device__ void phase_errors(const BaPtrs& p, const WinCtx& c, const BaWin& W, int robust, double* sm, int storeBuf = -1,
+                             bool zeroDead = false) {
   const int w = c.w;
   double chi = 0;
   // four edges per thread and iteration, loaded in two waves ahead of the arithmetic (see load_edge_idx)
@@ -1434,14 +1532,26 @@ __device__ void phase_errors(const BaPtrs& p, const WinCtx& c, const BaWin& W, i
     for (int h = 0; h < 4; h++) load_edge_ops(p, w, ix[h], op[h]);
 #pragma unroll
     for (int h = 0; h < 4; h++) {
-      if (!ix[h].live) continue;
+      const size_t eo = (size_t)w * p.capE + e + h * c.gthreads;
+      if (!ix[h].live) {
+        if (zeroDead && e + h * c.gthreads < W.nEdges) {  // in BOTH buffers: later passes of the round skip excluded edges
+          p.eWqB[0][eo] = 0.0;
+          p.eWqB[1][eo] = 0.0;
+        }
+        continue;
+      }
       double Xc[3], er[3];
       pose_map(op[h].P, op[h].X, Xc);
       const double c2 = edge_error(Xc, ix[h].stereo, ix[h].ob, (double)ix[h].wgt, W, er);
-      p.chi2[(size_t)w * p.capE + e + h * c.gthreads] = c2;
-      double rho0 = c2, rho1;
+      p.chi2[eo] = c2;
+      double rho0 = c2, rho1 = 1.0;
       if (robust) huber(c2, delta_of(ix[h].stereo), rho0, rho1);
       chi += rho0;
+      if (storeBuf >= 0) {
+        double* eb = p.errB[storeBuf] + eo * 3;
+        eb[0] = er[0]; eb[1] = er[1]; eb[2] = er[2];
+        p.eWqB[storeBuf][eo] = rho1 * (double)ix[h].wgt;
+      }
     }
   }
   const double s = block_sum(chi, sm);
@@ -1474,6 +1584,10 @@ __device__ void control_end(const BaPtrs& p, int w, int nCta) {
     st.lambda *= fmax(1. / 3., alpha);
     st.ni = 2;
     st.currentChi = tempChi;
+    if (p.schurRecompute && p.usePairs[w]) {  // phase_errors just stored this state's errors / weights in the other buffer
+      st.errBuf ^= 1;
+      st.errCurrent = 1;
+    }
   } else {
     st.lambda *= st.ni;
     st.ni *= 2;
@@ -1504,6 +1618,7 @@ __device__ void control_end(const BaPtrs& p, int w, int nCta) {
     st.it = 0;
     st.robust = 0;
     st.needBuild = 1;
+    st.errCurrent = 0;  // levels and kernels change: the stored weights are void
   } else {
     st.doOutlier = 2;  // final outlier test (:921-958); it also runs when round 2 is skipped
     st.active = 0;
@@ -1562,13 +1677,25 @@ __global__ void __launch_bounds__(BA_T) k_local_ba(BaPtrs p, int nCta, int wBase
   for (int guard = 0; guard < 4096; guard++) {
     if (!vst->active || *hung) break;
     const int needBuild = vst->needBuild, robust = vst->robust;
+    const bool rcMode = p.schurRecompute && p.usePairs[w];
+    const int cur = rcMode ? vst->errBuf : 0;
     if (needBuild) {
       for (int rr = ((dbgRepeat >> 8) == 2 ? (dbgRepeat & 255) : 1); rr > 0; rr--) {
-        phase_build_edges(p, c, W, robust, dsm, red);
-        win_barrier(bar, epoch, nCta, hung);
-        BA_PROF(0)
-        phase_reduce_landmarks(p, c, W);
-        phase_build_poses(p, c, W, robust);
+        if (rcMode) {
+          // errors + weights: after an accepted step they were stored by that step's phase_errors (same state, same values)
+          if (!vst->errCurrent) {
+            phase_errors(p, c, W, robust, red, cur, true);
+            win_barrier(bar, epoch, nCta, hung);
+          }
+          BA_PROF(0)
+          phase_reduce_landmarks_rc(p, c, W, cur, dsm);
+        } else {
+          phase_build_edges(p, c, W, robust, dsm, red);
+          win_barrier(bar, epoch, nCta, hung);
+          BA_PROF(0)
+          phase_reduce_landmarks(p, c, W);
+        }
+        phase_build_poses(p, c, W, robust, cur);
         win_barrier(bar, epoch, nCta, hung);
         BA_PROF(1)
       }
@@ -1583,18 +1710,18 @@ __global__ void __launch_bounds__(BA_T) k_local_ba(BaPtrs p, int nCta, int wBase
     // dbgRepeat (profiling only, B2S_BA_REPEAT=phase*256+count): re-run one idempotent phase so that a whole-kernel
     // ncu capture is dominated by it; 0 in production
     for (int rr = ((dbgRepeat >> 8) == 1 ? (dbgRepeat & 255) : 1); rr > 0; rr--) {
-      phase_schur_blocks(p, c, W, lambda, dsm);
+      phase_schur_blocks(p, c, W, lambda, dsm, cur);
       win_barrier(bar, epoch, nCta, hung);
     }
     BA_PROF(5)
     if (c.cta == 0) phase_chol(p, w, W, dsm);
     win_barrier(bar, epoch, nCta, hung);
     BA_PROF(6)
-    phase_backsub_update(p, c, W, lambda, vst->solveOk, red, dsm);
+    phase_backsub_update(p, c, W, lambda, vst->solveOk, red, dsm, cur);
     win_barrier(bar, epoch, nCta, hung);
     BA_PROF(7)
     for (int rr = ((dbgRepeat >> 8) == 3 ? (dbgRepeat & 255) : 1); rr > 0; rr--) {
-      phase_errors(p, c, W, robust, red);
+      phase_errors(p, c, W, robust, red, rcMode ? (cur ^ 1) : -1);
       win_barrier(bar, epoch, nCta, hung);
     }
     BA_PROF(8)
@@ -2176,6 +2303,10 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   A(&d.eStereo, B * max_edges); A(&d.eLevel, B * max_edges); A(&d.eOutlier, B * max_edges);
   A(&d.err, B * max_edges * 24); A(&d.chi2, B * max_edges * 8); A(&d.W, B * max_edges * 18 * 8);
   A(&d.eWq, B * max_edges * 8);
+  d.eWqB[0] = d.eWq;
+  A(&d.eWqB[1], B * max_edges * 8);
+  d.errB[0] = d.err;
+  A(&d.errB[1], B * max_edges * 24);
   d.schurRecompute = 1;
   if (const char* ev = getenv("B2S_BA_SCHUR_RC")) d.schurRecompute = atoi(ev) != 0;  // 0: gather the stored W blocks
   A(&d.mpStart, B * (max_mp + 1) * 4); A(&d.mpEdges, B * max_edges * 4);
