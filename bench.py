@@ -40,8 +40,8 @@ BA_BYTES_TRIAL = 16.0e6
 BA_FLOP_TRIAL = 64.0e6
 FP64_NOMINAL_TFLOPS = 37.0       # B200 data sheet (HGX B200: 296 TFLOP/s FP64 over 8 GPUs); not in MEASURED_PEAKS.json
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_local_ba launch (32 windows, 480 LM trials; ncu --set full,
-# profiles/r1_ncu_full_k_local_ba_v18.csv: 12.58 GB + 4.62 GB), per LM trial
-BA_TRAFFIC_TRIAL = (12.581749e9 + 4.623386e9) / 480.0
+# profiles/r1_ncu_full_k_local_ba_v19.csv: 1.57 GB + 1.48 GB; it was 12.58 + 4.62 GB before W_e was recomputed, v18), per LM trial
+BA_TRAFFIC_TRIAL = (1.569211e9 + 1.483268e9) / 480.0
 BA_EVERY = 5
 
 
@@ -331,15 +331,15 @@ def run_b200(args, rank, local_rank, world):
         roofline_ba = {"kernel": "k_local_ba (persistent LM loop: %d windows x 4 CTAs, one launch per LocalBA batch)" % ss.n_ba,
                        "bound": "hbm", "achieved": ba_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                        "frac": ba_gbs / peaks["hbm_gbs"], "traffic": BA_TRAFFIC_TRIAL * ba_trials,
-                       "traffic_source": "profiles/r1_ncu_full_k_local_ba_v18.csv (ncu --set full, 32-window launch)",
+                       "traffic_source": "profiles/r1_ncu_full_k_local_ba_v19.csv (ncu --set full, 32-window launch)",
                        "launch_ms": ba_kernel_ms, "launch_ms_source": "CUDA events on the solver stream, batch run alone",
                        "lm_trials": ba_trials, "algorithmic_bytes_per_launch": BA_BYTES_TRIAL * ba_trials,
                        "fp64": {"achieved_tflops": BA_FLOP_TRIAL * ba_trials / (ba_kernel_ms * 1e-3) / 1e12,
                                 "nominal_peak_tflops": FP64_NOMINAL_TFLOPS},
-                       "note": "latency-bound (long_scoreboard 4.9 + barrier 4.2 warps per issue at 8 warps/SM, FP64 pipe "
-                               "10 %); DRAM traffic is 2.2x the algorithmic bytes: 32 windows x ~10 MB of state exceed the "
-                               "126 MB L2 (hit rate 51 %), and the Schur phase re-gathers each 144-byte W_e block once per "
-                               "covisibility pair (see profiles/README.md)"}
+                       "note": "latency-bound (barrier 3.8 + long_scoreboard 2.4 warps per issue at 8 warps/SM, FP64 pipe "
+                               "18 %); since W_e is recomputed by its consumers and the error pass before buildSystem is "
+                               "reused, DRAM traffic (6.4 MB per LM trial) is below SURVEY's 16 MB estimate, which assumed a "
+                               "stored 4.3 MB W array per window (see profiles/README.md)"}
 
     fast_ms = stage[1] / max(1, calls.value)
     images_per_launch = 2 * F
