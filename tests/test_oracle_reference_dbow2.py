@@ -105,3 +105,47 @@ def test_trailing_newline_adds_a_phantom_word(tmp_path):
     assert same.mean() > 0.95                      # only features nearest to the phantom's descriptor differ ...
     assert np.all(rb["weight"][~same] == 0.0)      # ... and those are dropped
     assert np.array_equal(rb["word"][same], ra["word"][same])
+
+
+ORBVOC_TGZ = "/root/reference/Vocabulary/ORBvoc.txt.tar.gz"
+
+
+@pytest.mark.skipif(not os.path.exists(ORBVOC_TGZ), reason="the reference's vocabulary is only mounted in the build container")
+def test_real_orbvoc_transform_equals_reference_dbow2(oracle, tmp_path):
+    """The reference's one real fixture for this path: Vocabulary/ORBvoc.txt (k = 10, L = 6, 1,082,072 nodes, 971,814
+    words).  Loaded by the reference's own loadFromTextFile and by the flattened loader the oracle / product use; 2000
+    features (noisy copies of real words + random descriptors) must get the same word, weight and level-2 node
+    (levelsup = 4, as Frame::ComputeBoW asks) from both.  The file ends with a newline, so the reference side also carries
+    the phantom word described above; a feature that lands on it (none does here) would be excluded."""
+    import tarfile
+
+    import pandas as pd
+    with tarfile.open(ORBVOC_TGZ) as t:
+        t.extract("ORBvoc.txt", path=str(tmp_path))
+    path = str(tmp_path / "ORBvoc.txt")
+    with open(path) as f:
+        k, L, scoring, weighting = [int(x) for x in f.readline().split()]
+    assert (k, L, scoring, weighting) == (10, 6, 0, 0)
+    a = pd.read_csv(path, sep=r"\s+", header=None, skiprows=1, engine="c").values
+    voc = dict(k=k, L=L, parent=np.concatenate([[-1], a[:, 0].astype(np.int32)]), leaf_flag=np.concatenate([[0], a[:, 1].astype(np.uint8)]),
+               desc=np.concatenate([np.zeros((1, 32), np.uint8), a[:, 2:34].astype(np.uint8)]),
+               weight=np.concatenate([[0.0], a[:, 34].astype(np.float64)]))
+    assert len(voc["parent"]) == 1082073 and int(voc["leaf_flag"].sum()) == 971814
+    rng = np.random.RandomState(1)
+    leaves = np.nonzero(voc["leaf_flag"])[0]
+    feats = voc["desc"][rng.choice(leaves, 2000)].copy()
+    for i in range(2000):
+        for b in rng.choice(256, size=int(rng.randint(0, 40)), replace=False):
+            feats[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    feats[::10] = rng.randint(0, 256, size=(200, 32)).astype(np.uint8)
+    r = run_reference(path, feats, 4)
+    assert r["n_words"] == 971814 + 1  # + the phantom word of the trailing newline
+    nw, word, w, node = oracle.bow_transform(voc, feats, 4)
+    ok = r["word"] != r["n_words"] - 1
+    assert ok.mean() > 0.99
+    assert np.array_equal(r["word"][ok], word[ok]) and np.array_equal(r["weight"][ok], w[ok])
+    assert np.array_equal(r["node"][ok], node[ok])
+    bow, fv = assemble(word[ok], w[ok], node[ok])
+    if ok.all():
+        assert r["bow"] == bow
+    assert len(set(node[ok].tolist())) > 50  # the level-2 partition SearchByBoW joins on
