@@ -304,7 +304,7 @@ def run_b200(args, rank, local_rank, world):
             ba_kernel_ms, ba_trials = 0.0, 0
 
     # ---------------- end to end through the host-buffer C ABI (`e2e`)
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = args.steps if args.e2e_steps <= 0 else max(1, min(args.steps, args.e2e_steps))
     imgs_pinned = pinned.numpy()  # e2e inputs come from pinned host memory
     ss.step_host(imgs_pinned)  # warm
     torch.cuda.synchronize()
@@ -413,7 +413,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=160, help="stereo frames per step per GPU (160 -> 149 MB of images)")
     ap.add_argument("--ref-frames", type=int, default=24, help="stereo frames per step of the CPU reference arm")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end loop (0: the same K as --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="boundary", choices=["boundary", "all"],
                     help="NCCL all-gather of the shard-boundary left-image record only, or of every left-image record")
