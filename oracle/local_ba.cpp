@@ -891,6 +891,34 @@ extern "C" int orc_ba_debug_linear_system(const orc_ba_problem* p, int robust, d
   return ba.n_free;
 }
 
+// PoseOptimization: H (6x6), b, the damped solve x, per-edge error / chi2 (in edge order = features with a map point) at the
+// initial pose of the first iteration.  Returns the number of edges.
+extern "C" int orc_po_debug_linear_system(const orc_pose_problem* p, int robust, double lambda, double* H36, double* b6,
+                                          double* x6, double* err, double* chi2) {
+  PO po;
+  po.P = p;
+  for (int i = 0; i < p->n; i++)
+    if (p->has_mp[i]) po.edges.push_back(i);
+  po.pose = pose_from_Tcw(p->Tcw);
+  po.level.assign(po.edges.size(), 0);
+  po.err.assign(po.edges.size() * 3, 0.0);
+  po.chi2.assign(po.edges.size(), 0.0);
+  po.delta_mono = (double)(float)std::sqrt(5.991);
+  po.delta_stereo = (double)(float)std::sqrt(7.815);
+  po.robust = robust != 0;
+  po.compute_active_errors();
+  po.build_system();
+  std::copy(po.H, po.H + 36, H36);
+  std::copy(po.b, po.b + 6, b6);
+  std::copy(po.err.begin(), po.err.end(), err);
+  std::copy(po.chi2.begin(), po.chi2.end(), chi2);
+  if (x6) {
+    if (!po.solve(lambda)) return -1;
+    std::copy(po.x, po.x + 6, x6);
+  }
+  return (int)po.edges.size();
+}
+
 extern "C" void orc_se3_oplus(const float* Tcw16, const double* upd6, double* R9, double* t3) {
   Pose T = pose_from_Tcw(Tcw16);
   pose_oplus(T, upd6);

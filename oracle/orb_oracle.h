@@ -275,6 +275,9 @@ int orc_local_ba(const orc_ba_problem* p, const volatile uint8_t* stop, orc_ba_r
 int orc_ba_debug_linear_system(const orc_ba_problem* p, int robust, double lambda, double* Hpp, double* Hll, double* Hpl,
                                double* b, double* err, double* chi2, int32_t* pose_index, double* x);
 void orc_se3_oplus(const float* Tcw16, const double* upd6, double* R9, double* t3);
+/* PoseOptimization: the 6x6 system of the first LM iteration at the initial pose, its damped solve, per-edge error / chi2 */
+int orc_po_debug_linear_system(const orc_pose_problem* p, int robust, double lambda, double* H36, double* b6, double* x6,
+                               double* err, double* chi2);
 
 /* ---------------- helpers (orb_misc.cpp) ---------------- */
 void orc_sincosf_batch(const float* in, long n, float* s, float* c, int threads); /* glibc sinf/cosf */

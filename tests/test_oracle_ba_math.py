@@ -223,3 +223,68 @@ def test_local_ba_recovers_the_truth_from_exact_observations(oracle):
     assert np.median(perr) < 0.4 * np.median(perr0) and perr.max() < 0.2
     tr = r["trace"][:r["n_trials"]]
     assert tr.all()  # consistent data: every LM step reduces the error
+
+
+@pytest.mark.parametrize("seed,robust", [(23, True), (31, False)])
+def test_pose_optimization_system_matches_numeric_differentiation(oracle, seed, robust):
+    """The 6x6 system PoseOptimization builds (unary edges, types_six_dof_expmap.cpp:266-364) against central differences of
+    the plain projection under T <- expm(hat(delta)) T, with Huber weights; and its damped solve against numpy."""
+    from oracle_binding import pose_problem_arrays
+    from synth import synth_pose_problem
+    d = synth_pose_problem(n=600, seed=seed, mono_frac=0.3, outlier_frac=0.15)
+    arrs = pose_problem_arrays(d)
+    n = len(arrs["has_mp"])
+
+    class PP(ctypes.Structure):
+        _fields_ = [("Tcw", vp), ("n", ctypes.c_int32), ("has_mp", vp), ("Xw", vp), ("kpx", vp), ("kpy", vp), ("uright", vp),
+                    ("inv_sigma2", vp), ("fx", ctypes.c_float), ("fy", ctypes.c_float), ("cx", ctypes.c_float),
+                    ("cy", ctypes.c_float), ("bf", ctypes.c_float)]
+    p = PP(arrs["Tcw"].ctypes.data, n, arrs["has_mp"].ctypes.data, arrs["Xw"].ctypes.data, arrs["kpx"].ctypes.data,
+           arrs["kpy"].ctypes.data, arrs["uright"].ctypes.data, arrs["inv_sigma2"].ctypes.data, d["fx"], d["fy"], d["cx"], d["cy"],
+           d["bf"])
+    ne = int(arrs["has_mp"].sum())
+    H, b, x = np.zeros((6, 6)), np.zeros(6), np.zeros(6)
+    err, chi2 = np.zeros((ne, 3)), np.zeros(ne)
+    L = oracle.L
+    L.orc_po_debug_linear_system.argtypes = [vp, ctypes.c_int, ctypes.c_double, vp, vp, vp, vp, vp]
+    lam = 2.5
+    got = L.orc_po_debug_linear_system(ctypes.byref(p), int(robust), lam, H.ctypes.data, b.ctypes.data, x.ctypes.data,
+                                       err.ctypes.data, chi2.ctypes.data)
+    assert got == ne
+    fx, fy, cx, cy, bf = [float(np.float32(d[k])) for k in ("fx", "fy", "cx", "cy", "bf")]
+    T = arrs["Tcw"].astype(np.float64).reshape(4, 4)
+    U, _, Vt = np.linalg.svd(T[:3, :3])  # the oracle goes through a unit quaternion (Converter::toSE3Quat)
+    T[:3, :3] = U @ Vt
+    Hn, bn = np.zeros((6, 6)), np.zeros(6)
+    h = 1e-6
+    dm, ds = float(np.float32(np.sqrt(5.991))), float(np.float32(np.sqrt(7.815)))
+    e = 0
+    for i in range(n):
+        if not arrs["has_mp"][i]:
+            continue
+        stereo = not (arrs["uright"][i] < 0)
+        D = 3 if stereo else 2
+        obs = np.array([arrs["kpx"][i], arrs["kpy"][i], arrs["uright"][i]], np.float64)[:D]
+        X = arrs["Xw"].reshape(-1, 3)[i].astype(np.float64)
+        w = float(arrs["inv_sigma2"][i])
+        f = lambda Tm: obs - _project(Tm, X, fx, fy, cx, cy, bf, stereo)
+        er = f(T)
+        assert np.allclose(er, err[e][:D], atol=5e-4)
+        c2 = w * er @ er
+        Bm = np.zeros((D, 6))
+        for c in range(6):
+            dd = np.zeros(6)
+            dd[c] = h
+            Bm[:, c] = (f(expm(_hat(dd)) @ T) - f(expm(_hat(-dd)) @ T)) / (2 * h)
+        rho1 = 1.0
+        if robust:
+            delta = ds if stereo else dm
+            if c2 > delta * delta:
+                rho1 = delta / np.sqrt(c2)
+        Hn += Bm.T @ Bm * (w * rho1)
+        bn += -Bm.T @ er * (w * rho1)
+        e += 1
+    assert np.abs(H - Hn).max() <= 1e-4 * np.abs(Hn).max()
+    assert np.abs(b - bn).max() <= 1e-4 * np.abs(bn).max()
+    xs = np.linalg.solve(H + lam * np.eye(6), b)
+    assert np.abs(x - xs).max() <= 1e-9 * np.abs(xs).max()
