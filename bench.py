@@ -117,45 +117,63 @@ class ClockSampler:
         return out
 
 
-def run_reference(args, rank, world):
-    """The reference algorithm's CPU path (oracle port: oracle/ restates it step for step) on all host cores."""
-    if rank != 0:
-        return
+def cpu_stream_step_fn():
+    """The CPU arm's step function and what it is made of.  Preferred: oracle/_ref/libref_stream.so — the reference's OWN
+    src/ORBextractor.cc and src/ORBmatcher.cc compiled in place (oracle/Makefile `ref`, built where /root/reference is
+    mounted; the file travels to the GPU box) with the oracle port of LocalBA (src/Optimizer.cc needs g2o + Eigen, absent
+    here).  Otherwise the oracle port of all three stages (oracle/orb_misc.cpp orc_stream_step)."""
     import oracle_binding
-    o = oracle_binding.load()
-    threads = os.cpu_count() or 1
-    S = args.ref_frames
-    imgs = make_images(min(S, 8), S)
-    ba = ba_window()
-    L = o.L
-    L.orc_stream_step.restype = ctypes.c_double
     vp = ctypes.c_void_p
-    L.orc_stream_step.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
-                                  ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]
+    argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int,
+                ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]
+    ref_lib = os.path.join(ROOT, "oracle", "_ref", "libref_stream.so")
+    if os.path.exists(ref_lib) and not os.environ.get("B2S_BENCH_CPU_PORT"):
+        R = ctypes.CDLL(ref_lib)
+        fn = R.ref_stream_step
+        kind = "reference"
+        what = ("reference's own ORBextractor.cc + ORBmatcher.cc compiled in place (oracle/_ref) + oracle port of LocalBA "
+                "(Optimizer.cc needs Eigen)")
+    else:
+        fn = oracle_binding.load().L.orc_stream_step
+        kind = "port"
+        what = "oracle port (extract, match, LocalBA)"
+    fn.restype = ctypes.c_double
+    fn.argtypes = argtypes
+    ba = ba_window()
     keep = dict(Tcw=np.ascontiguousarray(ba["Tcw"], np.float32), fixed=np.ascontiguousarray(ba["fixed"], np.uint8),
                 points=np.ascontiguousarray(ba["points"], np.float32), edges=np.ascontiguousarray(ba["edges"]))
     prob = oracle_binding.BaProblem(ba["n_kf"], ba["n_local"], keep["Tcw"].ctypes.data, keep["fixed"].ctypes.data,
                                     len(keep["points"]), keep["points"].ctypes.data, len(keep["edges"]),
                                     keep["edges"].ctypes.data, ba["fx"], ba["fy"], ba["cx"], ba["cy"], ba["bf"], 5, 10)
 
-    def step():
-        return L.orc_stream_step(NFEAT, 1.2, 8, 20, 7, imgs.ctypes.data_as(vp), S, W_IMG, H_IMG, ctypes.byref(prob),
-                                 BA_EVERY, threads, None)
+    def step(imgs, S, threads):
+        assert keep is not None  # (the problem arrays must outlive the call)
+        return fn(NFEAT, 1.2, 8, 20, 7, imgs.ctypes.data_as(vp), S, W_IMG, H_IMG, ctypes.byref(prob), BA_EVERY, threads, None)
+    return step, kind, what
 
+
+def run_reference(args, rank, world):
+    """The reference algorithm's CPU path on all host cores (see cpu_stream_step_fn)."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    S = args.ref_frames
+    imgs = make_images(min(S, 8), S)
+    step, kind, what = cpu_stream_step_fn()
     for _ in range(args.warmup):
-        step()
+        step(imgs, S, threads)
     t = 0.0
     for _ in range(args.steps):
-        t += step()
+        t += step(imgs, S, threads)
     fps = S * args.steps / t
     line = {
         "impl": "reference", "metric": "stereo_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (extract, match), f64 (LocalBA)", "data": "synthetic",
         "config": workload_config(S, 1),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "%d stereo frames per step (bounded sample of the workload), oracle port on %d host threads"
-                                   % (S, threads)},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                         "sample": "%d stereo frames per step (bounded sample of the workload) on %d host threads: %s"
+                                   % (S, threads, what)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -381,27 +399,15 @@ def run_b200(args, rank, local_rank, world):
 
 
 def cpu_baseline():
-    """Oracle port timed on this box's host cores, bounded sample (about 10-30 core-seconds)."""
-    import oracle_binding
-    o = oracle_binding.load()
+    """The CPU arm timed on this box's host cores, bounded sample (about 10-30 core-seconds); see cpu_stream_step_fn."""
     threads = os.cpu_count() or 1
     S = 48
     imgs = make_images(8, S)
-    ba = ba_window()
-    L = o.L
-    vp = ctypes.c_void_p
-    L.orc_stream_step.restype = ctypes.c_double
-    L.orc_stream_step.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
-                                  ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]
-    keep = dict(Tcw=np.ascontiguousarray(ba["Tcw"], np.float32), fixed=np.ascontiguousarray(ba["fixed"], np.uint8),
-                points=np.ascontiguousarray(ba["points"], np.float32), edges=np.ascontiguousarray(ba["edges"]))
-    prob = oracle_binding.BaProblem(ba["n_kf"], ba["n_local"], keep["Tcw"].ctypes.data, keep["fixed"].ctypes.data,
-                                    len(keep["points"]), keep["points"].ctypes.data, len(keep["edges"]),
-                                    keep["edges"].ctypes.data, ba["fx"], ba["fy"], ba["cx"], ba["cy"], ba["bf"], 5, 10)
-    t = L.orc_stream_step(NFEAT, 1.2, 8, 20, 7, imgs.ctypes.data_as(vp), S, W_IMG, H_IMG, ctypes.byref(prob), BA_EVERY,
-                          threads, None)
-    return {"value": S / t, "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": "%d stereo frames (96 images, 48 matches, 10 LocalBA windows) on %d host threads, %.1f s" % (S, threads, t)}
+    step, kind, what = cpu_stream_step_fn()
+    t = step(imgs, S, threads)
+    return {"value": S / t, "unit": "frames/s", "cores": threads, "kind": kind,
+            "sample": "%d stereo frames (96 images, 48 matches, 10 LocalBA windows) on %d host threads, %.1f s: %s"
+                      % (S, threads, t, what)}
 
 
 def main():
