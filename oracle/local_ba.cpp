@@ -474,6 +474,13 @@ struct BA {
 
   // SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve
   void optimize(int iterations) {
+    // initializeOptimization(level) activates only the edges of that level and the vertices they touch
+    // (sparse_optimizer.cpp:292-358); with no active edge the index mapping is empty and optimize() returns at once
+    // ("0 vertices to optimize", sparse_optimizer.cpp:356-359).  Every edge has a free landmark, so "no active free vertex"
+    // is "no level-0 edge".  Pinned by tests/test_oracle_reference_optimizer.py::rejections_2 (round 1 flags everything).
+    bool any_active = false;
+    for (uint8_t l : level) any_active |= (l == 0);
+    if (!any_active) return;
     rebuild_structure();
     const int nx = n_free * 6 + P->n_mp * 3;
     bool ok = true;

@@ -46,6 +46,13 @@ struct Point_ {
 typedef Point_<int> Point2i;
 typedef Point2i Point;
 typedef Point_<float> Point2f;
+template <typename T>
+struct Point3_ {
+  T x, y, z;
+  Point3_() : x(0), y(0), z(0) {}
+  Point3_(T _x, T _y, T _z) : x(_x), y(_y), z(_z) {}
+};
+typedef Point3_<float> Point3f;
 
 struct Size {
   int width, height;
@@ -131,6 +138,12 @@ class Mat {
     return m;
   }
   Mat reshape(int) const { return *this; }  // only reached on the distortion path, which the pinning tests do not take
+  static Mat eye(int r, int c, int type) {  // CV_32F only (include/Converter.h users)
+    Mat m(r, c, type);
+    for (int i = 0; i < r; i++)
+      for (int j = 0; j < c; j++) m.at<float>(i, j) = i == j ? 1.0f : 0.0f;
+    return m;
+  }
   static Mat ones(int r, int c, int type) {
     Mat m(r, c, type);
     for (int i = 0; i < r; i++)

@@ -71,7 +71,7 @@ def build_oracle_ref():
     ref = os.environ.get("B2S_REFERENCE_ROOT", "/root/reference")
     if not os.path.isdir(os.path.join(ref, "src")):
         return None
-    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref", "REF=" + ref])
+    subprocess.check_call(["make", "-s", "-j8", "-C", ORACLE_DIR, "ref", "REF=" + ref])
     return os.path.join(ORACLE_DIR, "_ref")
 
 

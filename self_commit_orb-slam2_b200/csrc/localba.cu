@@ -31,6 +31,7 @@ constexpr int CHOL_BS = 32;
 struct BaState {
   int active, round, it, qmax, needBuild, restore, doOutlier, solveOk, stop, nTrials, nBad, robust, finishedRound0;
   int errBuf, errCurrent;  // recompute mode: which err / eWq buffer describes the linearisation state; it is up to date
+  int nLive;               // edges left at level 0 by the outlier pass between the rounds (0: round 2 has nothing to optimise)
   int its[2];
   double lambda, ni, currentChi, iniChi, tempChi, rho, chi2Final;
   unsigned long long maxDiagBits;
@@ -1614,6 +1615,7 @@ __device__ void control_end(const BaPtrs& p, int w, int nCta) {
   }
   if (st.round == 0 && !stop && st.its[1] > 0) {
     st.doOutlier = 1;  // setLevel(1) on outliers, drop the robust kernels, second round
+    st.nLive = 0;
     st.round = 1;
     st.it = 0;
     st.robust = 0;
@@ -1635,6 +1637,7 @@ __device__ void phase_restore(const BaPtrs& p, const WinCtx& c, const BaWin& W) 
 // chi2 / depth outlier tests (src/Optimizer.cc:880-958)
 __device__ void phase_outliers(const BaPtrs& p, const WinCtx& c, const BaWin& W, int mode) {
   const int w = c.w;
+  int live = 0;
   for (int e = c.gtid; e < W.nEdges; e += c.gthreads) {
     const size_t eo = (size_t)w * p.capE + e;
     double Xc[3];
@@ -1643,8 +1646,14 @@ __device__ void phase_outliers(const BaPtrs& p, const WinCtx& c, const BaWin& W,
     const bool out = p.chi2[eo] > th || !(Xc[2] > 0.0);
     if (mode == 1) {
       if (out) p.eLevel[eo] = 1;
+      live += out ? 0 : 1;
+      p.eOutlier[eo] = out ? 1 : 0;  // final answer already if round 2 turns out to be empty (see k_local_ba)
     } else
       p.eOutlier[eo] = out ? 1 : 0;
+  }
+  if (mode == 1) {  // level-0 edges that remain: warp sums, one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) live += __shfl_down_sync(0xffffffffu, live, o);
+    if ((threadIdx.x & 31) == 0 && live) atomicAdd(&p.st[w].nLive, live);
   }
 }
 
@@ -1735,6 +1744,13 @@ __global__ void __launch_bounds__(BA_T) k_local_ba(BaPtrs p, int nCta, int wBase
       phase_outliers(p, c, W, doOutlier);
     }
     win_barrier(bar, epoch, nCta, hung);
+    if (doOutlier == 1) {
+      // initializeOptimization(0) with every edge at level 1 leaves no active vertex: g2o's optimize() returns at once
+      // (sparse_optimizer.cpp:356-359) and src/Optimizer.cc:921-958 flags the edges with the chi2 they already have,
+      // which is what the level pass just stored in eOutlier.  Pinned by test_oracle_reference_optimizer (rejections_2).
+      if (c.cta == 0 && threadIdx.x == 0 && vst->nLive == 0) (p.st + w)->active = 0;
+      win_barrier(bar, epoch, nCta, hung);
+    }
     BA_PROF(10)
   }
 #undef BA_PROF

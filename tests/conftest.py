@@ -75,6 +75,13 @@ class CudaChecker:
             return ex.extract_batch([img])[0]
         return run
 
+    def local_ba(self, d, stop=None):
+        opt = self.pkg.Optimizer(max_kf=max(16, d["n_kf"]), max_mp=max(512, len(d["points"])), max_edges=max(4096, len(d["edges"])))
+        return opt.LocalBundleAdjustment(d, stop=stop)
+
+    def pose_optimization(self, d):
+        return self.pkg.Optimizer(max_kf=4, max_mp=16, max_edges=64).PoseOptimization(d)
+
     def bow_transform(self, voc, features, levelsup=4):
         v = self.pkg.ORBVocabulary(voc["k"], voc["L"], voc["parent"], voc["leaf_flag"], voc["desc"], voc["weight"])
         word, w, node = v.transform_features(features, levelsup)

@@ -34,8 +34,57 @@ class BaResult(ctypes.Structure):
                 ("n_trials", ctypes.c_int)]
 
 
+class PoseProblem(ctypes.Structure):
+    _fields_ = [("Tcw", vp), ("n", ctypes.c_int32), ("has_mp", vp), ("Xw", vp), ("kpx", vp), ("kpy", vp),
+                ("uright", vp), ("inv_sigma2", vp), ("fx", ctypes.c_float), ("fy", ctypes.c_float),
+                ("cx", ctypes.c_float), ("cy", ctypes.c_float), ("bf", ctypes.c_float)]
+
+
+class PoseResult(ctypes.Structure):
+    _fields_ = [("Tcw_out", vp), ("outlier", vp), ("trace", vp), ("n_trials", ctypes.c_int32)]
+
+
 def P(a):
     return None if a is None else a.ctypes.data_as(vp)
+
+
+def call_pose_optimization(fn, d):
+    """fn(const orc_pose_problem*, orc_pose_result*) -> inliers: the oracle's orc_pose_optimization or the reference's own
+    Optimizer::PoseOptimization behind oracle/ref_optimizer_glue.cpp (same flattened problem)."""
+    arrs = pose_problem_arrays(d)
+    n = len(arrs["has_mp"])
+    p = PoseProblem(arrs["Tcw"].ctypes.data, n, arrs["has_mp"].ctypes.data, arrs["Xw"].ctypes.data, arrs["kpx"].ctypes.data,
+                    arrs["kpy"].ctypes.data, arrs["uright"].ctypes.data, arrs["inv_sigma2"].ctypes.data, d["fx"], d["fy"],
+                    d["cx"], d["cy"], d["bf"])
+    Tout = np.zeros(16, np.float32)
+    outl = np.zeros(n, np.uint8)
+    trace = np.full(256, -1, np.int32)
+    r = PoseResult(Tout.ctypes.data, outl.ctypes.data, trace.ctypes.data, 0)
+    fn.argtypes = [vp, vp]
+    ninl = fn(ctypes.byref(p), ctypes.byref(r))
+    return dict(n_inliers=ninl, Tcw=Tout, outlier=outl, trace=trace, n_trials=r.n_trials)
+
+
+def call_local_ba(fn, d, stop=None, its1=5, its2=10):
+    """fn(const orc_ba_problem*, const uint8_t* stop, orc_ba_result*): orc_local_ba or ref_local_ba."""
+    Tcw = np.ascontiguousarray(d["Tcw"], np.float32)
+    fixed = np.ascontiguousarray(d["fixed"], np.uint8)
+    pts = np.ascontiguousarray(d["points"], np.float32)
+    edges = np.ascontiguousarray(d["edges"])
+    p = BaProblem(d["n_kf"], d["n_local"], Tcw.ctypes.data, fixed.ctypes.data, len(pts), pts.ctypes.data, len(edges),
+                  edges.ctypes.data, d["fx"], d["fy"], d["cx"], d["cy"], d["bf"], its1, its2)
+    out = dict(Tcw=np.zeros((d["n_local"], 16), np.float32), points=np.zeros((len(pts), 3), np.float32),
+               outlier=np.zeros(len(edges), np.uint8), trace=np.full(256, -1, np.int32))
+    r = BaResult(out["Tcw"].ctypes.data, out["points"].ctypes.data, out["outlier"].ctypes.data,
+                 out["trace"].ctypes.data, 0.0, 0)
+    fn.argtypes = [vp, vp, vp]
+    rc = fn(ctypes.byref(p), P(stop), ctypes.byref(r))
+    if rc == 1:
+        return None
+    assert rc == 0, "local_ba: window not expressible (rc=%d)" % rc
+    out["chi2"] = r.chi2_final
+    out["n_trials"] = r.n_trials
+    return out
 
 
 class Oracle:
@@ -254,44 +303,11 @@ class Oracle:
 
     # ---- PoseOptimization ----
     def pose_optimization(self, d):
-        class PP(ctypes.Structure):
-            _fields_ = [("Tcw", vp), ("n", ctypes.c_int32), ("has_mp", vp), ("Xw", vp), ("kpx", vp), ("kpy", vp),
-                        ("uright", vp), ("inv_sigma2", vp), ("fx", ctypes.c_float), ("fy", ctypes.c_float),
-                        ("cx", ctypes.c_float), ("cy", ctypes.c_float), ("bf", ctypes.c_float)]
-
-        class PR(ctypes.Structure):
-            _fields_ = [("Tcw_out", vp), ("outlier", vp), ("trace", vp), ("n_trials", ctypes.c_int32)]
-        arrs = pose_problem_arrays(d)
-        n = len(arrs["has_mp"])
-        p = PP(arrs["Tcw"].ctypes.data, n, arrs["has_mp"].ctypes.data, arrs["Xw"].ctypes.data, arrs["kpx"].ctypes.data,
-               arrs["kpy"].ctypes.data, arrs["uright"].ctypes.data, arrs["inv_sigma2"].ctypes.data, d["fx"], d["fy"],
-               d["cx"], d["cy"], d["bf"])
-        Tout = np.zeros(16, np.float32)
-        outl = np.zeros(n, np.uint8)
-        trace = np.full(256, -1, np.int32)
-        r = PR(Tout.ctypes.data, outl.ctypes.data, trace.ctypes.data, 0)
-        self.L.orc_pose_optimization.argtypes = [vp, vp]
-        ninl = self.L.orc_pose_optimization(ctypes.byref(p), ctypes.byref(r))
-        return dict(n_inliers=ninl, Tcw=Tout, outlier=outl, trace=trace, n_trials=r.n_trials)
+        return call_pose_optimization(self.L.orc_pose_optimization, d)
 
     # ---- LocalBA ----
     def local_ba(self, d, stop=None, its1=5, its2=10):
-        Tcw = np.ascontiguousarray(d["Tcw"], np.float32)
-        fixed = np.ascontiguousarray(d["fixed"], np.uint8)
-        pts = np.ascontiguousarray(d["points"], np.float32)
-        edges = np.ascontiguousarray(d["edges"])
-        p = BaProblem(d["n_kf"], d["n_local"], Tcw.ctypes.data, fixed.ctypes.data, len(pts), pts.ctypes.data, len(edges),
-                      edges.ctypes.data, d["fx"], d["fy"], d["cx"], d["cy"], d["bf"], its1, its2)
-        out = dict(Tcw=np.zeros((d["n_local"], 16), np.float32), points=np.zeros((len(pts), 3), np.float32),
-                   outlier=np.zeros(len(edges), np.uint8), trace=np.full(256, -1, np.int32))
-        r = BaResult(out["Tcw"].ctypes.data, out["points"].ctypes.data, out["outlier"].ctypes.data,
-                     out["trace"].ctypes.data, 0.0, 0)
-        rc = self.L.orc_local_ba(ctypes.byref(p), P(stop), ctypes.byref(r))
-        if rc == 1:
-            return None
-        out["chi2"] = r.chi2_final
-        out["n_trials"] = r.n_trials
-        return out
+        return call_local_ba(self.L.orc_local_ba, d, stop, its1, its2)
 
     def sincosf(self, x, threads=8):
         x = np.ascontiguousarray(x, np.float32)
