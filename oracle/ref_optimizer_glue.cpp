@@ -36,6 +36,15 @@ static cv::Mat mat44(const float* T) {
   return m;
 }
 
+// The same glue also drives the product's drop-in bodies (self_commit_orb-slam2_b200/host/adapters/Optimizer_b200.cc): built
+// with -DB2S_ADAPTER_BUILD into _ref/libadapter_optimizer.so, the entry points are adp_local_ba / adp_pose_optimization and
+// Optimizer:: resolves to the adapter (which calls libb200slam.so) instead of the reference's Optimizer.cc + g2o.
+#ifdef B2S_ADAPTER_BUILD
+#define ref_local_ba adp_local_ba
+#define ref_pose_optimization adp_pose_optimization
+#define ref_lm_iterations adp_lm_iterations
+#endif
+
 // LM iterations of this thread -> accept(1) / reject(0) per trial, -1 terminated
 static int flatten_trace(int32_t* trace, int cap) {
   std::vector<g2o::B2sLmIteration>& it = g2o::b2s_lm_trace();

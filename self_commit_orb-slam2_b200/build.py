@@ -16,7 +16,7 @@ ORACLE_LIB = os.path.join(ORACLE_DIR, "liborb_oracle.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler",
               "-fPIC,-O3"]
 # extractor/matcher: bit-exact float arithmetic, never contract a*b+c; LocalBA is FP64 with a 1e-5 bar -> FMA allowed
-NO_FMAD = {"extractor.cu", "matcher.cu", "common.cu"}
+NO_FMAD = {"extractor.cu", "extractor_tile.cu", "matcher.cu", "common.cu"}
 
 
 def _newer(target, sources):
@@ -30,18 +30,27 @@ def cuda_sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def _deps_of(src):
+    """Files whose change makes `src`'s object stale (the include graph of csrc/ is small and fixed)."""
+    base = os.path.basename(src)
+    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "b200slam.h")]
+    if base.startswith("extractor"):
+        deps.append(os.path.join(CSRC, "extractor.cuh"))
+    if base == "extractor.cu":
+        deps.append(os.path.join(ROOT, "data", "orb_pattern_31.inc"))
+    return deps
+
+
 def build_cuda(force=False, verbose=False):
     srcs = cuda_sources()
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [
-        os.path.join(ROOT, "include", "b200slam.h"), os.path.join(ROOT, "data", "orb_pattern_31.inc")]
-    if not force and _newer(LIB, deps):
-        return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
     for s in srcs:
         o = s[:-3] + ".o"
         objs.append(o)
+        if not force and not verbose and _newer(o, _deps_of(s)):
+            continue  # object up to date (localba.cu alone takes minutes to compile)
         cmd = [nvcc] + NVCC_FLAGS + (["--fmad=false"] if os.path.basename(s) in NO_FMAD else []) + (
             ["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -51,6 +60,8 @@ def build_cuda(force=False, verbose=False):
             sys.stderr.write(out.decode())
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    if not procs and not force and _newer(LIB, objs):
+        return LIB
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
     return LIB

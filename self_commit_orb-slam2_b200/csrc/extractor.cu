@@ -1143,6 +1143,10 @@ static int build_geometry(b2s_extractor* h, int W, int H) {
     }
     B2S_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(qsm, (size_t)49152)));
   }
+  {
+    const int rc = tile_build(h);
+    if (rc != B2S_OK) return rc;
+  }
   h->curW = W;
   h->curH = H;
   return B2S_OK;
@@ -1218,15 +1222,26 @@ static int run_pipeline(b2s_extractor* h, const DeviceBuffers& d, int batch, b2s
     if (h->evPending) b2s_extractor_timing_collect(h);
     cudaEventRecord(h->ev[0], st);
   }
-  for (int l = 1; l < g.nlevels; l++) {
-    dim3 grid(div_up(g.lv[l].w, 128), div_up(g.lv[l].h, 4), batch);
-    k_resize<<<grid, dim3(32, 4), 0, st>>>(g, l, d.pyr, d.rxOfs, d.rxAlpha, d.ryOfs, d.ryBeta);
-    h->launches++;
+  const int path = h->path;
+  if (path < 3) {
+    for (int l = 1; l < g.nlevels; l++) {
+      dim3 grid(div_up(g.lv[l].w, 128), div_up(g.lv[l].h, 4), batch);
+      k_resize<<<grid, dim3(32, 4), 0, st>>>(g, l, d.pyr, d.rxOfs, d.rxAlpha, d.ryOfs, d.ryBeta);
+      h->launches++;
+    }
   }
   if (tm) cudaEventRecord(h->ev[1], st);
-  k_fast_cells<<<dim3(g.totalCells, batch), 128, 0, st>>>(g, d.pyr, d.cellInfo, d.candXY, d.candKey, d.candResp, d.candCount,
-                                                          d.status);
-  h->launches++;
+  if (path == 0) {
+    k_fast_cells<<<dim3(g.totalCells, batch), 128, 0, st>>>(g, d.pyr, d.cellInfo, d.candXY, d.candKey, d.candResp, d.candCount,
+                                                            d.status);
+    h->launches++;
+  } else {
+    // fused front end: per level one tile kernel (TMA-staged tile -> FAST strength map [+ blur] [+ level l+1]), then the
+    // per-cell NMS / threshold rules.  `d` may be a slice of the handle's buffers: pass its image offset.
+    const int bBase = (int)((size_t)(d.pyr - h->d.pyr) / g.pyrBytes);
+    const int rc = tile_run(h, bBase, batch, path, st, nullptr);
+    if (rc != B2S_OK) return rc;
+  }
   if (tm) cudaEventRecord(h->ev[2], st);
   int capMax = 0;
   for (int l = 0; l < g.nlevels; l++) capMax = std::max(capMax, g.lv[l].nodeCap);
@@ -1235,8 +1250,10 @@ static int run_pipeline(b2s_extractor* h, const DeviceBuffers& d, int batch, b2s
                                                        d.candCount, d.selXYR, d.selCount, d.status);
   h->launches++;
   if (tm) cudaEventRecord(h->ev[3], st);
-  k_blur<<<dim3(g.totalBlurTiles, batch), 128, 0, st>>>(g, d.pyr, d.blur);
-  h->launches++;
+  if (path < 2) {
+    k_blur<<<dim3(g.totalBlurTiles, batch), 128, 0, st>>>(g, d.pyr, d.blur);
+    h->launches++;
+  }
   if (tm) cudaEventRecord(h->ev[4], st);
   k_orient_describe<<<dim3(div_up(g.totalSelCap, 8), batch), 256, 0, st>>>(g, d.pyr, d.blur, d.selXYR, d.selCount, dKps,
                                                                            dDesc, dCounts, cap, d.status);
@@ -1536,6 +1553,7 @@ extern "C" int b2s_extractor_create(int nfeatures, float scaleFactor, int nlevel
   h->maxH = max_height;
   h->maxBatch = max_batch;
   h->device = device;
+  if (const char* pe = getenv("B2S_EXTRACT_PATH")) h->path = std::min(3, std::max(0, atoi(pe)));
   // scale tables and per-level quotas — src/ORBextractor.cc:500-554
   h->scale.resize(nlevels);
   h->sigma2.resize(nlevels);
@@ -1599,6 +1617,10 @@ extern "C" int b2s_extractor_create(int nfeatures, float scaleFactor, int nlevel
   };
   A((void**)&d.pyr, B * pyrBytes);
   A((void**)&d.blur, B * pyrBytes);
+  A((void**)&d.score, B * pyrBytes);
+  h->tileTabAlloc = (size_t)nlevels * (size_t)(div_up(max_width, 32) + div_up(max_height, 32) + 8);
+  A((void**)&d.tileDx, h->tileTabAlloc * 2);
+  A((void**)&d.tileDy, h->tileTabAlloc * 2);
   if (max_batch > 1) A((void**)&d.raw, B * (size_t)max_width * max_height + 64);  // dense upload staging (batch path)
   A((void**)&d.candXY, B * candCap * 4);
   A((void**)&d.candKey, B * candCap * 4);
@@ -1649,7 +1671,7 @@ extern "C" void b2s_extractor_destroy(b2s_extractor* h) {
   DeviceBuffers& d = h->d;
   void* ptrs[] = {d.pyr, d.blur, d.candXY, d.candKey, d.candResp, d.candNode, d.candQ, d.candCount, d.selXYR,
                   d.selCount, d.status, d.rxOfs, d.rxAlpha, d.ryOfs, d.ryBeta, d.outKps, d.outDesc, d.outCounts, d.cellInfo,
-                  d.raw};
+                  d.raw, d.score, d.tileDx, d.tileDy};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->hKps) cudaFreeHost(h->hKps);

@@ -28,6 +28,8 @@ struct LevelGeom {
   float kpsize;           // (float)(int)(PATCH_SIZE*scale) (:1175,1189)
   int blurTileStart, blurTilesX, blurTilesY;
   uint32_t rxOff, ryOff;  // resize tables (entries) for producing this level from level-1
+  int tilesX, tilesY;     // 128 x 32 tiles of the fused front end (extractor_tile.cu)
+  uint32_t tdxOff, tdyOff;  // per tile column / row: first level l+1 column / row whose source sample starts in it
 };
 
 struct ExtractGeom {
@@ -42,6 +44,9 @@ struct DeviceBuffers {
   uint8_t* pyr = nullptr;      // B x pyrBytes
   uint8_t* blur = nullptr;     // B x pyrBytes
   uint8_t* raw = nullptr;      // B x width*height dense upload staging (host-buffer batch path)
+  uint8_t* score = nullptr;    // B x pyrBytes: FAST arc strength of every pixel (fused front end)
+  int16_t* tileDx = nullptr;   // resize ownership tables of the fused front end
+  int16_t* tileDy = nullptr;
   uint32_t* candXY = nullptr;  // B x totalCandCap   (x | y<<16, border-relative)
   uint32_t* candKey = nullptr; // B x totalCandCap   (order key: cell<<12 | ylocal<<6 | xlocal)
   uint8_t* candResp = nullptr; // B x totalCandCap
@@ -61,6 +66,12 @@ struct DeviceBuffers {
   int32_t* outCounts = nullptr;
 };
 
+}  // namespace b2s
+
+struct b2s_extractor;
+namespace b2s {
+int tile_build(b2s_extractor* h);  // tensor maps + resize ownership tables for the current geometry
+int tile_run(b2s_extractor* h, int bBase, int batch, int path, cudaStream_t st, cudaEvent_t evAfterTiles);
 }  // namespace b2s
 
 struct b2s_extractor {
@@ -88,6 +99,12 @@ struct b2s_extractor {
   int32_t* hCounts = nullptr;
   int32_t* hStatus = nullptr;
   long long launches = 0;
+  // fused front end (extractor_tile.cu): 0 = per-stage kernels, 1 = tile FAST, 2 = + blur, 3 = + pyramid (default)
+  int path = 3;
+  size_t tileTabAlloc = 0;
+  alignas(64) unsigned char tmPyr[b2s::kMaxLevels][128];    // CUtensorMap: level images (TMA load, 144 x 38 box)
+  alignas(64) unsigned char tmScore[b2s::kMaxLevels][128];  // strength map (TMA store, 128 x 32 box)
+  alignas(64) unsigned char tmBlur[b2s::kMaxLevels][128];   // blurred level (TMA store)
   // optional per-stage CUDA-event timing (bench.py roofline): resize chain, FAST, quadtree, blur, describe
   int timing = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

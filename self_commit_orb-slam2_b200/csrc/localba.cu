@@ -1748,7 +1748,10 @@ __global__ void __launch_bounds__(BA_T) k_local_ba(BaPtrs p, int nCta, int wBase
       // initializeOptimization(0) with every edge at level 1 leaves no active vertex: g2o's optimize() returns at once
       // (sparse_optimizer.cpp:356-359) and src/Optimizer.cc:921-958 flags the edges with the chi2 they already have,
       // which is what the level pass just stored in eOutlier.  Pinned by test_oracle_reference_optimizer (rejections_2).
-      if (c.cta == 0 && threadIdx.x == 0 && vst->nLive == 0) (p.st + w)->active = 0;
+      if (c.cta == 0 && threadIdx.x == 0 && vst->nLive == 0) {
+        (p.st + w)->active = 0;
+        (p.st + w)->chi2Final = 0;  // activeRobustChi2() over an empty active set
+      }
       win_barrier(bar, epoch, nCta, hung);
     }
     BA_PROF(10)
