@@ -22,14 +22,16 @@
 namespace b2s {
 
 constexpr int TW = 128, TH = 32;          // tile interior
-constexpr int HX = 8, HY = 3;             // halo left / top (right / bottom are HX / HY as well)
-constexpr int BW = TW + 2 * HX;           // 144: TMA box width in bytes (multiple of 16)
+// halo left / top (right / bottom are HX / HY as well).  Only 3 pixels are needed, but the innermost TMA coordinate must
+// be a multiple of 16 BYTES (x = tx*128 - 8 raises "illegal instruction" on B200; measured with tools/probe/tma_probe.cu)
+constexpr int HX = 16, HY = 3;
+constexpr int BW = TW + 2 * HX;           // 160: TMA box width in bytes (multiple of 16)
 constexpr int BH = TH + 2 * HY;           // 38
-constexpr int PWD = BW / 2;               // 72 pair words per plane row
+constexpr int PWD = BW / 2;               // 80 pair words per plane row
 constexpr int TILE_THREADS = 256;
 
 struct TileSmem {
-  alignas(128) uint8_t raw[BH * BW];        // TMA destination: rows ty*32-3 .., columns tx*128-8 ..
+  alignas(128) uint8_t raw[BH * BW];        // TMA destination: rows ty*32-3 .., columns tx*128-16 ..
   alignas(128) uint8_t scoreT[TH * TW];     // TMA store source: FAST arc strength M (0..255) per interior pixel
   alignas(128) uint8_t blurT[TH * TW];      // TMA store source: blurred interior
   alignas(16) uint32_t planeE[BH * PWD];    // (raw[2j], raw[2j+1]) as u16x2
@@ -180,10 +182,12 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ C
   // ---- FAST: pixel-pair planes, then the dense arc strength of the interior
   if (a.doFast) {
     const uint32_t* rw = reinterpret_cast<const uint32_t*>(S.raw);
-    for (int k = tid; k < BH * (BW / 4); k += TILE_THREADS) {
-      const int r = k / (BW / 4), q = k - r * (BW / 4);
-      const uint32_t w0 = rw[k];
-      const uint32_t w1 = (q + 1 < BW / 4) ? rw[k + 1] : 0u;
+    // (only the words the 16-point circles of the interior can reach: box columns [HX - 4, HX + TW + 4))
+    constexpr int Q0 = HX / 4 - 1, QN = TW / 4 + 2;
+    for (int k = tid; k < BH * QN; k += TILE_THREADS) {
+      const int r = k / QN, q = Q0 + (k - r * QN);
+      const uint32_t w0 = rw[r * (BW / 4) + q];
+      const uint32_t w1 = rw[r * (BW / 4) + q + 1];
       uint2 e, o;
       e.x = __byte_perm(w0, 0u, 0x4140);                 // (b0, b1)
       e.y = __byte_perm(w0, 0u, 0x4342);                 // (b2, b3)

@@ -43,14 +43,12 @@ int main() {
   CUtensorMap* gtm; cudaMalloc(&gtm, sizeof(CUtensorMap));
   struct V { int rank, bw, bh; int useGlobal; int x, y, z; CUtensorMapL2promotion l2; const char* name; };
   V vs[] = {
-    {2, 128, 32, 0, 0, 0, 0, CU_TENSOR_MAP_L2_PROMOTION_NONE, "2d 128x32 param"},
-    {2, 144, 38, 0, 0, 0, 0, CU_TENSOR_MAP_L2_PROMOTION_NONE, "2d 144x38 param"},
-    {3, 128, 32, 0, 0, 0, 1, CU_TENSOR_MAP_L2_PROMOTION_NONE, "3d 128x32 param z=1"},
-    {3, 144, 38, 0, 0, 0, 0, CU_TENSOR_MAP_L2_PROMOTION_NONE, "3d 144x38 param"},
-    {3, 144, 38, 0, 120, 29, 1, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "3d 144x38 param l2-128 x=120 y=29"},
-    {3, 144, 38, 0, -8, -3, 0, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "3d 144x38 param negative coords"},
-    {3, 144, 38, 1, -8, -3, 0, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "3d 144x38 GLOBAL desc negative coords"},
-    {3, 144, 38, 0, 632, 477, 1, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "3d 144x38 param past the edge"},
+    {3, 160, 38, 0, 128, 29, 1, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "3d 160x38 l2-128 x=128 y=29"},
+    {3, 160, 38, 0, 112, 29, 1, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "3d 160x38 l2-128 x=112 y=29"},
+    {3, 160, 38, 0, -16, -3, 0, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "3d 160x38 l2-128 x=-16 y=-3"},
+    {3, 160, 38, 1, -16, -3, 0, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "3d 160x38 GLOBAL desc x=-16 y=-3"},
+    {3, 160, 38, 0, 624, 477, 1, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "3d 160x38 past the edge x=624 y=477"},
+    {3, 144, 38, 0, 120, 0, 0, CU_TENSOR_MAP_L2_PROMOTION_NONE, "3d 144x38 none x=120 (8 mod 16)"},
   };
   for (V& v : vs) {
     CUtensorMap tm;
