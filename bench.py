@@ -7,9 +7,10 @@
         bench.py --gpus N --steps K --warmup W
 
 A "step" = one batch of F synthetic KITTI-shaped stereo frames (1241x376, 2000 features, 8 levels) per GPU:
-extraction of the 2F images, temporal SearchByBoW (2000x2000 brute force, one vocabulary node) of every left image
-against its predecessor, one LocalBA (50 KF / 5000 MP / 30k edges) per 5 frames; with N > 1 the left-image feature
-records are all-gathered over NCCL.  Prints ONE JSON line (see DESIGN.md "Measurement").
+extraction of the 2F images, Frame::ComputeStereoMatches of the F pairs, temporal SearchByBoW (2000x2000 brute force, one
+vocabulary node) of every left image against its predecessor, Optimizer::PoseOptimization of every frame and one LocalBA
+per 5 frames (32 DIFFERENT windows per step, 30-60 keyframes); with N > 1 the left-image feature records are all-gathered
+over NCCL.  Frames are distinct (seed = frame index).  Prints ONE JSON line (see DESIGN.md "Measurement").
 """
 import argparse
 import ctypes
@@ -30,6 +31,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 W_IMG, H_IMG, NFEAT = 1241, 376, 2000
 # algorithmic bytes per 1241x376 image
 B_STAGE_IMAGE = 9359539          # all extractor stages
+B_TILE_IMAGE = 2385248 + 1444097 + 2888194  # the stages the fused tile kernel replaces: pyramid R+W, FAST read, blur R+W
+STAGE_NAMES = ["resize_chain(legacy)", "tile_fast_blur_pyramid+cells", "quadtree", "blur(legacy)", "orient_describe"]
+# dram__bytes_read.sum + dram__bytes_write.sum of the eight k_tile launches of a 320-image batch (ncu --set full), per image;
+# None until a capture of the current kernel is committed under profiles/
+TRAFFIC_TILE_IMAGE = 0.0
+TRAFFIC_TILE_SOURCE = "pending: profiles/r2_ncu_full_k_tile_*.csv"
 B_FAST_IMAGE = 1444097           # FAST stage: every pyramid pixel read once (sum of the 8 level sizes)
 # dram__bytes_read.sum + dram__bytes_write.sum of one 320-image k_fast_cells launch (ncu --set full,
 # profiles/r1_ncu_full_k_fast_cells_v15.csv: 408.31 MB + 46.83 MB), per image
@@ -45,21 +52,65 @@ BA_TRAFFIC_TRIAL = (1.569211e9 + 1.483268e9) / 480.0
 BA_EVERY = 5
 
 
+def make_stream_images(n_distinct, seed0=0):
+    """uint8 [2, n_distinct, h, w]: left and right images of n_distinct DIFFERENT stereo frames (seed = frame index),
+    generated on a few host processes (38 ms per pair on one core)."""
+    from synth import synth_stereo_kitti
+    out = np.empty((2, n_distinct, H_IMG, W_IMG), np.uint8)
+    seeds = [seed0 + i for i in range(n_distinct)]
+    workers = max(1, min(16, (os.cpu_count() or 1) // 2, n_distinct // 8))
+    if workers > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            for i, (l, r) in enumerate(pool.imap(synth_stereo_kitti, seeds, chunksize=4)):
+                out[0, i], out[1, i] = l, r
+    else:
+        for i, sd in enumerate(seeds):
+            out[0, i], out[1, i] = synth_stereo_kitti(sd)
+    return out
+
+
 def make_images(n_distinct, total, seed0=0):
     """[2*total, h, w] uint8: L_0..L_{total-1}, R_0..R_{total-1}; n_distinct stereo pairs tiled."""
-    from synth import synth_stereo
-    base = [synth_stereo(W_IMG, H_IMG, seed0 + i) for i in range(n_distinct)]
+    base = make_stream_images(n_distinct, seed0)
     out = np.empty((2 * total, H_IMG, W_IMG), np.uint8)
     for i in range(total):
-        l, r = base[i % n_distinct]
-        out[i] = l
-        out[total + i] = r
+        out[i] = base[0, i % n_distinct]
+        out[total + i] = base[1, i % n_distinct]
     return out
 
 
 def ba_window():
     from synth import synth_local_ba
     return synth_local_ba(n_kf=50, n_fixed=10, n_mp=5000, obs_per_mp=6, seed=42)
+
+
+def ba_windows(n, seed0=0):
+    """n different LocalBA windows around the BASELINE.json shape (50 KF / 5000 MP / 30 k edges): 30-60 keyframes, 3000-6000
+    points, 4-7 observations per point, 0-8 % gross outliers, a fifth of them with monocular observations — so the LM traces
+    (accepted / rejected trials, early terminations) differ between the windows of one launch."""
+    from synth import synth_local_ba_fast
+    out = []
+    for i in range(n):
+        rng = np.random.RandomState(7000 + seed0 + i)
+        nkf = int(rng.randint(30, 61))
+        out.append(synth_local_ba_fast(n_kf=nkf, n_fixed=int(rng.randint(4, max(5, nkf // 4))),
+                                       n_mp=int(rng.randint(3000, 6001)), obs_per_mp=int(rng.randint(4, 8)),
+                                       seed=9000 + seed0 + i, mono_frac=0.2 if i % 5 == 4 else 0.0,
+                                       outlier_frac=float(rng.uniform(0.0, 0.08))))
+    return out
+
+
+def pose_problems(n, seed0=0):
+    """n different PoseOptimization problems (2000 features per frame, 50-70 % with a map point, 5-20 % gross outliers)."""
+    from synth import synth_pose_problem
+    out = []
+    for i in range(n):
+        rng = np.random.RandomState(11000 + seed0 + i)
+        out.append(synth_pose_problem(n=2000, seed=13000 + seed0 + i, mp_frac=float(rng.uniform(0.5, 0.7)),
+                                      mono_frac=0.2, outlier_frac=float(rng.uniform(0.05, 0.2)),
+                                      pert_t=float(rng.uniform(0.02, 0.15)), pert_deg=float(rng.uniform(0.2, 1.5))))
+    return out
 
 
 def load_peaks():
@@ -117,63 +168,193 @@ class ClockSampler:
         return out
 
 
-def cpu_stream_step_fn():
-    """The CPU arm's step function and what it is made of.  Preferred: oracle/_ref/libref_stream.so — the reference's OWN
-    src/ORBextractor.cc and src/ORBmatcher.cc compiled in place (oracle/Makefile `ref`, built where /root/reference is
-    mounted; the file travels to the GPU box) with the oracle port of LocalBA (src/Optimizer.cc needs g2o + Eigen, absent
-    here).  Otherwise the oracle port of all three stages (oracle/orb_misc.cpp orc_stream_step)."""
-    import oracle_binding
-    vp = ctypes.c_void_p
-    argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int,
-                ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]
-    ref_lib = os.path.join(ROOT, "oracle", "_ref", "libref_stream.so")
-    if os.path.exists(ref_lib) and not os.environ.get("B2S_BENCH_CPU_PORT"):
-        R = ctypes.CDLL(ref_lib)
-        fn = R.ref_stream_step
-        kind = "reference"
-        what = ("reference's own ORBextractor.cc + ORBmatcher.cc compiled in place (oracle/_ref) + oracle port of LocalBA "
-                "(Optimizer.cc needs Eigen)")
-    else:
-        fn = oracle_binding.load().L.orc_stream_step
-        kind = "port"
-        what = "oracle port (extract, match, LocalBA)"
-    fn.restype = ctypes.c_double
-    fn.argtypes = argtypes
-    ba = ba_window()
-    keep = dict(Tcw=np.ascontiguousarray(ba["Tcw"], np.float32), fixed=np.ascontiguousarray(ba["fixed"], np.uint8),
-                points=np.ascontiguousarray(ba["points"], np.float32), edges=np.ascontiguousarray(ba["edges"]))
-    prob = oracle_binding.BaProblem(ba["n_kf"], ba["n_local"], keep["Tcw"].ctypes.data, keep["fixed"].ctypes.data,
-                                    len(keep["points"]), keep["points"].ctypes.data, len(keep["edges"]),
-                                    keep["edges"].ctypes.data, ba["fx"], ba["fy"], ba["cx"], ba["cy"], ba["bf"], 5, 10)
+class CpuArm:
+    """The reference's own CPU implementation of the step on the host cores (oracle/ref_stream2_glue.cpp ->
+    oracle/_ref/libref_stream2.so, built where /root/reference is mounted; the files travel to the GPU box):
+    reference Frame constructor (two ORBextractor threads + ComputeStereoMatches), reference ORBmatcher::SearchByBoW,
+    Optimizer::PoseOptimization and Optimizer::LocalBundleAdjustment.  For the two optimizers both builds are timed on one
+    problem — the reference's Optimizer.cc + g2o on the Eigen stand-in (libref_optimizer.so) and the oracle's C++ port —
+    and the FASTER one runs in the arm (the stand-in Eigen is not vectorised: the port usually wins), so the CPU figure is
+    not held down by test scaffolding.  The cv stand-in's resize / FAST / blur are scalar C++ (OpenCV's are SIMD): the
+    `cv2_extract_ratio` field measures that gap on this box."""
 
-    def step(imgs, S, threads):
-        assert keep is not None  # (the problem arrays must outlive the call)
-        return fn(NFEAT, 1.2, 8, 20, 7, imgs.ctypes.data_as(vp), S, W_IMG, H_IMG, ctypes.byref(prob), BA_EVERY, threads, None)
-    return step, kind, what
+    def __init__(self):
+        import oracle_binding
+        self.ob = oracle_binding
+        vp = ctypes.c_void_p
+        lib2 = os.path.join(ROOT, "oracle", "_ref", "libref_stream2.so")
+        if not os.path.exists(lib2):
+            raise SystemExit("bench.py: oracle/_ref/libref_stream2.so is missing (python __graft_entry__.py builds it where "
+                             "/root/reference is mounted)")
+        self.R = ctypes.CDLL(lib2)
+        self.R.ref_stream2_step.restype = ctypes.c_double
+        self.R.ref_stream2_step.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp,
+                                            vp, ctypes.c_int, vp, vp]
+        self.O = oracle_binding.load().L
+        opt = os.path.join(ROOT, "oracle", "_ref", "libref_optimizer.so")
+        self.G = ctypes.CDLL(opt) if os.path.exists(opt) else None
+        self.keep = []
+
+    class Cfg(ctypes.Structure):
+        _fields_ = [("nfeatures", ctypes.c_int), ("nlevels", ctypes.c_int), ("iniTh", ctypes.c_int), ("minTh", ctypes.c_int),
+                    ("scaleFactor", ctypes.c_float), ("fx", ctypes.c_float), ("fy", ctypes.c_float), ("cx", ctypes.c_float),
+                    ("cy", ctypes.c_float), ("bf", ctypes.c_float), ("thDepth", ctypes.c_float)]
+
+    def _ba_array(self, windows):
+        ob = self.ob
+        arr = (ob.BaProblem * len(windows))()
+        for i, d in enumerate(windows):
+            k = dict(Tcw=np.ascontiguousarray(d["Tcw"], np.float32), fixed=np.ascontiguousarray(d["fixed"], np.uint8),
+                     points=np.ascontiguousarray(d["points"], np.float32), edges=np.ascontiguousarray(d["edges"]))
+            self.keep.append(k)
+            arr[i] = ob.BaProblem(d["n_kf"], d["n_local"], k["Tcw"].ctypes.data, k["fixed"].ctypes.data, len(k["points"]),
+                                  k["points"].ctypes.data, len(k["edges"]), k["edges"].ctypes.data, d["fx"], d["fy"], d["cx"],
+                                  d["cy"], d["bf"], 5, 10)
+        return arr
+
+    def _pose_array(self, poses):
+        ob = self.ob
+        arr = (ob.PoseProblem * len(poses))()
+        for i, d in enumerate(poses):
+            a = ob.pose_problem_arrays(d)
+            self.keep.append(a)
+            arr[i] = ob.PoseProblem(a["Tcw"].ctypes.data, len(a["has_mp"]), a["has_mp"].ctypes.data, a["Xw"].ctypes.data,
+                                    a["kpx"].ctypes.data, a["kpy"].ctypes.data, a["uright"].ctypes.data,
+                                    a["inv_sigma2"].ctypes.data, d["fx"], d["fy"], d["cx"], d["cy"], d["bf"])
+        return arr
+
+    def pick_solvers(self, window, pose):
+        """Single-thread time of one LocalBA window / one PoseOptimization with both builds; the faster one is used."""
+        ob = self.ob
+        info = {}
+        t = time.perf_counter(); ob.call_local_ba(self.O.orc_local_ba, window); info["local_ba_port_ms"] = (time.perf_counter() - t) * 1e3
+        t = time.perf_counter(); ob.call_pose_optimization(self.O.orc_pose_optimization, pose); info["pose_port_ms"] = (time.perf_counter() - t) * 1e3
+        self.ba_fn, self.pose_fn = self.O.orc_local_ba, self.O.orc_pose_optimization
+        info["local_ba_impl"] = info["pose_impl"] = "oracle port"
+        if self.G is not None:
+            t = time.perf_counter(); ob.call_local_ba(self.G.ref_local_ba, window); info["local_ba_ref_g2o_ms"] = (time.perf_counter() - t) * 1e3
+            t = time.perf_counter(); ob.call_pose_optimization(self.G.ref_pose_optimization, pose); info["pose_ref_g2o_ms"] = (time.perf_counter() - t) * 1e3
+            if info["local_ba_ref_g2o_ms"] < info["local_ba_port_ms"]:
+                self.ba_fn, info["local_ba_impl"] = self.G.ref_local_ba, "reference Optimizer.cc + g2o (Eigen stand-in)"
+            if info["pose_ref_g2o_ms"] < info["pose_port_ms"]:
+                self.pose_fn, info["pose_impl"] = self.G.ref_pose_optimization, "reference Optimizer.cc + g2o (Eigen stand-in)"
+        return info
+
+    def prepare(self, windows, poses):
+        self.nBa, self.nPose = len(windows), len(poses)
+        self.ba_arr = self._ba_array(windows) if windows else None
+        self.pose_arr = self._pose_array(poses) if poses else None
+        self.cfg = CpuArm.Cfg(NFEAT, 8, 20, 7, 1.2, 718.856, 718.856, 607.1928, 185.2157, 386.1448, 35.0)
+
+    def step(self, imgs_lr, threads):
+        """imgs_lr: uint8 [2, S, h, w] contiguous.  Returns (wall seconds, stats[8])."""
+        S = imgs_lr.shape[1]
+        stats = (ctypes.c_double * 8)()
+        vp = ctypes.c_void_p
+        wall = self.R.ref_stream2_step(ctypes.byref(self.cfg), imgs_lr.ctypes.data_as(vp), S, W_IMG, H_IMG, threads,
+                                       ctypes.cast(self.ba_arr, vp) if self.ba_arr is not None else None, self.nBa,
+                                       ctypes.cast(self.ba_fn, vp), ctypes.cast(self.pose_arr, vp) if self.pose_arr is not None else None,
+                                       self.nPose, ctypes.cast(self.pose_fn, vp), stats)
+        return wall, list(stats)
+
+
+def cv2_extract_ratio():
+    """How much faster OpenCV's own (SIMD) resize / FAST / GaussianBlur are than the scalar cv stand-in the reference's
+    ORBextractor.cc is compiled against here: single-thread time of those three stages on one 1241x376 image, both ways
+    (Python cv2 is the OpenCV build available in this image).  None if cv2 is not importable."""
+    try:
+        import cv2
+        import oracle_binding
+        from synth import synth_image
+    except Exception:
+        return None
+    cv2.setNumThreads(1)
+    o = oracle_binding.load()
+    img = synth_image(W_IMG, H_IMG, 3)
+    lv = [img]
+    for l in range(1, 8):
+        s = 1.2 ** l
+        lv.append(cv2.resize(lv[-1], (int(round(W_IMG / s)), int(round(H_IMG / s))), interpolation=cv2.INTER_LINEAR))
+    fd20 = cv2.FastFeatureDetector_create(20, True)
+
+    def run_cv2():
+        cur = img
+        for l in range(8):
+            if l:
+                cur = cv2.resize(cur, (lv[l].shape[1], lv[l].shape[0]), interpolation=cv2.INTER_LINEAR)
+            fd20.detect(cur[16:-16, 16:-16])
+            cv2.GaussianBlur(cur, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101)
+
+    def run_stand_in():
+        cur = img
+        for l in range(8):
+            if l:
+                cur = o.resize(cur, lv[l].shape[1], lv[l].shape[0])
+            o.fast(np.ascontiguousarray(cur[16:-16, 16:-16]), 20)
+            o.blur(cur)
+    out = {}
+    for name, fn in (("cv2_ms", run_cv2), ("stand_in_ms", run_stand_in)):
+        fn()
+        t = time.perf_counter()
+        for _ in range(3):
+            fn()
+        out[name] = (time.perf_counter() - t) / 3 * 1e3
+    out["ratio"] = out["stand_in_ms"] / max(out["cv2_ms"], 1e-9)
+    out["note"] = ("whole-level FAST instead of the reference's per-cell calls on both sides; pyramid + FAST(20) + blur of one "
+                   "1241x376 image, one thread")
+    return out
+
+
+def cpu_arm_measure(S, steps, warmup, seed0=0, with_cv2=True):
+    """`steps` timed steps of S stereo frames each on all host threads; returns the fields of the reference line."""
+    threads = os.cpu_count() or 1
+    arm = CpuArm()
+    windows = ba_windows((S + BA_EVERY - 1) // BA_EVERY, seed0)
+    poses = pose_problems(S, seed0)
+    info = arm.pick_solvers(windows[0], poses[0])
+    arm.prepare(windows, poses)
+    imgs = np.ascontiguousarray(make_stream_images(S, seed0))
+    for _ in range(warmup):
+        arm.step(imgs, threads)
+    tot, busy = 0.0, np.zeros(4)
+    last = None
+    for _ in range(steps):
+        wall, st = arm.step(imgs, threads)
+        tot += wall
+        busy += np.array(st[:4])
+        last = st
+    fps = S * steps / tot
+    stage = {"frame_extract_stereo_ms_per_frame": 1e3 * busy[0] / (S * steps), "search_by_bow_ms_per_frame": 1e3 * busy[1] / (S * steps),
+             "pose_optimization_ms_per_frame": 1e3 * busy[2] / (S * steps),
+             "local_ba_ms_per_window": 1e3 * busy[3] / max(1, len(windows) * steps)}
+    return {"fps": fps, "threads": threads, "seconds": tot, "S": S, "tasks_per_step": 2 * S + len(windows) + len(poses),
+            "utilisation": float(busy.sum() / (threads * tot)), "stage_ms_single_thread": stage, "solvers": info,
+            "keypoints_per_image": last[4], "stereo_matches_per_frame": last[5], "bow_matches_per_frame": last[6],
+            "cv2": cv2_extract_ratio() if with_cv2 else None}
+
+
+def cpu_sample_text(m):
+    return ("%d stereo frames per step (%d tasks on %d host threads, %.1f s timed, utilisation %.0f %%): reference's own Frame "
+            "constructor (ORBextractor.cc x2 threads + ComputeStereoMatches), ORBmatcher::SearchByBoW, PoseOptimization [%s], "
+            "LocalBundleAdjustment [%s]; OpenCV primitives = scalar stand-in (cv2 is %sx faster on pyramid+FAST+blur)"
+            % (m["S"], m["tasks_per_step"], m["threads"], m["seconds"], 100 * m["utilisation"], m["solvers"]["pose_impl"],
+               m["solvers"]["local_ba_impl"], ("%.1f" % m["cv2"]["ratio"]) if m.get("cv2") else "n/a "))
 
 
 def run_reference(args, rank, world):
-    """The reference algorithm's CPU path on all host cores (see cpu_stream_step_fn)."""
+    """The reference's own CPU implementation of the workload on all host cores (see CpuArm)."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    S = args.ref_frames
-    imgs = make_images(min(S, 8), S)
-    step, kind, what = cpu_stream_step_fn()
-    for _ in range(args.warmup):
-        step(imgs, S, threads)
-    t = 0.0
-    for _ in range(args.steps):
-        t += step(imgs, S, threads)
-    fps = S * args.steps / t
+    S = args.ref_frames if args.ref_frames > 0 else args.frames
+    m = cpu_arm_measure(S, args.steps, args.warmup)
+    fps = m["fps"]
     line = {
         "impl": "reference", "metric": "stereo_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * m["seconds"] / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (extract, match), f64 (LocalBA)", "data": "synthetic",
         "config": workload_config(S, 1),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
-                         "sample": "%d stereo frames per step (bounded sample of the workload) on %d host threads: %s"
-                                   % (S, threads, what)},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": m["threads"], "kind": "reference", "sample": cpu_sample_text(m),
+                         "detail": m},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -181,8 +362,9 @@ def run_reference(args, rank, world):
 
 
 def workload_config(frames_per_gpu, world):
-    return {"workload": "batched KITTI-shape stereo stream 1241x376, 2000 feat/img, 8 levels, FAST 20/7: extract L+R, "
-                        "temporal SearchByBoW 2000x2000 (one vocabulary node), LocalBA 50KF/5000MP/30k edges every 5th frame",
+    return {"workload": "batched KITTI-shape stereo stream 1241x376, 2000 feat/img, 8 levels, FAST 20/7, distinct frames: extract "
+                        "L+R, ComputeStereoMatches, temporal SearchByBoW 2000x2000 (one vocabulary node), PoseOptimization per "
+                        "frame, LocalBA every 5th frame (32 different windows per 160 frames, 30-60 KF / 3000-6000 MP / ~30k edges)",
             "frames_per_step_per_gpu": frames_per_gpu, "images_per_step_per_gpu": 2 * frames_per_gpu,
             "parallelism": "frames sharded x%d, NCCL all-gather of the shard-boundary left-image feature records" % world,
             "l2": "inputs per step (%.0f MB of images per GPU) exceed the 126 MB L2"
@@ -200,16 +382,24 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    F = args.frames
-    ba = ba_window()
+    F, D = args.frames, max(args.frames, args.distinct)
+    n_ba = (F + BA_EVERY - 1) // BA_EVERY
+    windows = ba_windows(n_ba, seed0=1000 * rank)
+    poses = pose_problems(F, seed0=1000 * rank)
     if world > 1:  # several ranks share the host cores: split them for the LocalBA window preparation threads
         os.environ.setdefault("B2S_BA_HOST_THREADS", str(max(2, min(16, (os.cpu_count() or 16) // world))))
-    ss = stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, ba_problem=ba, ba_every=BA_EVERY, device=local_rank, rank=rank,
-                                 world=world, ba_depth=args.ba_depth, exchange=args.exchange)
-    imgs = make_images(min(F, 16), F, seed0=1000 * rank)
+    ss = stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, ba_problems=windows, pose_problems=poses, stereo=True, ba_every=BA_EVERY,
+                                 device=local_rank, rank=rank, world=world, ba_depth=args.ba_depth, exchange=args.exchange)
+    imgs = make_stream_images(D, seed0=100000 * rank)  # [2, D, h, w], frame index = seed
     pinned = torch.from_numpy(imgs).pin_memory()
-    ss.upload(pinned)
+    d_all = pinned.cuda(non_blocking=True)
     torch.cuda.synchronize()
+    step_no = [0]
+
+    def dev_step():
+        ss.load_window(d_all, (step_no[0] * F) % D)
+        step_no[0] += 1
+        return ss.step_device(pipelined=True)  # solvers of step k overlap extraction / matching of step k+1
 
     def barrier():
         if dist is not None:
@@ -217,7 +407,7 @@ def run_b200(args, rank, local_rank, world):
 
     # ---------------- device-resident throughput (`value`)
     for _ in range(args.warmup):
-        ss.step_device(pipelined=True)
+        dev_step()
     ss.finish()
     ss.ex.check()
     torch.cuda.synchronize()
@@ -234,14 +424,15 @@ def run_b200(args, rank, local_rank, world):
     t0 = time.perf_counter()
     ev0.record(ss.stream)
     for _ in range(args.steps):
-        ss.step_device(pipelined=True)  # LocalBA of step k overlaps extraction/matching of step k+1
-    ss.finish()                         # ... and the last batch is joined inside the timed region
+        dev_step()
+    ss.finish()                         # the last solver batch is joined inside the timed region
     ev1.record(ss.stream)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if sampler else None
-    # the LocalBA batch runs on its own stream and is synchronous on the host, so the host wall clock bounds everything
+    # the solver batches run on their own streams and are synchronous on their host thread, so the host wall clock bounds
+    # everything
     dev_ms = max(ev0.elapsed_time(ev1), wall * 1e3)
     launches = ss.launch_count() - launches0
     stage = (ctypes.c_double * 5)()
@@ -255,16 +446,16 @@ def run_b200(args, rank, local_rank, world):
     dev_ms = float(t_all.item())
     value = world * F * args.steps / (dev_ms / 1e3)
 
-    # ---------------- phase breakdown (untimed extra passes, for DESIGN.md / profiles): extraction+matching alone, LocalBA alone
+    # ---------------- phase breakdown (untimed extra passes, for DESIGN.md / profiles)
     phase = {}
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     for _ in range(2):
+        ss.load_window(d_all, 0)
         ss.step_device(run_ba=False)
     torch.cuda.synchronize()
-    phase["extract_match_ms"] = (time.perf_counter() - t1) * 500.0
-    # extractor stage timing without LocalBA competing for the SMs
-    L.b2s_extractor_set_timing(ss.ex._h, 1)
+    phase["extract_stereo_match_ms"] = (time.perf_counter() - t1) * 500.0
+    L.b2s_extractor_set_timing(ss.ex._h, 1)  # extractor stage timing without the solvers competing for the SMs
     for _ in range(2):
         ss.step_device(run_ba=False)
     torch.cuda.synchronize()
@@ -272,64 +463,60 @@ def run_b200(args, rank, local_rank, world):
     calls_iso = ctypes.c_longlong(0)
     L.b2s_extractor_get_timing(ss.ex._h, stage_iso, ctypes.byref(calls_iso))
     L.b2s_extractor_set_timing(ss.ex._h, 0)
-    phase["extractor_stage_ms_isolated"] = {k: stage_iso[i] / max(1, calls_iso.value) for i, k in enumerate(
-        ["resize_chain", "fast_cells", "quadtree", "blur", "orient_describe"])}
-    # Frame::ComputeStereoMatches for the F pairs of the step, on the resident pyramids (reported next to
-    # the step, not part of the metric): left image i <-> right image F+i
+    phase["extractor_stage_ms_isolated"] = {k: stage_iso[i] / max(1, calls_iso.value) for i, k in enumerate(STAGE_NAMES)}
+    phase["stereo_matches_per_frame"] = float(ss.nstereo.float().mean().item())
+    phase["keypoints_per_image"] = float(ss.counts[1:].float().mean().item())
+    ba_kernel_ms, ba_trials = 0.0, 0
     try:
-        ur = torch.zeros((F, ss.cap), dtype=torch.float32, device="cuda")
-        dp = torch.zeros((F, ss.cap), dtype=torch.float32, device="cuda")
-        nmt = torch.zeros(F, dtype=torch.int32, device="cuda")
-        st = ss.stream
-        with torch.cuda.stream(st):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            for rep in range(2):
-                if rep == 1:
-                    e0.record(st)
-                ss.ex.stereo_match_device(0, F, F, ss.kps[1:].data_ptr(), ss.desc[1:].data_ptr(),
-                                          ss.counts[1:].data_ptr(), ss.cap, 386.1448, 0.0, ur.data_ptr(), dp.data_ptr(),
-                                          nmt.data_ptr(), stream=st.cuda_stream)
-            e1.record(st)
-        torch.cuda.synchronize()
-        phase["stereo_match_ms_isolated"] = e0.elapsed_time(e1)
-        phase["stereo_matches_per_frame"] = float(nmt.float().mean().item())
-    except Exception as ex:  # never let the side measurement break the bench line
-        phase["stereo_match_error"] = str(ex)[:200]
-    # Optimizer::PoseOptimization for the F frames of the step (side measurement through the host-buffer
-    # C ABI: packing, H2D, one CTA per frame, D2H)
-    try:
-        from synth import synth_pose_problem
-        pp = [synth_pose_problem(seed=1000 + (i % 8)) for i in range(8)]
-        frames_pp = [pp[i % 8] for i in range(F)]
-        popt = ss.opt if ss.opt is not None else None
-        if popt is not None:
-            popt.PoseOptimizationBatch(frames_pp)
-            t1 = time.perf_counter()
-            pr = popt.PoseOptimizationBatch(frames_pp)
-            phase["pose_optimization_batch_ms"] = (time.perf_counter() - t1) * 1e3
-            phase["pose_optimization_frames"] = F
-            phase["pose_optimization_inliers_per_frame"] = float(np.mean([r["n_inliers"] for r in pr]))
-    except Exception as ex:
-        phase["pose_optimization_error"] = str(ex)[:200]
-    if ss.n_ba:
         t1 = time.perf_counter()
-        ss.opt.LocalBundleAdjustmentBatch([ss.ba_problem] * ss.n_ba)
+        pr = ss.opt.PoseOptimizationBatch(poses)
+        phase["pose_optimization_batch_ms"] = (time.perf_counter() - t1) * 1e3
+        phase["pose_optimization_inliers_per_frame"] = float(np.mean([r["n_inliers"] for r in pr]))
+        t1 = time.perf_counter()
+        outs = ss.opt.LocalBundleAdjustmentBatch(windows)
         phase["local_ba_batch_ms"] = (time.perf_counter() - t1) * 1e3
-        phase["local_ba_windows"] = ss.n_ba
-        try:
-            ba_kernel_ms, ba_trials = ss.opt.last_kernel_ms()
-        except Exception:
-            ba_kernel_ms, ba_trials = 0.0, 0
+        phase["local_ba_windows"] = n_ba
+        phase["local_ba_trials_per_window"] = [int(o["n_trials"]) for o in outs]
+        ba_kernel_ms, ba_trials = ss.opt.last_kernel_ms()
+    except Exception as ex:  # never let a side measurement break the bench line
+        phase["solver_side_measurement_error"] = str(ex)[:200]
+    # the round-1 workload (no stereo matching / PoseOptimization, one LocalBA window x 32) for continuity
+    try:
+        w1 = ba_window()
+        ss1 = ss
+        keep = (ss1.windows, ss1.pose_problems, ss1.stereo)
+        ss1.windows, ss1.pose_problems, ss1.stereo = [w1], [], False
+        ss1._prep.clear()
+        for _ in range(2):
+            ss1.step_device(pipelined=True)
+        ss1.finish()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(4):
+            ss1.step_device(pipelined=True)
+        ss1.finish()
+        torch.cuda.synchronize()
+        phase["round1_workload_frames_per_s"] = 4 * F / (time.perf_counter() - t1)
+        ss1.windows, ss1.pose_problems, ss1.stereo = keep
+        ss1._prep.clear()
+    except Exception as ex:
+        phase["round1_workload_error"] = str(ex)[:200]
 
     # ---------------- end to end through the host-buffer C ABI (`e2e`)
     e2e_steps = args.steps if args.e2e_steps <= 0 else max(1, min(args.steps, args.e2e_steps))
-    imgs_pinned = pinned.numpy()  # e2e inputs come from pinned host memory
-    ss.step_host(imgs_pinned)  # warm
+    base_ptr, img_bytes = pinned.data_ptr(), W_IMG * H_IMG  # e2e inputs come from pinned host memory
+
+    def host_step(k):
+        idx = [(k * F + i) % D for i in range(F)]
+        ptrs = [base_ptr + i * img_bytes for i in idx] + [base_ptr + (D + i) * img_bytes for i in idx]
+        return ss.step_host(None, pipelined=True, img_ptrs=ptrs)
+    host_step(0)  # warm
+    ss.finish()
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        n, nm, ba_out, _ = ss.step_host(imgs_pinned, pipelined=True)
+    for k in range(e2e_steps):
+        n, nm, ba_out, _ = host_step(k + 1)
     ss.finish()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -343,26 +530,25 @@ def run_b200(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
     peaks, peak_src = load_peaks()
-    roofline_ba = None
-    if ss.n_ba and ba_kernel_ms > 0:
-        ba_gbs = BA_BYTES_TRIAL * ba_trials / (ba_kernel_ms * 1e-3) / 1e9
-        roofline_ba = {"kernel": "k_local_ba (persistent LM loop: %d windows x 4 CTAs, one launch per LocalBA batch)" % ss.n_ba,
-                       "bound": "hbm", "achieved": ba_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                       "frac": ba_gbs / peaks["hbm_gbs"], "traffic": BA_TRAFFIC_TRIAL * ba_trials,
-                       "traffic_source": "profiles/r1_ncu_full_k_local_ba_v19.csv (ncu --set full, 32-window launch)",
-                       "launch_ms": ba_kernel_ms, "launch_ms_source": "CUDA events on the solver stream, batch run alone",
-                       "lm_trials": ba_trials, "algorithmic_bytes_per_launch": BA_BYTES_TRIAL * ba_trials,
-                       "fp64": {"achieved_tflops": BA_FLOP_TRIAL * ba_trials / (ba_kernel_ms * 1e-3) / 1e12,
-                                "nominal_peak_tflops": FP64_NOMINAL_TFLOPS},
-                       "note": "latency-bound (barrier 3.8 + long_scoreboard 2.4 warps per issue at 8 warps/SM, FP64 pipe "
-                               "18 %); since W_e is recomputed by its consumers and the error pass before buildSystem is "
-                               "reused, DRAM traffic (6.4 MB per LM trial) is below SURVEY's 16 MB estimate, which assumed a "
-                               "stored 4.3 MB W array per window (see profiles/README.md)"}
-
-    fast_ms = stage[1] / max(1, calls.value)
+    micro = measure_device_peaks(pkg)
+    # ---- roofline of the dominant front-end kernel: the fused tile kernel (8 launches, one per level)
+    tile_ms = stage[1] / max(1, calls.value)
+    tile_iso = phase["extractor_stage_ms_isolated"].get(STAGE_NAMES[1])
     images_per_launch = 2 * F
-    achieved = B_FAST_IMAGE * images_per_launch / (fast_ms * 1e-3) / 1e9 if fast_ms > 0 else 0.0
+    achieved = B_TILE_IMAGE * images_per_launch / (tile_ms * 1e-3) / 1e9 if tile_ms > 0 else 0.0
     ex_ms = sum(stage) / max(1, calls.value)
+    roof = {"kernel": "k_tile x 8 levels + k_cells + k_fast_cells_list (TMA-staged tile: FAST strength + NMS bitmap + Q8 blur + "
+                      "next pyramid level; per-cell threshold rules)", "bound": "hbm", "achieved": achieved,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": TRAFFIC_TILE_IMAGE * images_per_launch,
+            "traffic_source": TRAFFIC_TILE_SOURCE, "peak_source": peak_src, "launch_ms": tile_ms, "launch_ms_isolated": tile_iso,
+            "algorithmic_bytes_per_launch": B_TILE_IMAGE * images_per_launch,
+            "algorithmic_bytes_note": "SURVEY 8d per image: pyramid R+W 2,385,248 + FAST read 1,444,097 + blur R+W 2,888,194 B",
+            "issue_bound": {"note": "the tile kernel is bound by the ALU pipe (packed u16x2 min/max of FAST), not by HBM",
+                            "alu_pipe_peak_gwarpinstr_s": micro.get("alu_vimnmx3_gwarp_s")},
+            "extractor_all_stages": {"ms_per_launch_set": ex_ms,
+                                     "achieved_GBps": B_STAGE_IMAGE * images_per_launch / (ex_ms * 1e-3) / 1e9 if ex_ms > 0 else 0.0,
+                                     "frac": (B_STAGE_IMAGE * images_per_launch / (ex_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if ex_ms > 0 else 0.0,
+                                     "stage_ms": {k: stage[i] / max(1, calls.value) for i, k in enumerate(STAGE_NAMES)}}}
     line = {
         "metric": "stereo_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -373,41 +559,54 @@ def run_b200(args, rank, local_rank, world):
         "gpu_launches": int(launches),
         "phase_ms": phase,
         "clocks": clocks,
-        "roofline": {"kernel": "k_fast_cells (per-cell FAST-9/16 score + NMS + dual threshold)", "bound": "hbm",
-                     "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": TRAFFIC_FAST_IMAGE * images_per_launch,
-                     "traffic_source": "profiles/r1_ncu_full_k_fast_cells_v15.csv (ncu --set full, 320-image launch)",
-                     "peak_source": peak_src, "launch_ms": fast_ms,
-                     "launch_ms_isolated": phase.get("extractor_stage_ms_isolated", {}).get("fast_cells"),
-                     "algorithmic_bytes_per_launch": B_FAST_IMAGE * images_per_launch,
-                     "extractor_all_stages": {"ms_per_launch_set": ex_ms,
-                                              "achieved_GBps": B_STAGE_IMAGE * images_per_launch / (ex_ms * 1e-3) / 1e9
-                                              if ex_ms > 0 else 0.0,
-                                              "stage_ms": {"resize_chain": stage[0] / max(1, calls.value),
-                                                           "fast_cells": fast_ms,
-                                                           "quadtree": stage[2] / max(1, calls.value),
-                                                           "blur": stage[3] / max(1, calls.value),
-                                                           "orient_describe": stage[4] / max(1, calls.value)}}},
+        "roofline": roof,
+        "device_peaks_measured": micro,
     }
-    if roofline_ba is not None:
-        line["roofline_local_ba"] = roofline_ba
+    line["config"]["distinct_frames_resident"] = D
+    if ba_kernel_ms > 0:
+        ba_gbs = BA_BYTES_TRIAL * ba_trials / (ba_kernel_ms * 1e-3) / 1e9
+        fp64_peak = micro.get("fp64_dfma_tflops") or FP64_NOMINAL_TFLOPS
+        line["roofline_local_ba"] = {
+            "kernel": "k_local_ba (persistent LM loop: %d different windows x 4 CTAs, one launch per LocalBA batch)" % n_ba,
+            "bound": "hbm", "achieved": ba_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ba_gbs / peaks["hbm_gbs"],
+            "traffic": None, "launch_ms": ba_kernel_ms, "launch_ms_source": "CUDA events on the solver stream, batch run alone",
+            "lm_trials": ba_trials, "algorithmic_bytes_per_launch": BA_BYTES_TRIAL * ba_trials,
+            "algorithmic_bytes_note": "SURVEY 8d: 16 MB per LM trial of a 50/5000/30k window (scaled by the launch's trial count)",
+            "fp64": {"achieved_tflops": BA_FLOP_TRIAL * ba_trials / (ba_kernel_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
+                     "peak_source": "measured DFMA micro-benchmark in this run" if micro.get("fp64_dfma_tflops") else "nominal",
+                     "frac": BA_FLOP_TRIAL * ba_trials / (ba_kernel_ms * 1e-3) / 1e12 / fp64_peak},
+            "note": "latency-bound (window barriers, dependent gathers at 8 warps/SM); measured DRAM traffic of the round-1 capture "
+                    "was 6.4 MB per LM trial (profiles/r1_ncu_full_k_local_ba_v19.csv)"}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline()
+        line["cpu_baseline"] = cpu_baseline(F)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
-def cpu_baseline():
-    """The CPU arm timed on this box's host cores, bounded sample (about 10-30 core-seconds); see cpu_stream_step_fn."""
-    threads = os.cpu_count() or 1
-    S = 48
-    imgs = make_images(8, S)
-    step, kind, what = cpu_stream_step_fn()
-    t = step(imgs, S, threads)
-    return {"value": S / t, "unit": "frames/s", "cores": threads, "kind": kind,
-            "sample": "%d stereo frames (96 images, 48 matches, 10 LocalBA windows) on %d host threads, %.1f s: %s"
-                      % (S, threads, t, what)}
+def measure_device_peaks(pkg):
+    """Issue-rate / FP64 / POPC micro-benchmarks of THIS device in THIS run (b2s_measure_peaks): the bounds the integer
+    front end, the FP64 solver and the Hamming matcher actually run against (MEASURED_PEAKS.json has HBM and bf16 only)."""
+    try:
+        L = pkg.lib()
+        out = (ctypes.c_double * 8)()
+        L.b2s_measure_peaks.argtypes = [ctypes.c_int, ctypes.c_void_p]
+        rc = L.b2s_measure_peaks(0, out)
+        if rc != 0:
+            return {"error": "b2s_measure_peaks rc=%d" % rc}
+        return {"alu_vimnmx3_gwarp_s": out[0], "fma_imad_gwarp_s": out[1], "fp64_dfma_tflops": out[2], "popc_gwarp_s": out[3],
+                "dual_issue_alu_fma_gwarp_s": out[4],
+                "how": "b2s_measure_peaks: dependent-free unrolled chains, 148 x 8 CTAs x 256 threads, CUDA events, best of 3"}
+    except Exception as ex:
+        return {"error": str(ex)[:200]}
+
+
+def cpu_baseline(F):
+    """The CPU arm on this box's host cores, bounded sample: one warm-up + two timed steps of the SAME workload (F frames per
+    step); see CpuArm."""
+    m = cpu_arm_measure(F, steps=2, warmup=1, with_cv2=True)
+    return {"value": m["fps"], "unit": "frames/s", "cores": m["threads"], "kind": "reference", "sample": cpu_sample_text(m),
+            "detail": m}
 
 
 def main():
@@ -418,7 +617,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=160, help="stereo frames per step per GPU (160 -> 149 MB of images)")
-    ap.add_argument("--ref-frames", type=int, default=24, help="stereo frames per step of the CPU reference arm")
+    ap.add_argument("--ref-frames", type=int, default=0, help="stereo frames per step of the CPU reference arm (0: --frames)")
+    ap.add_argument("--distinct", type=int, default=512, help="different stereo frames resident per GPU (seed = frame index)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end loop (0: the same K as --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="boundary", choices=["boundary", "all"],

@@ -40,6 +40,10 @@ enum {
 const char* b2s_last_error(void);   /* thread-local text of the last failure */
 int b2s_version(void);
 int b2s_device_count(void);
+/* Issue-rate micro-benchmarks of `device` (about 20 ms): out8[0] packed u16x2 min/max (ALU pipe) and [1] IMAD (FMA pipe) in
+ * G warp-instructions/s, [2] FP64 DFMA TFLOP/s, [3] POPC G warp-instructions/s, [4] ALU + FMA interleaved; the rest 0.
+ * bench.py reports the kernels' figures against these measured bounds. */
+int b2s_measure_peaks(int device, double* out8);
 
 /* Layout-identical to cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id */
 typedef struct {

@@ -10,6 +10,23 @@
 
 #include "ORBmatcher.h"
 
+// The same glue also drives the product's drop-in ORBmatcher (self_commit_orb-slam2_b200/host/adapters/ORBmatcher_b200.cc):
+// built with -DB2S_ADAPTER_BUILD into _ref/libadapter_matcher.so, the entry points are adp_* and ORBmatcher:: resolves to
+// the adapter (gather -> libb200slam.so -> scatter) instead of the reference's src/ORBmatcher.cc.
+#ifdef B2S_ADAPTER_BUILD
+#define ref_search_by_bow_kf_f adp_search_by_bow_kf_f
+#define ref_search_by_bow_kf_kf adp_search_by_bow_kf_kf
+#define ref_search_by_projection_map adp_search_by_projection_map
+#define ref_search_by_projection_last adp_search_by_projection_last
+#define ref_search_by_projection_reloc adp_search_by_projection_reloc
+#define ref_search_for_initialization adp_search_for_initialization
+#define ref_search_for_triangulation adp_search_for_triangulation
+#define ref_fuse adp_fuse
+#define ref_search_by_projection_scw adp_search_by_projection_scw
+#define ref_search_by_sim3 adp_search_by_sim3
+#define ref_descriptor_distance adp_descriptor_distance
+#endif
+
 using namespace ORB_SLAM2;
 
 float Frame::fx, Frame::fy, Frame::cx, Frame::cy, Frame::invfx, Frame::invfy;

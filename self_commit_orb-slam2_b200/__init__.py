@@ -668,6 +668,57 @@ class Optimizer:
     def PoseOptimization(self, d):
         return self.PoseOptimizationBatch([d])[0]
 
+    # ---- prepared batches: the ctypes problem / result arrays are built once, a step is then one C call (stream.py)
+    def prepare_pose_batch(self, ds):
+        class PP(ctypes.Structure):
+            _fields_ = [("Tcw", _vp), ("n", ctypes.c_int32), ("has_mp", _vp), ("Xw", _vp), ("kpx", _vp), ("kpy", _vp),
+                        ("uright", _vp), ("inv_sigma2", _vp), ("fx", ctypes.c_float), ("fy", ctypes.c_float),
+                        ("cx", ctypes.c_float), ("cy", ctypes.c_float), ("bf", ctypes.c_float)]
+
+        class PR(ctypes.Structure):
+            _fields_ = [("Tcw_out", _vp), ("outlier", _vp), ("trace", _vp), ("n_inliers", ctypes.c_int32),
+                        ("n_trials", ctypes.c_int32)]
+        B = len(ds)
+        probs, ress, keep = (PP * B)(), (PR * B)(), []
+        for i, d in enumerate(ds):
+            a = [np.ascontiguousarray(d["Tcw"], np.float32).reshape(16), np.ascontiguousarray(d["has_mp"], np.uint8),
+                 np.ascontiguousarray(d["Xw"], np.float32), np.ascontiguousarray(d["kpx"], np.float32),
+                 np.ascontiguousarray(d["kpy"], np.float32), np.ascontiguousarray(d["uright"], np.float32),
+                 np.ascontiguousarray(d["inv_sigma2"], np.float32)]
+            n = len(a[1])
+            o = [np.zeros(16, np.float32), np.zeros(max(n, 1), np.uint8)]
+            keep.append((a, o))
+            probs[i] = PP(a[0].ctypes.data, n, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data, a[4].ctypes.data,
+                          a[5].ctypes.data, a[6].ctypes.data, float(d["fx"]), float(d["fy"]), float(d["cx"]), float(d["cy"]),
+                          float(d["bf"]))
+            ress[i] = PR(o[0].ctypes.data, o[1].ctypes.data, None, 0, 0)
+        L = lib()
+        L.b2s_pose_optimization_batch.argtypes = [_vp, ctypes.c_int, _vp, _vp]
+        return dict(B=B, probs=probs, ress=ress, keep=keep)
+
+    def run_prepared_pose(self, prep):
+        _check(lib().b2s_pose_optimization_batch(self._h, prep["B"], ctypes.cast(prep["probs"], _vp),
+                                                 ctypes.cast(prep["ress"], _vp)))
+        return prep["ress"]
+
+    def prepare_ba_batch(self, ds, its1=5, its2=10):
+        B = len(ds)
+        probs, ress, keeps, outs = (_BaProblem * B)(), (_BaResult * B)(), [], []
+        for i, d in enumerate(ds):
+            p, keep = self._problem(d, its1, its2)
+            r, out = self._result(d)
+            probs[i], ress[i] = p, r
+            keeps.append(keep)
+            outs.append(out)
+        return dict(B=B, probs=probs, ress=ress, keeps=keeps, outs=outs)
+
+    def run_prepared_ba(self, prep):
+        _check(lib().b2s_local_ba_batch(self._h, prep["B"], ctypes.cast(prep["probs"], _vp), ctypes.cast(prep["ress"], _vp)))
+        for i in range(prep["B"]):
+            prep["outs"][i]["chi2"] = prep["ress"][i].chi2_final
+            prep["outs"][i]["n_trials"] = prep["ress"][i].n_trials
+        return prep["outs"]
+
     def LocalBundleAdjustmentBatch(self, ds, its1=5, its2=10):
         B = len(ds)
         probs = (_BaProblem * B)()

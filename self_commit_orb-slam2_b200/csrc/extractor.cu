@@ -142,18 +142,17 @@ __device__ __forceinline__ uint32_t fast_pair_full(const uint32_t (&d)[16]) {
   return (uint32_t)Ml | ((uint32_t)Mh << 16);
 }
 
-__global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t* __restrict__ pyr,
-                                                    const uint32_t* __restrict__ cellInfo,
-                                                    uint32_t* __restrict__ candXY, uint32_t* __restrict__ candKey,
-                                                    uint8_t* __restrict__ candResp, int32_t* __restrict__ candCount,
-                                                    int32_t* __restrict__ status) {
+// one cell, one CTA of 128 threads (every early return is CTA-uniform: it depends on the cell geometry only)
+__device__ __forceinline__ void fast_cell(const ExtractGeom& g, const uint8_t* __restrict__ pyr,
+                                          const uint32_t* __restrict__ cellInfo, uint32_t* __restrict__ candXY,
+                                          uint32_t* __restrict__ candKey, uint8_t* __restrict__ candResp,
+                                          int32_t* __restrict__ candCount, int32_t* __restrict__ status, const int b,
+                                          const int cid) {
   __shared__ __align__(16) uint8_t score[FR * FP];   // arc strength M per pixel, indexed by the ALIGNED column X
   __shared__ __align__(16) uint32_t planeE[FR * PW];  // (P[2i], P[2i+1])   P = pixels of the 4-byte aligned row
   __shared__ __align__(16) uint32_t planeO[FR * PW];  // (P[2i+1], P[2i+2])
   __shared__ uint32_t list[1024];
   __shared__ int sN, sHi, sBase, sEmit, sPass;
-  const int b = blockIdx.y;
-  const int cid = blockIdx.x;
   const uint32_t info = cellInfo[cid];  // level | cell row | cell column (built with the geometry)
   const int l = info >> 28, ci = (info >> 14) & 0x3fff, cj = info & 0x3fff;
   const LevelGeom& L = g.lv[l];
@@ -338,6 +337,37 @@ __global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t
     candKey[cbase + slot] = ((uint32_t)c << 12) | ((uint32_t)(y - 3) << 6) | (uint32_t)(x - 3);
     candResp[cbase + slot] = (uint8_t)(M - 1);
   }
+}
+
+// every cell of every image (the per-stage path, B2S_EXTRACT_PATH=0)
+__global__ void __launch_bounds__(128) k_fast_cells(ExtractGeom g, const uint8_t* __restrict__ pyr,
+                                                    const uint32_t* __restrict__ cellInfo,
+                                                    uint32_t* __restrict__ candXY, uint32_t* __restrict__ candKey,
+                                                    uint8_t* __restrict__ candResp, int32_t* __restrict__ candCount,
+                                                    int32_t* __restrict__ status) {
+  fast_cell(g, pyr, cellInfo, candXY, candKey, candResp, candCount, status, blockIdx.y, blockIdx.x);
+}
+
+// the fused front end's minThFAST fallback: only the cells listed by k_cells (those without a maximum above iniThFAST,
+// src/ORBextractor.cc:1132-1139), persistent CTAs striding over the list
+__global__ void __launch_bounds__(128) k_fast_cells_list(ExtractGeom g, const uint8_t* __restrict__ pyr,
+                                                         const uint32_t* __restrict__ cellInfo,
+                                                         uint32_t* __restrict__ candXY, uint32_t* __restrict__ candKey,
+                                                         uint8_t* __restrict__ candResp, int32_t* __restrict__ candCount,
+                                                         int32_t* __restrict__ status, const uint2* __restrict__ fbList,
+                                                         const int32_t* __restrict__ fbCount) {
+  const int n = *fbCount;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint2 e = fbList[i];  // (image, cell)
+    fast_cell(g, pyr, cellInfo, candXY, candKey, candResp, candCount, status, (int)e.x, (int)e.y);
+    __syncthreads();  // the cell's shared state is reused by the next one
+  }
+}
+
+int launch_fast_fallback(const ExtractGeom& g, const DeviceBuffers& d, int gridCtas, cudaStream_t st) {
+  k_fast_cells_list<<<gridCtas, 128, 0, st>>>(g, d.pyr, d.cellInfo, d.candXY, d.candKey, d.candResp, d.candCount, d.status,
+                                              d.fbList, d.fbCount);
+  return B2S_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1618,6 +1648,15 @@ extern "C" int b2s_extractor_create(int nfeatures, float scaleFactor, int nlevel
   A((void**)&d.pyr, B * pyrBytes);
   A((void**)&d.blur, B * pyrBytes);
   A((void**)&d.score, B * pyrBytes);
+  {
+    size_t bw = 0;  // per level: rows padded to 32, 4 words per 128 columns
+    for (int l = 0; l < nlevels; l++) {
+      const int w = cv_roundf((float)max_width * h->invScale[l]), hh = cv_roundf((float)max_height * h->invScale[l]);
+      bw += (size_t)(div_up(w + 1, 128) * 4) * (size_t)(div_up(hh + 1, 32) * 32);
+    }
+    h->bmWordsAlloc = bw + 1024;
+  }
+  A((void**)&d.bitmap, B * h->bmWordsAlloc * 4);
   h->tileTabAlloc = (size_t)nlevels * (size_t)(div_up(max_width, 32) + div_up(max_height, 32) + 8);
   A((void**)&d.tileDx, h->tileTabAlloc * 2);
   A((void**)&d.tileDy, h->tileTabAlloc * 2);
@@ -1633,6 +1672,8 @@ extern "C" int b2s_extractor_create(int nfeatures, float scaleFactor, int nlevel
   A((void**)&d.status, 4);
   h->cellAlloc = (size_t)(div_up(max_width, 28) + 2) * (size_t)(div_up(max_height, 28) + 2) * 4 + 64;
   A((void**)&d.cellInfo, h->cellAlloc * 4);
+  A((void**)&d.fbList, B * h->cellAlloc * sizeof(uint2));
+  A((void**)&d.fbCount, 4);
   A((void**)&d.rxOfs, h->rxAlloc * 2);
   A((void**)&d.rxAlpha, h->rxAlloc * 4);
   A((void**)&d.ryOfs, h->ryAlloc * 2);
@@ -1671,7 +1712,7 @@ extern "C" void b2s_extractor_destroy(b2s_extractor* h) {
   DeviceBuffers& d = h->d;
   void* ptrs[] = {d.pyr, d.blur, d.candXY, d.candKey, d.candResp, d.candNode, d.candQ, d.candCount, d.selXYR,
                   d.selCount, d.status, d.rxOfs, d.rxAlpha, d.ryOfs, d.ryBeta, d.outKps, d.outDesc, d.outCounts, d.cellInfo,
-                  d.raw, d.score, d.tileDx, d.tileDy};
+                  d.raw, d.score, d.tileDx, d.tileDy, d.bitmap, d.fbList, d.fbCount};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->hKps) cudaFreeHost(h->hKps);

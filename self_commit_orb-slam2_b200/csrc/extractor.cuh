@@ -30,6 +30,7 @@ struct LevelGeom {
   uint32_t rxOff, ryOff;  // resize tables (entries) for producing this level from level-1
   int tilesX, tilesY;     // 128 x 32 tiles of the fused front end (extractor_tile.cu)
   uint32_t tdxOff, tdyOff;  // per tile column / row: first level l+1 column / row whose source sample starts in it
+  uint32_t bmOff;           // word offset of the level inside one image's NMS bitmap
 };
 
 struct ExtractGeom {
@@ -37,6 +38,7 @@ struct ExtractGeom {
   int iniTh, minTh;
   int totalCells, totalCandCap, totalSelCap, totalBlurTiles;
   uint32_t pyrBytes;  // bytes of one image's pyramid
+  uint32_t bmWords;   // words of one image's NMS bitmap (fused front end)
   LevelGeom lv[kMaxLevels];
 };
 
@@ -45,6 +47,9 @@ struct DeviceBuffers {
   uint8_t* blur = nullptr;     // B x pyrBytes
   uint8_t* raw = nullptr;      // B x width*height dense upload staging (host-buffer batch path)
   uint8_t* score = nullptr;    // B x pyrBytes: FAST arc strength of every pixel (fused front end)
+  uint32_t* bitmap = nullptr;  // B x bmWords: 1 bit per pixel, maxima of their cell above minThFAST (fused front end)
+  uint2* fbList = nullptr;     // (image, cell) pairs that need the minThFAST pass (no maximum above iniThFAST)
+  int32_t* fbCount = nullptr;
   int16_t* tileDx = nullptr;   // resize ownership tables of the fused front end
   int16_t* tileDy = nullptr;
   uint32_t* candXY = nullptr;  // B x totalCandCap   (x | y<<16, border-relative)
@@ -72,6 +77,7 @@ struct b2s_extractor;
 namespace b2s {
 int tile_build(b2s_extractor* h);  // tensor maps + resize ownership tables for the current geometry
 int tile_run(b2s_extractor* h, int bBase, int batch, int path, cudaStream_t st, cudaEvent_t evAfterTiles);
+int launch_fast_fallback(const ExtractGeom& g, const DeviceBuffers& d, int gridCtas, cudaStream_t st);  // extractor.cu
 }  // namespace b2s
 
 struct b2s_extractor {
@@ -101,7 +107,7 @@ struct b2s_extractor {
   long long launches = 0;
   // fused front end (extractor_tile.cu): 0 = per-stage kernels, 1 = tile FAST, 2 = + blur, 3 = + pyramid (default)
   int path = 3;
-  size_t tileTabAlloc = 0;
+  size_t tileTabAlloc = 0, bmWordsAlloc = 0;
   alignas(64) unsigned char tmPyr[b2s::kMaxLevels][128];    // CUtensorMap: level images (TMA load, 144 x 38 box)
   alignas(64) unsigned char tmScore[b2s::kMaxLevels][128];  // strength map (TMA store, 128 x 32 box)
   alignas(64) unsigned char tmBlur[b2s::kMaxLevels][128];   // blurred level (TMA store)

@@ -24,7 +24,10 @@ KP_BYTES = keypoint_dtype.itemsize  # 28
 class StereoStream:
     def __init__(self, frames_per_step, width, height, nfeatures=2000, scale=1.2, nlevels=8, ini_th=20, min_th=7,
                  ba_problem=None, ba_every=5, device=0, rank=0, world=1, nnratio=0.7, ba_depth=1,
-                 exchange="boundary"):
+                 exchange="boundary", ba_problems=None, pose_problems=None, stereo=False, bf=386.1448):
+        """ba_problems: list of LocalBA windows (a step solves ceil(F / ba_every) of them, taken round-robin);
+        pose_problems: list of per-frame PoseOptimization problems (F per step, round-robin); stereo: run
+        Frame::ComputeStereoMatches for the F pairs of every step on the resident pyramids."""
         self.F, self.w, self.h = frames_per_step, width, height
         self.rank, self.world = rank, world
         self.dev = torch.device("cuda", device)
@@ -34,17 +37,23 @@ class StereoStream:
                                max_height=max(height, 64), max_batch=2 * self.F, device=device)
         self.cap = self.ex.cap
         self.matcher = ORBmatcher(nnratio, True, max_features=self.cap, max_batch=self.F, device=device)
-        self.ba_problem = ba_problem
+        self.windows = list(ba_problems) if ba_problems else ([ba_problem] if ba_problem is not None else [])
+        self.ba_problem = self.windows[0] if self.windows else None
         self.ba_every = ba_every
-        self.n_ba = (self.F + ba_every - 1) // ba_every if ba_problem is not None else 0
+        self.n_ba = (self.F + ba_every - 1) // ba_every if self.windows else 0
+        self.pose_problems = list(pose_problems) if pose_problems else []
+        self.stereo, self.bf = bool(stereo), float(bf)
         self.opt = None
         self.opts = []
-        if self.n_ba:
+        self._prep = {}
+        if self.n_ba or self.pose_problems:
             # ba_depth solver handles: with depth 2 the host preparation / upload / write-back of one LocalBA batch
             # overlaps the LM kernel of the previous one (pipelined mode only)
+            mk = max([16] + [w["n_kf"] for w in self.windows])
+            mm = max([16] + [len(w["points"]) for w in self.windows])
+            me = max([64] + [len(w["edges"]) for w in self.windows])
             for _ in range(max(1, int(ba_depth))):
-                self.opts.append(Optimizer(max_kf=max(16, ba_problem["n_kf"]), max_mp=len(ba_problem["points"]),
-                                           max_edges=len(ba_problem["edges"]), max_batch=self.n_ba, device=device))
+                self.opts.append(Optimizer(max_kf=mk, max_mp=mm, max_edges=me, max_batch=max(1, self.n_ba), device=device))
             self.opt = self.opts[0]
         F, cap = self.F, self.cap
         S = 1 + 2 * F  # slot 0: the frame before this shard; 1..F left images; F+1..2F right images
@@ -67,6 +76,11 @@ class StereoStream:
             self.g_desc = torch.zeros((world, self.G, cap, 32), dtype=torch.uint8, **z)
             self.g_counts = torch.zeros((world, self.G), dtype=torch.int32, **z)
         self.d_imgs = torch.zeros((2 * F, height, width), dtype=torch.uint8, **z)
+        if self.stereo:  # mvuRight / mvDepth per left feature, matches per pair
+            self.ur = torch.zeros((F, cap), dtype=torch.float32, **z)
+            self.dp = torch.zeros((F, cap), dtype=torch.float32, **z)
+            self.nstereo = torch.zeros(F, dtype=torch.int32, **z)
+        self._step_no = 0
         self._pool = None
         self._ba_future = None
         self._ba_futures = []  # (pipelined) in-flight LocalBA batches, oldest first; at most len(self.opts)
@@ -78,6 +92,19 @@ class StereoStream:
         with torch.cuda.stream(self.stream):
             self.d_imgs.copy_(imgs_host, non_blocking=True)
 
+    def load_window(self, d_all, start):
+        """d_all: device uint8 [2, D, h, w] (left / right images of D resident frames).  Copies frames start .. start+F-1
+        (modulo D) into the step's input batch on the stream (device-to-device, part of the timed step)."""
+        D, F = d_all.shape[1], self.F
+        with torch.cuda.stream(self.stream):
+            done = 0
+            while done < F:
+                a = (start + done) % D
+                n = min(F - done, D - a)
+                self.d_imgs[done:done + n].copy_(d_all[0, a:a + n], non_blocking=True)
+                self.d_imgs[F + done:F + done + n].copy_(d_all[1, a:a + n], non_blocking=True)
+                done += n
+
     def step_device(self, run_ba=True, pipelined=False):
         """Enqueue extraction (+ all-gather) + matching on the stream, then LocalBA of this step's windows.
 
@@ -88,12 +115,42 @@ class StereoStream:
         with torch.cuda.stream(self.stream):
             self._enqueue_extract_match()
         ba_out = None
-        if run_ba and self.n_ba:  # own stream inside the solver; overlaps the work enqueued above
+        if run_ba and (self.n_ba or self.pose_problems):  # own stream inside the solver; overlaps the work enqueued above
             if pipelined:
                 ba_out = self._submit_ba()
             else:
-                ba_out = self.opt.LocalBundleAdjustmentBatch([self.ba_problem] * self.n_ba)
+                ba_out = self._solve(self.opt, self._step_no)
+        self._step_no += 1
         return ba_out
+
+    def _step_windows(self, step):
+        if not self.n_ba:
+            return []
+        n = len(self.windows)
+        return [self.windows[(step * self.n_ba + i) % n] for i in range(self.n_ba)]
+
+    def _step_poses(self, step):
+        if not self.pose_problems:
+            return []
+        n = len(self.pose_problems)
+        return [self.pose_problems[(step * self.F + i) % n] for i in range(self.F)]
+
+    def _solve(self, opt, step):
+        """PoseOptimization of the step's F frames, then LocalBA of its windows, on solver handle `opt`.  The ctypes problem
+        arrays of a (handle, window set) are built once and reused (the per-step Python cost is one C call each)."""
+        out = None
+        poses, wins = self._step_poses(step), self._step_windows(step)
+        if poses:
+            key = ("pose", id(opt), (step * self.F) % len(self.pose_problems) if len(self.pose_problems) > self.F else 0)
+            if key not in self._prep:
+                self._prep[key] = opt.prepare_pose_batch(poses)
+            opt.run_prepared_pose(self._prep[key])
+        if wins:
+            key = ("ba", id(opt), (step * self.n_ba) % len(self.windows) if len(self.windows) > self.n_ba else 0)
+            if key not in self._prep:
+                self._prep[key] = opt.prepare_ba_batch(wins)
+            out = opt.run_prepared_ba(self._prep[key])
+        return out
 
     def _submit_ba(self):
         """Queue this step's LocalBA batch on the next solver handle; returns the result of the batch that used that
@@ -106,7 +163,7 @@ class StereoStream:
             out = self._ba_futures.pop(0).result()
         opt = self.opts[self._ba_next % len(self.opts)]
         self._ba_next += 1
-        self._ba_futures.append(self._pool.submit(opt.LocalBundleAdjustmentBatch, [self.ba_problem] * self.n_ba))
+        self._ba_futures.append(self._pool.submit(self._solve, opt, self._step_no))
         return out
 
     def finish(self):
@@ -122,6 +179,10 @@ class StereoStream:
         self.ex.extract_batch_device(self.d_imgs.data_ptr(), self.w * self.h, 2 * F, self.w, self.h, self.w,
                                      self.kps[1:].data_ptr(), self.desc[1:].data_ptr(), self.counts[1:].data_ptr(), cap,
                                      stream=st)
+        if self.stereo:  # Frame::ComputeStereoMatches, left image i <-> right image F + i, on the resident pyramids
+            self.ex.stereo_match_device(0, F, F, self.kps[1:].data_ptr(), self.desc[1:].data_ptr(),
+                                        self.counts[1:].data_ptr(), cap, self.bf, 0.0, self.ur.data_ptr(), self.dp.data_ptr(),
+                                        self.nstereo.data_ptr(), stream=st)
         if self.world > 1:
             lo = 1 + F - self.G  # first gathered slot: all F left images, or just the last one
             sharding.gather_records(self.kps[lo:1 + F], self.desc[lo:1 + F], self.counts[lo:1 + F], self.g_kps, self.g_desc,
@@ -143,8 +204,9 @@ class StereoStream:
                                           _vp(self.match.data_ptr()), _vp(self.nmatch.data_ptr()), _vp(st)))
 
     # ------------------------------------------------------------------ end-to-end step through the host-buffer C ABI
-    def step_host(self, imgs_host_np, run_ba=True, pipelined=False):
-        """imgs_host_np: numpy uint8 [2F, h, w]. Returns (counts, nmatches, ba_out); everything ends up in host memory."""
+    def step_host(self, imgs_host_np, run_ba=True, pipelined=False, img_ptrs=None):
+        """imgs_host_np: numpy uint8 [2F, h, w] (or img_ptrs: 2F host addresses of dense h x w images, left images first).
+        Returns (counts, nmatches, ba_out); everything ends up in host memory."""
         F, cap = self.F, self.cap
         if getattr(self, "_h_kps", None) is None:  # pinned result buffers, allocated once
             # slot 0 = the frame before the shard's first one (ring), slots 1..2F = this step's images: both sides of the
@@ -162,9 +224,13 @@ class StereoStream:
             self._h_ptrs = (_vp * (2 * F))()
         all_kps, all_desc, all_n = self._h_kps, self._h_desc, self._h_n
         res_kps, res_desc, n = all_kps[1:], all_desc[1:], all_n[1:]
-        base, stride0 = imgs_host_np.ctypes.data, imgs_host_np.strides[0]
-        for i in range(2 * F):
-            self._h_ptrs[i] = base + i * stride0
+        if img_ptrs is not None:
+            for i in range(2 * F):
+                self._h_ptrs[i] = img_ptrs[i]
+        else:
+            base, stride0 = imgs_host_np.ctypes.data, imgs_host_np.strides[0]
+            for i in range(2 * F):
+                self._h_ptrs[i] = base + i * stride0
         L = lib()
         _check(L.b2s_extract_batch(self.ex._h, ctypes.cast(self._h_ptrs, _vp), 2 * F, self.w, self.h, self.w,
                                    res_kps.ctypes.data_as(_vp), res_desc.ctypes.data_as(_vp), cap,
@@ -179,12 +245,22 @@ class StereoStream:
         _check(L.b2s_search_by_bow_batch(self.matcher._h, F, p(all_desc), p(node), p(valid), p(ang), p(all_n), cap,
                                          p(all_desc[1:]), p(node[1:]), None, p(ang[1:]), p(all_n[1:]), cap, 50,
                                          float(self.matcher.mfNNratio), 0, 1, p(match), p(nm)))
+        if self.stereo:  # mvuRight / mvDepth of the F left images, host arrays (the pyramids are still on the device)
+            if getattr(self, "_h_ur", None) is None:
+                self._h_ur = torch.zeros((F, cap), dtype=torch.float32).pin_memory().numpy()
+                self._h_dp = torch.zeros((F, cap), dtype=torch.float32).pin_memory().numpy()
+                self._h_ns = np.zeros(F, np.int32)
+            L.b2s_stereo_match.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, _vp,
+                                           _vp, ctypes.c_int, _vp]
+            _check(L.b2s_stereo_match(self.ex._h, 0, F, F, ctypes.c_float(self.bf), ctypes.c_float(0.0), p(self._h_ur),
+                                      p(self._h_dp), cap, p(self._h_ns)))
         ba_out = None
-        if run_ba and self.n_ba:
+        if run_ba and (self.n_ba or self.pose_problems):
             if pipelined:  # results of an earlier step's windows are returned; finish() joins the rest
                 ba_out = self._submit_ba()
             else:
-                ba_out = self.opt.LocalBundleAdjustmentBatch([self.ba_problem] * self.n_ba)
+                ba_out = self._solve(self.opt, self._step_no)
+        self._step_no += 1
         return n, nm, ba_out, (res_kps, res_desc, match)
 
     def launch_count(self):
@@ -196,15 +272,19 @@ class StereoStream:
     def h2d_bytes_per_step(self):
         b = 2 * self.F * self.w * self.h
         b += self.F * self.cap * (32 + 4 + 4 + 1) * 2  # descriptors, nodes, angles, valid for both sides of the matcher
-        if self.n_ba:
-            pr = self.ba_problem
-            b += self.n_ba * (pr["n_kf"] * 64 + len(pr["points"]) * 12 + len(pr["edges"]) * ba_edge_dtype.itemsize)
+        for pr in self._step_windows(0):
+            b += pr["n_kf"] * 64 + len(pr["points"]) * 12 + len(pr["edges"]) * ba_edge_dtype.itemsize
+        for pp in self._step_poses(0):
+            b += 64 + len(pp["has_mp"]) * (1 + 12 + 4 * 4)
         return int(b)
 
     def d2h_bytes_per_step(self):
         b = 2 * self.F * self.cap * (KP_BYTES + 32) + 2 * self.F * 4
         b += self.F * self.cap * 4 + self.F * 4
-        if self.n_ba:
-            pr = self.ba_problem
-            b += self.n_ba * (pr["n_local"] * 64 + len(pr["points"]) * 12 + len(pr["edges"]))
+        if self.stereo:
+            b += self.F * self.cap * 8 + self.F * 4
+        for pr in self._step_windows(0):
+            b += pr["n_local"] * 64 + len(pr["points"]) * 12 + len(pr["edges"])
+        for pp in self._step_poses(0):
+            b += 64 + len(pp["has_mp"])
         return int(b)

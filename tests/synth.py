@@ -393,3 +393,90 @@ def synth_voc_features(voc, n=2000, seed=5):
     noise = rng.uniform(size=n) < 0.1
     f[noise] = rng.randint(0, 256, size=(int(noise.sum()), 32)).astype(np.uint8)
     return f
+
+
+def synth_local_ba_fast(n_kf=50, n_fixed=10, n_mp=5000, obs_per_mp=6, seed=42, mono_frac=0.0, outlier_frac=0.03):
+    """Vectorised variant of synth_local_ba (same construction: KITTI-shaped forward path, points in the frustum of an
+    anchor keyframe, the obs_per_mp observing keyframes nearest to it, noise ~ 1.2^octave, gross outliers, perturbed
+    initial state) for callers that need many different windows quickly (bench.py).  Not stream-compatible with
+    synth_local_ba: the parity tests keep that one."""
+    rng = np.random.RandomState(seed)
+    fx = fy = 718.856
+    cx, cy, bf = 607.1928, 185.2157, 386.1448
+    W, H = 1241, 376
+    n_local = n_kf - n_fixed
+    yaw = np.deg2rad(rng.uniform(-2, 2, n_kf))
+    c, s = np.cos(yaw), np.sin(yaw)
+    R = np.zeros((n_kf, 3, 3))
+    R[:, 0, 0] = c; R[:, 0, 2] = -s; R[:, 1, 1] = 1; R[:, 2, 0] = s; R[:, 2, 2] = c
+    center = np.stack([rng.uniform(-0.1, 0.1, n_kf), rng.uniform(-0.05, 0.05, n_kf), 1.0 * np.arange(n_kf)], 1)
+    t = -np.einsum("kij,kj->ki", R, center)
+    pts = np.zeros((n_mp, 3))
+    chosen = np.full((n_mp, obs_per_mp), -1, np.int64)
+    todo = np.arange(n_mp)
+    for _ in range(50):
+        if len(todo) == 0:
+            break
+        m = len(todo)
+        ka = rng.randint(0, n_kf, m)
+        z = rng.uniform(5, 60, m)
+        u = rng.uniform(50, W - 50, m)
+        v = rng.uniform(30, H - 30, m)
+        Xc = np.stack([(u - cx) * z / fx, (v - cy) * z / fy, z], 1)
+        Xw = np.einsum("mji,mj->mi", R[ka], Xc - t[ka])
+        Xk = np.einsum("kij,mj->mki", R, Xw) + t[None]          # m x n_kf x 3
+        zz = Xk[..., 2]
+        uu = fx * Xk[..., 0] / np.where(zz > 0, zz, 1) + cx
+        vv = fy * Xk[..., 1] / np.where(zz > 0, zz, 1) + cy
+        vis = (zz >= 2.0) & (uu > 0) & (uu < W) & (vv > 0) & (vv < H)
+        ok = vis.sum(1) >= obs_per_mp
+        dist = np.where(vis, np.abs(np.arange(n_kf)[None] - ka[:, None]), 10 ** 6)
+        near = np.sort(np.argsort(dist, 1, kind="stable")[:, :obs_per_mp], 1)
+        pts[todo[ok]] = Xw[ok]
+        chosen[todo[ok]] = near[ok]
+        todo = todo[~ok]
+    good = chosen[:, 0] >= 0
+    pts, chosen = pts[good], chosen[good]
+    n_mp = len(pts)
+    kf = chosen.reshape(-1)
+    mp = np.repeat(np.arange(n_mp), obs_per_mp)
+    Xk = np.einsum("eij,ej->ei", R[kf], pts[mp]) + t[kf]
+    uu = fx * Xk[:, 0] / Xk[:, 2] + cx
+    vv = fy * Xk[:, 1] / Xk[:, 2] + cy
+    ur = uu - bf / Xk[:, 2]
+    ne = len(kf)
+    octv = rng.randint(0, 8, ne)
+    sig = 1.2 ** octv
+    noise = rng.normal(0, 1, (ne, 3)) * sig[:, None]
+    noise[:, 0] += np.where(rng.uniform(size=ne) < outlier_frac, 30.0, 0.0)
+    mono = rng.uniform(size=ne) < mono_frac
+    Tcw0 = np.zeros((n_kf, 4, 4))
+    Tcw0[:, :3, :3] = R
+    Tcw0[:, :3, 3] = t
+    Tcw0[:, 3, 3] = 1
+    dyaw = np.deg2rad(rng.normal(0, 0.2, n_local))
+    dc, ds = np.cos(dyaw), np.sin(dyaw)
+    dR = np.zeros((n_local, 3, 3))
+    dR[:, 0, 0] = dc; dR[:, 0, 2] = -ds; dR[:, 1, 1] = 1; dR[:, 2, 0] = ds; dR[:, 2, 2] = dc
+    Tcw0[:n_local, :3, :3] = np.einsum("kij,kjl->kil", dR, R[:n_local])
+    Tcw0[:n_local, :3, 3] = np.einsum("kij,kj->ki", dR, t[:n_local]) + rng.normal(0, 0.02, (n_local, 3))
+    pts0 = pts + rng.normal(0, 0.05, pts.shape)
+    fixed = np.zeros(n_kf, np.uint8)
+    fixed[n_local:] = 1
+    fixed[0] = 1
+    edge_dt = np.dtype([("kf", "i4"), ("mp", "i4"), ("obs", "f4", 3), ("inv_sigma2", "f4")])
+    E = np.zeros(ne, edge_dt)
+    E["kf"] = kf
+    E["mp"] = mp
+    E["obs"][:, 0] = (uu + noise[:, 0]).astype(np.float32)
+    E["obs"][:, 1] = (vv + noise[:, 1]).astype(np.float32)
+    E["obs"][:, 2] = np.where(mono, -1.0, ur + noise[:, 2]).astype(np.float32)
+    E["inv_sigma2"] = (1.0 / (1.2 ** (2 * octv))).astype(np.float32)
+    return dict(n_kf=n_kf, n_local=n_local, Tcw=Tcw0.astype(np.float32).reshape(n_kf, 16), fixed=fixed,
+                points=pts0.astype(np.float32), edges=E, fx=np.float32(fx), fy=np.float32(fy), cx=np.float32(cx),
+                cy=np.float32(cy), bf=np.float32(bf))
+
+
+def synth_stereo_kitti(seed):
+    """1241 x 376 stereo pair number `seed` (module-level so that process pools can pickle it)."""
+    return synth_stereo(1241, 376, seed)

@@ -103,27 +103,91 @@ class Keep:
                       self.arr(t.get("cos"), np.float32), self.arr(t.get("level"), np.int32), self.arr(t.get("in_view"), np.uint8))
 
 
+_SIGS = {
+    "ref_search_by_bow_kf_f": [vp, vp, vp, vp, c_f, c_i, vp],
+    "ref_search_by_bow_kf_kf": [vp, vp, vp, vp, c_f, c_i, vp],
+    "ref_search_by_projection_map": [vp, vp, vp, vp, c_i, c_f, c_f, vp],
+    "ref_search_by_projection_last": [vp, vp, vp, vp, c_f, c_i, c_i, vp, vp, vp],
+    "ref_search_for_triangulation": [vp, vp, vp, vp, vp, c_i, c_i, vp, vp],
+    "ref_search_for_initialization": [vp, vp, vp, vp, c_i, c_f, c_i, vp],
+    "ref_search_by_projection_reloc": [vp, vp, vp, vp, vp, c_f, c_i, c_i, vp, vp],
+    "ref_fuse": [vp, vp, vp, vp, c_i, vp, c_f, vp, vp],
+    "ref_search_by_projection_scw": [vp, vp, vp, vp, c_i, vp, vp, c_i, vp, vp],
+    "ref_search_by_sim3": [vp, vp, vp, vp, vp, c_f, vp, vp, c_f, vp, vp, vp],
+    "ref_descriptor_distance": [vp, vp],
+}
+# result arrays of every entry point: (argument index, numpy dtype, element count from the call's arguments); `inout`
+# arrays are restored before the second library runs
+_N = lambda i: (lambda a: a[i]._obj.n)
+_OUTS = {
+    "ref_search_by_bow_kf_f": [(6, np.int32, _N(3))],
+    "ref_search_by_bow_kf_kf": [(6, np.int32, _N(1))],
+    "ref_search_by_projection_map": [(7, np.int32, _N(1))],
+    "ref_search_by_projection_last": [(7, np.int32, _N(1)), (9, np.int32, lambda a: 1)],
+    "ref_search_by_projection_reloc": [(8, np.int32, _N(1))],
+    "ref_search_for_initialization": [(7, np.int32, _N(1)), (3, np.float32, lambda a: 2 * a[1]._obj.n)],
+    "ref_search_for_triangulation": [(7, np.int32, _N(1)), (8, np.float32, lambda a: 2)],
+    "ref_fuse": [(7, np.int32, lambda a: a[4])],
+    "ref_search_by_projection_scw": [(8, np.int32, lambda a: a[4])],
+    "ref_search_by_sim3": [(9, np.int32, _N(1))],
+}
+ADAPTER_LIB = os.path.join(ROOT, "oracle", "_ref", "libadapter_matcher.so")
+
+
+def _view(ptr, dt, n):
+    return np.ctypeslib.as_array((ctypes.c_uint8 * (n * np.dtype(dt).itemsize)).from_address(int(ptr))).view(dt)
+
+
+class _RefAndAdapter:
+    """The reference's ORBmatcher (libref_matcher.so) and — when a CUDA device is present — the product's drop-in
+    ORBmatcher with the same C++ signatures (host/adapters/ORBmatcher_b200.cc in libadapter_matcher.so), driven by the
+    same glue on the same stand-in objects: every ref_* call is repeated as adp_* and must return the same count and the
+    same result arrays."""
+
+    def __init__(self, R, A):
+        self.R, self.A = R, A
+        self.adapter_calls = 0
+
+    def __getattr__(self, name):
+        fr = getattr(self.R, name)
+        if self.A is None or name not in _OUTS:
+            return fr
+        fa = getattr(self.A, "adp_" + name[4:])
+
+        def both(*args):
+            outs = [(_view(args[i], dt, cnt(args)), i) for i, dt, cnt in _OUTS[name]]
+            before = [o.copy() for o, _ in outs]
+            nr = fr(*args)
+            want = [o.copy() for o, _ in outs]
+            for (o, _), b0 in zip(outs, before):
+                o[...] = b0
+            na = fa(*args)
+            self.adapter_calls += 1
+            assert na == nr, "%s: the adapter returns %d, the reference %d" % (name, na, nr)
+            for (o, i), w in zip(outs, want):
+                assert np.array_equal(o, w), "%s: result array (argument %d) differs between adapter and reference" % (name, i)
+            return nr
+        return both
+
+
 @pytest.fixture(scope="module")
-def ref():
+def ref(request):
     R = ctypes.CDLL(LIB)
-    for name in ("ref_search_by_bow_kf_f", "ref_search_by_bow_kf_kf", "ref_search_by_projection_map",
-                 "ref_search_by_projection_last", "ref_search_for_triangulation", "ref_fuse", "ref_search_by_projection_scw",
-                 "ref_search_by_sim3", "ref_descriptor_distance"):
+    A = None
+    if os.path.exists(ADAPTER_LIB):
+        try:
+            pkg = request.getfixturevalue("pkg")
+            if pkg.device_count() > 0:
+                A = ctypes.CDLL(ADAPTER_LIB)
+        except Exception:
+            A = None
+    for name, sig in _SIGS.items():
         getattr(R, name).restype = ctypes.c_int
-    R.ref_search_by_bow_kf_f.argtypes = [vp, vp, vp, vp, c_f, c_i, vp]
-    R.ref_search_by_bow_kf_kf.argtypes = [vp, vp, vp, vp, c_f, c_i, vp]
-    R.ref_search_by_projection_map.argtypes = [vp, vp, vp, vp, c_i, c_f, c_f, vp]
-    R.ref_search_by_projection_last.argtypes = [vp, vp, vp, vp, c_f, c_i, c_i, vp, vp, vp]
-    R.ref_search_for_triangulation.argtypes = [vp, vp, vp, vp, vp, c_i, c_i, vp, vp]
-    R.ref_search_for_initialization.restype = ctypes.c_int
-    R.ref_search_for_initialization.argtypes = [vp, vp, vp, vp, c_i, c_f, c_i, vp]
-    R.ref_search_by_projection_reloc.restype = ctypes.c_int
-    R.ref_search_by_projection_reloc.argtypes = [vp, vp, vp, vp, vp, c_f, c_i, c_i, vp, vp]
-    R.ref_fuse.argtypes = [vp, vp, vp, vp, c_i, vp, c_f, vp, vp]
-    R.ref_search_by_projection_scw.argtypes = [vp, vp, vp, vp, c_i, vp, vp, c_i, vp, vp]
-    R.ref_search_by_sim3.argtypes = [vp, vp, vp, vp, vp, c_f, vp, vp, c_f, vp, vp, vp]
-    R.ref_descriptor_distance.argtypes = [vp, vp]
-    return R
+        getattr(R, name).argtypes = sig
+        if A is not None:
+            getattr(A, "adp_" + name[4:]).restype = ctypes.c_int
+            getattr(A, "adp_" + name[4:]).argtypes = sig
+    return _RefAndAdapter(R, A)
 
 
 def B(x):
