@@ -469,7 +469,7 @@ def run_b200(args, rank, local_rank, world):
     ba_kernel_ms, ba_trials = 0.0, 0
     try:
         t1 = time.perf_counter()
-        pr = ss.opt.PoseOptimizationBatch(poses)
+        pr = ss.pose_opt.PoseOptimizationBatch(poses)
         phase["pose_optimization_batch_ms"] = (time.perf_counter() - t1) * 1e3
         phase["pose_optimization_inliers_per_frame"] = float(np.mean([r["n_inliers"] for r in pr]))
         t1 = time.perf_counter()

@@ -55,6 +55,10 @@ class StereoStream:
             for _ in range(max(1, int(ba_depth))):
                 self.opts.append(Optimizer(max_kf=mk, max_mp=mm, max_edges=me, max_batch=max(1, self.n_ba), device=device))
             self.opt = self.opts[0]
+            # PoseOptimization has its own handle (own stream, own worker thread): the Tracking-side solver does not queue
+            # behind the LocalMapping-side one
+            self.pose_opt = Optimizer(max_kf=4, max_mp=16, max_edges=64, max_batch=max(1, self.F), device=device) \
+                if self.pose_problems else None
         F, cap = self.F, self.cap
         S = 1 + 2 * F  # slot 0: the frame before this shard; 1..F left images; F+1..2F right images
         z = dict(device=self.dev)
@@ -119,6 +123,7 @@ class StereoStream:
             if pipelined:
                 ba_out = self._submit_ba()
             else:
+                self._solve_pose(self._step_no)
                 ba_out = self._solve(self.opt, self._step_no)
         self._step_no += 1
         return ba_out
@@ -139,12 +144,7 @@ class StereoStream:
         """PoseOptimization of the step's F frames, then LocalBA of its windows, on solver handle `opt`.  The ctypes problem
         arrays of a (handle, window set) are built once and reused (the per-step Python cost is one C call each)."""
         out = None
-        poses, wins = self._step_poses(step), self._step_windows(step)
-        if poses:
-            key = ("pose", id(opt), (step * self.F) % len(self.pose_problems) if len(self.pose_problems) > self.F else 0)
-            if key not in self._prep:
-                self._prep[key] = opt.prepare_pose_batch(poses)
-            opt.run_prepared_pose(self._prep[key])
+        wins = self._step_windows(step)
         if wins:
             key = ("ba", id(opt), (step * self.n_ba) % len(self.windows) if len(self.windows) > self.n_ba else 0)
             if key not in self._prep:
@@ -152,18 +152,32 @@ class StereoStream:
             out = opt.run_prepared_ba(self._prep[key])
         return out
 
+    def _solve_pose(self, step):
+        poses = self._step_poses(step)
+        if not poses:
+            return None
+        key = ("pose", (step * self.F) % len(self.pose_problems) if len(self.pose_problems) > self.F else 0)
+        if key not in self._prep:
+            self._prep[key] = self.pose_opt.prepare_pose_batch(poses)
+        return self.pose_opt.run_prepared_pose(self._prep[key])
+
     def _submit_ba(self):
         """Queue this step's LocalBA batch on the next solver handle; returns the result of the batch that used that
         handle before (or None)."""
         if self._pool is None:
             from concurrent.futures import ThreadPoolExecutor
-            self._pool = ThreadPoolExecutor(max_workers=len(self.opts))
+            self._pool = ThreadPoolExecutor(max_workers=len(self.opts) + 1)
+            self._pose_future = None
         out = None
         if len(self._ba_futures) >= len(self.opts):
             out = self._ba_futures.pop(0).result()
         opt = self.opts[self._ba_next % len(self.opts)]
         self._ba_next += 1
         self._ba_futures.append(self._pool.submit(self._solve, opt, self._step_no))
+        if self.pose_problems:  # one PoseOptimization batch in flight, on its own handle / thread
+            if self._pose_future is not None:
+                self._pose_future.result()
+            self._pose_future = self._pool.submit(self._solve_pose, self._step_no)
         return out
 
     def finish(self):
@@ -171,6 +185,9 @@ class StereoStream:
         out = None
         while self._ba_futures:
             out = self._ba_futures.pop(0).result()
+        if getattr(self, "_pose_future", None) is not None:
+            self._pose_future.result()
+            self._pose_future = None
         return out
 
     def _enqueue_extract_match(self):
@@ -259,6 +276,7 @@ class StereoStream:
             if pipelined:  # results of an earlier step's windows are returned; finish() joins the rest
                 ba_out = self._submit_ba()
             else:
+                self._solve_pose(self._step_no)
                 ba_out = self._solve(self.opt, self._step_no)
         self._step_no += 1
         return n, nm, ba_out, (res_kps, res_desc, match)
@@ -267,6 +285,8 @@ class StereoStream:
         c = self.ex.launch_count() + self.matcher.launch_count()
         for o in self.opts:
             c += o.launch_count()
+        if getattr(self, "pose_opt", None) is not None:
+            c += self.pose_opt.launch_count()
         return c
 
     def h2d_bytes_per_step(self):

@@ -135,7 +135,8 @@ ADAPTER_LIB = os.path.join(ROOT, "oracle", "_ref", "libadapter_matcher.so")
 
 
 def _view(ptr, dt, n):
-    return np.ctypeslib.as_array((ctypes.c_uint8 * (n * np.dtype(dt).itemsize)).from_address(int(ptr))).view(dt)
+    addr = ctypes.addressof(ptr._obj) if hasattr(ptr, "_obj") else int(ptr)  # byref(x) or a raw address
+    return np.ctypeslib.as_array((ctypes.c_uint8 * (n * np.dtype(dt).itemsize)).from_address(addr)).view(dt)
 
 
 class _RefAndAdapter:
