@@ -11,6 +11,8 @@
 // Work is dealt dynamically to `threads` host threads, longest tasks first; every frame task runs the two extractor
 // threads the reference itself spawns (src/Frame.cc:159-167).  Per-stage busy time is accumulated so that the bench line
 // can report utilisation and per-stage milliseconds.  Built into oracle/_ref/libref_stream2.so; never part of the product.
+#include <malloc.h>
+
 #include <atomic>
 #include <chrono>
 #include <cstdint>
@@ -57,6 +59,17 @@ double ref_stream2_step(const ref_stream2_cfg* cfg, const uint8_t* imgs, int S, 
                         const orc_ba_problem* ba, int nBa, ba_fn_t ba_fn, const orc_pose_problem* pose, int nPose,
                         pose_fn_t pose_fn, double* stats) {
   if (threads < 1) threads = 1;
+  {
+    // The reference allocates its pyramids / descriptor matrices per frame; with one frame per host thread in flight, glibc's
+    // default of serving every block above 128 KB with mmap / munmap serialises all threads on the kernel's address-space
+    // lock (measured: 5-9x longer tasks at 128 threads).  Keep big blocks in the per-thread arenas instead.
+    static bool tuned = false;
+    if (!tuned) {
+      mallopt(M_MMAP_THRESHOLD, 1 << 30);
+      mallopt(M_TRIM_THRESHOLD, 1 << 30);
+      tuned = true;
+    }
+  }
   {
     std::lock_guard<std::mutex> lock(g_exMutex);
     while ((int)g_extractors.size() < 2 * threads)
@@ -133,7 +146,8 @@ double ref_stream2_step(const ref_stream2_cfg* cfg, const uint8_t* imgs, int S, 
             kf.N = prev.N;
             kf.mvKeysUn = prev.mvKeysUn;
             kf.mvKeys = prev.mvKeys;
-            kf.mDescriptors = prev.mDescriptors;
+            kf.mDescriptors = prev.mDescriptors.clone();  // own buffer: cv::Mat::row() bumps the buffer's atomic reference
+                                                          // count per call, which two tasks must not share
             std::vector<MapPoint> pts((size_t)prev.N);
             kf.mvpMapPoints.resize((size_t)prev.N);
             std::vector<unsigned int>& allK = kf.mFeatVec[0];

@@ -216,13 +216,23 @@ __device__ __forceinline__ void win_barrier(unsigned int* bar, unsigned int& epo
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(bar, 1u);
+    // the CTAs of a cooperative launch are co-resident, so the wait always ends; the timeout only guards against a
+    // wedged partner and is generous (20 s of wall time on %globaltimer, checked every 1024 polls): preemption,
+    // time-slicing with another process or a profiler replay must not turn a slow barrier into a failed batch
     unsigned int spins = 0;
+    unsigned long long t0 = 0;
     while (ld_acquire_u32(bar) < epoch) {
       __nanosleep(20);
       if (*hung) break;
-      if (++spins > (1u << 24)) {  // ~1 s
-        *hung = 1;
-        break;
+      if ((++spins & 1023u) == 0u) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0)
+          t0 = now;
+        else if (now - t0 > 20000000000ull) {
+          *hung = 1;
+          break;
+        }
       }
     }
     __threadfence();
@@ -1186,8 +1196,8 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
   const int n = W.nFree * 6, ld = p.ldS;
   double* S = p.S + (size_t)w * ld * ld;
   double* Dblk = dsm;                                // 33 x 33 (last row: reciprocal diagonal)
-  double* panel = dsm + (CHOL_BS + 1) * CHOL_PP;     // (ld+4) x 33
-  double* xs = panel + (size_t)(ld + 4) * CHOL_PP;   // ld
+  double* panel = dsm + (CHOL_BS + 1) * CHOL_PP;     // (ld+8) x 33
+  double* xs = panel + (size_t)(ld + 8) * CHOL_PP;   // ld
   double* rdiag = xs + ld;                           // ld: 1 / L[i][i], kept for the back substitution
   int* rowList = reinterpret_cast<int*>(rdiag + ld);  // ld + 4 ints: compacted row list of the current block column
   int* bfirst = rowList + ld + 4;                     // nFree ints: first non-empty block of every block row (envelope)
@@ -1273,46 +1283,42 @@ __device__ void phase_chol(const BaPtrs& p, int w, const BaWin& W, double* dsm) 
         if (cc < wd) S[(size_t)i * ld + kb + cc] = v[cc];
       }
     }
-    for (int idx = tid; idx < 4 * CHOL_PP; idx += T) panel[(m + idx / CHOL_PP) * CHOL_PP + idx % CHOL_PP] = 0.0;
+    for (int idx = tid; idx < 8 * CHOL_PP; idx += T) panel[(m + idx / CHOL_PP) * CHOL_PP + idx % CHOL_PP] = 0.0;  // pad to a multiple of 8 rows
     __syncthreads();
     CH_PROF(12)
-    const int mt = (m + 3) >> 2;
-    const int ntile = mt * (mt + 1) / 2;
-    for (int t = tid; t < ntile; t += T) {
-      int ti, tj;
-      decode_block(t, ti, tj);
-      double acc[4][4];
+    // trailing update S[i][j] -= sum_k panel[i][k] * panel[j][k] on the FP64 tensor pipe: one warp per 8 x 8 tile of the
+    // (compacted) row list, eight DMMA.8x8x4 per tile (k = 32), fragments loaded straight from the panel in shared memory.
+    // mma.m8n8k4 f64 fragments: A[g][t] and B[t][g] one value per lane (g = lane / 4, t = lane % 4), C[g][2t], C[g][2t+1].
+    {
+      const int mt = (m + 7) >> 3;
+      const int ntile = mt * (mt + 1) / 2;
+      const int warp = tid >> 5, nwarp = T >> 5;
+      const int g = lane >> 2, t4 = lane & 3;
+      for (int t = warp; t < ntile; t += nwarp) {
+        int ti, tj;
+        decode_block(t, ti, tj);
+        const double* pa = panel + (size_t)(8 * ti + g) * CHOL_PP + t4;
+        const double* pb = panel + (size_t)(8 * tj + g) * CHOL_PP + t4;
+        double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-      for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b2 = 0; b2 < 4; b2++) acc[a][b2] = 0;
-      const double* pa = panel + (size_t)(4 * ti) * CHOL_PP;
-      const double* pb = panel + (size_t)(4 * tj) * CHOL_PP;
-#pragma unroll 8
-      for (int k = 0; k < CHOL_BS; k++) {
-        double av[4], bv[4];
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-          av[a] = pa[a * CHOL_PP + k];
-          bv[a] = pb[a * CHOL_PP + k];
+        for (int k0 = 0; k0 < CHOL_BS; k0 += 4) {
+          const double av = pa[k0], bv = pb[k0];
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                       : "+d"(c0), "+d"(c1)
+                       : "d"(av), "d"(bv));
         }
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-          for (int b2 = 0; b2 < 4; b2++) acc[a][b2] += av[a] * bv[b2];
-      }
-#pragma unroll
-      for (int a = 0; a < 4; a++) {
-        const int ia = 4 * ti + a;
-        if (ia >= m) continue;
-        const int i = rowList[ia];
-#pragma unroll
-        for (int b2 = 0; b2 < 4; b2++) {
-          const int jb = 4 * tj + b2;
-          if (jb > ia) continue;  // lower triangle only (the list is ascending)
-          const int j = rowList[jb];
-          if (j >= n) continue;   // column n is never needed
-          S[(size_t)i * ld + j] -= acc[a][b2];
+        const int ia = 8 * ti + g;
+        if (ia < m) {
+          const int i = rowList[ia];
+          const int jb0 = 8 * tj + 2 * t4;
+          if (jb0 <= ia) {  // lower triangle only (the list is ascending); column n is never needed
+            const int j = rowList[jb0];
+            if (j < n) S[(size_t)i * ld + j] -= c0;
+          }
+          if (jb0 + 1 <= ia) {
+            const int j = rowList[jb0 + 1];
+            if (j < n) S[(size_t)i * ld + j] -= c1;
+          }
         }
       }
     }
@@ -2351,7 +2357,7 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   HA(&s.eObs, B * max_edges * 12); HA(&s.eW, B * max_edges * 4);
   HA(&s.eSt, B * max_edges); HA(&s.eOutlier, B * max_edges);
   HA(&s.win, B * sizeof(BaWin)); HA(&s.st, B * sizeof(BaState));
-  h->smemBytes = (size_t)((CHOL_BS + 1) * CHOL_PP + (size_t)(d.ldS + 4) * CHOL_PP + 2 * d.ldS) * 8 + (size_t)(d.ldS + 8 + max_kf) * 4;
+  h->smemBytes = (size_t)((CHOL_BS + 1) * CHOL_PP + (size_t)(d.ldS + 8) * CHOL_PP + 2 * d.ldS) * 8 + (size_t)(d.ldS + 8 + max_kf) * 4;
   h->smemBytes = std::max(h->smemBytes, (size_t)(BA_T / 32) * 30 * 33 * 8);  // per-warp staging tiles of phase_build_edges
   h->smemBytes = std::max(h->smemBytes, (size_t)(BA_T / 32) * 2 * GATHER_TILE16 * 16  // double-buffered gather tiles (Schur)
                                             + (size_t)max_kf * 12 * 8);                  // + R|t table (back-substitution)
@@ -2560,6 +2566,10 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
     int dbgRepeat = 0;
     if (const char* ev = getenv("B2S_BA_REPEAT")) dbgRepeat = atoi(ev);  // profiling aid, see k_local_ba
     void* args[] = {(void*)&d, (void*)&nCta, (void*)&wBase, (void*)&dbgRepeat};
+    // the attribute is per FUNCTION, not per handle: another solver handle (different capacities) may have set a smaller
+    // limit since this one was created, which makes the cooperative launch fail with "too many blocks"
+    if (h->smemBytes > 48 * 1024)
+      B2S_CUDA(cudaFuncSetAttribute(k_local_ba, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
     B2S_CUDA(cudaLaunchCooperativeKernel((const void*)k_local_ba, dim3(nw * nCta), dim3(BA_T), args, h->smemBytes, st));
     h->launches++;
   }

@@ -84,7 +84,7 @@ __device__ __forceinline__ int rot_bin(float angA, float angB) {
 __global__ void k_rank_by_key(const int32_t* __restrict__ keyBase, const int32_t* __restrict__ nArr, int cap,
                               int32_t* __restrict__ orderBase) {
   const int pair = blockIdx.y;
-  const int n = nArr[pair];
+  const int n = min(nArr[pair], cap);  // counts come from device memory (another rank's record, a caller's array): never past the slice
   const int32_t* key = keyBase + (size_t)pair * cap;
   int32_t* order = orderBase + (size_t)pair * cap;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) k_bow_topk(const uint8_t* __restrict__ de
   __shared__ __align__(16) int32_t sNode[BOW_TILE];
   __shared__ __align__(16) uint8_t sValid[BOW_TILE];
   const int pair = blockIdx.y;
-  const int nA = nAarr[pair], nB = nBarr[pair];
+  const int nA = min(nAarr[pair], capA), nB = min(nBarr[pair], capB);  // (clamped: device-side counts are untrusted)
   if ((int)(blockIdx.x * blockDim.x) >= nA) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t oa = (size_t)pair * capA, ob = (size_t)pair * capB;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(128) k_bow_resolve(const uint8_t* __restrict__
                                                      const int32_t* __restrict__ candCnt, MatchParams mp,
                                                      int32_t* matchB, int32_t* __restrict__ binB) {
   const int pair = blockIdx.y;
-  const int nA = nAarr[pair], nB = nBarr[pair];
+  const int nA = min(nAarr[pair], capA), nB = min(nBarr[pair], capB);  // (clamped: device-side counts are untrusted)
   const int lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r0 >= nA) return;
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) k_rot_cull(const int32_t* __restrict__ nB
   __shared__ int keep[3];
   __shared__ int total, culled;
   const int pair = blockIdx.x;
-  const int nB = nBarr[pair];
+  const int nB = min(nBarr[pair], capB);
   int32_t* mB = matchB + (size_t)pair * capB;
   const int32_t* bB = binB + (size_t)pair * capB;
   if (threadIdx.x < HISTO) hist[threadIdx.x] = 0;

@@ -52,13 +52,13 @@ class StereoStream:
             mk = max([16] + [w["n_kf"] for w in self.windows])
             mm = max([16] + [len(w["points"]) for w in self.windows])
             me = max([64] + [len(w["edges"]) for w in self.windows])
+            # PoseOptimization has its own handle (own stream, own worker thread): the Tracking-side solver does not queue
+            # behind the LocalMapping-side one.  (Created first: see the shared-memory attribute note in b2s_ba_create.)
+            self.pose_opt = Optimizer(max_kf=4, max_mp=16, max_edges=64, max_batch=max(1, self.F), device=device) \
+                if self.pose_problems else None
             for _ in range(max(1, int(ba_depth))):
                 self.opts.append(Optimizer(max_kf=mk, max_mp=mm, max_edges=me, max_batch=max(1, self.n_ba), device=device))
             self.opt = self.opts[0]
-            # PoseOptimization has its own handle (own stream, own worker thread): the Tracking-side solver does not queue
-            # behind the LocalMapping-side one
-            self.pose_opt = Optimizer(max_kf=4, max_mp=16, max_edges=64, max_batch=max(1, self.F), device=device) \
-                if self.pose_problems else None
         F, cap = self.F, self.cap
         S = 1 + 2 * F  # slot 0: the frame before this shard; 1..F left images; F+1..2F right images
         z = dict(device=self.dev)
