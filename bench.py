@@ -113,6 +113,27 @@ def pose_problems(n, seed0=0):
     return out
 
 
+def effective_cpus():
+    """Host CPUs this process can actually use: the logical CPU count capped by the cgroup CPU quota (the GPU boxes expose
+    128 logical CPUs under a 16-CPU quota: 128 busy threads there are time-sliced onto 16 CPUs' worth of time)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    eff = n if quota is None else max(1, min(n, int(quota + 0.999)))
+    return eff, n, quota
+
+
 def load_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -307,7 +328,7 @@ def cv2_extract_ratio():
 
 def cpu_arm_measure(S, steps, warmup, seed0=0, with_cv2=True):
     """`steps` timed steps of S stereo frames each on all host threads; returns the fields of the reference line."""
-    threads = os.cpu_count() or 1
+    threads, logical, quota = effective_cpus()
     arm = CpuArm()
     windows = ba_windows((S + BA_EVERY - 1) // BA_EVERY, seed0)
     poses = pose_problems(S, seed0)
@@ -327,17 +348,19 @@ def cpu_arm_measure(S, steps, warmup, seed0=0, with_cv2=True):
     stage = {"frame_extract_stereo_ms_per_frame": 1e3 * busy[0] / (S * steps), "search_by_bow_ms_per_frame": 1e3 * busy[1] / (S * steps),
              "pose_optimization_ms_per_frame": 1e3 * busy[2] / (S * steps),
              "local_ba_ms_per_window": 1e3 * busy[3] / max(1, len(windows) * steps)}
-    return {"fps": fps, "threads": threads, "seconds": tot, "S": S, "tasks_per_step": 2 * S + len(windows) + len(poses),
+    return {"fps": fps, "threads": threads, "logical_cpus": logical, "cgroup_cpu_quota": quota, "seconds": tot, "S": S, "tasks_per_step": 2 * S + len(windows) + len(poses),
             "utilisation": float(busy.sum() / (threads * tot)), "stage_ms_single_thread": stage, "solvers": info,
             "keypoints_per_image": last[4], "stereo_matches_per_frame": last[5], "bow_matches_per_frame": last[6],
             "cv2": cv2_extract_ratio() if with_cv2 else None}
 
 
 def cpu_sample_text(m):
-    return ("%d stereo frames per step (%d tasks on %d host threads, %.1f s timed, utilisation %.0f %%): reference's own Frame "
+    return ("%d stereo frames per step (%d tasks on %d host threads = the usable CPUs [%d logical, cgroup quota %s], %.1f s timed, "
+            "utilisation %.0f %%): reference's own Frame "
             "constructor (ORBextractor.cc x2 threads + ComputeStereoMatches), ORBmatcher::SearchByBoW, PoseOptimization [%s], "
             "LocalBundleAdjustment [%s]; OpenCV primitives = scalar stand-in (cv2 is %sx faster on pyramid+FAST+blur)"
-            % (m["S"], m["tasks_per_step"], m["threads"], m["seconds"], 100 * m["utilisation"], m["solvers"]["pose_impl"],
+            % (m["S"], m["tasks_per_step"], m["threads"], m["logical_cpus"], m["cgroup_cpu_quota"], m["seconds"],
+               100 * m["utilisation"], m["solvers"]["pose_impl"],
                m["solvers"]["local_ba_impl"], ("%.1f" % m["cv2"]["ratio"]) if m.get("cv2") else "n/a "))
 
 
@@ -387,7 +410,7 @@ def run_b200(args, rank, local_rank, world):
     windows = ba_windows(n_ba, seed0=1000 * rank)
     poses = pose_problems(F, seed0=1000 * rank)
     if world > 1:  # several ranks share the host cores: split them for the LocalBA window preparation threads
-        os.environ.setdefault("B2S_BA_HOST_THREADS", str(max(2, min(16, (os.cpu_count() or 16) // world))))
+        os.environ.setdefault("B2S_BA_HOST_THREADS", str(max(2, min(16, effective_cpus()[0] // world))))
     ss = stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, ba_problems=windows, pose_problems=poses, stereo=True, ba_every=BA_EVERY,
                                  device=local_rank, rank=rank, world=world, ba_depth=args.ba_depth, exchange=args.exchange)
     imgs = make_stream_images(D, seed0=100000 * rank)  # [2, D, h, w], frame index = seed
@@ -623,7 +646,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="boundary", choices=["boundary", "all"],
                     help="NCCL all-gather of the shard-boundary left-image record only, or of every left-image record")
-    ap.add_argument("--ba-depth", type=int, default=int(os.environ.get("B2S_BA_DEPTH", "1")),
+    ap.add_argument("--ba-depth", type=int, default=int(os.environ.get("B2S_BA_DEPTH", "2")),
                     help="LocalBA solver handles used round-robin by the pipelined stream (host work of batch i+1 overlaps the kernel of batch i)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

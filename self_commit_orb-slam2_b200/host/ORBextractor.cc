@@ -35,9 +35,11 @@ void ORBextractor::EnsureHandle(int width, int height) {
   int rc = b2s_extractor_create(nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST, std::max(64, mMaxW),
                                 std::max(64, mMaxH), 1, pick_device(), &mpHandle);
   if (rc != B2S_OK) {
-    // The reference has no error channel here; failing loudly beats silently falling back to a CPU path.
+    // The reference has neither exceptions nor return codes here: report on stderr and leave the handle
+    // empty; operator() then returns no keypoints, like the reference does for an empty image.  There is no CPU fallback.
     fprintf(stderr, "ORBextractor: libb200slam error %d: %s\n", rc, b2s_last_error());
-    throw std::runtime_error(b2s_last_error());
+    mpHandle = nullptr;
+    return;
   }
   mvScaleFactor.resize(nlevels);
   mvInvScaleFactor.resize(nlevels);
@@ -60,6 +62,11 @@ void ORBextractor::operator()(b2s_cv::InputArray _image, b2s_cv::InputArray /*_m
   if (image.empty()) return;
 #endif
   EnsureHandle(image.cols, image.rows);
+  if (!mpHandle) {  // no device / allocation failure (reported above): no keypoints
+    _keypoints.clear();
+    _descriptors.release();
+    return;
+  }
   std::vector<uint8_t*> pyr(nlevels, nullptr);
   if (mbDownloadPyramid) {
     for (int l = 0; l < nlevels; l++) {
@@ -80,7 +87,9 @@ void ORBextractor::operator()(b2s_cv::InputArray _image, b2s_cv::InputArray /*_m
                        mbDownloadPyramid ? pyr.data() : nullptr);
   if (rc != B2S_OK) {
     fprintf(stderr, "ORBextractor::operator(): libb200slam error %d: %s\n", rc, b2s_last_error());
-    throw std::runtime_error(b2s_last_error());
+    _keypoints.clear();
+    _descriptors.release();
+    return;
   }
   _keypoints.clear();
   _keypoints.resize(n);

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <vector>
 
 namespace ORB_SLAM2 {
 
@@ -16,16 +17,41 @@ static void fail(const char* where, int rc) {
   throw std::runtime_error(b2s_last_error());
 }
 
+// ORBmatcher objects are stack temporaries in the reference (one per call site, several per tracked frame); the device
+// handle — a stream and ~30 device buffers — is therefore owned by the calling THREAD, not by the object: created on
+// first use, grown on demand, kept until the thread exits.  Handles that were outgrown stay alive as well, because a
+// FrameGrid built on one of them must remain usable.
+namespace {
+struct ThreadHandles {
+  std::vector<b2s_matcher*> all;
+  b2s_matcher* cur = nullptr;
+  int cap = 0;
+  ~ThreadHandles() {
+    for (b2s_matcher* h : all) b2s_matcher_destroy(h);
+  }
+};
+ThreadHandles& thread_handles() {
+  static thread_local ThreadHandles t;
+  return t;
+}
+}  // namespace
+
 ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
-ORBmatcher::~ORBmatcher() { b2s_matcher_destroy(mpHandle); }
+ORBmatcher::~ORBmatcher() {}  // the handle belongs to the thread
 
 void ORBmatcher::Ensure(int n) {
-  if (mpHandle && n <= mCap) return;
-  b2s_matcher_destroy(mpHandle);
-  mpHandle = nullptr;
-  mCap = n < 4096 ? 4096 : n;
-  int rc = b2s_matcher_create(mCap, 1, dev(), &mpHandle);
-  if (rc != B2S_OK) fail("ORBmatcher", rc);
+  ThreadHandles& t = thread_handles();
+  if (!t.cur || n > t.cap) {
+    const int cap = n < 4096 ? 4096 : n;
+    b2s_matcher* h = nullptr;
+    int rc = b2s_matcher_create(cap, 1, dev(), &h);
+    if (rc != B2S_OK) fail("ORBmatcher", rc);
+    t.all.push_back(h);
+    t.cur = h;
+    t.cap = cap;
+  }
+  mpHandle = t.cur;
+  mCap = t.cap;
 }
 
 int ORBmatcher::DescriptorDistance(const uint8_t* a, const uint8_t* b) {
