@@ -174,6 +174,25 @@ int b2s_search_by_projection_last(b2s_matcher* h, const b2s_proj_query* q, int n
                                   const uint8_t* occupied, const uint8_t* desc, int nf, const b2s_frame_geom* g, float th,
                                   int mode, int th_high, int check_ori, int32_t* match_cur, int* nmatches);
 
+/* Batched, device-resident form for a sequence (the stream mode of SURVEY.md 8d / 8e): pair b matches the queries
+ * d_q[b*capQ .. +d_nq[b]) against the current frame b given as the extractor's device records (d_kps, d_desc: stride capF
+ * entries per pair, d_nf[b] valid) and the stereo matcher's d_uright.  Same candidate order, thresholds, greedy resolution and
+ * rotation culling as b2s_search_by_projection_last (occupied = none: the current frame holds no MapPoint yet,
+ * src/Tracking.cc:881-883).  d_match_cur: [batch][capF], d_nmatches: [batch].  Asynchronous on `stream` (NULL = the
+ * matcher's own stream); needs batch <= max_batch and capQ, capF <= max_features of b2s_matcher_create. */
+int b2s_search_by_projection_last_device(b2s_matcher* h, int batch, const b2s_proj_query* d_q, const int32_t* d_nq, int capQ,
+                                         const b2s_keypoint* d_kps, const float* d_uright, const uint8_t* d_desc,
+                                         const int32_t* d_nf, int capF, const b2s_frame_geom* g, float th, int mode,
+                                         int th_high, int check_ori, int32_t* d_match_cur, int32_t* d_nmatches, void* stream);
+/* The projection half of the same function (src/ORBmatcher.cc:1600-1626) for a stereo sequence, on the device: feature i of
+ * last frame b with stereo depth d_depth_last > 0 stands for the map point Frame::UnprojectStereo (src/Frame.cc:679-696)
+ * gives it, is moved into the current camera by d_Tcl[b] = [R | t] (3 x 4 row-major floats) and projected with fx, fy, cx, cy;
+ * query i belongs to feature i (features without depth become skipped queries), d_nq[b] = d_n_last[b].  has_obs = what
+ * pMP->Observations() > 0 is for these points (0 for the temporal points of Tracking::UpdateLastFrame). */
+int b2s_track_queries_device(b2s_matcher* h, int batch, const b2s_keypoint* d_kps_last, const uint8_t* d_desc_last,
+                             const float* d_depth_last, const int32_t* d_n_last, int cap, const float* d_Tcl, float fx,
+                             float fy, float cx, float cy, int has_obs, b2s_proj_query* d_q, int32_t* d_nq, void* stream);
+
 /* SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, float th) (src/ORBmatcher.cc:70-175), the local-map
  * matcher of Tracking::SearchLocalPoints; queries are the map points after Frame::isInFrustum (src/Frame.cc:608-735). */
 typedef struct {

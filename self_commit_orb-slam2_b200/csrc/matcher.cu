@@ -394,12 +394,20 @@ struct ProjGeom {
   float scale[16];
   float invSigma2[16];  // mvInvLevelSigma2 (only the chi-square gate of the window search reads it)
   int winFlags;         // B2S_WIN_* of b2s_search_windows
+  // batched launches (b2s_search_by_projection_last_device): blockIdx.y = pair; all zero / null for the one-pair entry points
+  int strideF = 0, strideQ = 0;       // per-pair stride (entries) of the feature-side / query-side arrays
+  const int32_t* nfArr = nullptr;     // per-pair feature / query counts (device)
+  const int32_t* nqArr = nullptr;
 };
+constexpr int CELL_STRIDE = GRID_COLS * GRID_ROWS + 2;  // cellStart entries of one pair
 
 // PosInGrid (src/Frame.cc:863-877): cell = round(), features outside the grid get key = big (sorted last, ignored)
 __global__ void k_proj_cell_key(const float* __restrict__ kpx, const float* __restrict__ kpy, int nf, ProjGeom g,
                                 int32_t* __restrict__ cellKey) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g.nfArr) nf = min(g.nfArr[blockIdx.y], g.strideF);
+  const size_t fo = (size_t)blockIdx.y * g.strideF;
+  kpx += fo; kpy += fo; cellKey += fo;
   if (i >= nf) return;
   const int px = (int)roundf(__fmul_rn(__fsub_rn(kpx[i], g.minX), g.invW));
   const int py = (int)roundf(__fmul_rn(__fsub_rn(kpy[i], g.minY), g.invH));
@@ -408,8 +416,12 @@ __global__ void k_proj_cell_key(const float* __restrict__ kpx, const float* __re
 
 // cellStart[c] = first sorted position whose key >= c  (c in [0, 3072])
 __global__ void k_proj_cell_start(const int32_t* __restrict__ cellKey, const int32_t* __restrict__ order, int nf,
-                                  int32_t* __restrict__ cellStart) {
+                                  int32_t* __restrict__ cellStart, int strideF = 0, const int32_t* __restrict__ nfArr = nullptr) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nfArr) nf = min(nfArr[blockIdx.y], strideF);
+  cellKey += (size_t)blockIdx.y * strideF;
+  order += (size_t)blockIdx.y * strideF;
+  cellStart += (size_t)blockIdx.y * CELL_STRIDE;
   if (r > nf) return;
   const int kPrev = (r == 0) ? -1 : cellKey[order[r - 1]];
   const int kCur = (r == nf) ? (GRID_COLS * GRID_ROWS) : cellKey[order[r]];
@@ -531,6 +543,14 @@ __global__ void __launch_bounds__(256) k_proj_topk(const QT* __restrict__ q, int
                                                    int32_t* __restrict__ candCnt) {
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  {
+    const size_t fo = (size_t)blockIdx.y * g.strideF, qo = (size_t)blockIdx.y * g.strideQ;
+    if (g.nqArr) nq = min(g.nqArr[blockIdx.y], g.strideQ);
+    q += qo; kpx += fo; kpy += fo; octave += fo; uright += fo; desc += fo * 32; order += fo;
+    if (occupied) occupied += fo;
+    cellStart += (size_t)blockIdx.y * CELL_STRIDE;
+    topk += qo * TOPK; topkIdx += qo * TOPK; candCnt += qo;
+  }
   if (i >= nq) return;
   uint32_t t[TOPK];
 #pragma unroll
@@ -666,6 +686,16 @@ __global__ void __launch_bounds__(32) k_proj_resolve(const ProjQuery* __restrict
   __shared__ int hist[HISTO];
   if (lane < HISTO) hist[lane] = 0;
   __syncwarp();
+  {
+    const size_t fo = (size_t)blockIdx.y * g.strideF, qo = (size_t)blockIdx.y * g.strideQ;
+    if (g.nqArr) nq = min(g.nqArr[blockIdx.y], g.strideQ);
+    q += qo; kpx += fo; kpy += fo; octave += fo; angle += fo; uright += fo; desc += fo * 32; order += fo;
+    if (occupied) occupied += fo;
+    cellStart += (size_t)blockIdx.y * CELL_STRIDE;
+    topk += qo * TOPK; topkIdx += qo * TOPK; candCnt += qo;
+    taken += fo; matchCur += fo; pushList += qo;
+    accepted += (size_t)blockIdx.y * 4; histOut += (size_t)blockIdx.y * HISTO;
+  }
   int nAccepted = 0;
   for (int i = 0; i < nq; i++) {
     const int cc = candCnt[i];
@@ -1062,9 +1092,12 @@ __global__ void __launch_bounds__(32) k_map_resolve(const MapQuery* __restrict__
 // nmatches decremented per entry (:1713-1724).
 __global__ void __launch_bounds__(256) k_proj_cull(int checkOri, const int32_t* __restrict__ hist,
                                                    const int32_t* __restrict__ accepted, int32_t* __restrict__ matchCur,
-                                                   const int32_t* __restrict__ pushBins, int32_t* __restrict__ nmatches) {
+                                                   const int32_t* __restrict__ pushBins, int32_t* __restrict__ nmatches,
+                                                   int strideF = 0, int strideQ = 0) {
   __shared__ int keep[3];
   __shared__ int culled;
+  hist += (size_t)blockIdx.y * HISTO; accepted += (size_t)blockIdx.y * 4; nmatches += blockIdx.y;
+  matchCur += (size_t)blockIdx.y * strideF; pushBins += (size_t)blockIdx.y * strideQ;
   if (threadIdx.x == 0) {
     culled = 0;
     int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
@@ -1358,8 +1391,9 @@ extern "C" int b2s_matcher_create(int max_features, int max_batch, int device, b
   A((void**)&h->dOrder, F * 4); A((void**)&h->dCandCnt, F * 4);
   A((void**)&h->dMatch, F * 4); A((void**)&h->dBin, F * 4); A((void**)&h->dNMatches, max_batch * 4);
   A((void**)&h->dOct, F * 4); A((void**)&h->dCellKey, F * 4);
-  A((void**)&h->dCellStart, (GRID_COLS * GRID_ROWS + 2) * 4);
-  A((void**)&h->dTopkIdx, F * TOPK * 4); A((void**)&h->dExtra, 4 * 4); A((void**)&h->dHist, HISTO * 4);
+  A((void**)&h->dCellStart, (size_t)CELL_STRIDE * max_batch * 4);
+  A((void**)&h->dTopkIdx, F * TOPK * 4); A((void**)&h->dExtra, (size_t)max_batch * 4 * 4);
+  A((void**)&h->dHist, (size_t)max_batch * HISTO * 4);
   A((void**)&h->dPush, F * 4);
   A((void**)&h->dAngA, F * 4); A((void**)&h->dAngB, F * 4);
   A((void**)&h->dKpx, F * 4); A((void**)&h->dKpy, F * 4); A((void**)&h->dURight, F * 4);
@@ -1549,6 +1583,121 @@ extern "C" int b2s_search_by_projection_last(b2s_matcher* h, const b2s_proj_quer
   B2S_CUDA(cudaMemcpyAsync(match_cur, h->dMatch, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, 4, cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaStreamSynchronize(st));
+  return B2S_OK;
+}
+
+// ---------------------------------------------------------------- batched, device-resident SearchByProjection(Cur, Last)
+// cv::KeyPoint-layout records -> the arrays the window search reads (one pair per blockIdx.y)
+__global__ void k_proj_unpack(const b2s_keypoint* __restrict__ kps, const int32_t* __restrict__ nArr, int cap,
+                              float* __restrict__ kpx, float* __restrict__ kpy, int32_t* __restrict__ oct,
+                              float* __restrict__ ang) {
+  const int pair = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= min(nArr[pair], cap)) return;
+  const size_t o = (size_t)pair * cap + i;
+  const b2s_keypoint k = kps[o];
+  kpx[o] = k.x; kpy[o] = k.y; oct[o] = k.octave; ang[o] = k.angle;
+}
+
+// The projection half of SearchByProjection(CurrentFrame, LastFrame) (src/ORBmatcher.cc:1600-1626) for a stereo sequence:
+// feature i of the last frame with a stereo depth z > 0 stands for the map point Frame::UnprojectStereo gives it
+// (src/Frame.cc:679-696: x = (u-cx) z invfx, y = (v-cy) z invfy), moved into the current camera by the relative pose
+// Tcl = [R | t] (3 x 4, row major) and projected (u = fx xc invzc + cx, :1614-1621).  Features without depth become skipped
+// queries (invz < 0), like last-frame slots without a MapPoint (:1603-1606).  Single-precision, one rounding per operation.
+__global__ void k_track_queries(const b2s_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc,
+                                const float* __restrict__ depth, const int32_t* __restrict__ nArr, int cap,
+                                const float* __restrict__ Tcl, float fx, float fy, float cx, float cy, float invfx,
+                                float invfy, int hasObs, ProjQuery* __restrict__ q, int32_t* __restrict__ nq) {
+  const int pair = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(nArr[pair], cap);
+  if (i == 0) nq[pair] = n;
+  if (i >= n) return;
+  const size_t o = (size_t)pair * cap + i;
+  const b2s_keypoint k = kps[o];
+  const float z = depth[o];
+  ProjQuery Q;
+  Q.u = 0.f; Q.v = 0.f; Q.invz = -1.f; Q.angle = k.angle; Q.octave = k.octave; Q.has_obs = hasObs;
+  const uint4* d4 = reinterpret_cast<const uint4*>(desc + o * 32);
+  if (z > 0.f) {
+    const float* T = Tcl + (size_t)pair * 12;
+    const float x = __fmul_rn(__fmul_rn(__fsub_rn(k.x, cx), z), invfx);
+    const float y = __fmul_rn(__fmul_rn(__fsub_rn(k.y, cy), z), invfy);
+    const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], x), __fmul_rn(T[1], y)), __fmul_rn(T[2], z)), T[3]);
+    const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], x), __fmul_rn(T[5], y)), __fmul_rn(T[6], z)), T[7]);
+    const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], x), __fmul_rn(T[9], y)), __fmul_rn(T[10], z)), T[11]);
+    const float invzc = __fdiv_rn(1.0f, zc);
+    if (!(invzc < 0.f)) {  // :1616-1617
+      Q.u = __fadd_rn(__fmul_rn(__fmul_rn(fx, xc), invzc), cx);
+      Q.v = __fadd_rn(__fmul_rn(__fmul_rn(fy, yc), invzc), cy);
+      Q.invz = invzc;
+    }
+  }
+  // (desc[] sits at byte 24 of the 56-byte record: 8-byte aligned only)
+  const uint4 a = d4[0], b = d4[1];
+  uint2* q2 = reinterpret_cast<uint2*>(Q.desc);
+  q2[0] = make_uint2(a.x, a.y); q2[1] = make_uint2(a.z, a.w); q2[2] = make_uint2(b.x, b.y); q2[3] = make_uint2(b.z, b.w);
+  q[o] = Q;
+}
+
+extern "C" int b2s_track_queries_device(b2s_matcher* h, int batch, const b2s_keypoint* d_kps_last, const uint8_t* d_desc_last,
+                                        const float* d_depth_last, const int32_t* d_n_last, int cap, const float* d_Tcl,
+                                        float fx, float fy, float cx, float cy, int has_obs, b2s_proj_query* d_q,
+                                        int32_t* d_nq, void* stream) {
+  if (!h || batch < 1 || batch > h->maxBatch || cap < 1 || cap > h->maxF || !d_kps_last || !d_desc_last || !d_depth_last ||
+      !d_n_last || !d_Tcl || !d_q || !d_nq || !(fx != 0.f) || !(fy != 0.f)) {
+    set_error("b2s_track_queries_device: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  k_track_queries<<<dim3(div_up(cap, 128), batch), 128, 0, st>>>(d_kps_last, d_desc_last, d_depth_last, d_n_last, cap, d_Tcl,
+                                                                 fx, fy, cx, cy, 1.0f / fx, 1.0f / fy, has_obs ? 1 : 0,
+                                                                 reinterpret_cast<ProjQuery*>(d_q), d_nq);
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+extern "C" int b2s_search_by_projection_last_device(b2s_matcher* h, int batch, const b2s_proj_query* d_q, const int32_t* d_nq,
+                                                    int capQ, const b2s_keypoint* d_kps, const float* d_uright,
+                                                    const uint8_t* d_desc, const int32_t* d_nf, int capF,
+                                                    const b2s_frame_geom* g, float th, int mode, int th_high, int check_ori,
+                                                    int32_t* d_match_cur, int32_t* d_nmatches, void* stream) {
+  if (!h || batch < 1 || batch > h->maxBatch || capQ < 1 || capF < 1 || capQ > h->maxF || capF > h->maxF || !d_q || !d_nq ||
+      !d_kps || !d_uright || !d_desc || !d_nf || !d_match_cur || !d_nmatches || !g || !g->scale_factors || g->nlevels < 1 ||
+      g->nlevels > 16 || mode < 0 || mode > 2) {
+    set_error("b2s_search_by_projection_last_device: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  ProjGeom pg;
+  pg.minX = g->mnMinX; pg.minY = g->mnMinY; pg.maxX = g->mnMaxX; pg.maxY = g->mnMaxY;
+  pg.invW = (float)GRID_COLS / (g->mnMaxX - g->mnMinX);  // src/Frame.cc:213-214
+  pg.invH = (float)GRID_ROWS / (g->mnMaxY - g->mnMinY);
+  pg.bf = g->bf; pg.th = th; pg.mode = mode; pg.thHigh = th_high; pg.checkOri = check_ori; pg.nlevels = g->nlevels;
+  pg.winFlags = 0;
+  for (int i = 0; i < 16; i++) {
+    pg.scale[i] = i < g->nlevels ? g->scale_factors[i] : 0.f;
+    pg.invSigma2[i] = 0.f;
+  }
+  pg.strideF = capF; pg.strideQ = capQ; pg.nfArr = d_nf; pg.nqArr = d_nq;
+  const size_t FF = (size_t)batch * capF;
+  const ProjQuery* dq = reinterpret_cast<const ProjQuery*>(d_q);
+  B2S_CUDA(cudaMemsetAsync(h->dTaken, 0, FF, st));
+  k_fill_i32<<<div_up((int)FF, 256), 256, 0, st>>>(d_match_cur, -1, FF);
+  k_proj_unpack<<<dim3(div_up(capF, 256), batch), 256, 0, st>>>(d_kps, d_nf, capF, h->dKpx, h->dKpy, h->dOct, h->dAngB);
+  k_proj_cell_key<<<dim3(div_up(capF, 256), batch), 256, 0, st>>>(h->dKpx, h->dKpy, capF, pg, h->dCellKey);
+  k_rank_by_key<<<dim3(div_up(capF, 128), batch), 128, 0, st>>>(h->dCellKey, d_nf, capF, h->dOrder);
+  k_proj_cell_start<<<dim3(div_up(capF + 1, 256), batch), 256, 0, st>>>(h->dCellKey, h->dOrder, capF, h->dCellStart, capF, d_nf);
+  k_proj_topk<ProjQuery><<<dim3(div_up(capQ, 8), batch), 256, 0, st>>>(dq, capQ, h->dKpx, h->dKpy, h->dOct, d_uright, nullptr,
+                                                                        d_desc, h->dOrder, h->dCellStart, pg, h->dTopk,
+                                                                        h->dTopkIdx, h->dCandCnt);
+  k_proj_resolve<<<dim3(1, batch), 32, 0, st>>>(dq, capQ, h->dKpx, h->dKpy, h->dOct, h->dAngB, d_uright, nullptr, d_desc,
+                                                h->dOrder, h->dCellStart, pg, h->dTopk, h->dTopkIdx, h->dCandCnt, h->dTaken,
+                                                d_match_cur, h->dPush, h->dExtra, h->dHist);
+  k_proj_cull<<<dim3(1, batch), 256, 0, st>>>(check_ori, h->dHist, h->dExtra, d_match_cur, h->dPush, d_nmatches, capF, capQ);
+  h->launches += 8;
+  B2S_CUDA(cudaGetLastError());
   return B2S_OK;
 }
 
