@@ -29,6 +29,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W_IMG, H_IMG, NFEAT = 1241, 376, 2000
+FX, FY, CX, CY, BF = 718.856, 718.856, 607.1928, 185.2157, 386.1448  # KITTI 00-02 (Examples/Stereo/KITTI00-02.yaml)
+PROJ_TH = 7.0  # SearchByProjection(CurrentFrame, LastFrame) window for stereo (src/Tracking.cc:892-897)
+# pose of the current camera relative to the last one (3 x 4): 0.8 m forward with a small yaw -> the reference's forward branch
+STREAM_MOTION = np.array([[np.cos(0.01), 0, np.sin(0.01), 0.02], [0, 1, 0, 0.0], [-np.sin(0.01), 0, np.cos(0.01), -0.8]], np.float32)
 # algorithmic bytes per 1241x376 image
 B_STAGE_IMAGE = 9359539          # all extractor stages
 B_TILE_IMAGE = 2385248 + 1444097 + 2888194  # the stages the fused tile kernel replaces: pyramid R+W, FAST read, blur R+W
@@ -219,7 +223,8 @@ class CpuArm:
     class Cfg(ctypes.Structure):
         _fields_ = [("nfeatures", ctypes.c_int), ("nlevels", ctypes.c_int), ("iniTh", ctypes.c_int), ("minTh", ctypes.c_int),
                     ("scaleFactor", ctypes.c_float), ("fx", ctypes.c_float), ("fy", ctypes.c_float), ("cx", ctypes.c_float),
-                    ("cy", ctypes.c_float), ("bf", ctypes.c_float), ("thDepth", ctypes.c_float)]
+                    ("cy", ctypes.c_float), ("bf", ctypes.c_float), ("thDepth", ctypes.c_float), ("project", ctypes.c_int),
+                    ("projTh", ctypes.c_float), ("Tcl", ctypes.c_float * 12)]
 
     def _ba_array(self, windows):
         ob = self.ob
@@ -265,12 +270,13 @@ class CpuArm:
         self.nBa, self.nPose = len(windows), len(poses)
         self.ba_arr = self._ba_array(windows) if windows else None
         self.pose_arr = self._pose_array(poses) if poses else None
-        self.cfg = CpuArm.Cfg(NFEAT, 8, 20, 7, 1.2, 718.856, 718.856, 607.1928, 185.2157, 386.1448, 35.0)
+        self.cfg = CpuArm.Cfg(NFEAT, 8, 20, 7, 1.2, FX, FY, CX, CY, BF, 35.0, 1, PROJ_TH,
+                              (ctypes.c_float * 12)(*[float(v) for v in STREAM_MOTION.reshape(12)]))
 
     def step(self, imgs_lr, threads):
-        """imgs_lr: uint8 [2, S, h, w] contiguous.  Returns (wall seconds, stats[8])."""
+        """imgs_lr: uint8 [2, S, h, w] contiguous.  Returns (wall seconds, stats[12])."""
         S = imgs_lr.shape[1]
-        stats = (ctypes.c_double * 8)()
+        stats = (ctypes.c_double * 12)()
         vp = ctypes.c_void_p
         wall = self.R.ref_stream2_step(ctypes.byref(self.cfg), imgs_lr.ctypes.data_as(vp), S, W_IMG, H_IMG, threads,
                                        ctypes.cast(self.ba_arr, vp) if self.ba_arr is not None else None, self.nBa,
@@ -337,27 +343,29 @@ def cpu_arm_measure(S, steps, warmup, seed0=0, with_cv2=True):
     imgs = np.ascontiguousarray(make_stream_images(S, seed0))
     for _ in range(warmup):
         arm.step(imgs, threads)
-    tot, busy = 0.0, np.zeros(4)
+    tot, busy = 0.0, np.zeros(5)
     last = None
     for _ in range(steps):
         wall, st = arm.step(imgs, threads)
         tot += wall
-        busy += np.array(st[:4])
+        busy += np.array(st[:4] + [st[8]])
         last = st
     fps = S * steps / tot
     stage = {"frame_extract_stereo_ms_per_frame": 1e3 * busy[0] / (S * steps), "search_by_bow_ms_per_frame": 1e3 * busy[1] / (S * steps),
              "pose_optimization_ms_per_frame": 1e3 * busy[2] / (S * steps),
+             "search_by_projection_ms_per_frame": 1e3 * busy[4] / (S * steps),
              "local_ba_ms_per_window": 1e3 * busy[3] / max(1, len(windows) * steps)}
-    return {"fps": fps, "threads": threads, "logical_cpus": logical, "cgroup_cpu_quota": quota, "seconds": tot, "S": S, "tasks_per_step": 2 * S + len(windows) + len(poses),
+    return {"fps": fps, "threads": threads, "logical_cpus": logical, "cgroup_cpu_quota": quota, "seconds": tot, "S": S, "tasks_per_step": 3 * S + len(windows) + len(poses),
             "utilisation": float(busy.sum() / (threads * tot)), "stage_ms_single_thread": stage, "solvers": info,
-            "keypoints_per_image": last[4], "stereo_matches_per_frame": last[5], "bow_matches_per_frame": last[6],
+            "keypoints_per_image": last[4], "stereo_matches_per_frame": last[5], "bow_matches_per_frame": last[6], "projection_matches_per_frame": last[9],
             "cv2": cv2_extract_ratio() if with_cv2 else None}
 
 
 def cpu_sample_text(m):
     return ("%d stereo frames per step (%d tasks on %d host threads = the usable CPUs [%d logical, cgroup quota %s], %.1f s timed, "
             "utilisation %.0f %%): reference's own Frame "
-            "constructor (ORBextractor.cc x2 threads + ComputeStereoMatches), ORBmatcher::SearchByBoW, PoseOptimization [%s], "
+            "constructor (ORBextractor.cc x2 threads + ComputeStereoMatches), ORBmatcher::SearchByBoW, ORBmatcher::SearchByProjection"
+            "(CurrentFrame, LastFrame), PoseOptimization [%s], "
             "LocalBundleAdjustment [%s]; OpenCV primitives = scalar stand-in (cv2 is %sx faster on pyramid+FAST+blur)"
             % (m["S"], m["tasks_per_step"], m["threads"], m["logical_cpus"], m["cgroup_cpu_quota"], m["seconds"],
                100 * m["utilisation"], m["solvers"]["pose_impl"],
@@ -386,7 +394,8 @@ def run_reference(args, rank, world):
 
 def workload_config(frames_per_gpu, world):
     return {"workload": "batched KITTI-shape stereo stream 1241x376, 2000 feat/img, 8 levels, FAST 20/7, distinct frames: extract "
-                        "L+R, ComputeStereoMatches, temporal SearchByBoW 2000x2000 (one vocabulary node), PoseOptimization per "
+                        "L+R, ComputeStereoMatches, temporal SearchByBoW 2000x2000 (one vocabulary node) and SearchByProjection(CurrentFrame, "
+                        "LastFrame) of the last frame's stereo points (motion model, th 7), PoseOptimization per "
                         "frame, LocalBA every 5th frame (32 different windows per 160 frames, 30-60 KF / 3000-6000 MP / ~30k edges)",
             "frames_per_step_per_gpu": frames_per_gpu, "images_per_step_per_gpu": 2 * frames_per_gpu,
             "parallelism": "frames sharded x%d, NCCL all-gather of the shard-boundary left-image feature records" % world,
@@ -412,7 +421,8 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:  # several ranks share the host cores: split them for the LocalBA window preparation threads
         os.environ.setdefault("B2S_BA_HOST_THREADS", str(max(2, min(16, effective_cpus()[0] // world))))
     ss = stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, ba_problems=windows, pose_problems=poses, stereo=True, ba_every=BA_EVERY,
-                                 device=local_rank, rank=rank, world=world, ba_depth=args.ba_depth, exchange=args.exchange)
+                                 device=local_rank, rank=rank, world=world, ba_depth=args.ba_depth, exchange=args.exchange,
+                                 bf=BF, project=True, intrinsics=(FX, FY, CX, CY), motion=STREAM_MOTION)
     imgs = make_stream_images(D, seed0=100000 * rank)  # [2, D, h, w], frame index = seed
     pinned = torch.from_numpy(imgs).pin_memory()
     d_all = pinned.cuda(non_blocking=True)
@@ -489,6 +499,8 @@ def run_b200(args, rank, local_rank, world):
     phase["extractor_stage_ms_isolated"] = {k: stage_iso[i] / max(1, calls_iso.value) for i, k in enumerate(STAGE_NAMES)}
     phase["stereo_matches_per_frame"] = float(ss.nstereo.float().mean().item())
     phase["keypoints_per_image"] = float(ss.counts[1:].float().mean().item())
+    phase["projection_matches_per_frame"] = float(ss.npmatch.float().mean().item())
+    phase["bow_matches_per_frame"] = float(ss.nmatch.float().mean().item())
     ba_kernel_ms, ba_trials = 0.0, 0
     try:
         t1 = time.perf_counter()
@@ -507,8 +519,8 @@ def run_b200(args, rank, local_rank, world):
     try:
         w1 = ba_window()
         ss1 = ss
-        keep = (ss1.windows, ss1.pose_problems, ss1.stereo)
-        ss1.windows, ss1.pose_problems, ss1.stereo = [w1], [], False
+        keep = (ss1.windows, ss1.pose_problems, ss1.stereo, ss1.project)
+        ss1.windows, ss1.pose_problems, ss1.stereo, ss1.project = [w1], [], False, False
         ss1._prep.clear()
         for _ in range(2):
             ss1.step_device(pipelined=True)
@@ -520,7 +532,7 @@ def run_b200(args, rank, local_rank, world):
         ss1.finish()
         torch.cuda.synchronize()
         phase["round1_workload_frames_per_s"] = 4 * F / (time.perf_counter() - t1)
-        ss1.windows, ss1.pose_problems, ss1.stereo = keep
+        ss1.windows, ss1.pose_problems, ss1.stereo, ss1.project = keep
         ss1._prep.clear()
     except Exception as ex:
         phase["round1_workload_error"] = str(ex)[:200]

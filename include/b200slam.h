@@ -184,6 +184,18 @@ int b2s_search_by_projection_last_device(b2s_matcher* h, int batch, const b2s_pr
                                          const b2s_keypoint* d_kps, const float* d_uright, const uint8_t* d_desc,
                                          const int32_t* d_nf, int capF, const b2s_frame_geom* g, float th, int mode,
                                          int th_high, int check_ori, int32_t* d_match_cur, int32_t* d_nmatches, void* stream);
+/* The same with HOST buffers (one upload, one download, synchronous): q [batch][capQ], kps / uright / desc [batch][capF]. */
+int b2s_search_by_projection_last_batch(b2s_matcher* h, int batch, const b2s_proj_query* q, const int32_t* nq, int capQ,
+                                        const b2s_keypoint* kps, const float* uright, const uint8_t* desc, const int32_t* nf,
+                                        int capF, const b2s_frame_geom* g, float th, int mode, int th_high, int check_ori,
+                                        int32_t* match_cur, int32_t* nmatches);
+/* HOST-buffer form for a frame sequence: kps / desc / depth hold batch + 1 consecutive frames ([batch + 1][cap]), uright the
+ * mvuRight of frames 1 .. batch; frame b + 1 is matched against frame b, the queries being formed on the device exactly as
+ * b2s_track_queries_device forms them (Tcl: [batch][12]).  match_cur [batch][cap], nmatches [batch].  Synchronous. */
+int b2s_search_by_projection_sequence(b2s_matcher* h, int batch, const b2s_keypoint* kps, const uint8_t* desc,
+                                      const float* depth, const float* uright, const int32_t* n, int cap, const float* Tcl,
+                                      float fx, float fy, float cx, float cy, int has_obs, const b2s_frame_geom* g, float th,
+                                      int mode, int th_high, int check_ori, int32_t* match_cur, int32_t* nmatches);
 /* The projection half of the same function (src/ORBmatcher.cc:1600-1626) for a stereo sequence, on the device: feature i of
  * last frame b with stereo depth d_depth_last > 0 stands for the map point Frame::UnprojectStereo (src/Frame.cc:679-696)
  * gives it, is moved into the current camera by d_Tcl[b] = [R | t] (3 x 4 row-major floats) and projected with fx, fy, cx, cy;

@@ -4,6 +4,10 @@
 //     threads (src/ORBextractor.cc) + Frame::ComputeStereoMatches + AssignFeaturesToGrid;
 //   * temporal matching of every left image against its predecessor with the reference's ORBmatcher::SearchByBoW
 //     (KeyFrame*, Frame&) (src/ORBmatcher.cc:230), one vocabulary node = the 2000 x 2000 brute-force case;
+//   * optionally (cfg.project) the motion-model matcher of Tracking::TrackWithMotionModel: every stereo point of a frame
+//     becomes a MapPoint at Frame::UnprojectStereo (what Tracking::UpdateLastFrame / StereoInitialization do), the next
+//     frame gets the pose cfg.Tcl and the reference's ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono)
+//     (src/ORBmatcher.cc:1569) runs on a per-task copy of it (Tracking copies the frame once per frame as well);
 //   * Optimizer::PoseOptimization per frame and Optimizer::LocalBundleAdjustment per window through function pointers
 //     (the reference's own Optimizer.cc + g2o live in libref_optimizer.so because their stand-in Map / KeyFrame objects
 //     differ from the ones Frame.cc needs; bench.py passes ref_pose_optimization / ref_local_ba, or the oracle port when
@@ -49,12 +53,16 @@ extern "C" {
 typedef struct {
   int nfeatures, nlevels, iniTh, minTh;
   float scaleFactor, fx, fy, cx, cy, bf, thDepth;
+  int project;     /* 1: also run SearchByProjection(CurrentFrame, LastFrame) per frame */
+  float projTh;    /* its window (7 for stereo, src/Tracking.cc:892-897) */
+  float Tcl[12];   /* pose of the current camera relative to the last one, 3 x 4 row major */
 } ref_stream2_cfg;
 
 /* imgs: S left images then S right images (dense, w*h each).  ba / pose: arrays of problems (nBa windows, nPose frames;
  * either may be 0).  stats (8 doubles): busy seconds in [0] frame construction (extract L+R + stereo), [1] SearchByBoW,
  * [2] PoseOptimization, [3] LocalBA; [4] keypoints per left image (mean), [5] stereo matches per frame (mean),
- * [6] BoW matches per frame (mean), [7] wall seconds.  Returns the wall time of the step. */
+ * [6] BoW matches per frame (mean), [7] wall seconds, [8] busy seconds in SearchByProjection(Cur, Last) (+ the MapPoint
+ * creation it needs), [9] its matches per frame (mean); 12 doubles in all.  Returns the wall time of the step. */
 double ref_stream2_step(const ref_stream2_cfg* cfg, const uint8_t* imgs, int S, int w, int h, int threads,
                         const orc_ba_problem* ba, int nBa, ba_fn_t ba_fn, const orc_pose_problem* pose, int nPose,
                         pose_fn_t pose_fn, double* stats) {
@@ -84,8 +92,13 @@ double ref_stream2_step(const ref_stream2_cfg* cfg, const uint8_t* imgs, int S, 
     cv::Mat imL(h, w, CV_8UC1, (void*)imgs, (size_t)w), imR(h, w, CV_8UC1, (void*)(imgs + (size_t)S * img), (size_t)w);
     Frame warm(imL, imR, 0.0, g_extractors[0].get(), g_extractors[1].get(), &g_voc, K, D, cfg->bf, cfg->thDepth);
   }
-  std::vector<double> busy((size_t)threads * 4, 0.0);
-  std::vector<int> nBow((size_t)S, 0);
+  std::vector<double> busy((size_t)threads * 5, 0.0);
+  std::vector<int> nBow((size_t)S, 0), nProj((size_t)S, 0);
+  std::vector<std::vector<MapPoint> > framePts((size_t)S);
+  const bool project = cfg->project != 0;
+  cv::Mat Tcl = cv::Mat::eye(4, 4, CV_32F), Tid = cv::Mat::eye(4, 4, CV_32F);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 4; j++) Tcl.at<float>(i, j) = cfg->Tcl[i * 4 + j];
   const double t0 = now();
   {
     std::atomic<int> next(0);
@@ -106,14 +119,34 @@ double ref_stream2_step(const ref_stream2_cfg* cfg, const uint8_t* imgs, int S, 
             r.points_out = X.data();
             r.edge_outlier = o.data();
             ba_fn(&P, nullptr, &r);
-            busy[(size_t)t * 4 + 3] += now() - a;
+            busy[(size_t)t * 5 + 3] += now() - a;
           } else {
             const int f = task - nBa;
             cv::Mat imL(h, w, CV_8UC1, (void*)(imgs + (size_t)f * img), (size_t)w);
             cv::Mat imR(h, w, CV_8UC1, (void*)(imgs + (size_t)(S + f) * img), (size_t)w);
             frames[(size_t)f].reset(new Frame(imL, imR, (double)f, g_extractors[2 * t].get(), g_extractors[2 * t + 1].get(),
                                               &g_voc, K, D, cfg->bf, cfg->thDepth));
-            busy[(size_t)t * 4 + 0] += now() - a;
+            Frame& fr = *frames[(size_t)f];
+            // every feature in vocabulary node 0 (the 2000 x 2000 brute-force case); set here so that the matching phase only reads
+            std::vector<unsigned int>& allF = fr.mFeatVec[0];
+            allF.resize((size_t)fr.N);
+            for (int i = 0; i < fr.N; i++) allF[(size_t)i] = (unsigned)i;
+            const double b = now();
+            busy[(size_t)t * 5 + 0] += b - a;
+            if (project) {  // the frame as a LAST frame: pose = origin, one MapPoint per stereo point
+              fr.SetPose(Tid);
+              std::vector<MapPoint>& pts = framePts[(size_t)f];
+              pts.resize((size_t)fr.N);
+              for (int i = 0; i < fr.N; i++) {
+                if (!(fr.mvDepth[(size_t)i] > 0)) continue;
+                MapPoint& p = pts[(size_t)i];
+                p.mWorldPos = fr.UnprojectStereo(i);
+                p.mDescriptor = fr.mDescriptors.row(i).clone();
+                p.nObs = 1;
+                fr.mvpMapPoints[(size_t)i] = &p;
+              }
+              busy[(size_t)t * 5 + 4] += now() - b;
+            }
           }
         }
       });
@@ -126,7 +159,7 @@ double ref_stream2_step(const ref_stream2_cfg* cfg, const uint8_t* imgs, int S, 
       th.emplace_back([&, t]() {
         for (;;) {
           const int task = next.fetch_add(1);
-          if (task >= nPose + S) break;
+          if (task >= nPose + S + (project ? S : 0)) break;
           const double a = now();
           if (task < nPose) {
             const orc_pose_problem& P = pose[task];
@@ -137,7 +170,16 @@ double ref_stream2_step(const ref_stream2_cfg* cfg, const uint8_t* imgs, int S, 
             r.Tcw_out = T;
             r.outlier = o.data();
             pose_fn(&P, &r);
-            busy[(size_t)t * 4 + 2] += now() - a;
+            busy[(size_t)t * 5 + 2] += now() - a;
+          } else if (task >= nPose + S) {
+            const int f = task - nPose - S;
+            Frame cur(*frames[(size_t)f]);  // own copy: the shared one is some other task's last frame
+            const Frame& last = *frames[(size_t)((f + S - 1) % S)];
+            std::fill(cur.mvpMapPoints.begin(), cur.mvpMapPoints.end(), static_cast<MapPoint*>(NULL));
+            cur.SetPose(Tcl);
+            ORBmatcher m(0.9f, true);
+            nProj[(size_t)f] = m.SearchByProjection(cur, last, cfg->projTh, false);
+            busy[(size_t)t * 5 + 4] += now() - a;
           } else {
             const int f = task - nPose;
             Frame& cur = *frames[(size_t)f];
@@ -156,15 +198,10 @@ double ref_stream2_step(const ref_stream2_cfg* cfg, const uint8_t* imgs, int S, 
               kf.mvpMapPoints[(size_t)i] = &pts[(size_t)i];
               allK[(size_t)i] = (unsigned)i;
             }
-            DBoW2::FeatureVector saved = cur.mFeatVec;
-            std::vector<unsigned int>& allF = cur.mFeatVec[0];
-            allF.resize((size_t)cur.N);
-            for (int i = 0; i < cur.N; i++) allF[(size_t)i] = (unsigned)i;
             ORBmatcher m(0.7f, true);
             std::vector<MapPoint*> matches;
             nBow[(size_t)f] = m.SearchByBoW(&kf, cur, matches);
-            cur.mFeatVec = saved;
-            busy[(size_t)t * 4 + 1] += now() - a;
+            busy[(size_t)t * 5 + 1] += now() - a;
           }
         }
       });
@@ -174,8 +211,14 @@ double ref_stream2_step(const ref_stream2_cfg* cfg, const uint8_t* imgs, int S, 
   if (stats) {
     for (int s = 0; s < 4; s++) {
       stats[s] = 0;
-      for (int t = 0; t < threads; t++) stats[s] += busy[(size_t)t * 4 + s];
+      for (int t = 0; t < threads; t++) stats[s] += busy[(size_t)t * 5 + s];
     }
+    stats[8] = 0;
+    for (int t = 0; t < threads; t++) stats[8] += busy[(size_t)t * 5 + 4];
+    double pj = 0;
+    for (int f = 0; f < S; f++) pj += nProj[(size_t)f];
+    stats[9] = S ? pj / S : 0;
+    stats[10] = stats[11] = 0;
     double kp = 0, st = 0, bw = 0;
     for (int f = 0; f < S; f++) {
       kp += frames[(size_t)f]->N;

@@ -110,6 +110,19 @@ def lib():
             L.b2s_search_by_projection_last.argtypes = [_vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                                         ctypes.c_int, _vp, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                                         ctypes.c_int, _vp, _vp]
+            L.b2s_search_by_projection_last_device.argtypes = [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp,
+                                                               ctypes.c_int, _vp, ctypes.c_float, ctypes.c_int,
+                                                               ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]
+            L.b2s_search_by_projection_last_batch.argtypes = [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp,
+                                                              ctypes.c_int, _vp, ctypes.c_float, ctypes.c_int,
+                                                              ctypes.c_int, ctypes.c_int, _vp, _vp]
+            L.b2s_search_by_projection_sequence.argtypes = [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp,
+                                                            ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                                            ctypes.c_int, _vp, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                                            ctypes.c_int, _vp, _vp]
+            L.b2s_track_queries_device.argtypes = [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_float,
+                                                   ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, _vp, _vp,
+                                                   _vp]
             L.b2s_search_by_projection_map.argtypes = [_vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,
                                                        _vp, ctypes.c_float, ctypes.c_int, ctypes.c_float, _vp, _vp]
         if hasattr(L, "b2s_ba_create"):
@@ -321,6 +334,61 @@ class ORBmatcher:
                                                    ctypes.byref(nm)))
         return nm.value, match
 
+
+    @staticmethod
+    def frame_geom(geom):
+        """ctypes b2s_frame_geom (+ the array it points to, which the caller keeps alive) from a dict."""
+        sf = np.ascontiguousarray(geom["scale_factors"], np.float32)
+        return _FrameGeom(geom["mnMinX"], geom["mnMinY"], geom["mnMaxX"], geom["mnMaxY"], geom["bf"], sf.ctypes.data,
+                          len(sf)), sf
+
+    def track_queries_device(self, batch, d_kps_last, d_desc_last, d_depth_last, d_n_last, cap, d_Tcl, fx, fy, cx, cy, has_obs,
+                             d_q, d_nq, stream=None):
+        """Projection half of SearchByProjection(CurrentFrame, LastFrame) (src/ORBmatcher.cc:1600-1626) for `batch` stereo
+        frame pairs on the device (b2s_track_queries_device); all d_* are device addresses."""
+        _check(lib().b2s_track_queries_device(self._h, batch, _vp(d_kps_last), _vp(d_desc_last), _vp(d_depth_last),
+                                              _vp(d_n_last), cap, _vp(d_Tcl), float(fx), float(fy), float(cx), float(cy),
+                                              int(has_obs), _vp(d_q), _vp(d_nq), _vp(stream) if stream else None))
+
+    def search_by_projection_last_device(self, batch, d_q, d_nq, cap_q, d_kps, d_uright, d_desc, d_nf, cap_f, geom, th, mode,
+                                         d_match, d_nmatches, th_high=TH_HIGH, stream=None):
+        """Batched device-resident SearchByProjection(CurrentFrame, LastFrame) (b2s_search_by_projection_last_device)."""
+        g, keep = self.frame_geom(geom)
+        _check(lib().b2s_search_by_projection_last_device(self._h, batch, _vp(d_q), _vp(d_nq), cap_q, _vp(d_kps), _vp(d_uright),
+                                                          _vp(d_desc), _vp(d_nf), cap_f, ctypes.byref(g), float(th), int(mode),
+                                                          th_high, int(self.mbCheckOrientation), _vp(d_match),
+                                                          _vp(d_nmatches), _vp(stream) if stream else None))
+
+    def SearchByProjectionBatch(self, queries, nq, kps, uright, desc, nf, geom, th, mode=0, th_high=TH_HIGH):
+        """Host-buffer batch (b2s_search_by_projection_last_batch): queries [B, capQ] proj_query_dtype, kps [B, capF]
+        keypoint_dtype, uright [B, capF] f32, desc [B, capF, 32] u8.  Returns (nmatches [B], match_cur [B, capF])."""
+        queries, kps = np.ascontiguousarray(queries), np.ascontiguousarray(kps)
+        uright, desc = np.ascontiguousarray(uright, np.float32), np.ascontiguousarray(desc, np.uint8)
+        B, capQ = queries.shape
+        capF = kps.shape[1]
+        g, keep = self.frame_geom(geom)
+        match = np.full((B, capF), -1, np.int32)
+        nm = np.zeros(B, np.int32)
+        nq = np.ascontiguousarray(nq, np.int32)
+        nf = np.ascontiguousarray(nf, np.int32)
+        _check(lib().b2s_search_by_projection_last_batch(self._h, B, _p(queries), _p(nq), capQ, _p(kps), _p(uright), _p(desc),
+                                                         _p(nf), capF, ctypes.byref(g), float(th), int(mode), th_high,
+                                                         int(self.mbCheckOrientation), _p(match), _p(nm)))
+        return nm, match
+
+    def SearchByProjectionSequence(self, kps, desc, depth, uright, n, Tcl, fx, fy, cx, cy, geom, th, mode=0, has_obs=1,
+                                   th_high=TH_HIGH, out=None):
+        """b2s_search_by_projection_sequence: kps / desc / depth of B + 1 consecutive frames ([B + 1, cap, ...], C-contiguous
+        host arrays), uright [B, cap] of frames 1..B, Tcl [B, 12]; frame b + 1 is matched against frame b.  Returns
+        (nmatches [B], match_cur [B, cap]) (written into `out` = (nm, match) when given)."""
+        B, cap = uright.shape
+        g, keep = self.frame_geom(geom)
+        nm, match = out if out is not None else (np.zeros(B, np.int32), np.full((B, cap), -1, np.int32))
+        _check(lib().b2s_search_by_projection_sequence(self._h, B, _p(kps), _p(desc), _p(depth), _p(uright), _p(n), cap, _p(Tcl),
+                                                       float(fx), float(fy), float(cx), float(cy), int(has_obs),
+                                                       ctypes.byref(g), float(th), int(mode), th_high,
+                                                       int(self.mbCheckOrientation), _p(match), _p(nm)))
+        return nm, match
 
     def SearchForInitialization(self, prev, octave1, angle1, desc1, kpx2, kpy2, octave2, angle2, desc2, geom, window=10,
                                 th_low=TH_LOW):

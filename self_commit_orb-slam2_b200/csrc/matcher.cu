@@ -1365,6 +1365,13 @@ struct b2s_matcher {
   float *dAngA = nullptr, *dAngB = nullptr, *dKpx = nullptr, *dKpy = nullptr, *dURight = nullptr;
   uint32_t* dTopk = nullptr;
   ProjQuery* dQueries = nullptr;
+  b2s_keypoint* dKpsStage = nullptr;  // record staging of b2s_search_by_projection_last_batch (allocated on first use)
+  size_t kpsStageCap = 0;
+  // staging of b2s_search_by_projection_sequence: records of batch + 1 frames
+  uint8_t* dSeqDesc = nullptr;
+  float *dSeqDepth = nullptr, *dSeqT = nullptr;
+  int32_t* dSeqN = nullptr;
+  size_t seqCap = 0;
 };
 
 extern "C" int b2s_matcher_create(int max_features, int max_batch, int device, b2s_matcher** out) {
@@ -1414,7 +1421,7 @@ extern "C" void b2s_matcher_destroy(b2s_matcher* h) {
   void* ptrs[] = {h->dDescA, h->dDescB, h->dValidA, h->dValidB, h->dOcc, h->dTaken, h->dNodeA, h->dNodeB, h->dNA, h->dNB,
                   h->dOrder, h->dCandCnt, h->dMatch, h->dBin, h->dNMatches, h->dOct, h->dCellKey, h->dCellStart,
                   h->dTopkIdx, h->dExtra, h->dHist, h->dPush, h->dAngA, h->dAngB, h->dKpx, h->dKpy, h->dURight, h->dTopk,
-                  h->dQueries};
+                  h->dQueries, h->dKpsStage, h->dSeqDesc, h->dSeqDepth, h->dSeqT, h->dSeqN};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1698,6 +1705,94 @@ extern "C" int b2s_search_by_projection_last_device(b2s_matcher* h, int batch, c
   k_proj_cull<<<dim3(1, batch), 256, 0, st>>>(check_ori, h->dHist, h->dExtra, d_match_cur, h->dPush, d_nmatches, capF, capQ);
   h->launches += 8;
   B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+// host-buffer form of the batched search: one upload, the device path above, one download
+extern "C" int b2s_search_by_projection_last_batch(b2s_matcher* h, int batch, const b2s_proj_query* q, const int32_t* nq, int capQ,
+                                                   const b2s_keypoint* kps, const float* uright, const uint8_t* desc,
+                                                   const int32_t* nf, int capF, const b2s_frame_geom* g, float th, int mode,
+                                                   int th_high, int check_ori, int32_t* match_cur, int32_t* nmatches) {
+  if (!h || batch < 1 || batch > h->maxBatch || capQ < 1 || capF < 1 || capQ > h->maxF || capF > h->maxF || !q || !nq ||
+      !kps || !uright || !desc || !nf || !match_cur || !nmatches) {
+    set_error("b2s_search_by_projection_last_batch: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  for (int b = 0; b < batch; b++)
+    if (nq[b] < 0 || nq[b] > capQ || nf[b] < 0 || nf[b] > capF) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t FQ = (size_t)batch * capQ, FF = (size_t)batch * capF;
+  if (h->kpsStageCap < FF) {
+    if (h->dKpsStage) cudaFree(h->dKpsStage);
+    h->dKpsStage = nullptr;
+    h->kpsStageCap = 0;
+    B2S_CUDA(cudaMalloc((void**)&h->dKpsStage, FF * sizeof(b2s_keypoint)));
+    h->kpsStageCap = FF;
+  }
+  B2S_CUDA(cudaMemcpyAsync(h->dQueries, q, FQ * sizeof(ProjQuery), cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dKpsStage, kps, FF * sizeof(b2s_keypoint), cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dURight, uright, FF * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dDescB, desc, FF * 32, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNA, nq, (size_t)batch * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dNB, nf, (size_t)batch * 4, cudaMemcpyHostToDevice, st));
+  int rc = b2s_search_by_projection_last_device(h, batch, reinterpret_cast<const b2s_proj_query*>(h->dQueries), h->dNA, capQ,
+                                                h->dKpsStage, h->dURight, h->dDescB, h->dNB, capF, g, th, mode, th_high,
+                                                check_ori, h->dMatch, h->dNMatches, st);
+  if (rc != B2S_OK) return rc;
+  B2S_CUDA(cudaMemcpyAsync(match_cur, h->dMatch, FF * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  return B2S_OK;
+}
+
+// host-buffer form for a frame sequence: records of frames 0 .. batch (batch + 1 of them) are uploaded once, frame b + 1 is
+// matched against frame b with the queries formed on the device (b2s_track_queries_device)
+extern "C" int b2s_search_by_projection_sequence(b2s_matcher* h, int batch, const b2s_keypoint* kps, const uint8_t* desc,
+                                                 const float* depth, const float* uright, const int32_t* n, int cap,
+                                                 const float* Tcl, float fx, float fy, float cx, float cy, int has_obs,
+                                                 const b2s_frame_geom* g, float th, int mode, int th_high, int check_ori,
+                                                 int32_t* match_cur, int32_t* nmatches) {
+  if (!h || batch < 1 || batch > h->maxBatch || cap < 1 || cap > h->maxF || !kps || !desc || !depth || !uright || !n || !Tcl ||
+      !match_cur || !nmatches) {
+    set_error("b2s_search_by_projection_sequence: bad argument");
+    return B2S_ERR_BAD_ARG;
+  }
+  for (int b = 0; b <= batch; b++)
+    if (n[b] < 0 || n[b] > cap) return B2S_ERR_BAD_ARG;
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t S = (size_t)(batch + 1) * cap, FF = (size_t)batch * cap;
+  if (h->seqCap < S) {
+    void* old[] = {h->dKpsStage, h->dSeqDesc, h->dSeqDepth, h->dSeqN, h->dSeqT};
+    for (void* p : old)
+      if (p) cudaFree(p);
+    h->dKpsStage = nullptr; h->dSeqDesc = nullptr; h->dSeqDepth = nullptr; h->dSeqN = nullptr; h->dSeqT = nullptr;
+    h->seqCap = 0; h->kpsStageCap = 0;
+    B2S_CUDA(cudaMalloc((void**)&h->dKpsStage, S * sizeof(b2s_keypoint)));
+    B2S_CUDA(cudaMalloc((void**)&h->dSeqDesc, S * 32));
+    B2S_CUDA(cudaMalloc((void**)&h->dSeqDepth, S * 4));
+    B2S_CUDA(cudaMalloc((void**)&h->dSeqN, (size_t)(h->maxBatch + 1) * 4));
+    B2S_CUDA(cudaMalloc((void**)&h->dSeqT, (size_t)h->maxBatch * 12 * 4));
+    h->seqCap = S;
+    h->kpsStageCap = S;
+  }
+  B2S_CUDA(cudaMemcpyAsync(h->dKpsStage, kps, S * sizeof(b2s_keypoint), cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dSeqDesc, desc, S * 32, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dSeqDepth, depth, S * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dURight, uright, FF * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dSeqN, n, (size_t)(batch + 1) * 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(h->dSeqT, Tcl, (size_t)batch * 12 * 4, cudaMemcpyHostToDevice, st));
+  int rc = b2s_track_queries_device(h, batch, h->dKpsStage, h->dSeqDesc, h->dSeqDepth, h->dSeqN, cap, h->dSeqT, fx, fy, cx, cy,
+                                    has_obs, reinterpret_cast<b2s_proj_query*>(h->dQueries), h->dNA, st);
+  if (rc != B2S_OK) return rc;
+  rc = b2s_search_by_projection_last_device(h, batch, reinterpret_cast<const b2s_proj_query*>(h->dQueries), h->dNA, cap,
+                                            h->dKpsStage + cap, h->dURight, h->dSeqDesc + (size_t)cap * 32, h->dSeqN + 1, cap,
+                                            g, th, mode, th_high, check_ori, h->dMatch, h->dNMatches, st);
+  if (rc != B2S_OK) return rc;
+  B2S_CUDA(cudaMemcpyAsync(match_cur, h->dMatch, FF * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(nmatches, h->dNMatches, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
   return B2S_OK;
 }
 

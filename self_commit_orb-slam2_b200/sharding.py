@@ -28,6 +28,15 @@ def gather_records(kps, desc, counts, g_kps, g_desc, g_counts, group=None):
         dist.all_gather_into_tensor(g_counts, counts, group=group)
 
 
+def gather_array(x, g_x, group=None):
+    """All-gather one more fixed-size per-frame array (e.g. the stereo depths that travel with a feature record)."""
+    import torch.distributed as dist
+    if dist.get_backend(group) == "gloo":
+        dist.all_gather(list(g_x.unbind(0)), x.contiguous(), group=group)
+    else:
+        dist.all_gather_into_tensor(g_x, x.contiguous(), group=group)
+
+
 def take_predecessor(g_kps, g_desc, g_counts, rank, world, out_kps, out_desc, out_count):
     """Copy the record of the frame preceding this shard (last frame of the previous rank) into slot 0."""
     prev = predecessor_source(rank, world)

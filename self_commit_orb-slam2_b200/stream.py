@@ -7,6 +7,10 @@ Per step a rank owns F stereo frames (2F images).  Device-resident path:
   3. b2s_search_by_bow_device  : temporal match left(t-1) -> left(t) for the rank's F frames, all features in one
                                  vocabulary node (2000x2000 brute force); the frame before the shard's first one comes
                                  from the previous rank's gathered records
+  3b. b2s_track_queries_device + b2s_search_by_projection_last_device (project=True): the motion-model matcher of
+                                 Tracking::TrackWithMotionModel, SearchByProjection(CurrentFrame, LastFrame), for the same
+                                 F pairs: the last frame's stereo points are moved by the relative pose and searched in
+                                 the current frame's grid windows
   4. b2s_local_ba_batch        : one LocalBA window per `ba_every` frames (replicas; its own stream, overlaps 1-3)
 torch is plumbing only: device memory, streams, torch.distributed.
 """
@@ -15,7 +19,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import (ORBextractor, ORBmatcher, Optimizer, _check, _vp, ba_edge_dtype, keypoint_dtype, lib)
+from . import (ORBextractor, ORBmatcher, Optimizer, _check, _vp, ba_edge_dtype, keypoint_dtype, lib, proj_query_dtype)
 from . import sharding
 
 KP_BYTES = keypoint_dtype.itemsize  # 28
@@ -24,10 +28,14 @@ KP_BYTES = keypoint_dtype.itemsize  # 28
 class StereoStream:
     def __init__(self, frames_per_step, width, height, nfeatures=2000, scale=1.2, nlevels=8, ini_th=20, min_th=7,
                  ba_problem=None, ba_every=5, device=0, rank=0, world=1, nnratio=0.7, ba_depth=1,
-                 exchange="boundary", ba_problems=None, pose_problems=None, stereo=False, bf=386.1448):
+                 exchange="boundary", ba_problems=None, pose_problems=None, stereo=False, bf=386.1448, project=False,
+                 intrinsics=(718.856, 718.856, 607.1928, 185.2157), motion=None):
         """ba_problems: list of LocalBA windows (a step solves ceil(F / ba_every) of them, taken round-robin);
         pose_problems: list of per-frame PoseOptimization problems (F per step, round-robin); stereo: run
-        Frame::ComputeStereoMatches for the F pairs of every step on the resident pyramids."""
+        Frame::ComputeStereoMatches for the F pairs of every step on the resident pyramids; project (needs stereo): also
+        run SearchByProjection(CurrentFrame, LastFrame) for every frame against its predecessor, the predecessor's stereo
+        points moved by `motion` (Tcl, 3 x 4; default: 0.8 m forward with a small yaw, the KITTI-like case that takes the
+        reference's forward branch, src/ORBmatcher.cc:1595-1598)."""
         self.F, self.w, self.h = frames_per_step, width, height
         self.rank, self.world = rank, world
         self.dev = torch.device("cuda", device)
@@ -82,13 +90,73 @@ class StereoStream:
         self.d_imgs = torch.zeros((2 * F, height, width), dtype=torch.uint8, **z)
         if self.stereo:  # mvuRight / mvDepth per left feature, matches per pair
             self.ur = torch.zeros((F, cap), dtype=torch.float32, **z)
-            self.dp = torch.zeros((F, cap), dtype=torch.float32, **z)
+            self.dp_all = torch.zeros((1 + F, cap), dtype=torch.float32, **z)  # slot 0: depth of the shard's predecessor
+            self.dp = self.dp_all[1:]
             self.nstereo = torch.zeros(F, dtype=torch.int32, **z)
+        self.project = bool(project) and self.stereo
+        if self.project:
+            self.fx, self.fy, self.cx, self.cy = [float(v) for v in intrinsics]
+            if motion is None:
+                a = 0.01  # rad of yaw per frame
+                motion = np.array([[np.cos(a), 0, np.sin(a), 0.02], [0, 1, 0, 0.0], [-np.sin(a), 0, np.cos(a), -0.8]])
+            self.motion = np.ascontiguousarray(motion, np.float32).reshape(3, 4)
+            self.proj_mode = self.projection_mode(self.motion, self.bf / self.fx)
+            self.proj_th = 7.0  # stereo / RGB-D window of Tracking::TrackWithMotionModel (src/Tracking.cc:892-897)
+            self.geom = dict(mnMinX=0.0, mnMinY=0.0, mnMaxX=float(width), mnMaxY=float(height), bf=self.bf,
+                             scale_factors=np.asarray(self.ex.GetScaleFactors(), np.float32))
+            self.Tcl = torch.from_numpy(np.tile(self.motion.reshape(1, 12), (F, 1))).to(self.dev)
+            self.q = torch.zeros((F, cap, proj_query_dtype.itemsize), dtype=torch.uint8, **z)
+            self.nq = torch.zeros(F, dtype=torch.int32, **z)
+            self.pmatch = torch.full((F, cap), -1, dtype=torch.int32, **z)
+            self.npmatch = torch.zeros(F, dtype=torch.int32, **z)
+            if world > 1:
+                self.g_dp = torch.zeros((world, self.G, cap), dtype=torch.float32, **z)
         self._step_no = 0
         self._pool = None
         self._ba_future = None
         self._ba_futures = []  # (pipelined) in-flight LocalBA batches, oldest first; at most len(self.opts)
         self._ba_next = 0
+
+    @staticmethod
+    def projection_mode(Tcl, mb):
+        """0 / 1 (forward) / 2 (backward) as src/ORBmatcher.cc:1589-1598 decides it for a stereo frame: tlc = position of
+        the current camera centre in the last camera's frame."""
+        R, t = np.asarray(Tcl, np.float64)[:, :3], np.asarray(Tcl, np.float64)[:, 3]
+        tlc_z = float((-R.T @ t)[2])
+        return 1 if tlc_z > mb else (2 if -tlc_z > mb else 0)
+
+    @staticmethod
+    def track_queries_host(kps, desc, depth, n, Tcl, fx, fy, cx, cy, has_obs=1):
+        """numpy restatement of b2s_track_queries_device (same single-precision operation order), for host-buffer callers
+        and tests: kps [B, cap] keypoint_dtype, desc [B, cap, 32], depth [B, cap], n [B], Tcl [B, 3, 4]."""
+        f = np.float32
+        B, cap = depth.shape
+        q = np.zeros((B, cap), proj_query_dtype)
+        T = np.asarray(Tcl, f).reshape(B, 12)
+        z = depth.astype(f)
+        live = (np.arange(cap)[None, :] < np.asarray(n)[:, None])
+        ok = live & (z > 0)
+        invfx, invfy = f(1.0) / f(fx), f(1.0) / f(fy)
+        with np.errstate(all="ignore"):
+            x = (kps["x"] - f(cx)) * z * invfx
+            y = (kps["y"] - f(cy)) * z * invfy
+            c = lambda k: T[:, k:k + 1]
+            xc = ((c(0) * x + c(1) * y) + c(2) * z) + c(3)
+            yc = ((c(4) * x + c(5) * y) + c(6) * z) + c(7)
+            zc = ((c(8) * x + c(9) * y) + c(10) * z) + c(11)
+            invz = f(1.0) / zc
+            ok2 = ok & ~(invz < 0)
+            u = (f(fx) * xc) * invz + f(cx)
+            v = (f(fy) * yc) * invz + f(cy)
+        q["u"] = np.where(ok2, u, f(0))
+        q["v"] = np.where(ok2, v, f(0))
+        q["invz"] = np.where(ok2, invz, f(-1))
+        q["angle"] = kps["angle"]
+        q["octave"] = kps["octave"]
+        q["has_obs"] = has_obs
+        q["desc"] = desc
+        q[~live] = np.zeros((), proj_query_dtype)
+        return q
 
     # ------------------------------------------------------------------ device-resident step
     def upload(self, imgs_host):
@@ -206,10 +274,15 @@ class StereoStream:
                                     self.g_counts)
             sharding.take_predecessor(self.g_kps, self.g_desc, self.g_counts, self.rank, self.world, self.kps[0],
                                       self.desc[0], self.counts[0:1])
+            if self.project:  # the predecessor's stereo depths travel with its record
+                sharding.gather_array(self.dp_all[lo:1 + F], self.g_dp)
+                self.dp_all[0].copy_(self.g_dp[sharding.predecessor_source(self.rank, self.world), self.G - 1])
         else:  # ring inside the shard
             self.kps[0].copy_(self.kps[F])
             self.desc[0].copy_(self.desc[F])
             self.counts[0:1].copy_(self.counts[F:F + 1])
+            if self.project:
+                self.dp_all[0].copy_(self.dp_all[F])
         # angles of the left images (kpUn.angle), gathered out of the 28-byte records
         self.ang.copy_(self.kps[:1 + F].view(torch.float32)[:, :, 3])
         L = lib()
@@ -219,6 +292,15 @@ class StereoStream:
                                           _vp(self.node[1:].data_ptr()), None, _vp(self.ang[1:].data_ptr()),
                                           _vp(self.counts[1:].data_ptr()), cap, 50, float(self.matcher.mfNNratio), 0, 1,
                                           _vp(self.match.data_ptr()), _vp(self.nmatch.data_ptr()), _vp(st)))
+        if self.project:  # pair f: last = left image f-1 (slot f), current = left image f (slot f+1)
+            m = self.matcher
+            m.track_queries_device(F, self.kps.data_ptr(), self.desc.data_ptr(), self.dp_all.data_ptr(), self.counts.data_ptr(),
+                                   cap, self.Tcl.data_ptr(), self.fx, self.fy, self.cx, self.cy, 1, self.q.data_ptr(),
+                                   self.nq.data_ptr(), stream=st)
+            m.search_by_projection_last_device(F, self.q.data_ptr(), self.nq.data_ptr(), cap, self.kps[1:].data_ptr(),
+                                               self.ur.data_ptr(), self.desc[1:].data_ptr(), self.counts[1:].data_ptr(), cap,
+                                               self.geom, self.proj_th, self.proj_mode, self.pmatch.data_ptr(),
+                                               self.npmatch.data_ptr(), stream=st)
 
     # ------------------------------------------------------------------ end-to-end step through the host-buffer C ABI
     def step_host(self, imgs_host_np, run_ba=True, pipelined=False, img_ptrs=None):
@@ -265,12 +347,22 @@ class StereoStream:
         if self.stereo:  # mvuRight / mvDepth of the F left images, host arrays (the pyramids are still on the device)
             if getattr(self, "_h_ur", None) is None:
                 self._h_ur = torch.zeros((F, cap), dtype=torch.float32).pin_memory().numpy()
-                self._h_dp = torch.zeros((F, cap), dtype=torch.float32).pin_memory().numpy()
+                self._h_dp_all = torch.zeros((1 + F, cap), dtype=torch.float32).pin_memory().numpy()
+                self._h_dp = self._h_dp_all[1:]
                 self._h_ns = np.zeros(F, np.int32)
+                self._h_pm = torch.zeros((F, cap), dtype=torch.int32).pin_memory().numpy()
+                self._h_npm = np.zeros(F, np.int32)
+                self._h_Tcl = np.tile(self.motion.reshape(1, 12), (F, 1)) if self.project else None
             L.b2s_stereo_match.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, _vp,
                                            _vp, ctypes.c_int, _vp]
             _check(L.b2s_stereo_match(self.ex._h, 0, F, F, ctypes.c_float(self.bf), ctypes.c_float(0.0), p(self._h_ur),
                                       p(self._h_dp), cap, p(self._h_ns)))
+            if self.project:  # SearchByProjection(CurrentFrame, LastFrame): frame f against f-1 (slot 0 = ring predecessor)
+                self._h_dp_all[0] = self._h_dp_all[F]
+                self.matcher.SearchByProjectionSequence(all_kps[:1 + F], all_desc[:1 + F], self._h_dp_all, self._h_ur,
+                                                        all_n[:1 + F], self._h_Tcl, self.fx, self.fy, self.cx, self.cy,
+                                                        self.geom, self.proj_th, self.proj_mode,
+                                                        out=(self._h_npm, self._h_pm))
         ba_out = None
         if run_ba and (self.n_ba or self.pose_problems):
             if pipelined:  # results of an earlier step's windows are returned; finish() joins the rest
@@ -292,6 +384,8 @@ class StereoStream:
     def h2d_bytes_per_step(self):
         b = 2 * self.F * self.w * self.h
         b += self.F * self.cap * (32 + 4 + 4 + 1) * 2  # descriptors, nodes, angles, valid for both sides of the matcher
+        if self.project:  # records + depths of F + 1 frames, mvuRight of F, relative poses
+            b += (self.F + 1) * self.cap * (KP_BYTES + 32 + 4) + self.F * self.cap * 4 + self.F * 48
         for pr in self._step_windows(0):
             b += pr["n_kf"] * 64 + len(pr["points"]) * 12 + len(pr["edges"]) * ba_edge_dtype.itemsize
         for pp in self._step_poses(0):
@@ -303,6 +397,8 @@ class StereoStream:
         b += self.F * self.cap * 4 + self.F * 4
         if self.stereo:
             b += self.F * self.cap * 8 + self.F * 4
+        if self.project:
+            b += self.F * self.cap * 4 + self.F * 4
         for pr in self._step_windows(0):
             b += pr["n_local"] * 64 + len(pr["points"]) * 12 + len(pr["edges"])
         for pp in self._step_poses(0):

@@ -45,6 +45,13 @@ def _worker(rank, world, port, F, cap, ret):
     sh.take_predecessor(g_kps, g_desc, g_counts, rank, world, s_k, s_d, s_c)
     pred = (lo - 1) % total  # ring-ordered stream
     ok &= int(s_c[0]) == pred + 3 and int(s_k[0, 0]) == (pred * 7) % 251 and int(s_d[0, 0]) == (pred * 13) % 239
+    # the stereo depths travel the same way (gather_array): frame f carries depth f + 0.5 everywhere
+    dp = torch.zeros((F, cap), dtype=torch.float32)
+    for i, f in enumerate(range(lo, hi)):
+        dp[i] = f + 0.5
+    g_dp = torch.zeros((world, F, cap), dtype=torch.float32)
+    sh.gather_array(dp, g_dp)
+    ok &= float(g_dp[sh.predecessor_source(rank, world), F - 1, cap - 1]) == pred + 0.5
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -32,7 +32,7 @@ def test_two_ranks_equal_one_gpu(pkg, tmp_path, exchange):
     G = F * world
     pairs = [synth_stereo(w, h, 700 + i) for i in range(G)]
     imgs = np.stack([p[0] for p in pairs] + [p[1] for p in pairs])
-    ss = stream_mod.StereoStream(G, w, h, 2000, stereo=True)
+    ss = stream_mod.StereoStream(G, w, h, 2000, stereo=True, project=True)
     ss.upload(torch.from_numpy(imgs))
     ss.step_device()
     torch.cuda.synchronize()
@@ -41,6 +41,7 @@ def test_two_ranks_equal_one_gpu(pkg, tmp_path, exchange):
     kps, desc = ss.kps[1:1 + G].cpu().numpy(), ss.desc[1:1 + G].cpu().numpy()
     nmatch, match = ss.nmatch.cpu().numpy(), ss.match.cpu().numpy()
     ur, ns = ss.ur.cpu().numpy(), ss.nstereo.cpu().numpy()
+    pm, npm = ss.pmatch.cpu().numpy(), ss.npmatch.cpu().numpy()
     for r in range(world):
         d = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
         lo = r * F
@@ -50,4 +51,7 @@ def test_two_ranks_equal_one_gpu(pkg, tmp_path, exchange):
             assert np.array_equal(d["kps"][f, :n], kps[lo + f, :n]) and np.array_equal(d["desc"][f, :n], desc[lo + f, :n])
             assert np.array_equal(d["uright"][f, :n], ur[lo + f, :n])
             assert np.array_equal(d["match"][f, :n], match[lo + f, :n])  # frame lo+f against its global predecessor
+            assert np.array_equal(d["pmatch"][f, :n], pm[lo + f, :n])   # SearchByProjection(Cur, Last): the predecessor's
+                                                                         # depths crossed the rank boundary with its record
         assert np.array_equal(d["nmatch"], nmatch[lo:lo + F]) and np.array_equal(d["nstereo"], ns[lo:lo + F])
+        assert np.array_equal(d["npmatch"], npm[lo:lo + F]) and npm.sum() > 0

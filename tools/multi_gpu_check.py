@@ -23,13 +23,14 @@ stream_mod = importlib.import_module("self_commit_orb-slam2_b200.stream")
 w, h = 1241, 376
 pairs = [synth_stereo(w, h, 700 + rank * F + i) for i in range(F)]
 imgs = np.stack([p[0] for p in pairs] + [p[1] for p in pairs])
-ss = stream_mod.StereoStream(F, w, h, 2000, device=local, rank=rank, world=world, exchange=exchange, stereo=True)
+ss = stream_mod.StereoStream(F, w, h, 2000, device=local, rank=rank, world=world, exchange=exchange, stereo=True, project=True)
 ss.upload(torch.from_numpy(imgs))
 ss.step_device()
 torch.cuda.synchronize()
 ss.ex.check()
 np.savez(os.path.join(out_dir, "rank%d.npz" % rank), counts=ss.counts[1:].cpu().numpy(), kps=ss.kps[1:1 + F].cpu().numpy(),
          desc=ss.desc[1:1 + F].cpu().numpy(), nmatch=ss.nmatch.cpu().numpy(), match=ss.match.cpu().numpy(),
-         uright=ss.ur.cpu().numpy(), nstereo=ss.nstereo.cpu().numpy())
+         uright=ss.ur.cpu().numpy(), nstereo=ss.nstereo.cpu().numpy(), pmatch=ss.pmatch.cpu().numpy(),
+         npmatch=ss.npmatch.cpu().numpy())
 dist.barrier()
 dist.destroy_process_group()
