@@ -71,6 +71,9 @@ struct BaPtrs {  // strided per-window arrays
   double *partChi, *partScale;   // per-CTA partial sums [window][nCta]
   unsigned int* bar;             // per-window barrier counters
   long long* prof;               // per-window phase cycle counters (debug): 16 slots
+  // balanced launch: CTA -> (window << 8 | index inside the window) and CTAs per window; null = uniform nCta per window
+  const int* ctaMap;
+  const int* winCtas;
 };
 
 // ---------------------------------------------------------------- small FP64 helpers
@@ -1665,12 +1668,20 @@ __device__ void phase_outliers(const BaPtrs& p, const WinCtx& c, const BaWin& W,
 
 // ---------------------------------------------------------------- the persistent kernel: grid = batch * nCta CTAs
 constexpr int BA_T = 256;
-__global__ void __launch_bounds__(BA_T) k_local_ba(BaPtrs p, int nCta, int wBase, int dbgRepeat) {
+__global__ void __launch_bounds__(BA_T) k_local_ba(BaPtrs p, int nCtaUniform, int wBase, int dbgRepeat) {
   extern __shared__ __align__(16) double dsm[];
   __shared__ double red[32];
   WinCtx c;
-  c.w = blockIdx.x / nCta;
-  c.cta = blockIdx.x - c.w * nCta;
+  int nCta = nCtaUniform;
+  if (p.ctaMap) {  // balanced launch: bigger windows own more CTAs
+    const int m = p.ctaMap[blockIdx.x];
+    c.w = m >> 8;
+    c.cta = m & 255;
+    nCta = p.winCtas[c.w];
+  } else {
+    c.w = blockIdx.x / nCta;
+    c.cta = blockIdx.x - c.w * nCta;
+  }
   c.w += wBase;
   c.nCta = nCta;
   c.gtid = c.cta * blockDim.x + threadIdx.x;
@@ -2248,6 +2259,7 @@ struct b2s_ba_solver {
   cudaEvent_t evLm[2] = {nullptr, nullptr};  // around the persistent LM kernel of the last batch (b2s_ba_last_kernel_ms)
   float lastLmMs = 0.f;
   long long lastTrials = 0;
+  int *dCtaMap = nullptr, *dWinCtas = nullptr;  // balanced launch tables (see ba_run)
 };
 
 static void quat_from_R_host(const double m[3][3], double* q) {
@@ -2347,6 +2359,9 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   A(&d.partChi, B * d.nPartE * 8); A(&d.partScale, B * d.nPartM * 8);
   A(&d.bar, B * 4);
   A(&d.prof, B * 16 * 8);
+  A(&h->dCtaMap, 1024 * 4); A(&h->dWinCtas, B * 4);
+  d.ctaMap = nullptr;
+  d.winCtas = nullptr;
   BaHostStage& s = h->hs;
   HA(&s.pose, B * max_kf * PSTRIDE * 8); HA(&s.pts, B * max_mp * 3 * 8);
   HA(&s.pidx, B * max_kf * 4); HA(&s.freeKf, B * max_kf * 4);
@@ -2561,7 +2576,62 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
   if (const char* ev = getenv("B2S_BA_CHUNK")) chunk = std::max(1, std::min(chunk, atoi(ev)));  // tuning knob
   int nCta = std::max(1, std::min(16, h->numSMs / chunk));
   if (const char* ev = getenv("B2S_BA_NCTA")) nCta = std::max(1, std::min(nCta, atoi(ev)));  // tuning knob
-  for (int wBase = 0; wBase < batch; wBase += chunk) {
+  // Balanced launch (one chunk, more than one window): the kernel ends with its slowest window, so the SMs are dealt by
+  // estimated cost instead of evenly.  Cost model (cycles of the phases measured with B2S_DEBUG_TIMING on 32 windows of
+  // 23-51 free keyframes / 16-40 k edges): a serial part (single-CTA factorisation, control) that grows with the number of
+  // free keyframes, and a part that divides over the window's CTAs (linearisation, Schur pairs ~ edges x observations per
+  // point, back-substitution, error pass).  Greedy: every window starts with one CTA, the currently slowest gets the next.
+  d.ctaMap = nullptr;
+  d.winCtas = nullptr;
+  bool balanced = false;
+  {
+    const char* ev = getenv("B2S_BA_BALANCE");
+    const bool want = !ev || atoi(ev) != 0;
+    int budget = h->numSMs;
+    if (const char* e2 = getenv("B2S_BA_SMS")) budget = std::max(batch, std::min(h->numSMs, atoi(e2)));
+    if (want && batch > 1 && chunk == batch && batch * 2 <= budget && !getenv("B2S_BA_NCTA")) {
+      std::vector<double> ser(batch), par(batch);
+      std::vector<int> n(batch, 1);
+      for (int w = 0; w < batch; w++) {
+        const double e = probs[w].n_edges * 1e-3, obs = probs[w].n_mp > 0 ? (double)probs[w].n_edges / probs[w].n_mp : 0.0;
+        ser[w] = 0.8 + 0.12 * nFree[w];
+        par[w] = 4.0 * (1.65 + 0.127 * e + 0.024 * e * obs);
+      }
+      for (int used = batch; used < budget; used++) {
+        int worst = -1;
+        double tw = -1.0;
+        for (int w = 0; w < batch; w++) {
+          if (n[w] >= 16) continue;
+          const double t = ser[w] + par[w] / n[w];
+          if (t > tw) { tw = t; worst = w; }
+        }
+        if (worst < 0) break;
+        n[worst]++;
+      }
+      std::vector<int> map;
+      for (int w = 0; w < batch; w++)
+        for (int k = 0; k < n[w]; k++) map.push_back((w << 8) | k);
+      B2S_CUDA(cudaMemcpyAsync(h->dCtaMap, map.data(), map.size() * 4, cudaMemcpyHostToDevice, st));
+      B2S_CUDA(cudaMemcpyAsync(h->dWinCtas, n.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, st));
+      B2S_CUDA(cudaStreamSynchronize(st));  // (the vectors are pageable host memory)
+      d.ctaMap = h->dCtaMap;
+      d.winCtas = h->dWinCtas;
+      balanced = true;
+      int gridCtas = (int)map.size(), dbgRepeat = 0, wBase = 0, one = 1;
+      if (const char* e3 = getenv("B2S_BA_REPEAT")) dbgRepeat = atoi(e3);
+      void* args[] = {(void*)&d, (void*)&one, (void*)&wBase, (void*)&dbgRepeat};
+      if (h->smemBytes > 48 * 1024)
+        B2S_CUDA(cudaFuncSetAttribute(k_local_ba, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+      B2S_CUDA(cudaLaunchCooperativeKernel((const void*)k_local_ba, dim3(gridCtas), dim3(BA_T), args, h->smemBytes, st));
+      h->launches++;
+      if (dbg) {
+        fprintf(stderr, "[b2s_local_ba] balanced launch, %d CTAs:", gridCtas);
+        for (int w = 0; w < batch; w++) fprintf(stderr, " %d", n[w]);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
+  for (int wBase = 0; wBase < batch && !balanced; wBase += chunk) {
     int nw = std::min(chunk, batch - wBase);
     int dbgRepeat = 0;
     if (const char* ev = getenv("B2S_BA_REPEAT")) dbgRepeat = atoi(ev);  // profiling aid, see k_local_ba
@@ -2658,6 +2728,18 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
     fprintf(stderr, "[b2s_local_ba] window 0 phase Mcycles:");
     for (int k = 0; k < 15; k++) fprintf(stderr, " %s=%.2f", names[k], prof[k] / 1e6);
     fprintf(stderr, "\n");
+    {  // every window: total of the phase slots (cycles of its CTA 0), size, and the three main phases
+      std::vector<long long> all((size_t)batch * 16);
+      cudaMemcpy(all.data(), d.prof, all.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      for (int w = 0; w < batch; w++) {
+        const long long* q = all.data() + (size_t)w * 16;
+        long long tot = 0;
+        for (int k = 0; k <= 10; k++) tot += q[k];
+        fprintf(stderr, "[b2s_local_ba]   w%02d free=%d mp=%d e=%d trials=%d total=%.2f Mcyc: build=%.2f schur=%.2f chol=%.2f(diag %.2f) backsub=%.2f err=%.2f\n",
+                w, nFree[w], probs[w].n_mp, probs[w].n_edges, s.st[w].nTrials, tot / 1e6, (q[0] + q[1]) / 1e6, q[5] / 1e6,
+                q[6] / 1e6, q[11] / 1e6, q[7] / 1e6, q[8] / 1e6);
+      }
+    }
     fprintf(stderr, "[b2s_local_ba] batch=%d nCta=%d prep+upload %.2f ms, structure+LM kernel %.2f ms, write-back %.2f ms\n",
             batch, nCta, ms(tStart, tPrep), ms(tPrep, tLoop), ms(tLoop, tEnd));
     float e01 = 0, e12 = 0, e23 = 0;
