@@ -422,7 +422,7 @@ def run_b200(args, rank, local_rank, world):
         os.environ.setdefault("B2S_BA_HOST_THREADS", str(max(2, min(16, effective_cpus()[0] // world))))
     ss = stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, ba_problems=windows, pose_problems=poses, stereo=True, ba_every=BA_EVERY,
                                  device=local_rank, rank=rank, world=world, ba_depth=args.ba_depth, exchange=args.exchange,
-                                 bf=BF, project=True, intrinsics=(FX, FY, CX, CY), motion=STREAM_MOTION)
+                                 bf=BF, project=True, intrinsics=(FX, FY, CX, CY), motion=STREAM_MOTION, ba_sms=args.ba_sms)
     imgs = make_stream_images(D, seed0=100000 * rank)  # [2, D, h, w], frame index = seed
     pinned = torch.from_numpy(imgs).pin_memory()
     d_all = pinned.cuda(non_blocking=True)
@@ -602,7 +602,8 @@ def run_b200(args, rank, local_rank, world):
         ba_gbs = BA_BYTES_TRIAL * ba_trials / (ba_kernel_ms * 1e-3) / 1e9
         fp64_peak = micro.get("fp64_dfma_tflops") or FP64_NOMINAL_TFLOPS
         line["roofline_local_ba"] = {
-            "kernel": "k_local_ba (persistent LM loop: %d different windows x 4 CTAs, one launch per LocalBA batch)" % n_ba,
+            "kernel": "k_local_ba (persistent LM loop: %d different windows on %s SMs dealt by estimated cost, one launch per "
+                      "LocalBA batch)" % (n_ba, args.ba_sms if args.ba_sms > 0 else "all"),
             "bound": "hbm", "achieved": ba_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ba_gbs / peaks["hbm_gbs"],
             "traffic": 5.21e6 * ba_trials, "traffic_source": "profiles/r2_ncu_full_k_local_ba.csv: 1.266 GB read + 1.235 GB written per launch of 480 LM trials",
             "launch_ms": ba_kernel_ms, "launch_ms_source": "CUDA events on the solver stream, batch run alone",
@@ -658,6 +659,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="boundary", choices=["boundary", "all"],
                     help="NCCL all-gather of the shard-boundary left-image record only, or of every left-image record")
+    ap.add_argument("--ba-sms", type=int, default=int(os.environ.get("B2S_BENCH_BA_SMS", "68")),
+                    help="SMs one LocalBA batch may occupy (b2s_ba_set_sm_budget; 0 = all)")
     ap.add_argument("--ba-depth", type=int, default=int(os.environ.get("B2S_BA_DEPTH", "2")),
                     help="LocalBA solver handles used round-robin by the pipelined stream (host work of batch i+1 overlaps the kernel of batch i)")
     args = ap.parse_args()

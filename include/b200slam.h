@@ -379,6 +379,12 @@ typedef struct b2s_ba_solver b2s_ba_solver;
 int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batch, int device, b2s_ba_solver** out);
 void b2s_ba_destroy(b2s_ba_solver* h);
 long long b2s_ba_launch_count(const b2s_ba_solver* h);
+/* How many SMs (= thread blocks of the persistent LM kernel) one batched call may occupy; 0 = all of them (default).  A batch
+ * of several windows deals this budget to the windows by estimated cost (the kernel ends with its slowest window).  All SMs
+ * give the shortest LocalBA latency; a pipeline that runs other kernels next to LocalBA gets more total throughput from about
+ * half of them, because a window's serial part (the reduced-system factorisation) idles fewer blocks.  One-window calls are
+ * not affected (16 blocks). */
+int b2s_ba_set_sm_budget(b2s_ba_solver* h, int sms);
 /* Duration (CUDA events on the solver's stream) of the persistent LM kernel of the last b2s_local_ba(_batch) call and the
  * number of LM trials (accepted + rejected, all windows) it ran — measurement hook for bench.py's roofline. */
 float b2s_ba_last_kernel_ms(const b2s_ba_solver* h, long long* lm_trials);

@@ -134,6 +134,7 @@ def lib():
             L.b2s_ba_last_kernel_ms.restype = ctypes.c_float
             L.b2s_ba_last_kernel_ms.argtypes = [_vp, _vp]
             L.b2s_local_ba.argtypes = [_vp, _vp, _vp, _vp]
+            L.b2s_ba_set_sm_budget.argtypes = [_vp, ctypes.c_int]
             L.b2s_local_ba_batch.argtypes = [_vp, ctypes.c_int, _vp, _vp]
         _lib = L
     return _lib
@@ -663,6 +664,10 @@ class Optimizer:
 
     def launch_count(self):
         return lib().b2s_ba_launch_count(self._h)
+
+    def set_sm_budget(self, sms):
+        """SMs one batched LocalBA call may occupy (b2s_ba_set_sm_budget); 0 = all."""
+        _check(lib().b2s_ba_set_sm_budget(self._h, int(sms)))
 
     def last_kernel_ms(self):
         """(ms, trials): duration of the persistent LM kernel of the last LocalBundleAdjustment(Batch) call, measured with

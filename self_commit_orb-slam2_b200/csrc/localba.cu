@@ -2260,6 +2260,7 @@ struct b2s_ba_solver {
   float lastLmMs = 0.f;
   long long lastTrials = 0;
   int *dCtaMap = nullptr, *dWinCtas = nullptr;  // balanced launch tables (see ba_run)
+  int smBudget = 0;  // CTAs (= SMs) one LocalBA batch may occupy; 0 = all (b2s_ba_set_sm_budget)
 };
 
 static void quat_from_R_host(const double m[3][3], double* q) {
@@ -2400,6 +2401,11 @@ extern "C" void b2s_ba_destroy(b2s_ba_solver* h) {
   delete h;
 }
 extern "C" long long b2s_ba_launch_count(const b2s_ba_solver* h) { return h ? h->launches : 0; }
+extern "C" int b2s_ba_set_sm_budget(b2s_ba_solver* h, int sms) {
+  if (!h || sms < 0) return B2S_ERR_BAD_ARG;
+  h->smBudget = sms;
+  return B2S_OK;
+}
 
 // Converter::toSE3Quat / toVector3d + CSR structure of one window, written into the pinned staging area
 // host threads for window preparation / write-back: min(batch, 16, cores), or B2S_BA_HOST_THREADS (several ranks per box
@@ -2587,9 +2593,9 @@ static int ba_run(b2s_ba_solver* h, int batch, const b2s_ba_problem* probs, cons
   {
     const char* ev = getenv("B2S_BA_BALANCE");
     const bool want = !ev || atoi(ev) != 0;
-    int budget = h->numSMs;
+    int budget = h->smBudget > 0 ? std::max(batch, std::min(h->numSMs, h->smBudget)) : h->numSMs;
     if (const char* e2 = getenv("B2S_BA_SMS")) budget = std::max(batch, std::min(h->numSMs, atoi(e2)));
-    if (want && batch > 1 && chunk == batch && batch * 2 <= budget && !getenv("B2S_BA_NCTA")) {
+    if (want && batch > 1 && chunk == batch && batch <= budget && !getenv("B2S_BA_NCTA")) {
       std::vector<double> ser(batch), par(batch);
       std::vector<int> n(batch, 1);
       for (int w = 0; w < batch; w++) {

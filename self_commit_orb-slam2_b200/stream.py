@@ -29,13 +29,15 @@ class StereoStream:
     def __init__(self, frames_per_step, width, height, nfeatures=2000, scale=1.2, nlevels=8, ini_th=20, min_th=7,
                  ba_problem=None, ba_every=5, device=0, rank=0, world=1, nnratio=0.7, ba_depth=1,
                  exchange="boundary", ba_problems=None, pose_problems=None, stereo=False, bf=386.1448, project=False,
-                 intrinsics=(718.856, 718.856, 607.1928, 185.2157), motion=None):
+                 intrinsics=(718.856, 718.856, 607.1928, 185.2157), motion=None, ba_sms=68):
         """ba_problems: list of LocalBA windows (a step solves ceil(F / ba_every) of them, taken round-robin);
         pose_problems: list of per-frame PoseOptimization problems (F per step, round-robin); stereo: run
         Frame::ComputeStereoMatches for the F pairs of every step on the resident pyramids; project (needs stereo): also
         run SearchByProjection(CurrentFrame, LastFrame) for every frame against its predecessor, the predecessor's stereo
         points moved by `motion` (Tcl, 3 x 4; default: 0.8 m forward with a small yaw, the KITTI-like case that takes the
-        reference's forward branch, src/ORBmatcher.cc:1595-1598)."""
+        reference's forward branch, src/ORBmatcher.cc:1595-1598).  ba_sms: SMs one LocalBA batch may occupy (0 = all): the LM
+        kernel shares the GPU with extraction and matching, and about half of the SMs gives the best stream throughput
+        (measured: 16.2 ms / step at 64-72 against 17.5 at 128-148; profiles/README.md)."""
         self.F, self.w, self.h = frames_per_step, width, height
         self.rank, self.world = rank, world
         self.dev = torch.device("cuda", device)
@@ -66,6 +68,7 @@ class StereoStream:
                 if self.pose_problems else None
             for _ in range(max(1, int(ba_depth))):
                 self.opts.append(Optimizer(max_kf=mk, max_mp=mm, max_edges=me, max_batch=max(1, self.n_ba), device=device))
+                self.opts[-1].set_sm_budget(ba_sms)
             self.opt = self.opts[0]
         F, cap = self.F, self.cap
         S = 1 + 2 * F  # slot 0: the frame before this shard; 1..F left images; F+1..2F right images
