@@ -420,9 +420,10 @@ def run_b200(args, rank, local_rank, world):
     poses = pose_problems(F, seed0=1000 * rank)
     if world > 1:  # several ranks share the host cores: split them for the LocalBA window preparation threads
         os.environ.setdefault("B2S_BA_HOST_THREADS", str(max(2, min(16, effective_cpus()[0] // world))))
-    ss = stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, ba_problems=windows, pose_problems=poses, stereo=True, ba_every=BA_EVERY,
-                                 device=local_rank, rank=rank, world=world, ba_depth=args.ba_depth, exchange=args.exchange,
-                                 bf=BF, project=True, intrinsics=(FX, FY, CX, CY), motion=STREAM_MOTION, ba_sms=args.ba_sms)
+    ss_kw = dict(ba_problems=windows, pose_problems=poses, stereo=True, ba_every=BA_EVERY, device=local_rank, rank=rank,
+                 world=world, ba_depth=args.ba_depth, exchange=args.exchange, bf=BF, project=True, intrinsics=(FX, FY, CX, CY),
+                 motion=STREAM_MOTION, ba_sms=args.ba_sms)
+    ss = stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, **ss_kw)
     imgs = make_stream_images(D, seed0=100000 * rank)  # [2, D, h, w], frame index = seed
     pinned = torch.from_numpy(imgs).pin_memory()
     d_all = pinned.cuda(non_blocking=True)
@@ -541,18 +542,37 @@ def run_b200(args, rank, local_rank, world):
     e2e_steps = args.steps if args.e2e_steps <= 0 else max(1, min(args.steps, args.e2e_steps))
     base_ptr, img_bytes = pinned.data_ptr(), W_IMG * H_IMG  # e2e inputs come from pinned host memory
 
-    def host_step(k):
+    # `--e2e-lanes` host-API pipelines (own handles, own pinned result buffers) take the steps in turn, each on its own host
+    # thread, so that the transfers of one step overlap the kernels of the next; every step still uploads its 2F images from
+    # pinned host memory and downloads all its results inside the timed region
+    lanes = [ss]
+    for _ in range(max(1, args.e2e_lanes) - 1):
+        kw = dict(ss_kw)
+        kw["ba_depth"] = 1
+        lanes.append(stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, **kw))
+
+    def host_step(lane, k):
         idx = [(k * F + i) % D for i in range(F)]
         ptrs = [base_ptr + i * img_bytes for i in idx] + [base_ptr + (D + i) * img_bytes for i in idx]
-        return ss.step_host(None, pipelined=True, img_ptrs=ptrs)
-    host_step(0)  # warm
-    ss.finish()
+        return lane.step_host(None, pipelined=True, img_ptrs=ptrs)
+
+    def lane_loop(j, first, last):
+        for k in range(first + j, last, len(lanes)):
+            host_step(lanes[j], k)
+        lanes[j].finish()
+    for j, lane in enumerate(lanes):  # warm
+        host_step(lane, j)
+        lane.finish()
     torch.cuda.synchronize()
     barrier()
+    import threading
     t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        n, nm, ba_out, _ = host_step(k + 1)
-    ss.finish()
+    th = [threading.Thread(target=lane_loop, args=(j, 1, 1 + e2e_steps)) for j in range(1, len(lanes))]
+    for t in th:
+        t.start()
+    lane_loop(0, 1, 1 + e2e_steps)
+    for t in th:
+        t.join()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -590,7 +610,7 @@ def run_b200(args, rank, local_rank, world):
         "vs_baseline": None, "dtype": "u8/int32 (extract, match), f64 (LocalBA)", "data": "synthetic",
         "config": workload_config(F, world),
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": ss.h2d_bytes_per_step(),
-                "d2h_bytes_per_step": ss.d2h_bytes_per_step(), "steps": e2e_steps},
+                "d2h_bytes_per_step": ss.d2h_bytes_per_step(), "steps": e2e_steps, "host_api_lanes": len(lanes)},
         "gpu_launches": int(launches),
         "phase_ms": phase,
         "clocks": clocks,
@@ -655,6 +675,8 @@ def main():
     ap.add_argument("--frames", type=int, default=160, help="stereo frames per step per GPU (160 -> 149 MB of images)")
     ap.add_argument("--ref-frames", type=int, default=0, help="stereo frames per step of the CPU reference arm (0: --frames)")
     ap.add_argument("--distinct", type=int, default=512, help="different stereo frames resident per GPU (seed = frame index)")
+    ap.add_argument("--e2e-lanes", type=int, default=int(os.environ.get("B2S_E2E_LANES", "2")),
+                    help="host-API pipelines that take the e2e steps in turn (double buffering of transfers and kernels)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end loop (0: the same K as --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="boundary", choices=["boundary", "all"],

@@ -364,9 +364,10 @@ __global__ void __launch_bounds__(128) k_fast_cells_list(ExtractGeom g, const ui
   }
 }
 
-int launch_fast_fallback(const ExtractGeom& g, const DeviceBuffers& d, int gridCtas, cudaStream_t st) {
+int launch_fast_fallback(const ExtractGeom& g, const DeviceBuffers& d, const uint2* fbList, const int32_t* fbCount, int gridCtas,
+                         cudaStream_t st) {
   k_fast_cells_list<<<gridCtas, 128, 0, st>>>(g, d.pyr, d.cellInfo, d.candXY, d.candKey, d.candResp, d.candCount, d.status,
-                                              d.fbList, d.fbCount);
+                                              fbList, fbCount);
   return B2S_OK;
 }
 
@@ -1673,7 +1674,7 @@ extern "C" int b2s_extractor_create(int nfeatures, float scaleFactor, int nlevel
   h->cellAlloc = (size_t)(div_up(max_width, 28) + 2) * (size_t)(div_up(max_height, 28) + 2) * 4 + 64;
   A((void**)&d.cellInfo, h->cellAlloc * 4);
   A((void**)&d.fbList, B * h->cellAlloc * sizeof(uint2));
-  A((void**)&d.fbCount, 4);
+  A((void**)&d.fbCount, B * 4);  // one counter per possible first image of a chunk (chunks of a batch run on two streams)
   A((void**)&d.rxOfs, h->rxAlloc * 2);
   A((void**)&d.rxAlpha, h->rxAlloc * 4);
   A((void**)&d.ryOfs, h->ryAlloc * 2);

@@ -48,7 +48,8 @@ struct DeviceBuffers {
   uint8_t* raw = nullptr;      // B x width*height dense upload staging (host-buffer batch path)
   uint8_t* score = nullptr;    // B x pyrBytes: FAST arc strength of every pixel (fused front end)
   uint32_t* bitmap = nullptr;  // B x bmWords: 1 bit per pixel, maxima of their cell above minThFAST (fused front end)
-  uint2* fbList = nullptr;     // (image, cell) pairs that need the minThFAST pass (no maximum above iniThFAST)
+  uint2* fbList = nullptr;     // (image, cell) pairs that need the minThFAST pass (no maximum above iniThFAST); the chunk that
+                               // starts at image b owns the entries from b * totalCells on and the counter fbCount[b]
   int32_t* fbCount = nullptr;
   int16_t* tileDx = nullptr;   // resize ownership tables of the fused front end
   int16_t* tileDy = nullptr;
@@ -77,7 +78,8 @@ struct b2s_extractor;
 namespace b2s {
 int tile_build(b2s_extractor* h);  // tensor maps + resize ownership tables for the current geometry
 int tile_run(b2s_extractor* h, int bBase, int batch, int path, cudaStream_t st, cudaEvent_t evAfterTiles);
-int launch_fast_fallback(const ExtractGeom& g, const DeviceBuffers& d, int gridCtas, cudaStream_t st);  // extractor.cu
+int launch_fast_fallback(const ExtractGeom& g, const DeviceBuffers& d, const uint2* fbList, const int32_t* fbCount, int gridCtas,
+                         cudaStream_t st);  // extractor.cu
 }  // namespace b2s
 
 struct b2s_extractor {

@@ -740,16 +740,19 @@ int tile_run(b2s_extractor* h, int bBase, int batch, int path, cudaStream_t st, 
     h->launches++;
   }
   if (evAfterTiles) cudaEventRecord(evAfterTiles, st);
-  B2S_CUDA(cudaMemsetAsync(d.fbCount, 0, 4, st));
+  // chunks of one batch run concurrently on two streams: each owns a slice of the fallback list and its own counter
+  uint2* fbList = d.fbList + (size_t)bBase * g.totalCells;
+  int32_t* fbCount = d.fbCount + bBase;
+  B2S_CUDA(cudaMemsetAsync(fbCount, 0, 4, st));
   int cellRows = 0;
   for (int l = 0; l < g.nlevels; l++) cellRows += g.lv[l].nRows;
   k_cells<<<dim3(cellRows, batch), 256, 0, st>>>(
       g, d.score + (size_t)bBase * g.pyrBytes, d.bitmap + (size_t)bBase * g.bmWords, d.candXY + (size_t)bBase * g.totalCandCap,
       d.candKey + (size_t)bBase * g.totalCandCap, d.candResp + (size_t)bBase * g.totalCandCap,
-      d.candCount + (size_t)bBase * kMaxLevels, d.status, d.fbList, d.fbCount, bBase);
+      d.candCount + (size_t)bBase * kMaxLevels, d.status, fbList, fbCount, bBase);
   h->launches++;
   // minThFAST pass for the listed cells (persistent CTAs; the list length stays on the device)
-  launch_fast_fallback(g, d, std::min(g.totalCells * batch, 148 * 16), st);
+  launch_fast_fallback(g, d, fbList, fbCount, std::min(g.totalCells * batch, 148 * 16), st);
   h->launches++;
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;

@@ -119,3 +119,35 @@ def test_batch_upload_paths(pkg, oracle):
             for f in ("x", "y", "size", "angle", "response", "octave", "class_id"):
                 assert np.array_equal(k[f], ok[f]), (i, f)
             assert np.array_equal(d, od), i
+
+
+def test_chunked_batches_from_two_threads(pkg):
+    """b2s_extract_batch cuts batches of >= 16 images into chunks that run on two streams; two handles on two host threads
+    overlap them further.  Every chunk owns its slice of the minThFAST fallback list (weak-texture images put EVERY cell on
+    that list), so the results must equal the one-image-at-a-time results whatever the interleaving."""
+    import threading
+    w, h, B = 640, 480, 32
+    rng = np.random.RandomState(11)
+    imgs = []
+    for b in range(B):
+        if b % 3 == 0:
+            imgs.append((100 + rng.randint(0, 24, size=(h, w))).astype(np.uint8))  # weak texture: fallback in every cell
+        else:
+            imgs.append(synth_image(w, h, 300 + b))
+    one = pkg.ORBextractor(500, 1.2, 8, 20, 7, max_width=w, max_height=h)
+    ref = [one(im) for im in imgs]
+    exs = [pkg.ORBextractor(500, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B) for _ in range(2)]
+    bad = []
+
+    def run(ex, order):
+        for it in range(6):
+            out = ex.extract_batch([imgs[i] for i in order])
+            for j, i in enumerate(order):
+                if not (np.array_equal(out[j][0], ref[i][0]) and np.array_equal(out[j][1], ref[i][1])):
+                    bad.append((it, i))
+    th = [threading.Thread(target=run, args=(exs[0], list(range(B)))), threading.Thread(target=run, args=(exs[1], list(range(B - 1, -1, -1))))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not bad, bad[:8]
