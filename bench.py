@@ -595,7 +595,9 @@ def run_b200(args, rank, local_rank, world):
     roof = {"kernel": "k_tile x 8 levels + k_cells + k_fast_cells_list (TMA-staged tile: FAST strength + NMS bitmap + Q8 blur + "
                       "next pyramid level; per-cell threshold rules)", "bound": "hbm", "achieved": achieved,
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": TRAFFIC_TILE_IMAGE * images_per_launch,
-            "traffic_source": TRAFFIC_TILE_SOURCE, "peak_source": peak_src, "launch_ms": tile_ms, "launch_ms_isolated": tile_iso,
+            "traffic_source": TRAFFIC_TILE_SOURCE,
+            "traffic_frac": (TRAFFIC_TILE_IMAGE * images_per_launch / (tile_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if tile_ms > 0 else None,
+            "peak_source": peak_src, "launch_ms": tile_ms, "launch_ms_isolated": tile_iso,
             "algorithmic_bytes_per_launch": B_TILE_IMAGE * images_per_launch,
             "algorithmic_bytes_note": "SURVEY 8d per image: pyramid R+W 2,385,248 + FAST read 1,444,097 + blur R+W 2,888,194 B",
             "issue_bound": {"note": "the tile kernel is bound by the ALU pipe (packed u16x2 min/max of FAST), not by HBM",
@@ -626,6 +628,10 @@ def run_b200(args, rank, local_rank, world):
                       "LocalBA batch)" % (n_ba, args.ba_sms if args.ba_sms > 0 else "all"),
             "bound": "hbm", "achieved": ba_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ba_gbs / peaks["hbm_gbs"],
             "traffic": 5.21e6 * ba_trials, "traffic_source": "profiles/r2_ncu_full_k_local_ba.csv: 1.266 GB read + 1.235 GB written per launch of 480 LM trials",
+            "traffic_frac": 5.21e6 * ba_trials / (ba_kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "tensor_pipe": {"dmma_subpipe_pct": 0.07, "fp64_pipe_pct": 18.8, "source": "profiles/r2_ncu_full_k_local_ba.csv "
+                            "(sm__inst_executed_pipe_tensor_subpipe_dmma / sm__inst_executed_pipe_fp64, pct of peak sustained active): "
+                            "DMMA.8x8x4 carries the trailing update of the reduced-system factorisation only"},
             "launch_ms": ba_kernel_ms, "launch_ms_source": "CUDA events on the solver stream, batch run alone",
             "lm_trials": ba_trials, "algorithmic_bytes_per_launch": BA_BYTES_TRIAL * ba_trials,
             "algorithmic_bytes_note": "SURVEY 8d: 16 MB per LM trial of a 50/5000/30k window (scaled by the launch's trial count)",
