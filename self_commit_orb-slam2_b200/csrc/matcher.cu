@@ -102,6 +102,8 @@ __global__ void k_rank_by_key(const int32_t* __restrict__ keyBase, const int32_t
 // SearchByBoW, stage 1: per keyframe-side row, K best frame-side candidates of the same vocabulary node
 // key = dist<<16 | j   (j ascending == the reference's candidate iteration order inside a node)
 // ------------------------------------------------------------------------------------------------
+// Only candidates closer than `cut` are listed and counted (bow_distance_cut below): no other candidate can change a
+// decision of the resolver.
 // One thread per keyframe-side row (its descriptor and K-list live in registers); the frame-side descriptors of the pair
 // are staged once per CTA in shared memory and read as warp-wide broadcasts, so every distance costs
 // 8 XOR + 8 POPC + 8 IADD per lane and no cross-lane merge is needed.
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(256) k_bow_topk(const uint8_t* __restrict__ de
                                                   const uint8_t* __restrict__ validA, const int32_t* __restrict__ nAarr,
                                                   int capA, const uint8_t* __restrict__ descB,
                                                   const int32_t* __restrict__ nodeB, const uint8_t* __restrict__ validB,
-                                                  const int32_t* __restrict__ nBarr, int capB,
+                                                  const int32_t* __restrict__ nBarr, int capB, int cut,
                                                   uint32_t* __restrict__ topk, int32_t* __restrict__ candCnt) {
   __shared__ __align__(32) uint32_t sB[BOW_TILE * 8];
   __shared__ __align__(16) int32_t sNode[BOW_TILE];
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(256) k_bow_topk(const uint8_t* __restrict__ de
           const uint4 b1 = *reinterpret_cast<const uint4*>(&sB[(j + q) * 8 + 4]);
           const int d = hamming256_words(da.w[0] ^ b0.x, da.w[1] ^ b0.y, da.w[2] ^ b0.z, da.w[3] ^ b0.w, da.w[4] ^ b1.x,
                                          da.w[5] ^ b1.y, da.w[6] ^ b1.z, da.w[7] ^ b1.w);
-          const bool ok = (nds[q] == na) && ((vv >> (8 * q)) & 0xffu) && (j + q < tn);
+          const bool ok = (nds[q] == na) && ((vv >> (8 * q)) & 0xffu) && (j + q < tn) && (d < cut);
           cnt += ok ? 1 : 0;
           const uint32_t key = ok ? (((uint32_t)d << 16) | (uint32_t)(j0 + j + q)) : EMPTY;
           if (key < t[TOPK - 1]) topk_insert(t, key);
@@ -168,6 +170,169 @@ __global__ void __launch_bounds__(256) k_bow_topk(const uint8_t* __restrict__ de
 #pragma unroll
     for (int k = 0; k < TOPK; k++) topk[(oa + i) * TOPK + k] = t[k];
     candCnt[oa + i] = cnt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same stage on the integer tensor pipe.  popc(a ^ b) = popc(a) + popc(b) - 2 popc(a & b), and popc(a & b) of two
+// 256-bit strings is the dot product of their bits written as 0 / 1 bytes: a 16 x 8 tile of distances is eight
+// mma.sync.m16n8k32.u8 (IMMA.16832; the sm_100a tensor pipe issues one per 8 cycles and SMSP, measured
+// tools/probe/imma_probe.cu: 140 G warp-instructions/s = 2.2 T distances/s against 0.27 T/s of the scalar kernel above).
+// A CTA owns 128 keyframe-side rows (4 warps x 32 rows, bit-expanded A fragments live in registers for the whole sweep) and
+// walks the frame side in stages of 64 columns expanded into shared memory.  Because a dot product does not care about the
+// order of its terms, the 256 byte positions are laid out in FRAGMENT order: lane (g, t) of k-step s owns the eight bits of
+// descriptor byte 4 s + t, on both sides, so a B fragment is one conflict-free LDS.64 (column pitch 288 B).
+// Selection: lane (g, t) sees rows {g, g+8, g+16, g+24} x columns {2t, 2t+1} of every 8-column block and keeps a K-list
+// per row; keys are unique (column index in the low half), so the K smallest of the four lanes' lists are exactly the K
+// smallest of the row — the lists are merged once at the end and written in ascending order like k_bow_topk's.
+// ------------------------------------------------------------------------------------------------
+constexpr int BI_ROWS = 128, BI_COLS = 64, BI_PITCH = 288;
+__device__ __forceinline__ void expand_byte(uint32_t x, uint32_t& lo, uint32_t& hi) {  // bit i of x -> byte i (0 / 1)
+  lo = ((x & 0xFu) * 0x00204081u) & 0x01010101u;
+  hi = (((x >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+}
+__device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(128) k_bow_topk_imma(const uint8_t* __restrict__ descA, const int32_t* __restrict__ nodeA,
+                                                       const uint8_t* __restrict__ validA, const int32_t* __restrict__ nAarr,
+                                                       int capA, const uint8_t* __restrict__ descB,
+                                                       const int32_t* __restrict__ nodeB, const uint8_t* __restrict__ validB,
+                                                       const int32_t* __restrict__ nBarr, int capB, int cut,
+                                                       uint32_t* __restrict__ topk, int32_t* __restrict__ candCnt) {
+  __shared__ __align__(16) uint8_t sB[BI_COLS * BI_PITCH];
+  __shared__ __align__(8) int32_t sNode[BI_COLS];
+  // (popc(b) << 16 | column index); a column that is no candidate at all carries 0x7000 in the distance field, which no
+  // popc(a) - 2 popc(a & b) in [-512, 256] can bring below the cut
+  __shared__ __align__(8) uint32_t sBase[BI_COLS];
+  const uint32_t cutKey = (uint32_t)cut << 16;
+  const int pair = blockIdx.y;
+  const int nA = min(nAarr[pair], capA), nB = min(nBarr[pair], capB);
+  const int row0 = blockIdx.x * BI_ROWS;
+  if (row0 >= nA) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const size_t oa = (size_t)pair * capA, ob = (size_t)pair * capB;
+  // ---- A side: four rows per lane, expanded fragments for the 8 k-steps of both 16-row tiles
+  uint32_t aF[2][8][4];
+  int rowIdx[4], rowNode[4];
+  uint32_t rowPa16[4];  // popc(a) << 16
+  bool rowOk[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int i = row0 + warp * 32 + g + 8 * q;
+    rowIdx[q] = i;
+    rowOk[q] = (i < nA) && (!validA || validA[oa + i]);
+    u256 da;
+    if (rowOk[q]) {
+      da = ld_desc(descA + oa * 32, i);
+      rowNode[q] = nodeA[oa + i];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) da.w[k] = 0;
+      rowNode[q] = -1;
+    }
+    int pa = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) pa += __popc(da.w[k]);
+    rowPa16[q] = (uint32_t)pa << 16;
+#pragma unroll
+    for (int sx = 0; sx < 8; sx++) {
+      uint32_t lo, hi;
+      expand_byte((da.w[sx] >> (8 * t)) & 0xFFu, lo, hi);
+      // rows g (q = 0, 2) fill a0 / a2, rows g + 8 (q = 1, 3) fill a1 / a3 of tile q >> 1
+      aF[q >> 1][sx][q & 1] = lo;
+      aF[q >> 1][sx][2 + (q & 1)] = hi;
+    }
+  }
+  uint32_t kl[4][TOPK];
+  int cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+#pragma unroll
+    for (int k = 0; k < TOPK; k++) kl[q][k] = EMPTY;
+  for (int j0 = 0; j0 < nB; j0 += BI_COLS) {
+    __syncthreads();
+    {  // stage 64 frame-side descriptors: thread (column, half) expands 16 bytes into 128
+      const int col = tid >> 1, half = tid & 1, j = j0 + col;
+      uint4 w = make_uint4(0u, 0u, 0u, 0u);
+      bool ok = j < nB;
+      if (ok) {
+        w = *reinterpret_cast<const uint4*>(descB + (ob + j) * 32 + half * 16);
+        ok = !validB || validB[ob + j];
+      }
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+      uint8_t* dst = sB + col * BI_PITCH + half * 128;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t e[8];
+#pragma unroll
+        for (int bt = 0; bt < 4; bt++) expand_byte((ww[k] >> (8 * bt)) & 0xFFu, e[2 * bt], e[2 * bt + 1]);
+        *reinterpret_cast<uint4*>(dst + k * 32) = make_uint4(e[0], e[1], e[2], e[3]);
+        *reinterpret_cast<uint4*>(dst + k * 32 + 16) = make_uint4(e[4], e[5], e[6], e[7]);
+      }
+      int pb = __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+      pb += __shfl_xor_sync(0xffffffffu, pb, 1);
+      if (half == 0) {
+        sBase[col] = ((uint32_t)(ok ? pb : 0x7000) << 16) | (uint32_t)(j & 0xffff);
+        sNode[col] = (j < nB) ? nodeB[ob + j] : -2;
+      }
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int nb = 0; nb < BI_COLS / 8; nb++) {
+      int acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+      const uint8_t* bp = sB + (nb * 8 + g) * BI_PITCH + 8 * t;
+#pragma unroll
+      for (int sx = 0; sx < 8; sx++) {
+        const uint2 bf = *reinterpret_cast<const uint2*>(bp + 32 * sx);
+        imma_16832(acc[0], aF[0][sx], bf.x, bf.y);
+        imma_16832(acc[1], aF[1][sx], bf.x, bf.y);
+      }
+      // this lane's two columns of the block
+      const uint2 base = *reinterpret_cast<const uint2*>(&sBase[nb * 8 + 2 * t]);
+      const int2 nd = *reinterpret_cast<const int2*>(&sNode[nb * 8 + 2 * t]);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {  // row g + 8 q: tile q >> 1, accumulators (q & 1) * 2 + {0, 1}
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          const uint32_t bj = cc ? base.y : base.x;
+          const int ndj = cc ? nd.y : nd.x;
+          const int pc = acc[q >> 1][(q & 1) * 2 + cc];
+          const uint32_t key = bj + rowPa16[q] - ((uint32_t)pc << 17);  // dist << 16 | column
+          const bool ok = (key < cutKey) && (ndj == rowNode[q]);
+          cnt[q] += ok ? 1 : 0;
+          if (ok) topk_insert(kl[q], key);  // (rare: only candidates below the cut get here)
+        }
+      }
+    }
+  }
+  // ---- merge the four lanes of a row (t = 0..3): K rounds of "smallest head wins, its owner pops"
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    int c = cnt[q];
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    uint32_t out[TOPK];
+#pragma unroll
+    for (int k = 0; k < TOPK; k++) {
+      uint32_t m = kl[q][0];
+      m = min(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = min(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      out[k] = m;
+      if (m != EMPTY && kl[q][0] == m) {
+#pragma unroll
+        for (int z = 0; z < TOPK - 1; z++) kl[q][z] = kl[q][z + 1];
+        kl[q][TOPK - 1] = EMPTY;
+      }
+    }
+    if (t == 0 && rowIdx[q] < nA) {
+      uint4* dst = reinterpret_cast<uint4*>(topk + (oa + rowIdx[q]) * TOPK);
+      dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+      dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+      candCnt[oa + rowIdx[q]] = c;
+    }
   }
 }
 
@@ -1443,6 +1608,18 @@ extern "C" int b2s_descriptor_distance(b2s_matcher* h, const uint8_t* a, const u
   return B2S_OK;
 }
 
+// Distance from which a frame-side candidate cannot influence SearchByBoW (src/ORBmatcher.cc:284-310): a best candidate is
+// only accepted with bestDist1 <= TH_LOW, and a second best at distance b2 only enters through bestDist1 < ratio * b2, which
+// holds for every acceptable bestDist1 as soon as ratio * b2 > TH_LOW.  With cut = floor(TH_LOW / ratio) + 2 every candidate
+// at distance >= cut is (a) never an accepted best and (b) as second best indistinguishable from "no second candidate"
+// (bestDist2 = 256).  The K-lists therefore hold, and candCnt counts, only the candidates below the cut; the resolver's
+// "complete" test and its exact rescan keep their meaning on that set.  257 = no cut (distances are <= 256).
+static int bow_distance_cut(int th_low, float nnratio) {
+  if (!(nnratio > 0.f) || th_low < 0) return 257;
+  const double c = floor((double)th_low / (double)nnratio) + 2.0;
+  return c < 257.0 ? (int)c : 257;
+}
+
 // device-resident, batched core (asynchronous)
 extern "C" int b2s_search_by_bow_device(b2s_matcher* h, int batch, const uint8_t* d_descA, const int32_t* d_nodeA,
                                         const uint8_t* d_validA, const float* d_angA, const int32_t* d_nA, int capA,
@@ -1460,8 +1637,15 @@ extern "C" int b2s_search_by_bow_device(b2s_matcher* h, int batch, const uint8_t
   MatchParams mp{th_low, nnratio, strict_lt, check_ori};
   k_fill_i32<<<div_up(batch * capB, 256), 256, 0, st>>>(d_matchB, -1, (size_t)batch * capB);
   k_rank_by_key<<<dim3(div_up(capA, 128), batch), 128, 0, st>>>(d_nodeA, d_nA, capA, h->dOrder);
-  k_bow_topk<<<dim3(div_up(capA, 256), batch), 256, 0, st>>>(d_descA, d_nodeA, d_validA, d_nA, capA, d_descB, d_nodeB,
-                                                           d_validB, d_nB, capB, h->dTopk, h->dCandCnt);
+  static const int scalarTopk = getenv("B2S_BOW_SCALAR") ? atoi(getenv("B2S_BOW_SCALAR")) : 0;  // (A/B switch for profiling)
+  const int cut = bow_distance_cut(th_low, nnratio);
+  if (scalarTopk)
+    k_bow_topk<<<dim3(div_up(capA, 256), batch), 256, 0, st>>>(d_descA, d_nodeA, d_validA, d_nA, capA, d_descB, d_nodeB,
+                                                             d_validB, d_nB, capB, cut, h->dTopk, h->dCandCnt);
+  else
+    k_bow_topk_imma<<<dim3(div_up(capA, BI_ROWS), batch), 128, 0, st>>>(d_descA, d_nodeA, d_validA, d_nA, capA, d_descB,
+                                                                        d_nodeB, d_validB, d_nB, capB, cut, h->dTopk,
+                                                                        h->dCandCnt);
   k_bow_resolve<<<dim3(div_up(capA, 4), batch), 128, 0, st>>>(d_descA, d_nodeA, d_validA, d_angA, d_nA, capA, d_descB,
                                                               d_nodeB, d_validB, d_angB, d_nB, capB, h->dOrder, h->dTopk,
                                                               h->dCandCnt, mp, d_matchB, h->dBin);
