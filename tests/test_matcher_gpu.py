@@ -61,6 +61,54 @@ def test_search_by_bow_contention(pkg, oracle):
     assert cnt == on and np.array_equal(match, omatch)
 
 
+@pytest.mark.parametrize("nnratio,th_low", [(0.7, 50), (0.6, 50), (0.9, 50), (0.75, 100), (0.3, 50)])
+def test_search_by_bow_distance_cut_boundaries(pkg, oracle, nnratio, th_low):
+    """The K-list stage only lists candidates closer than cut = floor(TH_LOW / ratio) + 2 (bow_distance_cut): rows whose best /
+    second-best distances sit on and around TH_LOW, ratio * second and the cut itself, with 0, 1, 2 and > 8 candidates below
+    the cut, plus rows that compete for the same frame feature, must still match the oracle exactly."""
+    rng = np.random.RandomState(int(nnratio * 100) + th_low)
+    cut = int(np.floor(th_low / nnratio)) + 2
+
+    def flipped(d, k):
+        o = d.copy()
+        for b in rng.choice(256, size=k, replace=False):
+            o[b >> 3] ^= np.uint8(1 << (b & 7))
+        return o
+    A, B, nodeA, nodeB = [], [], [], []
+    dists = sorted(set([0, 1, th_low - 1, th_low, th_low + 1, cut - 2, cut - 1, cut, cut + 1, int(th_low * nnratio), 255, 256]))
+    dists = [d for d in dists if 0 <= d <= 256]
+    node = 0
+    for d1 in dists:
+        for d2 in dists:
+            if d2 < d1:
+                continue
+            a = rng.randint(0, 256, size=32).astype(np.uint8)
+            A.append(a)
+            nodeA.append(node)
+            B += [flipped(a, d1), flipped(a, d2)]
+            nodeB += [node, node]
+            node += 1
+    # a crowded node: 12 candidates below the cut for each of 6 rows that share them (K-list overflow + contention)
+    c = rng.randint(0, 256, size=32).astype(np.uint8)
+    for r in range(6):
+        A.append(flipped(c, r))
+        nodeA.append(node)
+    for k in range(12):
+        B.append(flipped(c, min(max(cut - 14 + k, 0), 256)))
+        nodeB.append(node)
+    A, B = np.array(A, np.uint8), np.array(B, np.uint8)
+    nodeA, nodeB = np.array(nodeA, np.int32), np.array(nodeB, np.int32)
+    vA = np.ones(len(A), np.uint8)
+    aA, aB = np.zeros(len(A), np.float32), np.zeros(len(B), np.float32)
+    for strict in (False, True):
+        m = pkg.ORBmatcher(nnratio, False)
+        n, match = m.SearchByBoW(A, nodeA, vA, aA, B, nodeB, aB, strict_lt=strict, th_low=th_low)
+        on, omatch = oracle.search_by_bow(A, nodeA, vA, aA, B, nodeB, aB, nnratio=nnratio, strict_lt=strict, check_ori=False,
+                                          th_low=th_low)
+        assert n == on and np.array_equal(match, omatch)
+        assert n > 0
+
+
 def test_search_by_bow_ragged(pkg, oracle):
     m = pkg.ORBmatcher(0.7, True)
     A, nA, vA, aA, B, nB, aB = synth_descriptors(333, seed=5, n_nodes=7)
