@@ -68,6 +68,7 @@ struct BaPtrs {  // strided per-window arrays
   int capPairs, capBlk;
   double* eWq;             // per edge: rho' * invSigma2 of the last build (0: edge excluded), for the W_e recomputation
   int schurRecompute;      // Schur phase recomputes W_e from (pose, landmark, eWq) instead of gathering the stored blocks
+  int schurDmma;           // ... and forms the 6 x 6 block products on the FP64 tensor pipe (DMMA.8x8x4)
   double *partChi, *partScale;   // per-CTA partial sums [window][nCta]
   unsigned int* bar;             // per-window barrier counters
   long long* prof;               // per-window phase cycle counters (debug): 16 slots
@@ -986,7 +987,8 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 
 // per-warp staging of the recomputing Schur loop (double2 units): W_a | W_c tiles (one 9-double2 record per lane each),
 // two Dinv tiles (5 per lane) and two operand tiles (3 per lane: X0 X1 | X2 wq_a | wq_c -), then R|t of the block's two poses
-constexpr int RC_W = 0, RC_D = 32 * 18, RC_OP = RC_D + 2 * 32 * 5, RC_RT = RC_OP + 2 * 32 * 3, RC_TOTAL = RC_RT + 12;
+constexpr int RC_W = 0, RC_D = 32 * 18, RC_OP = RC_D + 2 * 32 * 5, RC_RT = RC_OP + 2 * 32 * 3, RC_DB = RC_RT + 12,
+              RC_TOTAL = RC_DB + 48;  // RC_DB: Dinv b_l of the 32 pairs of an iteration (DMMA variant, diagonal blocks)
 static_assert(RC_TOTAL <= 2 * GATHER_TILE16, "the recomputing loop reuses the gather staging area");
 
 // Same accumulation as schur_block_pairs, but W_a / W_c are recomputed per pair from 40 bytes of operands that stay
@@ -1046,6 +1048,127 @@ __device__ __forceinline__ void schur_block_pairs_rc(const int4* prs, int qBeg, 
   cp_async_wait<0>();
 }
 
+// The same block sum on the FP64 tensor pipe.  With the pairs p of the block stacked along k = 3 p + j,
+//   S(i1,i2) -= A B,   A[r][k] = W_a,p[r][j]  (6 x 3P),   B[k][c] = (W_c,p Dinv_p)[c][j]  (3P x 6),
+// and for a diagonal block one more column B[k][6] = (Dinv_p b_p)[j], which makes column 6 of the product the block's
+// right-hand-side sum W_a (Dinv b).  An iteration handles 32 pairs: every lane recomputes its pair's W_a (and W_c), forms
+// Z = W_c Dinv in registers and leaves W_a | Z | Dinv b in the warp's staging tile; 24 mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4)
+// then consume the 96 k-positions, each lane feeding A[g][k0+t] and B[k0+t][g] (g = lane / 4, t = lane % 4; rows / columns
+// 6, 7 of the 8 x 8 tile are zero padding).  The warp's whole block lives in two accumulator registers per lane
+// (C[g][2t], C[g][2t+1]): no per-lane 6 x 6 partial sums and no 36-value warp reduction at the end of the block.
+template <bool DIAG>
+__device__ __forceinline__ void schur_block_pairs_dmma(const int4* prs, int qBeg, int qEnd, const double* __restrict__ pts,
+                                                       const double* __restrict__ eWq, const double2* Db, double2* buf, int lane,
+                                                       double fx, double fy, double bf, double& c0, double& c1) {
+  const int nIt = (qEnd - qBeg + 31) >> 5;
+  double* sA = reinterpret_cast<double*>(buf + RC_W);            // [pair][r * 3 + j]
+  double* sZ = reinterpret_cast<double*>(buf + RC_W + 32 * 9);   // [pair][c * 3 + j]
+  double* sDb = reinterpret_cast<double*>(buf + RC_DB);          // [pair][j]
+  const double* Rt = reinterpret_cast<const double*>(buf + RC_RT);
+  const int g = lane >> 2, t = lane & 3;
+  auto issue = [&](int slot, const int4& r, bool v) {
+    double2* op = buf + RC_OP + slot * (32 * 3) + lane * 3;
+    if (v) {
+      const double* X = pts + (size_t)r.z * 3;
+      double* o = reinterpret_cast<double*>(op);
+      cp_async8(o, X);
+      cp_async8(o + 1, X + 1);
+      cp_async8(o + 2, X + 2);
+      cp_async8(o + 3, eWq + r.x);
+      if (!DIAG) cp_async8(o + 4, eWq + r.y);
+    }
+    warp_gather16_async<DIAG ? 5 : 3, 5>(buf + RC_D + slot * (32 * 5), Db, r.z, lane);
+  };
+  auto loadRec = [&](int it, int4& r, bool& v) {
+    const int q = qBeg + it * 32 + lane;
+    v = q < qEnd;
+    r = v ? prs[q] : make_int4(0, 0, 0, 0);
+  };
+  int4 r0, r1 = make_int4(0, 0, 0, 0);
+  bool v0, v1 = false;
+  loadRec(0, r0, v0);
+  issue(0, r0, v0);
+  cp_async_commit();
+  if (nIt > 1) loadRec(1, r1, v1);
+  for (int it = 0; it < nIt; it++) {
+    const int slot = it & 1;
+    if (it + 1 < nIt) issue(slot ^ 1, r1, v1);
+    cp_async_commit();
+    int4 r2 = make_int4(0, 0, 0, 0);
+    bool v2 = false;
+    if (it + 2 < nIt) loadRec(it + 2, r2, v2);
+    cp_async_wait<1>();
+    __syncwarp();
+    {
+      double wa[18], z[18];
+      double db0 = 0.0, db1 = 0.0, db2 = 0.0;
+      if (v0) {
+        const double* o = reinterpret_cast<const double*>(buf + RC_OP + slot * (32 * 3) + lane * 3);
+        const double X0 = o[0], X1 = o[1], X2 = o[2];
+        edge_W_regs(Rt, X0, X1, X2, (r0.w & 1) != 0, o[3], fx, fy, bf, wa);
+        double wc[18];
+        if (!DIAG) edge_W_regs(Rt + 12, X0, X1, X2, (r0.w & 2) != 0, o[4], fx, fy, bf, wc);
+        const double2* rd = buf + RC_D + slot * (32 * 5) + lane * (DIAG ? 5 : 3);
+        const double2 dA = rd[0], dB = rd[1], dC = rd[2];
+        const double d00 = dA.x, d01 = dA.y, d02 = dB.x, d11 = dB.y, d12 = dC.x, d22 = dC.y;
+        if (DIAG) {
+          const double2 e0 = rd[3], e1 = rd[4];
+          db0 = e0.x; db1 = e0.y; db2 = e1.x;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 6; cc++) {
+          const double w0 = DIAG ? wa[cc * 3] : wc[cc * 3], w1 = DIAG ? wa[cc * 3 + 1] : wc[cc * 3 + 1],
+                       w2 = DIAG ? wa[cc * 3 + 2] : wc[cc * 3 + 2];
+          z[cc * 3] = w0 * d00 + w1 * d01 + w2 * d02;
+          z[cc * 3 + 1] = w0 * d01 + w1 * d11 + w2 * d12;
+          z[cc * 3 + 2] = w0 * d02 + w1 * d12 + w2 * d22;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 18; k++) {
+          wa[k] = 0.0;
+          z[k] = 0.0;
+        }
+      }
+      double2* oa = reinterpret_cast<double2*>(sA + lane * 18);
+      double2* oz = reinterpret_cast<double2*>(sZ + lane * 18);
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        oa[k] = make_double2(wa[2 * k], wa[2 * k + 1]);
+        oz[k] = make_double2(z[2 * k], z[2 * k + 1]);
+      }
+      if (DIAG) {
+        sDb[lane * 3] = db0;
+        sDb[lane * 3 + 1] = db1;
+        sDb[lane * 3 + 2] = db2;
+      }
+    }
+    __syncwarp();
+    const int kEnd = min(32, qEnd - qBeg - it * 32) * 3;  // k-positions that carry a pair (the rest of the tile is zero)
+#pragma unroll 4
+    for (int k0 = 0; k0 < 96; k0 += 4) {
+      if (k0 >= kEnd) break;  // (warp-uniform)
+      const int k = k0 + t;
+      const int pr = (k * 0xAAABu) >> 17;  // k / 3 for k < 98304
+      const int j = k - 3 * pr;
+      double av = 0.0, bv = 0.0;
+      if (g < 6) {
+        av = sA[pr * 18 + g * 3 + j];
+        bv = sZ[pr * 18 + g * 3 + j];
+      } else if (DIAG && g == 6) {
+        bv = sDb[pr * 3 + j];
+      }
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                   : "+d"(c0), "+d"(c1)
+                   : "d"(av), "d"(bv));
+    }
+    __syncwarp();
+    r0 = r1; v0 = v1;
+    r1 = r2; v1 = v2;
+  }
+  cp_async_wait<0>();
+}
+
 // Schur complement (block_solver.hpp:381-439): one warp per lower block (i1 >= i2); lanes stride over the block's
 // covisibility pairs (edge a of pose i1, edge c of pose i2, same landmark l) and accumulate (W_a Dinv_l) W_c^T; the
 // diagonal blocks also accumulate W_a (Dinv_l b_l) for the right-hand side.  S(i1,i2) = [Hpp + lambda I] - sum.
@@ -1080,10 +1203,31 @@ __device__ void phase_schur_blocks(const BaPtrs& p, const WinCtx& c, const BaWin
 #pragma unroll
     for (int z = 0; z < 10; z++) tail[z] = 0;
     bool any = true;
+    const bool dmma = usePairs && p.schurRecompute && p.schurDmma;
+    double c0 = 0.0, c1 = 0.0;  // DMMA variant: C[g][2t], C[g][2t+1] of the block's 8 x 8 product tile
     if (usePairs) {
       const int qBeg = off[t], qEnd = off[t + 1];
       any = qEnd > qBeg;
-      if (any && p.schurRecompute) {
+      if (any && dmma) {
+        __syncwarp();
+        if (lane < 2) {
+          const int kf = p.freeKf[(size_t)w * p.capKf + (lane ? i2 : i1)];
+          const double* P = p.pose + ((size_t)w * p.capKf + kf) * PSTRIDE;
+          double R[3][3];
+          quat_to_R(P, R);
+          double* o = reinterpret_cast<double*>(buf + RC_RT) + lane * 12;
+#pragma unroll
+          for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b2 = 0; b2 < 3; b2++) o[a * 3 + b2] = R[a][b2];
+          o[9] = P[4]; o[10] = P[5]; o[11] = P[6];
+        }
+        __syncwarp();
+        const double* ptsW = p.pts + (size_t)w * p.capMp * 3;
+        const double* wqW = p.eWqB[cur] + (size_t)w * p.capE;
+        if (diag) schur_block_pairs_dmma<true>(prs, qBeg, qEnd, ptsW, wqW, Db, buf, lane, W.fx, W.fy, W.bf, c0, c1);
+        else schur_block_pairs_dmma<false>(prs, qBeg, qEnd, ptsW, wqW, Db, buf, lane, W.fx, W.fy, W.bf, c0, c1);
+      } else if (any && p.schurRecompute) {
         // rotation / translation of the block's two cameras, staged once per block for the whole warp
         __syncwarp();
         if (lane < 2) {
@@ -1138,6 +1282,28 @@ __device__ void phase_schur_blocks(const BaPtrs& p, const WinCtx& c, const BaWin
         }
         __syncwarp();
       }
+    }
+    if (dmma) {  // lane (g, t) holds columns 2t, 2t+1 of row g; column 6 of a diagonal block is its right-hand-side sum
+      double* Sb = p.S + (size_t)w * p.ldS * p.ldS + (size_t)(i1 * 6) * p.ldS + i2 * 6;
+      const double* Hp = p.Hpp + ((size_t)w * p.capKf + i1) * 36;
+      const int g = lane >> 2, t4 = lane & 3;
+      if (g < 6 && t4 < 3) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int cc = 2 * t4 + h;
+          double base = 0;
+          if (diag) {
+            base = Hp[g * 6 + cc];
+            if (g == cc) base += lambda;
+          }
+          Sb[(size_t)g * p.ldS + cc] = base - (h ? c1 : c0);
+        }
+      }
+      if (diag && g < 6 && t4 == 3) {
+        const double* bp = p.b + (size_t)w * (p.capKf * 6 + p.capMp * 3) + (size_t)i1 * 6;
+        p.S[(size_t)w * p.ldS * p.ldS + (size_t)n * p.ldS + i1 * 6 + g] = bp[g] - c0;
+      }
+      continue;
     }
     double mine = 0;
     if (any) {  // (warp-uniform) a block without pairs is just its Hpp part
@@ -2347,6 +2513,12 @@ extern "C" int b2s_ba_create(int max_kf, int max_mp, int max_edges, int max_batc
   A(&d.errB[1], B * max_edges * 24);
   d.schurRecompute = 1;
   if (const char* ev = getenv("B2S_BA_SCHUR_RC")) d.schurRecompute = atoi(ev) != 0;  // 0: gather the stored W blocks
+  // Measured (32 different windows, profiles/README.md): the DMMA form of the Schur products is 2 x SLOWER than the per-lane
+  // FMA form (Schur phase 8.3 vs 4.1 Mcycles, LM kernel 9.2 vs 7.6 ms) — a 6 x 3 . 3 x 6 product fills 42 % of an 8 x 8 x 4 tile,
+  // the 24 DMMAs of an iteration form one dependent chain, and the FP64 tensor pipe of this GPU has no rate advantage over the
+  // FP64 FMA pipe.  Kept as a tested option (results identical within the LM tolerances, same traces), off by default.
+  d.schurDmma = 0;
+  if (const char* ev = getenv("B2S_BA_SCHUR_DMMA")) d.schurDmma = atoi(ev) != 0;     // 1: block products on DMMA.8x8x4
   A(&d.mpStart, B * (max_mp + 1) * 4); A(&d.mpEdges, B * max_edges * 4);
   A(&d.kfStart, B * (max_kf + 1) * 4); A(&d.kfEdges, B * max_edges * 4);
   A(&d.Hpp, B * max_kf * 36 * 8); A(&d.Hll, B * max_mp * 9 * 8);
