@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) k_bow_topk(const uint8_t* __restrict__ de
 // per row; keys are unique (column index in the low half), so the K smallest of the four lanes' lists are exactly the K
 // smallest of the row — the lists are merged once at the end and written in ascending order like k_bow_topk's.
 // ------------------------------------------------------------------------------------------------
-constexpr int BI_ROWS = 128, BI_COLS = 64, BI_PITCH = 288;
+constexpr int BI_ROWS = 128, BI_PITCH = 288;
 __device__ __forceinline__ void expand_byte(uint32_t x, uint32_t& lo, uint32_t& hi) {  // bit i of x -> byte i (0 / 1)
   lo = ((x & 0xFu) * 0x00204081u) & 0x01010101u;
   hi = (((x >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
@@ -196,7 +196,8 @@ __device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], 
                : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__global__ void __launch_bounds__(128) k_bow_topk_imma(const uint8_t* __restrict__ descA, const int32_t* __restrict__ nodeA,
+template <int BI_COLS, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_bow_topk_imma(const uint8_t* __restrict__ descA, const int32_t* __restrict__ nodeA,
                                                        const uint8_t* __restrict__ validA, const int32_t* __restrict__ nAarr,
                                                        int capA, const uint8_t* __restrict__ descB,
                                                        const int32_t* __restrict__ nodeB, const uint8_t* __restrict__ validB,
@@ -254,8 +255,8 @@ __global__ void __launch_bounds__(128) k_bow_topk_imma(const uint8_t* __restrict
     for (int k = 0; k < TOPK; k++) kl[q][k] = EMPTY;
   for (int j0 = 0; j0 < nB; j0 += BI_COLS) {
     __syncthreads();
-    {  // stage 64 frame-side descriptors: thread (column, half) expands 16 bytes into 128
-      const int col = tid >> 1, half = tid & 1, j = j0 + col;
+    for (int cbase = 0; cbase < BI_COLS; cbase += 64) {  // stage: thread (column, half) expands 16 bytes into 128
+      const int col = cbase + (tid >> 1), half = tid & 1, j = j0 + col;
       uint4 w = make_uint4(0u, 0u, 0u, 0u);
       bool ok = j < nB;
       if (ok) {
@@ -1643,9 +1644,16 @@ extern "C" int b2s_search_by_bow_device(b2s_matcher* h, int batch, const uint8_t
     k_bow_topk<<<dim3(div_up(capA, 256), batch), 256, 0, st>>>(d_descA, d_nodeA, d_validA, d_nA, capA, d_descB, d_nodeB,
                                                              d_validB, d_nB, capB, cut, h->dTopk, h->dCandCnt);
   else
-    k_bow_topk_imma<<<dim3(div_up(capA, BI_ROWS), batch), 128, 0, st>>>(d_descA, d_nodeA, d_validA, d_nA, capA, d_descB,
-                                                                        d_nodeB, d_validB, d_nB, capB, cut, h->dTopk,
-                                                                        h->dCandCnt);
+  {
+    static const int variant = getenv("B2S_BOW_VARIANT") ? atoi(getenv("B2S_BOW_VARIANT")) : 0;  // (tuning switch)
+    const dim3 grid(div_up(capA, BI_ROWS), batch);
+#define B2S_BOW_ARGS d_descA, d_nodeA, d_validA, d_nA, capA, d_descB, d_nodeB, d_validB, d_nB, capB, cut, h->dTopk, h->dCandCnt
+    if (variant == 1) k_bow_topk_imma<64, 4><<<grid, 128, 0, st>>>(B2S_BOW_ARGS);
+    else if (variant == 2) k_bow_topk_imma<128, 3><<<grid, 128, 0, st>>>(B2S_BOW_ARGS);
+    else if (variant == 3) k_bow_topk_imma<128, 4><<<grid, 128, 0, st>>>(B2S_BOW_ARGS);
+    else k_bow_topk_imma<64, 3><<<grid, 128, 0, st>>>(B2S_BOW_ARGS);
+#undef B2S_BOW_ARGS
+  }
   k_bow_resolve<<<dim3(div_up(capA, 4), batch), 128, 0, st>>>(d_descA, d_nodeA, d_validA, d_angA, d_nA, capA, d_descB,
                                                               d_nodeB, d_validB, d_angB, d_nB, capB, h->dOrder, h->dTopk,
                                                               h->dCandCnt, mp, d_matchB, h->dBin);
