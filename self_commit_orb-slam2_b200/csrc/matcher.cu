@@ -291,20 +291,29 @@ __global__ void __launch_bounds__(128, MINB) k_bow_topk_imma(const uint8_t* __re
         imma_16832(acc[0], aF[0][sx], bf.x, bf.y);
         imma_16832(acc[1], aF[1][sx], bf.x, bf.y);
       }
-      // this lane's two columns of the block
+      // this lane's two columns of the block: keys (dist << 16 | column) of its 8 elements; the common case is that none of
+      // them is below the cut, which ONE comparison of their minimum decides
       const uint2 base = *reinterpret_cast<const uint2*>(&sBase[nb * 8 + 2 * t]);
-      const int2 nd = *reinterpret_cast<const int2*>(&sNode[nb * 8 + 2 * t]);
+      uint32_t key[4][2];
 #pragma unroll
       for (int q = 0; q < 4; q++) {  // row g + 8 q: tile q >> 1, accumulators (q & 1) * 2 + {0, 1}
+        key[q][0] = base.x + rowPa16[q] - ((uint32_t)acc[q >> 1][(q & 1) * 2] << 17);
+        key[q][1] = base.y + rowPa16[q] - ((uint32_t)acc[q >> 1][(q & 1) * 2 + 1] << 17);
+      }
+      const uint32_t m01 = min(min(key[0][0], key[0][1]), min(key[1][0], key[1][1]));
+      const uint32_t m23 = min(min(key[2][0], key[2][1]), min(key[3][0], key[3][1]));
+      if (min(m01, m23) < cutKey) {  // rare: a candidate below the cut
+        const int2 nd = *reinterpret_cast<const int2*>(&sNode[nb * 8 + 2 * t]);
 #pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-          const uint32_t bj = cc ? base.y : base.x;
-          const int ndj = cc ? nd.y : nd.x;
-          const int pc = acc[q >> 1][(q & 1) * 2 + cc];
-          const uint32_t key = bj + rowPa16[q] - ((uint32_t)pc << 17);  // dist << 16 | column
-          const bool ok = (key < cutKey) && (ndj == rowNode[q]);
-          cnt[q] += ok ? 1 : 0;
-          if (ok) topk_insert(kl[q], key);  // (rare: only candidates below the cut get here)
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+          for (int cc = 0; cc < 2; cc++) {
+            const bool ok = (key[q][cc] < cutKey) && ((cc ? nd.y : nd.x) == rowNode[q]);
+            if (ok) {
+              cnt[q]++;
+              topk_insert(kl[q], key[q][cc]);
+            }
+          }
         }
       }
     }
