@@ -39,8 +39,8 @@ B_TILE_IMAGE = 2385248 + 1444097 + 2888194  # the stages the fused tile kernel r
 STAGE_NAMES = ["resize_chain(legacy)", "tile_fast_blur_pyramid+cells", "quadtree", "blur(legacy)", "orient_describe"]
 # dram__bytes_read.sum + dram__bytes_write.sum of the eight k_tile launches of a 320-image batch (ncu --set full), per image;
 # None until a capture of the current kernel is committed under profiles/
-TRAFFIC_TILE_IMAGE = 4387000.0  # (475.0 MB read + 928.8 MB written) / 320 images, 8 k_tile launches of one ncu --set full capture
-TRAFFIC_TILE_SOURCE = "profiles/r2_ncu_full_k_tile_all_levels.csv (dram__bytes_read.sum + dram__bytes_write.sum over the 8 level launches)"
+TRAFFIC_TILE_IMAGE = 4378000.0  # (475.0 MB read + 926.1 MB written) / 320 images, 8 k_tile launches of one ncu --set full capture
+TRAFFIC_TILE_SOURCE = "profiles/r2_final_ncu_full_k_tile.csv (dram__bytes_read.sum + dram__bytes_write.sum over the 8 level launches)"
 B_FAST_IMAGE = 1444097           # FAST stage: every pyramid pixel read once (sum of the 8 level sizes)
 # dram__bytes_read.sum + dram__bytes_write.sum of one 320-image k_fast_cells launch (ncu --set full,
 # profiles/r1_ncu_full_k_fast_cells_v15.csv: 408.31 MB + 46.83 MB), per image
@@ -627,9 +627,9 @@ def run_b200(args, rank, local_rank, world):
             "kernel": "k_local_ba (persistent LM loop: %d different windows on %s SMs dealt by estimated cost, one launch per "
                       "LocalBA batch)" % (n_ba, args.ba_sms if args.ba_sms > 0 else "all"),
             "bound": "hbm", "achieved": ba_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ba_gbs / peaks["hbm_gbs"],
-            "traffic": 5.21e6 * ba_trials, "traffic_source": "profiles/r2_ncu_full_k_local_ba.csv: 1.266 GB read + 1.235 GB written per launch of 480 LM trials",
+            "traffic": 5.21e6 * ba_trials, "traffic_source": "profiles/r2_final_ncu_full_k_local_ba.csv: 1.268 GB read + 1.242 GB written per launch of 480 LM trials",
             "traffic_frac": 5.21e6 * ba_trials / (ba_kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-            "tensor_pipe": {"dmma_subpipe_pct": 0.07, "fp64_pipe_pct": 18.8, "source": "profiles/r2_ncu_full_k_local_ba.csv "
+            "tensor_pipe": {"dmma_subpipe_pct": 0.09, "fp64_pipe_pct": 23.7, "source": "profiles/r2_final_ncu_full_k_local_ba.csv "
                             "(sm__inst_executed_pipe_tensor_subpipe_dmma / sm__inst_executed_pipe_fp64, pct of peak sustained active): "
                             "DMMA.8x8x4 carries the trailing update of the reduced-system factorisation only"},
             "launch_ms": ba_kernel_ms, "launch_ms_source": "CUDA events on the solver stream, batch run alone",
@@ -638,7 +638,8 @@ def run_b200(args, rank, local_rank, world):
             "fp64": {"achieved_tflops": BA_FLOP_TRIAL * ba_trials / (ba_kernel_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
                      "peak_source": "measured DFMA micro-benchmark in this run" if micro.get("fp64_dfma_tflops") else "nominal",
                      "frac": BA_FLOP_TRIAL * ba_trials / (ba_kernel_ms * 1e-3) / 1e12 / fp64_peak},
-            "note": "latency-bound (window barriers, dependent gathers at 8 warps/SM): issue slots 20 % busy, FP64 pipe 19 % in the capture"}
+            "note": "latency-bound (window barriers, dependent FP64 chains at 8 warps/SM): issue slots 25 % busy, FP64 pipe 24 %, "
+                    "barrier stall 1.9 warps per issue in the capture (68 SMs)"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(F)
     print(json.dumps(line), flush=True)
