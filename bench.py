@@ -596,6 +596,9 @@ def run_b200(args, rank, local_rank, world):
                       "next pyramid level; per-cell threshold rules)", "bound": "hbm", "achieved": achieved,
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": TRAFFIC_TILE_IMAGE * images_per_launch,
             "traffic_source": TRAFFIC_TILE_SOURCE,
+            "frac_isolated": (B_TILE_IMAGE * images_per_launch / (tile_iso * 1e-3) / 1e9 / peaks["hbm_gbs"]) if tile_iso else None,
+            "frac_note": "launch_ms is measured inside the timed steps, where LocalBA holds %s of the 148 SMs exclusively; "
+                         "launch_ms_isolated / frac_isolated are the same launches without the solvers running" % (args.ba_sms if args.ba_sms > 0 else "all"),
             "traffic_frac": (TRAFFIC_TILE_IMAGE * images_per_launch / (tile_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if tile_ms > 0 else None,
             "peak_source": peak_src, "launch_ms": tile_ms, "launch_ms_isolated": tile_iso,
             "algorithmic_bytes_per_launch": B_TILE_IMAGE * images_per_launch,
@@ -629,6 +632,10 @@ def run_b200(args, rank, local_rank, world):
             "bound": "hbm", "achieved": ba_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ba_gbs / peaks["hbm_gbs"],
             "traffic": 5.21e6 * ba_trials, "traffic_source": "profiles/r2_final_ncu_full_k_local_ba.csv: 1.268 GB read + 1.242 GB written per launch of 480 LM trials",
             "traffic_frac": 5.21e6 * ba_trials / (ba_kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "sms_used": (args.ba_sms if args.ba_sms > 0 else 148),
+            "frac_of_sm_share": ba_gbs / peaks["hbm_gbs"] / ((args.ba_sms if args.ba_sms > 0 else 148) / 148.0),
+            "sm_budget_note": "the batch runs on a budget of SMs (b2s_ba_set_sm_budget) because the step time is the SUM of the SM-time of "
+                              "LocalBA and of the front end; on all 148 SMs the same launch takes 7.5 ms (frac 0.156) but the step is slower",
             "tensor_pipe": {"dmma_subpipe_pct": 0.09, "fp64_pipe_pct": 23.7, "source": "profiles/r2_final_ncu_full_k_local_ba.csv "
                             "(sm__inst_executed_pipe_tensor_subpipe_dmma / sm__inst_executed_pipe_fp64, pct of peak sustained active): "
                             "DMMA.8x8x4 carries the trailing update of the reduced-system factorisation only"},
