@@ -430,19 +430,35 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.synchronize()
     step_no = [0]
 
+    # `--dev-lanes` device-resident pipelines (own handles and streams) take the steps in turn: the low-occupancy kernels of one
+    # step (greedy resolvers, quadtree, PoseOptimization) then overlap the wide kernels of the next
+    dev_lanes = [ss]
+    for _ in range(max(1, args.dev_lanes) - 1):
+        kw = dict(ss_kw)
+        kw["ba_depth"] = 1
+        dev_lanes.append(stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, **kw))
+
     def dev_step():
-        ss.load_window(d_all, (step_no[0] * F) % D)
+        lane = dev_lanes[step_no[0] % len(dev_lanes)]
+        lane.load_window(d_all, (step_no[0] * F) % D)
         step_no[0] += 1
-        return ss.step_device(pipelined=True)  # solvers of step k overlap extraction / matching of step k+1
+        return lane.step_device(pipelined=True)  # solvers of step k overlap extraction / matching of step k+1
+
+    def dev_finish():
+        for lane in dev_lanes:
+            lane.finish()
+
+    def dev_launches():
+        return sum(lane.launch_count() for lane in dev_lanes)
 
     def barrier():
         if dist is not None:
             dist.barrier()
 
     # ---------------- device-resident throughput (`value`)
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, len(dev_lanes))):
         dev_step()
-    ss.finish()
+    dev_finish()
     ss.ex.check()
     torch.cuda.synchronize()
     barrier()
@@ -450,7 +466,7 @@ def run_b200(args, rank, local_rank, world):
     L.b2s_extractor_set_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.b2s_extractor_get_timing.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.b2s_extractor_set_timing(ss.ex._h, 1)
-    launches0 = ss.launch_count()
+    launches0 = dev_launches()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -459,7 +475,7 @@ def run_b200(args, rank, local_rank, world):
     ev0.record(ss.stream)
     for _ in range(args.steps):
         dev_step()
-    ss.finish()                         # the last solver batch is joined inside the timed region
+    dev_finish()                        # the last solver batches are joined inside the timed region
     ev1.record(ss.stream)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -468,7 +484,7 @@ def run_b200(args, rank, local_rank, world):
     # the solver batches run on their own streams and are synchronous on their host thread, so the host wall clock bounds
     # everything
     dev_ms = max(ev0.elapsed_time(ev1), wall * 1e3)
-    launches = ss.launch_count() - launches0
+    launches = dev_launches() - launches0
     stage = (ctypes.c_double * 5)()
     calls = ctypes.c_longlong(0)
     L.b2s_extractor_get_timing(ss.ex._h, stage, ctypes.byref(calls))
@@ -545,8 +561,8 @@ def run_b200(args, rank, local_rank, world):
     # `--e2e-lanes` host-API pipelines (own handles, own pinned result buffers) take the steps in turn, each on its own host
     # thread, so that the transfers of one step overlap the kernels of the next; every step still uploads its 2F images from
     # pinned host memory and downloads all its results inside the timed region
-    lanes = [ss]
-    for _ in range(max(1, args.e2e_lanes) - 1):
+    lanes = list(dev_lanes[:max(1, args.e2e_lanes)])
+    for _ in range(max(1, args.e2e_lanes) - len(lanes)):
         kw = dict(ss_kw)
         kw["ba_depth"] = 1
         lanes.append(stream_mod.StereoStream(F, W_IMG, H_IMG, NFEAT, **kw))
@@ -623,6 +639,8 @@ def run_b200(args, rank, local_rank, world):
         "device_peaks_measured": micro,
     }
     line["config"]["distinct_frames_resident"] = D
+    line["config"]["pipelines"] = ("%d device-resident lanes (value) / %d host-API lanes (e2e) take the steps in turn; LocalBA batches on a "
+                                   "budget of %s SMs" % (len(dev_lanes), len(lanes), args.ba_sms if args.ba_sms > 0 else "all"))
     if ba_kernel_ms > 0:
         ba_gbs = BA_BYTES_TRIAL * ba_trials / (ba_kernel_ms * 1e-3) / 1e9
         fp64_peak = micro.get("fp64_dfma_tflops") or FP64_NOMINAL_TFLOPS
@@ -689,13 +707,15 @@ def main():
     ap.add_argument("--frames", type=int, default=160, help="stereo frames per step per GPU (160 -> 149 MB of images)")
     ap.add_argument("--ref-frames", type=int, default=0, help="stereo frames per step of the CPU reference arm (0: --frames)")
     ap.add_argument("--distinct", type=int, default=512, help="different stereo frames resident per GPU (seed = frame index)")
+    ap.add_argument("--dev-lanes", type=int, default=int(os.environ.get("B2S_DEV_LANES", "2")),
+                    help="device-resident pipelines that take the timed steps in turn")
     ap.add_argument("--e2e-lanes", type=int, default=int(os.environ.get("B2S_E2E_LANES", "2")),
                     help="host-API pipelines that take the e2e steps in turn (double buffering of transfers and kernels)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end loop (0: the same K as --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="boundary", choices=["boundary", "all"],
                     help="NCCL all-gather of the shard-boundary left-image record only, or of every left-image record")
-    ap.add_argument("--ba-sms", type=int, default=int(os.environ.get("B2S_BENCH_BA_SMS", "68")),
+    ap.add_argument("--ba-sms", type=int, default=int(os.environ.get("B2S_BENCH_BA_SMS", "64")),
                     help="SMs one LocalBA batch may occupy (b2s_ba_set_sm_budget; 0 = all)")
     ap.add_argument("--ba-depth", type=int, default=int(os.environ.get("B2S_BA_DEPTH", "2")),
                     help="LocalBA solver handles used round-robin by the pipelined stream (host work of batch i+1 overlaps the kernel of batch i)")

@@ -29,7 +29,7 @@ class StereoStream:
     def __init__(self, frames_per_step, width, height, nfeatures=2000, scale=1.2, nlevels=8, ini_th=20, min_th=7,
                  ba_problem=None, ba_every=5, device=0, rank=0, world=1, nnratio=0.7, ba_depth=1,
                  exchange="boundary", ba_problems=None, pose_problems=None, stereo=False, bf=386.1448, project=False,
-                 intrinsics=(718.856, 718.856, 607.1928, 185.2157), motion=None, ba_sms=68):
+                 intrinsics=(718.856, 718.856, 607.1928, 185.2157), motion=None, ba_sms=64):
         """ba_problems: list of LocalBA windows (a step solves ceil(F / ba_every) of them, taken round-robin);
         pose_problems: list of per-frame PoseOptimization problems (F per step, round-robin); stereo: run
         Frame::ComputeStereoMatches for the F pairs of every step on the resident pyramids; project (needs stereo): also
