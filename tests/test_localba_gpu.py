@@ -93,6 +93,22 @@ def test_local_ba_batch(pkg, oracle):
         _check(out, oracle.local_ba(d), d)
 
 
+@pytest.mark.parametrize("budget", [0, 5, 9, 24])
+def test_local_ba_batch_sm_budget(pkg, oracle, budget):
+    """b2s_ba_set_sm_budget: a batch deals its thread blocks to the windows by estimated cost (1 .. 16 per window); whatever
+    the split, every window must reproduce the oracle's LM trace, outlier flags and values."""
+    ds = [synth_local_ba(n_kf=12, n_fixed=3, n_mp=400, obs_per_mp=5, seed=21),
+          synth_local_ba(n_kf=16, n_fixed=4, n_mp=500, obs_per_mp=7, seed=22, mono_frac=0.2),
+          synth_local_ba(n_kf=6, n_fixed=1, n_mp=120, obs_per_mp=4, seed=23),
+          synth_local_ba(n_kf=9, n_fixed=2, n_mp=300, obs_per_mp=6, seed=24, outlier_frac=0.05),
+          synth_local_ba(n_kf=14, n_fixed=2, n_mp=200, obs_per_mp=4, seed=25)]
+    opt = pkg.Optimizer(max_kf=16, max_mp=512, max_edges=4096, max_batch=5)
+    opt.set_sm_budget(budget)
+    outs = opt.LocalBundleAdjustmentBatch(ds)
+    for d, out in zip(ds, outs):
+        _check(out, oracle.local_ba(d), d)
+
+
 def test_local_ba_shuffled_keyframes(pkg, oracle):
     """Keyframe ids permuted: the covisibility pattern of the reduced system is scattered instead of banded, so the
     envelope logic of the Cholesky and the sorted Schur block order see a general structure."""
