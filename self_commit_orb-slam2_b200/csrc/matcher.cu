@@ -1626,7 +1626,8 @@ extern "C" int b2s_descriptor_distance(b2s_matcher* h, const uint8_t* a, const u
 // "complete" test and its exact rescan keep their meaning on that set.  257 = no cut (distances are <= 256).
 static int bow_distance_cut(int th_low, float nnratio) {
   if (!(nnratio > 0.f) || th_low < 0) return 257;
-  const double c = floor((double)th_low / (double)nnratio) + 2.0;
+  double c = floor((double)th_low / (double)nnratio) + 2.0;
+  if (c < th_low + 2.0) c = th_low + 2.0;  // (a ratio above 1: every distance up to TH_LOW can still be an accepted best)
   return c < 257.0 ? (int)c : 257;
 }
 

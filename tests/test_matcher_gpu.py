@@ -61,13 +61,13 @@ def test_search_by_bow_contention(pkg, oracle):
     assert cnt == on and np.array_equal(match, omatch)
 
 
-@pytest.mark.parametrize("nnratio,th_low", [(0.7, 50), (0.6, 50), (0.9, 50), (0.75, 100), (0.3, 50)])
+@pytest.mark.parametrize("nnratio,th_low", [(0.7, 50), (0.6, 50), (0.9, 50), (0.75, 100), (0.3, 50), (1.5, 50)])
 def test_search_by_bow_distance_cut_boundaries(pkg, oracle, nnratio, th_low):
     """The K-list stage only lists candidates closer than cut = floor(TH_LOW / ratio) + 2 (bow_distance_cut): rows whose best /
     second-best distances sit on and around TH_LOW, ratio * second and the cut itself, with 0, 1, 2 and > 8 candidates below
     the cut, plus rows that compete for the same frame feature, must still match the oracle exactly."""
     rng = np.random.RandomState(int(nnratio * 100) + th_low)
-    cut = int(np.floor(th_low / nnratio)) + 2
+    cut = max(int(np.floor(th_low / nnratio)) + 2, th_low + 2)
 
     def flipped(d, k):
         o = d.copy()
