@@ -142,6 +142,11 @@ int b2s_search_by_bow_batch(b2s_matcher* h, int batch, const uint8_t* descA, con
                             const uint8_t* validB, const float* angB, const int32_t* nB, int capB, int th_low,
                             float nnratio, int strict_lt, int check_ori, int32_t* matchB, int32_t* nmatches);
 
+/* Test hook (host only, no GPU needed): the distance from which a frame-side candidate cannot influence SearchByBoW for
+ * (TH_LOW, ratio) — the K-list stage lists and counts only candidates below it (257 = no cut).  tests/test_bow_cut_logic.py
+ * checks by enumeration that no decision of src/ORBmatcher.cc:284-310 can depend on a candidate at or beyond it. */
+int b2s_debug_bow_distance_cut(int th_low, float nnratio);
+
 /* Batched device-resident variant: `batch` independent (A,B) pairs with strides capA/capB features. All pointers are
  * DEVICE pointers; nA/nB are device int arrays [batch]. Asynchronous on `stream`. */
 int b2s_search_by_bow_device(b2s_matcher* h, int batch, const uint8_t* d_descA, const int32_t* d_nodeA,

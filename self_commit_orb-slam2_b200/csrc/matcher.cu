@@ -1631,6 +1631,8 @@ static int bow_distance_cut(int th_low, float nnratio) {
   return c < 257.0 ? (int)c : 257;
 }
 
+extern "C" int b2s_debug_bow_distance_cut(int th_low, float nnratio) { return bow_distance_cut(th_low, nnratio); }
+
 // device-resident, batched core (asynchronous)
 extern "C" int b2s_search_by_bow_device(b2s_matcher* h, int batch, const uint8_t* d_descA, const int32_t* d_nodeA,
                                         const uint8_t* d_validA, const float* d_angA, const int32_t* d_nA, int capA,
