@@ -518,6 +518,30 @@ def run_b200(args, rank, local_rank, world):
     phase["keypoints_per_image"] = float(ss.counts[1:].float().mean().item())
     phase["projection_matches_per_frame"] = float(ss.npmatch.float().mean().item())
     phase["bow_matches_per_frame"] = float(ss.nmatch.float().mean().item())
+    try:  # the batched SearchByBoW call alone (rank + K-lists + resolver + cull) on the records of the last step
+        _vp = ctypes.c_void_p
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st = ss.stream.cuda_stream
+
+        def bow_call():
+            pkg._check(L.b2s_search_by_bow_device(ss.matcher._h, F, _vp(ss.desc.data_ptr()), _vp(ss.node.data_ptr()),
+                                                  _vp(ss.valid.data_ptr()), _vp(ss.ang.data_ptr()), _vp(ss.counts.data_ptr()),
+                                                  ss.cap, _vp(ss.desc[1:].data_ptr()), _vp(ss.node[1:].data_ptr()), None,
+                                                  _vp(ss.ang[1:].data_ptr()), _vp(ss.counts[1:].data_ptr()), ss.cap, 50,
+                                                  float(ss.matcher.mfNNratio), 0, 1, _vp(ss.match.data_ptr()),
+                                                  _vp(ss.nmatch.data_ptr()), _vp(st)))
+        bow_call()
+        torch.cuda.synchronize()
+        e0.record(ss.stream)
+        for _ in range(5):
+            bow_call()
+        e1.record(ss.stream)
+        torch.cuda.synchronize()
+        phase["search_by_bow_batch_ms"] = e0.elapsed_time(e1) / 5
+        cn = ss.counts.cpu().numpy().astype(np.float64)
+        phase["search_by_bow_descriptor_pairs"] = float((cn[:F] * cn[1:1 + F]).sum())
+    except Exception as ex:
+        phase["search_by_bow_side_measurement_error"] = str(ex)[:200]
     ba_kernel_ms, ba_trials = 0.0, 0
     try:
         t1 = time.perf_counter()
@@ -665,6 +689,16 @@ def run_b200(args, rank, local_rank, world):
                      "frac": BA_FLOP_TRIAL * ba_trials / (ba_kernel_ms * 1e-3) / 1e12 / fp64_peak},
             "note": "latency-bound (window barriers, dependent FP64 chains at 8 warps/SM): issue slots 25 % busy, FP64 pipe 24 %, "
                     "barrier stall 1.9 warps per issue in the capture (68 SMs)"}
+    if phase.get("search_by_bow_batch_ms") and micro.get("imma_hamming_pairs_per_s"):
+        pairs = phase["search_by_bow_descriptor_pairs"]
+        rate = pairs / (phase["search_by_bow_batch_ms"] * 1e-3)
+        line["roofline_matcher"] = {
+            "kernel": "batched SearchByBoW call: k_rank_by_key + k_bow_topk_imma (IMMA.16832 K-lists) + k_bow_resolve + k_rot_cull",
+            "bound": "tensor", "unit": "descriptor pairs/s", "achieved": rate, "peak": micro["imma_hamming_pairs_per_s"],
+            "frac": rate / micro["imma_hamming_pairs_per_s"], "call_ms": phase["search_by_bow_batch_ms"], "pairs_per_call": pairs,
+            "peak_source": "measured IMMA.16832.U8.U8 issue rate in this run x 16 pairs per instruction (8 IMMA per 16 x 8 tile of "
+                           "256-bit distances)",
+            "note": "the K-list kernel is about 40 % of the call (profiles/README.md); the rest are the rank and the greedy resolver"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(F)
     print(json.dumps(line), flush=True)
@@ -683,7 +717,8 @@ def measure_device_peaks(pkg):
         if rc != 0:
             return {"error": "b2s_measure_peaks rc=%d" % rc}
         return {"alu_vimnmx3_gwarp_s": out[0], "fma_imad_gwarp_s": out[1], "fp64_dfma_tflops": out[2], "popc_gwarp_s": out[3],
-                "dual_issue_alu_fma_gwarp_s": out[4],
+                "dual_issue_alu_fma_gwarp_s": out[4], "imma_16832_gwarp_s": out[5],
+                "imma_hamming_pairs_per_s": out[5] * 1e9 * 16,  # 8 IMMA per 16 x 8 tile of 256-bit distances
                 "how": "b2s_measure_peaks: dependent-free unrolled chains, 148 x 8 CTAs x 256 threads, CUDA events, best of 3"}
     except Exception as ex:
         return {"error": str(ex)[:200]}

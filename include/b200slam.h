@@ -41,7 +41,8 @@ const char* b2s_last_error(void);   /* thread-local text of the last failure */
 int b2s_version(void);
 int b2s_device_count(void);
 /* Issue-rate micro-benchmarks of `device` (about 20 ms): out8[0] packed u16x2 min/max (ALU pipe) and [1] IMAD (FMA pipe) in
- * G warp-instructions/s, [2] FP64 DFMA TFLOP/s, [3] POPC G warp-instructions/s, [4] ALU + FMA interleaved; the rest 0.
+ * G warp-instructions/s, [2] FP64 DFMA TFLOP/s, [3] POPC G warp-instructions/s, [4] ALU + FMA interleaved, [5] IMMA.16832.U8.U8 (the integer
+ * tensor pipe as mma.sync reaches it) in G warp-instructions/s; the rest 0.
  * bench.py reports the kernels' figures against these measured bounds. */
 int b2s_measure_peaks(int device, double* out8);
 
